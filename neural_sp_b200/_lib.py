@@ -1,0 +1,61 @@
+"""ctypes binding of libnsp_b200.so (the C ABI declared in include/nsp_b200.h).
+
+The CUDA library is the product: there is no CPU or PyTorch fallback.  Importing this module
+without a built library raises, and every call checks the returned nsp_status.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnsp_b200.so")
+
+
+class NspError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "neural_sp_b200: %s is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C neural_sp_b200/csrc`). There is no CPU fallback." % LIB_PATH)
+    return ctypes.CDLL(LIB_PATH)
+
+
+lib = _load()
+
+c_int, c_i64, c_f32, c_vp, c_sz = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every symbol declared in include/nsp_b200.h
+SIGNATURES = {
+    "nsp_version": (c_int, []),
+    "nsp_last_error": (ctypes.c_char_p, []),
+    "nsp_device_info": (c_int, [ctypes.POINTER(c_int)] * 3),
+    "nsp_ctc_loss_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
+    "nsp_ctc_loss_fwd_bwd": (c_int, [c_vp, c_i64, c_i64, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp,
+                                     c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "nsp_ctc_align_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
+    "nsp_ctc_forced_align": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_vp,
+                                     c_vp, c_sz, c_vp]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)   # AttributeError here = header/library mismatch: fail loudly
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def check(status, what=""):
+    if status != 0:
+        msg = lib.nsp_last_error().decode("utf-8", "replace")
+        raise NspError("%s failed with nsp_status=%d: %s" % (what or "nsp call", status, msg))
+
+
+def ptr(t):
+    """Device/host pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def current_stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

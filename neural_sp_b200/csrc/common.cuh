@@ -1,0 +1,103 @@
+// Shared device/host helpers for the neural_sp_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/nsp_b200.h"
+
+namespace nsp {
+
+// ---- error plumbing (C-ABI returns nsp_status; message kept per thread) ----
+void set_error(const char* fmt, ...);
+
+#define NSP_CHECK_ARG(cond, ...)                         \
+    do {                                                 \
+        if (!(cond)) {                                   \
+            ::nsp::set_error(__VA_ARGS__);               \
+            return NSP_ERR_INVALID;                      \
+        }                                                \
+    } while (0)
+
+#define NSP_CUDA_OK(expr)                                                              \
+    do {                                                                               \
+        cudaError_t _e = (expr);                                                       \
+        if (_e != cudaSuccess) {                                                       \
+            ::nsp::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__,            \
+                             cudaGetErrorName(_e), cudaGetErrorString(_e));            \
+            return NSP_ERR_CUDA;                                                       \
+        }                                                                              \
+    } while (0)
+
+#define NSP_LAUNCH_OK() NSP_CUDA_OK(cudaGetLastError())
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int num_sms();   // cached device query (148 on B200)
+
+// ---- device helpers ----
+#define NSP_NEG_BIG (-1.0e30f)   // finite stand-in for log(0): avoids inf-inf NaNs in log-sum-exp sweeps
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide reductions through a 32-float smem scratch; every thread gets the result.
+template <int NT>
+__device__ __forceinline__ float block_max(float v, float* scratch) {
+    constexpr int NW = NT / 32;
+    v = warp_max(v);
+    if constexpr (NW == 1) return v;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = (threadIdx.x & 31) < NW ? scratch[threadIdx.x & 31] : -INFINITY;
+    return warp_max(r);
+}
+template <int NT>
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+    constexpr int NW = NT / 32;
+    v = warp_sum(v);
+    if constexpr (NW == 1) return v;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = (threadIdx.x & 31) < NW ? scratch[threadIdx.x & 31] : 0.f;
+    return warp_sum(r);
+}
+
+// log(exp(a)+exp(b)+exp(c)) with the NSP_NEG_BIG convention (never produces NaN).
+__device__ __forceinline__ float lse3(float a, float b, float c) {
+    float m = fmaxf(a, fmaxf(b, c));
+    float s = __expf(a - m) + __expf(b - m) + __expf(c - m);
+    return m + __logf(s);
+}
+__device__ __forceinline__ float lse2(float a, float b) {
+    float m = fmaxf(a, b);
+    return m + __logf(__expf(a - m) + __expf(b - m));
+}
+
+// streaming 128-bit accesses (read-once inputs / write-once outputs bypass L1 allocation)
+__device__ __forceinline__ float4 ld_stream_f4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_f4(float* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+}  // namespace nsp

@@ -1,0 +1,534 @@
+// CTC loss forward+backward for sm_100a: one streaming pass over the logits, a per-utterance
+// alpha/beta lattice sweep, and a sparse fix-up of the gradient.
+//
+// Replaces (reference, /root/reference):
+//   CTC.loss_fn                neural_sp/models/seq2seq/decoders/ctc.py:139-150
+//   kldiv_lsm_ctc              neural_sp/models/criterion.py:110-127  (mixed at ctc.py:128-129)
+//   and the autograd backward of both (ATen ctc_loss_backward + log_softmax backward).
+//
+// Roofline: HBM.  Algorithmic traffic = read logits once + write d(loss)/d(logits) once
+// = 8 B per logit element.  Kernel plan:
+//   K1 ctc_rows_kernel     grid over (b,t) rows: row -> registers (128-bit streaming loads),
+//                          max / sum-exp / entropy, writes grad = softmax-part (+ label-smoothing
+//                          KL part) with streaming stores, gathers the 2L+1 path emissions.
+//                          Rows t >= elens[b] are zero-filled without being read.
+//   K2 ctc_lattice_kernel  one CTA per utterance; half the CTA sweeps alpha forward while the
+//                          other half sweeps beta backward (one state per thread, smem ping-pong,
+//                          register prefetch ring for the emissions), then all warps apply the
+//                          sparse "-= occupancy" fix-up to the <= L+1 touched columns of each row.
+//   K3 ctc_finalize_kernel deterministic reduction of nll / KL to the scalar loss.
+#include "common.cuh"
+
+namespace nsp {
+namespace {
+
+struct CtcParams {
+    const float* logits;
+    int64_t sb, st;
+    int B, T, V;
+    const int32_t* labels;
+    int Lmax;
+    const int32_t* elens;
+    const int32_t* ylens;
+    int blank;
+    float lsm;
+    float* nll;
+    float* loss;
+    float* grad;
+    // workspace
+    float* emit;   // [B,T,Sp]
+    float* alpha;  // [B,T,Sp]
+    float* beta;   // [B,T,Sp]
+    float* lse;    // [B,T]
+    float* hrow;   // [B,T]  sum_v p*lp
+    float* klrow;  // [B,T]
+    int Sp;
+};
+
+template <int G>
+__device__ __forceinline__ float group_max(float v, float* scratch) {
+    if constexpr (G == 32) return warp_max(v);
+    else return block_max<G>(v, scratch);
+}
+template <int G>
+__device__ __forceinline__ float group_sum(float v, float* scratch) {
+    if constexpr (G == 32) return warp_sum(v);
+    else return block_sum<G>(v, scratch);
+}
+
+__device__ __forceinline__ int path_label(const int32_t* lab, int s, int blank, int V) {
+    int l = (s & 1) ? lab[s >> 1] : blank;
+    return min(max(l, 0), V - 1);   // memory safety for out-of-range ids (reference would raise)
+}
+
+__device__ __forceinline__ float n_frames_of(const int32_t* elens, int B, int T) {
+    // sum_b elens[b] (criterion.py:126 denominator); B is small, L2-resident.
+    int acc = 0;
+    for (int i = 0; i < B; ++i) acc += min(max(elens[i], 0), T);
+    return (float)acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1, register-resident rows.  G threads cooperate on one row; 256 threads per CTA.
+// ---------------------------------------------------------------------------------------------
+template <int G, int VPT, int VEC>
+__global__ void __launch_bounds__(256) ctc_rows_kernel(CtcParams p) {
+    constexpr int NT = 256;
+    constexpr int RPB = NT / G;
+    __shared__ float scratch[32];
+    const int lane = threadIdx.x % G;
+    const int64_t row = (int64_t)blockIdx.x * RPB + threadIdx.x / G;
+    if (row >= (int64_t)p.B * p.T) return;   // uniform per group (G==256: per CTA)
+    const int b = (int)(row / p.T), t = (int)(row % p.T);
+    const int Tb = min(max(p.elens[b], 0), p.T);
+    float* grow = p.grad + row * (int64_t)p.V;
+    const int V = p.V;
+
+    if (t >= Tb) {   // padded frame: zero gradient, nothing read
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+            int idx = (j * G + lane) * VEC;
+            if (idx < V) {
+                if constexpr (VEC == 4) st_stream_f4(grow + idx, make_float4(0.f, 0.f, 0.f, 0.f));
+                else grow[idx] = 0.f;
+            }
+        }
+        if (lane == 0) { p.klrow[row] = 0.f; p.lse[row] = 0.f; p.hrow[row] = 0.f; }
+        return;
+    }
+
+    const float* xrow = p.logits + (int64_t)b * p.sb + (int64_t)t * p.st;
+    float x[VPT][VEC];
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+        int idx = (j * G + lane) * VEC;
+        if (idx < V) {
+            if constexpr (VEC == 4) {
+                float4 v = ld_stream_f4(xrow + idx);
+                x[j][0] = v.x; x[j][1] = v.y; x[j][2] = v.z; x[j][3] = v.w;
+            } else {
+                x[j][0] = __ldg(xrow + idx);
+            }
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) m = fmaxf(m, x[j][k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) x[j][k] = -INFINITY;
+        }
+    }
+    m = group_max<G>(m, scratch);
+    float e[VPT][VEC];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            e[j][k] = __expf(x[j][k] - m);   // exp(-inf) = 0 for the tail
+            sum += e[j][k];
+        }
+    sum = group_sum<G>(sum, scratch);
+    const float lse = m + __logf(sum);
+    const float inv = 1.f / sum;
+
+    const float c_ctc = (1.f - p.lsm) / (float)p.B;
+    float c_kl = 0.f, H = 0.f;
+    if (p.lsm > 0.f) {
+        float h = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPT; ++j)
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                float pv = e[j][k] * inv;
+                if (pv > 0.f) h += pv * (x[j][k] - lse);
+            }
+        H = group_sum<G>(h, scratch);
+        c_kl = p.lsm / n_frames_of(p.elens, p.B, p.T);
+    }
+
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+        int idx = (j * G + lane) * VEC;
+        if (idx < V) {
+            float g[VEC];
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                float pv = e[j][k] * inv;
+                g[k] = pv * (c_ctc + c_kl * ((x[j][k] - lse) - H));
+                if (!(pv > 0.f)) g[k] = 0.f;   // p == 0: lp may be -inf, 0 * inf guard
+            }
+            if constexpr (VEC == 4) st_stream_f4(grow + idx, make_float4(g[0], g[1], g[2], g[3]));
+            else grow[idx] = g[0];
+        }
+    }
+    if (lane == 0) {
+        p.lse[row] = lse;
+        p.hrow[row] = H;
+        // sum_v p (lp - log(1/(V-1))) = H + log(V-1)
+        p.klrow[row] = (p.lsm > 0.f) ? (H + __logf((float)(V - 1))) : 0.f;
+    }
+    // path emissions (L2 hits: this row was just streamed by this group)
+    const int S = 2 * min(max(p.ylens[b], 0), p.Lmax) + 1;
+    const int32_t* lab = p.labels + (int64_t)b * p.Lmax;
+    float* em = p.emit + row * (int64_t)p.Sp;
+    for (int s = lane; s < S; s += G) em[s] = __ldg(xrow + path_label(lab, s, p.blank, V)) - lse;
+}
+
+// K1, generic: row staged in shared memory (any V up to ~50k, any alignment).
+template <int NT>
+__global__ void __launch_bounds__(NT) ctc_rows_smem_kernel(CtcParams p) {
+    extern __shared__ float srow[];
+    __shared__ float scratch[32];
+    const int64_t row = blockIdx.x;
+    const int b = (int)(row / p.T), t = (int)(row % p.T);
+    const int Tb = min(max(p.elens[b], 0), p.T);
+    float* grow = p.grad + row * (int64_t)p.V;
+    const int V = p.V;
+    if (t >= Tb) {
+        for (int i = threadIdx.x; i < V; i += NT) grow[i] = 0.f;
+        if (threadIdx.x == 0) { p.klrow[row] = 0.f; p.lse[row] = 0.f; p.hrow[row] = 0.f; }
+        return;
+    }
+    const float* xrow = p.logits + (int64_t)b * p.sb + (int64_t)t * p.st;
+    float m = -INFINITY;
+    for (int i = threadIdx.x; i < V; i += NT) { float v = __ldg(xrow + i); srow[i] = v; m = fmaxf(m, v); }
+    m = block_max<NT>(m, scratch);
+    float sum = 0.f;
+    for (int i = threadIdx.x; i < V; i += NT) sum += __expf(srow[i] - m);
+    sum = block_sum<NT>(sum, scratch);
+    const float lse = m + __logf(sum);
+    const float c_ctc = (1.f - p.lsm) / (float)p.B;
+    float c_kl = 0.f, H = 0.f;
+    if (p.lsm > 0.f) {
+        float h = 0.f;
+        for (int i = threadIdx.x; i < V; i += NT) {
+            float lp = srow[i] - lse; float pv = __expf(lp);
+            if (pv > 0.f) h += pv * lp;
+        }
+        H = block_sum<NT>(h, scratch);
+        c_kl = p.lsm / n_frames_of(p.elens, p.B, p.T);
+    }
+    for (int i = threadIdx.x; i < V; i += NT) {
+        float lp = srow[i] - lse; float pv = __expf(lp);
+        grow[i] = (pv > 0.f) ? pv * (c_ctc + c_kl * (lp - H)) : 0.f;
+    }
+    if (threadIdx.x == 0) {
+        p.lse[row] = lse; p.hrow[row] = H;
+        p.klrow[row] = (p.lsm > 0.f) ? (H + __logf((float)(V - 1))) : 0.f;
+    }
+    const int S = 2 * min(max(p.ylens[b], 0), p.Lmax) + 1;
+    const int32_t* lab = p.labels + (int64_t)b * p.Lmax;
+    float* em = p.emit + row * (int64_t)p.Sp;
+    for (int s = threadIdx.x; s < S; s += NT) em[s] = srow[path_label(lab, s, p.blank, V)] - lse;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: lattice.  CTA = 2*HALF threads; threads [0,HALF) run alpha forward, [HALF,2*HALF) run beta
+// backward, SPT states per thread (state = htid + k*HALF).
+// ---------------------------------------------------------------------------------------------
+template <int SPT>
+__global__ void __launch_bounds__(1024) ctc_lattice_kernel(CtcParams p, int HALF) {
+    extern __shared__ float sm[];
+    const int Sp = p.Sp;
+    float* abuf = sm;                 // [2][Sp] alpha ping-pong
+    float* bbuf = sm + 2 * Sp;        // [2][Sp] beta ping-pong
+    int16_t* nxt = reinterpret_cast<int16_t*>(sm + 4 * Sp);   // [Sp] next state with the same label (-1: none)
+    int16_t* head = nxt + Sp;                                  // [Sp] 1 if first occurrence of its label
+    __shared__ float s_nll;
+
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const bool is_beta = tid >= HALF;
+    const int htid = is_beta ? tid - HALF : tid;
+    const int L = min(max(p.ylens[b], 0), p.Lmax);
+    const int S = 2 * L + 1;
+    const int Tb = min(max(p.elens[b], 0), p.T);
+    const int32_t* lab = p.labels + (int64_t)b * p.Lmax;
+    const int64_t base = (int64_t)b * p.T * Sp;
+    const float* em = p.emit + base;
+    float* gout = (is_beta ? p.beta : p.alpha) + base;
+
+    // same-label chains over the odd (label) states: O(L) per state, done once
+    for (int s = tid; s < S; s += blockDim.x) {
+        int nx = -1, hd = 1;
+        if (s & 1) {
+            int me = lab[s >> 1];
+            for (int q = (s >> 1) + 1; q < L; ++q) if (lab[q] == me) { nx = 2 * q + 1; break; }
+            for (int q = 0; q < (s >> 1); ++q) if (lab[q] == me) { hd = 0; break; }
+        }
+        nxt[s] = (int16_t)nx; head[s] = (int16_t)hd;
+    }
+
+    // per-state static info
+    bool valid[SPT], skip[SPT];
+    int st_[SPT];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+        int s = htid + k * HALF;
+        st_[k] = s;
+        valid[k] = s < S;
+        skip[k] = false;
+        if (valid[k] && (s & 1)) {
+            if (!is_beta) skip[k] = (s >= 2) && (lab[s >> 1] != lab[(s >> 1) - 1]);
+            else          skip[k] = (s + 2 < S) && (lab[s >> 1] != lab[(s >> 1) + 1]);
+        }
+    }
+    float* buf = is_beta ? bbuf : abuf;
+    // init ping-pong buffer 1 ("previous") to NEG so step 0 can use the common recurrence
+    for (int s = htid; s < Sp; s += HALF) { buf[s] = NSP_NEG_BIG; buf[Sp + s] = NSP_NEG_BIG; }
+    __syncthreads();
+
+    if (Tb > 0) {
+        constexpr int PF = 4;   // emission prefetch ring (steps)
+        float ering[SPT][PF];
+        auto tstep = [&](int i) { return is_beta ? (Tb - 1 - i) : i; };   // i-th step of this sweep
+#pragma unroll
+        for (int k = 0; k < SPT; ++k)
+#pragma unroll
+            for (int j = 0; j < PF; ++j)
+                ering[k][j] = (valid[k] && j < Tb) ? em[(int64_t)tstep(j) * Sp + st_[k]] : 0.f;
+
+        int cur = 0;
+        for (int i0 = 0; i0 < Tb; i0 += PF) {
+            float enext[SPT][PF];
+#pragma unroll
+            for (int k = 0; k < SPT; ++k)
+#pragma unroll
+                for (int j = 0; j < PF; ++j) {
+                    int i = i0 + PF + j;
+                    enext[k][j] = (valid[k] && i < Tb) ? em[(int64_t)tstep(i) * Sp + st_[k]] : 0.f;
+                }
+#pragma unroll
+            for (int j = 0; j < PF; ++j) {
+                int i = i0 + j;
+                if (i < Tb) {   // uniform across the CTA
+                    const float* prev = buf + (cur ^ 1) * Sp;
+                    float* now = buf + cur * Sp;
+                    int t = tstep(i);
+#pragma unroll
+                    for (int k = 0; k < SPT; ++k) {
+                        if (valid[k]) {
+                            int s = st_[k];
+                            float v;
+                            if (i == 0) {
+                                bool start = is_beta ? (s >= S - 2) : (s <= 1);
+                                v = start ? ering[k][j] : NSP_NEG_BIG;
+                            } else {
+                                float a0 = prev[s], a1, a2;
+                                if (!is_beta) {
+                                    a1 = (s >= 1) ? prev[s - 1] : NSP_NEG_BIG;
+                                    a2 = skip[k] ? prev[s - 2] : NSP_NEG_BIG;
+                                } else {
+                                    a1 = (s + 1 < S) ? prev[s + 1] : NSP_NEG_BIG;
+                                    a2 = skip[k] ? prev[s + 2] : NSP_NEG_BIG;
+                                }
+                                v = lse3(a0, a1, a2) + ering[k][j];
+                                v = fmaxf(v, NSP_NEG_BIG);
+                            }
+                            now[s] = v;
+                            gout[(int64_t)t * Sp + s] = v;
+                        }
+                    }
+                    __syncthreads();
+                    cur ^= 1;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < SPT; ++k)
+#pragma unroll
+                for (int j = 0; j < PF; ++j) ering[k][j] = enext[k][j];
+        }
+        if (tid == 0) {
+            const float* last = abuf + (cur ^ 1) * Sp;
+            float l1 = last[S - 1];
+            float l2 = (S > 1) ? last[S - 2] : NSP_NEG_BIG;
+            s_nll = -lse2(l1, l2);
+        }
+    } else if (tid == 0) {
+        s_nll = (L == 0) ? 0.f : 1.0e30f;
+    }
+    __syncthreads();   // also makes the alpha/beta global stores of this CTA visible to itself
+    const float nll = s_nll;
+    const bool feasible = nll < 1.0e29f;
+    if (tid == 0) p.nll[b] = feasible ? nll : 0.f;
+
+    const float c_ctc = (1.f - p.lsm) / (float)p.B;
+    float* gb = p.grad + (int64_t)b * p.T * p.V;
+    const int lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+
+    if (!feasible) {
+        // zero_infinity: CTC part of the gradient vanishes; only the label-smoothing KL part stays.
+        float c_kl = (p.lsm > 0.f) ? p.lsm / n_frames_of(p.elens, p.B, p.T) : 0.f;
+        for (int t = wid; t < Tb; t += nw) {
+            const float* xrow = p.logits + (int64_t)b * p.sb + (int64_t)t * p.st;
+            float lse = p.lse[(int64_t)b * p.T + t], H = p.hrow[(int64_t)b * p.T + t];
+            for (int v = lane; v < p.V; v += 32) {
+                float lp = xrow[v] - lse; float pv = __expf(lp);
+                gb[(int64_t)t * p.V + v] = (pv > 0.f) ? c_kl * pv * (lp - H) : 0.f;
+            }
+        }
+        return;
+    }
+
+    const float* al = p.alpha + base;
+    const float* be = p.beta + base;
+    const int bl = min(max(p.blank, 0), p.V - 1);
+    for (int t = wid; t < Tb; t += nw) {
+        const float* a = al + (int64_t)t * Sp;
+        const float* bt = be + (int64_t)t * Sp;
+        const float* e = em + (int64_t)t * Sp;
+        float* grow = gb + (int64_t)t * p.V;
+        // blank column: all even states
+        float m = NSP_NEG_BIG, sum = 0.f;
+        for (int s = 2 * lane; s < S; s += 64) {
+            float v = a[s] + bt[s];
+            float nm = fmaxf(m, v);
+            sum = sum * __expf(m - nm) + __expf(v - nm);
+            m = nm;
+        }
+        float M = warp_max(m);
+        sum = warp_sum(sum * __expf(m - M));
+        if (lane == 0) {
+            float lcab = M + __logf(sum);
+            grow[bl] -= c_ctc * __expf(lcab + nll - e[0]);
+        }
+        // label columns: head states walk their same-label chain (deterministic order)
+        for (int s = 2 * lane + 1; s < S; s += 64) {
+            if (head[s]) {
+                float mm = a[s] + bt[s], ss = 1.f;
+                for (int q = nxt[s]; q >= 0; q = nxt[q]) {
+                    float v = a[q] + bt[q];
+                    float nm = fmaxf(mm, v);
+                    ss = ss * __expf(mm - nm) + __expf(v - nm);
+                    mm = nm;
+                }
+                float lcab = mm + __logf(ss);
+                int v = min(max(lab[s >> 1], 0), p.V - 1);
+                if (v != bl) grow[v] -= c_ctc * __expf(lcab + nll - e[s]);
+                else atomicAdd(&grow[v], -c_ctc * __expf(lcab + nll - e[s]));   // label == blank id (degenerate input)
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) ctc_finalize_kernel(CtcParams p) {
+    __shared__ float scratch[32];
+    float a = 0.f;
+    for (int i = threadIdx.x; i < p.B; i += 256) a += p.nll[i];
+    a = block_sum<256>(a, scratch);
+    float loss = (1.f - p.lsm) * a / (float)p.B;
+    if (p.lsm > 0.f) {
+        float k = 0.f;
+        const int64_t n = (int64_t)p.B * p.T;
+        for (int64_t i = threadIdx.x; i < n; i += 256) k += p.klrow[i];
+        k = block_sum<256>(k, scratch);
+        loss += p.lsm * k / n_frames_of(p.elens, p.B, p.T);
+    }
+    if (threadIdx.x == 0) p.loss[0] = loss;
+}
+
+template <int G, int VEC>
+nsp_status launch_rows(const CtcParams& p, int nvec, cudaStream_t st) {
+    const int64_t rows = (int64_t)p.B * p.T;
+    const int rpb = 256 / G;
+    const unsigned grid = (unsigned)ceil_div64(rows, rpb);
+    const int vpt = ceil_div(nvec, G);
+#define NSP_ROWS(VPT) ctc_rows_kernel<G, VPT, VEC><<<grid, 256, 0, st>>>(p)
+    if (vpt <= 1) NSP_ROWS(1);
+    else if (vpt <= 2) NSP_ROWS(2);
+    else if (vpt <= 4) NSP_ROWS(4);
+    else if (vpt <= 8) NSP_ROWS(8);
+    else if (vpt <= 12) NSP_ROWS(12);
+    else { set_error("ctc rows: internal dispatch error (vpt=%d)", vpt); return NSP_ERR_INVALID; }
+#undef NSP_ROWS
+    NSP_LAUNCH_OK();
+    return NSP_OK;
+}
+
+}  // namespace
+}  // namespace nsp
+
+using namespace nsp;
+
+extern "C" size_t nsp_ctc_loss_workspace_bytes(int B, int T, int Lmax) {
+    if (B <= 0 || T <= 0 || Lmax < 0) return 0;
+    size_t Sp = 2 * (size_t)Lmax + 1;
+    size_t bt = (size_t)B * T;
+    return align_up(3 * bt * Sp * sizeof(float), 256) + 3 * align_up(bt * sizeof(float), 256) + 256;
+}
+
+extern "C" nsp_status nsp_ctc_loss_fwd_bwd(const float* logits, int64_t stride_b, int64_t stride_t,
+                                           int B, int T, int V,
+                                           const int32_t* labels, int Lmax,
+                                           const int32_t* elens, const int32_t* ylens,
+                                           int blank, float lsm_prob,
+                                           float* nll, float* loss, float* grad,
+                                           void* workspace, size_t workspace_bytes, void* stream) {
+    NSP_CHECK_ARG(logits && elens && ylens && nll && loss && grad && workspace, "ctc_loss: null pointer");
+    NSP_CHECK_ARG(labels || Lmax == 0, "ctc_loss: labels is null with Lmax=%d", Lmax);
+    NSP_CHECK_ARG(B > 0 && T > 0 && V > 1, "ctc_loss: bad shape B=%d T=%d V=%d", B, T, V);
+    NSP_CHECK_ARG(Lmax >= 0 && 2 * Lmax + 1 <= 4096, "ctc_loss: Lmax=%d unsupported (2L+1 <= 4096)", Lmax);
+    NSP_CHECK_ARG(blank >= 0 && blank < V, "ctc_loss: blank=%d out of range", blank);
+    NSP_CHECK_ARG(lsm_prob >= 0.f && lsm_prob < 1.f, "ctc_loss: lsm_prob=%f", lsm_prob);
+    NSP_CHECK_ARG(workspace_bytes >= nsp_ctc_loss_workspace_bytes(B, T, Lmax), "ctc_loss: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+
+    CtcParams p;
+    p.logits = logits; p.sb = stride_b; p.st = stride_t; p.B = B; p.T = T; p.V = V;
+    p.labels = labels; p.Lmax = Lmax; p.elens = elens; p.ylens = ylens;
+    p.blank = blank; p.lsm = lsm_prob; p.nll = nll; p.loss = loss; p.grad = grad;
+    p.Sp = 2 * Lmax + 1;
+    const size_t bt = (size_t)B * T;
+    char* w = (char*)workspace;
+    const size_t lat = bt * p.Sp * sizeof(float);
+    p.emit = (float*)w; p.alpha = (float*)(w + lat); p.beta = (float*)(w + 2 * lat);
+    w += align_up(3 * lat, 256);
+    p.lse = (float*)w; w += align_up(bt * sizeof(float), 256);
+    p.hrow = (float*)w; w += align_up(bt * sizeof(float), 256);
+    p.klrow = (float*)w;
+
+    // ---- K1 ----
+    const bool vec4 = (V % 4 == 0) && (stride_b % 4 == 0) && (stride_t % 4 == 0) &&
+                      (((uintptr_t)logits) % 16 == 0) && (((uintptr_t)grad) % 16 == 0);
+    const int vec = vec4 ? 4 : 1;
+    const int nvec = V / vec;
+    nsp_status s;
+    if (nvec <= 32 * 8) {
+        s = vec4 ? launch_rows<32, 4>(p, nvec, st) : launch_rows<32, 1>(p, nvec, st);
+    } else if (nvec <= 256 * 12) {
+        s = vec4 ? launch_rows<256, 4>(p, nvec, st) : launch_rows<256, 1>(p, nvec, st);
+    } else {
+        size_t smem = (size_t)V * sizeof(float);
+        if (smem > 200 * 1024) { set_error("ctc_loss: V=%d too large (max 51200)", V); return NSP_ERR_UNSUPPORTED; }
+        NSP_CUDA_OK(cudaFuncSetAttribute(ctc_rows_smem_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctc_rows_smem_kernel<512><<<(unsigned)bt, 512, smem, st>>>(p);
+        NSP_LAUNCH_OK();
+        s = NSP_OK;
+    }
+    if (s != NSP_OK) return s;
+
+    // ---- K2 ----
+    {
+        const int S = p.Sp;
+        int spt = 1, half = (int)align_up((size_t)S, 32);
+        if (half > 512) { spt = 2; half = (int)align_up((size_t)ceil_div(S, 2), 32); }
+        if (half > 512) { spt = 4; half = (int)align_up((size_t)ceil_div(S, 4), 32); }
+        if (half > 512) { spt = 8; half = 512; }
+        size_t smem = (size_t)4 * S * sizeof(float) + (size_t)2 * S * sizeof(int16_t) + 16;
+        dim3 block(2 * half);
+        if (smem > 48 * 1024) {
+            NSP_CUDA_OK(cudaFuncSetAttribute(ctc_lattice_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            NSP_CUDA_OK(cudaFuncSetAttribute(ctc_lattice_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            NSP_CUDA_OK(cudaFuncSetAttribute(ctc_lattice_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            NSP_CUDA_OK(cudaFuncSetAttribute(ctc_lattice_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        if (spt == 1) ctc_lattice_kernel<1><<<B, block, smem, st>>>(p, half);
+        else if (spt == 2) ctc_lattice_kernel<2><<<B, block, smem, st>>>(p, half);
+        else if (spt == 4) ctc_lattice_kernel<4><<<B, block, smem, st>>>(p, half);
+        else ctc_lattice_kernel<8><<<B, block, smem, st>>>(p, half);
+        NSP_LAUNCH_OK();
+    }
+    ctc_finalize_kernel<<<1, 256, 0, st>>>(p);
+    NSP_LAUNCH_OK();
+    return NSP_OK;
+}

@@ -1,0 +1,128 @@
+"""CTC head + loss + forced aligner, B200-native.
+
+Drop-in for ``neural_sp.models.seq2seq.decoders.ctc.CTC`` (reference ctc.py:35-150) and
+``CTCForcedAligner`` (ctc.py:628-753): same constructor, ``forward(eouts, elens, ys, forced_align)``
+-> ``(loss, trigger_points)``, ``loss_fn(logits[T,B,V], ys_ctc, elens, ylens)``, same ``state_dict``
+keys (``output.weight/bias`` or ``output.fc{i}.weight/bias``).  The arithmetic runs in
+libnsp_b200.so: one fused CUDA pass computes the loss AND d(loss)/d(logits); ``backward`` only scales.
+
+Host-side decode helpers of the reference class (greedy / beam search / prefix scorer,
+ctc.py:197-531, 756-871) are out of scope.
+"""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..modules.linear import Linear
+
+
+class _CTCLossFn(torch.autograd.Function):
+    """loss = (1-lsm) * sum_b nll_b / B + lsm * KL ; gradient produced by the same kernels."""
+
+    @staticmethod
+    def forward(ctx, logits_btv, labels, elens, ylens, blank, lsm_prob):
+        loss, nll, grad = ops.ctc_loss_fwd_bwd(logits_btv, labels, elens, ylens, blank, lsm_prob)
+        ctx.save_for_backward(grad)
+        ctx.mark_non_differentiable(nll)
+        return loss, nll
+
+    @staticmethod
+    def backward(ctx, g_loss, g_nll):
+        (grad,) = ctx.saved_tensors
+        return grad * g_loss, None, None, None, None, None
+
+
+def ctc_loss(logits_btv, labels, elens, ylens, blank=0, lsm_prob=0.0):
+    """Functional form on device-resident int32 labels/lengths. Returns (loss, nll)."""
+    return _CTCLossFn.apply(logits_btv, labels, elens, ylens, blank, lsm_prob)
+
+
+class CTCForcedAligner(object):
+    """Reference ctc.py:628-753; integer trigger points are bit-exact targets."""
+
+    def __init__(self, blank=0):
+        self.blank = blank
+
+    def __call__(self, logits, elens, ys, ylens=None):
+        """logits `[B, T, vocab]` (CUDA), elens IntTensor `[B]`, ys list of lists -> IntTensor `[B, Lmax+1]`."""
+        with torch.no_grad():
+            labels, ylens_d, _ = ops.pack_labels(ys, logits.device)
+            elens_d = elens.to(device=logits.device, dtype=torch.int32, non_blocking=True)
+            return ops.ctc_forced_align(logits.detach().float(), labels, elens_d, ylens_d, self.blank)
+
+
+class CTC(nn.Module):
+    """Connectionist temporal classification (reference ctc.py:35-137)."""
+
+    def __init__(self, eos, blank, enc_n_units, vocab, dropout=0., lsm_prob=0., fc_list=None,
+                 param_init=0.1, backward=False):
+        super().__init__()
+        self.eos = eos
+        self.blank = blank
+        self.vocab = vocab
+        self.lsm_prob = lsm_prob
+        self.bwd = backward
+        self.space = -1
+        self.prev_spk = ''
+        self.lmstate_final = None
+        self.prob_dict = {}
+        self.data_dict = {}
+
+        # Fully-connected layers before the softmax (no nonlinearity in between: ctc.py:82-89)
+        if fc_list is not None and len(fc_list) > 0:
+            _fc_list = [int(fc) for fc in fc_list.split('_')]
+            fc_layers = OrderedDict()
+            for i in range(len(_fc_list)):
+                input_dim = enc_n_units if i == 0 else _fc_list[i - 1]
+                fc_layers['fc' + str(i)] = Linear(input_dim, _fc_list[i])
+                fc_layers['dropout' + str(i)] = nn.Dropout(p=dropout)
+            fc_layers['fc' + str(len(_fc_list))] = Linear(_fc_list[-1], vocab)
+            self.output = nn.Sequential(fc_layers)
+        else:
+            self.output = Linear(enc_n_units, vocab)
+        self.forced_aligner = CTCForcedAligner(blank)
+
+    def forward(self, eouts, elens, ys, forced_align=False):
+        """Compute CTC loss.
+
+        Args:
+            eouts (FloatTensor): `[B, T, enc_n_units]` on the GPU
+            elens (IntTensor): `[B]`
+            ys (List): length `[B]`, each a list of label ids
+        Returns:
+            loss (FloatTensor): 0-dim
+            trigger_points (IntTensor): `[B, L+1]` or None
+        """
+        ys_dir = [list(y[::-1]) if self.bwd else list(y) for y in ys]
+        labels, ylens_d, _ = ops.pack_labels(ys_dir, eouts.device)
+        elens_d = elens.to(device=eouts.device, dtype=torch.int32, non_blocking=True)
+
+        logits = self.output(eouts)   # `[B, T, vocab]`
+        loss, _ = ctc_loss(logits.float(), labels, elens_d, ylens_d, self.blank, self.lsm_prob)
+
+        trigger_points = None
+        if forced_align:
+            with torch.no_grad():
+                labels_f, ylens_f, _ = ops.pack_labels([list(y) for y in ys], eouts.device)
+                trigger_points = ops.ctc_forced_align(logits.detach().float(), labels_f, elens_d, ylens_f, self.blank)
+
+        if not self.training:
+            self.data_dict['elens'] = elens.cpu().numpy() if torch.is_tensor(elens) else np.asarray(elens)
+            self.prob_dict['probs'] = torch.softmax(logits.detach(), dim=-1).cpu().numpy()
+        return loss, trigger_points
+
+    def loss_fn(self, logits, ys_ctc, elens, ylens):
+        """Reference op boundary (ctc.py:139-150): logits `[T, B, vocab]`, concatenated int32 targets."""
+        ylens_l = [int(v) for v in ylens]
+        ys, o = [], 0
+        flat = ys_ctc.tolist()
+        for n in ylens_l:
+            ys.append(flat[o:o + n])
+            o += n
+        labels, ylens_d, _ = ops.pack_labels(ys, logits.device)
+        elens_d = elens.to(device=logits.device, dtype=torch.int32, non_blocking=True)
+        loss, _ = ctc_loss(logits.transpose(1, 0), labels, elens_d, ylens_d, self.blank, 0.0)
+        return loss
