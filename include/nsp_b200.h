@@ -81,6 +81,76 @@ nsp_status nsp_ctc_forced_align(const float* logits, int B, int T, int V,
                                 int32_t* trigger_points,
                                 void* workspace, size_t workspace_bytes, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------
+ * Dense projection on the tcgen05 tensor cores with a fused epilogue (tensor-pipe bound):
+ *     out = residual + alpha * act(x[M,K] * w[N,K]^T + bias)
+ *
+ * Replaces every nn.Linear / kernel-size-1 nn.Conv1d of the encoder path:
+ *   PositionwiseFeedForward.w_1/w_2            modules/positionwise_feed_forward.py:47-48,89
+ *   RelMHA w_key/w_value/w_query/w_pos/w_out   modules/relative_multihead_attention.py:57-60,169-176,217
+ *   ConformerConvBlock.pointwise_conv1 (+F.glu) / pointwise_conv2   modules/conformer_convolution.py:44-69,110-126
+ *   ConvEncoder.bridge encoders/conv.py:87,193 ; CTC.output decoders/ctc.py:81-91,124
+ *
+ * prec  NSP_PREC_BF16: x, w are bf16.  NSP_PREC_TF32: x, w are fp32, one tf32 pass (~1e-3).
+ *       NSP_PREC_FP32: x/x_lo and w/w_lo are the hi/lo halves produced by nsp_split_tf32; three
+ *       tf32 passes accumulate hi*hi + lo*hi + hi*lo in TMEM (fp32-level accuracy; parity mode).
+ * x [M,K] row pitch ldx, w [N,K] row pitch ldw (elements; pitches must be 16-byte multiples).
+ * glu=1: w holds value rows [0,N/2) and gate rows [N/2,N); out[:, j] = v_j * sigmoid(g_j), width N/2.
+ * act: 0 none, 1 relu, 2 swish (x*sigmoid(x)); bias fp32 [N] or NULL; residual fp32 [M,ldr] or NULL.
+ * out: fp32 (out_bf16=0) or bf16 (out_bf16=1) with row pitch ldo; out2 (optional, may be NULL) receives a
+ * bf16 copy of an fp32 result with pitch ldo2.  out may alias residual.
+ * ------------------------------------------------------------------------------------------ */
+typedef enum { NSP_PREC_BF16 = 0, NSP_PREC_TF32 = 1, NSP_PREC_FP32 = 2 } nsp_precision;
+nsp_status nsp_linear_fwd(int prec, const void* x, const void* x_lo, int64_t ldx,
+                          const void* w, const void* w_lo, int64_t ldw,
+                          int M, int N, int K, int glu, int act,
+                          const float* bias, const float* residual, int64_t ldr, float alpha,
+                          void* out, int64_t ldo, int out_bf16, void* out2, int64_t ldo2, void* stream);
+/* hi = round-to-nearest tf32(x), lo = x - hi (both fp32, n elements). */
+nsp_status nsp_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
+/* fp32 -> bf16 (round to nearest even), n elements. */
+nsp_status nsp_cast_f32_to_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * LayerNorm over the last dimension (HBM-bound).  y = (x*in_scale - mean) * rstd * gamma + beta.
+ * Replaces nn.LayerNorm at encoders/conformer_block.py:53,58,70,76,80 and encoders/transformer.py:600.
+ * x fp32 [M, D] (pitch ldx); y fp32 [M, D] and/or y_bf16 bf16 [M, D] (either may be NULL, not both).
+ * ------------------------------------------------------------------------------------------ */
+nsp_status nsp_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps,
+                             float in_scale, float* y, int64_t ldy, void* y_bf16, int64_t ldyb, int M, int D,
+                             void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Relative-position multi-head self-attention, flash-style (scores never reach HBM).
+ * Replaces RelativeMultiheadAttentionMechanism.forward  modules/relative_multihead_attention.py:146-220
+ *   (between the input projections and w_out), _rel_shift :112-144, MultiheadAttentionMechanism.forward
+ *   modules/multihead_attention.py:93-157 (r == NULL), and the masks of encoders/transformer.py:633-686.
+ * q [B*Tq, >=H*dk], k,v [B*Tk, ...] element (b*T + t, h*dk + c), row pitches ldq/ldk/ldv; all bf16
+ * (is_bf16=1) or all fp32.  r: projected position table [rlen, H*dk] (row = relative distance) or NULL.
+ * e[b,h,i,j] = ((q_i+u_h).k_j + (q_i+v_h).r[min(|Tk-Tq+i-j|, clamp_len)]) / sqrt(dk); keys j >= klens[b]
+ * (and causal / chunk-wise exclusions) get finfo.min before the softmax; out[b*Tq+i, h*dk+c] = sum_j aw v.
+ * causal: key visible iff j <= Tk-Tq+i+lookahead.  chunk_c>0: keys restricted to
+ * [chunk_start-chunk_l, chunk_start+chunk_c) of the query's chunk (make_chunkwise_san_mask).
+ * ------------------------------------------------------------------------------------------ */
+nsp_status nsp_relpos_attention_fwd(int is_bf16, const void* q, int64_t ldq, const void* k, int64_t ldk,
+                                    const void* v, int64_t ldv, const void* r, int64_t ldr, int rlen,
+                                    const float* u_bias, const float* v_bias, const int32_t* klens,
+                                    void* out, int64_t ldo, int B, int H, int Tq, int Tk, int dk,
+                                    int clamp_len, int causal, int lookahead, int chunk_c, int chunk_l,
+                                    void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Conformer convolution module core: y = Swish(Norm(depthwise_conv1d_k(x) + bias)), x,y [B,T,d].
+ * Replaces ConformerConvBlock.forward  modules/conformer_convolution.py:113-124 (depthwise Conv1d,
+ * causal trim, LayerNorm | BatchNorm1d(eval) | GroupNorm(d/2 groups), Swish).  w: [d,k] taps.
+ * norm_mode 0 LayerNorm(eps) over d, 1 BatchNorm with running stats, 2 GroupNorm (2 channels/group).
+ * ------------------------------------------------------------------------------------------ */
+nsp_status nsp_conformer_conv_fwd(int is_bf16, const void* x, int64_t ldx, const float* w, const float* bias,
+                                  int norm_mode, const float* norm_w, const float* norm_b,
+                                  const float* run_mean, const float* run_var, float eps,
+                                  void* y, int64_t ldy, int B, int T, int d, int k, int causal, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,3 +59,30 @@ def ptr(t):
 def current_stream_ptr():
     import torch
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+# ---- GEMM / elementwise ----
+_more = {
+    "nsp_linear_fwd": (c_int, [c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int,
+                               c_vp, c_vp, c_i64, c_f32, c_vp, c_i64, c_int, c_vp, c_i64, c_vp]),
+    "nsp_split_tf32": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "nsp_cast_f32_to_bf16": (c_int, [c_vp, c_vp, c_i64, c_vp]),
+}
+for _name, (_res, _args) in _more.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+SIGNATURES.update(_more)
+
+_more = {
+    "nsp_layernorm_fwd": (c_int, [c_vp, c_i64, c_vp, c_vp, c_f32, c_f32, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_vp]),
+    "nsp_relpos_attention_fwd": (c_int, [c_int, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_vp,
+                                         c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                         c_int, c_int, c_vp]),
+    "nsp_conformer_conv_fwd": (c_int, [c_int, c_vp, c_i64, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_f32,
+                                       c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_vp]),
+}
+for _name, (_res, _args) in _more.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+SIGNATURES.update(_more)

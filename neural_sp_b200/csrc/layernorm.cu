@@ -1,0 +1,105 @@
+// LayerNorm over the last dimension (HBM-bound): one warp per row, row held in registers,
+// two-pass mean / variance in fp32 (eps = 1e-12 in the reference amplifies cancellation otherwise).
+//
+// Replaces nn.LayerNorm at  encoders/conformer_block.py:53,58,70,76,80 (norm1..norm5),
+// encoders/transformer.py:600 (norm_out), encoders/transformer_block.py (norm1/2).
+// Writes fp32 and/or bf16 so the next tensor-core GEMM can consume the bf16 copy directly.
+#include "common.cuh"
+
+namespace nsp {
+namespace {
+
+template <int VPT, int VEC>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int64_t ldx,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        float eps, float in_scale, float* __restrict__ y, int64_t ldy,
+                                                        __nv_bfloat16* __restrict__ yb, int64_t ldyb, int M, int D) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const float* xr = x + row * ldx;
+    float v[VPT][VEC];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+        int idx = (j * 32 + lane) * VEC;
+        if (idx < D) {
+            if constexpr (VEC == 4) {
+                float4 t = *reinterpret_cast<const float4*>(xr + idx);
+                v[j][0] = t.x * in_scale; v[j][1] = t.y * in_scale; v[j][2] = t.z * in_scale; v[j][3] = t.w * in_scale;
+            } else {
+                v[j][0] = xr[idx] * in_scale;
+            }
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) s += v[j][k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) v[j][k] = 0.f;
+        }
+    }
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+        int idx = (j * 32 + lane) * VEC;
+        if (idx < D) {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) { float d = v[j][k] - mean; q += d * d; }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+        int idx = (j * 32 + lane) * VEC;
+        if (idx < D) {
+            float o[VEC];
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) o[k] = (v[j][k] - mean) * rstd * __ldg(gamma + idx + k) + __ldg(beta + idx + k);
+            if (y) {
+                if constexpr (VEC == 4) *reinterpret_cast<float4*>(y + row * ldy + idx) = make_float4(o[0], o[1], o[2], o[3]);
+                else y[row * ldy + idx] = o[0];
+            }
+            if (yb) {
+                if constexpr (VEC == 4) {
+                    __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]), b = __floats2bfloat162_rn(o[2], o[3]);
+                    uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
+                    *reinterpret_cast<uint2*>(yb + row * ldyb + idx) = pk;
+                } else {
+                    yb[row * ldyb + idx] = __float2bfloat16_rn(o[0]);
+                }
+            }
+        }
+    }
+}
+
+}  // namespace
+}  // namespace nsp
+
+using namespace nsp;
+
+extern "C" nsp_status nsp_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps,
+                                        float in_scale, float* y, int64_t ldy, void* y_bf16, int64_t ldyb, int M, int D,
+                                        void* stream) {
+    NSP_CHECK_ARG(x && gamma && beta && (y || y_bf16), "layernorm: null pointer");
+    NSP_CHECK_ARG(M > 0 && D > 0, "layernorm: bad shape M=%d D=%d", M, D);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec4 = (D % 4 == 0) && (ldx % 4 == 0) && (!y || ldy % 4 == 0) && (!y_bf16 || ldyb % 4 == 0) &&
+                      ((uintptr_t)x % 16 == 0) && (!y || (uintptr_t)y % 16 == 0) && (!y_bf16 || (uintptr_t)y_bf16 % 8 == 0);
+    const unsigned grid = (unsigned)ceil_div(M, 8);
+    __nv_bfloat16* yb = (__nv_bfloat16*)y_bf16;
+#define NSP_LN(VPT, VEC) layernorm_kernel<VPT, VEC><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, eps, in_scale, y, ldy, yb, ldyb, M, D)
+    if (vec4) {
+        const int vpt = ceil_div(D / 4, 32);
+        if (vpt <= 1) NSP_LN(1, 4); else if (vpt <= 2) NSP_LN(2, 4); else if (vpt <= 4) NSP_LN(4, 4);
+        else if (vpt <= 8) NSP_LN(8, 4); else if (vpt <= 16) NSP_LN(16, 4);
+        else { set_error("layernorm: D=%d too large (max 2048)", D); return NSP_ERR_UNSUPPORTED; }
+    } else {
+        const int vpt = ceil_div(D, 32);
+        if (vpt <= 1) NSP_LN(1, 1); else if (vpt <= 2) NSP_LN(2, 1); else if (vpt <= 4) NSP_LN(4, 1);
+        else if (vpt <= 8) NSP_LN(8, 1); else if (vpt <= 16) NSP_LN(16, 1); else if (vpt <= 32) NSP_LN(32, 1);
+        else { set_error("layernorm: unaligned D=%d too large (max 1024)", D); return NSP_ERR_UNSUPPORTED; }
+    }
+#undef NSP_LN
+    NSP_LAUNCH_OK();
+    return NSP_OK;
+}

@@ -70,3 +70,144 @@ def ctc_forced_align(logits, labels, elens, ylens, blank=0):
                                    ptr(trig), ptr(ws), ws_bytes, current_stream_ptr()),
           "nsp_ctc_forced_align")
     return trig
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core projections
+# ---------------------------------------------------------------------------------------------
+PREC = {"bf16": 0, "tf32": 1, "fp32": 2}
+ACT = {None: 0, "none": 0, "relu": 1, "swish": 2}
+
+
+def split_tf32(x):
+    """fp32 tensor -> (hi, lo) with hi = tf32-rounded x and lo = x - hi (nsp_split_tf32)."""
+    _require_cuda(x)
+    x = x.contiguous()
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    check(lib.nsp_split_tf32(ptr(x), ptr(hi), ptr(lo), x.numel(), current_stream_ptr()), "nsp_split_tf32")
+    return hi, lo
+
+
+def to_bf16(x):
+    """fp32 -> bf16 on the library's cast kernel (bf16 input is returned as is)."""
+    if x.dtype == torch.bfloat16:
+        return x
+    _require_cuda(x)
+    x = x.contiguous()
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(lib.nsp_cast_f32_to_bf16(ptr(x), ptr(y), x.numel(), current_stream_ptr()), "nsp_cast_f32_to_bf16")
+    return y
+
+
+def prepare_weight(w, prec):
+    """Operand form of a [N, K] weight for the given precision: bf16 copy, fp32, or (hi, lo) split."""
+    if prec == "bf16":
+        return (to_bf16(w.detach()),)
+    if prec == "tf32":
+        return (w.detach().float().contiguous(),)
+    return split_tf32(w.detach().float())
+
+
+def linear(x, w_prepared, bias=None, prec="bf16", act=None, glu=False, residual=None, alpha=1.0,
+           out_dtype=torch.float32, out=None, out2_bf16=False):
+    """out = residual + alpha * act(x @ w^T + bias) on the tcgen05 GEMM (nsp_linear_fwd).
+
+    x: [..., K] (bf16 for prec='bf16', else fp32); w_prepared: tuple from prepare_weight.
+    Returns out (and a bf16 copy when out2_bf16).
+    """
+    _require_cuda(x)
+    K = x.shape[-1]
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, K)
+    if x2.stride(1) != 1:
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    w = w_prepared[0]
+    N = w.shape[0]
+    nout = N // 2 if glu else N
+    x_lo = None
+    if prec == "bf16":
+        x2 = to_bf16(x2)
+    else:
+        x2 = x2.float()
+        if prec == "fp32":
+            x2, x_lo = split_tf32(x2)
+    w_lo = w_prepared[1] if prec == "fp32" else None
+    if out is None:
+        out = torch.empty(M, nout, dtype=out_dtype, device=x.device)
+    out2d = out.reshape(-1, nout)
+    res2d = residual.reshape(-1, nout) if residual is not None else None
+    out2 = torch.empty(M, nout, dtype=torch.bfloat16, device=x.device) if out2_bf16 else None
+    check(lib.nsp_linear_fwd(PREC[prec], ptr(x2), ptr(x_lo), x2.stride(0), ptr(w), ptr(w_lo), w.stride(0),
+                             M, N, K, int(glu), ACT[act], ptr(bias), ptr(res2d),
+                             res2d.stride(0) if res2d is not None else 0, float(alpha),
+                             ptr(out2d), out2d.stride(0), int(out2d.dtype == torch.bfloat16),
+                             ptr(out2), out2.stride(0) if out2 is not None else 0, current_stream_ptr()),
+          "nsp_linear_fwd")
+    res = out2d.reshape(*lead, nout)
+    if out2_bf16:
+        return res, out2.reshape(*lead, nout)
+    return res
+
+
+# ---------------------------------------------------------------------------------------------
+# normalisation / attention / conformer convolution
+# ---------------------------------------------------------------------------------------------
+def layernorm(x, weight, bias, eps, out_fp32=True, out_bf16=False, in_scale=1.0):
+    """LayerNorm over the last dim of an fp32 tensor (nsp_layernorm_fwd). Returns fp32 and/or bf16 outputs."""
+    _require_cuda(x)
+    D = x.shape[-1]
+    x2 = x.reshape(-1, D)
+    if x2.stride(1) != 1:
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    y = torch.empty(M, D, dtype=torch.float32, device=x.device) if out_fp32 else None
+    yb = torch.empty(M, D, dtype=torch.bfloat16, device=x.device) if out_bf16 else None
+    check(lib.nsp_layernorm_fwd(ptr(x2), x2.stride(0), ptr(weight), ptr(bias), float(eps), float(in_scale),
+                                ptr(y), D, ptr(yb), D, M, D, current_stream_ptr()), "nsp_layernorm_fwd")
+    outs = tuple(t.reshape(x.shape) for t in (y, yb) if t is not None)
+    return outs[0] if len(outs) == 1 else outs
+
+
+def relpos_attention(q, k, v, klens, n_heads, r=None, u_bias=None, v_bias=None, clamp_len=-1, causal=False,
+                     lookahead=0, chunk_c=0, chunk_l=0):
+    """Flash-style (rel-pos) self-attention (nsp_relpos_attention_fwd).
+
+    q `[B, Tq, H*dk]`, k/v `[B, Tk, H*dk]` (may be strided views of a fused QKV buffer; last dim contiguous),
+    r `[rlen, H*dk]` projected position table or None, klens int32 `[B]` CUDA.  Returns `[B, Tq, H*dk]`.
+    """
+    _require_cuda(q, k, v, klens)
+    B, Tq, D = q.shape
+    Tk = k.shape[1]
+    dk = D // n_heads
+    is_bf16 = q.dtype == torch.bfloat16
+    for t in (q, k, v):
+        assert t.dtype == q.dtype and t.stride(2) == 1 and t.stride(0) == t.shape[1] * t.stride(1)
+    if r is not None:
+        assert r.dtype == q.dtype and r.stride(-1) == 1
+        r = r.reshape(-1, D) if r.dim() == 3 else r
+    out = torch.empty(B, Tq, D, dtype=q.dtype, device=q.device)
+    check(lib.nsp_relpos_attention_fwd(int(is_bf16), ptr(q), q.stride(1), ptr(k), k.stride(1), ptr(v), v.stride(1),
+                                       ptr(r), r.stride(0) if r is not None else 0, r.shape[0] if r is not None else 0,
+                                       ptr(u_bias), ptr(v_bias), ptr(klens), ptr(out), D, B, n_heads, Tq, Tk, dk,
+                                       int(clamp_len), int(causal), int(lookahead), int(chunk_c), int(chunk_l),
+                                       current_stream_ptr()), "nsp_relpos_attention_fwd")
+    return out
+
+
+NORM_MODE = {"layer_norm": 0, "batch_norm": 1, "group_norm": 2}
+
+
+def conformer_conv(x, dw_weight, dw_bias, norm_mode, norm_w, norm_b, eps, run_mean=None, run_var=None, causal=False):
+    """y = Swish(Norm(depthwise_conv(x) + bias)) on `[B, T, d]` (nsp_conformer_conv_fwd)."""
+    _require_cuda(x)
+    B, T, d = x.shape
+    x = x if x.stride(2) == 1 and x.stride(0) == T * x.stride(1) else x.contiguous()
+    k = dw_weight.shape[-1]
+    w = dw_weight.reshape(d, k)
+    y = torch.empty(B, T, d, dtype=x.dtype, device=x.device)
+    check(lib.nsp_conformer_conv_fwd(int(x.dtype == torch.bfloat16), ptr(x), x.stride(1), ptr(w), ptr(dw_bias),
+                                     NORM_MODE[norm_mode], ptr(norm_w), ptr(norm_b), ptr(run_mean), ptr(run_var),
+                                     float(eps), ptr(y), d, B, T, d, k, int(causal), current_stream_ptr()),
+          "nsp_conformer_conv_fwd")
+    return y

@@ -1,0 +1,126 @@
+"""LayerNorm, rel-pos attention and the Conformer conv core against plain PyTorch fp32 references of the
+same ops (written from the reference's formulas: relative_multihead_attention.py:146-220,
+conformer_convolution.py:113-124).  fp32 paths: 2e-5 of max|ref|; bf16 I/O paths: 2e-2."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("M,D", [(1000, 256), (333, 512), (50, 8), (77, 80), (64, 1024), (9, 100)])
+def test_layernorm(M, D):
+    from neural_sp_b200 import ops
+    torch.manual_seed(D)
+    x = torch.randn(M, D, device="cuda") * 3 + 1
+    w, b = torch.randn(D, device="cuda"), torch.randn(D, device="cuda")
+    ref = F.layer_norm(x.double(), (D,), w.double(), b.double(), 1e-12)
+    y, yb = ops.layernorm(x, w, b, 1e-12, out_fp32=True, out_bf16=True)
+    assert (y.double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+    assert (yb.double() - ref).abs().max().item() <= 8e-3 * ref.abs().max().item()
+
+
+def _attn_ref(q, k, v, r, u, vb, klens, H, clamp, causal, lookahead, chunk_c, chunk_l):
+    B, Tq, D = q.shape
+    Tk = k.shape[1]
+    dk = D // H
+    mlen = Tk - Tq
+    q4, k4, v4 = (t.double().view(B, -1, H, dk) for t in (q, k, v))
+    qu = q4 + (u.double()[None, None] if u is not None else 0)
+    qv = q4 + (vb.double()[None, None] if vb is not None else 0)
+    e = torch.einsum("bihd,bjhd->bijh", qu, k4)
+    if r is not None:
+        r3 = r.double().view(-1, H, dk)
+        bd_raw = torch.einsum("bihd,rhd->birh", qv, r3)
+        i = torch.arange(Tq, device=q.device)[:, None]
+        j = torch.arange(Tk, device=q.device)[None, :]
+        dist = (mlen + i - j).abs()
+        if clamp > 0:
+            dist = dist.clamp(max=clamp)
+        dist = dist.clamp(max=r3.shape[0] - 1)
+        bd = torch.gather(bd_raw, 2, dist[None, :, :, None].expand(B, Tq, Tk, H))
+        e = e + bd
+    e = e / math.sqrt(dk)
+    i = torch.arange(Tq, device=q.device)[None, :, None]
+    j = torch.arange(Tk, device=q.device)[None, None, :]
+    mask = j < klens[:, None, None]
+    if causal:
+        mask = mask & (j <= mlen + i + lookahead)
+    if chunk_c > 0:
+        cs = ((mlen + i) // chunk_c) * chunk_c
+        mask = mask & (j >= cs - chunk_l) & (j < cs + chunk_c)
+    e = e.masked_fill(~mask[..., None], torch.finfo(torch.float32).min)
+    aw = torch.softmax(e, dim=2)
+    return torch.einsum("bijh,bjhd->bihd", aw, v4).reshape(B, Tq, D)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(B=3, T=125, H=4, dk=64, clamp=10), dict(B=2, T=250, H=8, dk=64, clamp=10),
+    dict(B=2, T=97, H=4, dk=64, clamp=-1), dict(B=2, T=40, H=4, dk=2, clamp=-1),
+    dict(B=2, T=70, H=2, dk=128, clamp=5, xl=True), dict(B=2, T=64, H=4, dk=16, clamp=-1, rel=False),
+    dict(B=2, T=90, H=4, dk=64, clamp=10, causal=True, lookahead=2),
+    dict(B=2, T=96, H=4, dk=64, clamp=-1, chunk_c=16, chunk_l=32),
+    dict(B=2, T=33, Tk=80, H=4, dk=64, clamp=10),
+])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_relpos_attention(cfg, dtype):
+    from neural_sp_b200 import ops
+    B, T, H, dk = cfg["B"], cfg["T"], cfg["H"], cfg["dk"]
+    Tk = cfg.get("Tk", T)
+    D = H * dk
+    torch.manual_seed(T + dk)
+    dev = "cuda"
+    qkv = torch.randn(B, Tk, 3 * D, device=dev).to(dtype)
+    q, k, v = qkv[:, Tk - T:, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:]
+    q = q.contiguous() if Tk != T else q
+    r = (torch.randn(Tk, D, device=dev).to(dtype)) if cfg.get("rel", True) else None
+    u = torch.randn(H, dk, device=dev) * 0.3 if cfg.get("xl") else None
+    vb = torch.randn(H, dk, device=dev) * 0.3 if cfg.get("xl") else None
+    klens = torch.tensor([Tk - 7 * b for b in range(B)], dtype=torch.int32, device=dev)
+    ref = _attn_ref(q.float(), k.float(), v.float(), r.float() if r is not None else None, u, vb, klens, H,
+                    cfg["clamp"], cfg.get("causal", False), cfg.get("lookahead", 0), cfg.get("chunk_c", 0), cfg.get("chunk_l", 0))
+    out = ops.relpos_attention(q, k, v, klens, H, r=r, u_bias=u, v_bias=vb, clamp_len=cfg["clamp"],
+                               causal=cfg.get("causal", False), lookahead=cfg.get("lookahead", 0),
+                               chunk_c=cfg.get("chunk_c", 0), chunk_l=cfg.get("chunk_l", 0))
+    tol = 2e-5 if dtype == torch.float32 else 2e-2
+    err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err <= tol, err
+
+
+@pytest.mark.parametrize("d,k,T,mode,causal", [(256, 15, 125, "layer_norm", False), (512, 15, 250, "layer_norm", False),
+                                                (512, 31, 77, "layer_norm", False), (8, 3, 45, "batch_norm", False),
+                                                (64, 7, 50, "layer_norm", True), (64, 5, 33, "group_norm", False),
+                                                (144, 9, 40, "batch_norm", True)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_conformer_conv(d, k, T, mode, causal, dtype):
+    from neural_sp_b200 import ops
+    torch.manual_seed(d + k)
+    dev = "cuda"
+    B = 3
+    x = torch.randn(B, T, d, device=dev).to(dtype)
+    w = torch.randn(d, 1, k, device=dev) * 0.3
+    bias = torch.randn(d, device=dev) * 0.1
+    g, bt = torch.rand(d, device=dev) + 0.5, torch.randn(d, device=dev) * 0.1
+    rm, rv = torch.randn(d, device=dev) * 0.1, torch.rand(d, device=dev) + 0.5
+    pad = k - 1 if causal else (k - 1) // 2
+    xr = x.float().double().transpose(1, 2)
+    y = F.conv1d(xr, w.double(), bias.double(), padding=pad, groups=d)
+    if causal:
+        y = y[:, :, :-pad]
+    y = y.transpose(1, 2)
+    if mode == "layer_norm":
+        eps = 1e-12
+        y = F.layer_norm(y, (d,), g.double(), bt.double(), eps)
+    elif mode == "batch_norm":
+        eps = 1e-5
+        y = (y - rm.double()) / torch.sqrt(rv.double() + eps) * g.double() + bt.double()
+    else:
+        eps = 1e-5
+        y = F.group_norm(y.reshape(B * T, d, 1), d // 2, g.double(), bt.double(), eps).reshape(B, T, d)
+    ref = y * torch.sigmoid(y)
+    out = ops.conformer_conv(x, w, bias, mode, g, bt, eps, rm, rv, causal=causal)
+    tol = 3e-5 if dtype == torch.float32 else 2e-2
+    err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err <= tol, err
