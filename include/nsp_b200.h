@@ -151,6 +151,30 @@ nsp_status nsp_conformer_conv_fwd(int is_bf16, const void* x, int64_t ldx, const
                                   const float* run_mean, const float* run_var, float eps,
                                   void* y, int64_t ldy, int B, int T, int d, int k, int causal, void* stream);
 
+/* x *= a in place (LayerDrop's eval-time 1/(1-p) rescale, encoders/conformer_block.py:122-126). */
+nsp_status nsp_scale_inplace(float* x, float a, int64_t n, void* stream);
+/* y[n] = sum_m x[m, n] for a dense fp32 [M, N] matrix (bias gradients). */
+nsp_status nsp_colsum(const float* x, float* y, int M, int N, void* stream);
+/* TransformerXL sinusoid table: XLPositionalEmbedding.forward modules/positional_embedding.py:135-138.
+ * table fp32 [rows, d]; row r is position -(r+1) = relative distance r: cat(sin(pos*inv_freq), cos(pos*inv_freq)). */
+nsp_status nsp_xl_pos_table(const float* inv_freq, float* table, int rows, int d, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Convolutional front-end on channels-last activations [B, T, F, C].
+ * Replaces Conv2dBlock.forward encoders/conv.py:347-396 and the view/transposes of ConvEncoder.forward :181-189.
+ * nsp_conv3x3_relu_fwd: y = relu?(conv3x3(x, w, pad 1, stride 1) + bias); w is nn.Conv2d weight [CO, CI, 3, 3];
+ *   in_chmajor=1 reads the raw feature layout [B, T, CI, F] (conv.py:183).  in/out fp32 or bf16.
+ * nsp_maxpool2d_fwd: max-pool kernel=stride=(pool_t, pool_f), ceil_mode (conv.py:330-337); out_chmajor=1 writes
+ *   [B, T', C*F'] with index c*F'+f, the flatten of conv.py:189; f_keep>0 keeps only the first f_keep bins.
+ * nsp_maxpool_time_fwd: MaxPoolSubsampler  encoders/subsampling.py:175-209 on [B, T, D] -> [B, ceil(T/f), D].
+ * ------------------------------------------------------------------------------------------ */
+nsp_status nsp_conv3x3_relu_fwd(int in_bf16, int out_bf16, const void* x, int in_chmajor, const float* w,
+                                const float* bias, void* y, int B, int T, int F, int CI, int CO, int relu,
+                                void* stream);
+nsp_status nsp_maxpool2d_fwd(int in_bf16, int out_bf16, const void* x, void* y, int B, int T, int F, int C,
+                             int pool_t, int pool_f, int f_keep, int out_chmajor, void* stream);
+nsp_status nsp_maxpool_time_fwd(int is_bf16, const void* x, void* y, int B, int T, int D, int factor, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

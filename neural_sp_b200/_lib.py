@@ -86,3 +86,18 @@ for _name, (_res, _args) in _more.items():
     _fn.restype = _res
     _fn.argtypes = _args
 SIGNATURES.update(_more)
+
+_more = {
+    "nsp_scale_inplace": (c_int, [c_vp, c_f32, c_i64, c_vp]),
+    "nsp_colsum": (c_int, [c_vp, c_vp, c_int, c_int, c_vp]),
+    "nsp_xl_pos_table": (c_int, [c_vp, c_vp, c_int, c_int, c_vp]),
+    "nsp_conv3x3_relu_fwd": (c_int, [c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
+                                     c_int, c_vp]),
+    "nsp_maxpool2d_fwd": (c_int, [c_int, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "nsp_maxpool_time_fwd": (c_int, [c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
+}
+for _name, (_res, _args) in _more.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+SIGNATURES.update(_more)

@@ -24,6 +24,41 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
     for (; i < n; i += stride) y[i] = __float2bfloat16_rn(x[i]);
 }
 
+__global__ void __launch_bounds__(256) scale_kernel(float* __restrict__ x, float a, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (; i < n; i += stride) x[i] *= a;
+}
+
+// column sums of a row-major [M, N] fp32 matrix: block = 32 columns x 8 row slices
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, float* __restrict__ y, int M, int N) {
+    __shared__ float part[8][33];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31), rs = threadIdx.x >> 5;
+    float acc = 0.f;
+    if (c < N) for (int r = rs; r < M; r += 8) acc += x[(int64_t)r * N + c];
+    part[rs][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (rs == 0 && c < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x & 31];
+        y[c] = t;
+    }
+}
+
+// TransformerXL sinusoid table (positional_embedding.py:135-138): row r <-> position -(r+1):
+// tab[r, i] = sin(-(r+1) * inv_freq[i]) for i < d/2, cos(-(r+1) * inv_freq[i - d/2]) otherwise.
+__global__ void __launch_bounds__(256) xl_pos_table_kernel(const float* __restrict__ inv_freq, float* __restrict__ tab, int rows, int d) {
+    const int half = d / 2;
+    const int64_t n = (int64_t)rows * d;
+    for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < n; e += (int64_t)gridDim.x * 256) {
+        int r = (int)(e / d), i = (int)(e % d);
+        float pos = -(float)(r + 1);
+        float ang = pos * inv_freq[i < half ? i : i - half];
+        tab[e] = i < half ? sinf(ang) : cosf(ang);
+    }
+}
+
 }  // namespace
 }  // namespace nsp
 
@@ -47,6 +82,28 @@ extern "C" nsp_status nsp_cast_f32_to_bf16(const float* x, void* y, int64_t n, v
     NSP_CHECK_ARG(x && y && n >= 0, "cast_f32_to_bf16: bad arguments");
     if (n == 0) return NSP_OK;
     cast_bf16_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n);
+    NSP_LAUNCH_OK();
+    return NSP_OK;
+}
+
+extern "C" nsp_status nsp_scale_inplace(float* x, float a, int64_t n, void* stream) {
+    NSP_CHECK_ARG(x && n >= 0, "scale_inplace: bad arguments");
+    if (n == 0) return NSP_OK;
+    scale_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, a, n);
+    NSP_LAUNCH_OK();
+    return NSP_OK;
+}
+
+extern "C" nsp_status nsp_colsum(const float* x, float* y, int M, int N, void* stream) {
+    NSP_CHECK_ARG(x && y && M > 0 && N > 0, "colsum: bad arguments");
+    colsum_kernel<<<(unsigned)ceil_div(N, 32), 256, 0, (cudaStream_t)stream>>>(x, y, M, N);
+    NSP_LAUNCH_OK();
+    return NSP_OK;
+}
+
+extern "C" nsp_status nsp_xl_pos_table(const float* inv_freq, float* table, int rows, int d, void* stream) {
+    NSP_CHECK_ARG(inv_freq && table && rows > 0 && d > 0 && d % 2 == 0, "xl_pos_table: bad arguments");
+    xl_pos_table_kernel<<<ew_grid((int64_t)rows * d), 256, 0, (cudaStream_t)stream>>>(inv_freq, table, rows, d);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }

@@ -1,0 +1,29 @@
+"""Conformer encoder (reference encoders/conformer.py:18-111): TransformerEncoder with Conformer blocks."""
+import copy
+
+import torch.nn as nn
+
+from .conformer_block import ConformerEncoderBlock
+from .transformer import TransformerEncoder
+
+
+class ConformerEncoder(TransformerEncoder):
+    def __init__(self, input_dim, enc_type, n_heads, kernel_size, normalization, n_layers, n_layers_sub1,
+                 n_layers_sub2, d_model, d_ff, ffn_bottleneck_dim, ffn_activation, pe_type, layer_norm_eps,
+                 last_proj_dim, dropout_in, dropout, dropout_att, dropout_layer, subsample, subsample_type,
+                 n_stacks, n_splices, frontend_conv, task_specific_layer, param_init, clamp_len, lookahead,
+                 chunk_size_left, chunk_size_current, chunk_size_right, streaming_type):
+        super().__init__(input_dim, enc_type, n_heads, n_layers, n_layers_sub1, n_layers_sub2, d_model, d_ff,
+                         ffn_bottleneck_dim, ffn_activation, pe_type, layer_norm_eps, last_proj_dim, dropout_in,
+                         dropout, dropout_att, dropout_layer, subsample, subsample_type, n_stacks, n_splices,
+                         frontend_conv, task_specific_layer, param_init, clamp_len, lookahead, chunk_size_left,
+                         chunk_size_current, chunk_size_right, streaming_type)
+        if 'conformer_v2' in enc_type:
+            raise NotImplementedError("conformer_v2 blocks are not on the B200 path")
+        assert pe_type in ['relative', 'relative_xl']
+        causal = self.unidir or (self.streaming_type == 'mask')
+        self.layers = nn.ModuleList([copy.deepcopy(ConformerEncoderBlock(
+            d_model, d_ff, n_heads, kernel_size, dropout, dropout_att, dropout_layer * (lth + 1) / n_layers,
+            layer_norm_eps, ffn_activation, param_init, pe_type, clamp_len, ffn_bottleneck_dim, causal, normalization))
+            for lth in range(n_layers)])
+        self.reset_parameters(param_init)

@@ -1,0 +1,166 @@
+"""VGG-style CNN front-end (reference encoders/conv.py:18-195, 289-396, 451-505), B200-native.
+
+Same constructor, ``forward(xs, xlens, lookback, lookahead) -> (xs, xlens)`` and state_dict keys
+(``layers.N.conv1/conv2.{weight,bias}``, ``bridge.{weight,bias}``).  Activations are channels-last
+``[B, T, F, C]`` on the device; the reference's final flatten order (``c * F' + f``, conv.py:189) is
+produced by the last pooling kernel (or folded into the bridge weight's column order)."""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..modules._prep import prepared, get_precision, act_dtype
+from ..modules.initialization import init_with_lecun_normal
+from .encoder_base import EncoderBase
+
+
+def parse_cnn_config(channels, kernel_sizes, strides, poolings):
+    """'32_32', '(3,3)_(3,3)', ... -> lists (reference conv.py:480-505)."""
+    def pairs(s):
+        return [[int(v) for v in tok.strip('()').split(',')] for tok in s.split('_')] if s else []
+    is_1dconv = '(' not in kernel_sizes
+    if is_1dconv:
+        to_i = lambda s: [int(c) for c in s.split('_')] if s else []   # noqa: E731
+        return (to_i(channels), to_i(kernel_sizes), to_i(strides), to_i(poolings)), True
+    chans = [int(c) for c in channels.split('_')] if channels else []
+    return (chans, pairs(kernel_sizes), pairs(strides), pairs(poolings)), False
+
+
+def _conv_len(n, stride):       # k=3, p=1: floor((n + 2 - 2 - 1)/s) + 1   (conv.py:476-477)
+    return (n - 1) // stride + 1
+
+
+def _pool_len(n, k):            # ceil-mode pool, kernel = stride = k      (conv.py:472-474)
+    return (n + 1 - k) // k + 1
+
+
+class Conv2dBlock(EncoderBase):
+    """conv3x3 -> ReLU -> conv3x3 -> ReLU -> max-pool (reference conv.py:289-396)."""
+
+    def __init__(self, input_dim, in_channel, out_channel, kernel_size, stride, pooling, dropout, normalization,
+                 residual):
+        super().__init__()
+        if tuple(kernel_size) != (3, 3) or tuple(stride) != (1, 1):
+            raise NotImplementedError("B200 front-end supports 3x3 kernels with stride (1,1) (all reference recipes)")
+        if normalization:
+            raise NotImplementedError("conv_normalization=%r is not on the B200 path" % normalization)
+        self.residual = residual
+        self.dropout = nn.Dropout(p=dropout)
+        self.time_axis = 0
+        self.conv1 = nn.Conv2d(in_channel, out_channel, kernel_size=tuple(kernel_size), stride=(1, 1), padding=(1, 1))
+        self.conv2 = nn.Conv2d(out_channel, out_channel, kernel_size=tuple(kernel_size), stride=tuple(stride), padding=(1, 1))
+        self.norm1 = self.norm2 = None
+        self._odim = input_dim
+        self.pooling = [1, 1]
+        self._factor = 1
+        if len(pooling) > 0 and np.prod(pooling) > 1:
+            self.pooling = list(pooling)
+            self._odim = _pool_len(self._odim, pooling[1])
+            if self._odim % 2 != 0:
+                self._odim = (self._odim // 2) * 2
+            self._factor *= pooling[0]
+        self.pool = self.pooling if self._factor > 1 or self.pooling[1] > 1 else None
+
+    def forward(self, xs, xlens, B, T, F, first, last_chmajor, lookback=False, lookahead=False):
+        """xs: raw features (first block) or channels-last `[B, T, F, C]`.  Returns (xs, xlens, T', F')."""
+        if lookback or lookahead:
+            raise NotImplementedError("CNN lookback/lookahead trimming (streaming) is a 'next' row")
+        if self.training and self.dropout.p > 0:
+            raise NotImplementedError("dropout > 0 in training mode is not on the B200 path yet")
+        adt = act_dtype(get_precision(self))
+        res_in = xs
+        xs = ops.conv3x3_relu(xs, self.conv1.weight, self.conv1.bias, B, T, F, in_chmajor=first, out_dtype=adt)
+        if self.residual and self.conv1.in_channels == self.conv2.out_channels:
+            raise NotImplementedError("residual CNN blocks are not on the B200 path")
+        xs = ops.conv3x3_relu(xs, self.conv2.weight, self.conv2.bias, B, T, F, out_dtype=adt)
+        xlens = torch.IntTensor([_conv_len(_conv_len(int(n), 1), 1) for n in xlens])
+        del res_in
+        if self.pool is not None:
+            xs = ops.maxpool2d(xs, self.pooling[0], self.pooling[1], out_chmajor=last_chmajor)
+            xlens = torch.IntTensor([_pool_len(int(n), self.pooling[0]) for n in xlens])
+            T, F = -(-T // self.pooling[0]), -(-F // self.pooling[1])
+        elif last_chmajor:
+            xs = ops.maxpool2d(xs, 1, 1, out_chmajor=True)
+        return xs, xlens, T, F
+
+
+class ConvEncoder(EncoderBase):
+    def __init__(self, input_dim, in_channel, channels, kernel_sizes, strides, poolings, dropout, normalization,
+                 residual, bottleneck_dim, param_init):
+        super().__init__()
+        assert channels
+        (channels, kernel_sizes, strides, poolings), is_1dconv = parse_cnn_config(channels, kernel_sizes, strides, poolings)
+        if is_1dconv:
+            raise NotImplementedError("1-D CNN front-end (TDS-style) is out of scope")
+        self.is_1dconv = False
+        self.in_channel = in_channel
+        assert input_dim % in_channel == 0
+        self.input_freq = input_dim // in_channel
+        self.residual = residual
+        assert len(channels) > 0 and len(channels) == len(kernel_sizes) == len(strides) == len(poolings)
+        self.layers = nn.ModuleList()
+        C_i, in_freq = in_channel, self.input_freq
+        for lth in range(len(channels)):
+            block = Conv2dBlock(in_freq, C_i, channels[lth], kernel_sizes[lth], strides[lth], poolings[lth],
+                                dropout, normalization, residual)
+            self.layers += [block]
+            in_freq = block.output_dim
+            C_i = channels[lth]
+        self._c_last, self._f_last = C_i, in_freq
+        self._odim = int(C_i * in_freq)
+        self.bridge = None
+        if bottleneck_dim > 0 and bottleneck_dim != self._odim:
+            self.bridge = nn.Linear(self._odim, bottleneck_dim)
+            self._odim = bottleneck_dim
+        self._factor = 1
+        for s in strides:
+            self._factor *= s[0]
+        for p in poolings:
+            self._factor *= p[0]
+        self._context_size = self._calc_context(kernel_sizes, strides, poolings)
+        for n, p in self.named_parameters():
+            init_with_lecun_normal(n, p, param_init)
+
+    @staticmethod
+    def _calc_context(kernel_sizes, strides, poolings):     # reference conv.py:142-159
+        ctx, bottom, factor = 0, 0, 1
+        for ks, st, po in zip(kernel_sizes, strides, poolings):
+            look = ((ks[0] - 1) // 2) * 2
+            if factor == 1:
+                ctx += look
+                bottom = ctx
+            else:
+                ctx += bottom * look
+                bottom *= st[0] * po[0]
+            factor *= st[0] * po[0]
+        return ctx
+
+    @property
+    def context_size(self):
+        return self._context_size
+
+    def forward(self, xs, xlens, lookback=False, lookahead=False, out_scale=1.0):
+        """xs `[B, T, F]` fp32 on the GPU, xlens IntTensor `[B]` (CPU) -> (`[B, T', odim]` fp32, xlens)."""
+        B, T, Fdim = xs.size()
+        F = Fdim // self.in_channel
+        prec = get_precision(self)
+        xs = xs.contiguous().float()
+        n = len(self.layers)
+        for i, block in enumerate(self.layers):
+            # with a bridge the channels-last flatten is absorbed by permuting the bridge weight's columns
+            last_chmajor = (i == n - 1) and self.bridge is None
+            xs, xlens, T, F = block(xs, xlens, B, T, F, first=(i == 0), last_chmajor=last_chmajor,
+                                    lookback=lookback, lookahead=lookahead)
+        if self.bridge is not None:
+            C, Fo = self._c_last, F
+            wb = prepared(self, "bridge", prec, (self.bridge.weight,),
+                          build=lambda w: w.view(w.size(0), C, Fo).transpose(1, 2).reshape(w.size(0), Fo * C))
+            xs = ops.linear(xs.reshape(B, T, Fo * C), wb, self.bridge.bias, prec=prec, alpha=out_scale,
+                            out_dtype=torch.float32)
+        else:
+            xs = xs.float() if xs.dtype != torch.float32 else xs
+            if out_scale != 1.0:
+                xs = ops.scale_(xs.contiguous(), out_scale)
+        return xs, xlens

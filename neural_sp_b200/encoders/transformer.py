@@ -1,0 +1,201 @@
+"""Transformer encoder (reference encoders/transformer.py:40-617), B200-native.
+
+Same constructor arguments, ``forward(xs, xlens, task, ...) -> {'ys': {'xs', 'xlens'}, 'ys_sub1', 'ys_sub2'}``
+and state_dict keys (``conv.*``, ``embed.*``, ``pos_emb.inv_freq``, ``u_bias/v_bias``, ``layers.N.*``,
+``norm_out.*``, ``bridge*.*``).  The `[B,T',T']` boolean mask of the reference (:633-686) is never built:
+key-padding / causal / chunk visibility are evaluated inside the attention kernel from device-side lengths.
+Supported here: offline full-context and unidirectional ('uni', with per-layer lookahead) encoders with
+hierarchical max-pool subsampling and sub-task outputs.  Latency-controlled chunking ('reshape'/'mask') and
+streaming caches are 'next' rows and raise NotImplementedError."""
+import copy
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..modules._prep import prepared, get_precision
+from ..modules.positional_embedding import XLPositionalEmbedding
+from .encoder_base import EncoderBase
+from .subsampling import MaxPoolSubsampler
+from .transformer_block import TransformerEncoderBlock
+
+
+def lens_to_device(xlens, device):
+    """CPU IntTensor -> int32 CUDA tensor without a host sync (pinned staging buffer)."""
+    t = xlens.to(torch.int32)
+    if device.type == "cuda":
+        t = t.pin_memory()
+    return t.to(device, non_blocking=True)
+
+
+class TransformerEncoder(EncoderBase):
+    def __init__(self, input_dim, enc_type, n_heads, n_layers, n_layers_sub1, n_layers_sub2, d_model, d_ff,
+                 ffn_bottleneck_dim, ffn_activation, pe_type, layer_norm_eps, last_proj_dim, dropout_in, dropout,
+                 dropout_att, dropout_layer, subsample, subsample_type, n_stacks, n_splices, frontend_conv,
+                 task_specific_layer, param_init, clamp_len, lookahead, chunk_size_left, chunk_size_current,
+                 chunk_size_right, streaming_type):
+        super().__init__()
+        self.subsample_factors = [1] * n_layers
+        for lth, s in enumerate(list(map(int, subsample.split('_')[:n_layers]))):
+            self.subsample_factors[lth] = s
+        lookaheads = [0] * n_layers
+        for lth, s in enumerate(list(map(int, lookahead.split('_')[:n_layers]))):
+            lookaheads[lth] = s
+        self.enc_type = enc_type
+        self.d_model = d_model
+        self.n_layers = n_layers
+        self.n_heads = n_heads
+        self.pe_type = pe_type
+        self.scale = math.sqrt(d_model)
+        self.unidir = 'uni' in enc_type
+        self.lookaheads = lookaheads
+        if sum(lookaheads) > 0:
+            assert self.unidir
+        cl, cc, cr = str(chunk_size_left), str(chunk_size_current), str(chunk_size_right)
+        self.N_l = int(cl.split('_')[-1]) // n_stacks
+        self.N_c = int(cc.split('_')[-1]) // n_stacks
+        self.N_r = int(cr.split('_')[-1]) // n_stacks
+        self.lc_bidir = self.N_c > 0 and enc_type != 'conv' and 'uni' not in enc_type
+        self.cnn_lookahead = self.unidir or enc_type == 'conv'
+        self.streaming_type = streaming_type if self.lc_bidir else ''
+        self.causal = self.unidir or self.streaming_type == 'mask'
+        if self.lc_bidir:
+            raise NotImplementedError("latency-controlled chunking is a 'next' row (SURVEY.md 8f-4)")
+        self.n_layers_sub1 = n_layers_sub1
+        self.n_layers_sub2 = n_layers_sub2
+        self.task_specific_layer = task_specific_layer
+        if task_specific_layer and (n_layers_sub1 > 0 or n_layers_sub2 > 0):
+            raise NotImplementedError("task-specific sub-task layers are not on the B200 path")
+        self.bridge = self.bridge_sub1 = self.bridge_sub2 = None
+        self.aws_dict, self.data_dict = {}, {}
+
+        self.conv = frontend_conv
+        if self.conv is not None:
+            self._odim = self.conv.output_dim
+        else:
+            self._odim = input_dim * n_splices * n_stacks
+            self.embed = nn.Linear(self._odim, d_model)
+        self._factor = 1
+        self.conv_factor = self.conv.subsampling_factor if self.conv is not None else 1
+        self._factor *= self.conv_factor
+        self.subsample_layers = None
+        if np.prod(self.subsample_factors) > 1:
+            self._factor *= int(np.prod(self.subsample_factors))
+            if subsample_type != 'max_pool':
+                raise NotImplementedError("subsample_type=%r is not on the B200 path (max_pool is)" % subsample_type)
+            self.subsample_layers = nn.ModuleList([MaxPoolSubsampler(f) for f in self.subsample_factors])
+
+        self.pos_enc, self.pos_emb = None, None
+        self.u_bias, self.v_bias = None, None
+        if pe_type in ['relative', 'relative_xl']:
+            self.pos_emb = XLPositionalEmbedding(d_model, dropout)
+            if pe_type == 'relative_xl':
+                self.u_bias = nn.Parameter(torch.Tensor(n_heads, d_model // n_heads))
+                self.v_bias = nn.Parameter(torch.Tensor(n_heads, d_model // n_heads))
+        elif pe_type != 'none':
+            raise NotImplementedError("absolute positional encoding pe_type=%r is not on the B200 path "
+                                      "(none, relative, relative_xl are)" % pe_type)
+
+        self.layers = nn.ModuleList([copy.deepcopy(TransformerEncoderBlock(
+            d_model, d_ff, n_heads, dropout, dropout_att, dropout_layer * (lth + 1) / n_layers, layer_norm_eps,
+            ffn_activation, param_init, pe_type, clamp_len, ffn_bottleneck_dim)) for lth in range(n_layers)])
+        self.norm_out = nn.LayerNorm(d_model, eps=layer_norm_eps)
+        self._odim = d_model
+
+        for sub, nl in (('sub1', n_layers_sub1), ('sub2', n_layers_sub2)):
+            if nl > 0:
+                odim_sub = d_model
+                if last_proj_dim > 0 and last_proj_dim != self.output_dim:
+                    setattr(self, 'bridge_' + sub, nn.Linear(self._odim, last_proj_dim))
+                    odim_sub = last_proj_dim
+                setattr(self, 'norm_out_' + sub, None if nl == n_layers else nn.LayerNorm(odim_sub, eps=layer_norm_eps))
+        if last_proj_dim > 0 and last_proj_dim != self.output_dim:
+            self.bridge = nn.Linear(self._odim, last_proj_dim)
+            self._odim = last_proj_dim
+        self.reset_parameters(param_init)
+        self.reset_cache()
+
+    def reset_parameters(self, param_init):
+        if param_init == 'xavier_uniform':
+            lins = [getattr(self, 'embed', None), self.bridge, self.bridge_sub1, self.bridge_sub2]
+            for lin in lins:
+                if lin is not None:
+                    nn.init.xavier_uniform_(lin.weight)
+                    nn.init.constant_(lin.bias, 0.)
+            if self.pe_type == 'relative_xl':
+                nn.init.xavier_uniform_(self.u_bias)
+                nn.init.xavier_uniform_(self.v_bias)
+
+    def reset_cache(self):
+        self.cache = [None] * self.n_layers
+        self.offset = 0
+
+    def _proj(self, name, lin, xs, scale=1.0):
+        prec = get_precision(self)
+        return ops.linear(xs, prepared(self, name, prec, (lin.weight,)), lin.bias, prec=prec, alpha=scale,
+                          out_dtype=torch.float32)
+
+    def _sub_out(self, xs, module):
+        xs_sub = xs.clone()
+        bridge = getattr(self, 'bridge_' + module)
+        if bridge is not None:
+            xs_sub = self._proj('bridge_' + module, bridge, xs_sub)
+        norm = getattr(self, 'norm_out_' + module)
+        if norm is not None:
+            xs_sub = ops.layernorm(xs_sub, norm.weight, norm.bias, norm.eps)
+        return xs_sub
+
+    def forward(self, xs, xlens, task, streaming=False, lookback=False, lookahead=False):
+        """xs `[B, T, input_dim]` fp32 on the GPU; xlens IntTensor `[B]` on the CPU (reference contract)."""
+        if streaming:
+            raise NotImplementedError("streaming inference is a 'next' row (SURVEY.md 8f-4)")
+        eouts = {'ys': {'xs': None, 'xlens': None}, 'ys_sub1': {'xs': None, 'xlens': None},
+                 'ys_sub2': {'xs': None, 'xlens': None}}
+        with torch.no_grad():
+            rel = 'relative' in self.pe_type
+            if self.conv is None:
+                xs = self._proj('embed', self.embed, xs.float(), scale=self.scale if rel else 1.0)
+            else:
+                xs, xlens = self.conv(xs, xlens, lookback=lookback, lookahead=lookahead,
+                                      out_scale=self.scale if (rel and self.enc_type != 'conv') else 1.0)
+            if self.enc_type == 'conv':
+                eouts['ys']['xs'], eouts['ys']['xlens'] = xs, xlens
+                return eouts
+            self.reset_cache()
+            dev = xs.device
+            klens = lens_to_device(xlens, dev)
+            pos = self.pos_emb.table(xs.size(1)) if rel else None
+
+            def mask_kw(lth):
+                return dict(causal=True, lookahead=self.lookaheads[lth]) if self.unidir else {}
+
+            for lth, layer in enumerate(self.layers):
+                xs, _ = layer(xs, klens, cache=None, pos_embs=pos, rel_bias=(self.u_bias, self.v_bias),
+                              mask_kw=mask_kw(lth))
+                if lth == self.n_layers_sub1 - 1:
+                    xs_sub1, xlens_sub1 = self._sub_out(xs, 'sub1'), xlens.clone()
+                    if task == 'ys_sub1':
+                        eouts[task]['xs'], eouts[task]['xlens'] = xs_sub1, xlens_sub1
+                        return eouts
+                if lth == self.n_layers_sub2 - 1:
+                    xs_sub2, xlens_sub2 = self._sub_out(xs, 'sub2'), xlens.clone()
+                    if task == 'ys_sub2':
+                        eouts[task]['xs'], eouts[task]['xlens'] = xs_sub2, xlens_sub2
+                        return eouts
+                if lth < len(self.layers) - 1 and self.subsample_factors[lth] > 1:
+                    xs, xlens = self.subsample_layers[lth](xs, xlens)
+                    klens = lens_to_device(xlens, dev)
+                    if rel:
+                        pos = self.pos_emb.table(xs.size(1))
+            xs = ops.layernorm(xs, self.norm_out.weight, self.norm_out.bias, self.norm_out.eps)
+            if self.bridge is not None:
+                xs = self._proj('bridge', self.bridge, xs)
+        if task in ['all', 'ys']:
+            eouts['ys']['xs'], eouts['ys']['xlens'] = xs, xlens
+        if self.n_layers_sub1 >= 1 and task == 'all':
+            eouts['ys_sub1']['xs'], eouts['ys_sub1']['xlens'] = xs_sub1, xlens_sub1
+        if self.n_layers_sub2 >= 1 and task == 'all':
+            eouts['ys_sub2']['xs'], eouts['ys_sub2']['xlens'] = xs_sub2, xlens_sub2
+        return eouts

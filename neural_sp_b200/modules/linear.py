@@ -1,9 +1,49 @@
-"""Linear layer whose matmul runs on the library's tcgen05 GEMM (state_dict-compatible with nn.Linear)."""
+"""nn.Linear whose matmul runs on the library's tcgen05 GEMM (state_dict-compatible with nn.Linear).
+
+Forward under autograd is supported through a custom Function whose backward also uses the same GEMM
+(dX = dY W, dW = dY^T X), so heads such as the CTC output layers train through the CUDA path."""
+import torch
 import torch.nn as nn
-import torch.nn.functional as F
+
+from .. import ops
+from ._prep import prepared, get_precision
+
+
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, module, prec):
+        wp = prepared(module, "w", prec, (weight,))
+        y = ops.linear(x, wp, bias, prec=prec, out_dtype=torch.float32)
+        ctx.save_for_backward(x, weight)
+        ctx.module, ctx.prec, ctx.has_bias = module, prec, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        prec = ctx.prec
+        gy2 = gy.reshape(-1, gy.shape[-1]).float().contiguous()
+        x2 = x.reshape(-1, x.shape[-1]).float()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            # dX[M,K] = dY[M,N] @ W[N,K]  ->  GEMM with "weight" W^T [K,N]
+            wt = prepared(ctx.module, "wT", prec, (weight,), build=lambda w: w.t().contiguous())
+            gx = ops.linear(gy2, wt, None, prec=prec, out_dtype=torch.float32).reshape(x.shape)
+        if ctx.needs_input_grad[1]:
+            # dW[N,K] = dY^T[N,M] @ X[M,K]  ->  A = dY^T [N,M], "weight" = X^T [K,M]
+            gw = ops.linear(gy2.t().contiguous(), ops.prepare_weight(x2.t().contiguous(), prec), None, prec=prec,
+                            out_dtype=torch.float32)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = ops.colsum(gy2)
+        return gx, gw, gb, None, None
 
 
 class Linear(nn.Linear):
+    precision = "bf16"
+
     def forward(self, x):
-        # TODO(round 1): route through ops.linear (tcgen05 GEMM) once gemm_tcgen05.cu lands
-        return F.linear(x, self.weight, self.bias)
+        prec = get_precision(self)
+        if torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad):
+            return _LinearFn.apply(x, self.weight, self.bias, self, prec)
+        wp = prepared(self, "w", prec, (self.weight,))
+        return ops.linear(x, wp, self.bias, prec=prec, out_dtype=torch.float32)

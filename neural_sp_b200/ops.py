@@ -211,3 +211,68 @@ def conformer_conv(x, dw_weight, dw_bias, norm_mode, norm_w, norm_b, eps, run_me
                                      float(eps), ptr(y), d, B, T, d, k, int(causal), current_stream_ptr()),
           "nsp_conformer_conv_fwd")
     return y
+
+
+# ---------------------------------------------------------------------------------------------
+# small helpers, front-end
+# ---------------------------------------------------------------------------------------------
+def scale_(x, a):
+    _require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    check(lib.nsp_scale_inplace(ptr(x), float(a), x.numel(), current_stream_ptr()), "nsp_scale_inplace")
+    return x
+
+
+def colsum(x):
+    _require_cuda(x)
+    x = x.float().contiguous()
+    M, N = x.shape
+    y = torch.empty(N, dtype=torch.float32, device=x.device)
+    check(lib.nsp_colsum(ptr(x), ptr(y), M, N, current_stream_ptr()), "nsp_colsum")
+    return y
+
+
+def xl_pos_table(inv_freq, rows):
+    """[rows, d] TransformerXL sinusoid table, row r = relative distance r (nsp_xl_pos_table)."""
+    _require_cuda(inv_freq)
+    d = inv_freq.numel() * 2
+    tab = torch.empty(rows, d, dtype=torch.float32, device=inv_freq.device)
+    check(lib.nsp_xl_pos_table(ptr(inv_freq), ptr(tab), rows, d, current_stream_ptr()), "nsp_xl_pos_table")
+    return tab
+
+
+def conv3x3_relu(x, weight, bias, B, T, F, in_chmajor=False, relu=True, out_dtype=torch.float32):
+    """Channels-last 3x3 conv + bias + ReLU (nsp_conv3x3_relu_fwd). x holds B*T*F*CI elements."""
+    _require_cuda(x)
+    CO, CI = weight.shape[0], weight.shape[1]
+    assert weight.shape[2:] == (3, 3) and x.numel() == B * T * F * CI and x.is_contiguous()
+    y = torch.empty(B, T, F, CO, dtype=out_dtype, device=x.device)
+    check(lib.nsp_conv3x3_relu_fwd(int(x.dtype == torch.bfloat16), int(out_dtype == torch.bfloat16), ptr(x),
+                                   int(in_chmajor), ptr(weight), ptr(bias), ptr(y), B, T, F, CI, CO, int(relu),
+                                   current_stream_ptr()), "nsp_conv3x3_relu_fwd")
+    return y
+
+
+def maxpool2d(x, pool_t, pool_f, out_chmajor=False, out_dtype=None):
+    """ceil-mode max-pool on channels-last [B,T,F,C] (nsp_maxpool2d_fwd)."""
+    _require_cuda(x)
+    B, T, F, C = x.shape
+    To, Fo = -(-T // pool_t), -(-F // pool_f)
+    out_dtype = out_dtype or x.dtype
+    shape = (B, To, C * Fo) if out_chmajor else (B, To, Fo, C)
+    y = torch.empty(shape, dtype=out_dtype, device=x.device)
+    check(lib.nsp_maxpool2d_fwd(int(x.dtype == torch.bfloat16), int(out_dtype == torch.bfloat16), ptr(x), ptr(y),
+                                B, T, F, C, pool_t, pool_f, 0, int(out_chmajor), current_stream_ptr()),
+          "nsp_maxpool2d_fwd")
+    return y
+
+
+def maxpool_time(x, factor):
+    """MaxPoolSubsampler core on [B,T,D] (nsp_maxpool_time_fwd)."""
+    _require_cuda(x)
+    x = x.contiguous()
+    B, T, D = x.shape
+    y = torch.empty(B, -(-T // factor), D, dtype=x.dtype, device=x.device)
+    check(lib.nsp_maxpool_time_fwd(int(x.dtype == torch.bfloat16), ptr(x), ptr(y), B, T, D, factor,
+                                   current_stream_ptr()), "nsp_maxpool_time_fwd")
+    return y

@@ -1,0 +1,52 @@
+"""Shared helpers: rebuild encoders (ours and the oracle's cfg) from a golden fixture."""
+import json
+
+import numpy as np
+import torch
+
+
+def golden_cfg(g):
+    c = json.loads(str(g["cfg"]))
+    return c["args"], c["conv"], c["kind"]
+
+
+def oracle_cfg(g):
+    a, conv, kind = golden_cfg(g)
+    nl = a["n_layers"]
+    sub, la = [1] * nl, [0] * nl
+    for i, s in enumerate(a["subsample"].split("_")[:nl]):
+        sub[i] = int(s)
+    for i, s in enumerate(a["lookahead"].split("_")[:nl]):
+        la[i] = int(s)
+    cc = None
+    if conv:
+        pools = [tuple(int(v) for v in t.strip("()").split(",")) for t in conv["poolings"].split("_")]
+        cc = dict(in_channel=conv["in_channel"], poolings=pools)
+    return dict(kind=kind, n_layers=nl, n_heads=a["n_heads"], d_model=a["d_model"], pe_type=a["pe_type"],
+                clamp_len=a["clamp_len"], layer_norm_eps=a["layer_norm_eps"],
+                normalization=a.get("normalization", "layer_norm"), causal="uni" in a["enc_type"], lookaheads=la,
+                subsample=sub, dropout_layer=a["dropout_layer"], conv=cc, ffn_activation=a["ffn_activation"],
+                n_layers_sub1=a["n_layers_sub1"])
+
+
+def state_dict_of(g):
+    return {k[3:]: torch.from_numpy(np.asarray(g[k])) for k in g.files if k.startswith("sd.")}
+
+
+def build_ours(g, device, precision):
+    """Instantiate neural_sp_b200's encoder with the fixture's constructor args and load the reference weights."""
+    from neural_sp_b200.encoders.conformer import ConformerEncoder
+    from neural_sp_b200.encoders.conv import ConvEncoder
+    from neural_sp_b200.encoders.transformer import TransformerEncoder
+    a, conv, kind = golden_cfg(g)
+    a = dict(a)
+    a["frontend_conv"] = ConvEncoder(**conv) if conv else None
+    if kind == "conformer":
+        enc = ConformerEncoder(**a)
+    else:
+        a.pop("kernel_size"), a.pop("normalization")
+        enc = TransformerEncoder(**a)
+    missing, unexpected = enc.load_state_dict(state_dict_of(g), strict=True)
+    enc = enc.to(device).eval()
+    enc.set_precision(precision)
+    return enc

@@ -32,3 +32,49 @@ def test_ctc_oracle_zero_infinity():
     nll, loss, grad = ctc_oracle.ctc_nll_and_grad(g["logits"], ys, g["elens"])
     assert nll[1] == 0.0 and nll[2] == 0.0 and nll[0] > 0       # T < L (+repeats) -> zeroed
     assert np.all(grad[1] == 0) and np.all(grad[2] == 0)
+
+
+ENC_CASES = sorted(os.path.basename(f) for f in glob.glob(os.path.join(GOLDEN, "enc_*.npz")))
+
+
+@pytest.mark.parametrize("name", ENC_CASES)
+def test_encoder_oracle_matches_reference(name):
+    import torch
+    from enc_util import oracle_cfg
+    from oracle import encoder_oracle
+    g = load_golden(name)
+    sd = {k[3:]: g[k] for k in g.files if k.startswith("sd.")}
+    out = encoder_oracle.encoder_forward(sd, torch.from_numpy(g["xs"]), g["xlens"].tolist(), oracle_cfg(g), return_layers=True)
+    assert out["xlens"] == g["xlens_out"].tolist()
+    ref = g["ys"]
+    assert np.abs(out["xs"].numpy() - ref).max() <= 1e-5 * np.abs(ref).max()
+    for i, a in enumerate(out["layers"]):
+        r = g["act.%d" % i]
+        assert np.abs(a.numpy() - r).max() <= 1e-5 * np.abs(r).max(), i
+    if "ys_sub1" in g.files:
+        assert np.abs(out["sub1"].numpy() - g["ys_sub1"]).max() <= 1e-5 * np.abs(g["ys_sub1"]).max()
+
+
+def test_encoder_state_dict_contract_cpu():
+    """Our encoder classes expose exactly the reference's state_dict keys and shapes (no GPU needed)."""
+    import torch
+    from enc_util import golden_cfg, state_dict_of
+    from neural_sp_b200.encoders.conformer import ConformerEncoder
+    from neural_sp_b200.encoders.conv import ConvEncoder
+    from neural_sp_b200.encoders.transformer import TransformerEncoder
+    for name in ENC_CASES:
+        g = load_golden(name)
+        a, conv, kind = golden_cfg(g)
+        a = dict(a)
+        a["frontend_conv"] = ConvEncoder(**conv) if conv else None
+        if kind == "conformer":
+            enc = ConformerEncoder(**a)
+        else:
+            a.pop("kernel_size"), a.pop("normalization")
+            enc = TransformerEncoder(**a)
+        ref = state_dict_of(g)
+        mine = enc.state_dict()
+        assert set(mine) == set(ref), (name, set(mine) ^ set(ref))
+        for k in ref:
+            assert tuple(mine[k].shape) == tuple(ref[k].shape), (name, k)
+        enc.load_state_dict(ref, strict=True)
