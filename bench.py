@@ -1,0 +1,362 @@
+#!/usr/bin/env python3
+"""Benchmark of the hot path:  speech frames/sec through Conformer-L + CTC on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port) on host cores
+
+One "step" = one pass of the hot path over one batch of synthetic 80-dim log-mel input:
+encoder forward (conv front-end -> 17 Conformer blocks) -> CTC head -> fused CTC forward+backward
+(loss and d loss/d logits) -> head backward (d loss/d eouts, head weight grads) -> NCCL all-reduce of the
+gradients that exist (N > 1).  The encoder backward is not on the CUDA path yet and is NOT counted
+(config.step says so).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[2] per-GPU slice: Conformer-L 17L d512 ff2048 H8 k15 LN, relative clamp 10,
+    # conv 32_32 poolings (1,1)_(2,2), hierarchical max-pool x2 at layers 4 and 8 (…_large.yaml + enc_n_layers 17)
+    "conformer_l_ctc": dict(n_layers=17, d_model=512, d_ff=2048, n_heads=8, kernel_size=15, B=32, T=1000, vocab=10000,
+                            subsample="1_1_1_2_1_1_1_2_1_1_1_1_1_1_1_1_1", poolings="(1,1)_(2,2)"),
+    # BASELINE.json configs[1]: Conformer-M 12L d256 ff1024 H4
+    "conformer_m_ctc": dict(n_layers=12, d_model=256, d_ff=1024, n_heads=4, kernel_size=15, B=32, T=1000, vocab=10000,
+                            subsample="1_1_1_2_1_1_1_2_1_1_1_1", poolings="(1,1)_(2,2)"),
+}
+
+
+def enc_args(w):
+    return dict(input_dim=80, enc_type='conv_conformer', n_heads=w["n_heads"], kernel_size=w["kernel_size"],
+                normalization='layer_norm', n_layers=w["n_layers"], n_layers_sub1=0, n_layers_sub2=0,
+                d_model=w["d_model"], d_ff=w["d_ff"], ffn_bottleneck_dim=0, ffn_activation='swish', pe_type='relative',
+                layer_norm_eps=1e-12, last_proj_dim=0, dropout_in=0.0, dropout=0.0, dropout_att=0.0, dropout_layer=0.0,
+                subsample=w["subsample"], subsample_type='max_pool', n_stacks=1, n_splices=1, frontend_conv=None,
+                task_specific_layer=False, param_init='xavier_uniform', clamp_len=10,
+                lookahead="_".join(["0"] * w["n_layers"]), chunk_size_left="0", chunk_size_current="0",
+                chunk_size_right="0", streaming_type='mask')
+
+
+def conv_args(w):
+    return dict(input_dim=80, in_channel=1, channels="32_32", kernel_sizes="(3,3)_(3,3)", strides="(1,1)_(1,1)",
+                poolings=w["poolings"], dropout=0.0, normalization='', residual=False, bottleneck_dim=w["d_model"],
+                param_init=0.1)
+
+
+def synth_batch(w, B, seed):
+    """xs ~ N(0,1) fp32 [B,T,80]; fixed T; labels ylen = floor(0.45*T/8), ids uniform in [4, V)."""
+    rng = np.random.default_rng(seed)
+    T = w["T"]
+    xs = rng.standard_normal((B, T, 80)).astype(np.float32)
+    xlens = [T] * B
+    ylen = int(0.45 * T / 8)
+    ys = [rng.integers(4, w["vocab"], size=ylen).tolist() for _ in range(B)]
+    return xs, xlens, ys
+
+
+def flops_per_utt_fwd(w):
+    """Algorithmic encoder-forward FLOPs per utterance (SURVEY.md 8d formulas)."""
+    d, dff, k, T = w["d_model"], w["d_ff"], w["kernel_size"], w["T"]
+    pools = [tuple(int(v) for v in t.strip("()").split(",")) for t in w["poolings"].split("_")]
+    # front-end: block1 at full rate on 80 bins, block2 at rate 1/p_t on 80/p_f bins
+    fe = T * 2 * 9 * 80 * (1 * 32 + 32 * 32) + (T // pools[0][0]) * 2 * 9 * (80 // pools[0][1]) * (32 * 32 + 32 * 32)
+    Tp = T // (pools[0][0] * pools[1][0])
+    Fp = 80 // (pools[0][1] * pools[1][1])
+    total = fe + 2 * Tp * (32 * Fp) * d
+    for f in [int(s) for s in w["subsample"].split("_")]:
+        total += Tp * (8 * d * dff + 14 * d * d + 2 * d * k) + 6 * Tp * Tp * d
+        if f > 1:
+            Tp = -(-Tp // f)
+    total += 2 * Tp * (d * 512 + 512 * w["vocab"])      # CTC head fc "512"
+    return total, Tp
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thr = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thr.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [v for v in sm if v > 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_arm(w, steps, warmup, sample_B=2):
+    """The reference's CPU path, restated (oracle/): encoder forward + CTC forward/backward on the host cores."""
+    import torch
+    from oracle import encoder_oracle, ctc_oracle  # noqa: F401  (checker / baseline only)
+    from neural_sp_b200.encoders.conformer import ConformerEncoder
+    from neural_sp_b200.encoders.conv import ConvEncoder
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    a = enc_args(w)
+    a["frontend_conv"] = ConvEncoder(**conv_args(w))
+    enc = ConformerEncoder(**a)                      # parameter container only (random init); arithmetic = oracle
+    sd = {k: v.detach().float() for k, v in enc.state_dict().items()}
+    D, V = w["d_model"], w["vocab"]
+    W0, b0 = torch.randn(512, D) / D ** 0.5, torch.zeros(512)
+    W1, b1 = torch.randn(V, 512) / 512 ** 0.5, torch.zeros(V)
+    nl = w["n_layers"]
+    cfg = dict(kind="conformer", n_layers=nl, n_heads=w["n_heads"], d_model=D, pe_type="relative", clamp_len=10,
+               layer_norm_eps=1e-12, normalization="layer_norm", causal=False, lookaheads=[0] * nl,
+               subsample=[int(s) for s in w["subsample"].split("_")], dropout_layer=0.0,
+               conv=dict(in_channel=1, poolings=[tuple(int(v) for v in t.strip("()").split(",")) for t in w["poolings"].split("_")]),
+               ffn_activation="swish", n_layers_sub1=0)
+    xs, xlens, ys = synth_batch(w, sample_B, 1234)
+    xs_t = torch.from_numpy(xs)
+    ys_cat = torch.tensor([v for y in ys for v in y], dtype=torch.int32)
+    ylens = torch.tensor([len(y) for y in ys], dtype=torch.int32)
+
+    def step():
+        with torch.no_grad():
+            out = encoder_oracle.encoder_forward(sd, xs_t, xlens, cfg)
+        e = out["xs"].requires_grad_(True)
+        logits = torch.nn.functional.linear(torch.nn.functional.linear(e, W0, b0), W1, b1)
+        elens = torch.tensor(out["xlens"], dtype=torch.int32)
+        # reference CTC.forward arithmetic (ctc.py:124-129): log_softmax -> CTCLoss(sum, zero_infinity)/B + lsm KL
+        lp = logits.log_softmax(-1)
+        loss = torch.nn.functional.ctc_loss(lp.transpose(0, 1), ys_cat, elens, ylens, reduction="sum", zero_infinity=True) / sample_B
+        mask = (torch.arange(lp.size(1))[None, :] < elens[:, None]).unsqueeze(-1)
+        kl = (lp.exp() * (lp - float(np.log(1.0 / (V - 1)))) * mask).sum() / float(elens.sum())
+        (loss * 0.9 + kl * 0.1).backward()
+        return float(loss)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    frames = sum(xlens)
+    return dict(value=frames / dt, ms_per_step=dt * 1e3, cores=cores, sample="B=%d T=%d of workload, %d steps" % (sample_B, w["T"], steps))
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="conformer_l_ctc", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg_common = {"workload": "%s: Conformer %dL d%d ff%d H%d k15 LN rel-pos clamp10, conv 32_32 %s, hier. max-pool, "
+                              "CTC fc512 V=%d lsm0.1; B=%d/GPU T=%d fixed" % (args.workload, w["n_layers"], w["d_model"], w["d_ff"],
+                                                                            w["n_heads"], w["poolings"], w["vocab"], w["B"], w["T"]),
+                  "step": "encoder_fwd + ctc_head + ctc_fwd_bwd + head_bwd (encoder backward not built yet)",
+                  "global_batch": w["B"] * world, "seq_len": w["T"], "parallelism": "dp%d" % world}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+        r = cpu_reference_arm(w, steps, warmup)
+        line = {"impl": "reference", "metric": "speech_frames_per_sec", "value": r["value"], "unit": "frames/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": cfg_common,
+                "cpu_baseline": {"value": r["value"], "unit": "frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from neural_sp_b200 import ops
+    from neural_sp_b200.decoders.ctc import CTC
+    from neural_sp_b200.encoders.conformer import ConformerEncoder
+    from neural_sp_b200.encoders.conv import ConvEncoder
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the product path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    torch.manual_seed(0)
+    a = enc_args(w)
+    a["frontend_conv"] = ConvEncoder(**conv_args(w))
+    enc = ConformerEncoder(**a).to(dev).eval()
+    enc.set_precision(args.precision)
+    ctc = CTC(eos=2, blank=0, enc_n_units=w["d_model"], vocab=w["vocab"], lsm_prob=0.1, fc_list="512").to(dev)
+    ctc.train()
+    for m in ctc.modules():
+        m.precision = args.precision
+    head_params = [p for p in ctc.parameters()]
+
+    B = w["B"]
+    xs_np, xlens, ys = synth_batch(w, B, 1234 + rank)
+    xs_host = torch.from_numpy(xs_np).pin_memory()
+    xs_dev = xs_host.to(dev)
+    xlens_t = torch.IntTensor(xlens)
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+    frames_per_step = sum(xlens)
+
+    def step(x_dev):
+        out = enc(x_dev, xlens_t.clone(), task='ys')
+        eouts = out['ys']['xs'].detach().requires_grad_(True)
+        for p in head_params:
+            p.grad = None
+        loss, _ = ctc(eouts, out['ys']['xlens'], ys)
+        loss.backward()
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in head_params] + [eouts.grad.reshape(-1)[:0]])
+            dist.all_reduce(flat)          # the single gradient all-reduce of the step (sum; DDP semantics)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def timed(fn, steps):
+        evs = []
+        for _ in range(steps):
+            l2_flush.zero_()                                 # L2 flush between timed iterations (outside the timed pairs)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        return sum(s.elapsed_time(e) for s, e in evs) / steps
+
+    # ---- warm-up ----
+    for _ in range(max(3, args.warmup)):
+        step(xs_dev)
+    barrier()
+
+    # ---- device-resident timing (value) ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ops.LAUNCHES
+    barrier()
+    ms_dev = timed(lambda: step(xs_dev), args.steps)
+    barrier()
+    launches = ops.LAUNCHES - l0
+
+    # ---- end-to-end timing through the public API with host buffers (e2e) ----
+    def step_e2e():
+        x = xs_host.to(dev, non_blocking=True)
+        loss = step(x)
+        loss_host.copy_(loss.detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    ms_e2e = timed(step_e2e, args.steps)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-kernel-class timing for the roofline (eager, CUDA events around every library call) ----
+    ops.profile_start()
+    nprof = 3
+    for _ in range(nprof):
+        step(xs_dev)
+    prof = ops.profile_stop()
+
+    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        peak_src = "measured (MEASURED_PEAKS.json, sustained bf16)" if peaks else "fallback (B200_PROFILING.md)"
+        total_ms = sum(v["ms"] for v in prof.values()) or 1.0
+        dom = max(prof.items(), key=lambda kv: kv[1]["ms"])
+        gk = "gemm_%s" % args.precision
+        g = prof.get(gk, {"ms": 0.0, "flops": 0.0, "calls": 1})
+        gemm_tflops = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
+        roofline = {"kernel": "gemm_tcgen05 (%s)" % gk, "bound": "tensor", "achieved": gemm_tflops, "peak": tf_peak,
+                    "unit": "TFLOP/s", "frac": gemm_tflops / tf_peak, "traffic": None, "peak_source": peak_src,
+                    "share_of_step": g["ms"] / total_ms, "launches_per_step": g["calls"] / nprof,
+                    "dominant_by_time": dom[0]}
+        c = prof.get("ctc_loss", {"ms": 0.0, "bytes": 0.0, "calls": 1})
+        ctc_ms = c["ms"] / max(1, c["calls"])
+        ctc_gbs = c["bytes"] / (c["ms"] * 1e-3) / 1e9 if c["ms"] > 0 else 0.0
+        roofline_ctc = {"kernel": "ctc_loss fwd+bwd (3 launches)", "bound": "hbm", "achieved": ctc_gbs, "peak": hbm_peak,
+                        "unit": "GB/s", "frac": ctc_gbs / hbm_peak, "traffic": None, "ms_per_batch": ctc_ms}
+        fl_utt, Tp = flops_per_utt_fwd(w)
+        value = frames_per_step * world / (ms_dev * 1e-3)
+        e2e = frames_per_step * world / (ms_e2e * 1e-3)
+        line = {"metric": "speech_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_dev, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+                "config": dict(cfg_common, l2="256 MiB memset between timed iterations (outside the event pairs); "
+                                             "per-step working set >> 126 MB L2",
+                               encoder_fwd_tflop_per_step=fl_utt * B / 1e12, enc_out_frames=Tp),
+                "clocks": clocks,
+                "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e,
+                        "h2d_bytes_per_step": int(xs_host.numel() * 4), "d2h_bytes_per_step": 4},
+                "gpu_launches": int(launches),
+                "roofline": roofline, "roofline_ctc": roofline_ctc, "ctc_loss_ms_per_batch": ctc_ms,
+                "kernel_time_ms_per_step": {k: round(v["ms"] / nprof, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}}
+        if not args.no_cpu_baseline and world == 1:
+            r = cpu_reference_arm(w, 1, 1)
+            line["cpu_baseline"] = {"value": r["value"], "unit": "frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

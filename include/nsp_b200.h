@@ -175,6 +175,20 @@ nsp_status nsp_maxpool2d_fwd(int in_bf16, int out_bf16, const void* x, void* y, 
                              int pool_t, int pool_f, int f_keep, int out_chmajor, void* stream);
 nsp_status nsp_maxpool_time_fwd(int is_bf16, const void* x, void* y, int B, int T, int D, int factor, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * RNN-Transducer loss, forward + backward (HBM-bound; fp32), blank-first lattice.
+ * Replaces  warp_rnnt.rnnt_loss(log_probs, labels, frames_lengths, labels_lengths, average_frames=False,
+ *           reduction='mean', gather=False)     decoders/rnn_transducer.py:248-252
+ *           (and warprnnt_pytorch.RNNTLoss, :254-256) including its gradient w.r.t. log_probs.
+ * log_probs fp32 [B, T, U1, V] dense (U1 = Umax + 1); labels int32 [B, U1-1]; flens, ylens int32 [B].
+ * nll fp32 [B]; loss fp32 [1] = mean_b nll_b; grad fp32 [B, T, U1, V] = d loss / d log_probs (may be NULL).
+ * ------------------------------------------------------------------------------------------ */
+size_t nsp_rnnt_loss_workspace_bytes(int B, int T, int U1);
+nsp_status nsp_rnnt_loss_fwd_bwd(const float* log_probs, int B, int T, int U1, int V,
+                                 const int32_t* labels, const int32_t* flens, const int32_t* ylens, int blank,
+                                 float* nll, float* loss, float* grad,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

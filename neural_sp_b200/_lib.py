@@ -101,3 +101,14 @@ for _name, (_res, _args) in _more.items():
     _fn.restype = _res
     _fn.argtypes = _args
 SIGNATURES.update(_more)
+
+_more = {
+    "nsp_rnnt_loss_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
+    "nsp_rnnt_loss_fwd_bwd": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp,
+                                      c_vp, c_sz, c_vp]),
+}
+for _name, (_res, _args) in _more.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+SIGNATURES.update(_more)

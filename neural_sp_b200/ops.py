@@ -9,6 +9,45 @@ from . import _lib
 from ._lib import lib, check, ptr, current_stream_ptr
 
 
+# ---- launch accounting / optional per-op CUDA-event profiling (used by bench.py) ----
+LAUNCHES = 0          # number of CUDA kernels this library launched (claimed count; see KERNELS_PER_CALL)
+PROFILE = None        # None, or dict name -> [list of (start_event, end_event)], flops, bytes
+KERNELS_PER_CALL = {"nsp_ctc_loss_fwd_bwd": 3, "nsp_ctc_forced_align": 2}
+
+
+def profile_start():
+    global PROFILE
+    PROFILE = {}
+
+
+def profile_stop():
+    """-> {name: dict(ms=total, calls=n, flops=sum, bytes=sum)}; synchronises."""
+    global PROFILE
+    prof, PROFILE = PROFILE, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, rec in (prof or {}).items():
+        ms = sum(a.elapsed_time(b) for a, b in rec["ev"])
+        out[name] = dict(ms=ms, calls=len(rec["ev"]), flops=rec["flops"], bytes=rec["bytes"])
+    return out
+
+
+def _run(name, fn, *args, flops=0, nbytes=0, tag=None):
+    global LAUNCHES
+    LAUNCHES += KERNELS_PER_CALL.get(name, 1)
+    if PROFILE is None:
+        return check(fn(*args), name)
+    key = tag or name
+    rec = PROFILE.setdefault(key, {"ev": [], "flops": 0, "bytes": 0})
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    check(fn(*args), name)
+    b.record()
+    rec["ev"].append((a, b))
+    rec["flops"] += flops
+    rec["bytes"] += nbytes
+
+
 def _require_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -49,10 +88,10 @@ def ctc_loss_fwd_bwd(logits, labels, elens, ylens, blank=0, lsm_prob=0.0):
     nll = torch.empty(B, dtype=torch.float32, device=logits.device)
     loss = torch.empty((), dtype=torch.float32, device=logits.device)
     grad = torch.empty(B, T, V, dtype=torch.float32, device=logits.device)
-    check(lib.nsp_ctc_loss_fwd_bwd(ptr(logits), logits.stride(0), logits.stride(1), B, T, V,
+    _run("nsp_ctc_loss_fwd_bwd", lib.nsp_ctc_loss_fwd_bwd, ptr(logits), logits.stride(0), logits.stride(1), B, T, V,
                                    ptr(labels), Lmax, ptr(elens), ptr(ylens), int(blank), float(lsm_prob),
-                                   ptr(nll), ptr(loss), ptr(grad), ptr(ws), ws_bytes, current_stream_ptr()),
-          "nsp_ctc_loss_fwd_bwd")
+                                   ptr(nll), ptr(loss), ptr(grad), ptr(ws), ws_bytes, current_stream_ptr(),
+         nbytes=8.0 * B * T * V, tag="ctc_loss")
     return loss, nll, grad
 
 
@@ -66,9 +105,8 @@ def ctc_forced_align(logits, labels, elens, ylens, blank=0):
     ws_bytes = lib.nsp_ctc_align_workspace_bytes(B, T, Lmax)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=logits.device)
     trig = torch.empty(B, Lmax + 1, dtype=torch.int32, device=logits.device)
-    check(lib.nsp_ctc_forced_align(ptr(logits), B, T, V, ptr(labels), Lmax, ptr(elens), ptr(ylens), int(blank),
-                                   ptr(trig), ptr(ws), ws_bytes, current_stream_ptr()),
-          "nsp_ctc_forced_align")
+    _run("nsp_ctc_forced_align", lib.nsp_ctc_forced_align, ptr(logits), B, T, V, ptr(labels), Lmax, ptr(elens), ptr(ylens), int(blank),
+                                   ptr(trig), ptr(ws), ws_bytes, current_stream_ptr())
     return trig
 
 
@@ -84,7 +122,7 @@ def split_tf32(x):
     _require_cuda(x)
     x = x.contiguous()
     hi, lo = torch.empty_like(x), torch.empty_like(x)
-    check(lib.nsp_split_tf32(ptr(x), ptr(hi), ptr(lo), x.numel(), current_stream_ptr()), "nsp_split_tf32")
+    _run("nsp_split_tf32", lib.nsp_split_tf32, ptr(x), ptr(hi), ptr(lo), x.numel(), current_stream_ptr())
     return hi, lo
 
 
@@ -95,12 +133,23 @@ def to_bf16(x):
     _require_cuda(x)
     x = x.contiguous()
     y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-    check(lib.nsp_cast_f32_to_bf16(ptr(x), ptr(y), x.numel(), current_stream_ptr()), "nsp_cast_f32_to_bf16")
+    _run("nsp_cast_f32_to_bf16", lib.nsp_cast_f32_to_bf16, ptr(x), ptr(y), x.numel(), current_stream_ptr())
     return y
 
 
+def _pad_k(t, mult=8):
+    """Zero-pad the last (K) dim to a multiple of `mult` elements: TMA needs 16-byte row pitches."""
+    K = t.shape[-1]
+    Kp = -(-K // mult) * mult
+    if Kp == K:
+        return t
+    return torch.nn.functional.pad(t, (0, Kp - K))
+
+
 def prepare_weight(w, prec):
-    """Operand form of a [N, K] weight for the given precision: bf16 copy, fp32, or (hi, lo) split."""
+    """Operand form of a [N, K] weight for the given precision: bf16 copy, fp32, or (hi, lo) split.
+    K is zero-padded to a multiple of 8 so that every row pitch is a 16-byte multiple."""
+    w = _pad_k(w.detach())
     if prec == "bf16":
         return (to_bf16(w.detach()),)
     if prec == "tf32":
@@ -124,6 +173,10 @@ def linear(x, w_prepared, bias=None, prec="bf16", act=None, glu=False, residual=
     M = x2.shape[0]
     w = w_prepared[0]
     N = w.shape[0]
+    if w.shape[1] != K:                      # weight K was padded at prepare time
+        x2 = _pad_k(x2)
+        K = x2.shape[1]
+        assert K == w.shape[1], (K, w.shape)
     nout = N // 2 if glu else N
     x_lo = None
     if prec == "bf16":
@@ -138,12 +191,12 @@ def linear(x, w_prepared, bias=None, prec="bf16", act=None, glu=False, residual=
     out2d = out.reshape(-1, nout)
     res2d = residual.reshape(-1, nout) if residual is not None else None
     out2 = torch.empty(M, nout, dtype=torch.bfloat16, device=x.device) if out2_bf16 else None
-    check(lib.nsp_linear_fwd(PREC[prec], ptr(x2), ptr(x_lo), x2.stride(0), ptr(w), ptr(w_lo), w.stride(0),
-                             M, N, K, int(glu), ACT[act], ptr(bias), ptr(res2d),
-                             res2d.stride(0) if res2d is not None else 0, float(alpha),
-                             ptr(out2d), out2d.stride(0), int(out2d.dtype == torch.bfloat16),
-                             ptr(out2), out2.stride(0) if out2 is not None else 0, current_stream_ptr()),
-          "nsp_linear_fwd")
+    _run("nsp_linear_fwd", lib.nsp_linear_fwd, PREC[prec], ptr(x2), ptr(x_lo), x2.stride(0), ptr(w), ptr(w_lo), w.stride(0),
+         M, N, K, int(glu), ACT[act], ptr(bias), ptr(res2d),
+         res2d.stride(0) if res2d is not None else 0, float(alpha),
+         ptr(out2d), out2d.stride(0), int(out2d.dtype == torch.bfloat16),
+         ptr(out2), out2.stride(0) if out2 is not None else 0, current_stream_ptr(),
+         flops=2.0 * M * N * K, tag="gemm_%s" % prec)
     res = out2d.reshape(*lead, nout)
     if out2_bf16:
         return res, out2.reshape(*lead, nout)
@@ -163,8 +216,8 @@ def layernorm(x, weight, bias, eps, out_fp32=True, out_bf16=False, in_scale=1.0)
     M = x2.shape[0]
     y = torch.empty(M, D, dtype=torch.float32, device=x.device) if out_fp32 else None
     yb = torch.empty(M, D, dtype=torch.bfloat16, device=x.device) if out_bf16 else None
-    check(lib.nsp_layernorm_fwd(ptr(x2), x2.stride(0), ptr(weight), ptr(bias), float(eps), float(in_scale),
-                                ptr(y), D, ptr(yb), D, M, D, current_stream_ptr()), "nsp_layernorm_fwd")
+    _run("nsp_layernorm_fwd", lib.nsp_layernorm_fwd, ptr(x2), x2.stride(0), ptr(weight), ptr(bias), float(eps), float(in_scale),
+                                ptr(y), D, ptr(yb), D, M, D, current_stream_ptr())
     outs = tuple(t.reshape(x.shape) for t in (y, yb) if t is not None)
     return outs[0] if len(outs) == 1 else outs
 
@@ -187,11 +240,11 @@ def relpos_attention(q, k, v, klens, n_heads, r=None, u_bias=None, v_bias=None, 
         assert r.dtype == q.dtype and r.stride(-1) == 1
         r = r.reshape(-1, D) if r.dim() == 3 else r
     out = torch.empty(B, Tq, D, dtype=q.dtype, device=q.device)
-    check(lib.nsp_relpos_attention_fwd(int(is_bf16), ptr(q), q.stride(1), ptr(k), k.stride(1), ptr(v), v.stride(1),
+    _run("nsp_relpos_attention_fwd", lib.nsp_relpos_attention_fwd, int(is_bf16), ptr(q), q.stride(1), ptr(k), k.stride(1), ptr(v), v.stride(1),
                                        ptr(r), r.stride(0) if r is not None else 0, r.shape[0] if r is not None else 0,
                                        ptr(u_bias), ptr(v_bias), ptr(klens), ptr(out), D, B, n_heads, Tq, Tk, dk,
                                        int(clamp_len), int(causal), int(lookahead), int(chunk_c), int(chunk_l),
-                                       current_stream_ptr()), "nsp_relpos_attention_fwd")
+                                       current_stream_ptr())
     return out
 
 
@@ -206,10 +259,9 @@ def conformer_conv(x, dw_weight, dw_bias, norm_mode, norm_w, norm_b, eps, run_me
     k = dw_weight.shape[-1]
     w = dw_weight.reshape(d, k)
     y = torch.empty(B, T, d, dtype=x.dtype, device=x.device)
-    check(lib.nsp_conformer_conv_fwd(int(x.dtype == torch.bfloat16), ptr(x), x.stride(1), ptr(w), ptr(dw_bias),
+    _run("nsp_conformer_conv_fwd", lib.nsp_conformer_conv_fwd, int(x.dtype == torch.bfloat16), ptr(x), x.stride(1), ptr(w), ptr(dw_bias),
                                      NORM_MODE[norm_mode], ptr(norm_w), ptr(norm_b), ptr(run_mean), ptr(run_var),
-                                     float(eps), ptr(y), d, B, T, d, k, int(causal), current_stream_ptr()),
-          "nsp_conformer_conv_fwd")
+                                     float(eps), ptr(y), d, B, T, d, k, int(causal), current_stream_ptr())
     return y
 
 
@@ -219,7 +271,7 @@ def conformer_conv(x, dw_weight, dw_bias, norm_mode, norm_w, norm_b, eps, run_me
 def scale_(x, a):
     _require_cuda(x)
     assert x.dtype == torch.float32 and x.is_contiguous()
-    check(lib.nsp_scale_inplace(ptr(x), float(a), x.numel(), current_stream_ptr()), "nsp_scale_inplace")
+    _run("nsp_scale_inplace", lib.nsp_scale_inplace, ptr(x), float(a), x.numel(), current_stream_ptr())
     return x
 
 
@@ -228,7 +280,7 @@ def colsum(x):
     x = x.float().contiguous()
     M, N = x.shape
     y = torch.empty(N, dtype=torch.float32, device=x.device)
-    check(lib.nsp_colsum(ptr(x), ptr(y), M, N, current_stream_ptr()), "nsp_colsum")
+    _run("nsp_colsum", lib.nsp_colsum, ptr(x), ptr(y), M, N, current_stream_ptr())
     return y
 
 
@@ -237,7 +289,7 @@ def xl_pos_table(inv_freq, rows):
     _require_cuda(inv_freq)
     d = inv_freq.numel() * 2
     tab = torch.empty(rows, d, dtype=torch.float32, device=inv_freq.device)
-    check(lib.nsp_xl_pos_table(ptr(inv_freq), ptr(tab), rows, d, current_stream_ptr()), "nsp_xl_pos_table")
+    _run("nsp_xl_pos_table", lib.nsp_xl_pos_table, ptr(inv_freq), ptr(tab), rows, d, current_stream_ptr())
     return tab
 
 
@@ -247,9 +299,9 @@ def conv3x3_relu(x, weight, bias, B, T, F, in_chmajor=False, relu=True, out_dtyp
     CO, CI = weight.shape[0], weight.shape[1]
     assert weight.shape[2:] == (3, 3) and x.numel() == B * T * F * CI and x.is_contiguous()
     y = torch.empty(B, T, F, CO, dtype=out_dtype, device=x.device)
-    check(lib.nsp_conv3x3_relu_fwd(int(x.dtype == torch.bfloat16), int(out_dtype == torch.bfloat16), ptr(x),
+    _run("nsp_conv3x3_relu_fwd", lib.nsp_conv3x3_relu_fwd, int(x.dtype == torch.bfloat16), int(out_dtype == torch.bfloat16), ptr(x),
                                    int(in_chmajor), ptr(weight), ptr(bias), ptr(y), B, T, F, CI, CO, int(relu),
-                                   current_stream_ptr()), "nsp_conv3x3_relu_fwd")
+                                   current_stream_ptr())
     return y
 
 
@@ -261,9 +313,8 @@ def maxpool2d(x, pool_t, pool_f, out_chmajor=False, out_dtype=None):
     out_dtype = out_dtype or x.dtype
     shape = (B, To, C * Fo) if out_chmajor else (B, To, Fo, C)
     y = torch.empty(shape, dtype=out_dtype, device=x.device)
-    check(lib.nsp_maxpool2d_fwd(int(x.dtype == torch.bfloat16), int(out_dtype == torch.bfloat16), ptr(x), ptr(y),
-                                B, T, F, C, pool_t, pool_f, 0, int(out_chmajor), current_stream_ptr()),
-          "nsp_maxpool2d_fwd")
+    _run("nsp_maxpool2d_fwd", lib.nsp_maxpool2d_fwd, int(x.dtype == torch.bfloat16), int(out_dtype == torch.bfloat16), ptr(x), ptr(y),
+                                B, T, F, C, pool_t, pool_f, 0, int(out_chmajor), current_stream_ptr())
     return y
 
 
@@ -273,6 +324,31 @@ def maxpool_time(x, factor):
     x = x.contiguous()
     B, T, D = x.shape
     y = torch.empty(B, -(-T // factor), D, dtype=x.dtype, device=x.device)
-    check(lib.nsp_maxpool_time_fwd(int(x.dtype == torch.bfloat16), ptr(x), ptr(y), B, T, D, factor,
-                                   current_stream_ptr()), "nsp_maxpool_time_fwd")
+    _run("nsp_maxpool_time_fwd", lib.nsp_maxpool_time_fwd, int(x.dtype == torch.bfloat16), ptr(x), ptr(y), B, T, D, factor,
+                                   current_stream_ptr())
     return y
+
+
+# ---------------------------------------------------------------------------------------------
+# RNN-T
+# ---------------------------------------------------------------------------------------------
+KERNELS_PER_CALL["nsp_rnnt_loss_fwd_bwd"] = 4
+
+
+def rnnt_loss_fwd_bwd(log_probs, labels, flens, ylens, blank=0, need_grad=True):
+    """RNN-T loss + d loss/d log_probs (nsp_rnnt_loss_fwd_bwd).  log_probs fp32 `[B,T,U+1,V]` CUDA,
+    labels int32 `[B,U]`, flens/ylens int32 `[B]`.  Returns (loss 0-dim mean, nll [B], grad or None)."""
+    _require_cuda(log_probs, labels, flens, ylens)
+    log_probs = log_probs.contiguous()
+    assert log_probs.dtype == torch.float32 and log_probs.dim() == 4
+    B, T, U1, V = log_probs.shape
+    assert labels.shape == (B, U1 - 1) and labels.is_contiguous()
+    ws_bytes = lib.nsp_rnnt_loss_workspace_bytes(B, T, U1)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=log_probs.device)
+    nll = torch.empty(B, dtype=torch.float32, device=log_probs.device)
+    loss = torch.empty((), dtype=torch.float32, device=log_probs.device)
+    grad = torch.empty_like(log_probs) if need_grad else None
+    _run("nsp_rnnt_loss_fwd_bwd", lib.nsp_rnnt_loss_fwd_bwd, ptr(log_probs), B, T, U1, V, ptr(labels), ptr(flens),
+         ptr(ylens), int(blank), ptr(nll), ptr(loss), ptr(grad), ptr(ws), ws_bytes, current_stream_ptr(),
+         nbytes=8.0 * B * T * U1 * V, tag="rnnt_loss")
+    return loss, nll, grad

@@ -78,3 +78,14 @@ def test_encoder_state_dict_contract_cpu():
         for k in ref:
             assert tuple(mine[k].shape) == tuple(ref[k].shape), (name, k)
         enc.load_state_dict(ref, strict=True)
+
+
+@pytest.mark.parametrize("name", ["rnnt_small.npz", "rnnt_mid.npz"])
+def test_rnnt_oracle_matches_torchaudio_golden(name):
+    import torch
+    from oracle import rnnt_oracle
+    g = load_golden(name)
+    lp = torch.from_numpy(g["logits"]).log_softmax(-1).numpy()
+    nll, loss, grad = rnnt_oracle.rnnt_nll_and_grad(lp, g["ys"], g["flens"], g["ylens"])
+    np.testing.assert_allclose(nll, g["nll"], rtol=1e-5)
+    np.testing.assert_allclose(grad, g["grad_log_probs"], atol=1e-4, rtol=0)   # torchaudio is fp32
