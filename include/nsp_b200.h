@@ -189,6 +189,13 @@ nsp_status nsp_rnnt_loss_fwd_bwd(const float* log_probs, int B, int T, int U1, i
                                  float* nll, float* loss, float* grad,
                                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* 3x3 conv, C_in = C_out = 32, as an implicit GEMM on tcgen05 (bf16 in/out, fp32 accumulate), fused bias + ReLU
+ * and optional fused 2x2 ceil-mode max-pool.  Replaces nn.Conv2d(32,32,3,pad 1)+ReLU(+MaxPool2d) of
+ * Conv2dBlock.forward encoders/conv.py:362-394.  x bf16 [B,T,F,32]; w_taps bf16 [32, 288] with column
+ * (ky*3+kx)*32 + ci; y bf16 [B,T,F,32] or [B,ceil(T/2),ceil(F/2),32] when pool2x2. */
+nsp_status nsp_conv3x3_c32_tc_fwd(const void* x, const void* w_taps, const float* bias, void* y,
+                                  int B, int T, int F, int relu, int pool2x2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

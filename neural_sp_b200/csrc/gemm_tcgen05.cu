@@ -36,6 +36,8 @@ static bool get_encode_fn(void** fn) {
     return true;
 }
 
+bool get_tma_encode(void** fn) { return get_encode_fn(fn); }
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

@@ -85,6 +85,12 @@ class CTC(nn.Module):
             self.output = Linear(enc_n_units, vocab)
         self.forced_aligner = CTCForcedAligner(blank)
 
+    def set_precision(self, precision):
+        """'bf16' | 'tf32' | 'fp32' arithmetic of the output head's GEMMs (the loss itself is always fp32)."""
+        for m in self.modules():
+            m.precision = precision
+        return self
+
     def forward(self, eouts, elens, ys, forced_align=False):
         """Compute CTC loss.
 

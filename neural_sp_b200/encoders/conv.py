@@ -69,18 +69,28 @@ class Conv2dBlock(EncoderBase):
             raise NotImplementedError("CNN lookback/lookahead trimming (streaming) is a 'next' row")
         if self.training and self.dropout.p > 0:
             raise NotImplementedError("dropout > 0 in training mode is not on the B200 path yet")
-        adt = act_dtype(get_precision(self))
-        res_in = xs
-        xs = ops.conv3x3_relu(xs, self.conv1.weight, self.conv1.bias, B, T, F, in_chmajor=first, out_dtype=adt)
+        prec = get_precision(self)
+        adt = act_dtype(prec)
         if self.residual and self.conv1.in_channels == self.conv2.out_channels:
             raise NotImplementedError("residual CNN blocks are not on the B200 path")
-        xs = ops.conv3x3_relu(xs, self.conv2.weight, self.conv2.bias, B, T, F, out_dtype=adt)
+        pt, pf = self.pooling if self.pool is not None else (1, 1)
+
+        def conv(layer, name, x, first_layer, fuse_pool):
+            ci, co = layer.in_channels, layer.out_channels
+            if prec == "bf16" and ci == 32 and co == 32 and x.dtype == torch.bfloat16:
+                wt = prepared(self, name + ".taps", "bf16", (layer.weight,),
+                              build=lambda w: w.permute(0, 2, 3, 1).reshape(32, 288))[0][:, :288].contiguous()
+                return ops.conv3x3_c32_tc(x.view(B, T, F, 32), wt, layer.bias, relu=True, pool2x2=fuse_pool), fuse_pool
+            return ops.conv3x3_relu(x, layer.weight, layer.bias, B, T, F, in_chmajor=first_layer, out_dtype=adt), False
+
+        xs, _ = conv(self.conv1, "conv1", xs, first, False)
+        xs, pooled = conv(self.conv2, "conv2", xs, False, (pt, pf) == (2, 2) and not last_chmajor)
         xlens = torch.IntTensor([_conv_len(_conv_len(int(n), 1), 1) for n in xlens])
-        del res_in
         if self.pool is not None:
-            xs = ops.maxpool2d(xs, self.pooling[0], self.pooling[1], out_chmajor=last_chmajor)
-            xlens = torch.IntTensor([_pool_len(int(n), self.pooling[0]) for n in xlens])
-            T, F = -(-T // self.pooling[0]), -(-F // self.pooling[1])
+            if not pooled:
+                xs = ops.maxpool2d(xs, pt, pf, out_chmajor=last_chmajor)
+            xlens = torch.IntTensor([_pool_len(int(n), pt) for n in xlens])
+            T, F = -(-T // pt), -(-F // pf)
         elif last_chmajor:
             xs = ops.maxpool2d(xs, 1, 1, out_chmajor=True)
         return xs, xlens, T, F

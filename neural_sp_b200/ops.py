@@ -352,3 +352,16 @@ def rnnt_loss_fwd_bwd(log_probs, labels, flens, ylens, blank=0, need_grad=True):
          ptr(ylens), int(blank), ptr(nll), ptr(loss), ptr(grad), ptr(ws), ws_bytes, current_stream_ptr(),
          nbytes=8.0 * B * T * U1 * V, tag="rnnt_loss")
     return loss, nll, grad
+
+
+def conv3x3_c32_tc(x, w_taps, bias, relu=True, pool2x2=False):
+    """tcgen05 implicit-GEMM 3x3 conv for 32->32 channels (nsp_conv3x3_c32_tc_fwd).
+    x bf16 `[B,T,F,32]`, w_taps bf16 `[32,288]` (column = tap*32 + ci)."""
+    _require_cuda(x, w_taps)
+    B, T, F, C = x.shape
+    assert C == 32 and x.dtype == torch.bfloat16 and x.is_contiguous() and w_taps.shape == (32, 288)
+    To, Fo = (-(-T // 2), -(-F // 2)) if pool2x2 else (T, F)
+    y = torch.empty(B, To, Fo, 32, dtype=torch.bfloat16, device=x.device)
+    _run("nsp_conv3x3_c32_tc_fwd", lib.nsp_conv3x3_c32_tc_fwd, ptr(x), ptr(w_taps), ptr(bias), ptr(y), B, T, F,
+         int(relu), int(pool2x2), current_stream_ptr(), flops=2.0 * B * T * F * 32 * 288, tag="conv3x3_tc")
+    return y

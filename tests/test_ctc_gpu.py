@@ -79,6 +79,7 @@ def test_ctc_head_forward_matches_reference_golden():
     V = g["sd.output.fc1.weight"].shape[0]
     ctc = CTC(eos=2, blank=0, enc_n_units=D, vocab=V, lsm_prob=0.1, fc_list="16").to(dev)
     ctc.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")})
+    ctc.set_precision("fp32")          # parity mode: 3xTF32 GEMMs in the head (forward and backward)
     ctc.train()
     eouts = torch.from_numpy(g["eouts"]).to(dev).requires_grad_(True)
     ys = split_labels(g["ys_cat"], g["ylens"])

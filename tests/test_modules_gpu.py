@@ -124,3 +124,48 @@ def test_conformer_conv(d, k, T, mode, causal, dtype):
     tol = 3e-5 if dtype == torch.float32 else 2e-2
     err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
     assert err <= tol, err
+
+
+@pytest.mark.parametrize("B,T,F,pool", [(2, 64, 80, False), (3, 50, 80, True), (2, 37, 40, True), (1, 8, 16, False),
+                                        (2, 33, 21, True)])
+def test_conv3x3_tc_matches_fp32_conv(B, T, F, pool):
+    """tcgen05 implicit-GEMM conv vs F.conv2d (+max_pool2d ceil) on the same bf16-rounded operands."""
+    from neural_sp_b200 import ops
+    torch.manual_seed(T)
+    dev = "cuda"
+    x = torch.randn(B, T, F, 32, device=dev).bfloat16()
+    w = (torch.randn(32, 32, 3, 3, device=dev) / 17.0)
+    bias = torch.randn(32, device=dev) * 0.1
+    wt = w.permute(0, 2, 3, 1).reshape(32, 288).bfloat16().contiguous()
+    y = ops.conv3x3_c32_tc(x, wt, bias, relu=True, pool2x2=pool)
+    ref = F_conv_ref(x.float(), w.bfloat16().float(), bias, pool)
+    assert y.shape == ref.shape
+    err = (y.float() - ref).abs().max().item() / ref.abs().max().item()
+    assert err <= 1e-2, err
+
+
+def F_conv_ref(x_cl, w, bias, pool):
+    y = torch.relu(F.conv2d(x_cl.permute(0, 3, 1, 2).double(), w.double(), bias.double(), padding=1))
+    if pool:
+        y = F.max_pool2d(y, 2, 2, 0, ceil_mode=True)
+    return y.permute(0, 2, 3, 1).float()
+
+
+def test_frontend_simt_conv_pool_layouts():
+    """fp32 SIMT conv + pool kernels vs torch (channel-major input view and channel-major flatten output)."""
+    from neural_sp_b200 import ops
+    torch.manual_seed(1)
+    dev = "cuda"
+    B, T, Fq, CI, CO = 2, 21, 20, 3, 32
+    x = torch.randn(B, T, CI * Fq, device=dev)             # reference view: [B,T,CI,F]
+    w = torch.randn(CO, CI, 3, 3, device=dev) * 0.2
+    b = torch.randn(CO, device=dev) * 0.1
+    y = ops.conv3x3_relu(x, w, b, B, T, Fq, in_chmajor=True)
+    ref = torch.relu(F.conv2d(x.view(B, T, CI, Fq).transpose(1, 2), w, b, padding=1))     # [B,CO,T,F]
+    assert (y - ref.permute(0, 2, 3, 1)).abs().max().item() <= 1e-4
+    p = ops.maxpool2d(y, 2, 2, out_chmajor=True)
+    pref = F.max_pool2d(ref, 2, 2, 0, ceil_mode=True)
+    pref = pref.transpose(1, 2).reshape(B, pref.shape[2], -1)                             # conv.py:189 flatten
+    assert (p - pref).abs().max().item() <= 1e-4
+    pt = ops.maxpool_time(torch.randn(2, 9, 16, device=dev), 2)
+    assert pt.shape == (2, 5, 16)
