@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--workload", default="conformer_l_ctc", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a captured CUDA graph")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -275,6 +276,39 @@ def main():
     for _ in range(max(3, args.warmup)):
         step(xs_dev)
     barrier()
+    l_before = ops.LAUNCHES
+    step(xs_dev)
+    launches_per_step = ops.LAUNCHES - l_before
+
+    # ---- capture the step into a CUDA graph (launch-bound inner loop: ~300 kernels per step) ----
+    graph, loss_static = None, None
+    xs_static = xs_dev.clone()
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    step(xs_static)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                loss_static = step(xs_static)
+            graph.replay()
+            torch.cuda.synchronize()
+        except Exception as ex:                      # keep the eager path, say so in the JSON line
+            graph = None
+            graph_error = repr(ex)[:200]
+            torch.cuda.synchronize()
+    eager_step = step
+
+    def run_step(x_dev):
+        if graph is None:
+            return eager_step(x_dev)
+        if x_dev is not xs_static:
+            xs_static.copy_(x_dev, non_blocking=True)
+        graph.replay()
+        return loss_static
 
     # ---- device-resident timing (value) ----
     sampler = ClockSampler(local_rank)
@@ -282,14 +316,20 @@ def main():
         sampler.start()
     l0 = ops.LAUNCHES
     barrier()
-    ms_dev = timed(lambda: step(xs_dev), args.steps)
+    ms_dev = timed(lambda: run_step(xs_static), args.steps)
     barrier()
     launches = ops.LAUNCHES - l0
+    if graph is not None:
+        launches = launches_per_step * args.steps          # replays do not pass through the Python wrappers
 
     # ---- end-to-end timing through the public API with host buffers (e2e) ----
     def step_e2e():
-        x = xs_host.to(dev, non_blocking=True)
-        loss = step(x)
+        if graph is None:
+            loss = eager_step(xs_host.to(dev, non_blocking=True))
+        else:
+            xs_static.copy_(xs_host, non_blocking=True)      # H2D of this step's features (pinned -> device)
+            graph.replay()
+            loss = loss_static
         loss_host.copy_(loss.detach(), non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
@@ -343,7 +383,8 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
                 "config": dict(cfg_common, l2="256 MiB memset between timed iterations (outside the event pairs); "
                                              "per-step working set >> 126 MB L2",
-                               encoder_fwd_tflop_per_step=fl_utt * B / 1e12, enc_out_frames=Tp),
+                               encoder_fwd_tflop_per_step=fl_utt * B / 1e12, enc_out_frames=Tp,
+                               cuda_graph=graph is not None),
                 "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": int(xs_host.numel() * 4), "d2h_bytes_per_step": 4},

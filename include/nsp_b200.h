@@ -143,7 +143,7 @@ nsp_status nsp_relpos_attention_fwd(int is_bf16, const void* q, int64_t ldq, con
 /* ------------------------------------------------------------------------------------------
  * Conformer convolution module core: y = Swish(Norm(depthwise_conv1d_k(x) + bias)), x,y [B,T,d].
  * Replaces ConformerConvBlock.forward  modules/conformer_convolution.py:113-124 (depthwise Conv1d,
- * causal trim, LayerNorm | BatchNorm1d(eval) | GroupNorm(d/2 groups), Swish).  w: [d,k] taps.
+ * causal trim, LayerNorm | BatchNorm1d(eval) | GroupNorm(d/2 groups), Swish).  w: taps TRANSPOSED to [k,d].
  * norm_mode 0 LayerNorm(eps) over d, 1 BatchNorm with running stats, 2 GroupNorm (2 channels/group).
  * ------------------------------------------------------------------------------------------ */
 nsp_status nsp_conformer_conv_fwd(int is_bf16, const void* x, int64_t ldx, const float* w, const float* bias,

@@ -256,6 +256,13 @@ nsp_status launch_attn(const AttnParams& p, cudaStream_t st) {
 }  // namespace
 }  // namespace nsp
 
+namespace nsp {
+nsp_status attention_tc_dispatch(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                 const void* r, int64_t ldr, int rlen, const int32_t* klens, void* out, int64_t ldo,
+                                 int B, int H, int Tq, int Tk, int dk, int clamp_len, int causal, int lookahead,
+                                 int chunk_c, int chunk_l, cudaStream_t st);
+}
+
 using namespace nsp;
 
 extern "C" nsp_status nsp_relpos_attention_fwd(int is_bf16, const void* q, int64_t ldq, const void* k, int64_t ldk,
@@ -275,6 +282,12 @@ extern "C" nsp_status nsp_relpos_attention_fwd(int is_bf16, const void* q, int64
     p.lookahead = lookahead; p.chunk_c = chunk_c; p.chunk_l = chunk_l;
     p.inv_scale = 1.0f / sqrtf((float)dk);
     cudaStream_t st = (cudaStream_t)stream;
+    if (is_bf16 && !u_bias && !v_bias) {
+        // tensor-core kernel when the shape is inside its envelope (d_k = 64, clamped or no relative term)
+        nsp_status s = attention_tc_dispatch(q, ldq, k, ldk, v, ldv, r, ldr, rlen, klens, out, ldo, B, H, Tq, Tk, dk,
+                                             clamp_len, causal, lookahead, chunk_c, chunk_l, st);
+        if (s != NSP_ERR_UNSUPPORTED) return s;
+    }
     if (is_bf16) {
         if (dk <= 16) return launch_attn<__nv_bfloat16, 16>(p, st);
         if (dk <= 64) return launch_attn<__nv_bfloat16, 64>(p, st);

@@ -22,7 +22,7 @@ constexpr int TT = 8 * RT;     // frames per CTA
 
 struct ConvParams {
     const void* x; int64_t ldx;      // [B*T, d]
-    const float* w;                  // [d, k] depthwise taps (nn.Conv1d weight [d,1,k])
+    const float* w;                  // [k, d] depthwise taps, TRANSPOSED from nn.Conv1d weight [d,1,k]
     const float* bias;               // [d]
     const float* g; const float* b;  // norm weight / bias [d]
     const float* rmean; const float* rvar;   // BatchNorm running stats (mode 1)
@@ -49,14 +49,41 @@ __global__ void __launch_bounds__(256) conformer_conv_kernel(ConvParams p) {
     const int b = blockIdx.x / ttiles, t0 = (blockIdx.x % ttiles) * TT;
     const T* xg = reinterpret_cast<const T*>(p.x) + (int64_t)b * p.T * p.ldx;
 
-    for (int e = threadIdx.x; e < rows * d; e += 256) {
-        int r = e / d, c = e % d;
-        int t = t0 + r - p.left_pad;
-        tile[e] = (t >= 0 && t < p.T) ? cv_ld<T>(xg + (int64_t)t * p.ldx + c) : 0.f;
-    }
-    for (int e = threadIdx.x; e < k * d; e += 256) {
-        int j = e / d, c = e % d;
-        wT[e] = __ldg(p.w + (int64_t)c * k + j);
+    {
+        // stage the (TT + k - 1) x d input window (fp32 in smem) and the k x d taps; 128-bit loads when d % 8 == 0
+        const int w_ = threadIdx.x >> 5, l_ = threadIdx.x & 31;
+        const bool vec = (d % 8 == 0) && (p.ldx % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
+        for (int r = w_; r < rows; r += 8) {
+            const int t = t0 + r - p.left_pad;
+            const bool in = (t >= 0 && t < p.T);
+            float* trow = tile + (size_t)r * d;
+            if (vec) {
+                if constexpr (sizeof(T) == 2) {
+                    for (int c8 = l_; c8 < d / 8; c8 += 32) {
+                        float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+                        if (in) {
+                            uint4 raw = *reinterpret_cast<const uint4*>(xg + (int64_t)t * p.ldx + c8 * 8);
+                            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+                            float2 a = __bfloat1622float2(h2[0]), b2 = __bfloat1622float2(h2[1]);
+                            float2 c2 = __bfloat1622float2(h2[2]), d2 = __bfloat1622float2(h2[3]);
+                            lo = make_float4(a.x, a.y, b2.x, b2.y); hi = make_float4(c2.x, c2.y, d2.x, d2.y);
+                        }
+                        *reinterpret_cast<float4*>(trow + c8 * 8) = lo;
+                        *reinterpret_cast<float4*>(trow + c8 * 8 + 4) = hi;
+                    }
+                } else {
+                    for (int c4 = l_; c4 < d / 4; c4 += 32) {
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (in) v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(xg) + (int64_t)t * p.ldx + c4 * 4);
+                        *reinterpret_cast<float4*>(trow + c4 * 4) = v;
+                    }
+                }
+            } else {
+                for (int c = l_; c < d; c += 32) trow[c] = in ? cv_ld<T>(xg + (int64_t)t * p.ldx + c) : 0.f;
+            }
+        }
+        // taps arrive pre-transposed [k][d] (host prepares them once): straight coalesced copy
+        for (int e = threadIdx.x; e < k * d; e += 256) wT[e] = __ldg(p.w + e);
     }
     __syncthreads();
 
@@ -152,7 +179,11 @@ nsp_status launch_conv(const ConvParams& p, cudaStream_t st) {
 #define NSP_CONV(KK)                                                                                          \
     do {                                                                                                      \
         auto kern = conformer_conv_kernel<T, CPLMAX, KK>;                                                     \
-        NSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+        static size_t attr_smem = 0;                                                                          \
+        if (smem > attr_smem) {                                                                               \
+            NSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+            attr_smem = smem;                                                                                 \
+        }                                                                                                     \
         kern<<<grid, 256, smem, st>>>(p);                                                                     \
     } while (0)
     if (p.k == 15) NSP_CONV(15); else if (p.k == 31) NSP_CONV(31); else if (p.k == 7) NSP_CONV(7); else NSP_CONV(0);

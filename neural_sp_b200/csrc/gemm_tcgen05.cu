@@ -71,7 +71,8 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int KBYTES = 128;          // bytes of K per stage row (one 128B swizzle atom)
-constexpr int NTHREADS = 192;
+constexpr int NEPI_WARPS = 8;        // two warps per TMEM lane quadrant, each takes half of the tile's columns
+constexpr int NTHREADS = 64 + 32 * NEPI_WARPS;
 constexpr int MAX_SEG = 3;
 
 struct GemmMaps {
@@ -82,26 +83,36 @@ struct GemmMaps {
 struct GemmArgs {
     int M, N, K;            // N = rows of W (2*Nout for GLU)
     int nseg;
-    int glu;                // 1: out[:, j] = (acc[:, j] + b[j]) * sigmoid(acc[:, N/2 + j] + b[N/2 + j])
-    int act;                // 0 none, 1 relu, 2 swish
     const float* bias;      // [N] or null
     const float* residual;  // [M, ldr] fp32 or null
     int64_t ldr;
     float alpha;
     void* out;              // [M, ldo] fp32 or bf16
     int64_t ldo;
-    int out_bf16;
-    void* out2;             // optional second output (bf16 copy of fp32 out), or null
+    void* out2;             // optional second output (bf16 copy of an fp32 result), or null
     int64_t ldo2;
 };
 
-__device__ __forceinline__ float act_apply(float v, int act) {
-    if (act == 1) return fmaxf(v, 0.f);
-    if (act == 2) return __fdividef(v, 1.f + __expf(-v));
-    return v;
+// epilogue flavours (compile-time: the epilogue is instruction-bound, see profiles/r01_gemm_epilogue.md)
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SWISH = 2 };
+
+template <bool FAST>
+__device__ __forceinline__ float sigmoid_f(float x) {
+    if constexpr (FAST) {           // 0.5 + 0.5 * tanh(x/2): one MUFU instead of EX2 + RCP (bf16 operand mode)
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+        return fmaf(0.5f, t, 0.5f);
+    } else {
+        return __fdividef(1.f, 1.f + __expf(-x));
+    }
 }
 
-template <typename TIn, int BN, int STAGES>
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&p);
+}
+
+template <typename TIn, int BN, int STAGES, int ACT, bool GLU, bool RES, bool OUTBF16>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs g) {
     constexpr bool kBF16 = sizeof(TIn) == 2;
     constexpr int BK = KBYTES / (int)sizeof(TIn);        // 64 (bf16) or 32 (tf32)
@@ -110,7 +121,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
     constexpr int B_BYTES = BN * KBYTES;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr int TMEM_COLS = 2 * BN;                     // two accumulator stages
+    constexpr int BN_OUT = GLU ? BN / 2 : BN;             // output columns per tile
+    constexpr int COLS_PER_WARP = BN_OUT / 2;             // each quadrant is shared by two warps
     static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two");
+    static_assert(COLS_PER_WARP % 32 == 0 || COLS_PER_WARP == 16, "unsupported tile width");
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -121,10 +135,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nout = g.glu ? g.N / 2 : g.N;               // output columns
-    const int bn_out = g.glu ? BN / 2 : BN;               // output columns per tile
+    const int nout = GLU ? g.N / 2 : g.N;                 // output columns
     const int m_tiles = (g.M + BM - 1) / BM;
-    const int n_tiles = (nout + bn_out - 1) / bn_out;
+    const int n_tiles = (nout + BN_OUT - 1) / BN_OUT;
     const int num_tiles = m_tiles * n_tiles;
     const int kblocks = (g.K + BK - 1) / BK;
 
@@ -133,7 +146,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull_bar[i], 1); tc::mbar_init(&tempty_bar[i], 4); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull_bar[i], 1); tc::mbar_init(&tempty_bar[i], NEPI_WARPS); }
         tc::fence_barrier_init();
     }
     if (warp == 2) tc::tmem_alloc<TMEM_COLS>(tmem_holder);
@@ -155,7 +168,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
                         uint8_t* sb = sa + A_BYTES;
                         tc::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
                         tc::tma_load_2d(sa, &maps.a[s], &full_bar[stage], kb * BK, m_blk * BM);
-                        if (!g.glu) {
+                        if constexpr (!GLU) {
                             tc::tma_load_2d(sb, &maps.b[s], &full_bar[stage], kb * BK, n_blk * BN);
                         } else {   // value rows then gate rows of W land in one BN-row smem tile
                             tc::tma_load_2d(sb, &maps.b[s], &full_bar[stage], kb * BK, n_blk * (BN / 2));
@@ -203,8 +216,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
             }
         }
     } else {
-        // ===================== epilogue warps (2..5) =====================
+        // ===================== epilogue warps (2..9) =====================
         const int q = warp & 3;                                 // TMEM lane quadrant this warp may access
+        const int half = (warp - 2) >> 2;                       // which half of the tile's columns
+        const bool has_bias = g.bias != nullptr;
+        const bool bias_vec = (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
@@ -215,85 +231,98 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
             const int row = m_blk * BM + q * 32 + lane;
             const bool row_ok = row < g.M;
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-            const int col0 = n_blk * bn_out;
+            const int col0 = n_blk * BN_OUT + half * COLS_PER_WARP;
+            constexpr int CW = COLS_PER_WARP >= 32 ? 32 : 16;   // columns per chunk
 #pragma unroll 1
-            for (int c = 0; c < bn_out; c += 32) {
-                uint32_t r[32];
+            for (int c = 0; c < COLS_PER_WARP; c += CW) {
                 float v[32];
-                tc::tmem_ld_32x32(t_row + (uint32_t)c, r);
-                tc::tmem_ld_wait();
-                if (g.glu) {
-                    uint32_t r2[32];
-                    tc::tmem_ld_32x32(t_row + (uint32_t)(BN / 2 + c), r2);
+                const int cbase = col0 + c;
+                const int tcol = half * COLS_PER_WARP + c;      // column inside the accumulator (value part)
+                {
+                    uint32_t r[32];
+                    if constexpr (CW == 32) tc::tmem_ld_32x32(t_row + (uint32_t)tcol, r);
+                    else tc::tmem_ld_32x16(t_row + (uint32_t)tcol, r);
                     tc::tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        int col = col0 + c + j;
-                        float a = __uint_as_float(r[j]), gt = __uint_as_float(r2[j]);
-                        if (g.bias && col < nout) { a += __ldg(g.bias + col); gt += __ldg(g.bias + nout + col); }
-                        v[j] = __fdividef(a, 1.f + __expf(-gt));
-                    }
-                } else {
+                    for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(r[j]);
+                }
+                const bool full = (cbase + CW <= nout);
+                if (has_bias) {
+                    if (full && bias_vec) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        int col = col0 + c + j;
-                        float a = __uint_as_float(r[j]);
-                        if (g.bias && col < nout) a += __ldg(g.bias + col);
-                        v[j] = act_apply(a, g.act);
+                        for (int j = 0; j < CW; j += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + cbase + j));
+                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < CW; ++j) if (cbase + j < nout) v[j] += __ldg(g.bias + cbase + j);
                     }
                 }
+                if constexpr (GLU) {
+                    uint32_t r2[32];
+                    if constexpr (CW == 32) tc::tmem_ld_32x32(t_row + (uint32_t)(BN / 2 + tcol), r2);
+                    else tc::tmem_ld_32x16(t_row + (uint32_t)(BN / 2 + tcol), r2);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < CW; ++j) {
+                        float gt = __uint_as_float(r2[j]);
+                        if (has_bias && cbase + j < nout) gt += __ldg(g.bias + nout + cbase + j);
+                        v[j] *= sigmoid_f<kBF16>(gt);
+                    }
+                } else if constexpr (ACT == ACT_RELU) {
+#pragma unroll
+                    for (int j = 0; j < CW; ++j) v[j] = fmaxf(v[j], 0.f);
+                } else if constexpr (ACT == ACT_SWISH) {
+#pragma unroll
+                    for (int j = 0; j < CW; ++j) v[j] *= sigmoid_f<kBF16>(v[j]);
+                }
                 if (row_ok) {
-                    const int cbase = col0 + c;
-                    const bool full = (cbase + 32 <= nout);
-                    if (g.residual) {
+                    if constexpr (RES) {
                         const float* rr = g.residual + (int64_t)row * g.ldr + cbase;
                         if (full && (g.ldr % 4 == 0)) {
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                float4 x = *reinterpret_cast<const float4*>(rr + j);
-                                v[j] = x.x + g.alpha * v[j]; v[j + 1] = x.y + g.alpha * v[j + 1];
-                                v[j + 2] = x.z + g.alpha * v[j + 2]; v[j + 3] = x.w + g.alpha * v[j + 3];
+                            for (int j = 0; j < CW; j += 4) {
+                                const float4 x = *reinterpret_cast<const float4*>(rr + j);
+                                v[j] = fmaf(g.alpha, v[j], x.x); v[j + 1] = fmaf(g.alpha, v[j + 1], x.y);
+                                v[j + 2] = fmaf(g.alpha, v[j + 2], x.z); v[j + 3] = fmaf(g.alpha, v[j + 3], x.w);
                             }
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) if (cbase + j < nout) v[j] = rr[j] + g.alpha * v[j];
+                            for (int j = 0; j < CW; ++j) if (cbase + j < nout) v[j] = fmaf(g.alpha, v[j], rr[j]);
                         }
                     } else if (g.alpha != 1.f) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] *= g.alpha;
+                        for (int j = 0; j < CW; ++j) v[j] *= g.alpha;
                     }
-                    if (!g.out_bf16) {
+                    if constexpr (!OUTBF16) {
                         float* o = reinterpret_cast<float*>(g.out) + (int64_t)row * g.ldo + cbase;
                         if (full && (g.ldo % 4 == 0)) {
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4)
+                            for (int j = 0; j < CW; j += 4)
                                 *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) if (cbase + j < nout) o[j] = v[j];
+                            for (int j = 0; j < CW; ++j) if (cbase + j < nout) o[j] = v[j];
                         }
                     }
                     __nv_bfloat16* ob = nullptr;
                     int64_t ldb = 0;
-                    if (g.out_bf16) { ob = reinterpret_cast<__nv_bfloat16*>(g.out); ldb = g.ldo; }
+                    if constexpr (OUTBF16) { ob = reinterpret_cast<__nv_bfloat16*>(g.out); ldb = g.ldo; }
                     else if (g.out2) { ob = reinterpret_cast<__nv_bfloat16*>(g.out2); ldb = g.ldo2; }
                     if (ob) {
                         __nv_bfloat16* o = ob + (int64_t)row * ldb + cbase;
                         if (full && (ldb % 8 == 0)) {
 #pragma unroll
-                            for (int j = 0; j < 32; j += 8) {
-                                __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-                                __nv_bfloat162 p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                                __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-                                __nv_bfloat162 p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                            for (int j = 0; j < CW; j += 8) {
                                 uint4 pk;
-                                pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-                                pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+                                pk.x = pack_bf16(v[j], v[j + 1]); pk.y = pack_bf16(v[j + 2], v[j + 3]);
+                                pk.z = pack_bf16(v[j + 4], v[j + 5]); pk.w = pack_bf16(v[j + 6], v[j + 7]);
                                 *reinterpret_cast<uint4*>(o + j) = pk;
                             }
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) if (cbase + j < nout) o[j] = __float2bfloat16_rn(v[j]);
+                            for (int j = 0; j < CW; ++j) if (cbase + j < nout) o[j] = __float2bfloat16_rn(v[j]);
                         }
                     }
                 }
@@ -312,29 +341,58 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
     }
 }
 
-template <typename TIn, int BN>
+template <int BN>
 constexpr int stages_for() {
     // 227 KiB usable; keep ~3 KiB for barriers/alignment slack
     return ((224 * 1024) / (BM * KBYTES + BN * KBYTES)) > 8 ? 8 : ((224 * 1024) / (BM * KBYTES + BN * KBYTES));
 }
 
-template <typename TIn, int BN>
+template <typename TIn, int BN, int ACT, bool GLU, bool RES, bool OUTBF16>
 nsp_status launch_gemm(const GemmMaps& maps, const GemmArgs& g, cudaStream_t st) {
-    constexpr int STAGES = stages_for<TIn, BN>();
+    constexpr int STAGES = stages_for<BN>();
     constexpr size_t smem = (size_t)STAGES * (BM * KBYTES + BN * KBYTES) + 1024 /*align*/ + 256 /*barriers*/;
-    auto kern = gemm_kernel<TIn, BN, STAGES>;
+    auto kern = gemm_kernel<TIn, BN, STAGES, ACT, GLU, RES, OUTBF16>;
     static bool attr_set = false;
     if (!attr_set) {
         NSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    const int nout = g.glu ? g.N / 2 : g.N;
-    const int bn_out = g.glu ? BN / 2 : BN;
+    const int nout = GLU ? g.N / 2 : g.N;
+    const int bn_out = GLU ? BN / 2 : BN;
     const int tiles = ceil_div(g.M, BM) * ceil_div(nout, bn_out);
     const int grid = tiles < num_sms() ? tiles : num_sms();
     kern<<<grid, NTHREADS, smem, st>>>(maps, g);
     NSP_LAUNCH_OK();
     return NSP_OK;
+}
+
+// epilogue flavour dispatch for one operand type / tile width
+template <typename TIn, int BN>
+nsp_status dispatch_epi(const GemmMaps& maps, const GemmArgs& g, int glu, int act, int out_bf16, cudaStream_t st) {
+    const bool res = g.residual != nullptr;
+    if (glu) {
+        if constexpr (BN == 128) {
+            if (res) { set_error("gemm: GLU with residual is not instantiated"); return NSP_ERR_UNSUPPORTED; }
+            return out_bf16 ? launch_gemm<TIn, 128, ACT_NONE, true, false, true>(maps, g, st)
+                            : launch_gemm<TIn, 128, ACT_NONE, true, false, false>(maps, g, st);
+        } else {
+            set_error("gemm: GLU needs the 128-wide tile"); return NSP_ERR_INVALID;
+        }
+    }
+    if (res) {
+        if (act != ACT_NONE || out_bf16) { set_error("gemm: residual epilogue is fp32-out without activation"); return NSP_ERR_UNSUPPORTED; }
+        return launch_gemm<TIn, BN, ACT_NONE, false, true, false>(maps, g, st);
+    }
+    switch (act) {
+        case ACT_NONE: return out_bf16 ? launch_gemm<TIn, BN, ACT_NONE, false, false, true>(maps, g, st)
+                                       : launch_gemm<TIn, BN, ACT_NONE, false, false, false>(maps, g, st);
+        case ACT_RELU: return out_bf16 ? launch_gemm<TIn, BN, ACT_RELU, false, false, true>(maps, g, st)
+                                       : launch_gemm<TIn, BN, ACT_RELU, false, false, false>(maps, g, st);
+        case ACT_SWISH: return out_bf16 ? launch_gemm<TIn, BN, ACT_SWISH, false, false, true>(maps, g, st)
+                                        : launch_gemm<TIn, BN, ACT_SWISH, false, false, false>(maps, g, st);
+    }
+    set_error("gemm: act=%d", act);
+    return NSP_ERR_INVALID;
 }
 
 }  // namespace
@@ -354,9 +412,11 @@ nsp_status gemm_dispatch(int precision, const void* a, const void* a_lo, int64_t
     const int es = bf16 ? 2 : 4;
     GemmMaps maps;
     GemmArgs g;
-    g.M = M; g.N = N; g.K = K; g.glu = glu; g.act = act; g.bias = bias; g.residual = residual; g.ldr = ldr;
-    g.alpha = alpha; g.out = out; g.ldo = ldo; g.out_bf16 = out_bf16; g.out2 = out2; g.ldo2 = ldo2;
+    g.M = M; g.N = N; g.K = K; g.bias = bias; g.residual = residual; g.ldr = ldr;
+    g.alpha = alpha; g.out = out; g.ldo = ldo; g.out2 = out2; g.ldo2 = ldo2;
     g.nseg = precision == 2 ? 3 : 1;
+    NSP_CHECK_ARG(act >= 0 && act <= 2, "gemm: act=%d", act);
+    NSP_CHECK_ARG(!(out2 && out_bf16), "gemm: out2 is only meaningful with an fp32 primary output");
     const int nout = glu ? N / 2 : N;
     // tile width: 128 unless the problem is too small to fill the machine, then 64 (GLU always 128 = 64 value + 64 gate)
     int BN = 128;
@@ -368,8 +428,10 @@ nsp_status gemm_dispatch(int precision, const void* a, const void* a_lo, int64_t
         if (!make_tmap_2d(&maps.a[s], as[s], es, bf16, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM)) return NSP_ERR_INVALID;
         if (!make_tmap_2d(&maps.b[s], ws[s], es, bf16, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, box_b)) return NSP_ERR_INVALID;
     }
-    if (bf16) return BN == 128 ? launch_gemm<__nv_bfloat16, 128>(maps, g, st) : launch_gemm<__nv_bfloat16, 64>(maps, g, st);
-    return BN == 128 ? launch_gemm<float, 128>(maps, g, st) : launch_gemm<float, 64>(maps, g, st);
+    if (bf16) return BN == 128 ? dispatch_epi<__nv_bfloat16, 128>(maps, g, glu, act, out_bf16, st)
+                               : dispatch_epi<__nv_bfloat16, 64>(maps, g, glu, act, out_bf16, st);
+    return BN == 128 ? dispatch_epi<float, 128>(maps, g, glu, act, out_bf16, st)
+                     : dispatch_epi<float, 64>(maps, g, glu, act, out_bf16, st);
 }
 
 }  // namespace nsp

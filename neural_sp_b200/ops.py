@@ -54,8 +54,22 @@ def _require_cuda(*ts):
             raise _lib.NspError("neural_sp_b200 ops need CUDA tensors (no CPU fallback); got device %s" % t.device)
 
 
+_LABEL_CACHE = {}
+
+
 def pack_labels(ys, device):
-    """List of label lists -> (labels int32 [B, Lmax] on device, ylens int32 [B] on device, Lmax)."""
+    """List of label lists -> (labels int32 [B, Lmax] on device, ylens int32 [B] on device, Lmax).
+    The last packed batch is cached (same labels again -> no new H2D copy; needed for CUDA-graph replays)."""
+    key = (tuple(tuple(int(v) for v in y) for y in ys), str(device))
+    hit = _LABEL_CACHE.get("last")
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    out = _pack_labels(ys, device)
+    _LABEL_CACHE["last"] = (key, out)
+    return out
+
+
+def _pack_labels(ys, device):
     B = len(ys)
     ylens = [len(y) for y in ys]
     Lmax = max(1, max(ylens) if ylens else 1)
@@ -251,13 +265,27 @@ def relpos_attention(q, k, v, klens, n_heads, r=None, u_bias=None, v_bias=None, 
 NORM_MODE = {"layer_norm": 0, "batch_norm": 1, "group_norm": 2}
 
 
+_TAPS_CACHE = {}
+
+
+def _taps_kd(dw_weight, d, k):
+    """nn.Conv1d depthwise weight [d,1,k] -> fp32 [k,d] (cached per parameter version)."""
+    key = (dw_weight.data_ptr(), dw_weight._version, d, k)
+    hit = _TAPS_CACHE.get(dw_weight.data_ptr())
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    w = dw_weight.detach().reshape(d, k).t().contiguous().float()
+    _TAPS_CACHE[dw_weight.data_ptr()] = (key, w)
+    return w
+
+
 def conformer_conv(x, dw_weight, dw_bias, norm_mode, norm_w, norm_b, eps, run_mean=None, run_var=None, causal=False):
     """y = Swish(Norm(depthwise_conv(x) + bias)) on `[B, T, d]` (nsp_conformer_conv_fwd)."""
     _require_cuda(x)
     B, T, d = x.shape
     x = x if x.stride(2) == 1 and x.stride(0) == T * x.stride(1) else x.contiguous()
     k = dw_weight.shape[-1]
-    w = dw_weight.reshape(d, k)
+    w = _taps_kd(dw_weight, d, k)
     y = torch.empty(B, T, d, dtype=x.dtype, device=x.device)
     _run("nsp_conformer_conv_fwd", lib.nsp_conformer_conv_fwd, int(x.dtype == torch.bfloat16), ptr(x), x.stride(1), ptr(w), ptr(dw_bias),
                                      NORM_MODE[norm_mode], ptr(norm_w), ptr(norm_b), ptr(run_mean), ptr(run_var),

@@ -1,0 +1,42 @@
+"""Small drivers for ncu captures of single kernels (run under gpurun; see profiles/README.md)."""
+import sys
+import torch
+
+sys.path.insert(0, ".")
+from neural_sp_b200 import ops  # noqa: E402
+
+which = sys.argv[1] if len(sys.argv) > 1 else "gemm_ffn1"
+dev = "cuda"
+torch.manual_seed(0)
+if which.startswith("gemm"):
+    shapes = {"gemm_ffn1": (16000, 2048, 512, "swish", True, False), "gemm_ffn2": (16000, 512, 2048, None, False, True),
+              "gemm_qkv": (16000, 1536, 512, None, True, False)}
+    M, N, K, act, out_bf16, res = shapes[which]
+    x = torch.randn(M, K, device=dev).bfloat16()
+    w = ops.prepare_weight(torch.randn(N, K, device=dev) / K ** 0.5, "bf16")
+    b = torch.randn(N, device=dev)
+    r = torch.randn(M, N, device=dev) if res else None
+    for _ in range(5):
+        y = ops.linear(x, w, b, prec="bf16", act=act, residual=r, alpha=0.5 if res else 1.0,
+                       out_dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(20):
+        y = ops.linear(x, w, b, prec="bf16", act=act, residual=r, alpha=0.5 if res else 1.0,
+                       out_dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / 20
+    print(which, "ms", ms, "TFLOP/s", 2.0 * M * N * K / ms / 1e9)
+elif which == "ctc":
+    B, T, V = 32, 125, 10000
+    import numpy as np
+    rng = np.random.default_rng(0)
+    logits = torch.randn(B, T, V, device=dev)
+    ys = [rng.integers(4, V, size=56).tolist() for _ in range(B)]
+    labels, ylens, _ = ops.pack_labels(ys, logits.device)
+    elens = torch.full((B,), T, dtype=torch.int32, device=dev)
+    for _ in range(5):
+        ops.ctc_loss_fwd_bwd(logits, labels, elens, ylens, 0, 0.1)
+    torch.cuda.synchronize()

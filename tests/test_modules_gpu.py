@@ -63,6 +63,8 @@ def _attn_ref(q, k, v, r, u, vb, klens, H, clamp, causal, lookahead, chunk_c, ch
     dict(B=2, T=90, H=4, dk=64, clamp=10, causal=True, lookahead=2),
     dict(B=2, T=96, H=4, dk=64, clamp=-1, chunk_c=16, chunk_l=32),
     dict(B=2, T=33, Tk=80, H=4, dk=64, clamp=10),
+    dict(B=2, T=300, H=2, dk=64, clamp=10, chunk_c=32, chunk_l=64), dict(B=2, T=200, H=4, dk=64, clamp=-1, rel=False),
+    dict(B=3, T=500, H=8, dk=64, clamp=10), dict(B=2, T=129, H=1, dk=64, clamp=1),
 ])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_relpos_attention(cfg, dtype):
