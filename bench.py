@@ -281,7 +281,7 @@ def main():
     launches_per_step = ops.LAUNCHES - l_before
 
     # ---- capture the step into a CUDA graph (launch-bound inner loop: ~300 kernels per step) ----
-    graph, loss_static = None, None
+    graph, loss_static, graph_error = None, None, None
     xs_static = xs_dev.clone()
     if not args.no_graph:
         try:
@@ -298,7 +298,8 @@ def main():
             torch.cuda.synchronize()
         except Exception as ex:                      # keep the eager path, say so in the JSON line
             graph = None
-            graph_error = repr(ex)[:200]
+            graph_error = repr(ex)[:300]
+            print('[bench] CUDA graph capture failed, timing eager launches: ' + graph_error, file=sys.stderr)
             torch.cuda.synchronize()
     eager_step = step
 
@@ -384,7 +385,7 @@ def main():
                 "config": dict(cfg_common, l2="256 MiB memset between timed iterations (outside the event pairs); "
                                              "per-step working set >> 126 MB L2",
                                encoder_fwd_tflop_per_step=fl_utt * B / 1e12, enc_out_frames=Tp,
-                               cuda_graph=graph is not None),
+                               cuda_graph=graph is not None, cuda_graph_error=graph_error),
                 "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": int(xs_host.numel() * 4), "d2h_bytes_per_step": 4},

@@ -42,7 +42,10 @@ struct CtcParams {
     float* lse;    // [B,T]
     float* hrow;   // [B,T]  sum_v p*lp
     float* klrow;  // [B,T]
-    int Sp;
+    float* nll_raw;    // [B] un-zeroed nll (>= 1e29 when infeasible)
+    int16_t* nxt;      // [B,Sp] next state carrying the same label (-1: none)
+    int16_t* head;     // [B,Sp] 1 if first occurrence of its label in the path
+    int Sp;            // lattice row pitch (2*Lmax+1 rounded up to a multiple of 4)
 };
 
 template <int G>
@@ -72,7 +75,7 @@ __device__ __forceinline__ float n_frames_of(const int32_t* elens, int B, int T)
 // K1, register-resident rows.  G threads cooperate on one row; 256 threads per CTA.
 // ---------------------------------------------------------------------------------------------
 template <int G, int VPT, int VEC>
-__global__ void __launch_bounds__(256) ctc_rows_kernel(CtcParams p) {
+__global__ void __launch_bounds__(256, (VPT * VEC <= 32) ? 4 : 3) ctc_rows_kernel(CtcParams p) {
     constexpr int NT = 256;
     constexpr int RPB = NT / G;
     __shared__ float scratch[32];
@@ -118,18 +121,13 @@ __global__ void __launch_bounds__(256) ctc_rows_kernel(CtcParams p) {
         }
     }
     m = group_max<G>(m, scratch);
-    float e[VPT][VEC];
     float sum = 0.f;
 #pragma unroll
     for (int j = 0; j < VPT; ++j)
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-            e[j][k] = __expf(x[j][k] - m);   // exp(-inf) = 0 for the tail
-            sum += e[j][k];
-        }
+        for (int k = 0; k < VEC; ++k) sum += __expf(x[j][k] - m);   // exp(-inf) = 0 for the tail
     sum = group_sum<G>(sum, scratch);
     const float lse = m + __logf(sum);
-    const float inv = 1.f / sum;
 
     const float c_ctc = (1.f - p.lsm) / (float)p.B;
     float c_kl = 0.f, H = 0.f;
@@ -139,13 +137,16 @@ __global__ void __launch_bounds__(256) ctc_rows_kernel(CtcParams p) {
         for (int j = 0; j < VPT; ++j)
 #pragma unroll
             for (int k = 0; k < VEC; ++k) {
-                float pv = e[j][k] * inv;
-                if (pv > 0.f) h += pv * (x[j][k] - lse);
+                float lp = x[j][k] - lse;
+                float pv = __expf(lp);
+                if (pv > 0.f) h += pv * lp;
             }
         H = group_sum<G>(h, scratch);
         c_kl = p.lsm / n_frames_of(p.elens, p.B, p.T);
     }
 
+    // the exponentials are recomputed (MUFU has headroom at HBM speed) instead of kept: half the registers,
+    // twice the resident CTAs, more bytes in flight per SM
 #pragma unroll
     for (int j = 0; j < VPT; ++j) {
         int idx = (j * G + lane) * VEC;
@@ -153,9 +154,9 @@ __global__ void __launch_bounds__(256) ctc_rows_kernel(CtcParams p) {
             float g[VEC];
 #pragma unroll
             for (int k = 0; k < VEC; ++k) {
-                float pv = e[j][k] * inv;
-                g[k] = pv * (c_ctc + c_kl * ((x[j][k] - lse) - H));
-                if (!(pv > 0.f)) g[k] = 0.f;   // p == 0: lp may be -inf, 0 * inf guard
+                float lp = x[j][k] - lse;
+                float pv = __expf(lp);
+                g[k] = (pv > 0.f) ? pv * (c_ctc + c_kl * (lp - H)) : 0.f;   // p == 0: lp may be -inf
             }
             if constexpr (VEC == 4) st_stream_f4(grow + idx, make_float4(g[0], g[1], g[2], g[3]));
             else grow[idx] = g[0];
@@ -411,6 +412,248 @@ __global__ void __launch_bounds__(1024) ctc_lattice_kernel(CtcParams p, int HALF
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// K2 (default): warp-per-sweep lattice.  CTA = 2 warps for one utterance: warp 0 runs alpha forward, warp 1 runs beta
+// backward, each lane owns K consecutive states in registers, neighbours come from __shfl_up/down_sync -- no block
+// barriers on the serial chain; emissions are prefetched PF steps ahead with 128-bit loads.
+// ---------------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ void ld_states(const float* p, float (&v)[K]) {
+    if constexpr (K >= 4) {
+#pragma unroll
+        for (int i = 0; i < K; i += 4) {
+            float4 t = *reinterpret_cast<const float4*>(p + i);
+            v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+        }
+    } else if constexpr (K == 2) {
+        float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y;
+    } else {
+        v[0] = *p;
+    }
+}
+template <int K>
+__device__ __forceinline__ void st_states(float* p, const float (&v)[K]) {
+    if constexpr (K >= 4) {
+#pragma unroll
+        for (int i = 0; i < K; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    } else if constexpr (K == 2) {
+        *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+    } else {
+        *p = v[0];
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(64) ctc_lattice_warp_kernel(CtcParams p) {
+    constexpr int PF = (K <= 4) ? 8 : (K == 8 ? 4 : 2);      // emission prefetch depth (steps)
+    __shared__ int32_t s_lab[256 + 8];
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool is_beta = warp == 1;
+    const int Sp = p.Sp;
+    const int L = min(max(p.ylens[b], 0), p.Lmax);
+    const int S = 2 * L + 1;
+    const int Tb = min(max(p.elens[b], 0), p.T);
+    const int32_t* lab = p.labels + (int64_t)b * p.Lmax;
+    const int64_t base = (int64_t)b * p.T * Sp;
+    const float* em = p.emit + base;
+    float* gout = (is_beta ? p.beta : p.alpha) + base;
+
+    for (int i = threadIdx.x; i < L; i += 64) s_lab[i] = lab[i];
+    __syncthreads();
+    // same-label chains for the sparse gradient fix-up (consumed by ctc_fixup_kernel)
+    for (int s = threadIdx.x; s < S; s += 64) {
+        int nx = -1, hd = 1;
+        if (s & 1) {
+            const int me = s_lab[s >> 1];
+            for (int q = (s >> 1) + 1; q < L; ++q) if (s_lab[q] == me) { nx = 2 * q + 1; break; }
+            for (int q = 0; q < (s >> 1); ++q) if (s_lab[q] == me) { hd = 0; break; }
+        }
+        p.nxt[(int64_t)b * Sp + s] = (int16_t)nx;
+        p.head[(int64_t)b * Sp + s] = (int16_t)hd;
+    }
+
+    const int s0 = lane * K;
+    bool valid[K], skip[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int s = s0 + k;
+        valid[k] = s < S;
+        skip[k] = false;
+        if (valid[k] && (s & 1)) {
+            if (!is_beta) skip[k] = (s >= 2) && (s_lab[s >> 1] != s_lab[(s >> 1) - 1]);
+            else          skip[k] = (s + 2 < S) && (s_lab[s >> 1] != s_lab[(s >> 1) + 1]);
+        }
+    }
+    if (Tb <= 0) {
+        if (threadIdx.x == 0) { const float v = (L == 0) ? 0.f : 1.0e30f; p.nll_raw[b] = v; p.nll[b] = (L == 0) ? 0.f : 0.f; }
+        return;
+    }
+    const bool lane_active = s0 < S;                      // lanes beyond the path never touch memory
+    auto trow = [&](int i) { return is_beta ? (Tb - 1 - i) : i; };
+
+    float ring[PF][K];
+#pragma unroll
+    for (int q = 0; q < PF; ++q) {
+        if (lane_active && q < Tb) ld_states<K>(em + (int64_t)trow(q) * Sp + s0, ring[q]);
+        else {
+#pragma unroll
+            for (int k = 0; k < K; ++k) ring[q][k] = 0.f;
+        }
+    }
+    float own[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) own[k] = NSP_NEG_BIG;
+
+    for (int i0 = 0; i0 < Tb; i0 += PF) {
+#pragma unroll
+        for (int q = 0; q < PF; ++q) {
+            const int i = i0 + q;
+            if (i < Tb) {                                  // warp-uniform
+                float e[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) e[k] = ring[q][k];
+                // refill this ring slot with the row PF steps ahead
+                if (lane_active && i + PF < Tb) ld_states<K>(em + (int64_t)trow(i + PF) * Sp + s0, ring[q]);
+                float nw[K];
+                if (i == 0) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const int s = s0 + k;
+                        const bool start = is_beta ? (s >= S - 2) : (s <= 1);
+                        nw[k] = (valid[k] && start) ? e[k] : NSP_NEG_BIG;
+                    }
+                } else {
+                    float n1, n2;     // neighbours across the lane boundary
+                    if (!is_beta) {
+                        n1 = __shfl_up_sync(0xffffffffu, own[K - 1], 1);
+                        n2 = (K >= 2) ? __shfl_up_sync(0xffffffffu, own[K >= 2 ? K - 2 : 0], 1) : __shfl_up_sync(0xffffffffu, own[0], 2);
+                        if (lane == 0) { n1 = NSP_NEG_BIG; n2 = NSP_NEG_BIG; }
+                        if (K == 1 && lane == 1) n2 = NSP_NEG_BIG;
+                    } else {
+                        n1 = __shfl_down_sync(0xffffffffu, own[0], 1);
+                        n2 = (K >= 2) ? __shfl_down_sync(0xffffffffu, own[K >= 2 ? 1 : 0], 1) : __shfl_down_sync(0xffffffffu, own[0], 2);
+                        if (lane == 31) { n1 = NSP_NEG_BIG; n2 = NSP_NEG_BIG; }
+                        if (K == 1 && lane == 30) n2 = NSP_NEG_BIG;
+                    }
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        float a1, a2;
+                        if (!is_beta) {
+                            a1 = (k >= 1) ? own[k >= 1 ? k - 1 : 0] : n1;
+                            a2 = (k >= 2) ? own[k >= 2 ? k - 2 : 0] : ((k == 1) ? n1 : n2);
+                        } else {
+                            a1 = (k + 1 < K) ? own[k + 1 < K ? k + 1 : 0] : n1;
+                            a2 = (k + 2 < K) ? own[k + 2 < K ? k + 2 : 0] : ((k + 2 == K) ? n1 : n2);
+                        }
+                        if (!skip[k]) a2 = NSP_NEG_BIG;
+                        float v = lse3(own[k], a1, a2) + e[k];
+                        nw[k] = valid[k] ? fmaxf(v, NSP_NEG_BIG) : NSP_NEG_BIG;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) own[k] = nw[k];
+                if (lane_active) st_states<K>(gout + (int64_t)trow(i) * Sp + s0, own);
+            }
+        }
+    }
+    if (!is_beta) {
+        // nll = -lse(alpha_{T-1}(S-1), alpha_{T-1}(S-2))
+        float m = NSP_NEG_BIG;
+#pragma unroll
+        for (int k = 0; k < K; ++k) { const int s = s0 + k; if (s == S - 1 || s == S - 2) m = fmaxf(m, own[k]); }
+        const float M = warp_max(m);
+        float sm_ = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) { const int s = s0 + k; if (s == S - 1 || s == S - 2) sm_ += __expf(own[k] - M); }
+        sm_ = warp_sum(sm_);
+        if (lane == 0) {
+            const float nll = -(M + __logf(sm_));
+            p.nll_raw[b] = nll;
+            p.nll[b] = (nll < 1.0e29f) ? nll : 0.f;
+        }
+    }
+}
+
+// K3: sparse gradient fix-up, one warp per (b, t) row (thousands of independent HBM read-modify-writes in flight),
+// plus the scalar loss reduction in CTA 0.
+__global__ void __launch_bounds__(256) ctc_fixup_kernel(CtcParams p) {
+    __shared__ float scratch[32];
+    if (blockIdx.x == gridDim.x - 1) {     // dedicated last CTA: loss = (1-lsm) * sum nll / B + lsm * KL
+        float a = 0.f;
+        for (int i = threadIdx.x; i < p.B; i += 256) a += p.nll[i];
+        a = block_sum<256>(a, scratch);
+        float loss = (1.f - p.lsm) * a / (float)p.B;
+        if (p.lsm > 0.f) {
+            float k = 0.f;
+            const int64_t n = (int64_t)p.B * p.T;
+            for (int64_t i = threadIdx.x; i < n; i += 256) k += p.klrow[i];
+            k = block_sum<256>(k, scratch);
+            loss += p.lsm * k / n_frames_of(p.elens, p.B, p.T);
+        }
+        if (threadIdx.x == 0) p.loss[0] = loss;
+        return;
+    }
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= (int64_t)p.B * p.T) return;
+    const int b = (int)(row / p.T), t = (int)(row % p.T);
+    const int Tb = min(max(p.elens[b], 0), p.T);
+    if (t >= Tb) return;
+    const int Sp = p.Sp;
+    const int L = min(max(p.ylens[b], 0), p.Lmax);
+    const int S = 2 * L + 1;
+    const float nll = p.nll_raw[b];
+    const float c_ctc = (1.f - p.lsm) / (float)p.B;
+    float* grow = p.grad + row * (int64_t)p.V;
+    if (!(nll < 1.0e29f)) {
+        // zero_infinity: CTC part of the gradient vanishes; only the label-smoothing KL part stays
+        const float c_kl = (p.lsm > 0.f) ? p.lsm / n_frames_of(p.elens, p.B, p.T) : 0.f;
+        const float* xrow = p.logits + (int64_t)b * p.sb + (int64_t)t * p.st;
+        const float lse = p.lse[row], H = p.hrow[row];
+        for (int v = lane; v < p.V; v += 32) {
+            float lp = xrow[v] - lse; float pv = __expf(lp);
+            grow[v] = (pv > 0.f) ? c_kl * pv * (lp - H) : 0.f;
+        }
+        return;
+    }
+    const float* a = p.alpha + row * (int64_t)Sp;
+    const float* bt = p.beta + row * (int64_t)Sp;
+    const float* e = p.emit + row * (int64_t)Sp;
+    const int16_t* nxt = p.nxt + (int64_t)b * Sp;
+    const int16_t* head = p.head + (int64_t)b * Sp;
+    const int32_t* lab = p.labels + (int64_t)b * p.Lmax;
+    const int bl = min(max(p.blank, 0), p.V - 1);
+    // blank column: all even states
+    float m = NSP_NEG_BIG, sum = 0.f;
+    for (int s = 2 * lane; s < S; s += 64) {
+        float v = a[s] + bt[s];
+        float nm = fmaxf(m, v);
+        sum = sum * __expf(m - nm) + __expf(v - nm);
+        m = nm;
+    }
+    const float M = warp_max(m);
+    sum = warp_sum(sum * __expf(m - M));
+    if (lane == 0) grow[bl] -= c_ctc * __expf(M + __logf(sum) + nll - e[0]);
+    // label columns: head states walk their same-label chain (deterministic order)
+    for (int s = 2 * lane + 1; s < S; s += 64) {
+        if (head[s]) {
+            float mm = a[s] + bt[s], ss = 1.f;
+            for (int q = nxt[s]; q >= 0; q = nxt[q]) {
+                float v = a[q] + bt[q];
+                float nm = fmaxf(mm, v);
+                ss = ss * __expf(mm - nm) + __expf(v - nm);
+                mm = nm;
+            }
+            const float lcab = mm + __logf(ss);
+            const int v = min(max(lab[s >> 1], 0), p.V - 1);
+            if (v != bl) grow[v] -= c_ctc * __expf(lcab + nll - e[s]);
+            else atomicAdd(&grow[v], -c_ctc * __expf(lcab + nll - e[s]));   // label == blank id (degenerate input)
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) ctc_finalize_kernel(CtcParams p) {
     __shared__ float scratch[32];
     float a = 0.f;
@@ -452,9 +695,10 @@ using namespace nsp;
 
 extern "C" size_t nsp_ctc_loss_workspace_bytes(int B, int T, int Lmax) {
     if (B <= 0 || T <= 0 || Lmax < 0) return 0;
-    size_t Sp = 2 * (size_t)Lmax + 1;
+    size_t Sp = align_up(2 * (size_t)Lmax + 1, 4);
     size_t bt = (size_t)B * T;
-    return align_up(3 * bt * Sp * sizeof(float), 256) + 3 * align_up(bt * sizeof(float), 256) + 256;
+    return align_up(3 * bt * Sp * sizeof(float), 256) + 3 * align_up(bt * sizeof(float), 256) +
+           align_up((size_t)B * sizeof(float), 256) + 2 * align_up((size_t)B * Sp * sizeof(int16_t), 256) + 256;
 }
 
 extern "C" nsp_status nsp_ctc_loss_fwd_bwd(const float* logits, int64_t stride_b, int64_t stride_t,
@@ -477,7 +721,7 @@ extern "C" nsp_status nsp_ctc_loss_fwd_bwd(const float* logits, int64_t stride_b
     p.logits = logits; p.sb = stride_b; p.st = stride_t; p.B = B; p.T = T; p.V = V;
     p.labels = labels; p.Lmax = Lmax; p.elens = elens; p.ylens = ylens;
     p.blank = blank; p.lsm = lsm_prob; p.nll = nll; p.loss = loss; p.grad = grad;
-    p.Sp = 2 * Lmax + 1;
+    p.Sp = (int)align_up((size_t)(2 * Lmax + 1), 4);
     const size_t bt = (size_t)B * T;
     char* w = (char*)workspace;
     const size_t lat = bt * p.Sp * sizeof(float);
@@ -485,7 +729,10 @@ extern "C" nsp_status nsp_ctc_loss_fwd_bwd(const float* logits, int64_t stride_b
     w += align_up(3 * lat, 256);
     p.lse = (float*)w; w += align_up(bt * sizeof(float), 256);
     p.hrow = (float*)w; w += align_up(bt * sizeof(float), 256);
-    p.klrow = (float*)w;
+    p.klrow = (float*)w; w += align_up(bt * sizeof(float), 256);
+    p.nll_raw = (float*)w; w += align_up((size_t)B * sizeof(float), 256);
+    p.nxt = (int16_t*)w; w += align_up((size_t)B * p.Sp * sizeof(int16_t), 256);
+    p.head = (int16_t*)w;
 
     // ---- K1 ----
     const bool vec4 = (V % 4 == 0) && (stride_b % 4 == 0) && (stride_t % 4 == 0) &&
@@ -507,8 +754,21 @@ extern "C" nsp_status nsp_ctc_loss_fwd_bwd(const float* logits, int64_t stride_b
     }
     if (s != NSP_OK) return s;
 
-    // ---- K2 ----
-    {
+    // ---- K2 / K3 ----
+    const int Smax = 2 * Lmax + 1;
+    if (Smax <= 512 && Lmax <= 256) {
+        const int k = ceil_div(Smax, 32);
+        if (k <= 1) ctc_lattice_warp_kernel<1><<<B, 64, 0, st>>>(p);
+        else if (k <= 2) ctc_lattice_warp_kernel<2><<<B, 64, 0, st>>>(p);
+        else if (k <= 4) ctc_lattice_warp_kernel<4><<<B, 64, 0, st>>>(p);
+        else if (k <= 8) ctc_lattice_warp_kernel<8><<<B, 64, 0, st>>>(p);
+        else ctc_lattice_warp_kernel<16><<<B, 64, 0, st>>>(p);
+        NSP_LAUNCH_OK();
+        ctc_fixup_kernel<<<(unsigned)(ceil_div64((int64_t)bt, 8) + 1), 256, 0, st>>>(p);
+        NSP_LAUNCH_OK();
+        return NSP_OK;
+    }
+    {   // very long label sequences: block-per-utterance lattice with the fix-up fused in
         const int S = p.Sp;
         int spt = 1, half = (int)align_up((size_t)S, 32);
         if (half > 512) { spt = 2; half = (int)align_up((size_t)ceil_div(S, 2), 32); }
