@@ -211,13 +211,30 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
                 if (jj >= a.Tk) s = -INFINITY;
                 return s;
             };
+            // warp-uniform fast path per 32-key chunk: every key visible to every row of this warp and the whole chunk
+            // outside the clamped band -> score = raw * scale + const (one FFMA), no per-element mask / gather logic
+            const int iw0 = i0 + q * 32, iw1 = iw0 + 31;
+            const float bdfs = bd_far * a.scale_log2;
+            auto chunk_fast = [&](int c) -> bool {
+                const int jc0 = j0 + c, jc1 = jc0 + 31;
+                const bool vis = (jc1 < klen) && !a.causal && (a.chunk_c == 0);
+                const bool far = !a.has_rel || (jc1 <= mlen + iw0 - clamp) || (jc0 >= mlen + iw1 + clamp);
+                return vis && far;
+            };
 #pragma unroll 1
             for (int c = 0; c < KT; c += 32) {
                 uint32_t r[32];
                 tc::tmem_ld_32x32(tm_S + lane_addr + (uint32_t)c, r);
                 tc::tmem_ld_wait();
+                if (chunk_fast(c)) {
+                    float mr = -FLT_MAX;
 #pragma unroll
-                for (int e = 0; e < 32; ++e) mx = fmaxf(mx, score(__uint_as_float(r[e]), j0 + c + e));
+                    for (int e = 0; e < 32; ++e) mr = fmaxf(mr, __uint_as_float(r[e]));
+                    mx = fmaxf(mx, fmaf(mr, a.scale_log2, bdfs));
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) mx = fmaxf(mx, score(__uint_as_float(r[e]), j0 + c + e));
+                }
             }
             const float m_new = fmaxf(m_run, mx);
             const float corr = ex2(m_run - m_new);
@@ -229,16 +246,28 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
                 tc::tmem_ld_32x32(tm_S + lane_addr + (uint32_t)c, r);
                 tc::tmem_ld_wait();
                 uint32_t pk[16];
+                if (chunk_fast(c)) {
+                    const float off = bdfs - m_new;
 #pragma unroll
-                for (int e = 0; e < 32; e += 2) {
-                    float s0 = score(__uint_as_float(r[e]), j0 + c + e);
-                    float s1 = score(__uint_as_float(r[e + 1]), j0 + c + e + 1);
-                    float p0 = (s0 == -INFINITY) ? 0.f : ex2(s0 - m_new);
-                    float p1 = (s1 == -INFINITY) ? 0.f : ex2(s1 - m_new);
-                    __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-                    // accumulate the row sum from the ROUNDED probabilities so that P V and l stay consistent
-                    rsum += __bfloat162float(pb.x) + __bfloat162float(pb.y);
-                    pk[e >> 1] = *reinterpret_cast<uint32_t*>(&pb);
+                    for (int e = 0; e < 32; e += 2) {
+                        float p0 = ex2(fmaf(__uint_as_float(r[e]), a.scale_log2, off));
+                        float p1 = ex2(fmaf(__uint_as_float(r[e + 1]), a.scale_log2, off));
+                        __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+                        rsum += __bfloat162float(pb.x) + __bfloat162float(pb.y);
+                        pk[e >> 1] = *reinterpret_cast<uint32_t*>(&pb);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; e += 2) {
+                        float s0 = score(__uint_as_float(r[e]), j0 + c + e);
+                        float s1 = score(__uint_as_float(r[e + 1]), j0 + c + e + 1);
+                        float p0 = (s0 == -INFINITY) ? 0.f : ex2(s0 - m_new);
+                        float p1 = (s1 == -INFINITY) ? 0.f : ex2(s1 - m_new);
+                        __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+                        // accumulate the row sum from the ROUNDED probabilities so that P V and l stay consistent
+                        rsum += __bfloat162float(pb.x) + __bfloat162float(pb.y);
+                        pk[e >> 1] = *reinterpret_cast<uint32_t*>(&pb);
+                    }
                 }
                 uint8_t* half = sP + (c >> 6) * TILE_BYTES + row * 128;
 #pragma unroll

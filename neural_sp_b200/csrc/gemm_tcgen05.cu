@@ -419,8 +419,10 @@ nsp_status gemm_dispatch(int precision, const void* a, const void* a_lo, int64_t
     NSP_CHECK_ARG(!(out2 && out_bf16), "gemm: out2 is only meaningful with an fp32 primary output");
     const int nout = glu ? N / 2 : N;
     // tile width: 128 unless the problem is too small to fill the machine, then 64 (GLU always 128 = 64 value + 64 gate)
+    // 256 for wide outputs: halves the A re-reads per FLOP (the kernel is L2->SMEM bound, profiles/r01_gemm.md)
     int BN = 128;
     if (!glu && (int64_t)ceil_div(M, BM) * ceil_div(nout, 128) < num_sms() && nout > 64) BN = 64;
+    else if (!glu && nout % 256 == 0 && (int64_t)ceil_div(M, BM) * (nout / 256) >= 3 * (int64_t)num_sms()) BN = 256;
     const uint32_t box_b = glu ? (uint32_t)(BN / 2) : (uint32_t)BN;
     const void* as[3] = {a, a_lo, a};
     const void* ws[3] = {w, w, w_lo};
@@ -428,8 +430,12 @@ nsp_status gemm_dispatch(int precision, const void* a, const void* a_lo, int64_t
         if (!make_tmap_2d(&maps.a[s], as[s], es, bf16, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM)) return NSP_ERR_INVALID;
         if (!make_tmap_2d(&maps.b[s], ws[s], es, bf16, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, box_b)) return NSP_ERR_INVALID;
     }
-    if (bf16) return BN == 128 ? dispatch_epi<__nv_bfloat16, 128>(maps, g, glu, act, out_bf16, st)
-                               : dispatch_epi<__nv_bfloat16, 64>(maps, g, glu, act, out_bf16, st);
+    if (bf16) {
+        if (BN == 256) return dispatch_epi<__nv_bfloat16, 256>(maps, g, glu, act, out_bf16, st);
+        return BN == 128 ? dispatch_epi<__nv_bfloat16, 128>(maps, g, glu, act, out_bf16, st)
+                         : dispatch_epi<__nv_bfloat16, 64>(maps, g, glu, act, out_bf16, st);
+    }
+    if (BN == 256) return dispatch_epi<float, 256>(maps, g, glu, act, out_bf16, st);
     return BN == 128 ? dispatch_epi<float, 128>(maps, g, glu, act, out_bf16, st)
                      : dispatch_epi<float, 64>(maps, g, glu, act, out_bf16, st);
 }

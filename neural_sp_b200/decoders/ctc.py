@@ -19,6 +19,11 @@ from .. import ops
 from ..modules.linear import Linear
 
 
+def _lens_dev(elens, device):
+    from ..encoders.transformer import lens_to_device
+    return lens_to_device(elens, device)
+
+
 class _CTCLossFn(torch.autograd.Function):
     """loss = (1-lsm) * sum_b nll_b / B + lsm * KL ; gradient produced by the same kernels."""
 
@@ -104,7 +109,7 @@ class CTC(nn.Module):
         """
         ys_dir = [list(y[::-1]) if self.bwd else list(y) for y in ys]
         labels, ylens_d, _ = ops.pack_labels(ys_dir, eouts.device)
-        elens_d = elens.to(device=eouts.device, dtype=torch.int32, non_blocking=True)
+        elens_d = _lens_dev(elens, eouts.device)      # cached pinned copy: no sync, CUDA-graph safe
 
         logits = self.output(eouts)   # `[B, T, vocab]`
         loss, _ = ctc_loss(logits.float(), labels, elens_d, ylens_d, self.blank, self.lsm_prob)

@@ -65,11 +65,18 @@ class RelativeMultiheadAttentionMechanism(nn.Module):
         if klen != qlen:
             q = q.contiguous()
         k, v = qkv[:, :, D:2 * D], qkv[:, :, 2 * D:]
-        # projected position table; only distances 0..clamp_len are ever gathered when clamp_len > 0
+        # projected position table; only distances 0..clamp_len are ever gathered when clamp_len > 0.
+        # The sinusoid rows are constants, so R depends only on the projection weight: cached per weight version.
         nrows = min(klen, self.clamp_len + 1) if self.clamp_len > 0 else klen
         wp_lin = self.w_pos if self.xl_like else self.w_value
-        wp = prepared(self, "pos", prec, (wp_lin.weight,))
-        r = ops.linear(pos_embs[:nrows], wp, wp_lin.bias, prec=prec, out_dtype=act_dtype(prec))   # `[nrows, D]`
+        ckey = (prec, nrows, wp_lin.weight.data_ptr(), wp_lin.weight._version, pos_embs.data_ptr())
+        cached = self.__dict__.get("_r_cache")
+        if cached is not None and cached[0] == ckey:
+            r = cached[1]
+        else:
+            wp = prepared(self, "pos", prec, (wp_lin.weight,))
+            r = ops.linear(pos_embs[:nrows], wp, wp_lin.bias, prec=prec, out_dtype=act_dtype(prec))   # `[nrows, D]`
+            self.__dict__["_r_cache"] = (ckey, r)
         cv = ops.relpos_attention(q, k, v, klens, self.n_heads, r=r, u_bias=u_bias, v_bias=v_bias,
                                   clamp_len=self.clamp_len, causal=causal, lookahead=lookahead,
                                   chunk_c=chunk_c, chunk_l=chunk_l)
