@@ -45,7 +45,7 @@ struct CtcParams {
     float* nll_raw;    // [B] un-zeroed nll (>= 1e29 when infeasible)
     int16_t* nxt;      // [B,Sp] next state carrying the same label (-1: none)
     int16_t* head;     // [B,Sp] 1 if first occurrence of its label in the path
-    int Sp;            // lattice row pitch (2*Lmax+1 rounded up to a multiple of 4)
+    int Sp;            // lattice row pitch (2*Lmax+1 rounded up to a multiple of 16)
 };
 
 template <int G>
@@ -695,7 +695,7 @@ using namespace nsp;
 
 extern "C" size_t nsp_ctc_loss_workspace_bytes(int B, int T, int Lmax) {
     if (B <= 0 || T <= 0 || Lmax < 0) return 0;
-    size_t Sp = align_up(2 * (size_t)Lmax + 1, 4);
+    size_t Sp = align_up(2 * (size_t)Lmax + 1, 16);
     size_t bt = (size_t)B * T;
     return align_up(3 * bt * Sp * sizeof(float), 256) + 3 * align_up(bt * sizeof(float), 256) +
            align_up((size_t)B * sizeof(float), 256) + 2 * align_up((size_t)B * Sp * sizeof(int16_t), 256) + 256;
@@ -721,7 +721,8 @@ extern "C" nsp_status nsp_ctc_loss_fwd_bwd(const float* logits, int64_t stride_b
     p.logits = logits; p.sb = stride_b; p.st = stride_t; p.B = B; p.T = T; p.V = V;
     p.labels = labels; p.Lmax = Lmax; p.elens = elens; p.ylens = ylens;
     p.blank = blank; p.lsm = lsm_prob; p.nll = nll; p.loss = loss; p.grad = grad;
-    p.Sp = (int)align_up((size_t)(2 * Lmax + 1), 4);
+    // pitch is a multiple of 16 states: a lane's K-wide (K <= 16) vector access never crosses into the next row
+    p.Sp = (int)align_up((size_t)(2 * Lmax + 1), 16);
     const size_t bt = (size_t)B * T;
     char* w = (char*)workspace;
     const size_t lat = bt * p.Sp * sizeof(float);

@@ -15,7 +15,7 @@ ws = torch.zeros(n, dtype=torch.uint8, device="cuda")
 nll = torch.empty(B, device="cuda"); loss = torch.empty((), device="cuda"); grad = torch.empty(B, T, V, device="cuda")
 check(lib.nsp_ctc_loss_fwd_bwd(ptr(logits), T * V, V, B, T, V, ptr(labels), L, ptr(elens), ptr(ylens), 0, 0.0, ptr(nll), ptr(loss), ptr(grad), ptr(ws), n, current_stream_ptr()))
 torch.cuda.synchronize()
-Sp = (2 * L + 1 + 3) // 4 * 4
+Sp = (2 * L + 1 + 15) // 16 * 16
 lat = B * T * Sp
 f = ws.view(torch.float32)
 emit = f[:lat].view(T, Sp).cpu().numpy(); alpha = f[lat:2 * lat].view(T, Sp).cpu().numpy(); beta = f[2 * lat:3 * lat].view(T, Sp).cpu().numpy()
