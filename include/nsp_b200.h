@@ -174,6 +174,9 @@ nsp_status nsp_conv3x3_relu_fwd(int in_bf16, int out_bf16, const void* x, int in
 nsp_status nsp_maxpool2d_fwd(int in_bf16, int out_bf16, const void* x, void* y, int B, int T, int F, int C,
                              int pool_t, int pool_f, int f_keep, int out_chmajor, void* stream);
 nsp_status nsp_maxpool_time_fwd(int is_bf16, const void* x, void* y, int B, int T, int D, int factor, void* stream);
+/* Same with mode: 0 max, 1 mean of the in-range frames (MeanPoolSubsampler subsampling.py:212-246), 2 first frame
+ * (DropSubsampler :97-126), 3 sum (AddSubsampler :129-172). */
+nsp_status nsp_pool_time_fwd(int is_bf16, const void* x, void* y, int B, int T, int D, int factor, int mode, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * RNN-Transducer loss, forward + backward (HBM-bound; fp32), blank-first lattice.
@@ -195,6 +198,19 @@ nsp_status nsp_rnnt_loss_fwd_bwd(const float* log_probs, int B, int T, int U1, i
  * (ky*3+kx)*32 + ci; y bf16 [B,T,F,32] or [B,ceil(T/2),ceil(F/2),32] when pool2x2. */
 nsp_status nsp_conv3x3_c32_tc_fwd(const void* x, const void* w_taps, const float* bias, void* y,
                                   int B, int T, int F, int relu, int pool2x2, void* stream);
+
+/* Row-wise softmax (log_mode=0) or log-softmax (log_mode=1) of x / temperature, fp32 [rows, V]; y may alias x.
+ * Replaces CTC.probs / CTC.scores decoders/ctc.py:197-217 and torch.log_softmax at decoders/rnn_transducer.py:242. */
+nsp_status nsp_softmax_rows(const float* x, float* y, int64_t rows, int V, int log_mode, float temperature, void* stream);
+/* Greedy CTC path: best[b,t] = argmax_v logits[b,t,v] (first max); hyp[b,:hyp_lens[b]] = collapsed non-blank labels of
+ * frames t < elens[b]; trigger[b,n] = first frame of the n-th non-blank run.  All int32; hyp/trigger are [B,T].
+ * Replaces CTC.greedy decoders/ctc.py:219-243 and CTC.trigger_points decoders/ctc.py:152-195. */
+nsp_status nsp_ctc_greedy(const float* logits, int B, int T, int V, const int32_t* elens, int blank,
+                          int32_t* best, int32_t* hyp, int32_t* hyp_lens, int32_t* trigger, void* stream);
+/* RNN-T joint pre-activation out[b,t,u,:] = tanh(enc[b,t,:] + dec[b,u,:]) (decoders/rnn_transducer.py:272-275);
+ * enc fp32 [B,T,J], dec fp32 [B,U1,J], out fp32 or bf16 [B,T,U1,J]; J % 4 == 0. */
+nsp_status nsp_rnnt_joint_tanh(const float* enc, const float* dec, void* out, int out_bf16, int B, int T, int U1,
+                               int J, void* stream);
 
 #ifdef __cplusplus
 }

@@ -119,3 +119,21 @@ for _name, (_res, _args) in _more.items():
     _fn.restype = _res
     _fn.argtypes = _args
 SIGNATURES.update(_more)
+
+_more = {
+    "nsp_softmax_rows": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_f32, c_vp]),
+    "nsp_ctc_greedy": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "nsp_rnnt_joint_tanh": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
+}
+for _name, (_res, _args) in _more.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+SIGNATURES.update(_more)
+
+_more = {"nsp_pool_time_fwd": (c_int, [c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp])}
+for _name, (_res, _args) in _more.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+SIGNATURES.update(_more)

@@ -107,3 +107,41 @@ extern "C" nsp_status nsp_xl_pos_table(const float* inv_freq, float* table, int 
     NSP_LAUNCH_OK();
     return NSP_OK;
 }
+
+// RNN-T joint pre-activation (decoders/rnn_transducer.py:272-275): out[b,t,u,:] = tanh(enc[b,t,:] + dec[b,u,:])
+namespace nsp {
+namespace {
+template <typename TO>
+__global__ void __launch_bounds__(256) joint_tanh_kernel(const float* __restrict__ enc, const float* __restrict__ dec,
+                                                         TO* __restrict__ out, int B, int T, int U1, int J) {
+    const int64_t n4 = (int64_t)B * T * U1 * (J / 4);
+    for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < n4; e += (int64_t)gridDim.x * 256) {
+        const int j4 = (int)(e % (J / 4));
+        int64_t r = e / (J / 4);
+        const int u = (int)(r % U1); r /= U1;
+        const int t = (int)(r % T);
+        const int b = (int)(r / T);
+        const float4 a = __ldg(reinterpret_cast<const float4*>(enc + ((int64_t)b * T + t) * J) + j4);
+        const float4 d = __ldg(reinterpret_cast<const float4*>(dec + ((int64_t)b * U1 + u) * J) + j4);
+        float v0 = tanhf(a.x + d.x), v1 = tanhf(a.y + d.y), v2 = tanhf(a.z + d.z), v3 = tanhf(a.w + d.w);
+        if constexpr (sizeof(TO) == 4) {
+            reinterpret_cast<float4*>(out)[e] = make_float4(v0, v1, v2, v3);
+        } else {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v0, v1), p1 = __floats2bfloat162_rn(v2, v3);
+            uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+            reinterpret_cast<uint2*>(out)[e] = pk;
+        }
+    }
+}
+}  // namespace
+}  // namespace nsp
+
+extern "C" nsp_status nsp_rnnt_joint_tanh(const float* enc, const float* dec, void* out, int out_bf16, int B, int T, int U1,
+                                          int J, void* stream) {
+    NSP_CHECK_ARG(enc && dec && out && B > 0 && T > 0 && U1 > 0 && J > 0 && J % 4 == 0, "rnnt_joint_tanh: bad arguments");
+    const int64_t n4 = (int64_t)B * T * U1 * (J / 4);
+    if (out_bf16) nsp::joint_tanh_kernel<__nv_bfloat16><<<ew_grid(n4), 256, 0, (cudaStream_t)stream>>>(enc, dec, (__nv_bfloat16*)out, B, T, U1, J);
+    else nsp::joint_tanh_kernel<float><<<ew_grid(n4), 256, 0, (cudaStream_t)stream>>>(enc, dec, (float*)out, B, T, U1, J);
+    NSP_LAUNCH_OK();
+    return NSP_OK;
+}

@@ -142,20 +142,28 @@ __global__ void __launch_bounds__(256) maxpool_kernel(PoolParams p) {
     }
 }
 
-// 1-D max-pool over time on [B, T, D] rows (MaxPoolSubsampler, subsampling.py:175-209; ceil_mode=True)
+// 1-D pooling over time on [B, T, D] rows, kernel = stride = factor, ceil_mode (windows clipped at T):
+// mode 0 max (MaxPoolSubsampler subsampling.py:175-209), 1 mean over the in-range frames (MeanPoolSubsampler :212-246),
+// 2 first frame (DropSubsampler :97-126), 3 sum (AddSubsampler :129-172)
 template <typename T>
-__global__ void __launch_bounds__(256) maxpool_time_kernel(const T* x, T* y, int B, int Tin, int Tout, int D, int factor) {
+__global__ void __launch_bounds__(256) pool_time_kernel(const T* x, T* y, int B, int Tin, int Tout, int D, int factor, int mode) {
     const int64_t n = (int64_t)B * Tout * D;
     for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < n; e += (int64_t)gridDim.x * 256) {
         int c = (int)(e % D);
         int64_t r = e / D;
         int to = (int)(r % Tout), b = (int)(r / Tout);
-        float m = -INFINITY;
+        float m = (mode == 0) ? -INFINITY : 0.f;
+        int cnt = 0;
         for (int dt = 0; dt < factor; ++dt) {
             int t = to * factor + dt;
             if (t >= Tin) break;
-            m = fmaxf(m, fe_ld<T>(x + ((int64_t)b * Tin + t) * D + c));
+            float v = fe_ld<T>(x + ((int64_t)b * Tin + t) * D + c);
+            if (mode == 0) m = fmaxf(m, v);
+            else if (mode == 2) { if (dt == 0) m = v; }
+            else m += v;
+            ++cnt;
         }
+        if (mode == 1) m /= (float)cnt;
         fe_st<T>(y + e, m);
     }
 }
@@ -220,13 +228,17 @@ extern "C" nsp_status nsp_maxpool2d_fwd(int in_bf16, int out_bf16, const void* x
     return NSP_OK;
 }
 
-extern "C" nsp_status nsp_maxpool_time_fwd(int is_bf16, const void* x, void* y, int B, int T, int D, int factor, void* stream) {
-    NSP_CHECK_ARG(x && y && B > 0 && T > 0 && D > 0 && factor > 0, "maxpool_time: bad arguments");
+extern "C" nsp_status nsp_pool_time_fwd(int is_bf16, const void* x, void* y, int B, int T, int D, int factor, int mode, void* stream) {
+    NSP_CHECK_ARG(x && y && B > 0 && T > 0 && D > 0 && factor > 0 && mode >= 0 && mode <= 3, "pool_time: bad arguments");
     const int To = ceil_div(T, factor);
     const int64_t n = (int64_t)B * To * D;
     cudaStream_t st = (cudaStream_t)stream;
-    if (is_bf16) maxpool_time_kernel<__nv_bfloat16><<<fe_grid(n), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, B, T, To, D, factor);
-    else maxpool_time_kernel<float><<<fe_grid(n), 256, 0, st>>>((const float*)x, (float*)y, B, T, To, D, factor);
+    if (is_bf16) pool_time_kernel<__nv_bfloat16><<<fe_grid(n), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, B, T, To, D, factor, mode);
+    else pool_time_kernel<float><<<fe_grid(n), 256, 0, st>>>((const float*)x, (float*)y, B, T, To, D, factor, mode);
     NSP_LAUNCH_OK();
     return NSP_OK;
+}
+
+extern "C" nsp_status nsp_maxpool_time_fwd(int is_bf16, const void* x, void* y, int B, int T, int D, int factor, void* stream) {
+    return nsp_pool_time_fwd(is_bf16, x, y, B, T, D, factor, 0, stream);
 }

@@ -233,18 +233,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
             const int col0 = n_blk * BN_OUT + half * COLS_PER_WARP;
             constexpr int CW = COLS_PER_WARP >= 32 ? 32 : 16;   // columns per chunk
-#pragma unroll 1
-            for (int c = 0; c < COLS_PER_WARP; c += CW) {
+            constexpr int NCH = COLS_PER_WARP / CW;
+            // software pipeline over the chunks: the TMEM load of chunk c+1 is in flight while chunk c is processed
+            uint32_t rbuf[2][32];
+            if constexpr (CW == 32) tc::tmem_ld_32x32(t_row + (uint32_t)(half * COLS_PER_WARP), rbuf[0]);
+            else tc::tmem_ld_32x16(t_row + (uint32_t)(half * COLS_PER_WARP), rbuf[0]);
+#pragma unroll
+            for (int ci = 0; ci < NCH; ++ci) {
+                const int c = ci * CW;
                 float v[32];
                 const int cbase = col0 + c;
                 const int tcol = half * COLS_PER_WARP + c;      // column inside the accumulator (value part)
-                {
-                    uint32_t r[32];
-                    if constexpr (CW == 32) tc::tmem_ld_32x32(t_row + (uint32_t)tcol, r);
-                    else tc::tmem_ld_32x16(t_row + (uint32_t)tcol, r);
-                    tc::tmem_ld_wait();
+                tc::tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(r[j]);
+                for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(rbuf[ci & 1][j]);
+                if (ci + 1 < NCH) {
+                    if constexpr (CW == 32) tc::tmem_ld_32x32(t_row + (uint32_t)(tcol + CW), rbuf[(ci + 1) & 1]);
+                    else tc::tmem_ld_32x16(t_row + (uint32_t)(tcol + CW), rbuf[(ci + 1) & 1]);
                 }
                 const bool full = (cbase + CW <= nout);
                 if (has_bias) {

@@ -125,6 +125,39 @@ class CTC(nn.Module):
             self.prob_dict['probs'] = torch.softmax(logits.detach(), dim=-1).cpu().numpy()
         return loss, trigger_points
 
+    def probs(self, eouts, temperature=1.):
+        """CTC probabilities `[B, T, vocab]` (reference ctc.py:197-206)."""
+        with torch.no_grad():
+            return ops.softmax_rows(self.output(eouts).float(), log=False, temperature=temperature)
+
+    def scores(self, eouts, temperature=1.):
+        """Log-scale CTC probabilities `[B, T, vocab]` (reference ctc.py:208-217)."""
+        with torch.no_grad():
+            return ops.softmax_rows(self.output(eouts).float(), log=True, temperature=temperature)
+
+    def _greedy_device(self, eouts, elens):
+        with torch.no_grad():
+            logits = self.output(eouts).float()
+            elens_d = _lens_dev(torch.as_tensor(np.asarray(elens), dtype=torch.int32), eouts.device)
+            return ops.ctc_greedy(logits, elens_d, self.blank)
+
+    def greedy(self, eouts, elens):
+        """Greedy decoding (reference ctc.py:219-243): argmax path, repeats collapsed, blanks removed.
+        Returns ``[[hyp_b]]`` per utterance like the reference."""
+        _, hyp, hyp_lens, _ = self._greedy_device(eouts, elens)
+        hyp, hyp_lens = hyp.cpu().numpy(), hyp_lens.cpu().numpy()
+        return [[hyp[b, :hyp_lens[b]].tolist()] for b in range(eouts.size(0))]
+
+    def trigger_points(self, eouts, elens):
+        """Trigger points of the greedy path (reference ctc.py:152-195): IntTensor `[B, Lmax+1]`."""
+        _, _, hyp_lens, trig = self._greedy_device(eouts, elens)
+        ymax = int(hyp_lens.max().item())
+        out = torch.zeros(eouts.size(0), ymax + 1, dtype=torch.int32, device=eouts.device)
+        if ymax > 0:
+            mask = torch.arange(ymax, device=eouts.device)[None, :] < hyp_lens[:, None]
+            out[:, :ymax] = torch.where(mask, trig[:, :ymax], torch.zeros_like(trig[:, :ymax]))
+        return out
+
     def loss_fn(self, logits, ys_ctc, elens, ylens):
         """Reference op boundary (ctc.py:139-150): logits `[T, B, vocab]`, concatenated int32 targets."""
         ylens_l = [int(v) for v in ylens]

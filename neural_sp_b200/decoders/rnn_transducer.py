@@ -1,0 +1,126 @@
+"""RNN-Transducer decoder, training path (reference decoders/rnn_transducer.py:32-311), B200-native.
+
+Same constructor and parameter names (``rnn.N``, ``embed``, ``w_enc``, ``w_dec``, ``output``, ``ctc.*``).
+``forward`` / ``forward_transducer`` compute the loss value: prediction network (embedding + stacked nn.LSTM, kept
+as plain torch -- SURVEY.md section 2 row 4), joint network on the library's kernels (two GEMMs, fused add+tanh,
+vocabulary GEMM, row log-softmax) and the RNN-T lattice kernel, which also yields d loss / d log_probs.
+Beam search (:419-819) is out of scope."""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..modules._prep import prepared, get_precision, act_dtype
+from .ctc import CTC, _lens_dev
+
+
+class RNNTransducer(nn.Module):
+    def __init__(self, special_symbols, enc_n_units, n_units, n_projs, n_layers, bottleneck_dim, emb_dim, vocab,
+                 dropout, dropout_emb, ctc_weight, ctc_lsm_prob, ctc_fc_list, external_lm, global_weight,
+                 mtl_per_batch, param_init):
+        super().__init__()
+        self.eos = special_symbols['eos']
+        self.unk = special_symbols['unk']
+        self.pad = special_symbols['pad']
+        self.blank = special_symbols['blank']
+        self.vocab = vocab
+        self.enc_n_units = enc_n_units
+        self.dec_n_units = n_units
+        self.n_projs = n_projs
+        self.n_layers = n_layers
+        self.rnnt_weight = global_weight - ctc_weight
+        self.ctc_weight = ctc_weight
+        self.mtl_per_batch = mtl_per_batch
+        self.prev_spk = ''
+        self.lmstate_final = None
+        self.embed_cache = None
+        if external_lm is not None:
+            raise NotImplementedError("LM initialisation of the prediction network is out of scope")
+        if ctc_weight > 0:
+            self.ctc = CTC(eos=self.eos, blank=self.blank, enc_n_units=enc_n_units, vocab=vocab, dropout=dropout,
+                           lsm_prob=ctc_lsm_prob, fc_list=ctc_fc_list, param_init=0.1)
+        if self.rnnt_weight > 0:
+            self.rnn = nn.ModuleList()
+            dec_odim = emb_dim
+            self.proj = nn.ModuleList([nn.Linear(n_units, n_projs) for _ in range(n_layers)]) if n_projs > 0 else None
+            self.dropout = nn.Dropout(p=dropout)
+            for _ in range(n_layers):
+                self.rnn += [nn.LSTM(dec_odim, n_units, 1, batch_first=True)]
+                dec_odim = n_projs if n_projs > 0 else n_units
+            self.embed = nn.Embedding(vocab, emb_dim, padding_idx=self.pad)
+            self.dropout_emb = nn.Dropout(p=dropout_emb)
+            self.w_enc = nn.Linear(enc_n_units, bottleneck_dim)
+            self.w_dec = nn.Linear(dec_odim, bottleneck_dim, bias=False)
+            self.output = nn.Linear(bottleneck_dim, vocab)
+        for n, p in self.named_parameters():       # reference :161-172: uniform(-param_init, param_init), biases 0
+            if 'ctc.' in n:
+                continue
+            if p.dim() == 1:
+                nn.init.constant_(p, 0.)
+            else:
+                nn.init.uniform_(p, a=-param_init, b=param_init)
+
+    def set_precision(self, precision):
+        for m in self.modules():
+            m.precision = precision
+        return self
+
+    def recurrency(self, ys_emb):
+        """Prediction network (reference :278-311); plain torch (cuDNN LSTM), no state carried in training."""
+        out = ys_emb
+        for lth in range(self.n_layers):
+            out, _ = self.rnn[lth](out)
+            out = self.dropout(out)
+            if self.proj is not None:
+                out = torch.relu(self.proj[lth](out))
+        return out
+
+    def joint(self, eouts, dout):
+        """log_probs `[B, T, U+1, vocab]` = log_softmax(output(tanh(w_enc(e)[:, :, None] + w_dec(d)[:, None]))) (:262-276, :242)."""
+        prec = get_precision(self)
+        B, T, _ = eouts.shape
+        U1 = dout.shape[1]
+        e = ops.linear(eouts, prepared(self, "w_enc", prec, (self.w_enc.weight,)), self.w_enc.bias, prec=prec)
+        d = ops.linear(dout, prepared(self, "w_dec", prec, (self.w_dec.weight,)), None, prec=prec)
+        h = ops.rnnt_joint_tanh(e, d, out_dtype=act_dtype(prec))
+        logits = ops.linear(h.view(B * T * U1, -1), prepared(self, "output", prec, (self.output.weight,)),
+                            self.output.bias, prec=prec, out_dtype=torch.float32)
+        return ops.softmax_rows(logits.view(B, T, U1, self.vocab), log=True, inplace=True)
+
+    def forward_transducer(self, eouts, elens, ys):
+        """RNN-T loss (reference :217-260): mean over the batch of -log p(y|x); returns a `[1]` tensor."""
+        device = eouts.device
+        B = len(ys)
+        ylens = [len(y) for y in ys]
+        U = max(ylens) if ylens else 0
+        ys_in = torch.full((B, U + 1), self.pad, dtype=torch.long)
+        ys_out = torch.zeros((B, max(U, 1)), dtype=torch.int32)
+        for b, y in enumerate(ys):
+            ys_in[b, 0] = self.eos
+            if len(y):
+                ys_in[b, 1:len(y) + 1] = torch.as_tensor(list(y), dtype=torch.long)
+                ys_out[b, :len(y)] = torch.as_tensor(list(y), dtype=torch.int32)
+        with torch.no_grad():
+            dout = self.recurrency(self.dropout_emb(self.embed(ys_in.to(device))))
+            log_probs = self.joint(eouts.float(), dout.float())
+            flens = _lens_dev(elens, device)
+            ylens_d = _lens_dev(torch.tensor(ylens, dtype=torch.int32), device)
+            labels = ys_out[:, :U].contiguous().to(device) if U > 0 else torch.zeros(B, 0, dtype=torch.int32, device=device)
+            loss, nll, grad = ops.rnnt_loss_fwd_bwd(log_probs, labels, flens, ylens_d, self.blank, need_grad=True)
+        self._grad_log_probs = grad            # d loss / d log_probs, kept for callers that chain the backward by hand
+        return loss.reshape(1)
+
+    def forward(self, eouts, elens, ys, task='all', teacher_logits=None, recog_params={}, idx2token=None, trigger_points=None):
+        """Reference :174-215: total loss = ctc_weight * CTC + rnnt_weight * RNN-T; observation dict of floats."""
+        observation = {'loss': None, 'loss_transducer': None, 'loss_ctc': None, 'loss_mbr': None}
+        loss = eouts.new_zeros((1,))
+        if self.ctc_weight > 0 and (task == 'all' or 'ctc' in task):
+            loss_ctc, _ = self.ctc(eouts, elens, ys)
+            observation['loss_ctc'] = float(loss_ctc.detach())
+            loss = loss + (loss_ctc * (1 if self.mtl_per_batch else self.ctc_weight)).reshape(1)
+        if self.rnnt_weight > 0 and (task == 'all' or 'ctc' not in task):
+            loss_t = self.forward_transducer(eouts, elens, ys)
+            observation['loss_transducer'] = float(loss_t.detach())
+            loss = loss + loss_t * (1 if self.mtl_per_batch else self.rnnt_weight)
+        observation['loss'] = float(loss.detach())
+        return loss, observation

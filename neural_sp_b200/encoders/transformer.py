@@ -18,7 +18,8 @@ from .. import ops
 from ..modules._prep import prepared, get_precision
 from ..modules.positional_embedding import XLPositionalEmbedding
 from .encoder_base import EncoderBase
-from .subsampling import MaxPoolSubsampler
+from .subsampling import (AddSubsampler, ConcatSubsampler, Conv1dSubsampler, DropSubsampler, MaxPoolSubsampler,
+                          MeanPoolSubsampler)
 from .transformer_block import TransformerEncoderBlock
 
 
@@ -95,9 +96,15 @@ class TransformerEncoder(EncoderBase):
         self.subsample_layers = None
         if np.prod(self.subsample_factors) > 1:
             self._factor *= int(np.prod(self.subsample_factors))
-            if subsample_type != 'max_pool':
-                raise NotImplementedError("subsample_type=%r is not on the B200 path (max_pool is)" % subsample_type)
-            self.subsample_layers = nn.ModuleList([MaxPoolSubsampler(f) for f in self.subsample_factors])
+            odim = self._odim
+            make = {'max_pool': MaxPoolSubsampler, 'mean_pool': MeanPoolSubsampler, 'drop': DropSubsampler,
+                    'add': AddSubsampler, 'concat': lambda f: ConcatSubsampler(f, odim),
+                    'conv1d': lambda f: Conv1dSubsampler(f, odim)}
+            if subsample_type not in make:
+                raise NotImplementedError(subsample_type)
+            if subsample_type == 'conv1d':
+                assert not self.causal
+            self.subsample_layers = nn.ModuleList([make[subsample_type](f) for f in self.subsample_factors])
 
         self.pos_enc, self.pos_emb = None, None
         self.u_bias, self.v_bias = None, None

@@ -393,3 +393,59 @@ def conv3x3_c32_tc(x, w_taps, bias, relu=True, pool2x2=False):
     _run("nsp_conv3x3_c32_tc_fwd", lib.nsp_conv3x3_c32_tc_fwd, ptr(x), ptr(w_taps), ptr(bias), ptr(y), B, T, F,
          int(relu), int(pool2x2), current_stream_ptr(), flops=2.0 * B * T * F * 32 * 288, tag="conv3x3_tc")
     return y
+
+
+# ---------------------------------------------------------------------------------------------
+# softmax rows, greedy CTC, RNN-T joint
+# ---------------------------------------------------------------------------------------------
+KERNELS_PER_CALL["nsp_ctc_greedy"] = 2
+
+
+def softmax_rows(x, log=False, temperature=1.0, inplace=False):
+    """(log-)softmax over the last dim of an fp32 tensor (nsp_softmax_rows)."""
+    _require_cuda(x)
+    x = x.contiguous()
+    assert x.dtype == torch.float32
+    V = x.shape[-1]
+    y = x if inplace else torch.empty_like(x)
+    _run("nsp_softmax_rows", lib.nsp_softmax_rows, ptr(x), ptr(y), x.numel() // V, V, int(log), float(temperature),
+         current_stream_ptr(), nbytes=8.0 * x.numel())
+    return y
+
+
+def ctc_greedy(logits, elens, blank=0):
+    """Greedy CTC path on the device (nsp_ctc_greedy) -> (best [B,T], hyp [B,T], hyp_lens [B], trigger [B,T]) int32."""
+    _require_cuda(logits, elens)
+    logits = logits.contiguous().float()
+    B, T, V = logits.shape
+    mk = lambda *s: torch.zeros(*s, dtype=torch.int32, device=logits.device)   # noqa: E731
+    best, hyp, hyp_lens, trig = mk(B, T), mk(B, T), mk(B), mk(B, T)
+    _run("nsp_ctc_greedy", lib.nsp_ctc_greedy, ptr(logits), B, T, V, ptr(elens), int(blank), ptr(best), ptr(hyp),
+         ptr(hyp_lens), ptr(trig), current_stream_ptr())
+    return best, hyp, hyp_lens, trig
+
+
+def rnnt_joint_tanh(enc, dec, out_dtype=torch.float32):
+    """tanh(enc[:, :, None] + dec[:, None]) (nsp_rnnt_joint_tanh): enc `[B,T,J]`, dec `[B,U1,J]` fp32 -> `[B,T,U1,J]`."""
+    _require_cuda(enc, dec)
+    enc, dec = enc.contiguous().float(), dec.contiguous().float()
+    B, T, J = enc.shape
+    U1 = dec.shape[1]
+    out = torch.empty(B, T, U1, J, dtype=out_dtype, device=enc.device)
+    _run("nsp_rnnt_joint_tanh", lib.nsp_rnnt_joint_tanh, ptr(enc), ptr(dec), ptr(out), int(out_dtype == torch.bfloat16),
+         B, T, U1, J, current_stream_ptr())
+    return out
+
+
+POOL_MODE = {"max": 0, "mean": 1, "drop": 2, "add": 3}
+
+
+def pool_time(x, factor, mode):
+    """Time pooling on `[B,T,D]` with kernel = stride = factor, ceil-mode (nsp_pool_time_fwd)."""
+    _require_cuda(x)
+    x = x.contiguous()
+    B, T, D = x.shape
+    y = torch.empty(B, -(-T // factor), D, dtype=x.dtype, device=x.device)
+    _run("nsp_pool_time_fwd", lib.nsp_pool_time_fwd, int(x.dtype == torch.bfloat16), ptr(x), ptr(y), B, T, D, factor,
+         POOL_MODE[mode], current_stream_ptr())
+    return y

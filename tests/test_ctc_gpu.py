@@ -167,3 +167,29 @@ def test_ops_reject_cpu_tensors():
     with pytest.raises(_lib.NspError):
         ops.ctc_loss_fwd_bwd(torch.zeros(1, 2, 4), torch.zeros(1, 1, dtype=torch.int32),
                              torch.ones(1, dtype=torch.int32), torch.ones(1, dtype=torch.int32))
+
+
+def test_greedy_trigger_points_probs_scores():
+    """CTC.greedy / trigger_points / probs / scores (ctc.py:152-243) vs the reference's formulas in plain torch."""
+    from itertools import groupby
+    from neural_sp_b200.decoders.ctc import CTC
+    torch.manual_seed(0)
+    dev = _dev()
+    ctc = CTC(eos=2, blank=0, enc_n_units=24, vocab=12, lsm_prob=0.0).to(dev).eval()
+    ctc.set_precision("fp32")
+    eouts = torch.randn(3, 40, 24, device=dev) * 3
+    elens = torch.IntTensor([40, 33, 9])
+    with torch.no_grad():
+        logits = torch.nn.functional.linear(eouts, ctc.output.weight, ctc.output.bias)
+    best = logits.log_softmax(-1).argmax(-1).cpu()
+    hyps = ctc.greedy(eouts, elens.numpy())
+    trig = ctc.trigger_points(eouts, elens).cpu()
+    for b in range(3):
+        idx = [int(best[b, t]) for t in range(int(elens[b]))]
+        ref = [x for x in (g[0] for g in groupby(idx)) if x != 0]
+        assert hyps[b][0] == ref
+        tp = [t for t in range(int(elens[b])) if idx[t] != 0 and (t == 0 or idx[t] != idx[t - 1])]
+        assert trig[b, :len(tp)].tolist() == tp and trig[b, len(tp):].abs().sum().item() == 0
+    p, s = ctc.probs(eouts, temperature=2.0), ctc.scores(eouts)
+    assert torch.allclose(p, torch.softmax(logits / 2.0, -1), atol=1e-5)
+    assert torch.allclose(s, torch.log_softmax(logits, -1), atol=2e-4)

@@ -171,3 +171,48 @@ def test_frontend_simt_conv_pool_layouts():
     assert (p - pref).abs().max().item() <= 1e-4
     pt = ops.maxpool_time(torch.randn(2, 9, 16, device=dev), 2)
     assert pt.shape == (2, 5, 16)
+
+
+@pytest.mark.parametrize("kind", ["max_pool", "mean_pool", "drop", "add", "concat", "conv1d"])
+@pytest.mark.parametrize("T", [40, 45])
+def test_subsamplers_match_reference_formulas(kind, T):
+    """The six intermediate subsamplers (subsampling.py:13-246) vs their torch formulas, incl. odd lengths."""
+    import math
+    from neural_sp_b200.encoders import subsampling as ss
+    torch.manual_seed(T)
+    dev, B, D, f = "cuda", 3, 64, 2
+    xs = torch.randn(B, T, D, device=dev)
+    xlens = torch.IntTensor([T, T - 3, 7])
+    if kind == "max_pool":
+        m = ss.MaxPoolSubsampler(f)
+        ref = F.max_pool1d(xs.transpose(1, 2), f, f, 0, ceil_mode=True).transpose(1, 2)
+        rl = [(n + 1 - f) // f + 1 for n in xlens.tolist()]
+    elif kind == "mean_pool":
+        m = ss.MeanPoolSubsampler(f)
+        ref = F.avg_pool1d(xs.transpose(1, 2), f, f, 0, ceil_mode=True).transpose(1, 2)
+        rl = [(n + 1 - f) // f + 1 for n in xlens.tolist()]
+    elif kind == "drop":
+        m = ss.DropSubsampler(f)
+        ref = xs[:, ::f]
+        rl = [max(1, math.ceil(n / f)) for n in xlens.tolist()]
+    elif kind == "add":
+        m = ss.AddSubsampler(f)
+        xp = torch.cat([xs, xs.new_zeros(B, 1, D)], 1) if T % 2 else xs
+        ref = xp[:, ::2][:, :(T + 1) // 2] + xp[:, 1::2]
+        rl = [max(1, math.ceil(n / f)) for n in xlens.tolist()]
+    elif kind == "concat":
+        m = ss.ConcatSubsampler(f, D).to(dev)
+        m.precision = "fp32"
+        To = T // f
+        ref = torch.relu(F.linear(xs[:, :To * f].reshape(B, To, f * D), m.proj.weight, m.proj.bias))
+        rl = [max(1, n // f) for n in xlens.tolist()]
+    else:
+        m = ss.Conv1dSubsampler(f, D).to(dev)
+        m.precision = "fp32"
+        ref = torch.relu(m.conv1d(xs.transpose(1, 2)).transpose(1, 2))
+        rl = [(n + 2 - 2 - 1) // f + 1 for n in xlens.tolist()]
+    with torch.no_grad():
+        y, yl = m(xs, xlens)
+    assert y.shape == ref.shape, (y.shape, ref.shape)
+    assert (y - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
+    assert [int(v) for v in yl] == rl

@@ -59,3 +59,39 @@ def test_rnnt_config4_scale_vs_torchaudio():
     assert (grad - lp.grad).abs().max().item() <= 2e-4
     # property: every cell's outgoing probability mass is conserved -> sum over the blank column at t = T-1, u = U is -1/B
     assert abs(grad[0, int(flens[0]) - 1, int(ylens[0]), 0].item() + 1.0 / B) < 5e-4    # fp32 lattice noise at T=250
+
+
+def test_rnn_transducer_module_matches_torch_chain():
+    """RNNTransducer.forward_transducer (joint GEMMs + tanh + log-softmax + lattice kernel) vs the same chain in plain
+    torch fp32 with torchaudio's loss as the stand-in for warp_rnnt (rnn_transducer.py:236-258)."""
+    import torchaudio
+    from neural_sp_b200.decoders.rnn_transducer import RNNTransducer
+    torch.manual_seed(0)
+    sym = {'eos': 2, 'unk': 1, 'pad': 3, 'blank': 0}
+    dec = RNNTransducer(sym, enc_n_units=48, n_units=32, n_projs=0, n_layers=2, bottleneck_dim=40, emb_dim=16, vocab=50,
+                        dropout=0.0, dropout_emb=0.0, ctc_weight=0.0, ctc_lsm_prob=0.0, ctc_fc_list="", external_lm=None,
+                        global_weight=1.0, mtl_per_batch=False, param_init=0.1).cuda().eval()
+    dec.set_precision("fp32")
+    B, T = 3, 30
+    eouts = torch.randn(B, T, 48, device="cuda")
+    elens = torch.IntTensor([30, 25, 18])
+    ys = [[5, 6, 7, 8, 9], [10, 11, 12], [4]]
+    loss = dec.forward_transducer(eouts, elens, ys)
+    # reference chain
+    U = 5
+    ys_in = torch.full((B, U + 1), 3, dtype=torch.long)
+    ys_out = torch.zeros(B, U, dtype=torch.int32)
+    for b, y in enumerate(ys):
+        ys_in[b, 0] = 2
+        ys_in[b, 1:len(y) + 1] = torch.tensor(y)
+        ys_out[b, :len(y)] = torch.tensor(y, dtype=torch.int32)
+    with torch.no_grad():
+        d = dec.embed(ys_in.cuda())
+        for l in range(2):
+            d, _ = dec.rnn[l](d)
+        z = torch.tanh(dec.w_enc(eouts)[:, :, None] + dec.w_dec(d)[:, None])
+        lp = torch.log_softmax(dec.output(z), -1)
+        ref = torchaudio.functional.rnnt_loss(lp, ys_out.cuda(), elens.cuda(), torch.tensor([5, 3, 1], dtype=torch.int32).cuda(),
+                                              blank=0, reduction="mean", fused_log_softmax=False)
+    assert loss.shape == (1,)
+    assert abs(loss.item() - ref.item()) <= 1e-3 * abs(ref.item()), (loss.item(), ref.item())
