@@ -97,7 +97,7 @@ nsp_status nsp_ctc_forced_align(const float* logits, int B, int T, int V,
  *       tf32 passes accumulate hi*hi + lo*hi + hi*lo in TMEM (fp32-level accuracy; parity mode).
  * x [M,K] row pitch ldx, w [N,K] row pitch ldw (elements; pitches must be 16-byte multiples).
  * glu=1: w holds value rows [0,N/2) and gate rows [N/2,N); out[:, j] = v_j * sigmoid(g_j), width N/2.
- * act: 0 none, 1 relu, 2 swish (x*sigmoid(x)); bias fp32 [N] or NULL; residual fp32 [M,ldr] or NULL.
+ * act: 0 none, 1 relu, 2 swish (x*sigmoid(x)), 3 gelu (erf), 4 gelu (tanh approximation); bias fp32 [N] or NULL; residual fp32 [M,ldr] or NULL.
  * out: fp32 (out_bf16=0) or bf16 (out_bf16=1) with row pitch ldo; out2 (optional, may be NULL) receives a
  * bf16 copy of an fp32 result with pitch ldo2.  out may alias residual.
  * ------------------------------------------------------------------------------------------ */

@@ -98,11 +98,19 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(Conv3Params p) {
         for (int i = 0; i < 4; ++i) {
             const int f = f0 + pc + i;
             if (f < p.F) {
+                float o[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float v = acc[i][j] + bb[j];
-                    if (p.relu) v = fmaxf(v, 0.f);
-                    fe_st<TO>(yg + (int64_t)f * CO + cg * 4 + j, v);
+                    o[j] = p.relu ? fmaxf(v, 0.f) : v;
+                }
+                TO* dst = yg + (int64_t)f * CO + cg * 4;
+                if constexpr (sizeof(TO) == 2) {          // 4 bf16 = one 8-byte store
+                    __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]), b2 = __floats2bfloat162_rn(o[2], o[3]);
+                    uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b2);
+                    *reinterpret_cast<uint2*>(dst) = pk;
+                } else {
+                    *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
                 }
             }
         }

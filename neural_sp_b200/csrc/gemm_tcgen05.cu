@@ -94,7 +94,7 @@ struct GemmArgs {
 };
 
 // epilogue flavours (compile-time: the epilogue is instruction-bound, see profiles/r01_gemm_epilogue.md)
-enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SWISH = 2 };
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SWISH = 2, ACT_GELU = 3, ACT_GELU_TANH = 4 };
 
 template <bool FAST>
 __device__ __forceinline__ float sigmoid_f(float x) {
@@ -281,6 +281,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
                 } else if constexpr (ACT == ACT_SWISH) {
 #pragma unroll
                     for (int j = 0; j < CW; ++j) v[j] *= sigmoid_f<kBF16>(v[j]);
+                } else if constexpr (ACT == ACT_GELU) {          // F.gelu (modules/gelu.py:17-21): x * Phi(x)
+#pragma unroll
+                    for (int j = 0; j < CW; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752f));
+                } else if constexpr (ACT == ACT_GELU_TANH) {     // tanh approximation (modules/gelu.py:11-14)
+#pragma unroll
+                    for (int j = 0; j < CW; ++j) {
+                        const float x = v[j];
+                        v[j] = 0.5f * x * (1.f + tanhf(0.79788456080286536f * (x + 0.044715f * x * x * x)));
+                    }
                 }
                 if (row_ok) {
                     if constexpr (RES) {
@@ -395,6 +404,10 @@ nsp_status dispatch_epi(const GemmMaps& maps, const GemmArgs& g, int glu, int ac
                                        : launch_gemm<TIn, BN, ACT_RELU, false, false, false>(maps, g, st);
         case ACT_SWISH: return out_bf16 ? launch_gemm<TIn, BN, ACT_SWISH, false, false, true>(maps, g, st)
                                         : launch_gemm<TIn, BN, ACT_SWISH, false, false, false>(maps, g, st);
+        case ACT_GELU: return out_bf16 ? launch_gemm<TIn, BN, ACT_GELU, false, false, true>(maps, g, st)
+                                       : launch_gemm<TIn, BN, ACT_GELU, false, false, false>(maps, g, st);
+        case ACT_GELU_TANH: return out_bf16 ? launch_gemm<TIn, BN, ACT_GELU_TANH, false, false, true>(maps, g, st)
+                                            : launch_gemm<TIn, BN, ACT_GELU_TANH, false, false, false>(maps, g, st);
     }
     set_error("gemm: act=%d", act);
     return NSP_ERR_INVALID;
@@ -420,7 +433,7 @@ nsp_status gemm_dispatch(int precision, const void* a, const void* a_lo, int64_t
     g.M = M; g.N = N; g.K = K; g.bias = bias; g.residual = residual; g.ldr = ldr;
     g.alpha = alpha; g.out = out; g.ldo = ldo; g.out2 = out2; g.ldo2 = ldo2;
     g.nseg = precision == 2 ? 3 : 1;
-    NSP_CHECK_ARG(act >= 0 && act <= 2, "gemm: act=%d", act);
+    NSP_CHECK_ARG(act >= 0 && act <= 4, "gemm: act=%d", act);
     NSP_CHECK_ARG(!(out2 && out_bf16), "gemm: out2 is only meaningful with an fp32 primary output");
     const int nout = glu ? N / 2 : N;
     // tile width: 128 unless the problem is too small to fill the machine, then 64 (GLU always 128 = 64 value + 64 gate)

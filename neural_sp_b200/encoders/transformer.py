@@ -4,9 +4,9 @@ Same constructor arguments, ``forward(xs, xlens, task, ...) -> {'ys': {'xs', 'xl
 and state_dict keys (``conv.*``, ``embed.*``, ``pos_emb.inv_freq``, ``u_bias/v_bias``, ``layers.N.*``,
 ``norm_out.*``, ``bridge*.*``).  The `[B,T',T']` boolean mask of the reference (:633-686) is never built:
 key-padding / causal / chunk visibility are evaluated inside the attention kernel from device-side lengths.
-Supported here: offline full-context and unidirectional ('uni', with per-layer lookahead) encoders with
-hierarchical max-pool subsampling and sub-task outputs.  Latency-controlled chunking ('reshape'/'mask') and
-streaming caches are 'next' rows and raise NotImplementedError."""
+Supported here: offline full-context, unidirectional ('uni', per-layer lookahead) and latency-controlled
+('reshape' overlapped windows / 'mask' chunk-wise visibility) encoders with all six hierarchical subsamplers and
+sub-task outputs.  Streaming inference with caches is a 'next' row and raises NotImplementedError."""
 import copy
 import math
 
@@ -24,6 +24,17 @@ from .transformer_block import TransformerEncoderBlock
 
 
 _LENS_CACHE = {}
+
+
+def chunkwise(xs, N_l, N_c, N_r):
+    """`[B, T, D]` -> `[B * ceil(T / N_c), N_l + N_c + N_r, D]` overlapped windows, zero padded at both ends
+    (reference encoders/utils.py:13-45, padding=True).  Pure data movement."""
+    bs, xmax, idim = xs.size()
+    n_chunks = math.ceil(xmax / N_c)
+    width = N_l + N_c + N_r
+    xp = torch.nn.functional.pad(xs, (0, 0, N_l, n_chunks * N_c - xmax + N_r))
+    out = xp.unfold(1, width, N_c)[:, :n_chunks]                 # [B, n_chunks, D, width]
+    return out.permute(0, 1, 3, 2).reshape(bs * n_chunks, width, idim)
 
 
 def lens_to_device(xlens, device):
@@ -75,7 +86,9 @@ class TransformerEncoder(EncoderBase):
         self.streaming_type = streaming_type if self.lc_bidir else ''
         self.causal = self.unidir or self.streaming_type == 'mask'
         if self.lc_bidir:
-            raise NotImplementedError("latency-controlled chunking is a 'next' row (SURVEY.md 8f-4)")
+            assert n_layers_sub1 == 0 and n_layers_sub2 == 0 and not self.unidir
+        if self.streaming_type == 'mask':
+            assert self.N_r == 0 and self.N_l % self.N_c == 0
         self.n_layers_sub1 = n_layers_sub1
         self.n_layers_sub2 = n_layers_sub2
         self.task_specific_layer = task_specific_layer
@@ -174,21 +187,41 @@ class TransformerEncoder(EncoderBase):
                  'ys_sub2': {'xs': None, 'xlens': None}}
         with torch.no_grad():
             rel = 'relative' in self.pe_type
+            bs = xs.size(0)
+            N_l, N_c, N_r = self.N_l, self.N_c, self.N_r
+            n_chunks = 0
+            if self.lc_bidir:                                         # offline latency-controlled encoders (:456-462)
+                xs = chunkwise(xs, 0, N_c, 0) if self.streaming_type == 'mask' else chunkwise(xs, N_l, N_c, N_r)
+                n_chunks = xs.size(0) // bs
             if self.conv is None:
                 xs = self._proj('embed', self.embed, xs.float(), scale=self.scale if rel else 1.0)
             else:
-                xs, xlens = self.conv(xs, xlens, lookback=lookback, lookahead=lookahead,
+                xs, xlens = self.conv(xs, xlens, lookback=False if self.lc_bidir else lookback,
+                                      lookahead=False if self.lc_bidir else lookahead,
                                       out_scale=self.scale if (rel and self.enc_type != 'conv') else 1.0)
+                N_l, N_c, N_r = max(0, N_l // self.conv_factor), N_c // self.conv_factor, N_r // self.conv_factor
+            if self.streaming_type == 'mask':                         # back to utterance shape (:481-483)
+                xs = xs.contiguous().view(bs, -1, xs.size(2))[:, :int(xlens.max())].contiguous()
             if self.enc_type == 'conv':
                 eouts['ys']['xs'], eouts['ys']['xlens'] = xs, xlens
                 return eouts
             self.reset_cache()
             dev = xs.device
-            klens = lens_to_device(xlens, dev)
+
+            def key_lens():
+                if self.streaming_type == 'reshape':                  # no mask at all inside a chunk (:512)
+                    return lens_to_device(torch.IntTensor([xs.size(1)] * xs.size(0)), dev)
+                return lens_to_device(xlens, dev)
+
+            klens = key_lens()
             pos = self.pos_emb.table(xs.size(1)) if rel else None
 
             def mask_kw(lth):
-                return dict(causal=True, lookahead=self.lookaheads[lth]) if self.unidir else {}
+                if self.unidir:
+                    return dict(causal=True, lookahead=self.lookaheads[lth])
+                if self.streaming_type == 'mask':
+                    return dict(chunk_c=N_c, chunk_l=N_l)
+                return {}
 
             for lth, layer in enumerate(self.layers):
                 xs, _ = layer(xs, klens, cache=None, pos_embs=pos, rel_bias=(self.u_bias, self.v_bias),
@@ -205,9 +238,13 @@ class TransformerEncoder(EncoderBase):
                         return eouts
                 if lth < len(self.layers) - 1 and self.subsample_factors[lth] > 1:
                     xs, xlens = self.subsample_layers[lth](xs, xlens)
-                    klens = lens_to_device(xlens, dev)
+                    f = self.subsample_factors[lth]
+                    N_l, N_c, N_r = max(0, N_l // f), N_c // f, N_r // f
+                    klens = key_lens()
                     if rel:
                         pos = self.pos_emb.table(xs.size(1))
+            if self.streaming_type == 'reshape':                      # keep the centre of every window (:546-550)
+                xs = xs[:, N_l:N_l + N_c].contiguous().view(bs, -1, xs.size(2))[:, :int(xlens.max())].contiguous()
             xs = ops.layernorm(xs, self.norm_out.weight, self.norm_out.bias, self.norm_out.eps)
             if self.bridge is not None:
                 xs = self._proj('bridge', self.bridge, xs)

@@ -9,7 +9,15 @@ from .. import ops
 from ._prep import prepared, get_precision, act_dtype
 from .initialization import init_with_xavier_uniform
 
-_ACTS = {"relu": "relu", "swish": "swish"}
+_ACTS = {"relu": "relu", "swish": "swish", "gelu": "gelu", "gelu_accurate": "gelu_accurate", "glu": "glu"}
+
+
+class LinearGLUBlock(nn.Module):
+    """`F.glu(Linear(idim, 2*idim)(x))` (reference modules/glu.py:11-22); runs as one GEMM with a GLU epilogue."""
+
+    def __init__(self, idim):
+        super().__init__()
+        self.fc = nn.Linear(idim, idim * 2)
 
 
 class PositionwiseFeedForward(nn.Module):
@@ -18,11 +26,13 @@ class PositionwiseFeedForward(nn.Module):
         if bottleneck_dim > 0:
             raise NotImplementedError("low-rank FFN (ffn_bottleneck_dim > 0) is not on the B200 path yet")
         if activation not in _ACTS:
-            raise NotImplementedError("FFN activation %r is not on the B200 path yet (relu, swish)" % activation)
+            raise NotImplementedError(activation)
         self.bottleneck_dim = 0
         self.act_name = _ACTS[activation]
         self.w_1 = nn.Linear(d_model, d_ff)
         self.w_2 = nn.Linear(d_ff, d_model)
+        if activation == "glu":
+            self.activation = LinearGLUBlock(d_ff)          # parameter name `activation.fc.*` as in the reference
         self.dropout = nn.Dropout(p=dropout)
         if param_init == 'xavier_uniform':
             for n, p in self.named_parameters():
@@ -34,6 +44,11 @@ class PositionwiseFeedForward(nn.Module):
         prec = get_precision(self)
         w1 = prepared(self, "w_1", prec, (self.w_1.weight,))
         w2 = prepared(self, "w_2", prec, (self.w_2.weight,))
-        h = ops.linear(xs, w1, self.w_1.bias, prec=prec, act=self.act_name, out_dtype=act_dtype(prec))
+        if self.act_name == "glu":
+            h = ops.linear(xs, w1, self.w_1.bias, prec=prec, out_dtype=act_dtype(prec))
+            wg = prepared(self, "glu_fc", prec, (self.activation.fc.weight,))
+            h = ops.linear(h, wg, self.activation.fc.bias, prec=prec, glu=True, out_dtype=act_dtype(prec))
+        else:
+            h = ops.linear(xs, w1, self.w_1.bias, prec=prec, act=self.act_name, out_dtype=act_dtype(prec))
         return ops.linear(h, w2, self.w_2.bias, prec=prec, residual=residual, alpha=scale,
                           out_dtype=torch.float32, out=out)

@@ -128,7 +128,7 @@ def ctc_forced_align(logits, labels, elens, ylens, blank=0):
 # tensor-core projections
 # ---------------------------------------------------------------------------------------------
 PREC = {"bf16": 0, "tf32": 1, "fp32": 2}
-ACT = {None: 0, "none": 0, "relu": 1, "swish": 2}
+ACT = {None: 0, "none": 0, "relu": 1, "swish": 2, "gelu": 3, "gelu_accurate": 4}
 
 
 def split_tf32(x):

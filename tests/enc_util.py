@@ -22,11 +22,20 @@ def oracle_cfg(g):
     if conv:
         pools = [tuple(int(v) for v in t.strip("()").split(",")) for t in conv["poolings"].split("_")]
         cc = dict(in_channel=conv["in_channel"], poolings=pools)
-    return dict(kind=kind, n_layers=nl, n_heads=a["n_heads"], d_model=a["d_model"], pe_type=a["pe_type"],
+    n_c = int(str(a["chunk_size_current"]).split("_")[-1])
+    lc = n_c > 0 and "uni" not in a["enc_type"]
+    st = a["streaming_type"] if lc else ""
+    extra = dict(streaming_type=st, N_l=int(str(a["chunk_size_left"]).split("_")[-1]), N_c=n_c,
+                 N_r=int(str(a["chunk_size_right"]).split("_")[-1]))
+    causal_attn = "uni" in a["enc_type"]
+    cfg = dict(kind=kind, n_layers=nl, n_heads=a["n_heads"], d_model=a["d_model"], pe_type=a["pe_type"],
                 clamp_len=a["clamp_len"], layer_norm_eps=a["layer_norm_eps"],
-                normalization=a.get("normalization", "layer_norm"), causal="uni" in a["enc_type"], lookaheads=la,
+                normalization=a.get("normalization", "layer_norm"), causal=causal_attn, lookaheads=la,
                 subsample=sub, dropout_layer=a["dropout_layer"], conv=cc, ffn_activation=a["ffn_activation"],
                 n_layers_sub1=a["n_layers_sub1"])
+    cfg.update(extra)
+    cfg["causal_conv"] = causal_attn or st == "mask"
+    return cfg
 
 
 def state_dict_of(g):

@@ -38,6 +38,14 @@ CASES = {
     "enc_transformer_plain": dict(args=dict(enc_type='transformer', pe_type='relative', ffn_activation='relu',
                                             n_layers=2, subsample="1_2", lookahead="0_0", n_heads=2, d_model=32, d_ff=64),
                                   conv=None, B=2, T=50, xlens=[50, 44], kind='transformer'),
+    # latency-controlled, overlapped windows (no mask inside a window), centre extraction
+    "enc_lc_reshape": dict(args=dict(n_layers=2, subsample="1_1", lookahead="0_0", chunk_size_left="16",
+                                     chunk_size_current="32", chunk_size_right="16", streaming_type='reshape',
+                                     kernel_size=3), conv=dict(poolings="(2,2)_(2,2)"), B=2, T=90, xlens=[90, 61]),
+    # latency-controlled, chunk-wise attention mask + causal conv module, CNN applied chunk by chunk
+    "enc_lc_mask": dict(args=dict(n_layers=2, subsample="1_1", lookahead="0_0", chunk_size_left="32",
+                                  chunk_size_current="32", chunk_size_right="0", streaming_type='mask',
+                                  kernel_size=3), conv=dict(poolings="(2,2)_(2,2)"), B=2, T=96, xlens=[96, 70]),
     # unidirectional Conformer: causal attention with lookahead, causal depthwise conv
     "enc_uni_conformer": dict(args=dict(enc_type='conv_uni_conformer', lookahead="1_0", n_layers=2, subsample="1_1",
                                         kernel_size=5), conv=dict(poolings="(2,2)_(2,2)"), B=2, T=60, xlens=[60, 48]),

@@ -204,12 +204,13 @@ def test_subsamplers_match_reference_formulas(kind, T):
         m = ss.ConcatSubsampler(f, D).to(dev)
         m.precision = "fp32"
         To = T // f
-        ref = torch.relu(F.linear(xs[:, :To * f].reshape(B, To, f * D), m.proj.weight, m.proj.bias))
+        ref = torch.relu(F.linear(xs[:, :To * f].reshape(B, To, f * D).double(), m.proj.weight.double(), m.proj.bias.double())).float()
         rl = [max(1, n // f) for n in xlens.tolist()]
     else:
         m = ss.Conv1dSubsampler(f, D).to(dev)
         m.precision = "fp32"
-        ref = torch.relu(m.conv1d(xs.transpose(1, 2)).transpose(1, 2))
+        ref = torch.relu(F.conv1d(xs.transpose(1, 2).double(), m.conv1d.weight.double(), m.conv1d.bias.double(), stride=f,
+                                  padding=1).transpose(1, 2)).float()     # fp64: cuDNN conv defaults to TF32
         rl = [(n + 2 - 2 - 1) // f + 1 for n in xlens.tolist()]
     with torch.no_grad():
         y, yl = m(xs, xlens)
