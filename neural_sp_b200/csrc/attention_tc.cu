@@ -23,7 +23,8 @@ namespace {
 
 constexpr int QT = 128, KT = 128, DK = 64;
 constexpr int TILE_BYTES = 128 * 128;                 // [128 rows x 64 bf16]
-constexpr int NTHREADS = 192;
+constexpr int NSM_WARPS = 8;                        // softmax warps: two per TMEM lane quadrant (key halves)
+constexpr int NTHREADS = 64 + 32 * NSM_WARPS;
 
 struct AttnTcArgs {
     const int32_t* klens;
@@ -72,7 +73,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
     uint8_t* sP = sV + TILE_BYTES;                    // 2 x 16 KiB (keys 0-63, 64-127)
     uint8_t* sR = sP + 2 * TILE_BYTES;                // 16 rows x 128 B = 2 KiB
     float* sBD = reinterpret_cast<float*>(sR + 2048); // [128][17]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sBD + 128 * 17);
+    float* sMX = sBD + 128 * 17;                      // [2][128] partial row maxima of the two key halves
+    float* sL = sMX + 256;                            // [2][128] partial row sums (final combine)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sL + 256);
     uint64_t* q_full = bars + 0; uint64_t* k_full = bars + 1; uint64_t* k_empty = bars + 2;
     uint64_t* v_full = bars + 3; uint64_t* v_empty = bars + 4; uint64_t* s_full = bars + 5;
     uint64_t* p_full = bars + 6; uint64_t* o_full = bars + 7; uint64_t* bd_full = bars + 8;
@@ -99,7 +102,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
     if (warp == 1 && lane == 0) {
         tc::mbar_init(q_full, 1); tc::mbar_init(k_full, 1); tc::mbar_init(k_empty, 1);
         tc::mbar_init(v_full, 1); tc::mbar_init(v_empty, 1); tc::mbar_init(s_full, 1);
-        tc::mbar_init(p_full, 128); tc::mbar_init(o_full, 1); tc::mbar_init(bd_full, 1);
+        tc::mbar_init(p_full, 32 * NSM_WARPS); tc::mbar_init(o_full, 1); tc::mbar_init(bd_full, 1);
         tc::fence_barrier_init();
     }
     if (warp == 2) tc::tmem_alloc<256>(tmem_holder);
@@ -165,35 +168,43 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
             }
         }
     } else {
+        // two threads per query row: `half` 0/1 owns keys [0,64) / [64,128) of every key tile and d_k columns
+        // [0,32) / [32,64) of the output; they meet through shared memory + a named barrier over the 8 softmax warps
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int row = q * 32 + lane;                       // query row inside the tile == TMEM lane
         const int i = i0 + row;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        auto sm_barrier = [&]() { asm volatile("bar.sync 1, %0;" :: "n"(32 * NSM_WARPS) : "memory"); };
         float bd_far = 0.f;
         const int clamp = a.clamp_len;
         if (a.has_rel) {
             tc::mbar_wait(bd_full, 0);
             tc::tc_fence_after();
-            uint32_t r16[16];
-            tmem_ld_32x32_x16(tm_BD + lane_addr, r16);
-            tc::tmem_ld_wait();
+            if (half == 0) {
+                uint32_t r16[16];
+                tmem_ld_32x32_x16(tm_BD + lane_addr, r16);
+                tc::tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 16; ++c) sBD[row * 17 + c] = __uint_as_float(r16[c]);
-            __syncwarp();
+                for (int c = 0; c < 16; ++c) sBD[row * 17 + c] = __uint_as_float(r16[c]);
+            }
+            sm_barrier();
             bd_far = sBD[row * 17 + clamp];                  // every |i-j| >= clamp_len shares this value
         }
-        float O[DK];
+        constexpr int DH = DK / 2;
+        float O[DH];
 #pragma unroll
-        for (int c = 0; c < DK; ++c) O[c] = 0.f;
-        float m_run = -FLT_MAX, l_run = 0.f;
+        for (int c = 0; c < DH; ++c) O[c] = 0.f;
+        float m_run = -FLT_MAX, l_run = 0.f;                 // l_run: this half's share of the row sum
+        const int iw0 = i0 + q * 32, iw1 = iw0 + 31;
+        const float bdfs = bd_far * a.scale_log2;
 
         for (int j = 0; j < ntiles; ++j) {
             const uint32_t ph = j & 1;
-            const int j0 = j * KT;
+            const int j0 = j * KT + half * (KT / 2);         // first key of this thread's half tile
+            const uint32_t s_col = (uint32_t)(half * (KT / 2));
             tc::mbar_wait(s_full, ph);
             tc::tc_fence_after();
-            // ---- pass 1: row max of the masked, biased scores (exp2 domain) ----
-            float mx = -FLT_MAX;
             auto score = [&](float raw, int jj) -> float {
                 float s = raw;
                 if (a.has_rel) {
@@ -211,20 +222,20 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
                 if (jj >= a.Tk) s = -INFINITY;
                 return s;
             };
-            // warp-uniform fast path per 32-key chunk: every key visible to every row of this warp and the whole chunk
+            // warp-uniform fast path per 32-key chunk: every key visible to every row of this warp and the chunk
             // outside the clamped band -> score = raw * scale + const (one FFMA), no per-element mask / gather logic
-            const int iw0 = i0 + q * 32, iw1 = iw0 + 31;
-            const float bdfs = bd_far * a.scale_log2;
             auto chunk_fast = [&](int c) -> bool {
                 const int jc0 = j0 + c, jc1 = jc0 + 31;
                 const bool vis = (jc1 < klen) && !a.causal && (a.chunk_c == 0);
                 const bool far = !a.has_rel || (jc1 <= mlen + iw0 - clamp) || (jc0 >= mlen + iw1 + clamp);
                 return vis && far;
             };
+            // ---- pass 1: row max over this half's 64 keys ----
+            float mx = -FLT_MAX;
 #pragma unroll 1
-            for (int c = 0; c < KT; c += 32) {
+            for (int c = 0; c < KT / 2; c += 32) {
                 uint32_t r[32];
-                tc::tmem_ld_32x32(tm_S + lane_addr + (uint32_t)c, r);
+                tc::tmem_ld_32x32(tm_S + lane_addr + s_col + (uint32_t)c, r);
                 tc::tmem_ld_wait();
                 if (chunk_fast(c)) {
                     float mr = -FLT_MAX;
@@ -236,14 +247,16 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
                     for (int e = 0; e < 32; ++e) mx = fmaxf(mx, score(__uint_as_float(r[e]), j0 + c + e));
                 }
             }
-            const float m_new = fmaxf(m_run, mx);
+            sMX[half * 128 + row] = mx;
+            sm_barrier();
+            const float m_new = fmaxf(m_run, fmaxf(mx, sMX[(half ^ 1) * 128 + row]));
             const float corr = ex2(m_run - m_new);
             float rsum = 0.f;
-            // ---- pass 2: probabilities -> bf16 P tile (K-major, 128B swizzle) ----
+            // ---- pass 2: probabilities -> bf16 P half tile (K-major, 128B swizzle) ----
 #pragma unroll 1
-            for (int c = 0; c < KT; c += 32) {
+            for (int c = 0; c < KT / 2; c += 32) {
                 uint32_t r[32];
-                tc::tmem_ld_32x32(tm_S + lane_addr + (uint32_t)c, r);
+                tc::tmem_ld_32x32(tm_S + lane_addr + s_col + (uint32_t)c, r);
                 tc::tmem_ld_wait();
                 uint32_t pk[16];
                 if (chunk_fast(c)) {
@@ -264,17 +277,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
                         float p0 = (s0 == -INFINITY) ? 0.f : ex2(s0 - m_new);
                         float p1 = (s1 == -INFINITY) ? 0.f : ex2(s1 - m_new);
                         __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-                        // accumulate the row sum from the ROUNDED probabilities so that P V and l stay consistent
+                        // the row sum is accumulated from the ROUNDED probabilities so that P V and l stay consistent
                         rsum += __bfloat162float(pb.x) + __bfloat162float(pb.y);
                         pk[e >> 1] = *reinterpret_cast<uint32_t*>(&pb);
                     }
                 }
-                uint8_t* half = sP + (c >> 6) * TILE_BYTES + row * 128;
+                uint8_t* hrow = sP + half * TILE_BYTES + row * 128;
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int unit = ((c & 32) >> 3) + u;                 // 16-byte unit inside the 128 B row
                     uint4 v4 = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-                    *reinterpret_cast<uint4*>(half + ((unit ^ (row & 7)) << 4)) = v4;
+                    *reinterpret_cast<uint4*>(hrow + ((unit ^ (row & 7)) << 4)) = v4;
                 }
             }
             l_run = l_run * corr + rsum;
@@ -282,24 +295,25 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
             tc::tc_fence_before();
             tc::fence_proxy_async_smem();                                 // generic-proxy smem writes -> visible to the MMA
             tc::mbar_arrive(p_full);
-            // ---- O += P V ----
+            // ---- O += P V (this thread keeps d_k columns [half*32, half*32+32)) ----
             tc::mbar_wait(o_full, ph);
             tc::tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < DK; c += 32) {
+            {
                 uint32_t r[32];
-                tc::tmem_ld_32x32(tm_O + lane_addr + (uint32_t)c, r);
+                tc::tmem_ld_32x32(tm_O + lane_addr + (uint32_t)(half * DH), r);
                 tc::tmem_ld_wait();
 #pragma unroll
-                for (int e = 0; e < 32; ++e) O[c + e] = O[c + e] * corr + __uint_as_float(r[e]);
+                for (int e = 0; e < DH; ++e) O[e] = O[e] * corr + __uint_as_float(r[e]);
             }
             tc::tc_fence_before();
         }
+        sL[half * 128 + row] = l_run;
+        sm_barrier();
         if (i < a.Tq) {
-            const float inv = 1.f / l_run;
-            __nv_bfloat16* o = a.out + ((int64_t)b * a.Tq + i) * a.ldo + (int64_t)h * DK;
+            const float inv = 1.f / (l_run + sL[(half ^ 1) * 128 + row]);
+            __nv_bfloat16* o = a.out + ((int64_t)b * a.Tq + i) * a.ldo + (int64_t)h * DK + half * DH;
 #pragma unroll
-            for (int c = 0; c < DK; c += 8) {
+            for (int c = 0; c < DH; c += 8) {
                 __nv_bfloat162 p0 = __floats2bfloat162_rn(O[c] * inv, O[c + 1] * inv);
                 __nv_bfloat162 p1 = __floats2bfloat162_rn(O[c + 2] * inv, O[c + 3] * inv);
                 __nv_bfloat162 p2 = __floats2bfloat162_rn(O[c + 4] * inv, O[c + 5] * inv);
@@ -373,7 +387,7 @@ nsp_status attention_tc_dispatch(const void* q, int64_t ldq, const void* k, int6
     a.has_rel = r ? 1 : 0; a.clamp_len = r ? (clamp_len < rlen - 1 ? clamp_len : rlen - 1) : 0;
     a.causal = causal; a.lookahead = lookahead; a.chunk_c = chunk_c; a.chunk_l = chunk_l;
     a.scale_log2 = 1.4426950408889634f / sqrtf((float)dk);
-    const size_t smem = 1024 + 5 * TILE_BYTES + 2048 + 128 * 17 * sizeof(float) + 128;
+    const size_t smem = 1024 + 5 * TILE_BYTES + 2048 + (128 * 17 + 512) * sizeof(float) + 128;
     static bool attr = false;
     if (!attr) { NSP_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     const int qtiles = ceil_div(Tq, QT);

@@ -9,7 +9,7 @@
 // Padding semantics: zeros outside [0, T) of the PADDED batch tensor; frames beyond an utterance's
 // own length are NOT masked (reference behaviour).
 //
-// One CTA = 8 warps = 32 consecutive frames of one utterance; the (32 + k - 1) x d input window and the
+// One CTA = 16 warps = 64 consecutive frames of one utterance; the (32 + k - 1) x d input window and the
 // k x d taps sit in shared memory; a warp owns 4 frames, a lane owns channels lane, lane+32, ...;
 // the per-frame normalisation statistics are warp-shuffle reductions over registers.
 #include "common.cuh"
@@ -18,7 +18,7 @@ namespace nsp {
 namespace {
 
 constexpr int RT = 4;          // frames per warp
-constexpr int TT = 8 * RT;     // frames per CTA
+// warps per CTA: 16 (64 frames per CTA, one CTA per SM, more latency hiding) or 8 when the window would not fit in smem
 
 struct ConvParams {
     const void* x; int64_t ldx;      // [B*T, d]
@@ -38,8 +38,10 @@ template <typename T> __device__ __forceinline__ void cv_st(T* p, float v);
 template <> __device__ __forceinline__ void cv_st<float>(float* p, float v) { *p = v; }
 template <> __device__ __forceinline__ void cv_st<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
-template <typename T, int CPLMAX, int K>   // K == 0: runtime kernel size
-__global__ void __launch_bounds__(256) conformer_conv_kernel(ConvParams p) {
+template <typename T, int CPLMAX, int K, int NW>   // K == 0: runtime kernel size
+__global__ void __launch_bounds__(32 * NW) conformer_conv_kernel(ConvParams p) {
+    constexpr int NT = 32 * NW;
+    constexpr int TT = NW * RT;    // frames per CTA
     extern __shared__ float sm[];
     const int d = p.d, k = (K > 0) ? K : p.k;
     const int rows = TT + k - 1;
@@ -53,7 +55,7 @@ __global__ void __launch_bounds__(256) conformer_conv_kernel(ConvParams p) {
         // stage the (TT + k - 1) x d input window (fp32 in smem) and the k x d taps; 128-bit loads when d % 8 == 0
         const int w_ = threadIdx.x >> 5, l_ = threadIdx.x & 31;
         const bool vec = (d % 8 == 0) && (p.ldx % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
-        for (int r = w_; r < rows; r += 8) {
+        for (int r = w_; r < rows; r += NW) {
             const int t = t0 + r - p.left_pad;
             const bool in = (t >= 0 && t < p.T);
             float* trow = tile + (size_t)r * d;
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(256) conformer_conv_kernel(ConvParams p) {
             }
         }
         // taps arrive pre-transposed [k][d] (host prepares them once): straight coalesced copy
-        for (int e = threadIdx.x; e < k * d; e += 256) wT[e] = __ldg(p.w + e);
+        for (int e = threadIdx.x; e < k * d; e += NT) wT[e] = __ldg(p.w + e);
     }
     __syncthreads();
 
@@ -173,18 +175,30 @@ __global__ void __launch_bounds__(256) conformer_conv_kernel(ConvParams p) {
 
 template <typename T, int CPLMAX>
 nsp_status launch_conv(const ConvParams& p, cudaStream_t st) {
-    const size_t smem = sizeof(float) * ((size_t)(TT + p.k - 1) * p.d + (size_t)p.k * p.d);
+    int nw = 16;
+    size_t smem = sizeof(float) * ((size_t)(nw * RT + p.k - 1) * p.d + (size_t)p.k * p.d);
+    if (smem > 220 * 1024) { nw = 8; smem = sizeof(float) * ((size_t)(nw * RT + p.k - 1) * p.d + (size_t)p.k * p.d); }
     if (smem > 220 * 1024) { set_error("conformer_conv: d=%d k=%d needs %zu B smem", p.d, p.k, smem); return NSP_ERR_UNSUPPORTED; }
-    const unsigned grid = (unsigned)(p.B * ceil_div(p.T, TT));
+    const unsigned grid = (unsigned)(p.B * ceil_div(p.T, nw * RT));
 #define NSP_CONV(KK)                                                                                          \
     do {                                                                                                      \
-        auto kern = conformer_conv_kernel<T, CPLMAX, KK>;                                                     \
-        static size_t attr_smem = 0;                                                                          \
-        if (smem > attr_smem) {                                                                               \
-            NSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-            attr_smem = smem;                                                                                 \
+        if (nw == 16) {                                                                                       \
+            auto kern = conformer_conv_kernel<T, CPLMAX, KK, 16>;                                             \
+            static size_t attr_smem = 0;                                                                      \
+            if (smem > attr_smem) {                                                                           \
+                NSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                attr_smem = smem;                                                                             \
+            }                                                                                                 \
+            kern<<<grid, 512, smem, st>>>(p);                                                                 \
+        } else {                                                                                              \
+            auto kern = conformer_conv_kernel<T, CPLMAX, KK, 8>;                                              \
+            static size_t attr_smem = 0;                                                                      \
+            if (smem > attr_smem) {                                                                           \
+                NSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                attr_smem = smem;                                                                             \
+            }                                                                                                 \
+            kern<<<grid, 256, smem, st>>>(p);                                                                 \
         }                                                                                                     \
-        kern<<<grid, 256, smem, st>>>(p);                                                                     \
     } while (0)
     if (p.k == 15) NSP_CONV(15); else if (p.k == 31) NSP_CONV(31); else if (p.k == 7) NSP_CONV(7); else NSP_CONV(0);
 #undef NSP_CONV

@@ -53,8 +53,15 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
         int idx = (j * 32 + lane) * VEC;
         if (idx < D) {
             float o[VEC];
+            if constexpr (VEC == 4) {
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + idx));
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + idx));
+                o[0] = (v[j][0] - mean) * rstd * g4.x + b4.x; o[1] = (v[j][1] - mean) * rstd * g4.y + b4.y;
+                o[2] = (v[j][2] - mean) * rstd * g4.z + b4.z; o[3] = (v[j][3] - mean) * rstd * g4.w + b4.w;
+            } else {
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) o[k] = (v[j][k] - mean) * rstd * __ldg(gamma + idx + k) + __ldg(beta + idx + k);
+                for (int k = 0; k < VEC; ++k) o[k] = (v[j][k] - mean) * rstd * __ldg(gamma + idx + k) + __ldg(beta + idx + k);
+            }
             if (y) {
                 if constexpr (VEC == 4) *reinterpret_cast<float4*>(y + row * ldy + idx) = make_float4(o[0], o[1], o[2], o[3]);
                 else y[row * ldy + idx] = o[0];
@@ -84,7 +91,8 @@ extern "C" nsp_status nsp_layernorm_fwd(const float* x, int64_t ldx, const float
     NSP_CHECK_ARG(M > 0 && D > 0, "layernorm: bad shape M=%d D=%d", M, D);
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec4 = (D % 4 == 0) && (ldx % 4 == 0) && (!y || ldy % 4 == 0) && (!y_bf16 || ldyb % 4 == 0) &&
-                      ((uintptr_t)x % 16 == 0) && (!y || (uintptr_t)y % 16 == 0) && (!y_bf16 || (uintptr_t)y_bf16 % 8 == 0);
+                      ((uintptr_t)x % 16 == 0) && (!y || (uintptr_t)y % 16 == 0) && (!y_bf16 || (uintptr_t)y_bf16 % 8 == 0) &&
+                      ((uintptr_t)gamma % 16 == 0) && ((uintptr_t)beta % 16 == 0);
     const unsigned grid = (unsigned)ceil_div(M, 8);
     __nv_bfloat16* yb = (__nv_bfloat16*)y_bf16;
 #define NSP_LN(VPT, VEC) layernorm_kernel<VPT, VEC><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, eps, in_scale, y, ldy, yb, ldyb, M, D)

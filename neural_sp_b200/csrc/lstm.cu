@@ -1,0 +1,183 @@
+// (Bi)LSTM layer recurrence over packed (length-masked) sequences, persistent cooperative kernel, fp32 math.
+//
+// Replaces  Padding.forward  encoders/rnn.py:534-546  (pack_padded_sequence -> nn.LSTM (cuDNN) -> pad_packed_sequence)
+//           for one layer; the input projection x W_ih^T + b_ih + b_hh of all frames is a tcgen05 GEMM done before.
+// PyTorch parameter layout: weight_hh_l0[_reverse] [4H, H], gate order i, f, g, o.
+// Semantics kept: per-utterance lengths -- state freezes and outputs are zero for t >= len_b; the reverse direction
+// of utterance b starts at its own last frame len_b - 1.
+//
+// Grid = n_dir x (H / 8) CTAs, all co-resident (cooperative launch).  A CTA owns 8 hidden units = 32 gate rows of W_hh,
+// resident in shared memory for the whole sequence (fp32, padded rows: conflict-free).  Per time step every CTA reads
+// h_{t-1} [B, H] from a double-buffered global array (L2, ld.global.cg), computes its 32 x B pre-activations with a
+// 2-row x 4-batch register tile per thread, applies the cell update for its units (c and h live in registers) and
+// publishes h_t; one device-scope barrier per direction per step orders the exchange.
+#include <cooperative_groups.h>
+#include "common.cuh"
+
+namespace nsp {
+namespace {
+
+constexpr int UPC = 8;            // hidden units per CTA
+constexpr int ROWS = 4 * UPC;     // gate rows per CTA
+constexpr int BT = 32;            // batch tile
+constexpr int KC = 128;           // k chunk staged per iteration
+
+struct LstmParams {
+    const float* gx;        // [B, T, ndir*4H]  x W_ih^T + b_ih + b_hh
+    const float* whh;       // [ndir, 4H, H]
+    const int32_t* lens;    // [B]
+    float* y;               // [B, T, ndir*H]   (pre-zeroed)
+    float* hbuf;            // [ndir, 2, B, H]  (pre-zeroed: h_0 = 0)
+    unsigned int* bar;      // [ndir] (pre-zeroed)
+    int B, T, H, ndir;
+};
+
+__device__ __forceinline__ float sigmoid_exact(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void __launch_bounds__(256, 1) lstm_seq_kernel(LstmParams p) {
+    extern __shared__ float sm[];
+    const int H = p.H;
+    const int WP = H + 4;                              // padded row pitch (16-byte aligned, bank-staggered)
+    float* Ws = sm;                                    // [ROWS][WP]   row r = gate * UPC + u
+    float* hs = Ws + ROWS * WP;                        // [BT][KC + 4]
+    float* pre = hs + BT * (KC + 4);                   // [2][ROWS][BT + 1] partial sums of the two k halves
+    const int ctas_per_dir = H / UPC;
+    const int dir = blockIdx.x / ctas_per_dir;
+    const int j0 = (blockIdx.x % ctas_per_dir) * UPC;
+    const int tid = threadIdx.x;
+    const int G = p.ndir * 4 * H;
+
+    // resident W_hh slice
+    const float* wg = p.whh + (size_t)dir * 4 * H * H;
+    for (int e = tid; e < ROWS * H; e += 256) {
+        const int r = e / H, k = e % H;
+        const int gate = r / UPC, u = r % UPC;
+        Ws[r * WP + k] = __ldg(wg + (size_t)(gate * H + j0 + u) * H + k);
+    }
+    __syncthreads();
+
+    // GEMV-like tile: thread = (k half, row pair, batch quad)
+    const int kh = tid >> 7, rp = (tid & 127) >> 3, bq = tid & 7;
+    // cell-update mapping: thread = (unit, batch)
+    const int cu = tid >> 5, cb = tid & 31;
+    const int nbt = (p.B + BT - 1) / BT;
+    float c_state[4], h_state[4];                      // up to 4 batch tiles (B <= 128) kept in registers
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { c_state[i] = 0.f; h_state[i] = 0.f; }
+
+    for (int s = 0; s < p.T; ++s) {
+        const float* hprev = p.hbuf + ((size_t)(dir * 2 + (s & 1)) * p.B) * H;
+        float* hnext = p.hbuf + ((size_t)(dir * 2 + ((s + 1) & 1)) * p.B) * H;
+#pragma unroll 1
+        for (int bt = 0; bt < nbt; ++bt) {
+            const int b0 = bt * BT;
+            float acc[2][4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+            for (int k0 = 0; k0 < H; k0 += KC) {
+                __syncthreads();
+                for (int e = tid; e < BT * (KC / 4); e += 256) {       // stage h_{t-1}[b0:b0+32, k0:k0+KC]
+                    const int b = e / (KC / 4), k4 = e % (KC / 4);
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (b0 + b < p.B && k0 + k4 * 4 < H) v = __ldcg(reinterpret_cast<const float4*>(hprev + (size_t)(b0 + b) * H + k0) + k4);
+                    *reinterpret_cast<float4*>(hs + b * (KC + 4) + k4 * 4) = v;
+                }
+                __syncthreads();
+                const int kbeg = kh * (KC / 2), kend = kbeg + KC / 2;
+                const float* w0 = Ws + (2 * rp) * WP + k0;
+                const float* w1 = w0 + WP;
+                const float* hb = hs + (bq * 4) * (KC + 4);
+#pragma unroll 4
+                for (int k = kbeg; k < kend; k += 4) {
+                    if (k0 + k >= H) break;
+                    const float4 a0 = *reinterpret_cast<const float4*>(w0 + k);
+                    const float4 a1 = *reinterpret_cast<const float4*>(w1 + k);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 hv = *reinterpret_cast<const float4*>(hb + j * (KC + 4) + k);
+                        acc[0][j] = fmaf(a0.x, hv.x, fmaf(a0.y, hv.y, fmaf(a0.z, hv.z, fmaf(a0.w, hv.w, acc[0][j]))));
+                        acc[1][j] = fmaf(a1.x, hv.x, fmaf(a1.y, hv.y, fmaf(a1.z, hv.z, fmaf(a1.w, hv.w, acc[1][j]))));
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) pre[(kh * ROWS + 2 * rp + i) * (BT + 1) + bq * 4 + j] = acc[i][j];
+            __syncthreads();
+            // cell update for (unit cu, batch b0 + cb)
+            const int b = b0 + cb;
+            if (b < p.B) {
+                const int len = min(max(p.lens[b], 0), p.T);
+                if (s < len) {
+                    const int t = dir == 0 ? s : (len - 1 - s);
+                    const float* gxr = p.gx + ((size_t)b * p.T + t) * G + (size_t)dir * 4 * H + j0 + cu;
+                    float g4[4];
+#pragma unroll
+                    for (int gate = 0; gate < 4; ++gate) {
+                        const int r = gate * UPC + cu;
+                        g4[gate] = pre[r * (BT + 1) + cb] + pre[(ROWS + r) * (BT + 1) + cb] + __ldg(gxr + (size_t)gate * H);
+                    }
+                    const float ig = sigmoid_exact(g4[0]), fg = sigmoid_exact(g4[1]), gg = tanhf(g4[2]), og = sigmoid_exact(g4[3]);
+                    float c = c_state[bt], h;
+                    c = fg * c + ig * gg;
+                    h = og * tanhf(c);
+                    c_state[bt] = c; h_state[bt] = h;
+                    p.y[((size_t)b * p.T + t) * (p.ndir * H) + (size_t)dir * H + j0 + cu] = h;
+                }
+                __stcg(hnext + (size_t)b * H + j0 + cu, h_state[bt]);   // frozen state keeps being republished
+            }
+        }
+        // device-scope barrier among the CTAs of this direction
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            atomicAdd(p.bar + dir, 1u);
+            const unsigned target = (unsigned)(s + 1) * (unsigned)ctas_per_dir;
+            while (atomicAdd(p.bar + dir, 0u) < target) { __nanosleep(20); }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+}  // namespace nsp
+
+using namespace nsp;
+
+extern "C" size_t nsp_lstm_workspace_bytes(int B, int H, int ndir) {
+    if (B <= 0 || H <= 0 || ndir <= 0) return 0;
+    return align_up((size_t)ndir * 2 * B * H * sizeof(float), 256) + 256;
+}
+
+extern "C" nsp_status nsp_lstm_seq_fwd(const float* gates_x, const float* w_hh, const int32_t* lens, float* y,
+                                       int B, int T, int H, int ndir, void* workspace, size_t workspace_bytes, void* stream) {
+    NSP_CHECK_ARG(gates_x && w_hh && lens && y && workspace, "lstm_seq: null pointer");
+    NSP_CHECK_ARG(B > 0 && T > 0 && H > 0 && (ndir == 1 || ndir == 2), "lstm_seq: bad shape");
+    if (H % UPC != 0 || H % 4 != 0) { set_error("lstm_seq: H=%d must be a multiple of 8", H); return NSP_ERR_UNSUPPORTED; }
+    if (B > 4 * BT) { set_error("lstm_seq: B=%d unsupported (max 128)", B); return NSP_ERR_UNSUPPORTED; }
+    NSP_CHECK_ARG(workspace_bytes >= nsp_lstm_workspace_bytes(B, H, ndir), "lstm_seq: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = ndir * (H / UPC);
+    const size_t smem = sizeof(float) * ((size_t)ROWS * (H + 4) + (size_t)BT * (KC + 4) + (size_t)2 * ROWS * (BT + 1));
+    if (smem > 226 * 1024) { set_error("lstm_seq: H=%d needs %zu B of shared memory", H, smem); return NSP_ERR_UNSUPPORTED; }
+    NSP_CUDA_OK(cudaFuncSetAttribute(lstm_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    NSP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_seq_kernel, 256, smem));
+    if (per_sm * num_sms() < grid) {
+        set_error("lstm_seq: %d CTAs cannot be co-resident (%d per SM x %d SMs)", grid, per_sm, num_sms());
+        return NSP_ERR_UNSUPPORTED;
+    }
+    LstmParams p;
+    p.gx = gates_x; p.whh = w_hh; p.lens = lens; p.y = y; p.B = B; p.T = T; p.H = H; p.ndir = ndir;
+    const size_t hbytes = align_up((size_t)ndir * 2 * B * H * sizeof(float), 256);
+    p.hbuf = (float*)workspace;
+    p.bar = (unsigned int*)((char*)workspace + hbytes);
+    NSP_CUDA_OK(cudaMemsetAsync(workspace, 0, hbytes + 256, st));
+    NSP_CUDA_OK(cudaMemsetAsync(y, 0, (size_t)B * T * ndir * H * sizeof(float), st));
+    void* args[] = {&p};
+    NSP_CUDA_OK(cudaLaunchCooperativeKernel((void*)lstm_seq_kernel, dim3(grid), dim3(256), args, smem, st));
+    return NSP_OK;
+}
