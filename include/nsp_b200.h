@@ -212,6 +212,17 @@ nsp_status nsp_ctc_greedy(const float* logits, int B, int T, int V, const int32_
 nsp_status nsp_rnnt_joint_tanh(const float* enc, const float* dec, void* out, int out_bf16, int B, int T, int U1,
                                int J, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * (Bi)LSTM layer recurrence over length-masked sequences (persistent cooperative kernel, fp32 math).
+ * Replaces Padding.forward encoders/rnn.py:534-546 (pack_padded_sequence -> nn.LSTM -> pad_packed_sequence) for one
+ * layer; the input projection gates_x = x W_ih^T + b_ih + b_hh [B, T, ndir*4H] (PyTorch gate order i,f,g,o; direction-
+ * major) is computed beforehand with nsp_linear_fwd.  w_hh fp32 [ndir, 4H, H]; lens int32 [B]; y fp32 [B, T, ndir*H]
+ * (zeros for t >= lens[b], like pad_packed_sequence).  H % 8 == 0, B <= 128.
+ * ------------------------------------------------------------------------------------------ */
+size_t nsp_lstm_workspace_bytes(int B, int H, int ndir);
+nsp_status nsp_lstm_seq_fwd(const float* gates_x, const float* w_hh, const int32_t* lens, float* y,
+                            int B, int T, int H, int ndir, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,7 @@ struct LstmParams {
     float* hbuf;            // [ndir, 2, B, H]  (pre-zeroed: h_0 = 0)
     unsigned int* bar;      // [ndir] (pre-zeroed)
     int B, T, H, ndir;
+    int dir0;               // first direction handled by this launch (directions may be launched one at a time)
 };
 
 __device__ __forceinline__ float sigmoid_exact(float x) { return 1.f / (1.f + expf(-x)); }
@@ -42,7 +43,7 @@ __global__ void __launch_bounds__(256, 1) lstm_seq_kernel(LstmParams p) {
     float* hs = Ws + ROWS * WP;                        // [BT][KC + 4]
     float* pre = hs + BT * (KC + 4);                   // [2][ROWS][BT + 1] partial sums of the two k halves
     const int ctas_per_dir = H / UPC;
-    const int dir = blockIdx.x / ctas_per_dir;
+    const int dir = p.dir0 + blockIdx.x / ctas_per_dir;
     const int j0 = (blockIdx.x % ctas_per_dir) * UPC;
     const int tid = threadIdx.x;
     const int G = p.ndir * 4 * H;
@@ -160,14 +161,15 @@ extern "C" nsp_status nsp_lstm_seq_fwd(const float* gates_x, const float* w_hh, 
     if (B > 4 * BT) { set_error("lstm_seq: B=%d unsupported (max 128)", B); return NSP_ERR_UNSUPPORTED; }
     NSP_CHECK_ARG(workspace_bytes >= nsp_lstm_workspace_bytes(B, H, ndir), "lstm_seq: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
-    const int grid = ndir * (H / UPC);
     const size_t smem = sizeof(float) * ((size_t)ROWS * (H + 4) + (size_t)BT * (KC + 4) + (size_t)2 * ROWS * (BT + 1));
     if (smem > 226 * 1024) { set_error("lstm_seq: H=%d needs %zu B of shared memory", H, smem); return NSP_ERR_UNSUPPORTED; }
     NSP_CUDA_OK(cudaFuncSetAttribute(lstm_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     NSP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_seq_kernel, 256, smem));
-    if (per_sm * num_sms() < grid) {
-        set_error("lstm_seq: %d CTAs cannot be co-resident (%d per SM x %d SMs)", grid, per_sm, num_sms());
+    const int capacity = per_sm * num_sms();
+    const int per_dir = H / UPC;
+    if (capacity < per_dir) {
+        set_error("lstm_seq: %d CTAs per direction cannot be co-resident (%d per SM x %d SMs)", per_dir, per_sm, num_sms());
         return NSP_ERR_UNSUPPORTED;
     }
     LstmParams p;
@@ -177,7 +179,12 @@ extern "C" nsp_status nsp_lstm_seq_fwd(const float* gates_x, const float* w_hh, 
     p.bar = (unsigned int*)((char*)workspace + hbytes);
     NSP_CUDA_OK(cudaMemsetAsync(workspace, 0, hbytes + 256, st));
     NSP_CUDA_OK(cudaMemsetAsync(y, 0, (size_t)B * T * ndir * H * sizeof(float), st));
-    void* args[] = {&p};
-    NSP_CUDA_OK(cudaLaunchCooperativeKernel((void*)lstm_seq_kernel, dim3(grid), dim3(256), args, smem, st));
+    // both directions in one cooperative launch when they fit together, else one launch per direction
+    const int dirs_per_launch = (ndir * per_dir <= capacity) ? ndir : 1;
+    for (int d0 = 0; d0 < ndir; d0 += dirs_per_launch) {
+        p.dir0 = d0;
+        void* args[] = {&p};
+        NSP_CUDA_OK(cudaLaunchCooperativeKernel((void*)lstm_seq_kernel, dim3(dirs_per_launch * per_dir), dim3(256), args, smem, st));
+    }
     return NSP_OK;
 }

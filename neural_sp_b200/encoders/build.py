@@ -34,4 +34,14 @@ def build_encoder(args):
         return TransformerEncoder(ffn_activation=args.transformer_ffn_activation, **common)
     if args.enc_type == 'conv':
         return conv
-    raise NotImplementedError("enc_type=%r: RNN encoders run on the reference's cuDNN path (see DESIGN.md)" % args.enc_type)
+    from .rnn import RNNEncoder
+    return RNNEncoder(input_dim=args.input_dim if args.input_type == 'speech' else args.emb_dim, enc_type=args.enc_type,
+                      n_units=args.enc_n_units, n_projs=args.enc_n_projs,
+                      last_proj_dim=args.transformer_dec_d_model if 'transformer' in args.dec_type else 0,
+                      n_layers=args.enc_n_layers, n_layers_sub1=args.enc_n_layers_sub1,
+                      n_layers_sub2=args.enc_n_layers_sub2, dropout_in=args.dropout_in, dropout=args.dropout_enc,
+                      subsample=args.subsample, subsample_type=args.subsample_type, n_stacks=args.n_stacks,
+                      n_splices=args.n_splices, frontend_conv=conv, bidir_sum_fwd_bwd=args.bidirectional_sum_fwd_bwd,
+                      task_specific_layer=args.task_specific_layer, param_init=args.param_init,
+                      chunk_size_current=args.lc_chunk_size_left, chunk_size_right=args.lc_chunk_size_right,
+                      cnn_lookahead=args.cnn_lookahead, rsp_prob=args.rsp_prob_enc)

@@ -1,0 +1,171 @@
+"""(CNN-)LSTM / BLSTM encoder (reference encoders/rnn.py:35-510), B200-native.
+
+Same constructor arguments and state_dict keys (``rnn.N.weight_ih_l0[_reverse]`` ..., ``proj.N.*``, ``subsample.N.*``,
+``bridge*.*``, ``conv.*``); the nn.LSTM modules only hold the parameters.  Per layer the input projection of all frames
+is one tcgen05 GEMM (both directions and both biases folded in) and the recurrence is the persistent LSTM kernel of the
+library, which implements the packed-sequence semantics of ``Padding`` (:534-546) from device-side lengths -- so the
+reference's sort / pack / unsort round trip (:296-298, :375-377) is unnecessary.
+Supported: lstm / blstm (+ conv front-end), projections, sum of directions, the six subsamplers, sub-task outputs,
+bridge.  Latency-controlled BLSTM (``_forward_latency_controlled``), streaming state carry-over and RSP are 'next' rows."""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..modules._prep import prepared, cached, get_precision
+from .encoder_base import EncoderBase
+from .subsampling import (AddSubsampler, ConcatSubsampler, Conv1dSubsampler, DropSubsampler, MaxPoolSubsampler,
+                          MeanPoolSubsampler)
+from .transformer import lens_to_device
+
+
+class RNNEncoder(EncoderBase):
+    def __init__(self, input_dim, enc_type, n_units, n_projs, last_proj_dim, n_layers, n_layers_sub1, n_layers_sub2,
+                 dropout_in, dropout, subsample, subsample_type, n_stacks, n_splices, frontend_conv, bidir_sum_fwd_bwd,
+                 task_specific_layer, param_init, chunk_size_current, chunk_size_right, cnn_lookahead, rsp_prob):
+        super().__init__()
+        subsamples = [1] * n_layers
+        for lth, s in enumerate(list(map(int, subsample.split('_')[:n_layers]))):
+            subsamples[lth] = s
+        self.enc_type = enc_type
+        self.bidirectional = 'blstm' in enc_type
+        self.n_units = n_units
+        self.n_dirs = 2 if self.bidirectional else 1
+        self.n_layers = n_layers
+        self.bidir_sum = bidir_sum_fwd_bwd
+        self.N_c = int(str(chunk_size_current).split('_')[0]) // n_stacks
+        self.N_r = int(str(chunk_size_right).split('_')[0]) // n_stacks
+        self.lc_bidir = (self.N_c > 0 or self.N_r > 0) and self.bidirectional
+        if self.lc_bidir:
+            raise NotImplementedError("latency-controlled BLSTM is a 'next' row (SURVEY.md 8f-4)")
+        if rsp_prob > 0:
+            raise NotImplementedError("random state passing is a training-time streaming feature (out of scope)")
+        self.rsp_prob = rsp_prob
+        self.n_layers_sub1, self.n_layers_sub2 = n_layers_sub1, n_layers_sub2
+        self.task_specific_layer = task_specific_layer
+        self.bridge = self.bridge_sub1 = self.bridge_sub2 = None
+        self.dropout_in = nn.Dropout(p=dropout_in)
+        self.conv = frontend_conv
+        self._odim = self.conv.output_dim if self.conv is not None else input_dim * n_splices * n_stacks
+        self.cnn_lookahead = cnn_lookahead
+        if enc_type != 'conv':
+            self.rnn = nn.ModuleList()
+            self.dropout = nn.Dropout(p=dropout)
+            self.proj = nn.ModuleList() if n_projs > 0 else None
+            self.subsample = nn.ModuleList() if np.prod(subsamples) > 1 else None
+            for lth in range(n_layers):
+                self.rnn += [nn.LSTM(self._odim, n_units, 1, batch_first=True, bidirectional=self.bidirectional)]
+                self._odim = n_units if bidir_sum_fwd_bwd else n_units * self.n_dirs
+                for sub, nl in (('sub1', n_layers_sub1), ('sub2', n_layers_sub2)):
+                    if lth == nl - 1 and task_specific_layer:
+                        setattr(self, 'layer_' + sub, nn.Linear(self._odim, n_units))
+                        setattr(self, '_odim_' + sub, n_units)
+                        if last_proj_dim > 0 and last_proj_dim != self.output_dim:
+                            setattr(self, 'bridge_' + sub, nn.Linear(n_units, last_proj_dim))
+                            setattr(self, '_odim_' + sub, last_proj_dim)
+                if self.proj is not None and lth != n_layers - 1:
+                    self.proj += [nn.Linear(self._odim, n_projs)]
+                    self._odim = n_projs
+                if self.subsample is not None:
+                    odim = self._odim
+                    make = {'max_pool': MaxPoolSubsampler, 'mean_pool': MeanPoolSubsampler, 'drop': DropSubsampler,
+                            'add': AddSubsampler, 'concat': lambda f: ConcatSubsampler(f, odim),
+                            'conv1d': lambda f: Conv1dSubsampler(f, odim)}
+                    self.subsample += [make[subsample_type](subsamples[lth])]
+            if last_proj_dim > 0 and last_proj_dim != self.output_dim:
+                self.bridge = nn.Linear(self._odim, last_proj_dim)
+                self._odim = last_proj_dim
+        self.conv_factor = self.conv.subsampling_factor if self.conv is not None else 1
+        self._factor = self._factor_sub1 = self._factor_sub2 = self.conv_factor
+        if n_layers_sub1 > 1:
+            self._factor_sub1 *= int(np.prod(subsamples[:n_layers_sub1 - 1]))
+        if n_layers_sub2 > 1:
+            self._factor_sub2 *= int(np.prod(subsamples[:n_layers_sub2 - 1]))
+        self._factor *= int(np.prod(subsamples))
+        for n, p in self.named_parameters():       # reference :256-262: uniform(-param_init, param_init), biases 0
+            if 'conv' in n.split('.')[0]:
+                continue
+            if p.dim() == 1:
+                nn.init.constant_(p, 0.)
+            else:
+                nn.init.uniform_(p, a=-param_init, b=param_init)
+        self.reset_cache()
+
+    def reset_cache(self):
+        self.hx_fwd = [None] * self.n_layers
+        self.hx_bwd = [None] * self.n_layers
+
+    def _lstm_layer(self, lth, xs, lens_dev):
+        """One (bi)directional LSTM layer over `[B, T, I]` with packed-sequence semantics."""
+        rnn = self.rnn[lth]
+        prec = get_precision(self)
+        names = ['_l0'] + (['_l0_reverse'] if self.bidirectional else [])
+        w_ih = [getattr(rnn, 'weight_ih' + n) for n in names]
+        w_ihp = prepared(self, 'w_ih%d' % lth, prec, tuple(w_ih), build=lambda *ws: torch.cat(ws, dim=0))
+        bias = cached(self, 'b%d' % lth, tuple(getattr(rnn, 'bias_ih' + n) for n in names) +
+                      tuple(getattr(rnn, 'bias_hh' + n) for n in names),
+                      lambda *bs: (torch.cat(bs[:len(names)]) + torch.cat(bs[len(names):])).float().contiguous())
+        w_hh = cached(self, 'w_hh%d' % lth, tuple(getattr(rnn, 'weight_hh' + n) for n in names),
+                      lambda *ws: torch.stack(ws, dim=0).float().contiguous())
+        gates_x = ops.linear(xs, w_ihp, bias, prec=prec, out_dtype=torch.float32)
+        ys = ops.lstm_seq(gates_x, w_hh, lens_dev, self.n_dirs)
+        if self.bidir_sum and self.bidirectional:
+            half = ys.size(-1) // 2
+            ys = ys[:, :, :half] + ys[:, :, half:]
+        return ys
+
+    def _sub_out(self, xs, module):
+        prec = get_precision(self)
+        if self.task_specific_layer:
+            lin = getattr(self, 'layer_' + module)
+            xs_sub = ops.linear(xs, prepared(self, 'layer_' + module, prec, (lin.weight,)), lin.bias, prec=prec, act='relu')
+        else:
+            xs_sub = xs.clone()
+        bridge = getattr(self, 'bridge_' + module)
+        if bridge is not None:
+            xs_sub = ops.linear(xs_sub, prepared(self, 'bridge_' + module, prec, (bridge.weight,)), bridge.bias, prec=prec)
+        return xs_sub
+
+    def forward(self, xs, xlens, task, streaming=False, lookback=False, lookahead=False):
+        if streaming:
+            raise NotImplementedError("streaming inference is a 'next' row (SURVEY.md 8f-4)")
+        if self.training and (self.dropout_in.p > 0 or (self.enc_type != 'conv' and self.dropout.p > 0)):
+            raise NotImplementedError("dropout > 0 in training mode is not on the B200 path yet")
+        eouts = {'ys': {'xs': None, 'xlens': None}, 'ys_sub1': {'xs': None, 'xlens': None},
+                 'ys_sub2': {'xs': None, 'xlens': None}}
+        xlens = torch.IntTensor([int(v) for v in xlens])
+        prec = get_precision(self)
+        with torch.no_grad():
+            if self.conv is not None:
+                xs, xlens = self.conv(xs, xlens, lookback=lookback, lookahead=lookahead)
+                if self.enc_type == 'conv':
+                    eouts['ys']['xs'], eouts['ys']['xlens'] = xs, xlens
+                    return eouts
+            xs = xs.float()
+            for lth in range(self.n_layers):
+                xs = self._lstm_layer(lth, xs, lens_to_device(xlens, xs.device))
+                if lth == self.n_layers_sub1 - 1:
+                    xs_sub1, xlens_sub1 = self._sub_out(xs, 'sub1'), xlens.clone()
+                    if task == 'ys_sub1':
+                        eouts[task]['xs'], eouts[task]['xlens'] = xs_sub1, xlens_sub1
+                        return eouts
+                if lth == self.n_layers_sub2 - 1:
+                    xs_sub2, xlens_sub2 = self._sub_out(xs, 'sub2'), xlens.clone()
+                    if task == 'ys_sub2':
+                        eouts[task]['xs'], eouts[task]['xlens'] = xs_sub2, xlens_sub2
+                        return eouts
+                if self.proj is not None and lth != self.n_layers - 1:
+                    lin = self.proj[lth]
+                    xs = ops.linear(xs, prepared(self, 'proj%d' % lth, prec, (lin.weight,)), lin.bias, prec=prec, act='relu')
+                if self.subsample is not None:
+                    xs, xlens = self.subsample[lth](xs, xlens)
+            if self.bridge is not None:
+                xs = ops.linear(xs, prepared(self, 'bridge', prec, (self.bridge.weight,)), self.bridge.bias, prec=prec)
+            xs = xs[:, :int(xlens.max())]
+        if task in ['all', 'ys']:
+            eouts['ys']['xs'], eouts['ys']['xlens'] = xs, xlens
+        if self.n_layers_sub1 >= 1 and task == 'all':
+            eouts['ys_sub1']['xs'], eouts['ys_sub1']['xlens'] = xs_sub1, xlens_sub1
+        if self.n_layers_sub2 >= 1 and task == 'all':
+            eouts['ys_sub2']['xs'], eouts['ys_sub2']['xlens'] = xs_sub2, xlens_sub2
+        return eouts

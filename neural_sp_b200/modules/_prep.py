@@ -29,3 +29,17 @@ def prepared(module, name, prec, params, build=None):
 
 def act_dtype(prec):
     return torch.bfloat16 if prec == "bf16" else torch.float32
+
+
+def cached(module, name, params, build):
+    """Generic per-module cache of a tensor derived from parameters (same invalidation rule as ``prepared``).
+    Caches live on the module object: a global cache keyed by data_ptr would go stale when memory is reused."""
+    cache = module.__dict__.setdefault("_nsp_cache", {})
+    ver = tuple((p.data_ptr(), p._version) for p in params)
+    hit = cache.get((name, "raw"))
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    with torch.no_grad():
+        val = build(*params)
+    cache[(name, "raw")] = (ver, val)
+    return val

@@ -8,7 +8,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ._prep import prepared, get_precision, act_dtype
+from ._prep import prepared, cached, get_precision, act_dtype
 from .initialization import init_with_xavier_uniform, init_with_lecun_normal
 
 
@@ -55,7 +55,9 @@ class ConformerConvBlock(nn.Module):
         g = ops.linear(xs, w1, self.pointwise_conv1.bias, prec=prec, glu=True, out_dtype=act_dtype(prec))
         rm = getattr(self.norm, "running_mean", None)
         rv = getattr(self.norm, "running_var", None)
-        c = ops.conformer_conv(g, self.depthwise_conv.weight, self.depthwise_conv.bias, self.normalization,
+        taps = cached(self, "dw_taps", (self.depthwise_conv.weight,),
+                      lambda w: w.reshape(w.size(0), -1).t().contiguous().float())          # [k, d]
+        c = ops.conformer_conv(g, taps, self.depthwise_conv.bias, self.normalization,
                                self.norm.weight, self.norm.bias, self.norm.eps, rm, rv, causal=self.causal)
         w2 = prepared(self, "pw2", prec, (self.pointwise_conv2.weight,), build=lambda w: w.squeeze(-1))
         return ops.linear(c, w2, self.pointwise_conv2.bias, prec=prec, residual=residual, out_dtype=torch.float32, out=out)

@@ -265,27 +265,16 @@ def relpos_attention(q, k, v, klens, n_heads, r=None, u_bias=None, v_bias=None, 
 NORM_MODE = {"layer_norm": 0, "batch_norm": 1, "group_norm": 2}
 
 
-_TAPS_CACHE = {}
-
-
-def _taps_kd(dw_weight, d, k):
-    """nn.Conv1d depthwise weight [d,1,k] -> fp32 [k,d] (cached per parameter version)."""
-    key = (dw_weight.data_ptr(), dw_weight._version, d, k)
-    hit = _TAPS_CACHE.get(dw_weight.data_ptr())
-    if hit is not None and hit[0] == key:
-        return hit[1]
-    w = dw_weight.detach().reshape(d, k).t().contiguous().float()
-    _TAPS_CACHE[dw_weight.data_ptr()] = (key, w)
-    return w
-
-
 def conformer_conv(x, dw_weight, dw_bias, norm_mode, norm_w, norm_b, eps, run_mean=None, run_var=None, causal=False):
     """y = Swish(Norm(depthwise_conv(x) + bias)) on `[B, T, d]` (nsp_conformer_conv_fwd)."""
     _require_cuda(x)
     B, T, d = x.shape
     x = x if x.stride(2) == 1 and x.stride(0) == T * x.stride(1) else x.contiguous()
-    k = dw_weight.shape[-1]
-    w = _taps_kd(dw_weight, d, k)
+    if dw_weight.dim() == 2:                      # already transposed taps [k, d] (cached by the caller)
+        k, w = dw_weight.shape[0], dw_weight
+    else:                                         # nn.Conv1d depthwise weight [d, 1, k]
+        k = dw_weight.shape[-1]
+        w = dw_weight.detach().reshape(d, k).t().contiguous().float()
     y = torch.empty(B, T, d, dtype=x.dtype, device=x.device)
     _run("nsp_conformer_conv_fwd", lib.nsp_conformer_conv_fwd, int(x.dtype == torch.bfloat16), ptr(x), x.stride(1), ptr(w), ptr(dw_bias),
                                      NORM_MODE[norm_mode], ptr(norm_w), ptr(norm_b), ptr(run_mean), ptr(run_var),
@@ -448,4 +437,20 @@ def pool_time(x, factor, mode):
     y = torch.empty(B, -(-T // factor), D, dtype=x.dtype, device=x.device)
     _run("nsp_pool_time_fwd", lib.nsp_pool_time_fwd, int(x.dtype == torch.bfloat16), ptr(x), ptr(y), B, T, D, factor,
          POOL_MODE[mode], current_stream_ptr())
+    return y
+
+
+def lstm_seq(gates_x, w_hh, lens, n_dirs):
+    """LSTM recurrence of one layer (nsp_lstm_seq_fwd): gates_x fp32 `[B,T,n_dirs*4H]`, w_hh fp32 `[n_dirs,4H,H]`,
+    lens int32 `[B]` CUDA -> y fp32 `[B,T,n_dirs*H]` (zeros beyond each length)."""
+    _require_cuda(gates_x, w_hh, lens)
+    gates_x = gates_x.contiguous().float()
+    w_hh = w_hh.contiguous().float()
+    B, T, G = gates_x.shape
+    H = G // (4 * n_dirs)
+    ws_bytes = lib.nsp_lstm_workspace_bytes(B, H, n_dirs)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=gates_x.device)
+    y = torch.empty(B, T, n_dirs * H, dtype=torch.float32, device=gates_x.device)
+    _run("nsp_lstm_seq_fwd", lib.nsp_lstm_seq_fwd, ptr(gates_x), ptr(w_hh), ptr(lens), ptr(y), B, T, H, n_dirs, ptr(ws),
+         ws_bytes, current_stream_ptr(), flops=2.0 * B * T * n_dirs * 4 * H * H, tag="lstm_seq")
     return y

@@ -100,12 +100,15 @@ def gen_ctc():
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["ctc", "encoder", "rnnt"]
+    what = sys.argv[1:] or ["ctc", "encoder", "rnn", "rnnt"]
     if "ctc" in what:
         gen_ctc()
     if "encoder" in what:
         from gen_golden_encoder import gen_encoder
         gen_encoder()
+    if "rnn" in what:
+        from gen_golden_encoder import gen_rnn_encoder
+        gen_rnn_encoder()
     if "rnnt" in what:
         from gen_golden_encoder import gen_rnnt
         gen_rnnt()

@@ -149,3 +149,49 @@ if __name__ == "__main__":
     import_reference()
     gen_encoder()
     gen_rnnt()
+
+
+def gen_rnn_encoder():
+    """RNNEncoder goldens: BASELINE configs[0] structure (BLSTM 2x256, no CNN) and a small conv_lstm with projections."""
+    import importlib
+    mod = importlib.import_module('neural_sp.models.seq2seq.encoders.rnn')
+    conv_mod = importlib.import_module('neural_sp.models.seq2seq.encoders.conv')
+    base = dict(input_dim=80, enc_type='blstm', n_units=256, n_projs=0, last_proj_dim=0, n_layers=2, n_layers_sub1=0,
+                n_layers_sub2=0, dropout_in=0.0, dropout=0.0, subsample="1_1", subsample_type='drop', n_stacks=1,
+                n_splices=1, frontend_conv=None, bidir_sum_fwd_bwd=False, task_specific_layer=False, param_init=0.1,
+                chunk_size_current="0", chunk_size_right="0", cnn_lookahead=True, rsp_prob=0.)
+    cases = {
+        "rnn_c1_blstm": dict(args={}, conv=None, B=2, T=200, xlens=[200, 173]),
+        "rnn_conv_lstm_proj": dict(args=dict(enc_type='conv_lstm', n_units=64, n_projs=32, n_layers=3, subsample="1_2_1",
+                                             subsample_type='max_pool', last_proj_dim=40, n_layers_sub1=2),
+                                   conv=dict(CONV, poolings="(2,2)_(2,2)", bottleneck_dim=0), B=3, T=90, xlens=[90, 77, 41]),
+        "rnn_blstm_sum": dict(args=dict(n_units=32, bidir_sum_fwd_bwd=True, subsample="2_1", subsample_type='concat'),
+                              conv=None, B=3, T=37, xlens=[37, 30, 5]),
+    }
+    for name, case in cases.items():
+        torch.manual_seed(0)
+        args = dict(base)
+        args.update(case["args"])
+        if case["conv"] is not None:
+            args["frontend_conv"] = conv_mod.ConvEncoder(**case["conv"])
+        enc = mod.RNNEncoder(**args)
+        with torch.no_grad():                      # weights rounded to fp16-representable values: fixture stored as fp16
+            for p_ in enc.parameters():
+                p_.copy_(p_.half().float())
+        enc.eval()
+        rng = np.random.default_rng(4321)
+        B, T = case["B"], case["T"]
+        xs = np.zeros((B, T, 80), np.float32)
+        for b, n in enumerate(case["xlens"]):
+            xs[b, :n] = rng.standard_normal((n, 80)).astype(np.float32)
+        with torch.no_grad():
+            out = enc(torch.from_numpy(xs), torch.IntTensor(case["xlens"]), task='all')
+        save = {"sd." + k: v.numpy().astype(np.float16) for k, v in enc.state_dict().items()}
+        save.update(xs=xs, xlens=np.array(case["xlens"], np.int32), ys=out['ys']['xs'].numpy(),
+                    xlens_out=np.asarray(out['ys']['xlens']).astype(np.int32))
+        if out['ys_sub1']['xs'] is not None:
+            save["ys_sub1"] = out['ys_sub1']['xs'].numpy()
+        cfg = {k: v for k, v in args.items() if k != "frontend_conv"}
+        save["cfg"] = np.array(json.dumps(dict(args=cfg, conv=case["conv"])))
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **save)
+        print("rnn", name, out['ys']['xs'].shape, np.asarray(out['ys']['xlens']).tolist())
