@@ -444,13 +444,21 @@ __device__ __forceinline__ void st_states(float* p, const float (&v)[K]) {
     }
 }
 
-template <int K>
-__global__ void __launch_bounds__(64) ctc_lattice_warp_kernel(CtcParams p) {
+template <int K, int NWD>
+__global__ void __launch_bounds__(64 * NWD) ctc_lattice_warp_kernel(CtcParams p) {
+    // NWD warps per direction (alpha: warps [0,NWD), beta: warps [NWD,2*NWD)); each lane owns K consecutive states.
+    // Inside a warp neighbours travel by shuffle; across warps through a double-buffered smem slot + a named barrier
+    // per direction.  Spreading one utterance over 4 SM sub-partitions quarters the serial instruction stream per step.
     constexpr int PF = (K <= 4) ? 8 : (K == 8 ? 4 : 2);      // emission prefetch depth (steps)
+    constexpr int NL = 32 * NWD;                              // lanes per direction
     __shared__ int32_t s_lab[256 + 8];
+    __shared__ float s_bnd[2][2][NWD][2];                     // [dir][parity][warp][2 boundary states]
+    __shared__ float s_red[NWD][2];
     const int b = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool is_beta = warp == 1;
+    const bool is_beta = warp >= NWD;
+    const int wd = warp % NWD;
+    const int glane = wd * 32 + lane;
     const int Sp = p.Sp;
     const int L = min(max(p.ylens[b], 0), p.Lmax);
     const int S = 2 * L + 1;
@@ -459,11 +467,17 @@ __global__ void __launch_bounds__(64) ctc_lattice_warp_kernel(CtcParams p) {
     const int64_t base = (int64_t)b * p.T * Sp;
     const float* em = p.emit + base;
     float* gout = (is_beta ? p.beta : p.alpha) + base;
+    auto dir_barrier = [&]() {
+        if constexpr (NWD > 1) {
+            if (is_beta) asm volatile("bar.sync 2, %0;" :: "n"(NL) : "memory");
+            else asm volatile("bar.sync 1, %0;" :: "n"(NL) : "memory");
+        }
+    };
 
-    for (int i = threadIdx.x; i < L; i += 64) s_lab[i] = lab[i];
+    for (int i = threadIdx.x; i < L; i += 64 * NWD) s_lab[i] = lab[i];
     __syncthreads();
     // same-label chains for the sparse gradient fix-up (consumed by ctc_fixup_kernel)
-    for (int s = threadIdx.x; s < S; s += 64) {
+    for (int s = threadIdx.x; s < S; s += 64 * NWD) {
         int nx = -1, hd = 1;
         if (s & 1) {
             const int me = s_lab[s >> 1];
@@ -474,7 +488,7 @@ __global__ void __launch_bounds__(64) ctc_lattice_warp_kernel(CtcParams p) {
         p.head[(int64_t)b * Sp + s] = (int16_t)hd;
     }
 
-    const int s0 = lane * K;
+    const int s0 = glane * K;
     bool valid[K], skip[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -487,7 +501,7 @@ __global__ void __launch_bounds__(64) ctc_lattice_warp_kernel(CtcParams p) {
         }
     }
     if (Tb <= 0) {
-        if (threadIdx.x == 0) { const float v = (L == 0) ? 0.f : 1.0e30f; p.nll_raw[b] = v; p.nll[b] = (L == 0) ? 0.f : 0.f; }
+        if (threadIdx.x == 0) { p.nll_raw[b] = (L == 0) ? 0.f : 1.0e30f; p.nll[b] = 0.f; }
         return;
     }
     const bool lane_active = s0 < S;                      // lanes beyond the path never touch memory
@@ -505,16 +519,16 @@ __global__ void __launch_bounds__(64) ctc_lattice_warp_kernel(CtcParams p) {
     float own[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) own[k] = NSP_NEG_BIG;
+    const int dsel = is_beta ? 1 : 0;
 
     for (int i0 = 0; i0 < Tb; i0 += PF) {
 #pragma unroll
         for (int q = 0; q < PF; ++q) {
             const int i = i0 + q;
-            if (i < Tb) {                                  // warp-uniform
+            if (i < Tb) {                                  // uniform over the CTA
                 float e[K];
 #pragma unroll
                 for (int k = 0; k < K; ++k) e[k] = ring[q][k];
-                // refill this ring slot with the row PF steps ahead
                 if (lane_active && i + PF < Tb) ld_states<K>(em + (int64_t)trow(i + PF) * Sp + s0, ring[q]);
                 float nw[K];
                 if (i == 0) {
@@ -525,17 +539,24 @@ __global__ void __launch_bounds__(64) ctc_lattice_warp_kernel(CtcParams p) {
                         nw[k] = (valid[k] && start) ? e[k] : NSP_NEG_BIG;
                     }
                 } else {
-                    float n1, n2;     // neighbours across the lane boundary
+                    // the two states adjacent to this lane's block, from the previous step:
+                    //   alpha: n1 = state s0-1, n2 = state s0-2;   beta: n1 = state s0+K, n2 = state s0+K+1
+                    float n1, n2;
+                    float b1 = NSP_NEG_BIG, b2 = NSP_NEG_BIG;    // values owned by the neighbouring warp
+                    if constexpr (NWD > 1) {
+                        const int nbw = is_beta ? wd + 1 : wd - 1;
+                        if (nbw >= 0 && nbw < NWD) { b1 = s_bnd[dsel][(i - 1) & 1][nbw][0]; b2 = s_bnd[dsel][(i - 1) & 1][nbw][1]; }
+                    }
                     if (!is_beta) {
                         n1 = __shfl_up_sync(0xffffffffu, own[K - 1], 1);
                         n2 = (K >= 2) ? __shfl_up_sync(0xffffffffu, own[K >= 2 ? K - 2 : 0], 1) : __shfl_up_sync(0xffffffffu, own[0], 2);
-                        if (lane == 0) { n1 = NSP_NEG_BIG; n2 = NSP_NEG_BIG; }
-                        if (K == 1 && lane == 1) n2 = NSP_NEG_BIG;
+                        if (lane == 0) { n1 = b1; n2 = b2; }
+                        if (K == 1 && lane == 1) n2 = b1;
                     } else {
                         n1 = __shfl_down_sync(0xffffffffu, own[0], 1);
                         n2 = (K >= 2) ? __shfl_down_sync(0xffffffffu, own[K >= 2 ? 1 : 0], 1) : __shfl_down_sync(0xffffffffu, own[0], 2);
-                        if (lane == 31) { n1 = NSP_NEG_BIG; n2 = NSP_NEG_BIG; }
-                        if (K == 1 && lane == 30) n2 = NSP_NEG_BIG;
+                        if (lane == 31) { n1 = b1; n2 = b2; }
+                        if (K == 1 && lane == 30) n2 = b1;
                     }
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
@@ -555,20 +576,46 @@ __global__ void __launch_bounds__(64) ctc_lattice_warp_kernel(CtcParams p) {
 #pragma unroll
                 for (int k = 0; k < K; ++k) own[k] = nw[k];
                 if (lane_active) st_states<K>(gout + (int64_t)trow(i) * Sp + s0, own);
+                if constexpr (NWD > 1) {
+                    // publish this warp's boundary states for the neighbouring warp's next step
+                    if (!is_beta) {
+                        // neighbour (wd+1) needs states (first-1, first-2) = last two states of this warp
+                        if (K >= 2) { if (lane == 31) { s_bnd[0][i & 1][wd][0] = own[K - 1]; s_bnd[0][i & 1][wd][1] = own[K >= 2 ? K - 2 : 0]; } }
+                        else { if (lane == 31) s_bnd[0][i & 1][wd][0] = own[0]; if (lane == 30) s_bnd[0][i & 1][wd][1] = own[0]; }
+                    } else {
+                        if (K >= 2) { if (lane == 0) { s_bnd[1][i & 1][wd][0] = own[0]; s_bnd[1][i & 1][wd][1] = own[K >= 2 ? 1 : 0]; } }
+                        else { if (lane == 0) s_bnd[1][i & 1][wd][0] = own[0]; if (lane == 1) s_bnd[1][i & 1][wd][1] = own[0]; }
+                    }
+                    dir_barrier();
+                }
             }
         }
     }
     if (!is_beta) {
-        // nll = -lse(alpha_{T-1}(S-1), alpha_{T-1}(S-2))
+        // nll = -lse(alpha_{T-1}(S-1), alpha_{T-1}(S-2)); the two states may sit in different warps
         float m = NSP_NEG_BIG;
 #pragma unroll
         for (int k = 0; k < K; ++k) { const int s = s0 + k; if (s == S - 1 || s == S - 2) m = fmaxf(m, own[k]); }
-        const float M = warp_max(m);
+        float M = warp_max(m);
+        if constexpr (NWD > 1) {
+            if (lane == 0) s_red[wd][0] = M;
+            dir_barrier();
+            M = s_red[0][0];
+#pragma unroll
+            for (int w = 1; w < NWD; ++w) M = fmaxf(M, s_red[w][0]);
+        }
         float sm_ = 0.f;
 #pragma unroll
         for (int k = 0; k < K; ++k) { const int s = s0 + k; if (s == S - 1 || s == S - 2) sm_ += __expf(own[k] - M); }
         sm_ = warp_sum(sm_);
-        if (lane == 0) {
+        if constexpr (NWD > 1) {
+            if (lane == 0) s_red[wd][1] = sm_;
+            dir_barrier();
+            sm_ = 0.f;
+#pragma unroll
+            for (int w = 0; w < NWD; ++w) sm_ += s_red[w][1];
+        }
+        if (threadIdx.x == 0) {
             const float nll = -(M + __logf(sm_));
             p.nll_raw[b] = nll;
             p.nll[b] = (nll < 1.0e29f) ? nll : 0.f;
@@ -758,12 +805,15 @@ extern "C" nsp_status nsp_ctc_loss_fwd_bwd(const float* logits, int64_t stride_b
     // ---- K2 / K3 ----
     const int Smax = 2 * Lmax + 1;
     if (Smax <= 512 && Lmax <= 256) {
-        const int k = ceil_div(Smax, 32);
-        if (k <= 1) ctc_lattice_warp_kernel<1><<<B, 64, 0, st>>>(p);
-        else if (k <= 2) ctc_lattice_warp_kernel<2><<<B, 64, 0, st>>>(p);
-        else if (k <= 4) ctc_lattice_warp_kernel<4><<<B, 64, 0, st>>>(p);
-        else if (k <= 8) ctc_lattice_warp_kernel<8><<<B, 64, 0, st>>>(p);
-        else ctc_lattice_warp_kernel<16><<<B, 64, 0, st>>>(p);
+        // four warps per direction (one per SM sub-partition) unless the path is so short that one warp holds it
+        if (Smax <= 32) {
+            ctc_lattice_warp_kernel<1, 1><<<B, 64, 0, st>>>(p);
+        } else {
+            const int k = ceil_div(Smax, 128);
+            if (k <= 1) ctc_lattice_warp_kernel<1, 4><<<B, 256, 0, st>>>(p);
+            else if (k <= 2) ctc_lattice_warp_kernel<2, 4><<<B, 256, 0, st>>>(p);
+            else ctc_lattice_warp_kernel<4, 4><<<B, 256, 0, st>>>(p);
+        }
         NSP_LAUNCH_OK();
         ctc_fixup_kernel<<<(unsigned)(ceil_div64((int64_t)bt, 8) + 1), 256, 0, st>>>(p);
         NSP_LAUNCH_OK();

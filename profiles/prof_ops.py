@@ -37,6 +37,21 @@ elif which == "ctc":
     ys = [rng.integers(4, V, size=56).tolist() for _ in range(B)]
     labels, ylens, _ = ops.pack_labels(ys, logits.device)
     elens = torch.full((B,), T, dtype=torch.int32, device=dev)
-    for _ in range(5):
-        ops.ctc_loss_fwd_bwd(logits, labels, elens, ylens, 0, 0.1)
-    torch.cuda.synchronize()
+    for (B, T, V) in [(32, 125, 10000), (32, 250, 10000), (32, 125, 1000)]:
+        logits = torch.randn(B, T, V, device=dev)
+        L = int(0.45 * T)
+        ys = [rng.integers(4, V, size=L).tolist() for _ in range(B)]
+        labels, ylens, _ = ops._pack_labels(ys, logits.device)
+        elens = torch.full((B,), T, dtype=torch.int32, device=dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        for _ in range(5):
+            ops.ctc_loss_fwd_bwd(logits, labels, elens, ylens, 0, 0.1)
+        torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(20):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); ops.ctc_loss_fwd_bwd(logits, labels, elens, ylens, 0, 0.1); e.record()
+            torch.cuda.synchronize(); tot += s.elapsed_time(e)
+        ms = tot / 20
+        print("ctc B=%d T=%d V=%d L=%d: %.4f ms/batch  %.1f GB/s algorithmic (8 B/logit)" % (B, T, V, L, ms, 8.0 * B * T * V / ms / 1e6))
