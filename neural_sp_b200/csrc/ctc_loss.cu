@@ -444,13 +444,21 @@ __device__ __forceinline__ void st_states(float* p, const float (&v)[K]) {
     }
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
 template <int K, int NWD>
 __global__ void __launch_bounds__(64 * NWD) ctc_lattice_warp_kernel(CtcParams p) {
     // NWD warps per direction (alpha: warps [0,NWD), beta: warps [NWD,2*NWD)); each lane owns K consecutive states.
     // Inside a warp neighbours travel by shuffle; across warps through a double-buffered smem slot + a named barrier
-    // per direction.  Spreading one utterance over 4 SM sub-partitions quarters the serial instruction stream per step.
-    constexpr int PF = (K <= 4) ? 8 : (K == 8 ? 4 : 2);      // emission prefetch depth (steps)
+    // per direction.  Emission rows are staged CT steps at a time into shared memory with cp.async (double buffered),
+    // so the serial chain per step is: 1 LDS, 2 shuffles, one log-sum-exp, 1 STG, boundary publish, barrier.
+    constexpr int CT = 8;                                     // time steps per staged chunk
     constexpr int NL = 32 * NWD;                              // lanes per direction
+    extern __shared__ __align__(16) float s_em[];             // [dir][2 buffers][CT][Sp]
     __shared__ int32_t s_lab[256 + 8];
     __shared__ float s_bnd[2][2][NWD][2];                     // [dir][parity][warp][2 boundary states]
     __shared__ float s_red[NWD][2];
@@ -467,11 +475,11 @@ __global__ void __launch_bounds__(64 * NWD) ctc_lattice_warp_kernel(CtcParams p)
     const int64_t base = (int64_t)b * p.T * Sp;
     const float* em = p.emit + base;
     float* gout = (is_beta ? p.beta : p.alpha) + base;
+    const int dsel = is_beta ? 1 : 0;
+    float* my_em = s_em + (size_t)dsel * 2 * CT * Sp;
     auto dir_barrier = [&]() {
-        if constexpr (NWD > 1) {
-            if (is_beta) asm volatile("bar.sync 2, %0;" :: "n"(NL) : "memory");
-            else asm volatile("bar.sync 1, %0;" :: "n"(NL) : "memory");
-        }
+        if (is_beta) asm volatile("bar.sync 2, %0;" :: "n"(NL) : "memory");
+        else asm volatile("bar.sync 1, %0;" :: "n"(NL) : "memory");
     };
 
     for (int i = threadIdx.x; i < L; i += 64 * NWD) s_lab[i] = lab[i];
@@ -504,92 +512,108 @@ __global__ void __launch_bounds__(64 * NWD) ctc_lattice_warp_kernel(CtcParams p)
         if (threadIdx.x == 0) { p.nll_raw[b] = (L == 0) ? 0.f : 1.0e30f; p.nll[b] = 0.f; }
         return;
     }
-    const bool lane_active = s0 < S;                      // lanes beyond the path never touch memory
-    auto trow = [&](int i) { return is_beta ? (Tb - 1 - i) : i; };
-
-    float ring[PF][K];
-#pragma unroll
-    for (int q = 0; q < PF; ++q) {
-        if (lane_active && q < Tb) ld_states<K>(em + (int64_t)trow(q) * Sp + s0, ring[q]);
-        else {
-#pragma unroll
-            for (int k = 0; k < K; ++k) ring[q][k] = 0.f;
+    const bool lane_active = s0 < S;                      // lanes beyond the path never store
+    // stage chunk c (steps c*CT .. c*CT+CT-1 of this direction's sweep) into buffer c & 1
+    const int vec_per_row = Sp / 4;
+    auto stage = [&](int c) {
+        float* dst = my_em + (size_t)(c & 1) * CT * Sp;
+        for (int e = glane; e < CT * vec_per_row; e += NL) {
+            const int tt = e / vec_per_row, v4 = e % vec_per_row;
+            const int i = c * CT + tt;
+            if (i < Tb) {
+                const int t = is_beta ? (Tb - 1 - i) : i;
+                cp_async16(dst + tt * Sp + v4 * 4, em + (int64_t)t * Sp + v4 * 4);
+            }
         }
-    }
+        cp_async_commit();
+    };
+    const int nchunks = (Tb + CT - 1) / CT;
+    stage(0);
+    if (nchunks > 1) stage(1); else cp_async_commit();
+
     float own[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) own[k] = NSP_NEG_BIG;
-    const int dsel = is_beta ? 1 : 0;
+    const int nbw = is_beta ? wd + 1 : wd - 1;
+    const bool has_nb = (nbw >= 0 && nbw < NWD);
+    const int64_t gstep = is_beta ? -(int64_t)Sp : (int64_t)Sp;
+    float* gptr = gout + (int64_t)(is_beta ? (Tb - 1) : 0) * Sp + s0;
 
-    for (int i0 = 0; i0 < Tb; i0 += PF) {
+    for (int c = 0; c < nchunks; ++c) {
+        cp_async_wait<1>();
+        dir_barrier();                                     // chunk c landed for every thread of this direction
+        const float* ebuf = my_em + (size_t)(c & 1) * CT * Sp + s0;
+        const int nst = min(CT, Tb - c * CT);
+        for (int tt = 0; tt < nst; ++tt) {
+            const int i = c * CT + tt;
+            float e[K];
+            if constexpr (K == 1) e[0] = ebuf[tt * Sp];
+            else if constexpr (K == 2) { float2 t2 = *reinterpret_cast<const float2*>(ebuf + tt * Sp); e[0] = t2.x; e[1] = t2.y; }
+            else {
 #pragma unroll
-        for (int q = 0; q < PF; ++q) {
-            const int i = i0 + q;
-            if (i < Tb) {                                  // uniform over the CTA
-                float e[K];
-#pragma unroll
-                for (int k = 0; k < K; ++k) e[k] = ring[q][k];
-                if (lane_active && i + PF < Tb) ld_states<K>(em + (int64_t)trow(i + PF) * Sp + s0, ring[q]);
-                float nw[K];
-                if (i == 0) {
-#pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const int s = s0 + k;
-                        const bool start = is_beta ? (s >= S - 2) : (s <= 1);
-                        nw[k] = (valid[k] && start) ? e[k] : NSP_NEG_BIG;
-                    }
-                } else {
-                    // the two states adjacent to this lane's block, from the previous step:
-                    //   alpha: n1 = state s0-1, n2 = state s0-2;   beta: n1 = state s0+K, n2 = state s0+K+1
-                    float n1, n2;
-                    float b1 = NSP_NEG_BIG, b2 = NSP_NEG_BIG;    // values owned by the neighbouring warp
-                    if constexpr (NWD > 1) {
-                        const int nbw = is_beta ? wd + 1 : wd - 1;
-                        if (nbw >= 0 && nbw < NWD) { b1 = s_bnd[dsel][(i - 1) & 1][nbw][0]; b2 = s_bnd[dsel][(i - 1) & 1][nbw][1]; }
-                    }
-                    if (!is_beta) {
-                        n1 = __shfl_up_sync(0xffffffffu, own[K - 1], 1);
-                        n2 = (K >= 2) ? __shfl_up_sync(0xffffffffu, own[K >= 2 ? K - 2 : 0], 1) : __shfl_up_sync(0xffffffffu, own[0], 2);
-                        if (lane == 0) { n1 = b1; n2 = b2; }
-                        if (K == 1 && lane == 1) n2 = b1;
-                    } else {
-                        n1 = __shfl_down_sync(0xffffffffu, own[0], 1);
-                        n2 = (K >= 2) ? __shfl_down_sync(0xffffffffu, own[K >= 2 ? 1 : 0], 1) : __shfl_down_sync(0xffffffffu, own[0], 2);
-                        if (lane == 31) { n1 = b1; n2 = b2; }
-                        if (K == 1 && lane == 30) n2 = b1;
-                    }
-#pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        float a1, a2;
-                        if (!is_beta) {
-                            a1 = (k >= 1) ? own[k >= 1 ? k - 1 : 0] : n1;
-                            a2 = (k >= 2) ? own[k >= 2 ? k - 2 : 0] : ((k == 1) ? n1 : n2);
-                        } else {
-                            a1 = (k + 1 < K) ? own[k + 1 < K ? k + 1 : 0] : n1;
-                            a2 = (k + 2 < K) ? own[k + 2 < K ? k + 2 : 0] : ((k + 2 == K) ? n1 : n2);
-                        }
-                        if (!skip[k]) a2 = NSP_NEG_BIG;
-                        float v = lse3(own[k], a1, a2) + e[k];
-                        nw[k] = valid[k] ? fmaxf(v, NSP_NEG_BIG) : NSP_NEG_BIG;
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < K; ++k) own[k] = nw[k];
-                if (lane_active) st_states<K>(gout + (int64_t)trow(i) * Sp + s0, own);
-                if constexpr (NWD > 1) {
-                    // publish this warp's boundary states for the neighbouring warp's next step
-                    if (!is_beta) {
-                        // neighbour (wd+1) needs states (first-1, first-2) = last two states of this warp
-                        if (K >= 2) { if (lane == 31) { s_bnd[0][i & 1][wd][0] = own[K - 1]; s_bnd[0][i & 1][wd][1] = own[K >= 2 ? K - 2 : 0]; } }
-                        else { if (lane == 31) s_bnd[0][i & 1][wd][0] = own[0]; if (lane == 30) s_bnd[0][i & 1][wd][1] = own[0]; }
-                    } else {
-                        if (K >= 2) { if (lane == 0) { s_bnd[1][i & 1][wd][0] = own[0]; s_bnd[1][i & 1][wd][1] = own[K >= 2 ? 1 : 0]; } }
-                        else { if (lane == 0) s_bnd[1][i & 1][wd][0] = own[0]; if (lane == 1) s_bnd[1][i & 1][wd][1] = own[0]; }
-                    }
-                    dir_barrier();
+                for (int k = 0; k < K; k += 4) {
+                    float4 t4 = *reinterpret_cast<const float4*>(ebuf + tt * Sp + k);
+                    e[k] = t4.x; e[k + 1] = t4.y; e[k + 2] = t4.z; e[k + 3] = t4.w;
                 }
             }
+            float nw[K];
+            if (i == 0) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int s = s0 + k;
+                    const bool start = is_beta ? (s >= S - 2) : (s <= 1);
+                    nw[k] = (valid[k] && start) ? e[k] : NSP_NEG_BIG;
+                }
+            } else {
+                // the two states adjacent to this lane's block, from the previous step:
+                //   alpha: n1 = state s0-1, n2 = state s0-2;   beta: n1 = state s0+K, n2 = state s0+K+1
+                float n1, n2;
+                float b1 = NSP_NEG_BIG, b2 = NSP_NEG_BIG;    // values owned by the neighbouring warp
+                if (has_nb) { b1 = s_bnd[dsel][(i - 1) & 1][nbw][0]; b2 = s_bnd[dsel][(i - 1) & 1][nbw][1]; }
+                if (!is_beta) {
+                    n1 = __shfl_up_sync(0xffffffffu, own[K - 1], 1);
+                    n2 = (K >= 2) ? __shfl_up_sync(0xffffffffu, own[K >= 2 ? K - 2 : 0], 1) : __shfl_up_sync(0xffffffffu, own[0], 2);
+                    if (lane == 0) { n1 = b1; n2 = b2; }
+                    if (K == 1 && lane == 1) n2 = b1;
+                } else {
+                    n1 = __shfl_down_sync(0xffffffffu, own[0], 1);
+                    n2 = (K >= 2) ? __shfl_down_sync(0xffffffffu, own[K >= 2 ? 1 : 0], 1) : __shfl_down_sync(0xffffffffu, own[0], 2);
+                    if (lane == 31) { n1 = b1; n2 = b2; }
+                    if (K == 1 && lane == 30) n2 = b1;
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    float a1, a2;
+                    if (!is_beta) {
+                        a1 = (k >= 1) ? own[k >= 1 ? k - 1 : 0] : n1;
+                        a2 = (k >= 2) ? own[k >= 2 ? k - 2 : 0] : ((k == 1) ? n1 : n2);
+                    } else {
+                        a1 = (k + 1 < K) ? own[k + 1 < K ? k + 1 : 0] : n1;
+                        a2 = (k + 2 < K) ? own[k + 2 < K ? k + 2 : 0] : ((k + 2 == K) ? n1 : n2);
+                    }
+                    if (!skip[k]) a2 = NSP_NEG_BIG;
+                    float v = lse3(own[k], a1, a2) + e[k];
+                    nw[k] = valid[k] ? fmaxf(v, NSP_NEG_BIG) : NSP_NEG_BIG;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) own[k] = nw[k];
+            if (lane_active) st_states<K>(gptr, own);
+            gptr += gstep;
+            if constexpr (NWD > 1) {
+                // publish this warp's boundary states for the neighbouring warp's next step
+                if (!is_beta) {
+                    if (K >= 2) { if (lane == 31) { s_bnd[0][i & 1][wd][0] = own[K - 1]; s_bnd[0][i & 1][wd][1] = own[K >= 2 ? K - 2 : 0]; } }
+                    else { if (lane == 31) s_bnd[0][i & 1][wd][0] = own[0]; if (lane == 30) s_bnd[0][i & 1][wd][1] = own[0]; }
+                } else {
+                    if (K >= 2) { if (lane == 0) { s_bnd[1][i & 1][wd][0] = own[0]; s_bnd[1][i & 1][wd][1] = own[K >= 2 ? 1 : 0]; } }
+                    else { if (lane == 0) s_bnd[1][i & 1][wd][0] = own[0]; if (lane == 1) s_bnd[1][i & 1][wd][1] = own[0]; }
+                }
+                dir_barrier();
+            }
         }
+        if constexpr (NWD == 1) dir_barrier();             // everyone done reading buffer c & 1 before it is refilled
+        if (c + 2 < nchunks) stage(c + 2); else cp_async_commit();
     }
     if (!is_beta) {
         // nll = -lse(alpha_{T-1}(S-1), alpha_{T-1}(S-2)); the two states may sit in different warps
@@ -806,13 +830,18 @@ extern "C" nsp_status nsp_ctc_loss_fwd_bwd(const float* logits, int64_t stride_b
     const int Smax = 2 * Lmax + 1;
     if (Smax <= 512 && Lmax <= 256) {
         // four warps per direction (one per SM sub-partition) unless the path is so short that one warp holds it
+        const size_t lsm = (size_t)2 * 2 * 8 * p.Sp * sizeof(float);     // [dir][buffer][CT = 8][Sp]
         if (Smax <= 32) {
-            ctc_lattice_warp_kernel<1, 1><<<B, 64, 0, st>>>(p);
+            ctc_lattice_warp_kernel<1, 1><<<B, 64, lsm, st>>>(p);
         } else {
             const int k = ceil_div(Smax, 128);
-            if (k <= 1) ctc_lattice_warp_kernel<1, 4><<<B, 256, 0, st>>>(p);
-            else if (k <= 2) ctc_lattice_warp_kernel<2, 4><<<B, 256, 0, st>>>(p);
-            else ctc_lattice_warp_kernel<4, 4><<<B, 256, 0, st>>>(p);
+            if (lsm > 48 * 1024) {
+                NSP_CUDA_OK(cudaFuncSetAttribute(ctc_lattice_warp_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
+                NSP_CUDA_OK(cudaFuncSetAttribute(ctc_lattice_warp_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
+            }
+            if (k <= 1) ctc_lattice_warp_kernel<1, 4><<<B, 256, lsm, st>>>(p);
+            else if (k <= 2) ctc_lattice_warp_kernel<2, 4><<<B, 256, lsm, st>>>(p);
+            else ctc_lattice_warp_kernel<4, 4><<<B, 256, lsm, st>>>(p);
         }
         NSP_LAUNCH_OK();
         ctc_fixup_kernel<<<(unsigned)(ceil_div64((int64_t)bt, 8) + 1), 256, 0, st>>>(p);
