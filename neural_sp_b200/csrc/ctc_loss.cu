@@ -547,13 +547,17 @@ __global__ void __launch_bounds__(64 * NWD) ctc_lattice_warp_kernel(CtcParams p)
         for (int tt = 0; tt < nst; ++tt) {
             const int i = c * CT + tt;
             float e[K];
-            if constexpr (K == 1) e[0] = ebuf[tt * Sp];
-            else if constexpr (K == 2) { float2 t2 = *reinterpret_cast<const float2*>(ebuf + tt * Sp); e[0] = t2.x; e[1] = t2.y; }
-            else {
 #pragma unroll
-                for (int k = 0; k < K; k += 4) {
-                    float4 t4 = *reinterpret_cast<const float4*>(ebuf + tt * Sp + k);
-                    e[k] = t4.x; e[k + 1] = t4.y; e[k + 2] = t4.z; e[k + 3] = t4.w;
+            for (int k = 0; k < K; ++k) e[k] = 0.f;
+            if (lane_active) {                             // lanes past the row pitch must not touch the staging buffer
+                if constexpr (K == 1) e[0] = ebuf[tt * Sp];
+                else if constexpr (K == 2) { float2 t2 = *reinterpret_cast<const float2*>(ebuf + tt * Sp); e[0] = t2.x; e[1] = t2.y; }
+                else {
+#pragma unroll
+                    for (int k = 0; k < K; k += 4) {
+                        float4 t4 = *reinterpret_cast<const float4*>(ebuf + tt * Sp + k);
+                        e[k] = t4.x; e[k + 1] = t4.y; e[k + 2] = t4.z; e[k + 3] = t4.w;
+                    }
                 }
             }
             float nw[K];
