@@ -223,6 +223,79 @@ size_t nsp_lstm_workspace_bytes(int B, int H, int ndir);
 nsp_status nsp_lstm_seq_fwd(const float* gates_x, const float* w_hh, const int32_t* lens, float* y,
                             int B, int T, int H, int ndir, void* workspace, size_t workspace_bytes, void* stream);
 
+
+/* ==========================================================================================
+ * Backward pass of the encoder path (training).  The reference obtains all of these from torch autograd over
+ * the modules cited at the forward entry points above; each function below is the hand-written gradient of
+ * one forward entry point.  Gradients of parameters are ACCUMULATED into caller-provided fp32 buffers
+ * (red.global.add / atomicAdd), matching autograd's .grad accumulation.
+ * ========================================================================================== */
+
+/* nsp_linear_fwd that additionally saves the pre-activation (acc + bias) for the backward pass.
+ * pre: [M, N] in the operand dtype (bf16 for NSP_PREC_BF16, fp32 otherwise), pitch ldpre; for glu=1 columns
+ * [0,N/2) hold the value half and [N/2,N) the gate half.  pre may be NULL (then identical to nsp_linear_fwd). */
+nsp_status nsp_linear_fwd_save(int prec, const void* x, const void* x_lo, int64_t ldx,
+                               const void* w, const void* w_lo, int64_t ldw,
+                               int M, int N, int K, int glu, int act,
+                               const float* bias, const float* residual, int64_t ldr, float alpha,
+                               void* out, int64_t ldo, int out_bf16, void* out2, int64_t ldo2,
+                               void* pre, int64_t ldpre, void* stream);
+
+/* Weight gradient of out = x w^T (nn.Linear / 1x1 Conv1d):  dw[N,K] (+)= alpha * dy[M,N]^T x[M,K]  on tcgen05
+ * with MN-major operands (no transposed copies) and split-K reduction by red.global.add.  prec as in
+ * nsp_linear_fwd (NSP_PREC_FP32: dy/dy_lo and x/x_lo are tf32 hi/lo splits).  accumulate=0 zeroes dw first.
+ * (The input gradient dx = dy w is nsp_linear_fwd with the transposed weight.) */
+nsp_status nsp_linear_wgrad(int prec, const void* dy, const void* dy_lo, int64_t lddy,
+                            const void* x, const void* x_lo, int64_t ldx, int M, int N, int K,
+                            float alpha, float* dw, int64_t lddw, int accumulate, void* stream);
+
+/* LayerNorm backward with the residual-branch gradient fused in:
+ *   dx = dres + d/dx [ LN(x * in_scale) ] . dy ;  dgamma += sum_rows dy*xhat ;  dbeta += sum_rows dy.
+ * dy, x fp32 [M,D]; dres fp32 [M,D] or NULL; dx fp32 and/or dx_bf16 outputs; dgamma/dbeta fp32 [D] or NULL. */
+nsp_status nsp_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* gamma,
+                             float eps, float in_scale, const float* dres, int64_t lddr,
+                             float* dx, int64_t lddx, void* dx_bf16, int64_t lddxb,
+                             float* dgamma, float* dbeta, int M, int D, void* stream);
+
+/* dz = dh * act'(z) elementwise (act codes of nsp_linear_fwd); all bf16 (is_bf16=1) or all fp32. */
+nsp_status nsp_act_bwd(int is_bf16, int act, const void* dh, const void* z, void* dz, int64_t n, void* stream);
+/* GLU backward: pre = [a | b] ([M, 2d]), out = a*sigmoid(b); dpre = [dg*s | dg*a*s*(1-s)]. */
+nsp_status nsp_glu_bwd(int is_bf16, const void* dg, const void* pre, void* dpre, int64_t M, int d, void* stream);
+/* y[n] += alpha * sum_m x[m,n]  (bias gradients); x bf16 or fp32 [M,N] with pitch ldx. */
+nsp_status nsp_colsum_acc(int is_bf16, const void* x, int64_t ldx, int M, int N, float alpha, float* y, void* stream);
+/* MaxPoolSubsampler backward (encoders/subsampling.py:175-209): x, dx fp32 [B,T,D], dy fp32 [B,ceil(T/f),D]. */
+nsp_status nsp_maxpool_time_bwd(const float* x, const float* dy, float* dx, int B, int T, int D, int factor, void* stream);
+/* ReLU backward through the saved post-activation: dz = a > 0 ? dx : 0. */
+nsp_status nsp_relu_mask(int is_bf16, const void* dx, const void* a, void* dz, int64_t n, void* stream);
+/* ReLU + MaxPool2d(ceil_mode) backward on channels-last [B,T,F,C] (encoders/conv.py:362-394): a = saved post-ReLU
+ * activation, dy = gradient of the pooled tensor ([B,T',F',C], or [B,T',C*F'] when in_chmajor=1). */
+nsp_status nsp_maxpool2d_relu_bwd(int is_bf16, int dy_bf16, const void* a, const void* dy, void* dz, int B, int T, int F,
+                                  int C, int pool_t, int pool_f, int in_chmajor, void* stream);
+/* 3x3 conv weight/bias gradient: dw[CO,CI,3,3] += sum dz[b,t,f,co] * a[b,t+ky-1,f+kx-1,ci]; dbias[CO] += sum dz. */
+nsp_status nsp_conv3x3_wgrad(int a_bf16, int dz_bf16, const void* a, int in_chmajor, const void* dz, float* dw,
+                             float* dbias, int B, int T, int F, int CI, int CO, void* stream);
+
+/* Backward of nsp_relpos_attention_fwd (same argument meaning).  out is the forward result, dout its gradient;
+ * dq/dk/dv receive the gradients in the I/O dtype (may point into one fused [B*T, 3*H*dk] buffer);
+ * dr fp32 [rlen, H*dk] (pitch lddr), du / dvb fp32 [H*dk] are ACCUMULATED (may be NULL). */
+size_t nsp_relpos_attention_bwd_workspace_bytes(int B, int H, int Tq, int rlen, int clamp_len, int has_r);
+nsp_status nsp_relpos_attention_bwd(int is_bf16, const void* q, int64_t ldq, const void* k, int64_t ldk,
+                                    const void* v, int64_t ldv, const void* r, int64_t ldr, int rlen,
+                                    const float* u_bias, const float* v_bias, const int32_t* klens,
+                                    const void* out, int64_t ldo, const void* dout, int64_t lddo,
+                                    void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                                    float* dr, int64_t lddr, float* du, float* dvb,
+                                    int B, int H, int Tq, int Tk, int dk_dim, int clamp_len, int causal, int lookahead,
+                                    int chunk_c, int chunk_l, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of nsp_conformer_conv_fwd (LayerNorm variant only): dy = gradient of y; dz_ws = scratch [B*T, d] in the
+ * I/O dtype; dx = gradient of x; dw [k,d], dbias [d], dnorm_w [d], dnorm_b [d] fp32 are ACCUMULATED. */
+nsp_status nsp_conformer_conv_bwd(int is_bf16, const void* x, int64_t ldx, const float* w, const float* bias,
+                                  int norm_mode, const float* norm_w, const float* norm_b, float eps,
+                                  const void* dy, int64_t lddy, void* dz_ws, int64_t lddz, void* dx, int64_t lddx,
+                                  float* dw, float* dbias, float* dnorm_w, float* dnorm_b,
+                                  int B, int T, int d, int k, int causal, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

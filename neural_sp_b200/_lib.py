@@ -145,3 +145,32 @@ for _name, (_res, _args) in _more.items():
     _fn.restype = _res
     _fn.argtypes = _args
 SIGNATURES.update(_more)
+
+# ---- backward pass ----
+_more = {
+    "nsp_linear_fwd_save": (c_int, [c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int,
+                                    c_vp, c_vp, c_i64, c_f32, c_vp, c_i64, c_int, c_vp, c_i64, c_vp, c_i64, c_vp]),
+    "nsp_linear_wgrad": (c_int, [c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_f32, c_vp, c_i64,
+                                 c_int, c_vp]),
+    "nsp_layernorm_bwd": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_f32, c_f32, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64,
+                                  c_vp, c_vp, c_int, c_int, c_vp]),
+    "nsp_act_bwd": (c_int, [c_int, c_int, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "nsp_glu_bwd": (c_int, [c_int, c_vp, c_vp, c_vp, c_i64, c_int, c_vp]),
+    "nsp_colsum_acc": (c_int, [c_int, c_vp, c_i64, c_int, c_int, c_f32, c_vp, c_vp]),
+    "nsp_maxpool_time_bwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
+    "nsp_relu_mask": (c_int, [c_int, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "nsp_maxpool2d_relu_bwd": (c_int, [c_int, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "nsp_conv3x3_wgrad": (c_int, [c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "nsp_relpos_attention_bwd_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "nsp_relpos_attention_bwd": (c_int, [c_int, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_vp, c_vp,
+                                         c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64,
+                                         c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                         c_vp, c_sz, c_vp]),
+    "nsp_conformer_conv_bwd": (c_int, [c_int, c_vp, c_i64, c_vp, c_vp, c_int, c_vp, c_vp, c_f32, c_vp, c_i64, c_vp, c_i64,
+                                       c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
+}
+for _name, (_res, _args) in _more.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+SIGNATURES.update(_more)

@@ -1,0 +1,425 @@
+"""Training path of the encoder: hand-written backward chains wired into torch.autograd.
+
+The reference trains through torch autograd over its nn.Modules (encoders/conformer_block.py:95-182,
+encoders/transformer_block.py, encoders/conv.py:347-396, modules/*).  Here every encoder block, the CNN
+front-end, the time max-pool and the final LayerNorm is ONE ``torch.autograd.Function`` whose forward runs
+the same fused CUDA kernels as inference (out of place, keeping what the backward needs) and whose backward
+is a hand-written chain of CUDA kernels (tcgen05 dgrad / wgrad GEMMs, flash attention backward, fused
+LayerNorm / depthwise-conv backward).  PyTorch only orders the Functions and accumulates ``.grad``.
+
+Python here is orchestration only: no arithmetic on tensors outside the library kernels, except views,
+allocation and the handful of `torch.zeros` gradient buffers.
+"""
+import torch
+
+from . import ops
+from .modules._prep import prepared, cached, act_dtype
+
+
+def training_enabled(module):
+    """The autograd path is taken iff grad mode is on and the module is in train() mode."""
+    return torch.is_grad_enabled() and module.training
+
+
+class _Grads:
+    """fp32 gradient buffers keyed by parameter (created zeroed on first use)."""
+
+    def __init__(self):
+        self.g = {}
+
+    def buf(self, p):
+        t = self.g.get(id(p))
+        if t is None:
+            t = torch.zeros(p.shape, dtype=torch.float32, device=p.device)
+            self.g[id(p)] = t
+        return t
+
+    def get(self, p):
+        return self.g.get(id(p))
+
+
+def _wT(module, name, prec, params, build=None):
+    """Prepared TRANSPOSED weight (operand of the input-gradient GEMM dx = dy W)."""
+    if build is None:
+        return prepared(module, name + ".T", prec, params, build=lambda w: w.reshape(w.shape[0], -1).t().contiguous())
+    return prepared(module, name + ".T", prec, params, build=lambda *ws: build(*ws).t().contiguous())
+
+
+def _as2d(w):
+    return w.reshape(w.shape[0], -1)
+
+
+def _gop(x, prec):
+    """Gradient tensor in the GEMM operand dtype (bf16 copy in bf16 mode)."""
+    return ops.to_bf16(x.contiguous()) if prec == "bf16" else x
+
+
+# ------------------------------------------------------------------------------------------------
+# residual branches  y = x + scale * F(LN(x))
+# ------------------------------------------------------------------------------------------------
+def _ln_fwd(norm, x, prec):
+    if prec == "bf16":
+        return ops.layernorm(x, norm.weight, norm.bias, norm.eps, out_fp32=False, out_bf16=True)
+    return ops.layernorm(x, norm.weight, norm.bias, norm.eps)
+
+
+def _ln_bwd(norm, dn, x, dres, G):
+    return ops.layernorm_bwd(dn, x, norm.weight, norm.eps, dres=dres, dgamma=G.buf(norm.weight), dbeta=G.buf(norm.bias))
+
+
+def ffn_fwd(ffn, norm, x, scale, prec):
+    if ffn.act_name == "glu":
+        raise NotImplementedError("training with the GLU feed-forward activation is not on the B200 path yet")
+    n = _ln_fwd(norm, x, prec)
+    w1 = prepared(ffn, "w_1", prec, (ffn.w_1.weight,))
+    w2 = prepared(ffn, "w_2", prec, (ffn.w_2.weight,))
+    h, z = ops.linear(n, w1, ffn.w_1.bias, prec=prec, act=ffn.act_name, out_dtype=act_dtype(prec), save_pre=True)
+    y = ops.linear(h, w2, ffn.w_2.bias, prec=prec, residual=x, alpha=scale, out_dtype=torch.float32)
+    return y, (x, n, z, h)
+
+
+def ffn_bwd(ffn, norm, saved, dy, scale, prec, G):
+    x, n, z, h = saved
+    dyo = _gop(dy, prec)
+    ops.linear_wgrad(dyo, h, prec, G.buf(ffn.w_2.weight), alpha=scale)
+    ops.colsum_acc(dy, G.buf(ffn.w_2.bias), alpha=scale)
+    dh = ops.linear(dyo, _wT(ffn, "w_2", prec, (ffn.w_2.weight,)), None, prec=prec, alpha=scale, out_dtype=act_dtype(prec))
+    dz = ops.act_bwd(dh, z, ffn.act_name)
+    ops.linear_wgrad(dz, n, prec, G.buf(ffn.w_1.weight))
+    ops.colsum_acc(dz, G.buf(ffn.w_1.bias))
+    dn = ops.linear(dz, _wT(ffn, "w_1", prec, (ffn.w_1.weight,)), None, prec=prec, out_dtype=torch.float32)
+    return _ln_bwd(norm, dn, x, dy, G)
+
+
+def _qkv_weight(attn, prec, transposed=False):
+    params = (attn.w_query.weight, attn.w_key.weight, attn.w_value.weight)
+    cat = lambda q, k, v: torch.cat([q, k, v], dim=0)     # noqa: E731
+    if transposed:
+        return _wT(attn, "qkv", prec, params, build=cat)
+    return prepared(attn, "qkv", prec, params, build=cat)
+
+
+def attn_fwd(attn, norm, x, pos, klens, u_bias, v_bias, mask_kw, prec, rel):
+    n = _ln_fwd(norm, x, prec)
+    D = attn.n_heads * attn.d_k
+    bias = None
+    if attn.w_key.bias is not None:
+        bias = torch.cat([attn.w_query.bias, attn.w_key.bias, attn.w_value.bias]).detach()
+    qkv = ops.linear(n, _qkv_weight(attn, prec), bias, prec=prec, out_dtype=act_dtype(prec))
+    r, nrows = None, 0
+    if rel:
+        T = x.shape[1]
+        nrows = min(T, attn.clamp_len + 1) if attn.clamp_len > 0 else T
+        wp_lin = attn.w_pos if attn.xl_like else attn.w_value
+        r = ops.linear(pos[:nrows], prepared(attn, "pos", prec, (wp_lin.weight,)), wp_lin.bias, prec=prec,
+                       out_dtype=act_dtype(prec))
+    clamp = attn.clamp_len if rel else -1
+    cv = ops.relpos_attention(qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:], klens, attn.n_heads, r=r,
+                              u_bias=u_bias if rel else None, v_bias=v_bias if rel else None, clamp_len=clamp, **mask_kw)
+    y = ops.linear(cv, prepared(attn, "w_out", prec, (attn.w_out.weight,)), attn.w_out.bias, prec=prec, residual=x,
+                   out_dtype=torch.float32)
+    return y, (x, n, qkv, r, cv, nrows)
+
+
+def attn_bwd(attn, norm, saved, dy, pos, klens, u_bias, v_bias, mask_kw, prec, rel, G, enc_bias_params):
+    x, n, qkv, r, cv, nrows = saved
+    D = attn.n_heads * attn.d_k
+    d_in = x.shape[-1]
+    dyo = _gop(dy, prec)
+    ops.linear_wgrad(dyo, cv, prec, G.buf(attn.w_out.weight))
+    if attn.w_out.bias is not None:
+        ops.colsum_acc(dy, G.buf(attn.w_out.bias))
+    dcv = ops.linear(dyo, _wT(attn, "w_out", prec, (attn.w_out.weight,)), None, prec=prec, out_dtype=act_dtype(prec))
+    dr = torch.zeros(nrows, D, dtype=torch.float32, device=x.device) if rel else None
+    du = dvb = None
+    if rel and u_bias is not None:
+        du, dvb = G.buf(enc_bias_params[0]).view(-1), G.buf(enc_bias_params[1]).view(-1)
+    clamp = attn.clamp_len if rel else -1
+    dqkv = ops.relpos_attention_bwd(qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:], klens, attn.n_heads, cv, dcv, r=r,
+                                    u_bias=u_bias if rel else None, v_bias=v_bias if rel else None, clamp_len=clamp,
+                                    dr=dr, du=du, dvb=dvb, **mask_kw)
+    gw = torch.zeros(3 * D, d_in, dtype=torch.float32, device=x.device)
+    ops.linear_wgrad(dqkv, n, prec, gw)
+    for i, lin in enumerate((attn.w_query, attn.w_key, attn.w_value)):
+        G.g[id(lin.weight)] = gw[i * D:(i + 1) * D]          # row blocks of the fused gradient (views)
+    if attn.w_key.bias is not None:
+        gb = torch.zeros(3 * D, dtype=torch.float32, device=x.device)
+        ops.colsum_acc(dqkv, gb)
+        for i, lin in enumerate((attn.w_query, attn.w_key, attn.w_value)):
+            G.g[id(lin.bias)] = gb[i * D:(i + 1) * D]
+    if rel:   # r = pos[:nrows] @ Wp^T (+ bp): the position projection shares w_value when not xl_like (reference :176)
+        wp_lin = attn.w_pos if attn.xl_like else attn.w_value
+        ops.linear_wgrad(dr, pos[:nrows], prec, G.buf(wp_lin.weight))
+        if wp_lin.bias is not None:
+            ops.colsum_acc(dr, G.buf(wp_lin.bias))
+    dn = ops.linear(dqkv, _qkv_weight(attn, prec, transposed=True), None, prec=prec, out_dtype=torch.float32)
+    return _ln_bwd(norm, dn, x, dy, G)
+
+
+def convmod_fwd(conv, norm, x, prec):
+    if conv.normalization != 'layer_norm':
+        raise NotImplementedError("training the Conformer conv module needs conformer_normalization=layer_norm on the B200 "
+                                  "path (the LibriSpeech recipes' setting)")
+    n = _ln_fwd(norm, x, prec)
+    w1 = prepared(conv, "pw1", prec, (conv.pointwise_conv1.weight,), build=lambda w: w.squeeze(-1))
+    g, pre = ops.linear(n, w1, conv.pointwise_conv1.bias, prec=prec, glu=True, out_dtype=act_dtype(prec), save_pre=True)
+    taps = cached(conv, "dw_taps", (conv.depthwise_conv.weight,), lambda w: w.reshape(w.size(0), -1).t().contiguous().float())
+    c = ops.conformer_conv(g, taps, conv.depthwise_conv.bias, 'layer_norm', conv.norm.weight, conv.norm.bias, conv.norm.eps,
+                           None, None, causal=conv.causal)
+    w2 = prepared(conv, "pw2", prec, (conv.pointwise_conv2.weight,), build=lambda w: w.squeeze(-1))
+    y = ops.linear(c, w2, conv.pointwise_conv2.bias, prec=prec, residual=x, out_dtype=torch.float32)
+    return y, (x, n, pre, g, c, taps)
+
+
+def convmod_bwd(conv, norm, saved, dy, prec, G):
+    x, n, pre, g, c, taps = saved
+    d = x.shape[-1]
+    dyo = _gop(dy, prec)
+    ops.linear_wgrad(dyo, c, prec, _as2d(G.buf(conv.pointwise_conv2.weight)))
+    ops.colsum_acc(dy, G.buf(conv.pointwise_conv2.bias))
+    dc = ops.linear(dyo, _wT(conv, "pw2", prec, (conv.pointwise_conv2.weight,)), None, prec=prec, out_dtype=act_dtype(prec))
+    dtaps = torch.zeros_like(taps)
+    dg = ops.conformer_conv_bwd(g, taps, conv.depthwise_conv.bias, conv.norm.weight, conv.norm.bias, conv.norm.eps, dc,
+                                dtaps, G.buf(conv.depthwise_conv.bias), G.buf(conv.norm.weight), G.buf(conv.norm.bias),
+                                causal=conv.causal)
+    G.g[id(conv.depthwise_conv.weight)] = dtaps.t().reshape(conv.depthwise_conv.weight.shape)
+    dpre = ops.glu_bwd(dg, pre)
+    ops.linear_wgrad(dpre, n, prec, _as2d(G.buf(conv.pointwise_conv1.weight)))
+    ops.colsum_acc(dpre, G.buf(conv.pointwise_conv1.bias))
+    dn = ops.linear(dpre, _wT(conv, "pw1", prec, (conv.pointwise_conv1.weight,)), None, prec=prec, out_dtype=torch.float32)
+    return _ln_bwd(norm, dn, x, dy, G)
+
+
+# ------------------------------------------------------------------------------------------------
+# encoder blocks
+# ------------------------------------------------------------------------------------------------
+def _param_list(block, extra):
+    return [p for p in block.parameters()] + [p for p in extra if p is not None]
+
+
+class _BlockFn(torch.autograd.Function):
+    """One encoder block (Conformer or Transformer) as a single autograd node."""
+
+    @staticmethod
+    def forward(ctx, xs, block, klens, pos, rel_bias, mask_kw, prec, in_scale, *params):
+        u_bias, v_bias = rel_bias
+        saved = {}
+        x = xs
+        if in_scale != 1.0:
+            x = ops.scale_(xs.clone(), in_scale)
+        if hasattr(block, "feed_forward_macaron"):
+            x, saved["ffm"] = ffn_fwd(block.feed_forward_macaron, block.norm1, x, block.fc_factor, prec)
+            x, saved["att"] = attn_fwd(block.self_attn, block.norm2, x, pos, klens, u_bias, v_bias, mask_kw, prec, True)
+            x, saved["conv"] = convmod_fwd(block.conv, block.norm3, x, prec)
+            x, saved["ff"] = ffn_fwd(block.feed_forward, block.norm4, x, block.fc_factor, prec)
+            saved["x5"] = x
+            x = ops.layernorm(x, block.norm5.weight, block.norm5.bias, block.norm5.eps)
+        else:
+            x, saved["att"] = attn_fwd(block.self_attn, block.norm1, x, pos, klens, u_bias, v_bias, mask_kw, prec,
+                                       block.rel_attn)
+            x, saved["ff"] = ffn_fwd(block.feed_forward, block.norm2, x, 1.0, prec)
+        ctx.block, ctx.saved, ctx.klens, ctx.pos, ctx.rel_bias = block, saved, klens, pos, rel_bias
+        ctx.mask_kw, ctx.prec, ctx.in_scale, ctx.params = mask_kw, prec, in_scale, params
+        return x
+
+    @staticmethod
+    def backward(ctx, dy):
+        block, S, prec = ctx.block, ctx.saved, ctx.prec
+        u_bias, v_bias = ctx.rel_bias
+        G = _Grads()
+        dy = dy.contiguous().float()
+        if hasattr(block, "feed_forward_macaron"):
+            dx = ops.layernorm_bwd(dy, S["x5"], block.norm5.weight, block.norm5.eps, dres=None,
+                                   dgamma=G.buf(block.norm5.weight), dbeta=G.buf(block.norm5.bias))
+            dx = ffn_bwd(block.feed_forward, block.norm4, S["ff"], dx, block.fc_factor, prec, G)
+            dx = convmod_bwd(block.conv, block.norm3, S["conv"], dx, prec, G)
+            dx = attn_bwd(block.self_attn, block.norm2, S["att"], dx, ctx.pos, ctx.klens, u_bias, v_bias, ctx.mask_kw, prec,
+                          True, G, ctx.rel_bias)
+            dx = ffn_bwd(block.feed_forward_macaron, block.norm1, S["ffm"], dx, block.fc_factor, prec, G)
+        else:
+            dx = ffn_bwd(block.feed_forward, block.norm2, S["ff"], dy, 1.0, prec, G)
+            dx = attn_bwd(block.self_attn, block.norm1, S["att"], dx, ctx.pos, ctx.klens, u_bias, v_bias, ctx.mask_kw, prec,
+                          block.rel_attn, G, ctx.rel_bias)
+        if ctx.in_scale != 1.0:
+            ops.scale_(dx, ctx.in_scale)
+        ctx.saved = None
+        grads = tuple(G.get(p) for p in ctx.params)
+        return (dx, None, None, None, None, None, None, None) + grads
+
+
+def block_forward(block, xs, klens, pos, rel_bias, mask_kw, prec, in_scale=1.0):
+    """Training forward of one encoder block through its autograd node."""
+    extra = rel_bias if (rel_bias[0] is not None and getattr(block.self_attn, "xl_like", False)) else ()
+    params = _param_list(block, extra)
+    rb = rel_bias if extra else (None, None)
+    return _BlockFn.apply(xs, block, klens, pos, rb, mask_kw or {}, prec, float(in_scale), *params)
+
+
+# ------------------------------------------------------------------------------------------------
+# small nodes: LayerNorm, time max-pool, scaling
+# ------------------------------------------------------------------------------------------------
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        ctx.save_for_backward(x, weight)
+        ctx.eps = eps
+        return ops.layernorm(x, weight, bias, eps)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dg, db = torch.zeros_like(weight, dtype=torch.float32), torch.zeros_like(weight, dtype=torch.float32)
+        dx = ops.layernorm_bwd(dy.contiguous().float(), x, weight, ctx.eps, dres=None, dgamma=dg, dbeta=db)
+        return dx, dg, db, None
+
+
+def layernorm(norm, x):
+    return _LayerNormFn.apply(x, norm.weight, norm.bias, norm.eps)
+
+
+class _MaxPoolTimeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, factor):
+        ctx.save_for_backward(x)
+        ctx.factor = factor
+        return ops.pool_time(x, factor, "max")
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return ops.maxpool_time_bwd(x, dy, ctx.factor), None
+
+
+def maxpool_time(x, factor):
+    return _MaxPoolTimeFn.apply(x, factor)
+
+
+class _ScaleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, a):
+        ctx.a = a
+        return ops.scale_(x.contiguous().clone(), a)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.scale_(dy.contiguous().clone(), ctx.a), None
+
+
+def scale(x, a):
+    return x if a == 1.0 else _ScaleFn.apply(x, float(a))
+
+
+def linear(module, name, lin, x, prec):
+    """nn.Linear through the tcgen05 GEMM with autograd (dgrad + wgrad on the same kernels)."""
+    from .modules.linear import _LinearFn
+    return _LinearFn.apply(x, lin.weight, lin.bias, lin, prec)
+
+
+# ------------------------------------------------------------------------------------------------
+# CNN front-end (Conv2dBlock stack + bridge) as one node
+# ------------------------------------------------------------------------------------------------
+def _conv_any(block, name, layer, x, B, T, F, first, prec, weight=None, relu=True):
+    """3x3 conv (+bias, +ReLU): tcgen05 implicit GEMM for 32->32 bf16, CUDA-core kernel otherwise."""
+    ci, co = layer.in_channels, layer.out_channels
+    adt = act_dtype(prec)
+    if prec == "bf16" and ci == 32 and co == 32 and x.dtype == torch.bfloat16:
+        if weight is None:
+            wt = prepared(block, name + ".taps", "bf16", (layer.weight,),
+                          build=lambda w: w.permute(0, 2, 3, 1).reshape(32, 288))[0][:, :288].contiguous()
+            bias = layer.bias
+        else:
+            wt = prepared(block, name + ".dtaps", "bf16", (layer.weight,),
+                          build=lambda w: ops.conv3x3_dgrad_weight(w).permute(0, 2, 3, 1).reshape(32, 288))[0][:, :288].contiguous()
+            bias = cached(block, name + ".zero_bias", (layer.bias,), lambda b: torch.zeros_like(b, dtype=torch.float32))
+        return ops.conv3x3_c32_tc(x.view(B, T, F, 32), wt, bias, relu=relu, pool2x2=False)
+    if weight is None:
+        return ops.conv3x3_relu(x, layer.weight, layer.bias, B, T, F, in_chmajor=first, relu=relu, out_dtype=adt)
+    wd = cached(block, name + ".dgrad_w", (layer.weight,), lambda w: ops.conv3x3_dgrad_weight(w).float())
+    zb = cached(block, name + ".zero_bias_in", (layer.weight,), lambda w: torch.zeros(w.shape[1], dtype=torch.float32, device=w.device))
+    return ops.conv3x3_relu(x, wd, zb, B, T, F, in_chmajor=False, relu=False, out_dtype=adt)
+
+
+class _FrontendFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xs, enc, out_scale, prec, *params):
+        B, T, Fdim = xs.shape
+        F = Fdim // enc.in_channel
+        x = xs.contiguous().float()
+        tape = []
+        n = len(enc.layers)
+        for i, blk in enumerate(enc.layers):
+            last_chmajor = (i == n - 1) and enc.bridge is None
+            pt, pf = blk.pooling if blk.pool is not None else (1, 1)
+            a1 = _conv_any(blk, "conv1", blk.conv1, x, B, T, F, i == 0, prec)
+            a2 = _conv_any(blk, "conv2", blk.conv2, a1, B, T, F, False, prec)
+            rec = dict(x=x, a1=a1, a2=a2, T=T, F=F, pt=pt, pf=pf, chmajor=last_chmajor, first=(i == 0))
+            if blk.pool is not None or last_chmajor:
+                x = ops.maxpool2d(a2, pt, pf, out_chmajor=last_chmajor)
+                rec["pooled"] = True
+                T, F = -(-T // pt), -(-F // pf)
+            else:
+                x = a2
+                rec["pooled"] = False
+            tape.append(rec)
+        C, Fo = enc._c_last, F
+        if enc.bridge is not None:
+            wb = prepared(enc, "bridge", prec, (enc.bridge.weight,),
+                          build=lambda w: w.view(w.size(0), C, Fo).transpose(1, 2).reshape(w.size(0), Fo * C))
+            feat = x.reshape(B, T, Fo * C)
+            y = ops.linear(feat, wb, enc.bridge.bias, prec=prec, alpha=out_scale, out_dtype=torch.float32)
+            ctx.feat = feat
+        else:
+            y = x.float() if x.dtype != torch.float32 else x
+            y = y.reshape(B, T, C * Fo)
+            if out_scale != 1.0:
+                y = ops.scale_(y.contiguous().clone(), out_scale)
+        ctx.enc, ctx.tape, ctx.prec, ctx.out_scale, ctx.params = enc, tape, prec, out_scale, params
+        ctx.dims = (B, T, Fo, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        enc, tape, prec = ctx.enc, ctx.tape, ctx.prec
+        B, Tl, Fo, C = ctx.dims
+        G = _Grads()
+        adt = act_dtype(prec)
+        dy = dy.contiguous().float()
+        if enc.bridge is not None:
+            dyo = _gop(dy, prec)
+            gperm = torch.zeros(enc.bridge.weight.shape[0], Fo * C, dtype=torch.float32, device=dy.device)
+            ops.linear_wgrad(dyo, ctx.feat, prec, gperm, alpha=ctx.out_scale)
+            # undo the (f, c) -> (c, f) column permutation of the cached operand: pure view + copy by autograd's accumulate
+            G.g[id(enc.bridge.weight)] = gperm.view(-1, Fo, C).transpose(1, 2).reshape(enc.bridge.weight.shape)
+            ops.colsum_acc(dy, G.buf(enc.bridge.bias), alpha=ctx.out_scale)
+            wbT = prepared(enc, "bridge.T", prec, (enc.bridge.weight,),
+                           build=lambda w: w.view(w.size(0), C, Fo).transpose(1, 2).reshape(w.size(0), Fo * C).t().contiguous())
+            d = ops.linear(dyo, wbT, None, prec=prec, alpha=ctx.out_scale, out_dtype=adt).view(B, Tl, Fo, C)
+        else:
+            d = dy if ctx.out_scale == 1.0 else ops.scale_(dy.clone(), ctx.out_scale)
+            if adt == torch.bfloat16:
+                d = ops.to_bf16(d)
+        for blk, rec in zip(reversed(list(enc.layers)), reversed(tape)):
+            T, F = rec["T"], rec["F"]
+            a1, a2, x = rec["a1"], rec["a2"], rec["x"]
+            if rec["pooled"]:
+                dz2 = ops.maxpool2d_relu_bwd(a2.view(B, T, F, -1), d, rec["pt"], rec["pf"], in_chmajor=rec["chmajor"])
+            else:
+                dz2 = ops.relu_mask(d.reshape(a2.shape).to(a2.dtype), a2)
+            ops.conv3x3_wgrad(a1, dz2, G.buf(blk.conv2.weight), G.buf(blk.conv2.bias), B, T, F)
+            da1 = _conv_any(blk, "conv2", blk.conv2, dz2, B, T, F, False, prec, weight="dgrad", relu=False)
+            dz1 = ops.relu_mask(da1.reshape(a1.shape), a1)
+            ops.conv3x3_wgrad(x, dz1, G.buf(blk.conv1.weight), G.buf(blk.conv1.bias), B, T, F, in_chmajor=rec["first"])
+            if not rec["first"]:
+                d = _conv_any(blk, "conv1", blk.conv1, dz1, B, T, F, False, prec, weight="dgrad", relu=False)
+        ctx.tape = None
+        return (None, None, None, None) + tuple(G.get(p) for p in ctx.params)
+
+
+def frontend_forward(enc, xs, out_scale, prec):
+    for blk in enc.layers:
+        if blk.training and blk.dropout.p > 0:
+            raise NotImplementedError("dropout > 0 in training mode is not on the B200 path yet")
+        if blk.residual and blk.conv1.in_channels == blk.conv2.out_channels:
+            raise NotImplementedError("residual CNN blocks are not on the B200 path")
+    params = [p for p in enc.parameters()]
+    return _FrontendFn.apply(xs, enc, float(out_scale), prec, *params)

@@ -1,0 +1,369 @@
+// Streaming (HBM-bound) backward kernels of the encoder path: LayerNorm backward with the residual gradient fused in,
+// activation / GLU derivatives, accumulating column sums (bias gradients), time max-pool backward, ReLU masks and the
+// 2-D max-pool backward of the convolutional front-end.
+//
+// The reference obtains all of these from autograd over
+//   nn.LayerNorm                       encoders/conformer_block.py:53-80, encoders/transformer.py:600
+//   Swish / ReLU / GELU, F.glu         modules/positionwise_feed_forward.py:77-89, modules/conformer_convolution.py:110-112
+//   nn.Linear / nn.Conv1d biases       (column sums of the output gradient)
+//   MaxPoolSubsampler (ceil_mode)      encoders/subsampling.py:175-209
+//   ReLU + nn.MaxPool2d(ceil_mode)     encoders/conv.py:362-394
+#include "common.cuh"
+
+namespace nsp {
+namespace {
+
+template <typename T> __device__ __forceinline__ float bw_ld(const T* p);
+template <> __device__ __forceinline__ float bw_ld<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float bw_ld<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T> __device__ __forceinline__ void bw_st(T* p, float v);
+template <> __device__ __forceinline__ void bw_st<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void bw_st<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward.  y = (x*s - mean) * rstd * gamma + beta
+//   dx = s * rstd * (g - mean(g) - xhat * mean(g * xhat)) + dres,  g = dy * gamma
+//   dgamma += sum_rows dy * xhat ;  dbeta += sum_rows dy
+// One warp per row (row in registers, statistics recomputed from x exactly like the forward kernel), rows are
+// grid-strided so that each thread keeps its dgamma / dbeta partials in registers; one smem reduction over the
+// 8 warps and one atomicAdd per column per CTA at the end.
+// ------------------------------------------------------------------------------------------------
+template <int VPT>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, int64_t lddy,
+                                                            const float* __restrict__ x, int64_t ldx,
+                                                            const float* __restrict__ gamma, float eps, float in_scale,
+                                                            const float* __restrict__ dres, int64_t lddr,
+                                                            float* __restrict__ dx, int64_t lddx,
+                                                            __nv_bfloat16* __restrict__ dxb, int64_t lddxb,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                            int M, int D) {
+    extern __shared__ float red[];     // [8][2][D]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float gsum[VPT][4], bsum[VPT][4], gm[VPT][4];
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+        const int idx = (j * 32 + lane) * 4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            gsum[j][k] = 0.f; bsum[j][k] = 0.f;
+            gm[j][k] = (idx + k < D) ? __ldg(gamma + idx + k) : 0.f;
+        }
+    }
+    for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < M; row += (int64_t)gridDim.x * 8) {
+        const float* xr = x + row * ldx;
+        const float* dyr = dy + row * lddy;
+        float v[VPT][4], g[VPT][4];
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+            const int idx = (j * 32 + lane) * 4;
+            if (idx < D) {      // D % 4 == 0 is required by the host wrapper
+                const float4 t = *reinterpret_cast<const float4*>(xr + idx);
+                const float4 u = *reinterpret_cast<const float4*>(dyr + idx);
+                v[j][0] = t.x * in_scale; v[j][1] = t.y * in_scale; v[j][2] = t.z * in_scale; v[j][3] = t.w * in_scale;
+                g[j][0] = u.x; g[j][1] = u.y; g[j][2] = u.z; g[j][3] = u.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { v[j][k] = 0.f; g[j][k] = 0.f; }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s += v[j][k];
+        }
+        const float mean = warp_sum(s) / (float)D;
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+            const int idx = (j * 32 + lane) * 4;
+            if (idx < D) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { const float d = v[j][k] - mean; q += d * d; }
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+            const int idx = (j * 32 + lane) * 4;
+            if (idx < D) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float xh = (v[j][k] - mean) * rstd;
+                    const float dyv = g[j][k];
+                    gsum[j][k] += dyv * xh;
+                    bsum[j][k] += dyv;
+                    const float gg = dyv * gm[j][k];
+                    v[j][k] = xh;
+                    g[j][k] = gg;
+                    s1 += gg;
+                    s2 += gg * xh;
+                }
+            }
+        }
+        const float m1 = warp_sum(s1) / (float)D, m2 = warp_sum(s2) / (float)D;
+        const float sc = rstd * in_scale;
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+            const int idx = (j * 32 + lane) * 4;
+            if (idx < D) {
+                float o[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) o[k] = sc * (g[j][k] - m1 - v[j][k] * m2);
+                if (dres) {
+                    const float4 r = *reinterpret_cast<const float4*>(dres + row * lddr + idx);
+                    o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
+                }
+                if (dx) *reinterpret_cast<float4*>(dx + row * lddx + idx) = make_float4(o[0], o[1], o[2], o[3]);
+                if (dxb) {
+                    __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]), b = __floats2bfloat162_rn(o[2], o[3]);
+                    uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
+                    *reinterpret_cast<uint2*>(dxb + row * lddxb + idx) = pk;
+                }
+            }
+        }
+    }
+    // ---- CTA reduction of the parameter gradients ----
+    float* rg = red + (size_t)warp * 2 * D;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+        const int idx = (j * 32 + lane) * 4;
+        if (idx < D) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { rg[idx + k] = gsum[j][k]; rg[D + idx + k] = bsum[j][k]; }
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * D; c += 256) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[(size_t)w * 2 * D + c];
+        if (c < D) { if (dgamma) atomicAdd(dgamma + c, t); }
+        else if (dbeta) atomicAdd(dbeta + (c - D), t);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dz = dh * act'(z)    (act: 1 relu, 2 swish, 3 gelu(erf), 4 gelu(tanh))
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float dact(int act, float z) {
+    if (act == 1) return z > 0.f ? 1.f : 0.f;
+    if (act == 2) { const float s = 1.f / (1.f + __expf(-z)); return s * (1.f + z * (1.f - s)); }
+    if (act == 3) {
+        const float cdf = 0.5f * (1.f + erff(z * 0.70710678118654752f));
+        return cdf + z * 0.3989422804014327f * __expf(-0.5f * z * z);
+    }
+    if (act == 4) {
+        const float u = 0.79788456080286536f * (z + 0.044715f * z * z * z);
+        const float t = tanhf(u);
+        return 0.5f * (1.f + t) + 0.5f * z * (1.f - t * t) * 0.79788456080286536f * (1.f + 3.f * 0.044715f * z * z);
+    }
+    return 1.f;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) act_bwd_kernel(const T* __restrict__ dh, const T* __restrict__ z, T* __restrict__ dz,
+                                                      int64_t n, int act) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
+        bw_st<T>(dz + i, bw_ld<T>(dh + i) * dact(act, bw_ld<T>(z + i)));
+}
+
+// GLU backward: out = a * sigmoid(b) with pre = [a | b] of width 2*d per row.
+template <typename T>
+__global__ void __launch_bounds__(256) glu_bwd_kernel(const T* __restrict__ dg, const T* __restrict__ pre, T* __restrict__ dpre,
+                                                      int64_t M, int d) {
+    const int64_t n = M * d;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const int64_t r = i / d;
+        const int c = (int)(i - r * d);
+        const float a = bw_ld<T>(pre + r * 2 * d + c), b = bw_ld<T>(pre + r * 2 * d + d + c);
+        const float g = bw_ld<T>(dg + i);
+        const float s = 1.f / (1.f + __expf(-b));
+        bw_st<T>(dpre + r * 2 * d + c, g * s);
+        bw_st<T>(dpre + r * 2 * d + d + c, g * a * s * (1.f - s));
+    }
+}
+
+// y[n] += alpha * sum_m x[m, n]; grid = (column blocks of 32, row slices)
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_acc_kernel(const T* __restrict__ x, int64_t ldx, float* __restrict__ y,
+                                                         int M, int N, float alpha) {
+    __shared__ float part[8][33];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31), rs = threadIdx.x >> 5;
+    float acc = 0.f;
+    if (c < N)
+        for (int r = blockIdx.y * 8 + rs; r < M; r += gridDim.y * 8) acc += bw_ld<T>(x + (int64_t)r * ldx + c);
+    part[rs][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (rs == 0 && c < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x & 31];
+        atomicAdd(y + c, alpha * t);
+    }
+}
+
+// MaxPoolSubsampler backward (kernel = stride = factor, ceil_mode): the gradient of output frame to goes to the FIRST
+// frame of its window holding the maximum (torch's max_pool1d tie rule), zeros elsewhere.  x, dx fp32 [B,T,D].
+__global__ void __launch_bounds__(256) maxpool_time_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                               float* __restrict__ dx, int B, int T, int D, int factor) {
+    const int To = (T + factor - 1) / factor;
+    const int64_t n = (int64_t)B * To * D;
+    for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < n; e += (int64_t)gridDim.x * 256) {
+        const int c = (int)(e % D);
+        const int64_t r = e / D;
+        const int to = (int)(r % To), b = (int)(r / To);
+        const int t0 = to * factor, t1 = min(T, t0 + factor);
+        const float* xp = x + ((int64_t)b * T) * D + c;
+        float best = xp[(int64_t)t0 * D];
+        int arg = t0;
+        for (int t = t0 + 1; t < t1; ++t) {
+            const float v = xp[(int64_t)t * D];
+            if (v > best) { best = v; arg = t; }
+        }
+        const float g = dy[e];
+        for (int t = t0; t < t1; ++t) dx[((int64_t)b * T + t) * D + c] = (t == arg) ? g : 0.f;
+    }
+}
+
+// dz = (a > 0) ? dx : 0   (ReLU backward through the saved post-activation a)
+template <typename T>
+__global__ void __launch_bounds__(256) relu_mask_kernel(const T* __restrict__ dx, const T* __restrict__ a, T* __restrict__ dz, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
+        bw_st<T>(dz + i, bw_ld<T>(a + i) > 0.f ? bw_ld<T>(dx + i) : 0.f);
+}
+
+// ReLU + MaxPool2d(ceil_mode, kernel = stride = (pt, pf)) backward on channels-last [B,T,F,C]:
+//   dz[b,t,f,c] = dy[b,to,fo,c] if (t,f) is the first arg-max of its window and a > 0 else 0.
+// a is the saved post-ReLU activation; dy is [B,To,Fo,C] (in_chmajor=0) or the flattened [B,To,C*Fo] (index c*Fo+fo).
+template <typename T, typename TG>
+__global__ void __launch_bounds__(256) maxpool2d_relu_bwd_kernel(const T* __restrict__ a, const TG* __restrict__ dy, T* __restrict__ dz,
+                                                                 int B, int Tn, int F, int C, int pt, int pf, int in_chmajor) {
+    const int To = (Tn + pt - 1) / pt, Fo = (F + pf - 1) / pf;
+    const int64_t n = (int64_t)B * To * Fo * C;
+    for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < n; e += (int64_t)gridDim.x * 256) {
+        const int c = (int)(e % C);
+        int64_t r = e / C;
+        const int fo = (int)(r % Fo); r /= Fo;
+        const int to = (int)(r % To), b = (int)(r / To);
+        const int t0 = to * pt, t1 = min(Tn, t0 + pt), f0 = fo * pf, f1 = min(F, f0 + pf);
+        float best = -INFINITY;
+        int at = t0, af = f0;
+        for (int t = t0; t < t1; ++t)
+            for (int f = f0; f < f1; ++f) {
+                const float v = bw_ld<T>(a + (((int64_t)b * Tn + t) * F + f) * C + c);
+                if (v > best) { best = v; at = t; af = f; }
+            }
+        const float g = in_chmajor ? bw_ld<TG>(dy + ((int64_t)b * To + to) * ((int64_t)C * Fo) + (int64_t)c * Fo + fo)
+                                   : bw_ld<TG>(dy + e);
+        for (int t = t0; t < t1; ++t)
+            for (int f = f0; f < f1; ++f)
+                bw_st<T>(dz + (((int64_t)b * Tn + t) * F + f) * C + c, (t == at && f == af && best > 0.f) ? g : 0.f);
+    }
+}
+
+unsigned bw_grid(int64_t n) {
+    int64_t b = ceil_div64(n, 256);
+    int64_t cap = (int64_t)num_sms() * 16;
+    return (unsigned)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace
+}  // namespace nsp
+
+using namespace nsp;
+
+extern "C" nsp_status nsp_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* gamma,
+                                        float eps, float in_scale, const float* dres, int64_t lddr,
+                                        float* dx, int64_t lddx, void* dx_bf16, int64_t lddxb,
+                                        float* dgamma, float* dbeta, int M, int D, void* stream) {
+    NSP_CHECK_ARG(dy && x && gamma && (dx || dx_bf16), "layernorm_bwd: null pointer");
+    NSP_CHECK_ARG(M > 0 && D > 0 && D % 4 == 0 && D <= 2048, "layernorm_bwd: bad shape M=%d D=%d (D %% 4 == 0, <= 2048)", M, D);
+    NSP_CHECK_ARG(lddy % 4 == 0 && ldx % 4 == 0 && (!dres || lddr % 4 == 0) && (!dx || lddx % 4 == 0) && (!dx_bf16 || lddxb % 4 == 0),
+                  "layernorm_bwd: row pitches must be multiples of 4 elements");
+    NSP_CHECK_ARG(((uintptr_t)dy % 16 == 0) && ((uintptr_t)x % 16 == 0) && (!dres || (uintptr_t)dres % 16 == 0) &&
+                  (!dx || (uintptr_t)dx % 16 == 0) && (!dx_bf16 || (uintptr_t)dx_bf16 % 8 == 0), "layernorm_bwd: unaligned pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    int grid = ceil_div(M, 8);
+    const int cap = num_sms() * 4;
+    if (grid > cap) grid = cap;
+    const size_t smem = sizeof(float) * 16 * (size_t)D;
+    __nv_bfloat16* dxb = (__nv_bfloat16*)dx_bf16;
+#define NSP_LNB(VPT)                                                                                                     \
+    do {                                                                                                                 \
+        auto kern = layernorm_bwd_kernel<VPT>;                                                                           \
+        static size_t attr = 0;                                                                                          \
+        if (smem > attr) { NSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; } \
+        kern<<<grid, 256, smem, st>>>(dy, lddy, x, ldx, gamma, eps, in_scale, dres, lddr, dx, lddx, dxb, lddxb, dgamma, dbeta, M, D); \
+    } while (0)
+    const int vpt = ceil_div(D / 4, 32);
+    if (vpt <= 1) NSP_LNB(1); else if (vpt <= 2) NSP_LNB(2); else if (vpt <= 4) NSP_LNB(4);
+    else if (vpt <= 8) NSP_LNB(8); else NSP_LNB(16);
+#undef NSP_LNB
+    NSP_LAUNCH_OK();
+    return NSP_OK;
+}
+
+extern "C" nsp_status nsp_act_bwd(int is_bf16, int act, const void* dh, const void* z, void* dz, int64_t n, void* stream) {
+    NSP_CHECK_ARG(dh && z && dz && n >= 0 && act >= 0 && act <= 4, "act_bwd: bad arguments");
+    if (n == 0) return NSP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (is_bf16) act_bwd_kernel<__nv_bfloat16><<<bw_grid(n), 256, 0, st>>>((const __nv_bfloat16*)dh, (const __nv_bfloat16*)z, (__nv_bfloat16*)dz, n, act);
+    else act_bwd_kernel<float><<<bw_grid(n), 256, 0, st>>>((const float*)dh, (const float*)z, (float*)dz, n, act);
+    NSP_LAUNCH_OK();
+    return NSP_OK;
+}
+
+extern "C" nsp_status nsp_glu_bwd(int is_bf16, const void* dg, const void* pre, void* dpre, int64_t M, int d, void* stream) {
+    NSP_CHECK_ARG(dg && pre && dpre && M > 0 && d > 0, "glu_bwd: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (is_bf16) glu_bwd_kernel<__nv_bfloat16><<<bw_grid(M * d), 256, 0, st>>>((const __nv_bfloat16*)dg, (const __nv_bfloat16*)pre, (__nv_bfloat16*)dpre, M, d);
+    else glu_bwd_kernel<float><<<bw_grid(M * d), 256, 0, st>>>((const float*)dg, (const float*)pre, (float*)dpre, M, d);
+    NSP_LAUNCH_OK();
+    return NSP_OK;
+}
+
+extern "C" nsp_status nsp_colsum_acc(int is_bf16, const void* x, int64_t ldx, int M, int N, float alpha, float* y, void* stream) {
+    NSP_CHECK_ARG(x && y && M > 0 && N > 0, "colsum_acc: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    int slices = ceil_div(M, 256);
+    const int cap = ceil_div(num_sms() * 8, ceil_div(N, 32));
+    if (slices > cap) slices = cap < 1 ? 1 : cap;
+    dim3 grid((unsigned)ceil_div(N, 32), (unsigned)slices);
+    if (is_bf16) colsum_acc_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, y, M, N, alpha);
+    else colsum_acc_kernel<float><<<grid, 256, 0, st>>>((const float*)x, ldx, y, M, N, alpha);
+    NSP_LAUNCH_OK();
+    return NSP_OK;
+}
+
+extern "C" nsp_status nsp_maxpool_time_bwd(const float* x, const float* dy, float* dx, int B, int T, int D, int factor, void* stream) {
+    NSP_CHECK_ARG(x && dy && dx && B > 0 && T > 0 && D > 0 && factor >= 1, "maxpool_time_bwd: bad arguments");
+    const int To = (T + factor - 1) / factor;
+    maxpool_time_bwd_kernel<<<bw_grid((int64_t)B * To * D), 256, 0, (cudaStream_t)stream>>>(x, dy, dx, B, T, D, factor);
+    NSP_LAUNCH_OK();
+    return NSP_OK;
+}
+
+extern "C" nsp_status nsp_relu_mask(int is_bf16, const void* dx, const void* a, void* dz, int64_t n, void* stream) {
+    NSP_CHECK_ARG(dx && a && dz && n >= 0, "relu_mask: bad arguments");
+    if (n == 0) return NSP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (is_bf16) relu_mask_kernel<__nv_bfloat16><<<bw_grid(n), 256, 0, st>>>((const __nv_bfloat16*)dx, (const __nv_bfloat16*)a, (__nv_bfloat16*)dz, n);
+    else relu_mask_kernel<float><<<bw_grid(n), 256, 0, st>>>((const float*)dx, (const float*)a, (float*)dz, n);
+    NSP_LAUNCH_OK();
+    return NSP_OK;
+}
+
+extern "C" nsp_status nsp_maxpool2d_relu_bwd(int is_bf16, int dy_bf16, const void* a, const void* dy, void* dz, int B, int T, int F,
+                                             int C, int pool_t, int pool_f, int in_chmajor, void* stream) {
+    NSP_CHECK_ARG(a && dy && dz && B > 0 && T > 0 && F > 0 && C > 0 && pool_t >= 1 && pool_f >= 1, "maxpool2d_relu_bwd: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = (int64_t)B * ceil_div(T, pool_t) * ceil_div(F, pool_f) * C;
+    if (is_bf16 && dy_bf16)
+        maxpool2d_relu_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<bw_grid(n), 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dz, B, T, F, C, pool_t, pool_f, in_chmajor);
+    else if (is_bf16)
+        maxpool2d_relu_bwd_kernel<__nv_bfloat16, float><<<bw_grid(n), 256, 0, st>>>((const __nv_bfloat16*)a, (const float*)dy, (__nv_bfloat16*)dz, B, T, F, C, pool_t, pool_f, in_chmajor);
+    else if (!dy_bf16)
+        maxpool2d_relu_bwd_kernel<float, float><<<bw_grid(n), 256, 0, st>>>((const float*)a, (const float*)dy, (float*)dz, B, T, F, C, pool_t, pool_f, in_chmajor);
+    else { set_error("maxpool2d_relu_bwd: fp32 activations with bf16 gradients are not instantiated"); return NSP_ERR_UNSUPPORTED; }
+    NSP_LAUNCH_OK();
+    return NSP_OK;
+}

@@ -5,7 +5,7 @@ namespace nsp {
 nsp_status gemm_dispatch(int precision, const void* a, const void* a_lo, int64_t lda, const void* w, const void* w_lo,
                          int64_t ldw, int M, int N, int K, int glu, int act, const float* bias,
                          const float* residual, int64_t ldr, float alpha, void* out, int64_t ldo, int out_bf16,
-                         void* out2, int64_t ldo2, cudaStream_t st);
+                         void* out2, int64_t ldo2, void* pre, int64_t ldpre, cudaStream_t st);
 }
 
 extern "C" nsp_status nsp_linear_fwd(int prec, const void* x, const void* x_lo, int64_t ldx,
@@ -14,5 +14,15 @@ extern "C" nsp_status nsp_linear_fwd(int prec, const void* x, const void* x_lo, 
                                      const float* bias, const float* residual, int64_t ldr, float alpha,
                                      void* out, int64_t ldo, int out_bf16, void* out2, int64_t ldo2, void* stream) {
     return nsp::gemm_dispatch(prec, x, x_lo, ldx, w, w_lo, ldw, M, N, K, glu, act, bias, residual, ldr, alpha,
-                              out, ldo, out_bf16, out2, ldo2, (cudaStream_t)stream);
+                              out, ldo, out_bf16, out2, ldo2, nullptr, 0, (cudaStream_t)stream);
+}
+
+extern "C" nsp_status nsp_linear_fwd_save(int prec, const void* x, const void* x_lo, int64_t ldx,
+                                          const void* w, const void* w_lo, int64_t ldw,
+                                          int M, int N, int K, int glu, int act,
+                                          const float* bias, const float* residual, int64_t ldr, float alpha,
+                                          void* out, int64_t ldo, int out_bf16, void* out2, int64_t ldo2,
+                                          void* pre, int64_t ldpre, void* stream) {
+    return nsp::gemm_dispatch(prec, x, x_lo, ldx, w, w_lo, ldw, M, N, K, glu, act, bias, residual, ldr, alpha,
+                              out, ldo, out_bf16, out2, ldo2, pre, ldpre, (cudaStream_t)stream);
 }

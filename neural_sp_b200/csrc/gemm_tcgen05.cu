@@ -91,6 +91,8 @@ struct GemmArgs {
     int64_t ldo;
     void* out2;             // optional second output (bf16 copy of an fp32 result), or null
     int64_t ldo2;
+    void* pre;              // optional: pre-activation (acc + bias) saved for the backward pass, operand dtype
+    int64_t ldpre;          //           [M, N] (GLU: value columns [0,N/2), gate columns [N/2,N)), or null
 };
 
 // epilogue flavours (compile-time: the epilogue is instruction-bound, see profiles/r01_gemm_epilogue.md)
@@ -110,6 +112,35 @@ __device__ __forceinline__ float sigmoid_f(float x) {
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&p);
+}
+
+// store CW consecutive values of one row in the operand dtype (bf16 or fp32); nvalid = columns inside the matrix
+template <bool BF16, int CW>
+__device__ __forceinline__ void store_pre(void* base, int64_t ld, int row, int col, const float* v, int nvalid) {
+    if constexpr (BF16) {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(base) + (int64_t)row * ld + col;
+        if (nvalid >= CW && (ld % 8 == 0) && (col % 8 == 0)) {
+#pragma unroll
+            for (int j = 0; j < CW; j += 8) {
+                uint4 pk;
+                pk.x = pack_bf16(v[j], v[j + 1]); pk.y = pack_bf16(v[j + 2], v[j + 3]);
+                pk.z = pack_bf16(v[j + 4], v[j + 5]); pk.w = pack_bf16(v[j + 6], v[j + 7]);
+                *reinterpret_cast<uint4*>(o + j) = pk;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) if (j < nvalid) o[j] = __float2bfloat16_rn(v[j]);
+        }
+    } else {
+        float* o = reinterpret_cast<float*>(base) + (int64_t)row * ld + col;
+        if (nvalid >= CW && (ld % 4 == 0) && (col % 4 == 0)) {
+#pragma unroll
+            for (int j = 0; j < CW; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) if (j < nvalid) o[j] = v[j];
+        }
+    }
 }
 
 template <typename TIn, int BN, int STAGES, int ACT, bool GLU, bool RES, bool OUTBF16>
@@ -264,17 +295,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
                         for (int j = 0; j < CW; ++j) if (cbase + j < nout) v[j] += __ldg(g.bias + cbase + j);
                     }
                 }
+                if (g.pre && row_ok) store_pre<kBF16, CW>(g.pre, g.ldpre, row, cbase, v, nout - cbase);
                 if constexpr (GLU) {
                     uint32_t r2[32];
                     if constexpr (CW == 32) tc::tmem_ld_32x32(t_row + (uint32_t)(BN / 2 + tcol), r2);
                     else tc::tmem_ld_32x16(t_row + (uint32_t)(BN / 2 + tcol), r2);
                     tc::tmem_ld_wait();
+                    float gv[CW];
 #pragma unroll
                     for (int j = 0; j < CW; ++j) {
                         float gt = __uint_as_float(r2[j]);
                         if (has_bias && cbase + j < nout) gt += __ldg(g.bias + nout + cbase + j);
+                        gv[j] = gt;
                         v[j] *= sigmoid_f<kBF16>(gt);
                     }
+                    if (g.pre && row_ok) store_pre<kBF16, CW>(g.pre, g.ldpre, row, nout + cbase, gv, nout - cbase);
                 } else if constexpr (ACT == ACT_RELU) {
 #pragma unroll
                     for (int j = 0; j < CW; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -420,7 +455,7 @@ nsp_status dispatch_epi(const GemmMaps& maps, const GemmArgs& g, int glu, int ac
 nsp_status gemm_dispatch(int precision, const void* a, const void* a_lo, int64_t lda, const void* w, const void* w_lo,
                          int64_t ldw, int M, int N, int K, int glu, int act, const float* bias,
                          const float* residual, int64_t ldr, float alpha, void* out, int64_t ldo, int out_bf16,
-                         void* out2, int64_t ldo2, cudaStream_t st) {
+                         void* out2, int64_t ldo2, void* pre, int64_t ldpre, cudaStream_t st) {
     NSP_CHECK_ARG(a && w && out, "gemm: null pointer");
     NSP_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
     NSP_CHECK_ARG(precision >= 0 && precision <= 2, "gemm: precision=%d", precision);
@@ -432,6 +467,7 @@ nsp_status gemm_dispatch(int precision, const void* a, const void* a_lo, int64_t
     GemmArgs g;
     g.M = M; g.N = N; g.K = K; g.bias = bias; g.residual = residual; g.ldr = ldr;
     g.alpha = alpha; g.out = out; g.ldo = ldo; g.out2 = out2; g.ldo2 = ldo2;
+    g.pre = pre; g.ldpre = ldpre;
     g.nseg = precision == 2 ? 3 : 1;
     NSP_CHECK_ARG(act >= 0 && act <= 4, "gemm: act=%d", act);
     NSP_CHECK_ARG(!(out2 && out_bf16), "gemm: out2 is only meaningful with an fp32 primary output");

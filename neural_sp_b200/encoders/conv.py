@@ -151,6 +151,14 @@ class ConvEncoder(EncoderBase):
     def context_size(self):
         return self._context_size
 
+    def output_lens(self, xlens):
+        """Length arithmetic of the block stack alone (reference conv.py:451-477), for the training path."""
+        for block in self.layers:
+            xlens = torch.IntTensor([_conv_len(_conv_len(int(n), 1), 1) for n in xlens])
+            if block.pool is not None:
+                xlens = torch.IntTensor([_pool_len(int(n), block.pooling[0]) for n in xlens])
+        return xlens
+
     def forward(self, xs, xlens, lookback=False, lookahead=False, out_scale=1.0):
         """xs `[B, T, F]` fp32 on the GPU, xlens IntTensor `[B]` (CPU) -> (`[B, T', odim]` fp32, xlens)."""
         B, T, Fdim = xs.size()

@@ -14,6 +14,9 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+import random
+
+from .. import autograd as ag
 from .. import ops
 from ..modules._prep import prepared, get_precision
 from ..modules.positional_embedding import XLPositionalEmbedding
@@ -164,20 +167,38 @@ class TransformerEncoder(EncoderBase):
         self.cache = [None] * self.n_layers
         self.offset = 0
 
-    def _proj(self, name, lin, xs, scale=1.0):
+    def _proj(self, name, lin, xs, scale=1.0, train=False):
         prec = get_precision(self)
+        if train:
+            return ag.scale(ag.linear(self, name, lin, xs, prec), scale)
         return ops.linear(xs, prepared(self, name, prec, (lin.weight,)), lin.bias, prec=prec, alpha=scale,
                           out_dtype=torch.float32)
 
-    def _sub_out(self, xs, module):
+    def _norm(self, norm, xs, train=False):
+        if train:
+            return ag.layernorm(norm, xs)
+        return ops.layernorm(xs, norm.weight, norm.bias, norm.eps)
+
+    def _sub_out(self, xs, module, train=False):
         xs_sub = xs.clone()
         bridge = getattr(self, 'bridge_' + module)
         if bridge is not None:
-            xs_sub = self._proj('bridge_' + module, bridge, xs_sub)
+            xs_sub = self._proj('bridge_' + module, bridge, xs_sub, train=train)
         norm = getattr(self, 'norm_out_' + module)
         if norm is not None:
-            xs_sub = ops.layernorm(xs_sub, norm.weight, norm.bias, norm.eps)
+            xs_sub = self._norm(norm, xs_sub, train)
         return xs_sub
+
+    def _train_layer(self, lth, layer, xs, klens, pos, mask_kw, prec):
+        """One block through its autograd node (training): LayerDrop as in conformer_block.py:122-126."""
+        if layer.dropout.p > 0 or layer.self_attn.dropout_attn.p > 0:
+            raise NotImplementedError("dropout > 0 in training mode is not on the B200 path yet")
+        in_scale = 1.0
+        if layer.dropout_layer > 0:
+            if random.random() < layer.dropout_layer:
+                return xs
+            in_scale = 1.0 / (1 - layer.dropout_layer)
+        return ag.block_forward(layer, xs, klens, pos, (self.u_bias, self.v_bias), mask_kw, prec, in_scale)
 
     def forward(self, xs, xlens, task, streaming=False, lookback=False, lookahead=False):
         """xs `[B, T, input_dim]` fp32 on the GPU; xlens IntTensor `[B]` on the CPU (reference contract)."""
@@ -185,7 +206,11 @@ class TransformerEncoder(EncoderBase):
             raise NotImplementedError("streaming inference is a 'next' row (SURVEY.md 8f-4)")
         eouts = {'ys': {'xs': None, 'xlens': None}, 'ys_sub1': {'xs': None, 'xlens': None},
                  'ys_sub2': {'xs': None, 'xlens': None}}
-        with torch.no_grad():
+        # train() + grad mode: every block / the front-end is one autograd node with a hand-written CUDA backward
+        # (neural_sp_b200/autograd.py); otherwise inference kernels under no_grad (in-place residual stream).
+        train = ag.training_enabled(self)
+        prec = get_precision(self)
+        with (torch.enable_grad() if train else torch.no_grad()):
             rel = 'relative' in self.pe_type
             bs = xs.size(0)
             N_l, N_c, N_r = self.N_l, self.N_c, self.N_r
@@ -194,7 +219,13 @@ class TransformerEncoder(EncoderBase):
                 xs = chunkwise(xs, 0, N_c, 0) if self.streaming_type == 'mask' else chunkwise(xs, N_l, N_c, N_r)
                 n_chunks = xs.size(0) // bs
             if self.conv is None:
-                xs = self._proj('embed', self.embed, xs.float(), scale=self.scale if rel else 1.0)
+                xs = self._proj('embed', self.embed, xs.float(), scale=self.scale if rel else 1.0, train=train)
+            elif train:
+                if lookback or lookahead:
+                    raise NotImplementedError("CNN lookback/lookahead trimming (streaming) is a 'next' row")
+                xs = ag.frontend_forward(self.conv, xs, self.scale if (rel and self.enc_type != 'conv') else 1.0, prec)
+                xlens = self.conv.output_lens(xlens)
+                N_l, N_c, N_r = max(0, N_l // self.conv_factor), N_c // self.conv_factor, N_r // self.conv_factor
             else:
                 xs, xlens = self.conv(xs, xlens, lookback=False if self.lc_bidir else lookback,
                                       lookahead=False if self.lc_bidir else lookahead,
@@ -224,20 +255,29 @@ class TransformerEncoder(EncoderBase):
                 return {}
 
             for lth, layer in enumerate(self.layers):
-                xs, _ = layer(xs, klens, cache=None, pos_embs=pos, rel_bias=(self.u_bias, self.v_bias),
-                              mask_kw=mask_kw(lth))
+                if train:
+                    xs = self._train_layer(lth, layer, xs, klens, pos, mask_kw(lth), prec)
+                else:
+                    xs, _ = layer(xs, klens, cache=None, pos_embs=pos, rel_bias=(self.u_bias, self.v_bias),
+                                  mask_kw=mask_kw(lth))
                 if lth == self.n_layers_sub1 - 1:
-                    xs_sub1, xlens_sub1 = self._sub_out(xs, 'sub1'), xlens.clone()
+                    xs_sub1, xlens_sub1 = self._sub_out(xs, 'sub1', train), xlens.clone()
                     if task == 'ys_sub1':
                         eouts[task]['xs'], eouts[task]['xlens'] = xs_sub1, xlens_sub1
                         return eouts
                 if lth == self.n_layers_sub2 - 1:
-                    xs_sub2, xlens_sub2 = self._sub_out(xs, 'sub2'), xlens.clone()
+                    xs_sub2, xlens_sub2 = self._sub_out(xs, 'sub2', train), xlens.clone()
                     if task == 'ys_sub2':
                         eouts[task]['xs'], eouts[task]['xlens'] = xs_sub2, xlens_sub2
                         return eouts
                 if lth < len(self.layers) - 1 and self.subsample_factors[lth] > 1:
-                    xs, xlens = self.subsample_layers[lth](xs, xlens)
+                    if train:
+                        sub = self.subsample_layers[lth]
+                        if not isinstance(sub, MaxPoolSubsampler):
+                            raise NotImplementedError("training: only subsample_type=max_pool has a CUDA backward")
+                        xs, xlens = ag.maxpool_time(xs, sub.factor), sub._lens(xlens)
+                    else:
+                        xs, xlens = self.subsample_layers[lth](xs, xlens)
                     f = self.subsample_factors[lth]
                     N_l, N_c, N_r = max(0, N_l // f), N_c // f, N_r // f
                     klens = key_lens()
@@ -245,9 +285,9 @@ class TransformerEncoder(EncoderBase):
                         pos = self.pos_emb.table(xs.size(1))
             if self.streaming_type == 'reshape':                      # keep the centre of every window (:546-550)
                 xs = xs[:, N_l:N_l + N_c].contiguous().view(bs, -1, xs.size(2))[:, :int(xlens.max())].contiguous()
-            xs = ops.layernorm(xs, self.norm_out.weight, self.norm_out.bias, self.norm_out.eps)
+            xs = self._norm(self.norm_out, xs, train)
             if self.bridge is not None:
-                xs = self._proj('bridge', self.bridge, xs)
+                xs = self._proj('bridge', self.bridge, xs, train=train)
         if task in ['all', 'ys']:
             eouts['ys']['xs'], eouts['ys']['xlens'] = xs, xlens
         if self.n_layers_sub1 >= 1 and task == 'all':

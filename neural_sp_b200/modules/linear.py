@@ -30,11 +30,12 @@ class _LinearFn(torch.autograd.Function):
             wt = prepared(ctx.module, "wT", prec, (weight,), build=lambda w: w.t().contiguous())
             gx = ops.linear(gy2, wt, None, prec=prec, out_dtype=torch.float32).reshape(x.shape)
         if ctx.needs_input_grad[1]:
-            # dW[N,K] = dY^T[N,M] @ X[M,K]  ->  A = dY^T [N,M], "weight" = X^T [K,M]
-            gw = ops.linear(gy2.t().contiguous(), ops.prepare_weight(x2.t().contiguous(), prec), None, prec=prec,
-                            out_dtype=torch.float32)
+            # dW[N,K] = dY^T[N,M] @ X[M,K] on the MN-major wgrad kernel (no transposed copies)
+            gw = torch.zeros(weight.shape, dtype=torch.float32, device=weight.device)
+            ops.linear_wgrad(gy2, x2, prec, gw)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = ops.colsum(gy2)
+            gb = torch.zeros(gy2.shape[1], dtype=torch.float32, device=gy2.device)
+            ops.colsum_acc(gy2, gb)
         return gx, gw, gb, None, None
 
 

@@ -172,7 +172,7 @@ def prepare_weight(w, prec):
 
 
 def linear(x, w_prepared, bias=None, prec="bf16", act=None, glu=False, residual=None, alpha=1.0,
-           out_dtype=torch.float32, out=None, out2_bf16=False):
+           out_dtype=torch.float32, out=None, out2_bf16=False, save_pre=False):
     """out = residual + alpha * act(x @ w^T + bias) on the tcgen05 GEMM (nsp_linear_fwd).
 
     x: [..., K] (bf16 for prec='bf16', else fp32); w_prepared: tuple from prepare_weight.
@@ -205,16 +205,20 @@ def linear(x, w_prepared, bias=None, prec="bf16", act=None, glu=False, residual=
     out2d = out.reshape(-1, nout)
     res2d = residual.reshape(-1, nout) if residual is not None else None
     out2 = torch.empty(M, nout, dtype=torch.bfloat16, device=x.device) if out2_bf16 else None
-    _run("nsp_linear_fwd", lib.nsp_linear_fwd, PREC[prec], ptr(x2), ptr(x_lo), x2.stride(0), ptr(w), ptr(w_lo), w.stride(0),
+    pre = torch.empty(M, N, dtype=torch.bfloat16 if prec == "bf16" else torch.float32, device=x.device) if save_pre else None
+    _run("nsp_linear_fwd_save", lib.nsp_linear_fwd_save, PREC[prec], ptr(x2), ptr(x_lo), x2.stride(0), ptr(w), ptr(w_lo), w.stride(0),
          M, N, K, int(glu), ACT[act], ptr(bias), ptr(res2d),
          res2d.stride(0) if res2d is not None else 0, float(alpha),
          ptr(out2d), out2d.stride(0), int(out2d.dtype == torch.bfloat16),
-         ptr(out2), out2.stride(0) if out2 is not None else 0, current_stream_ptr(),
+         ptr(out2), out2.stride(0) if out2 is not None else 0, ptr(pre), N, current_stream_ptr(),
          flops=2.0 * M * N * K, tag="gemm_%s" % prec)
     res = out2d.reshape(*lead, nout)
+    rets = (res,)
     if out2_bf16:
-        return res, out2.reshape(*lead, nout)
-    return res
+        rets += (out2.reshape(*lead, nout),)
+    if save_pre:
+        rets += (pre.reshape(*lead, N),)
+    return rets if len(rets) > 1 else res
 
 
 # ---------------------------------------------------------------------------------------------
@@ -454,3 +458,192 @@ def lstm_seq(gates_x, w_hh, lens, n_dirs):
     _run("nsp_lstm_seq_fwd", lib.nsp_lstm_seq_fwd, ptr(gates_x), ptr(w_hh), ptr(lens), ptr(y), B, T, H, n_dirs, ptr(ws),
          ws_bytes, current_stream_ptr(), flops=2.0 * B * T * n_dirs * 4 * H * H, tag="lstm_seq")
     return y
+
+
+# ---------------------------------------------------------------------------------------------
+# backward pass (training): hand-written gradients of the forward ops above
+# ---------------------------------------------------------------------------------------------
+KERNELS_PER_CALL["nsp_relpos_attention_bwd"] = 2
+KERNELS_PER_CALL["nsp_conformer_conv_bwd"] = 2
+
+
+def _operand(x, prec):
+    """2-D contiguous operand in the GEMM dtype of `prec`: bf16, fp32, or (hi, lo) for 'fp32'."""
+    x = x.reshape(-1, x.shape[-1])
+    if prec == "bf16":
+        return to_bf16(x.contiguous()), None
+    x = x.float().contiguous()
+    if prec == "fp32":
+        return split_tf32(x)
+    return x, None
+
+
+def linear_wgrad(dy, x, prec, dw, alpha=1.0, accumulate=True):
+    """dw[N,K] (+)= alpha * dy[M,N]^T x[M,K] on the tcgen05 MN-major wgrad kernel (nsp_linear_wgrad)."""
+    _require_cuda(dy, x, dw)
+    assert dw.dtype == torch.float32 and dw.dim() == 2 and dw.stride(1) == 1
+    N, K = dw.shape
+    dy2, x2 = dy.reshape(-1, N), x.reshape(-1, x.shape[-1])[:, :K]
+    M = dy2.shape[0]
+    assert x2.shape[0] == M, (dy.shape, x.shape)
+    mult = 8 if prec == "bf16" else 4
+    if N % mult or K % mult:                       # TMA pitches are 16-byte multiples: pad odd widths through a temporary
+        Np, Kp = -(-N // mult) * mult, -(-K // mult) * mult
+        tmp = torch.zeros(Np, Kp, dtype=torch.float32, device=dw.device)
+        linear_wgrad(torch.nn.functional.pad(dy2, (0, Np - N)), torch.nn.functional.pad(x2, (0, Kp - K)), prec, tmp, alpha, True)
+        if accumulate:
+            dw.add_(tmp[:N, :K])
+        else:
+            dw.copy_(tmp[:N, :K])
+        return dw
+    dyh, dyl = _operand(dy2, prec)
+    xh, xl = _operand(x2, prec)
+    _run("nsp_linear_wgrad", lib.nsp_linear_wgrad, PREC[prec], ptr(dyh), ptr(dyl), dyh.stride(0), ptr(xh), ptr(xl), xh.stride(0),
+         M, N, K, float(alpha), ptr(dw), dw.stride(0), int(accumulate), current_stream_ptr(),
+         flops=2.0 * M * N * K, tag="gemm_wgrad_%s" % prec)
+    return dw
+
+
+def layernorm_bwd(dy, x, gamma, eps, dres=None, dgamma=None, dbeta=None, want_fp32=True, want_bf16=False, in_scale=1.0):
+    """dx = dres + LN'(x).dy (nsp_layernorm_bwd); dgamma/dbeta fp32 [D] are accumulated.  Returns fp32 and/or bf16 dx."""
+    _require_cuda(dy, x)
+    D = x.shape[-1]
+    dy2, x2 = dy.reshape(-1, D).float(), x.reshape(-1, D)
+    dy2 = dy2 if dy2.stride(1) == 1 else dy2.contiguous()
+    M = x2.shape[0]
+    dr2 = dres.reshape(-1, D) if dres is not None else None
+    dx = torch.empty(M, D, dtype=torch.float32, device=x.device) if want_fp32 else None
+    dxb = torch.empty(M, D, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    _run("nsp_layernorm_bwd", lib.nsp_layernorm_bwd, ptr(dy2), dy2.stride(0), ptr(x2), x2.stride(0), ptr(gamma), float(eps),
+         float(in_scale), ptr(dr2), dr2.stride(0) if dr2 is not None else 0, ptr(dx), D, ptr(dxb), D,
+         ptr(dgamma), ptr(dbeta), M, D, current_stream_ptr(), nbytes=M * D * 12.0)
+    outs = tuple(t.reshape(x.shape) for t in (dx, dxb) if t is not None)
+    return outs[0] if len(outs) == 1 else outs
+
+
+def act_bwd(dh, z, act):
+    """dz = dh * act'(z) (nsp_act_bwd)."""
+    _require_cuda(dh, z)
+    assert dh.dtype == z.dtype and dh.shape == z.shape
+    dh, z = dh.contiguous(), z.contiguous()
+    dz = torch.empty_like(dh)
+    _run("nsp_act_bwd", lib.nsp_act_bwd, int(dh.dtype == torch.bfloat16), ACT[act], ptr(dh), ptr(z), ptr(dz), dh.numel(),
+         current_stream_ptr())
+    return dz
+
+
+def glu_bwd(dg, pre):
+    """Backward of out = a * sigmoid(b), pre = [a | b] (nsp_glu_bwd) -> dpre like pre."""
+    _require_cuda(dg, pre)
+    d = dg.shape[-1]
+    dg, pre = dg.contiguous(), pre.contiguous()
+    assert pre.shape[-1] == 2 * d and dg.dtype == pre.dtype
+    dpre = torch.empty_like(pre)
+    _run("nsp_glu_bwd", lib.nsp_glu_bwd, int(dg.dtype == torch.bfloat16), ptr(dg), ptr(pre), ptr(dpre), dg.numel() // d, d,
+         current_stream_ptr())
+    return dpre
+
+
+def colsum_acc(x, y, alpha=1.0):
+    """y[N] += alpha * column sums of x [M,N] (bf16 or fp32) (nsp_colsum_acc)."""
+    _require_cuda(x, y)
+    x2 = x.reshape(-1, x.shape[-1])
+    x2 = x2 if x2.stride(1) == 1 else x2.contiguous()
+    if x2.dtype not in (torch.bfloat16, torch.float32):
+        x2 = x2.float()
+    _run("nsp_colsum_acc", lib.nsp_colsum_acc, int(x2.dtype == torch.bfloat16), ptr(x2), x2.stride(0), x2.shape[0], x2.shape[1],
+         float(alpha), ptr(y), current_stream_ptr())
+    return y
+
+
+def maxpool_time_bwd(x, dy, factor):
+    """MaxPoolSubsampler backward (nsp_maxpool_time_bwd): x fp32 [B,T,D] forward input, dy fp32 [B,T',D]."""
+    _require_cuda(x, dy)
+    x, dy = x.contiguous().float(), dy.contiguous().float()
+    B, T, D = x.shape
+    dx = torch.empty_like(x)
+    _run("nsp_maxpool_time_bwd", lib.nsp_maxpool_time_bwd, ptr(x), ptr(dy), ptr(dx), B, T, D, int(factor), current_stream_ptr())
+    return dx
+
+
+def relu_mask(dx, a):
+    """dz = a > 0 ? dx : 0 (nsp_relu_mask)."""
+    _require_cuda(dx, a)
+    dx, a = dx.contiguous(), a.contiguous()
+    assert dx.dtype == a.dtype and dx.numel() == a.numel()
+    dz = torch.empty_like(dx)
+    _run("nsp_relu_mask", lib.nsp_relu_mask, int(dx.dtype == torch.bfloat16), ptr(dx), ptr(a), ptr(dz), dx.numel(), current_stream_ptr())
+    return dz
+
+
+def maxpool2d_relu_bwd(a, dy, pool_t, pool_f, in_chmajor=False):
+    """ReLU + ceil-mode max-pool backward on channels-last a `[B,T,F,C]` (nsp_maxpool2d_relu_bwd)."""
+    _require_cuda(a, dy)
+    a, dy = a.contiguous(), dy.contiguous()
+    B, T, F, C = a.shape
+    dz = torch.empty_like(a)
+    _run("nsp_maxpool2d_relu_bwd", lib.nsp_maxpool2d_relu_bwd, int(a.dtype == torch.bfloat16), int(dy.dtype == torch.bfloat16),
+         ptr(a), ptr(dy), ptr(dz), B, T, F, C, int(pool_t), int(pool_f), int(in_chmajor), current_stream_ptr())
+    return dz
+
+
+def conv3x3_wgrad(a, dz, dw, dbias, B, T, F, in_chmajor=False):
+    """dw[CO,CI,3,3] += ..., dbias[CO] += ... (nsp_conv3x3_wgrad); a holds B*T*F*CI elements, dz `[B,T,F,CO]`."""
+    _require_cuda(a, dz, dw)
+    CO, CI = dw.shape[0], dw.shape[1]
+    a, dz = a.contiguous(), dz.contiguous()
+    assert a.numel() == B * T * F * CI and dz.numel() == B * T * F * CO and dw.is_contiguous()
+    _run("nsp_conv3x3_wgrad", lib.nsp_conv3x3_wgrad, int(a.dtype == torch.bfloat16), int(dz.dtype == torch.bfloat16), ptr(a),
+         int(in_chmajor), ptr(dz), ptr(dw), ptr(dbias), B, T, F, CI, CO, current_stream_ptr(),
+         flops=2.0 * B * T * F * 9 * CI * CO, tag="conv3x3_wgrad")
+    return dw
+
+
+def conv3x3_dgrad_weight(weight):
+    """Taps of the input-gradient convolution: w'[ci, co, ky, kx] = w[co, ci, 2-ky, 2-kx]."""
+    return weight.detach().flip(2, 3).transpose(0, 1).contiguous()
+
+
+def relpos_attention_bwd(q, k, v, klens, n_heads, out, dout, r=None, u_bias=None, v_bias=None, clamp_len=-1, causal=False,
+                         lookahead=0, chunk_c=0, chunk_l=0, dr=None, du=None, dvb=None):
+    """Backward of relpos_attention (nsp_relpos_attention_bwd).  Returns dqkv `[B, T, 3*D]` (requires Tq == Tk) with
+    dq | dk | dv in the I/O dtype; dr `[rlen, D]`, du, dvb fp32 are accumulated in place when given."""
+    _require_cuda(q, k, v, klens, out, dout)
+    B, Tq, D = q.shape
+    Tk = k.shape[1]
+    assert Tq == Tk, "training path: no cache (Tq == Tk)"
+    dk = D // n_heads
+    dout = dout.to(q.dtype)
+    dout = dout if dout.stride(2) == 1 and dout.stride(0) == Tq * dout.stride(1) else dout.contiguous()
+    out = out if out.stride(2) == 1 and out.stride(0) == Tq * out.stride(1) else out.contiguous()
+    if r is not None:
+        r = r.reshape(-1, D) if r.dim() == 3 else r
+    rlen = r.shape[0] if r is not None else 0
+    dqkv = torch.empty(B, Tq, 3 * D, dtype=q.dtype, device=q.device)
+    ws_bytes = lib.nsp_relpos_attention_bwd_workspace_bytes(B, n_heads, Tq, rlen, int(clamp_len), int(r is not None))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device)
+    dq_, dk_, dv_ = dqkv[:, :, :D], dqkv[:, :, D:2 * D], dqkv[:, :, 2 * D:]
+    _run("nsp_relpos_attention_bwd", lib.nsp_relpos_attention_bwd, int(q.dtype == torch.bfloat16), ptr(q), q.stride(1), ptr(k), k.stride(1),
+         ptr(v), v.stride(1), ptr(r), r.stride(0) if r is not None else 0, rlen, ptr(u_bias), ptr(v_bias), ptr(klens),
+         ptr(out), out.stride(1), ptr(dout), dout.stride(1), ptr(dq_), 3 * D, ptr(dk_), 3 * D, ptr(dv_), 3 * D,
+         ptr(dr), dr.stride(0) if dr is not None else 0, ptr(du), ptr(dvb), B, n_heads, Tq, Tk, dk, int(clamp_len),
+         int(causal), int(lookahead), int(chunk_c), int(chunk_l), ptr(ws), ws_bytes, current_stream_ptr(),
+         flops=16.0 * B * n_heads * Tq * Tk * dk, tag="attention_bwd")
+    return dqkv
+
+
+def conformer_conv_bwd(x, taps, dw_bias, norm_w, norm_b, eps, dy, dtaps, dbias, dnorm_w, dnorm_b, causal=False):
+    """Backward of conformer_conv (LayerNorm variant; nsp_conformer_conv_bwd).  x, dy `[B,T,d]` in the I/O dtype;
+    taps fp32 `[k,d]`; dtaps `[k,d]`, dbias, dnorm_w, dnorm_b fp32 `[d]` are accumulated.  Returns dx like x."""
+    _require_cuda(x, dy)
+    B, T, d = x.shape
+    k = taps.shape[0]
+    x = x if x.stride(2) == 1 and x.stride(0) == T * x.stride(1) else x.contiguous()
+    dy = dy.to(x.dtype)
+    dy = dy if dy.stride(2) == 1 and dy.stride(0) == T * dy.stride(1) else dy.contiguous()
+    dz = torch.empty(B, T, d, dtype=x.dtype, device=x.device)
+    dx = torch.empty(B, T, d, dtype=x.dtype, device=x.device)
+    _run("nsp_conformer_conv_bwd", lib.nsp_conformer_conv_bwd, int(x.dtype == torch.bfloat16), ptr(x), x.stride(1), ptr(taps), ptr(dw_bias),
+         0, ptr(norm_w), ptr(norm_b), float(eps), ptr(dy), dy.stride(1), ptr(dz), d, ptr(dx), d,
+         ptr(dtaps), ptr(dbias), ptr(dnorm_w), ptr(dnorm_b), B, T, d, k, int(causal), current_stream_ptr())
+    return dx

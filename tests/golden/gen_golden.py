@@ -106,6 +106,9 @@ if __name__ == "__main__":
     if "encoder" in what:
         from gen_golden_encoder import gen_encoder
         gen_encoder()
+    if "encoder_grads" in what:
+        from gen_golden_encoder import gen_encoder_grads
+        gen_encoder_grads()
     if "rnn" in what:
         from gen_golden_encoder import gen_rnn_encoder
         gen_rnn_encoder()

@@ -195,3 +195,33 @@ def gen_rnn_encoder():
         save["cfg"] = np.array(json.dumps(dict(args=cfg, conv=case["conv"])))
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **save)
         print("rnn", name, out['ys']['xs'].shape, np.asarray(out['ys']['xlens']).tolist())
+
+
+GRAD_CASES = ["enc_conformer_small", "enc_transformer_xl", "enc_transformer_plain", "enc_uni_conformer"]
+
+
+def grad_loss_weights(shape, seed=4321):
+    """Fixed projection of the encoder output to a scalar: loss = sum(ys * w) (shared by generator and tests)."""
+    return np.random.default_rng(seed).standard_normal(shape).astype(np.float32)
+
+
+def gen_encoder_grads():
+    """Parameter gradients of the UNMODIFIED reference (torch autograd, CPU fp32) for loss = sum(ys * w):
+    encgrad_<case>.npz holds ``g.<param>`` for every parameter; inputs / weights are those of enc_<case>.npz."""
+    for name in GRAD_CASES:
+        case = CASES[name]
+        enc, args, conv_args, kind = build_reference(name)      # eval(): dropouts are 0, LayerDrop is 0 in these cases
+        base = np.load(os.path.join(HERE, name + ".npz"))
+        for k, v in enc.state_dict().items():
+            assert np.array_equal(v.numpy(), base["sd." + k]), k
+        xs = torch.from_numpy(base["xs"])
+        out = enc(xs, torch.IntTensor(case["xlens"]), task='all')
+        ys = out['ys']['xs']
+        w = torch.from_numpy(grad_loss_weights(tuple(ys.shape)))
+        loss = (ys * w).sum()
+        loss.backward()
+        save = {"g." + k: p.grad.numpy() for k, p in enc.named_parameters() if p.grad is not None}
+        missing = [k for k, p in enc.named_parameters() if p.grad is None]
+        save["loss"] = np.array(float(loss.detach()), np.float32)
+        np.savez_compressed(os.path.join(HERE, "encgrad_" + name[4:] + ".npz"), **save)
+        print("encoder grads", name, float(loss), len(save) - 1, "tensors; no grad:", missing)
