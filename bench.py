@@ -4,11 +4,13 @@
     python bench.py --gpus N --steps K --warmup W            # our CUDA path (one rank per GPU under torchrun)
     python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port) on host cores
 
-One "step" = one pass of the hot path over one batch of synthetic 80-dim log-mel input:
-encoder forward (conv front-end -> 17 Conformer blocks) -> CTC head -> fused CTC forward+backward
-(loss and d loss/d logits) -> head backward (d loss/d eouts, head weight grads) -> NCCL all-reduce of the
-gradients that exist (N > 1).  The encoder backward is not on the CUDA path yet and is NOT counted
-(config.step says so).  Prints ONE JSON line on rank 0.
+One "step" (--step train, the default) = one training pass of the hot path over one batch of synthetic 80-dim
+log-mel input: encoder forward (conv front-end -> 17 Conformer blocks) -> CTC head -> fused CTC forward+backward
+(loss and d loss/d logits) -> head backward -> encoder backward (hand-written CUDA chains behind autograd nodes)
+-> ONE NCCL all-reduce of the flat gradient buffer (N > 1) -> torch.optim.Adam(fused) parameter update (library
+code, as in the reference's trainer; --optimizer none drops it).  --step fwd times the forward + loss only
+(the round-1 definition); the JSON line of a train run also carries the fwd-only figure under "fwd".
+Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -121,7 +123,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_arm(w, steps, warmup, sample_B=2):
+def cpu_reference_arm(w, steps, warmup, sample_B=2, train=True):
     """The reference's CPU path, restated (oracle/): encoder forward + CTC forward/backward on the host cores."""
     import torch
     from oracle import encoder_oracle, ctc_oracle  # noqa: F401  (checker / baseline only)
@@ -133,7 +135,7 @@ def cpu_reference_arm(w, steps, warmup, sample_B=2):
     a = enc_args(w)
     a["frontend_conv"] = ConvEncoder(**conv_args(w))
     enc = ConformerEncoder(**a)                      # parameter container only (random init); arithmetic = oracle
-    sd = {k: v.detach().float() for k, v in enc.state_dict().items()}
+    sd = {k: v.detach().float().requires_grad_(train and v.is_floating_point()) for k, v in enc.state_dict().items()}
     D, V = w["d_model"], w["vocab"]
     W0, b0 = torch.randn(512, D) / D ** 0.5, torch.zeros(512)
     W1, b1 = torch.randn(V, 512) / 512 ** 0.5, torch.zeros(V)
@@ -149,9 +151,15 @@ def cpu_reference_arm(w, steps, warmup, sample_B=2):
     ylens = torch.tensor([len(y) for y in ys], dtype=torch.int32)
 
     def step():
-        with torch.no_grad():
+        if train:                      # reference training step: autograd through the whole encoder (torch CPU kernels)
+            for v in sd.values():
+                v.grad = None
             out = encoder_oracle.encoder_forward(sd, xs_t, xlens, cfg)
-        e = out["xs"].requires_grad_(True)
+            e = out["xs"]
+        else:
+            with torch.no_grad():
+                out = encoder_oracle.encoder_forward(sd, xs_t, xlens, cfg)
+            e = out["xs"].requires_grad_(True)
         logits = torch.nn.functional.linear(torch.nn.functional.linear(e, W0, b0), W1, b1)
         elens = torch.tensor(out["xlens"], dtype=torch.int32)
         # reference CTC.forward arithmetic (ctc.py:124-129): log_softmax -> CTCLoss(sum, zero_infinity)/B + lsm KL
@@ -169,7 +177,9 @@ def cpu_reference_arm(w, steps, warmup, sample_B=2):
         step()
     dt = (time.perf_counter() - t0) / steps
     frames = sum(xlens)
-    return dict(value=frames / dt, ms_per_step=dt * 1e3, cores=cores, sample="B=%d T=%d of workload, %d steps" % (sample_B, w["T"], steps))
+    return dict(value=frames / dt, ms_per_step=dt * 1e3, cores=cores,
+                sample="B=%d T=%d of workload, %d %s steps (oracle port of the reference's torch-CPU path)" %
+                       (sample_B, w["T"], steps, "training (fwd+loss+bwd)" if train else "fwd+loss"))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -183,6 +193,9 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a captured CUDA graph")
+    ap.add_argument("--step", default="train", choices=["train", "fwd"],
+                    help="train: fwd + loss + bwd + grad all-reduce + optimizer; fwd: encoder fwd + CTC fwd/bwd + head bwd")
+    ap.add_argument("--optimizer", default="adam", choices=["adam", "none"])
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -191,14 +204,16 @@ def main():
     cfg_common = {"workload": "%s: Conformer %dL d%d ff%d H%d k15 LN rel-pos clamp10, conv 32_32 %s, hier. max-pool, "
                               "CTC fc512 V=%d lsm0.1; B=%d/GPU T=%d fixed" % (args.workload, w["n_layers"], w["d_model"], w["d_ff"],
                                                                             w["n_heads"], w["poolings"], w["vocab"], w["B"], w["T"]),
-                  "step": "encoder_fwd + ctc_head + ctc_fwd_bwd + head_bwd (encoder backward not built yet)",
+                  "step": ("train: encoder_fwd + ctc_head + ctc_fwd_bwd + head_bwd + encoder_bwd + grad all-reduce + "
+                           "optimizer(%s)" % args.optimizer) if args.step == "train" else
+                          "fwd: encoder_fwd + ctc_head + ctc_fwd_bwd + head_bwd (no encoder backward)",
                   "global_batch": w["B"] * world, "seq_len": w["T"], "parallelism": "dp%d" % world}
 
     if args.impl == "reference":
         if rank != 0:
             return
         steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
-        r = cpu_reference_arm(w, steps, warmup)
+        r = cpu_reference_arm(w, steps, warmup, train=args.step == "train")
         line = {"impl": "reference", "metric": "speech_frames_per_sec", "value": r["value"], "unit": "frames/s",
                 "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -225,7 +240,8 @@ def main():
     torch.manual_seed(0)
     a = enc_args(w)
     a["frontend_conv"] = ConvEncoder(**conv_args(w))
-    enc = ConformerEncoder(**a).to(dev).eval()
+    enc = ConformerEncoder(**a).to(dev)
+    enc = enc.train() if args.step == "train" else enc.eval()
     enc.set_precision(args.precision)
     ctc = CTC(eos=2, blank=0, enc_n_units=w["d_model"], vocab=w["vocab"], lsm_prob=0.1, fc_list="512").to(dev)
     ctc.train()
@@ -241,7 +257,13 @@ def main():
     loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
     frames_per_step = sum(xlens)
 
-    def step(x_dev):
+    all_params = [p for p in enc.parameters()] + head_params
+    n_params = sum(p.numel() for p in all_params)
+    opt = None
+    if args.step == "train" and args.optimizer == "adam":
+        opt = torch.optim.Adam(all_params, lr=1e-5, fused=True, capturable=True)
+
+    def step_fwd(x_dev):
         out = enc(x_dev, xlens_t.clone(), task='ys')
         eouts = out['ys']['xs'].detach().requires_grad_(True)
         for p in head_params:
@@ -252,6 +274,28 @@ def main():
             flat = torch.cat([p.grad.reshape(-1) for p in head_params] + [eouts.grad.reshape(-1)[:0]])
             dist.all_reduce(flat)          # the single gradient all-reduce of the step (sum; DDP semantics)
         return loss
+
+    def step_train(x_dev):
+        for p in all_params:
+            p.grad = None
+        out = enc(x_dev, xlens_t.clone(), task='ys')
+        loss, _ = ctc(out['ys']['xs'], out['ys']['xlens'], ys)
+        loss.backward()
+        if world > 1:
+            # ONE all-reduce of the flat gradient buffer (sum of per-rank mean losses = the reference's DDP semantics,
+            # train.py:423-424), then scatter the views back for the optimizer
+            flat = torch.cat([p.grad.reshape(-1) for p in all_params])
+            dist.all_reduce(flat)
+            off = 0
+            for p in all_params:
+                n = p.numel()
+                p.grad = flat[off:off + n].view_as(p)
+                off += n
+        if opt is not None:
+            opt.step()
+        return loss.detach()
+
+    step = step_train if args.step == "train" else step_fwd
 
     def barrier():
         if world > 1:
@@ -272,74 +316,77 @@ def main():
         torch.cuda.synchronize()
         return sum(s.elapsed_time(e) for s, e in evs) / steps
 
-    # ---- warm-up ----
-    for _ in range(max(3, args.warmup)):
-        step(xs_dev)
-    barrier()
-    l_before = ops.LAUNCHES
-    step(xs_dev)
-    launches_per_step = ops.LAUNCHES - l_before
-
-    # ---- capture the step into a CUDA graph (launch-bound inner loop: ~300 kernels per step) ----
-    graph, loss_static, graph_error = None, None, None
-    xs_static = xs_dev.clone()
-    if not args.no_graph:
-        try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(2):
-                    step(xs_static)
-            torch.cuda.current_stream().wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                loss_static = step(xs_static)
-            graph.replay()
-            torch.cuda.synchronize()
-        except Exception as ex:                      # keep the eager path, say so in the JSON line
-            graph = None
-            graph_error = repr(ex)[:300]
-            print('[bench] CUDA graph capture failed, timing eager launches: ' + graph_error, file=sys.stderr)
-            torch.cuda.synchronize()
-    eager_step = step
-
-    def run_step(x_dev):
-        if graph is None:
-            return eager_step(x_dev)
-        if x_dev is not xs_static:
-            xs_static.copy_(x_dev, non_blocking=True)
-        graph.replay()
-        return loss_static
-
-    # ---- device-resident timing (value) ----
     sampler = ClockSampler(local_rank)
+
+    def measure(step_fn, with_e2e=True):
+        """Warm up, capture the step into a CUDA graph (launch-bound: hundreds of kernels per step), time K replays with
+        device-resident input (value) and K end-to-end steps with pinned-host input + loss read-back (e2e)."""
+        for _ in range(max(3, args.warmup)):
+            step_fn(xs_dev)
+        barrier()
+        l_before = ops.LAUNCHES
+        step_fn(xs_dev)
+        lps = ops.LAUNCHES - l_before
+        graph, loss_static, graph_error = None, None, None
+        xs_static = xs_dev.clone()
+        if not args.no_graph:
+            try:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(2):
+                        step_fn(xs_static)
+                torch.cuda.current_stream().wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    loss_static = step_fn(xs_static)
+                graph.replay()
+                torch.cuda.synchronize()
+            except Exception as ex:                      # keep the eager path, say so in the JSON line
+                graph = None
+                graph_error = repr(ex)[:300]
+                print('[bench] CUDA graph capture failed, timing eager launches: ' + graph_error, file=sys.stderr)
+                torch.cuda.synchronize()
+
+        def run_step():
+            if graph is None:
+                return step_fn(xs_static)
+            graph.replay()
+            return loss_static
+
+        barrier()
+        ms_dev = timed(run_step, args.steps)
+        barrier()
+        ms_e2e = None
+        if with_e2e:
+            def step_e2e():
+                if graph is None:
+                    loss = step_fn(xs_host.to(dev, non_blocking=True))
+                else:
+                    xs_static.copy_(xs_host, non_blocking=True)      # H2D of this step's features (pinned -> device)
+                    graph.replay()
+                    loss = loss_static
+                loss_host.copy_(loss.detach(), non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+            for _ in range(2):
+                step_e2e()
+            barrier()
+            ms_e2e = timed(step_e2e, args.steps)
+            barrier()
+        return dict(ms_dev=ms_dev, ms_e2e=ms_e2e, launches_per_step=lps, graph=graph is not None, graph_error=graph_error)
+
     if rank == 0:
         sampler.start()
-    l0 = ops.LAUNCHES
-    barrier()
-    ms_dev = timed(lambda: run_step(xs_static), args.steps)
-    barrier()
-    launches = ops.LAUNCHES - l0
-    if graph is not None:
-        launches = launches_per_step * args.steps          # replays do not pass through the Python wrappers
-
-    # ---- end-to-end timing through the public API with host buffers (e2e) ----
-    def step_e2e():
-        if graph is None:
-            loss = eager_step(xs_host.to(dev, non_blocking=True))
-        else:
-            xs_static.copy_(xs_host, non_blocking=True)      # H2D of this step's features (pinned -> device)
-            graph.replay()
-            loss = loss_static
-        loss_host.copy_(loss.detach(), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    ms_e2e = timed(step_e2e, args.steps)
-    barrier()
+    main = measure(step)
     clocks = sampler.stop() if rank == 0 else None
+    ms_dev, ms_e2e = main["ms_dev"], main["ms_e2e"]
+    launches = main["launches_per_step"] * args.steps
+    graph_ok, graph_error = main["graph"], main["graph_error"]
+    fwd = None
+    if args.step == "train":                                  # the forward + loss figure of the same model (eval path)
+        enc.eval()
+        fwd = measure(step_fwd, with_e2e=False)
+        enc.train()
 
     # ---- per-kernel-class timing for the roofline (eager, CUDA events around every library call) ----
     # The host must run AHEAD of the device here, otherwise each event pair also brackets the idle gap while the
@@ -352,10 +399,10 @@ def main():
         step(xs_dev)
     prof = ops.profile_stop()
 
-    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_dev, ms_e2e, fwd["ms_dev"] if fwd else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    ms_dev, ms_e2e, ms_fwd = float(t[0]), float(t[1]), float(t[2])
 
     if rank == 0:
         peaks = {}
@@ -369,7 +416,10 @@ def main():
         total_ms = sum(v["ms"] for v in prof.values()) or 1.0
         dom = max(prof.items(), key=lambda kv: kv[1]["ms"])
         gk = "gemm_%s" % args.precision
-        g = prof.get(gk, {"ms": 0.0, "flops": 0.0, "calls": 1})
+        g = dict(prof.get(gk, {"ms": 0.0, "flops": 0.0, "calls": 0}))
+        gw = prof.get("gemm_wgrad_%s" % args.precision)       # the wgrad GEMMs are the same tcgen05 pipe: one roofline
+        if gw:
+            g = {k: g[k] + gw[k] for k in ("ms", "flops", "calls")}
         gemm_tflops = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
         traffic = {}
         try:
@@ -397,15 +447,19 @@ def main():
                 "config": dict(cfg_common, l2="256 MiB memset between timed iterations (outside the event pairs); "
                                              "per-step working set >> 126 MB L2",
                                encoder_fwd_tflop_per_step=fl_utt * B / 1e12, enc_out_frames=Tp,
-                               cuda_graph=graph is not None, cuda_graph_error=graph_error),
+                               cuda_graph=graph_ok, cuda_graph_error=graph_error, n_params=n_params),
                 "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": int(xs_host.numel() * 4), "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches),
                 "roofline": roofline, "roofline_ctc": roofline_ctc, "ctc_loss_ms_per_batch": ctc_ms,
                 "kernel_time_ms_per_step": {k: round(v["ms"] / nprof, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}}
+        if fwd is not None:
+            line["fwd"] = {"value": frames_per_step * world / (ms_fwd * 1e-3), "unit": "frames/s", "ms_per_step": ms_fwd,
+                           "step": "encoder_fwd + ctc_head + ctc_fwd_bwd + head_bwd (inference kernels, eval mode)",
+                           "cuda_graph": fwd["graph"]}
         if not args.no_cpu_baseline and world == 1:
-            r = cpu_reference_arm(w, 1, 1)
+            r = cpu_reference_arm(w, 1, 1, train=args.step == "train")
             line["cpu_baseline"] = {"value": r["value"], "unit": "frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
         print(json.dumps(line))
     if world > 1:

@@ -242,8 +242,9 @@ nsp_status nsp_linear_fwd_save(int prec, const void* x, const void* x_lo, int64_
                                void* pre, int64_t ldpre, void* stream);
 
 /* Weight gradient of out = x w^T (nn.Linear / 1x1 Conv1d):  dw[N,K] (+)= alpha * dy[M,N]^T x[M,K]  on tcgen05
- * with MN-major operands (no transposed copies) and split-K reduction by red.global.add.  prec as in
- * nsp_linear_fwd (NSP_PREC_FP32: dy/dy_lo and x/x_lo are tf32 hi/lo splits).  accumulate=0 zeroes dw first.
+ * with MN-major operands (no transposed copies) and split-K reduction by red.global.add.  NSP_PREC_BF16 only
+ * (returns NSP_ERR_UNSUPPORTED otherwise: tf32 MN-major operands need another swizzle atom; parity-mode weight
+ * gradients go through nsp_linear_fwd on transposed operands).  accumulate=0 zeroes dw first.
  * (The input gradient dx = dy w is nsp_linear_fwd with the transposed weight.) */
 nsp_status nsp_linear_wgrad(int prec, const void* dy, const void* dy_lo, int64_t lddy,
                             const void* x, const void* x_lo, int64_t ldx, int M, int N, int K,
@@ -275,7 +276,23 @@ nsp_status nsp_maxpool2d_relu_bwd(int is_bf16, int dy_bf16, const void* a, const
 nsp_status nsp_conv3x3_wgrad(int a_bf16, int dz_bf16, const void* a, int in_chmajor, const void* dz, float* dw,
                              float* dbias, int B, int T, int F, int CI, int CO, void* stream);
 
+/* Same weight gradient for the 32 -> 32 channel layers as an implicit GEMM on tcgen05 (bf16 a, dz [B,T,F,32];
+ * dw fp32 [32,32,3,3] accumulated; the bias gradient is nsp_colsum_acc over dz viewed as [B*T*F, 32]). */
+nsp_status nsp_conv3x3_c32_wgrad_tc(const void* a, const void* dz, float* dw, int B, int T, int F, void* stream);
+
+/* nsp_relpos_attention_fwd that also returns the softmax statistics the tensor-core backward needs:
+ * stats fp32 [B,H,Tq,2] = (row maximum in the log2 domain, 1 / row sum).  *stats_written_host (HOST int) is set to 1
+ * iff the tcgen05 kernel ran and filled them (bf16, d_k = 64, clamped or absent relative term, no XL biases). */
+nsp_status nsp_relpos_attention_fwd_stats(int is_bf16, const void* q, int64_t ldq, const void* k, int64_t ldk,
+                                          const void* v, int64_t ldv, const void* r, int64_t ldr, int rlen,
+                                          const float* u_bias, const float* v_bias, const int32_t* klens,
+                                          void* out, int64_t ldo, int B, int H, int Tq, int Tk, int dk,
+                                          int clamp_len, int causal, int lookahead, int chunk_c, int chunk_l,
+                                          float* stats, int* stats_written_host, void* stream);
+
 /* Backward of nsp_relpos_attention_fwd (same argument meaning).  out is the forward result, dout its gradient;
+ * stats (optional) = the statistics of nsp_relpos_attention_fwd_stats: when given and the shape is inside the
+ * tensor-core envelope the five GEMMs of the backward run on tcgen05, otherwise exact fp32 CUDA-core kernels.
  * dq/dk/dv receive the gradients in the I/O dtype (may point into one fused [B*T, 3*H*dk] buffer);
  * dr fp32 [rlen, H*dk] (pitch lddr), du / dvb fp32 [H*dk] are ACCUMULATED (may be NULL). */
 size_t nsp_relpos_attention_bwd_workspace_bytes(int B, int H, int Tq, int rlen, int clamp_len, int has_r);
@@ -284,7 +301,7 @@ nsp_status nsp_relpos_attention_bwd(int is_bf16, const void* q, int64_t ldq, con
                                     const float* u_bias, const float* v_bias, const int32_t* klens,
                                     const void* out, int64_t ldo, const void* dout, int64_t lddo,
                                     void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
-                                    float* dr, int64_t lddr, float* du, float* dvb,
+                                    float* dr, int64_t lddr, float* du, float* dvb, const float* stats,
                                     int B, int H, int Tq, int Tk, int dk_dim, int clamp_len, int causal, int lookahead,
                                     int chunk_c, int chunk_l, void* workspace, size_t workspace_bytes, void* stream);
 

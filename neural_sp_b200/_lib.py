@@ -160,12 +160,16 @@ _more = {
     "nsp_maxpool_time_bwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     "nsp_relu_mask": (c_int, [c_int, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "nsp_maxpool2d_relu_bwd": (c_int, [c_int, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "nsp_conv3x3_c32_wgrad_tc": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp]),
     "nsp_conv3x3_wgrad": (c_int, [c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "nsp_relpos_attention_bwd_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "nsp_relpos_attention_bwd": (c_int, [c_int, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_vp, c_vp,
                                          c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64,
-                                         c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                         c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                          c_vp, c_sz, c_vp]),
+    "nsp_relpos_attention_fwd_stats": (c_int, [c_int, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_vp,
+                                               c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                               c_int, c_int, c_vp, ctypes.POINTER(c_int), c_vp]),
     "nsp_conformer_conv_bwd": (c_int, [c_int, c_vp, c_i64, c_vp, c_vp, c_int, c_vp, c_vp, c_f32, c_vp, c_i64, c_vp, c_i64,
                                        c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
 }

@@ -63,8 +63,14 @@ def _ln_fwd(norm, x, prec):
     return ops.layernorm(x, norm.weight, norm.bias, norm.eps)
 
 
-def _ln_bwd(norm, dn, x, dres, G):
-    return ops.layernorm_bwd(dn, x, norm.weight, norm.eps, dres=dres, dgamma=G.buf(norm.weight), dbeta=G.buf(norm.bias))
+def _ln_bwd(norm, dn, x, dres, G, prec):
+    """-> (dx fp32, dx in the GEMM operand dtype): in bf16 mode the kernel also emits the bf16 copy the next branch's
+    dgrad / wgrad GEMMs read, so no separate cast pass is needed."""
+    if prec == "bf16":
+        return ops.layernorm_bwd(dn, x, norm.weight, norm.eps, dres=dres, dgamma=G.buf(norm.weight), dbeta=G.buf(norm.bias),
+                                 want_bf16=True)
+    dx = ops.layernorm_bwd(dn, x, norm.weight, norm.eps, dres=dres, dgamma=G.buf(norm.weight), dbeta=G.buf(norm.bias))
+    return dx, dx
 
 
 def ffn_fwd(ffn, norm, x, scale, prec):
@@ -78,9 +84,8 @@ def ffn_fwd(ffn, norm, x, scale, prec):
     return y, (x, n, z, h)
 
 
-def ffn_bwd(ffn, norm, saved, dy, scale, prec, G):
+def ffn_bwd(ffn, norm, saved, dy, dyo, scale, prec, G):
     x, n, z, h = saved
-    dyo = _gop(dy, prec)
     ops.linear_wgrad(dyo, h, prec, G.buf(ffn.w_2.weight), alpha=scale)
     ops.colsum_acc(dy, G.buf(ffn.w_2.bias), alpha=scale)
     dh = ops.linear(dyo, _wT(ffn, "w_2", prec, (ffn.w_2.weight,)), None, prec=prec, alpha=scale, out_dtype=act_dtype(prec))
@@ -88,7 +93,7 @@ def ffn_bwd(ffn, norm, saved, dy, scale, prec, G):
     ops.linear_wgrad(dz, n, prec, G.buf(ffn.w_1.weight))
     ops.colsum_acc(dz, G.buf(ffn.w_1.bias))
     dn = ops.linear(dz, _wT(ffn, "w_1", prec, (ffn.w_1.weight,)), None, prec=prec, out_dtype=torch.float32)
-    return _ln_bwd(norm, dn, x, dy, G)
+    return _ln_bwd(norm, dn, x, dy, G, prec)
 
 
 def _qkv_weight(attn, prec, transposed=False):
@@ -114,18 +119,18 @@ def attn_fwd(attn, norm, x, pos, klens, u_bias, v_bias, mask_kw, prec, rel):
         r = ops.linear(pos[:nrows], prepared(attn, "pos", prec, (wp_lin.weight,)), wp_lin.bias, prec=prec,
                        out_dtype=act_dtype(prec))
     clamp = attn.clamp_len if rel else -1
-    cv = ops.relpos_attention(qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:], klens, attn.n_heads, r=r,
-                              u_bias=u_bias if rel else None, v_bias=v_bias if rel else None, clamp_len=clamp, **mask_kw)
+    cv, stats = ops.relpos_attention(qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:], klens, attn.n_heads, r=r,
+                                     u_bias=u_bias if rel else None, v_bias=v_bias if rel else None, clamp_len=clamp,
+                                     want_stats=True, **mask_kw)
     y = ops.linear(cv, prepared(attn, "w_out", prec, (attn.w_out.weight,)), attn.w_out.bias, prec=prec, residual=x,
                    out_dtype=torch.float32)
-    return y, (x, n, qkv, r, cv, nrows)
+    return y, (x, n, qkv, r, cv, nrows, stats)
 
 
-def attn_bwd(attn, norm, saved, dy, pos, klens, u_bias, v_bias, mask_kw, prec, rel, G, enc_bias_params):
-    x, n, qkv, r, cv, nrows = saved
+def attn_bwd(attn, norm, saved, dy, dyo, pos, klens, u_bias, v_bias, mask_kw, prec, rel, G, enc_bias_params):
+    x, n, qkv, r, cv, nrows, stats = saved
     D = attn.n_heads * attn.d_k
     d_in = x.shape[-1]
-    dyo = _gop(dy, prec)
     ops.linear_wgrad(dyo, cv, prec, G.buf(attn.w_out.weight))
     if attn.w_out.bias is not None:
         ops.colsum_acc(dy, G.buf(attn.w_out.bias))
@@ -137,7 +142,7 @@ def attn_bwd(attn, norm, saved, dy, pos, klens, u_bias, v_bias, mask_kw, prec, r
     clamp = attn.clamp_len if rel else -1
     dqkv = ops.relpos_attention_bwd(qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:], klens, attn.n_heads, cv, dcv, r=r,
                                     u_bias=u_bias if rel else None, v_bias=v_bias if rel else None, clamp_len=clamp,
-                                    dr=dr, du=du, dvb=dvb, **mask_kw)
+                                    dr=dr, du=du, dvb=dvb, stats=stats, **mask_kw)
     gw = torch.zeros(3 * D, d_in, dtype=torch.float32, device=x.device)
     ops.linear_wgrad(dqkv, n, prec, gw)
     for i, lin in enumerate((attn.w_query, attn.w_key, attn.w_value)):
@@ -153,7 +158,7 @@ def attn_bwd(attn, norm, saved, dy, pos, klens, u_bias, v_bias, mask_kw, prec, r
         if wp_lin.bias is not None:
             ops.colsum_acc(dr, G.buf(wp_lin.bias))
     dn = ops.linear(dqkv, _qkv_weight(attn, prec, transposed=True), None, prec=prec, out_dtype=torch.float32)
-    return _ln_bwd(norm, dn, x, dy, G)
+    return _ln_bwd(norm, dn, x, dy, G, prec)
 
 
 def convmod_fwd(conv, norm, x, prec):
@@ -171,10 +176,9 @@ def convmod_fwd(conv, norm, x, prec):
     return y, (x, n, pre, g, c, taps)
 
 
-def convmod_bwd(conv, norm, saved, dy, prec, G):
+def convmod_bwd(conv, norm, saved, dy, dyo, prec, G):
     x, n, pre, g, c, taps = saved
     d = x.shape[-1]
-    dyo = _gop(dy, prec)
     ops.linear_wgrad(dyo, c, prec, _as2d(G.buf(conv.pointwise_conv2.weight)))
     ops.colsum_acc(dy, G.buf(conv.pointwise_conv2.bias))
     dc = ops.linear(dyo, _wT(conv, "pw2", prec, (conv.pointwise_conv2.weight,)), None, prec=prec, out_dtype=act_dtype(prec))
@@ -187,7 +191,7 @@ def convmod_bwd(conv, norm, saved, dy, prec, G):
     ops.linear_wgrad(dpre, n, prec, _as2d(G.buf(conv.pointwise_conv1.weight)))
     ops.colsum_acc(dpre, G.buf(conv.pointwise_conv1.bias))
     dn = ops.linear(dpre, _wT(conv, "pw1", prec, (conv.pointwise_conv1.weight,)), None, prec=prec, out_dtype=torch.float32)
-    return _ln_bwd(norm, dn, x, dy, G)
+    return _ln_bwd(norm, dn, x, dy, G, prec)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -229,17 +233,16 @@ class _BlockFn(torch.autograd.Function):
         G = _Grads()
         dy = dy.contiguous().float()
         if hasattr(block, "feed_forward_macaron"):
-            dx = ops.layernorm_bwd(dy, S["x5"], block.norm5.weight, block.norm5.eps, dres=None,
-                                   dgamma=G.buf(block.norm5.weight), dbeta=G.buf(block.norm5.bias))
-            dx = ffn_bwd(block.feed_forward, block.norm4, S["ff"], dx, block.fc_factor, prec, G)
-            dx = convmod_bwd(block.conv, block.norm3, S["conv"], dx, prec, G)
-            dx = attn_bwd(block.self_attn, block.norm2, S["att"], dx, ctx.pos, ctx.klens, u_bias, v_bias, ctx.mask_kw, prec,
-                          True, G, ctx.rel_bias)
-            dx = ffn_bwd(block.feed_forward_macaron, block.norm1, S["ffm"], dx, block.fc_factor, prec, G)
+            dx, dxo = _ln_bwd(block.norm5, dy, S["x5"], None, G, prec)
+            dx, dxo = ffn_bwd(block.feed_forward, block.norm4, S["ff"], dx, dxo, block.fc_factor, prec, G)
+            dx, dxo = convmod_bwd(block.conv, block.norm3, S["conv"], dx, dxo, prec, G)
+            dx, dxo = attn_bwd(block.self_attn, block.norm2, S["att"], dx, dxo, ctx.pos, ctx.klens, u_bias, v_bias,
+                               ctx.mask_kw, prec, True, G, ctx.rel_bias)
+            dx, dxo = ffn_bwd(block.feed_forward_macaron, block.norm1, S["ffm"], dx, dxo, block.fc_factor, prec, G)
         else:
-            dx = ffn_bwd(block.feed_forward, block.norm2, S["ff"], dy, 1.0, prec, G)
-            dx = attn_bwd(block.self_attn, block.norm1, S["att"], dx, ctx.pos, ctx.klens, u_bias, v_bias, ctx.mask_kw, prec,
-                          block.rel_attn, G, ctx.rel_bias)
+            dx, dxo = ffn_bwd(block.feed_forward, block.norm2, S["ff"], dy, _gop(dy, prec), 1.0, prec, G)
+            dx, dxo = attn_bwd(block.self_attn, block.norm1, S["att"], dx, dxo, ctx.pos, ctx.klens, u_bias, v_bias,
+                               ctx.mask_kw, prec, block.rel_attn, G, ctx.rel_bias)
         if ctx.in_scale != 1.0:
             ops.scale_(dx, ctx.in_scale)
         ctx.saved = None

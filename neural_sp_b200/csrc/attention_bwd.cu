@@ -499,6 +499,17 @@ nsp_status launch_bwd(const AttnBwdParams& p, cudaStream_t st) {
 }  // namespace
 }  // namespace nsp
 
+namespace nsp {
+size_t attention_bwd_tc_workspace_bytes(int B, int H, int T);
+nsp_status attention_bwd_tc_dispatch(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                     const void* r, int64_t ldr, int rlen, const int32_t* klens, const float* stats,
+                                     const void* out, int64_t ldo, const void* dout, int64_t lddo,
+                                     void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                                     float* dr, int64_t lddr, int B, int H, int T, int dkdim, int clamp_len, int causal,
+                                     int lookahead, int chunk_c, int chunk_l, void* workspace, size_t workspace_bytes,
+                                     cudaStream_t st);
+}
+
 using namespace nsp;
 
 static int attn_bwd_ndp(int rlen, int clamp_len, int has_r) {
@@ -510,7 +521,9 @@ static int attn_bwd_ndp(int rlen, int clamp_len, int has_r) {
 
 extern "C" size_t nsp_relpos_attention_bwd_workspace_bytes(int B, int H, int Tq, int rlen, int clamp_len, int has_r) {
     const size_t rows = (size_t)B * H * Tq;
-    return sizeof(float) * rows * (3 + (size_t)attn_bwd_ndp(rlen, clamp_len, has_r));
+    const size_t simt = sizeof(float) * rows * (3 + (size_t)attn_bwd_ndp(rlen, clamp_len, has_r));
+    const size_t tcb = attention_bwd_tc_workspace_bytes(B, H, Tq);
+    return simt > tcb ? simt : tcb;
 }
 
 extern "C" nsp_status nsp_relpos_attention_bwd(int is_bf16, const void* q, int64_t ldq, const void* k, int64_t ldk,
@@ -518,7 +531,7 @@ extern "C" nsp_status nsp_relpos_attention_bwd(int is_bf16, const void* q, int64
                                                const float* u_bias, const float* v_bias, const int32_t* klens,
                                                const void* out, int64_t ldo, const void* dout, int64_t lddo,
                                                void* dq, int64_t lddq, void* dk_, int64_t lddk, void* dv, int64_t lddv,
-                                               float* dr, int64_t lddr, float* du, float* dvb,
+                                               float* dr, int64_t lddr, float* du, float* dvb, const float* stats,
                                                int B, int H, int Tq, int Tk, int dk, int clamp_len, int causal, int lookahead,
                                                int chunk_c, int chunk_l, void* workspace, size_t workspace_bytes, void* stream) {
     NSP_CHECK_ARG(q && k && v && klens && out && dout && dq && dk_ && dv && workspace, "attention_bwd: null pointer");
@@ -527,6 +540,13 @@ extern "C" nsp_status nsp_relpos_attention_bwd(int is_bf16, const void* q, int64
     if (dk > 128) { set_error("attention_bwd: d_k=%d unsupported (max 128)", dk); return NSP_ERR_UNSUPPORTED; }
     NSP_CHECK_ARG(workspace_bytes >= nsp_relpos_attention_bwd_workspace_bytes(B, H, Tq, rlen, clamp_len, r != nullptr),
                   "attention_bwd: workspace too small");
+    if (is_bf16 && stats && !u_bias && !v_bias && Tq == Tk) {
+        // tensor-core path (needs the forward kernel's softmax statistics); falls through when outside its envelope
+        nsp_status s = attention_bwd_tc_dispatch(q, ldq, k, ldk, v, ldv, r, ldr, rlen, klens, stats, out, ldo, dout, lddo,
+                                                 dq, lddq, dk_, lddk, dv, lddv, dr, lddr, B, H, Tq, dk, clamp_len, causal,
+                                                 lookahead, chunk_c, chunk_l, workspace, workspace_bytes, (cudaStream_t)stream);
+        if (s != NSP_ERR_UNSUPPORTED) return s;
+    }
     AttnBwdParams p;
     p.q = q; p.k = k; p.v = v; p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.r = r; p.ldr = ldr; p.rlen = rlen;
     p.u_bias = u_bias; p.v_bias = v_bias; p.klens = klens; p.o = out; p.ldo = ldo; p.dout = dout; p.lddo = lddo;

@@ -260,17 +260,18 @@ namespace nsp {
 nsp_status attention_tc_dispatch(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                                  const void* r, int64_t ldr, int rlen, const int32_t* klens, void* out, int64_t ldo,
                                  int B, int H, int Tq, int Tk, int dk, int clamp_len, int causal, int lookahead,
-                                 int chunk_c, int chunk_l, cudaStream_t st);
+                                 int chunk_c, int chunk_l, float* stats, cudaStream_t st);
 }
 
 using namespace nsp;
 
-extern "C" nsp_status nsp_relpos_attention_fwd(int is_bf16, const void* q, int64_t ldq, const void* k, int64_t ldk,
-                                               const void* v, int64_t ldv, const void* r, int64_t ldr, int rlen,
-                                               const float* u_bias, const float* v_bias, const int32_t* klens,
-                                               void* out, int64_t ldo, int B, int H, int Tq, int Tk, int dk,
-                                               int clamp_len, int causal, int lookahead, int chunk_c, int chunk_l,
-                                               void* stream) {
+static nsp_status attention_fwd_impl(int is_bf16, const void* q, int64_t ldq, const void* k, int64_t ldk,
+                                     const void* v, int64_t ldv, const void* r, int64_t ldr, int rlen,
+                                     const float* u_bias, const float* v_bias, const int32_t* klens,
+                                     void* out, int64_t ldo, int B, int H, int Tq, int Tk, int dk,
+                                     int clamp_len, int causal, int lookahead, int chunk_c, int chunk_l,
+                                     float* stats, int* stats_written, void* stream) {
+    if (stats_written) *stats_written = 0;
     NSP_CHECK_ARG(q && k && v && klens && out, "attention: null pointer");
     NSP_CHECK_ARG(B > 0 && H > 0 && Tq > 0 && Tk >= Tq && dk > 0, "attention: bad shape B=%d H=%d Tq=%d Tk=%d dk=%d", B, H, Tq, Tk, dk);
     NSP_CHECK_ARG(!r || rlen > 0, "attention: rlen must be positive when r is given");
@@ -285,8 +286,8 @@ extern "C" nsp_status nsp_relpos_attention_fwd(int is_bf16, const void* q, int64
     if (is_bf16 && !u_bias && !v_bias) {
         // tensor-core kernel when the shape is inside its envelope (d_k = 64, clamped or no relative term)
         nsp_status s = attention_tc_dispatch(q, ldq, k, ldk, v, ldv, r, ldr, rlen, klens, out, ldo, B, H, Tq, Tk, dk,
-                                             clamp_len, causal, lookahead, chunk_c, chunk_l, st);
-        if (s != NSP_ERR_UNSUPPORTED) return s;
+                                             clamp_len, causal, lookahead, chunk_c, chunk_l, stats, st);
+        if (s != NSP_ERR_UNSUPPORTED) { if (s == NSP_OK && stats && stats_written) *stats_written = 1; return s; }
     }
     if (is_bf16) {
         if (dk <= 16) return launch_attn<__nv_bfloat16, 16>(p, st);
@@ -296,4 +297,24 @@ extern "C" nsp_status nsp_relpos_attention_fwd(int is_bf16, const void* q, int64
     if (dk <= 16) return launch_attn<float, 16>(p, st);
     if (dk <= 64) return launch_attn<float, 64>(p, st);
     return launch_attn<float, 128>(p, st);
+}
+
+extern "C" nsp_status nsp_relpos_attention_fwd(int is_bf16, const void* q, int64_t ldq, const void* k, int64_t ldk,
+                                               const void* v, int64_t ldv, const void* r, int64_t ldr, int rlen,
+                                               const float* u_bias, const float* v_bias, const int32_t* klens,
+                                               void* out, int64_t ldo, int B, int H, int Tq, int Tk, int dk,
+                                               int clamp_len, int causal, int lookahead, int chunk_c, int chunk_l,
+                                               void* stream) {
+    return attention_fwd_impl(is_bf16, q, ldq, k, ldk, v, ldv, r, ldr, rlen, u_bias, v_bias, klens, out, ldo, B, H, Tq, Tk, dk,
+                              clamp_len, causal, lookahead, chunk_c, chunk_l, nullptr, nullptr, stream);
+}
+
+extern "C" nsp_status nsp_relpos_attention_fwd_stats(int is_bf16, const void* q, int64_t ldq, const void* k, int64_t ldk,
+                                                     const void* v, int64_t ldv, const void* r, int64_t ldr, int rlen,
+                                                     const float* u_bias, const float* v_bias, const int32_t* klens,
+                                                     void* out, int64_t ldo, int B, int H, int Tq, int Tk, int dk,
+                                                     int clamp_len, int causal, int lookahead, int chunk_c, int chunk_l,
+                                                     float* stats, int* stats_written_host, void* stream) {
+    return attention_fwd_impl(is_bf16, q, ldq, k, ldk, v, ldv, r, ldr, rlen, u_bias, v_bias, klens, out, ldo, B, H, Tq, Tk, dk,
+                              clamp_len, causal, lookahead, chunk_c, chunk_l, stats, stats_written_host, stream);
 }

@@ -33,6 +33,7 @@ struct AttnTcArgs {
     int has_rel, clamp_len;
     int causal, lookahead, chunk_c, chunk_l;
     float scale_log2;                                 // log2(e) / sqrt(dk)
+    float* stats;                                     // optional [B,H,Tq,2]: (row max in the log2 domain, 1 / row sum) for the backward
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -311,6 +312,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
         sm_barrier();
         if (i < a.Tq) {
             const float inv = 1.f / (l_run + sL[(half ^ 1) * 128 + row]);
+            if (a.stats && half == 0) {
+                float* st = a.stats + (((int64_t)b * a.H + h) * a.Tq + i) * 2;
+                st[0] = m_run; st[1] = inv;
+            }
             __nv_bfloat16* o = a.out + ((int64_t)b * a.Tq + i) * a.ldo + (int64_t)h * DK + half * DH;
 #pragma unroll
             for (int c = 0; c < DH; c += 8) {
@@ -358,7 +363,7 @@ bool get_tma_encode(void** fn);
 nsp_status attention_tc_dispatch(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                                  const void* r, int64_t ldr, int rlen, const int32_t* klens, void* out, int64_t ldo,
                                  int B, int H, int Tq, int Tk, int dk, int clamp_len, int causal, int lookahead,
-                                 int chunk_c, int chunk_l, cudaStream_t st) {
+                                 int chunk_c, int chunk_l, float* stats, cudaStream_t st) {
     if (dk != 64) return NSP_ERR_UNSUPPORTED;
     if (r && !(clamp_len >= 1 && clamp_len <= 15)) return NSP_ERR_UNSUPPORTED;
     if (ldo % 8 != 0 || ((uintptr_t)out % 16) != 0) return NSP_ERR_UNSUPPORTED;
@@ -387,6 +392,7 @@ nsp_status attention_tc_dispatch(const void* q, int64_t ldq, const void* k, int6
     a.has_rel = r ? 1 : 0; a.clamp_len = r ? (clamp_len < rlen - 1 ? clamp_len : rlen - 1) : 0;
     a.causal = causal; a.lookahead = lookahead; a.chunk_c = chunk_c; a.chunk_l = chunk_l;
     a.scale_log2 = 1.4426950408889634f / sqrtf((float)dk);
+    a.stats = stats;
     const size_t smem = 1024 + 5 * TILE_BYTES + 2048 + (128 * 17 + 512) * sizeof(float) + 128;
     static bool attr = false;
     if (!attr) { NSP_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }

@@ -182,7 +182,45 @@ __global__ void __launch_bounds__(256) glu_bwd_kernel(const T* __restrict__ dg, 
     }
 }
 
-// y[n] += alpha * sum_m x[m, n]; grid = (column blocks of 32, row slices)
+// y[n] += alpha * sum_m x[m, n]; grid = (column blocks, row slices).  Vector variant: a thread owns VEC consecutive
+// columns (16-byte loads), a warp covers 32*VEC columns of one row, the 8 warps stride over the rows of the slice.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) colsum_acc_vec_kernel(const T* __restrict__ x, int64_t ldx, float* __restrict__ y,
+                                                             int M, int N, float alpha) {
+    __shared__ float part[8][32 * VEC + 1];
+    const int lane = threadIdx.x & 31, rs = threadIdx.x >> 5;
+    const int c0 = (blockIdx.x * 32 + lane) * VEC;
+    float acc[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+    if (c0 < N) {                                     // N % VEC == 0 (host)
+        for (int r = blockIdx.y * 8 + rs; r < M; r += gridDim.y * 8) {
+            const T* p = x + (int64_t)r * ldx + c0;
+            if constexpr (sizeof(T) == 2) {
+                const uint4 raw = *reinterpret_cast<const uint4*>(p);
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h2[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
+            } else {
+                const float4 f = *reinterpret_cast<const float4*>(p);
+                acc[0] += f.x; acc[1] += f.y; acc[2] += f.z; acc[3] += f.w;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) part[rs][lane * VEC + k] = acc[k];
+    __syncthreads();
+    for (int c = threadIdx.x; c < 32 * VEC; c += 256) {
+        const int col = blockIdx.x * 32 * VEC + c;
+        if (col < N) {
+            float t = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t += part[i][c];
+            atomicAdd(y + col, alpha * t);
+        }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_acc_kernel(const T* __restrict__ x, int64_t ldx, float* __restrict__ y,
                                                          int M, int N, float alpha) {
@@ -324,6 +362,18 @@ extern "C" nsp_status nsp_glu_bwd(int is_bf16, const void* dg, const void* pre, 
 extern "C" nsp_status nsp_colsum_acc(int is_bf16, const void* x, int64_t ldx, int M, int N, float alpha, float* y, void* stream) {
     NSP_CHECK_ARG(x && y && M > 0 && N > 0, "colsum_acc: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
+    const int vec = is_bf16 ? 8 : 4;
+    if (N % vec == 0 && ldx % vec == 0 && ((uintptr_t)x % 16 == 0)) {
+        const int cblocks = ceil_div(N, 32 * vec);
+        int slices = ceil_div(M, 64);
+        const int cap = ceil_div(num_sms() * 4, cblocks);
+        if (slices > cap) slices = cap < 1 ? 1 : cap;
+        dim3 vgrid((unsigned)cblocks, (unsigned)slices);
+        if (is_bf16) colsum_acc_vec_kernel<__nv_bfloat16, 8><<<vgrid, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, y, M, N, alpha);
+        else colsum_acc_vec_kernel<float, 4><<<vgrid, 256, 0, st>>>((const float*)x, ldx, y, M, N, alpha);
+        NSP_LAUNCH_OK();
+        return NSP_OK;
+    }
     int slices = ceil_div(M, 256);
     const int cap = ceil_div(num_sms() * 8, ceil_div(N, 32));
     if (slices > cap) slices = cap < 1 ? 1 : cap;

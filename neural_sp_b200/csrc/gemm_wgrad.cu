@@ -234,5 +234,8 @@ extern "C" nsp_status nsp_linear_wgrad(int prec, const void* dy, const void* dy_
         if (K > 128) return launch_wgrad<__nv_bfloat16, 256, 4>(maps, g, st);
         return launch_wgrad<__nv_bfloat16, 128, 6>(maps, g, st);
     }
-    return launch_wgrad<float, 128, 3>(maps, g, st);
+    // tf32 operands: the MN-major path needs the 128B_BASE32B swizzle atom (not wired up); the host side computes
+    // parity-mode weight gradients on the K-major GEMM instead.
+    set_error("linear_wgrad: only NSP_PREC_BF16 runs on the MN-major kernel; use nsp_linear_fwd on transposed operands for tf32/fp32");
+    return NSP_ERR_UNSUPPORTED;
 }

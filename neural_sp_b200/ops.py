@@ -241,7 +241,7 @@ def layernorm(x, weight, bias, eps, out_fp32=True, out_bf16=False, in_scale=1.0)
 
 
 def relpos_attention(q, k, v, klens, n_heads, r=None, u_bias=None, v_bias=None, clamp_len=-1, causal=False,
-                     lookahead=0, chunk_c=0, chunk_l=0):
+                     lookahead=0, chunk_c=0, chunk_l=0, want_stats=False):
     """Flash-style (rel-pos) self-attention (nsp_relpos_attention_fwd).
 
     q `[B, Tq, H*dk]`, k/v `[B, Tk, H*dk]` (may be strided views of a fused QKV buffer; last dim contiguous),
@@ -258,11 +258,21 @@ def relpos_attention(q, k, v, klens, n_heads, r=None, u_bias=None, v_bias=None, 
         assert r.dtype == q.dtype and r.stride(-1) == 1
         r = r.reshape(-1, D) if r.dim() == 3 else r
     out = torch.empty(B, Tq, D, dtype=q.dtype, device=q.device)
+    if want_stats:          # training: keep the softmax statistics for the tensor-core backward (None if the CUDA-core kernel ran)
+        import ctypes
+        stats = torch.empty(B, n_heads, Tq, 2, dtype=torch.float32, device=q.device)
+        written = ctypes.c_int(0)
+        _run("nsp_relpos_attention_fwd_stats", lib.nsp_relpos_attention_fwd_stats, int(is_bf16), ptr(q), q.stride(1), ptr(k), k.stride(1),
+             ptr(v), v.stride(1), ptr(r), r.stride(0) if r is not None else 0, r.shape[0] if r is not None else 0,
+             ptr(u_bias), ptr(v_bias), ptr(klens), ptr(out), D, B, n_heads, Tq, Tk, dk,
+             int(clamp_len), int(causal), int(lookahead), int(chunk_c), int(chunk_l), ptr(stats), ctypes.byref(written),
+             current_stream_ptr(), flops=4.0 * B * n_heads * Tq * Tk * dk, tag="nsp_relpos_attention_fwd")
+        return out, (stats if written.value else None)
     _run("nsp_relpos_attention_fwd", lib.nsp_relpos_attention_fwd, int(is_bf16), ptr(q), q.stride(1), ptr(k), k.stride(1), ptr(v), v.stride(1),
                                        ptr(r), r.stride(0) if r is not None else 0, r.shape[0] if r is not None else 0,
                                        ptr(u_bias), ptr(v_bias), ptr(klens), ptr(out), D, B, n_heads, Tq, Tk, dk,
                                        int(clamp_len), int(causal), int(lookahead), int(chunk_c), int(chunk_l),
-                                       current_stream_ptr())
+                                       current_stream_ptr(), flops=4.0 * B * n_heads * Tq * Tk * dk)
     return out
 
 
@@ -463,7 +473,7 @@ def lstm_seq(gates_x, w_hh, lens, n_dirs):
 # ---------------------------------------------------------------------------------------------
 # backward pass (training): hand-written gradients of the forward ops above
 # ---------------------------------------------------------------------------------------------
-KERNELS_PER_CALL["nsp_relpos_attention_bwd"] = 2
+KERNELS_PER_CALL["nsp_relpos_attention_bwd"] = 3
 KERNELS_PER_CALL["nsp_conformer_conv_bwd"] = 2
 
 
@@ -495,6 +505,13 @@ def linear_wgrad(dy, x, prec, dw, alpha=1.0, accumulate=True):
             dw.add_(tmp[:N, :K])
         else:
             dw.copy_(tmp[:N, :K])
+        return dw
+    if prec != "bf16":
+        # parity modes: tcgen05 has no 128B-swizzled MN-major layout for tf32 operands, so the fp32 / tf32 weight gradient
+        # runs on the K-major GEMM (3xTF32 in 'fp32' mode) over transposed copies (pure data movement; not the perf path)
+        a_t = dy2.float().t().contiguous()
+        b_t = prepare_weight(x2.float().t().contiguous(), prec)
+        linear(a_t, b_t, None, prec=prec, residual=dw if accumulate else None, alpha=alpha, out_dtype=torch.float32, out=dw)
         return dw
     dyh, dyl = _operand(dy2, prec)
     xh, xl = _operand(x2, prec)
@@ -593,6 +610,12 @@ def conv3x3_wgrad(a, dz, dw, dbias, B, T, F, in_chmajor=False):
     CO, CI = dw.shape[0], dw.shape[1]
     a, dz = a.contiguous(), dz.contiguous()
     assert a.numel() == B * T * F * CI and dz.numel() == B * T * F * CO and dw.is_contiguous()
+    if CI == 32 and CO == 32 and not in_chmajor and a.dtype == torch.bfloat16 and dz.dtype == torch.bfloat16:
+        _run("nsp_conv3x3_c32_wgrad_tc", lib.nsp_conv3x3_c32_wgrad_tc, ptr(a), ptr(dz), ptr(dw), B, T, F, current_stream_ptr(),
+             flops=2.0 * B * T * F * 9 * CI * CO, tag="conv3x3_wgrad_tc")
+        if dbias is not None:
+            colsum_acc(dz.view(-1, CO), dbias)
+        return dw
     _run("nsp_conv3x3_wgrad", lib.nsp_conv3x3_wgrad, int(a.dtype == torch.bfloat16), int(dz.dtype == torch.bfloat16), ptr(a),
          int(in_chmajor), ptr(dz), ptr(dw), ptr(dbias), B, T, F, CI, CO, current_stream_ptr(),
          flops=2.0 * B * T * F * 9 * CI * CO, tag="conv3x3_wgrad")
@@ -605,7 +628,7 @@ def conv3x3_dgrad_weight(weight):
 
 
 def relpos_attention_bwd(q, k, v, klens, n_heads, out, dout, r=None, u_bias=None, v_bias=None, clamp_len=-1, causal=False,
-                         lookahead=0, chunk_c=0, chunk_l=0, dr=None, du=None, dvb=None):
+                         lookahead=0, chunk_c=0, chunk_l=0, dr=None, du=None, dvb=None, stats=None):
     """Backward of relpos_attention (nsp_relpos_attention_bwd).  Returns dqkv `[B, T, 3*D]` (requires Tq == Tk) with
     dq | dk | dv in the I/O dtype; dr `[rlen, D]`, du, dvb fp32 are accumulated in place when given."""
     _require_cuda(q, k, v, klens, out, dout)
@@ -626,7 +649,7 @@ def relpos_attention_bwd(q, k, v, klens, n_heads, out, dout, r=None, u_bias=None
     _run("nsp_relpos_attention_bwd", lib.nsp_relpos_attention_bwd, int(q.dtype == torch.bfloat16), ptr(q), q.stride(1), ptr(k), k.stride(1),
          ptr(v), v.stride(1), ptr(r), r.stride(0) if r is not None else 0, rlen, ptr(u_bias), ptr(v_bias), ptr(klens),
          ptr(out), out.stride(1), ptr(dout), dout.stride(1), ptr(dq_), 3 * D, ptr(dk_), 3 * D, ptr(dv_), 3 * D,
-         ptr(dr), dr.stride(0) if dr is not None else 0, ptr(du), ptr(dvb), B, n_heads, Tq, Tk, dk, int(clamp_len),
+         ptr(dr), dr.stride(0) if dr is not None else 0, ptr(du), ptr(dvb), ptr(stats), B, n_heads, Tq, Tk, dk, int(clamp_len),
          int(causal), int(lookahead), int(chunk_c), int(chunk_l), ptr(ws), ws_bytes, current_stream_ptr(),
          flops=16.0 * B * n_heads * Tq * Tk * dk, tag="attention_bwd")
     return dqkv

@@ -200,9 +200,13 @@ def gen_rnn_encoder():
 GRAD_CASES = ["enc_conformer_small", "enc_transformer_xl", "enc_transformer_plain", "enc_uni_conformer"]
 
 
-def grad_loss_weights(shape, seed=4321):
-    """Fixed projection of the encoder output to a scalar: loss = sum(ys * w) (shared by generator and tests)."""
-    return np.random.default_rng(seed).standard_normal(shape).astype(np.float32)
+def grad_loss_weights(shape, xlens_out, seed=4321):
+    """Fixed projection of the encoder output to a scalar: loss = sum(ys * w), w = 0 on padded output frames (as every
+    real loss of the path: CTC / attention only read frames < xlens).  Shared by generator and tests."""
+    w = np.random.default_rng(seed).standard_normal(shape).astype(np.float32)
+    for b, n in enumerate(xlens_out):
+        w[b, int(n):] = 0.0
+    return w
 
 
 def gen_encoder_grads():
@@ -217,7 +221,7 @@ def gen_encoder_grads():
         xs = torch.from_numpy(base["xs"])
         out = enc(xs, torch.IntTensor(case["xlens"]), task='all')
         ys = out['ys']['xs']
-        w = torch.from_numpy(grad_loss_weights(tuple(ys.shape)))
+        w = torch.from_numpy(grad_loss_weights(tuple(ys.shape), out['ys']['xlens'].tolist()))
         loss = (ys * w).sum()
         loss.backward()
         save = {"g." + k: p.grad.numpy() for k, p in enc.named_parameters() if p.grad is not None}
