@@ -123,7 +123,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_arm(w, steps, warmup, sample_B=2, train=True):
+def cpu_reference_arm(w, steps, warmup, sample_B=1, sample_T=500, train=True):
     """The reference's CPU path, restated (oracle/): encoder forward + CTC forward/backward on the host cores."""
     import torch
     from oracle import encoder_oracle, ctc_oracle  # noqa: F401  (checker / baseline only)
@@ -145,6 +145,7 @@ def cpu_reference_arm(w, steps, warmup, sample_B=2, train=True):
                subsample=[int(s) for s in w["subsample"].split("_")], dropout_layer=0.0,
                conv=dict(in_channel=1, poolings=[tuple(int(v) for v in t.strip("()").split(",")) for t in w["poolings"].split("_")]),
                ffn_activation="swish", n_layers_sub1=0)
+    w = dict(w, T=sample_T)          # bounded sample: fewer, shorter utterances of the same model (frames/s normalises)
     xs, xlens, ys = synth_batch(w, sample_B, 1234)
     xs_t = torch.from_numpy(xs)
     ys_cat = torch.tensor([v for y in ys for v in y], dtype=torch.int32)
@@ -196,6 +197,7 @@ def main():
     ap.add_argument("--step", default="train", choices=["train", "fwd"],
                     help="train: fwd + loss + bwd + grad all-reduce + optimizer; fwd: encoder fwd + CTC fwd/bwd + head bwd")
     ap.add_argument("--optimizer", default="adam", choices=["adam", "none"])
+    ap.add_argument("--allreduce", default="bucketed", choices=["bucketed", "single"])
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -212,7 +214,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+        steps, warmup = max(1, min(args.steps, 2)), 0      # one training step of the sample is ~40 s of 128-core CPU time
         r = cpu_reference_arm(w, steps, warmup, train=args.step == "train")
         line = {"impl": "reference", "metric": "speech_frames_per_sec", "value": r["value"], "unit": "frames/s",
                 "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"],
@@ -275,22 +277,34 @@ def main():
             dist.all_reduce(flat)          # the single gradient all-reduce of the step (sum; DDP semantics)
         return loss
 
+    # Gradient exchange (N > 1): the reference's DDP semantics (sum of per-rank mean losses, train.py:423-424).
+    #   bucketed (default): every autograd node (encoder block, front-end, head layer) hands its flat fp32 gradient bucket
+    #     to NCCL as soon as its backward is enqueued -> the all-reduce overlaps the rest of the backward pass;
+    #   single: one all-reduce of the concatenated gradients after the backward pass.
+    works = []
+    if world > 1 and args.step == "train" and args.allreduce == "bucketed":
+        from neural_sp_b200 import autograd as ag
+        ag.set_grad_sync(lambda flat: works.append(dist.all_reduce(flat, async_op=True)))
+
     def step_train(x_dev):
         for p in all_params:
-            p.grad = None
+            p.grad = None                      # grads are views of the nodes' buckets: set-to-none, never accumulate
         out = enc(x_dev, xlens_t.clone(), task='ys')
         loss, _ = ctc(out['ys']['xs'], out['ys']['xlens'], ys)
         loss.backward()
         if world > 1:
-            # ONE all-reduce of the flat gradient buffer (sum of per-rank mean losses = the reference's DDP semantics,
-            # train.py:423-424), then scatter the views back for the optimizer
-            flat = torch.cat([p.grad.reshape(-1) for p in all_params])
-            dist.all_reduce(flat)
-            off = 0
-            for p in all_params:
-                n = p.numel()
-                p.grad = flat[off:off + n].view_as(p)
-                off += n
+            if args.allreduce == "bucketed":
+                for wk in works:
+                    wk.wait()
+                works.clear()
+            else:
+                flat = torch.cat([p.grad.reshape(-1) for p in all_params])
+                dist.all_reduce(flat)
+                off = 0
+                for p in all_params:
+                    n = p.numel()
+                    p.grad = flat[off:off + n].view_as(p)
+                    off += n
         if opt is not None:
             opt.step()
         return loss.detach()
@@ -447,7 +461,8 @@ def main():
                 "config": dict(cfg_common, l2="256 MiB memset between timed iterations (outside the event pairs); "
                                              "per-step working set >> 126 MB L2",
                                encoder_fwd_tflop_per_step=fl_utt * B / 1e12, enc_out_frames=Tp,
-                               cuda_graph=graph_ok, cuda_graph_error=graph_error, n_params=n_params),
+                               cuda_graph=graph_ok, cuda_graph_error=graph_error, n_params=n_params,
+                               allreduce=(args.allreduce if world > 1 else None)),
                 "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": int(xs_host.numel() * 4), "d2h_bytes_per_step": 4},
@@ -459,7 +474,7 @@ def main():
                            "step": "encoder_fwd + ctc_head + ctc_fwd_bwd + head_bwd (inference kernels, eval mode)",
                            "cuda_graph": fwd["graph"]}
         if not args.no_cpu_baseline and world == 1:
-            r = cpu_reference_arm(w, 1, 1, train=args.step == "train")
+            r = cpu_reference_arm(w, 1, 0, train=args.step == "train")
             line["cpu_baseline"] = {"value": r["value"], "unit": "frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
         print(json.dumps(line))
     if world > 1:

@@ -252,14 +252,18 @@ nsp_status nsp_linear_wgrad(int prec, const void* dy, const void* dy_lo, int64_t
 
 /* LayerNorm backward with the residual-branch gradient fused in:
  *   dx = dres + d/dx [ LN(x * in_scale) ] . dy ;  dgamma += sum_rows dy*xhat ;  dbeta += sum_rows dy.
- * dy, x fp32 [M,D]; dres fp32 [M,D] or NULL; dx fp32 and/or dx_bf16 outputs; dgamma/dbeta fp32 [D] or NULL. */
+ * dy, x fp32 [M,D]; dres fp32 [M,D] or NULL; dx fp32 and/or dx_bf16 outputs; dgamma/dbeta fp32 [D] or NULL.
+ * dcol (optional) += dcol_alpha * column sums of dx: the bias gradient of the residual-branch GEMM that receives dx as dy. */
 nsp_status nsp_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* gamma,
                              float eps, float in_scale, const float* dres, int64_t lddr,
                              float* dx, int64_t lddx, void* dx_bf16, int64_t lddxb,
-                             float* dgamma, float* dbeta, int M, int D, void* stream);
+                             float* dgamma, float* dbeta, float* dcol, float dcol_alpha, int M, int D, void* stream);
 
 /* dz = dh * act'(z) elementwise (act codes of nsp_linear_fwd); all bf16 (is_bf16=1) or all fp32. */
 nsp_status nsp_act_bwd(int is_bf16, int act, const void* dh, const void* z, void* dz, int64_t n, void* stream);
+/* nsp_act_bwd (mode 0, [M,N]) / nsp_glu_bwd (mode 1, dh = dg [M,N/2], z = pre, dz = dpre [M,N]) for bf16 tensors with the
+ * bias gradient of that pre-activation fused: dbias fp32 [N] += column sums of dz. */
+nsp_status nsp_act_bwd_bias(int mode, int act, const void* dh, const void* z, void* dz, float* dbias, int M, int N, void* stream);
 /* GLU backward: pre = [a | b] ([M, 2d]), out = a*sigmoid(b); dpre = [dg*s | dg*a*s*(1-s)]. */
 nsp_status nsp_glu_bwd(int is_bf16, const void* dg, const void* pre, void* dpre, int64_t M, int d, void* stream);
 /* y[n] += alpha * sum_m x[m,n]  (bias gradients); x bf16 or fp32 [M,N] with pitch ldx. */

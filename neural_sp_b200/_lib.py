@@ -153,7 +153,8 @@ _more = {
     "nsp_linear_wgrad": (c_int, [c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_f32, c_vp, c_i64,
                                  c_int, c_vp]),
     "nsp_layernorm_bwd": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_f32, c_f32, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64,
-                                  c_vp, c_vp, c_int, c_int, c_vp]),
+                                  c_vp, c_vp, c_vp, c_f32, c_int, c_int, c_vp]),
+    "nsp_act_bwd_bias": (c_int, [c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
     "nsp_act_bwd": (c_int, [c_int, c_int, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "nsp_glu_bwd": (c_int, [c_int, c_vp, c_vp, c_vp, c_i64, c_int, c_vp]),
     "nsp_colsum_acc": (c_int, [c_int, c_vp, c_i64, c_int, c_int, c_f32, c_vp, c_vp]),

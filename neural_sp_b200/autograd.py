@@ -22,10 +22,23 @@ def training_enabled(module):
 
 
 class _Grads:
-    """fp32 gradient buffers keyed by parameter (created zeroed on first use)."""
+    """fp32 gradient buffers of one autograd node, carved out of ONE zero-initialised flat tensor (one memset per node
+    instead of one per parameter).  The flat tensor is also the node's all-reduce bucket: when a gradient-sync hook is
+    installed (``set_grad_sync``), the node hands it over as soon as its backward has been enqueued, so the NCCL
+    all-reduce of block k overlaps the backward of blocks k-1, k-2, ... (the returned ``.grad`` tensors are views of it)."""
 
-    def __init__(self):
+    def __init__(self, params=()):
         self.g = {}
+        self.flat = None
+        params = [p for p in params if p is not None]
+        if params:
+            total = sum(p.numel() for p in params)
+            self.flat = torch.zeros(total, dtype=torch.float32, device=params[0].device)
+            off = 0
+            for p in params:
+                if id(p) not in self.g:
+                    self.g[id(p)] = self.flat[off:off + p.numel()].view(p.shape)
+                    off += p.numel()
 
     def buf(self, p):
         t = self.g.get(id(p))
@@ -36,6 +49,35 @@ class _Grads:
 
     def get(self, p):
         return self.g.get(id(p))
+
+    def put(self, p, value):
+        """Store a gradient computed in another layout (tiny tensors only: one strided copy)."""
+        self.buf(p).copy_(value.reshape(p.shape))
+
+    def fused(self, params):
+        """One [sum rows, cols] view over parameters that are adjacent in the flat buffer (fused QKV weight gradient)."""
+        views = [self.g[id(p)] for p in params]
+        rows = sum(v.shape[0] for v in views)
+        first = views[0]
+        ok = self.flat is not None and all(
+            views[i + 1].data_ptr() == views[i].data_ptr() + views[i].numel() * 4 for i in range(len(views) - 1))
+        if not ok:
+            return None
+        off = (first.data_ptr() - self.flat.data_ptr()) // 4
+        return self.flat[off:off + rows * first[0].numel()].view(rows, *first.shape[1:])
+
+    def done(self):
+        if _GRAD_SYNC is not None and self.flat is not None:
+            _GRAD_SYNC(self.flat)
+
+
+_GRAD_SYNC = None
+
+
+def set_grad_sync(fn):
+    """Install (or clear with None) the hook called with every node's flat gradient bucket right after its backward."""
+    global _GRAD_SYNC
+    _GRAD_SYNC = fn
 
 
 def _wT(module, name, prec, params, build=None):
@@ -63,14 +105,21 @@ def _ln_fwd(norm, x, prec):
     return ops.layernorm(x, norm.weight, norm.bias, norm.eps)
 
 
-def _ln_bwd(norm, dn, x, dres, G, prec):
+def _ln_bwd(norm, dn, x, dres, G, prec, next_bias=None, next_alpha=1.0):
     """-> (dx fp32, dx in the GEMM operand dtype): in bf16 mode the kernel also emits the bf16 copy the next branch's
-    dgrad / wgrad GEMMs read, so no separate cast pass is needed."""
+    dgrad / wgrad GEMMs read, so no separate cast pass is needed.  next_bias: bias parameter of the residual-branch output
+    layer that will receive dx as its dy (its gradient = alpha * column sums of dx, accumulated by the same kernel)."""
+    dcol = G.buf(next_bias) if next_bias is not None else None
     if prec == "bf16":
         return ops.layernorm_bwd(dn, x, norm.weight, norm.eps, dres=dres, dgamma=G.buf(norm.weight), dbeta=G.buf(norm.bias),
-                                 want_bf16=True)
-    dx = ops.layernorm_bwd(dn, x, norm.weight, norm.eps, dres=dres, dgamma=G.buf(norm.weight), dbeta=G.buf(norm.bias))
+                                 want_bf16=True, dcol=dcol, dcol_alpha=next_alpha)
+    dx = ops.layernorm_bwd(dn, x, norm.weight, norm.eps, dres=dres, dgamma=G.buf(norm.weight), dbeta=G.buf(norm.bias),
+                           dcol=dcol, dcol_alpha=next_alpha)
     return dx, dx
+
+
+def _fusable(t):
+    return t.dtype == torch.bfloat16 and t.shape[-1] % 16 == 0
 
 
 def ffn_fwd(ffn, norm, x, scale, prec):
@@ -84,16 +133,22 @@ def ffn_fwd(ffn, norm, x, scale, prec):
     return y, (x, n, z, h)
 
 
-def ffn_bwd(ffn, norm, saved, dy, dyo, scale, prec, G):
+def ffn_bwd(ffn, norm, saved, dy, dyo, scale, prec, G, bias_done=False, nxt=(None, 1.0)):
+    """bias_done: the producer of dy already accumulated w_2.bias' gradient; nxt = (bias param, alpha) of the branch that
+    consumes this function's dx."""
     x, n, z, h = saved
     ops.linear_wgrad(dyo, h, prec, G.buf(ffn.w_2.weight), alpha=scale)
-    ops.colsum_acc(dy, G.buf(ffn.w_2.bias), alpha=scale)
+    if not bias_done:
+        ops.colsum_acc(dy, G.buf(ffn.w_2.bias), alpha=scale)
     dh = ops.linear(dyo, _wT(ffn, "w_2", prec, (ffn.w_2.weight,)), None, prec=prec, alpha=scale, out_dtype=act_dtype(prec))
-    dz = ops.act_bwd(dh, z, ffn.act_name)
+    if _fusable(z):
+        dz = ops.act_bwd_bias(dh, z, ffn.act_name, G.buf(ffn.w_1.bias))
+    else:
+        dz = ops.act_bwd(dh, z, ffn.act_name)
+        ops.colsum_acc(dz, G.buf(ffn.w_1.bias))
     ops.linear_wgrad(dz, n, prec, G.buf(ffn.w_1.weight))
-    ops.colsum_acc(dz, G.buf(ffn.w_1.bias))
     dn = ops.linear(dz, _wT(ffn, "w_1", prec, (ffn.w_1.weight,)), None, prec=prec, out_dtype=torch.float32)
-    return _ln_bwd(norm, dn, x, dy, G, prec)
+    return _ln_bwd(norm, dn, x, dy, G, prec, nxt[0], nxt[1])
 
 
 def _qkv_weight(attn, prec, transposed=False):
@@ -127,12 +182,13 @@ def attn_fwd(attn, norm, x, pos, klens, u_bias, v_bias, mask_kw, prec, rel):
     return y, (x, n, qkv, r, cv, nrows, stats)
 
 
-def attn_bwd(attn, norm, saved, dy, dyo, pos, klens, u_bias, v_bias, mask_kw, prec, rel, G, enc_bias_params):
+def attn_bwd(attn, norm, saved, dy, dyo, pos, klens, u_bias, v_bias, mask_kw, prec, rel, G, enc_bias_params,
+             bias_done=False, nxt=(None, 1.0)):
     x, n, qkv, r, cv, nrows, stats = saved
     D = attn.n_heads * attn.d_k
     d_in = x.shape[-1]
     ops.linear_wgrad(dyo, cv, prec, G.buf(attn.w_out.weight))
-    if attn.w_out.bias is not None:
+    if attn.w_out.bias is not None and not bias_done:
         ops.colsum_acc(dy, G.buf(attn.w_out.bias))
     dcv = ops.linear(dyo, _wT(attn, "w_out", prec, (attn.w_out.weight,)), None, prec=prec, out_dtype=act_dtype(prec))
     dr = torch.zeros(nrows, D, dtype=torch.float32, device=x.device) if rel else None
@@ -143,22 +199,27 @@ def attn_bwd(attn, norm, saved, dy, dyo, pos, klens, u_bias, v_bias, mask_kw, pr
     dqkv = ops.relpos_attention_bwd(qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:], klens, attn.n_heads, cv, dcv, r=r,
                                     u_bias=u_bias if rel else None, v_bias=v_bias if rel else None, clamp_len=clamp,
                                     dr=dr, du=du, dvb=dvb, stats=stats, **mask_kw)
-    gw = torch.zeros(3 * D, d_in, dtype=torch.float32, device=x.device)
-    ops.linear_wgrad(dqkv, n, prec, gw)
-    for i, lin in enumerate((attn.w_query, attn.w_key, attn.w_value)):
-        G.g[id(lin.weight)] = gw[i * D:(i + 1) * D]          # row blocks of the fused gradient (views)
+    qkv_lins = (attn.w_query, attn.w_key, attn.w_value)
+    gw = G.fused([lin.weight for lin in qkv_lins])             # the three weights are adjacent in the node's flat buffer
+    if gw is not None:
+        ops.linear_wgrad(dqkv, n, prec, gw)
+    else:
+        gw = torch.zeros(3 * D, d_in, dtype=torch.float32, device=x.device)
+        ops.linear_wgrad(dqkv, n, prec, gw)
+        for i, lin in enumerate(qkv_lins):
+            G.put(lin.weight, gw[i * D:(i + 1) * D])
     if attn.w_key.bias is not None:
         gb = torch.zeros(3 * D, dtype=torch.float32, device=x.device)
         ops.colsum_acc(dqkv, gb)
-        for i, lin in enumerate((attn.w_query, attn.w_key, attn.w_value)):
-            G.g[id(lin.bias)] = gb[i * D:(i + 1) * D]
+        for i, lin in enumerate(qkv_lins):
+            G.put(lin.bias, gb[i * D:(i + 1) * D])
     if rel:   # r = pos[:nrows] @ Wp^T (+ bp): the position projection shares w_value when not xl_like (reference :176)
         wp_lin = attn.w_pos if attn.xl_like else attn.w_value
         ops.linear_wgrad(dr, pos[:nrows], prec, G.buf(wp_lin.weight))
         if wp_lin.bias is not None:
             ops.colsum_acc(dr, G.buf(wp_lin.bias))
     dn = ops.linear(dqkv, _qkv_weight(attn, prec, transposed=True), None, prec=prec, out_dtype=torch.float32)
-    return _ln_bwd(norm, dn, x, dy, G, prec)
+    return _ln_bwd(norm, dn, x, dy, G, prec, nxt[0], nxt[1])
 
 
 def convmod_fwd(conv, norm, x, prec):
@@ -176,29 +237,39 @@ def convmod_fwd(conv, norm, x, prec):
     return y, (x, n, pre, g, c, taps)
 
 
-def convmod_bwd(conv, norm, saved, dy, dyo, prec, G):
+def convmod_bwd(conv, norm, saved, dy, dyo, prec, G, bias_done=False, nxt=(None, 1.0)):
     x, n, pre, g, c, taps = saved
     d = x.shape[-1]
     ops.linear_wgrad(dyo, c, prec, _as2d(G.buf(conv.pointwise_conv2.weight)))
-    ops.colsum_acc(dy, G.buf(conv.pointwise_conv2.bias))
+    if not bias_done:
+        ops.colsum_acc(dy, G.buf(conv.pointwise_conv2.bias))
     dc = ops.linear(dyo, _wT(conv, "pw2", prec, (conv.pointwise_conv2.weight,)), None, prec=prec, out_dtype=act_dtype(prec))
     dtaps = torch.zeros_like(taps)
     dg = ops.conformer_conv_bwd(g, taps, conv.depthwise_conv.bias, conv.norm.weight, conv.norm.bias, conv.norm.eps, dc,
                                 dtaps, G.buf(conv.depthwise_conv.bias), G.buf(conv.norm.weight), G.buf(conv.norm.bias),
                                 causal=conv.causal)
-    G.g[id(conv.depthwise_conv.weight)] = dtaps.t().reshape(conv.depthwise_conv.weight.shape)
-    dpre = ops.glu_bwd(dg, pre)
+    G.put(conv.depthwise_conv.weight, dtaps.t())
+    if _fusable(pre) and pre.shape[-1] % 32 == 0:
+        dpre = ops.act_bwd_bias(dg, pre, None, G.buf(conv.pointwise_conv1.bias), glu=True)
+    else:
+        dpre = ops.glu_bwd(dg, pre)
+        ops.colsum_acc(dpre, G.buf(conv.pointwise_conv1.bias))
     ops.linear_wgrad(dpre, n, prec, _as2d(G.buf(conv.pointwise_conv1.weight)))
-    ops.colsum_acc(dpre, G.buf(conv.pointwise_conv1.bias))
     dn = ops.linear(dpre, _wT(conv, "pw1", prec, (conv.pointwise_conv1.weight,)), None, prec=prec, out_dtype=torch.float32)
-    return _ln_bwd(norm, dn, x, dy, G, prec)
+    return _ln_bwd(norm, dn, x, dy, G, prec, nxt[0], nxt[1])
 
 
 # ------------------------------------------------------------------------------------------------
 # encoder blocks
 # ------------------------------------------------------------------------------------------------
 def _param_list(block, extra):
-    return [p for p in block.parameters()] + [p for p in extra if p is not None]
+    """Parameters of a block, with w_query / w_key / w_value weights moved next to each other (in that order) so that
+    the fused QKV weight gradient is one contiguous region of the node's flat gradient buffer."""
+    att = block.self_attn
+    qkv = [att.w_query.weight, att.w_key.weight, att.w_value.weight]
+    ids = {id(p) for p in qkv}
+    rest = [p for p in block.parameters() if id(p) not in ids]
+    return qkv + rest + [p for p in extra if p is not None]
 
 
 class _BlockFn(torch.autograd.Function):
@@ -230,22 +301,29 @@ class _BlockFn(torch.autograd.Function):
     def backward(ctx, dy):
         block, S, prec = ctx.block, ctx.saved, ctx.prec
         u_bias, v_bias = ctx.rel_bias
-        G = _Grads()
+        G = _Grads(ctx.params)
         dy = dy.contiguous().float()
         if hasattr(block, "feed_forward_macaron"):
-            dx, dxo = _ln_bwd(block.norm5, dy, S["x5"], None, G, prec)
-            dx, dxo = ffn_bwd(block.feed_forward, block.norm4, S["ff"], dx, dxo, block.fc_factor, prec, G)
-            dx, dxo = convmod_bwd(block.conv, block.norm3, S["conv"], dx, dxo, prec, G)
+            # every LayerNorm backward also accumulates the bias gradient of the branch that consumes its dx
+            fc = block.fc_factor
+            dx, dxo = _ln_bwd(block.norm5, dy, S["x5"], None, G, prec, block.feed_forward.w_2.bias, fc)
+            dx, dxo = ffn_bwd(block.feed_forward, block.norm4, S["ff"], dx, dxo, fc, prec, G, bias_done=True,
+                              nxt=(block.conv.pointwise_conv2.bias, 1.0))
+            dx, dxo = convmod_bwd(block.conv, block.norm3, S["conv"], dx, dxo, prec, G, bias_done=True,
+                                  nxt=(block.self_attn.w_out.bias, 1.0))
             dx, dxo = attn_bwd(block.self_attn, block.norm2, S["att"], dx, dxo, ctx.pos, ctx.klens, u_bias, v_bias,
-                               ctx.mask_kw, prec, True, G, ctx.rel_bias)
-            dx, dxo = ffn_bwd(block.feed_forward_macaron, block.norm1, S["ffm"], dx, dxo, block.fc_factor, prec, G)
+                               ctx.mask_kw, prec, True, G, ctx.rel_bias, bias_done=True,
+                               nxt=(block.feed_forward_macaron.w_2.bias, fc))
+            dx, dxo = ffn_bwd(block.feed_forward_macaron, block.norm1, S["ffm"], dx, dxo, fc, prec, G, bias_done=True)
         else:
-            dx, dxo = ffn_bwd(block.feed_forward, block.norm2, S["ff"], dy, _gop(dy, prec), 1.0, prec, G)
+            dx, dxo = ffn_bwd(block.feed_forward, block.norm2, S["ff"], dy, _gop(dy, prec), 1.0, prec, G,
+                              nxt=(block.self_attn.w_out.bias, 1.0))
             dx, dxo = attn_bwd(block.self_attn, block.norm1, S["att"], dx, dxo, ctx.pos, ctx.klens, u_bias, v_bias,
-                               ctx.mask_kw, prec, block.rel_attn, G, ctx.rel_bias)
+                               ctx.mask_kw, prec, block.rel_attn, G, ctx.rel_bias, bias_done=True)
         if ctx.in_scale != 1.0:
             ops.scale_(dx, ctx.in_scale)
         ctx.saved = None
+        G.done()
         grads = tuple(G.get(p) for p in ctx.params)
         return (dx, None, None, None, None, None, None, None) + grads
 
@@ -271,8 +349,11 @@ class _LayerNormFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, weight = ctx.saved_tensors
-        dg, db = torch.zeros_like(weight, dtype=torch.float32), torch.zeros_like(weight, dtype=torch.float32)
+        flat = torch.zeros(2 * weight.numel(), dtype=torch.float32, device=weight.device)
+        dg, db = flat[:weight.numel()], flat[weight.numel():]
         dx = ops.layernorm_bwd(dy.contiguous().float(), x, weight, ctx.eps, dres=None, dgamma=dg, dbeta=db)
+        if _GRAD_SYNC is not None:
+            _GRAD_SYNC(flat)
         return dx, dg, db, None
 
 
@@ -384,7 +465,7 @@ class _FrontendFn(torch.autograd.Function):
     def backward(ctx, dy):
         enc, tape, prec = ctx.enc, ctx.tape, ctx.prec
         B, Tl, Fo, C = ctx.dims
-        G = _Grads()
+        G = _Grads(ctx.params)
         adt = act_dtype(prec)
         dy = dy.contiguous().float()
         if enc.bridge is not None:
@@ -392,7 +473,7 @@ class _FrontendFn(torch.autograd.Function):
             gperm = torch.zeros(enc.bridge.weight.shape[0], Fo * C, dtype=torch.float32, device=dy.device)
             ops.linear_wgrad(dyo, ctx.feat, prec, gperm, alpha=ctx.out_scale)
             # undo the (f, c) -> (c, f) column permutation of the cached operand: pure view + copy by autograd's accumulate
-            G.g[id(enc.bridge.weight)] = gperm.view(-1, Fo, C).transpose(1, 2).reshape(enc.bridge.weight.shape)
+            G.put(enc.bridge.weight, gperm.view(-1, Fo, C).transpose(1, 2))
             ops.colsum_acc(dy, G.buf(enc.bridge.bias), alpha=ctx.out_scale)
             wbT = prepared(enc, "bridge.T", prec, (enc.bridge.weight,),
                            build=lambda w: w.view(w.size(0), C, Fo).transpose(1, 2).reshape(w.size(0), Fo * C).t().contiguous())
@@ -415,6 +496,7 @@ class _FrontendFn(torch.autograd.Function):
             if not rec["first"]:
                 d = _conv_any(blk, "conv1", blk.conv1, dz1, B, T, F, False, prec, weight="dgrad", relu=False)
         ctx.tape = None
+        G.done()
         return (None, None, None, None) + tuple(G.get(p) for p in ctx.params)
 
 

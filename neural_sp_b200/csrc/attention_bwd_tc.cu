@@ -62,6 +62,15 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t smem_addr, uint32_t lbo_byt
     d |= (uint64_t)2 << 61;
     return d;
 }
+// Bounded mbarrier wait: a protocol error becomes a trap with a message instead of a hung GPU.
+__device__ __forceinline__ void bwait(uint64_t* bar, uint32_t parity, int code) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < 2000000000ll)                 // ~1 s
+        if (tc::mbar_try_wait(bar, parity)) return;
+    printf("attn_bwd_tc: mbarrier wait %d timed out (block %d thread %d parity %u)\n", code, (int)blockIdx.x, (int)threadIdx.x, parity);
+    __trap();
+}
+
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -132,7 +141,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_bwd_tc_kernel(const __grid_c
             if (a.has_rel) tc::tma_load_2d(sR, &tmap_r, kv_full, h * DK, 0);
             for (int t = 0; t < ntiles; ++t) {
                 const int buf = t & 1;
-                tc::mbar_wait(&qd_empty[buf], ((t >> 1) & 1) ^ 1);
+                bwait(&qd_empty[buf], ((t >> 1) & 1) ^ 1, 1);
                 tc::mbar_arrive_expect_tx(&qd_full[buf], 2 * TILE);
                 tc::tma_load_3d(sQ + buf * TILE, &tmap_q, &qd_full[buf], h * DK, (t_first + t) * QT, b);
                 tc::tma_load_3d(sDO + buf * TILE, &tmap_do, &qd_full[buf], h * DK, (t_first + t) * QT, b);
@@ -144,7 +153,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_bwd_tc_kernel(const __grid_c
             constexpr uint32_t idesc_bd = tc::make_idesc(1u, 128, 16);
             constexpr uint32_t idesc_acc = tc::make_idesc(1u, 128, 64) | (1u << 16);                // B MN-major
             constexpr uint32_t idesc_dq = tc::make_idesc(1u, 128, 64) | (1u << 15) | (1u << 16);    // A and B MN-major
-            tc::mbar_wait(kv_full, 0);
+            bwait(kv_full, 0, 2);
             tc::tc_fence_after();
             const uint64_t kdesc = tc::make_smem_desc_sw128(tc::smem_u32(sK));
             const uint64_t vdesc = tc::make_smem_desc_sw128(tc::smem_u32(sV));
@@ -156,7 +165,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_bwd_tc_kernel(const __grid_c
             for (int t = 0; t < ntiles; ++t) {
                 const int buf = t & 1;
                 const uint32_t ph = t & 1;
-                tc::mbar_wait(&qd_full[buf], (t >> 1) & 1);
+                bwait(&qd_full[buf], (t >> 1) & 1, 3);
                 tc::tc_fence_after();
                 const uint64_t qdesc = tc::make_smem_desc_sw128(tc::smem_u32(sQ + buf * TILE));
                 const uint64_t dodesc = tc::make_smem_desc_sw128(tc::smem_u32(sDO + buf * TILE));
@@ -171,7 +180,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_bwd_tc_kernel(const __grid_c
 #pragma unroll
                 for (int k = 0; k < 4; ++k) tc::umma_f16(tm_DP, vdesc + 2 * k, dodesc + 2 * k, idesc_s, k > 0);
                 tc::umma_commit(s_full);
-                tc::mbar_wait(p_full, ph);
+                bwait(p_full, ph, 4);
                 tc::tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -214,7 +223,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_bwd_tc_kernel(const __grid_c
                 if (i < a.T) v = (which < 2) ? a.stats[(bh * a.T + i) * 2 + which] : a.dsum[bh * a.T + i];
                 sST[e] = v;
             }
-            tc::mbar_wait(s_full, ph);
+            bwait(s_full, ph, 5);
             tc::tc_fence_after();
             if (a.has_rel && half == 0) {
                 uint32_t r16[16];
@@ -274,7 +283,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_bwd_tc_kernel(const __grid_c
             tc::fence_proxy_async_smem();
             tc::mbar_arrive(p_full);
             // ---- dQ_t: lane = query row; this thread adds 32 of the 64 columns ----
-            tc::mbar_wait(o_full, ph);
+            bwait(o_full, ph, 6);
             tc::tc_fence_after();
             {
                 uint32_t r[32];
@@ -291,11 +300,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_bwd_tc_kernel(const __grid_c
             tc::tc_fence_before();
         }
         // ---- dK, dV of this key tile (complete after the last o_full) ----
-        if (ntiles > 0 && jin) {
-            uint32_t rv[32], rk[32];
+        // tcgen05.ld is warp-collective (.sync.aligned): issue it from the whole warp, guard only the stores by `jin`
+        uint32_t rv[32], rk[32];
+        if (ntiles > 0) {
             tc::tmem_ld_32x32(tm_DV + lane_addr + (uint32_t)(half * 32), rv);
             tc::tmem_ld_32x32(tm_DK + lane_addr + (uint32_t)(half * 32), rk);
             tc::tmem_ld_wait();
+        }
+        if (ntiles > 0 && jin) {
             __nv_bfloat16* ov = a.dv + ((int64_t)b * a.T + j) * a.lddv + h * DK + half * 32;
             __nv_bfloat16* ok = a.dk + ((int64_t)b * a.T + j) * a.lddk + h * DK + half * 32;
 #pragma unroll

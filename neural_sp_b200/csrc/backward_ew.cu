@@ -36,16 +36,17 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                             float* __restrict__ dx, int64_t lddx,
                                                             __nv_bfloat16* __restrict__ dxb, int64_t lddxb,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                            float* __restrict__ dcol, float dcol_alpha,
                                                             int M, int D) {
-    extern __shared__ float red[];     // [8][2][D]
+    extern __shared__ float red[];     // [8][D]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float gsum[VPT][4], bsum[VPT][4], gm[VPT][4];
+    float gsum[VPT][4], bsum[VPT][4], gm[VPT][4], csum[VPT][4];
 #pragma unroll
     for (int j = 0; j < VPT; ++j) {
         const int idx = (j * 32 + lane) * 4;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            gsum[j][k] = 0.f; bsum[j][k] = 0.f;
+            gsum[j][k] = 0.f; bsum[j][k] = 0.f; csum[j][k] = 0.f;
             gm[j][k] = (idx + k < D) ? __ldg(gamma + idx + k) : 0.f;
         }
     }
@@ -112,6 +113,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                     const float4 r = *reinterpret_cast<const float4*>(dres + row * lddr + idx);
                     o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
                 }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) csum[j][k] += o[k];
                 if (dx) *reinterpret_cast<float4*>(dx + row * lddx + idx) = make_float4(o[0], o[1], o[2], o[3]);
                 if (dxb) {
                     __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]), b = __floats2bfloat162_rn(o[2], o[3]);
@@ -121,23 +124,30 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
             }
         }
     }
-    // ---- CTA reduction of the parameter gradients ----
-    float* rg = red + (size_t)warp * 2 * D;
+    // ---- CTA reduction of the parameter gradients: three rounds through one [8][D] buffer (keeps shared memory, and with
+    //      it the number of resident CTAs, independent of how many sums are formed) ----
+#pragma unroll 1
+    for (int round = 0; round < 3; ++round) {
+        float* out = round == 0 ? dgamma : (round == 1 ? dbeta : dcol);
+        if (out == nullptr) continue;                       // uniform
+        float* rg = red + (size_t)warp * D;
 #pragma unroll
-    for (int j = 0; j < VPT; ++j) {
-        const int idx = (j * 32 + lane) * 4;
-        if (idx < D) {
+        for (int j = 0; j < VPT; ++j) {
+            const int idx = (j * 32 + lane) * 4;
+            if (idx < D) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { rg[idx + k] = gsum[j][k]; rg[D + idx + k] = bsum[j][k]; }
+                for (int k = 0; k < 4; ++k) rg[idx + k] = round == 0 ? gsum[j][k] : (round == 1 ? bsum[j][k] : csum[j][k]);
+            }
         }
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < 2 * D; c += 256) {
-        float t = 0.f;
+        __syncthreads();
+        const float sc_out = round == 2 ? dcol_alpha : 1.f;
+        for (int c = threadIdx.x; c < D; c += 256) {
+            float t = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) t += red[(size_t)w * 2 * D + c];
-        if (c < D) { if (dgamma) atomicAdd(dgamma + c, t); }
-        else if (dbeta) atomicAdd(dbeta + (c - D), t);
+            for (int w = 0; w < 8; ++w) t += red[(size_t)w * D + c];
+            atomicAdd(out + c, sc_out * t);
+        }
+        __syncthreads();
     }
 }
 
@@ -164,6 +174,117 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const T* __restrict__ dh, 
                                                       int64_t n, int act) {
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
         bw_st<T>(dz + i, bw_ld<T>(dh + i) * dact(act, bw_ld<T>(z + i)));
+}
+
+// 16-byte vector variants for bf16 tensors (8 elements per thread and iteration; n % 8 == 0, 16-byte aligned pointers)
+__device__ __forceinline__ void unpack8(const uint4& raw, float (&f)[8]) {
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float2 t = __bfloat1622float2(h2[k]); f[2 * k] = t.x; f[2 * k + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 o;
+    __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b = __floats2bfloat162_rn(f[2], f[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(f[4], f[5]), d = __floats2bfloat162_rn(f[6], f[7]);
+    o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
+    o.z = *reinterpret_cast<uint32_t*>(&c); o.w = *reinterpret_cast<uint32_t*>(&d);
+    return o;
+}
+
+__global__ void __launch_bounds__(256) act_bwd_vec_kernel(const uint4* __restrict__ dh, const uint4* __restrict__ z,
+                                                          uint4* __restrict__ dz, int64_t n8, int act) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n8; i += (int64_t)gridDim.x * 256) {
+        float a[8], b[8];
+        unpack8(dh[i], a); unpack8(z[i], b);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] *= dact(act, b[k]);
+        dz[i] = pack8(a);
+    }
+}
+
+// GLU backward, bf16, one thread = 8 consecutive channels of one row (d % 8 == 0)
+__global__ void __launch_bounds__(256) glu_bwd_vec_kernel(const uint4* __restrict__ dg, const uint4* __restrict__ pre,
+                                                          uint4* __restrict__ dpre, int64_t M, int d8) {
+    const int64_t n = M * d8;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const int64_t r = i / d8;
+        const int c = (int)(i - r * d8);
+        float g[8], a[8], b[8], oa[8], ob[8];
+        unpack8(dg[i], g); unpack8(pre[r * 2 * d8 + c], a); unpack8(pre[r * 2 * d8 + d8 + c], b);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float sgm = 1.f / (1.f + __expf(-b[k]));
+            oa[k] = g[k] * sgm;
+            ob[k] = g[k] * a[k] * sgm * (1.f - sgm);
+        }
+        dpre[r * 2 * d8 + c] = pack8(oa);
+        dpre[r * 2 * d8 + d8 + c] = pack8(ob);
+    }
+}
+
+// Row-structured variants that also accumulate dbias[c] += sum_rows(result[., c]) (the bias gradient of the layer whose
+// pre-activation this is): thread = 8 fixed columns, the 8 warps of a CTA stride over the rows of its slice.
+// MODE 0: dz = dh * act'(z) on [M, N];  MODE 1: GLU backward, dg [M, N/2], pre / dpre [M, N].
+template <int MODE>
+__global__ void __launch_bounds__(256) act_bwd_bias_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ z,
+                                                           __nv_bfloat16* __restrict__ dz, float* __restrict__ dbias,
+                                                           int M, int N, int act) {
+    __shared__ float part[8][257];
+    const int lane = threadIdx.x & 31, rs = threadIdx.x >> 5;
+    const int c0 = (blockIdx.x * 32 + lane) * 8;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    if (c0 < N) {
+        for (int r = blockIdx.y * 8 + rs; r < M; r += gridDim.y * 8) {
+            float o[8];
+            if constexpr (MODE == 0) {
+                float a[8], b[8];
+                unpack8(*reinterpret_cast<const uint4*>(dh + (int64_t)r * N + c0), a);
+                unpack8(*reinterpret_cast<const uint4*>(z + (int64_t)r * N + c0), b);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] = a[k] * dact(act, b[k]);
+            } else {
+                const int d = N / 2;
+                const bool gate = c0 >= d;                        // columns [d, 2d) are the gate half
+                const int c = gate ? c0 - d : c0;
+                float g[8], a[8], b[8];
+                unpack8(*reinterpret_cast<const uint4*>(dh + (int64_t)r * d + c), g);
+                unpack8(*reinterpret_cast<const uint4*>(z + (int64_t)r * N + c), a);
+                unpack8(*reinterpret_cast<const uint4*>(z + (int64_t)r * N + d + c), b);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float sgm = 1.f / (1.f + __expf(-b[k]));
+                    o[k] = gate ? g[k] * a[k] * sgm * (1.f - sgm) : g[k] * sgm;
+                }
+            }
+            *reinterpret_cast<uint4*>(dz + (int64_t)r * N + c0) = pack8(o);
+            // the bias gradient sums the ROUNDED values the weight-gradient GEMM will read
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += o[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) part[rs][lane * 8 + k] = acc[k];
+    __syncthreads();
+    const int col = blockIdx.x * 256 + threadIdx.x;
+    if (col < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
+        atomicAdd(dbias + col, t);
+    }
+}
+
+__global__ void __launch_bounds__(256) relu_mask_vec_kernel(const uint4* __restrict__ dx, const uint4* __restrict__ a,
+                                                            uint4* __restrict__ dz, int64_t n8) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n8; i += (int64_t)gridDim.x * 256) {
+        float x[8], y[8];
+        unpack8(dx[i], x); unpack8(a[i], y);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = y[k] > 0.f ? x[k] : 0.f;
+        dz[i] = pack8(x);
+    }
 }
 
 // GLU backward: out = a * sigmoid(b) with pre = [a | b] of width 2*d per row.
@@ -312,7 +433,7 @@ using namespace nsp;
 extern "C" nsp_status nsp_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* gamma,
                                         float eps, float in_scale, const float* dres, int64_t lddr,
                                         float* dx, int64_t lddx, void* dx_bf16, int64_t lddxb,
-                                        float* dgamma, float* dbeta, int M, int D, void* stream) {
+                                        float* dgamma, float* dbeta, float* dcol, float dcol_alpha, int M, int D, void* stream) {
     NSP_CHECK_ARG(dy && x && gamma && (dx || dx_bf16), "layernorm_bwd: null pointer");
     NSP_CHECK_ARG(M > 0 && D > 0 && D % 4 == 0 && D <= 2048, "layernorm_bwd: bad shape M=%d D=%d (D %% 4 == 0, <= 2048)", M, D);
     NSP_CHECK_ARG(lddy % 4 == 0 && ldx % 4 == 0 && (!dres || lddr % 4 == 0) && (!dx || lddx % 4 == 0) && (!dx_bf16 || lddxb % 4 == 0),
@@ -323,14 +444,14 @@ extern "C" nsp_status nsp_layernorm_bwd(const float* dy, int64_t lddy, const flo
     int grid = ceil_div(M, 8);
     const int cap = num_sms() * 4;
     if (grid > cap) grid = cap;
-    const size_t smem = sizeof(float) * 16 * (size_t)D;
+    const size_t smem = sizeof(float) * 8 * (size_t)D;
     __nv_bfloat16* dxb = (__nv_bfloat16*)dx_bf16;
 #define NSP_LNB(VPT)                                                                                                     \
     do {                                                                                                                 \
         auto kern = layernorm_bwd_kernel<VPT>;                                                                           \
         static size_t attr = 0;                                                                                          \
         if (smem > attr) { NSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; } \
-        kern<<<grid, 256, smem, st>>>(dy, lddy, x, ldx, gamma, eps, in_scale, dres, lddr, dx, lddx, dxb, lddxb, dgamma, dbeta, M, D); \
+        kern<<<grid, 256, smem, st>>>(dy, lddy, x, ldx, gamma, eps, in_scale, dres, lddr, dx, lddx, dxb, lddxb, dgamma, dbeta, dcol, dcol_alpha, M, D); \
     } while (0)
     const int vpt = ceil_div(D / 4, 32);
     if (vpt <= 1) NSP_LNB(1); else if (vpt <= 2) NSP_LNB(2); else if (vpt <= 4) NSP_LNB(4);
@@ -344,7 +465,10 @@ extern "C" nsp_status nsp_act_bwd(int is_bf16, int act, const void* dh, const vo
     NSP_CHECK_ARG(dh && z && dz && n >= 0 && act >= 0 && act <= 4, "act_bwd: bad arguments");
     if (n == 0) return NSP_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if (is_bf16) act_bwd_kernel<__nv_bfloat16><<<bw_grid(n), 256, 0, st>>>((const __nv_bfloat16*)dh, (const __nv_bfloat16*)z, (__nv_bfloat16*)dz, n, act);
+    const bool al16 = (((uintptr_t)dh | (uintptr_t)z | (uintptr_t)dz) & 15) == 0;
+    if (is_bf16 && al16 && n % 8 == 0)
+        act_bwd_vec_kernel<<<bw_grid(n / 8), 256, 0, st>>>((const uint4*)dh, (const uint4*)z, (uint4*)dz, n / 8, act);
+    else if (is_bf16) act_bwd_kernel<__nv_bfloat16><<<bw_grid(n), 256, 0, st>>>((const __nv_bfloat16*)dh, (const __nv_bfloat16*)z, (__nv_bfloat16*)dz, n, act);
     else act_bwd_kernel<float><<<bw_grid(n), 256, 0, st>>>((const float*)dh, (const float*)z, (float*)dz, n, act);
     NSP_LAUNCH_OK();
     return NSP_OK;
@@ -353,7 +477,10 @@ extern "C" nsp_status nsp_act_bwd(int is_bf16, int act, const void* dh, const vo
 extern "C" nsp_status nsp_glu_bwd(int is_bf16, const void* dg, const void* pre, void* dpre, int64_t M, int d, void* stream) {
     NSP_CHECK_ARG(dg && pre && dpre && M > 0 && d > 0, "glu_bwd: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    if (is_bf16) glu_bwd_kernel<__nv_bfloat16><<<bw_grid(M * d), 256, 0, st>>>((const __nv_bfloat16*)dg, (const __nv_bfloat16*)pre, (__nv_bfloat16*)dpre, M, d);
+    const bool al16 = (((uintptr_t)dg | (uintptr_t)pre | (uintptr_t)dpre) & 15) == 0;
+    if (is_bf16 && al16 && d % 8 == 0)
+        glu_bwd_vec_kernel<<<bw_grid(M * (d / 8)), 256, 0, st>>>((const uint4*)dg, (const uint4*)pre, (uint4*)dpre, M, d / 8);
+    else if (is_bf16) glu_bwd_kernel<__nv_bfloat16><<<bw_grid(M * d), 256, 0, st>>>((const __nv_bfloat16*)dg, (const __nv_bfloat16*)pre, (__nv_bfloat16*)dpre, M, d);
     else glu_bwd_kernel<float><<<bw_grid(M * d), 256, 0, st>>>((const float*)dg, (const float*)pre, (float*)dpre, M, d);
     NSP_LAUNCH_OK();
     return NSP_OK;
@@ -396,7 +523,10 @@ extern "C" nsp_status nsp_relu_mask(int is_bf16, const void* dx, const void* a, 
     NSP_CHECK_ARG(dx && a && dz && n >= 0, "relu_mask: bad arguments");
     if (n == 0) return NSP_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if (is_bf16) relu_mask_kernel<__nv_bfloat16><<<bw_grid(n), 256, 0, st>>>((const __nv_bfloat16*)dx, (const __nv_bfloat16*)a, (__nv_bfloat16*)dz, n);
+    const bool al16 = (((uintptr_t)dx | (uintptr_t)a | (uintptr_t)dz) & 15) == 0;
+    if (is_bf16 && al16 && n % 8 == 0)
+        relu_mask_vec_kernel<<<bw_grid(n / 8), 256, 0, st>>>((const uint4*)dx, (const uint4*)a, (uint4*)dz, n / 8);
+    else if (is_bf16) relu_mask_kernel<__nv_bfloat16><<<bw_grid(n), 256, 0, st>>>((const __nv_bfloat16*)dx, (const __nv_bfloat16*)a, (__nv_bfloat16*)dz, n);
     else relu_mask_kernel<float><<<bw_grid(n), 256, 0, st>>>((const float*)dx, (const float*)a, (float*)dz, n);
     NSP_LAUNCH_OK();
     return NSP_OK;
@@ -414,6 +544,25 @@ extern "C" nsp_status nsp_maxpool2d_relu_bwd(int is_bf16, int dy_bf16, const voi
     else if (!dy_bf16)
         maxpool2d_relu_bwd_kernel<float, float><<<bw_grid(n), 256, 0, st>>>((const float*)a, (const float*)dy, (float*)dz, B, T, F, C, pool_t, pool_f, in_chmajor);
     else { set_error("maxpool2d_relu_bwd: fp32 activations with bf16 gradients are not instantiated"); return NSP_ERR_UNSUPPORTED; }
+    NSP_LAUNCH_OK();
+    return NSP_OK;
+}
+
+// act / GLU backward with the bias gradient fused (bf16 only): mode 0: dz[M,N] = dh * act'(z); mode 1: GLU, dh = dg [M,N/2],
+// z = pre [M,N], dz = dpre [M,N].  dbias fp32 [N] is ACCUMULATED.  N % 8 == 0 (mode 1: (N/2) % 8 == 0), dense rows.
+extern "C" nsp_status nsp_act_bwd_bias(int mode, int act, const void* dh, const void* z, void* dz, float* dbias, int M, int N,
+                                       void* stream) {
+    NSP_CHECK_ARG(dh && z && dz && dbias && M > 0 && N > 0, "act_bwd_bias: bad arguments");
+    NSP_CHECK_ARG((mode == 0 && N % 8 == 0) || (mode == 1 && N % 16 == 0), "act_bwd_bias: N=%d not vectorisable", N);
+    NSP_CHECK_ARG((((uintptr_t)dh | (uintptr_t)z | (uintptr_t)dz) & 15) == 0, "act_bwd_bias: unaligned pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int cblocks = ceil_div(N, 256);
+    int slices = ceil_div(M, 64);
+    const int cap = ceil_div(num_sms() * 4, cblocks);
+    if (slices > cap) slices = cap < 1 ? 1 : cap;
+    dim3 grid((unsigned)cblocks, (unsigned)slices);
+    if (mode == 0) act_bwd_bias_kernel<0><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dh, (const __nv_bfloat16*)z, (__nv_bfloat16*)dz, dbias, M, N, act);
+    else act_bwd_bias_kernel<1><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dh, (const __nv_bfloat16*)z, (__nv_bfloat16*)dz, dbias, M, N, act);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }

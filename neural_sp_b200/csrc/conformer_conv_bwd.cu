@@ -51,11 +51,27 @@ __global__ void __launch_bounds__(32 * NW) conv_bwd_norm_kernel(ConvBwdParams p)
     const T* xg = reinterpret_cast<const T*>(p.x) + (int64_t)b * p.T * p.ldx;
     {
         const int w_ = threadIdx.x >> 5, l_ = threadIdx.x & 31;
+        const bool vec = (sizeof(T) == 2) && (d % 8 == 0) && (p.ldx % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
         for (int r = w_; r < rows; r += NW) {
             const int t = t0 + r - p.left_pad;
             const bool in = (t >= 0 && t < p.T);
             float* trow = tile + (size_t)r * d;
-            for (int c = l_; c < d; c += 32) trow[c] = in ? cb_ld<T>(xg + (int64_t)t * p.ldx + c) : 0.f;
+            if (vec) {
+                for (int c8 = l_; c8 < d / 8; c8 += 32) {
+                    float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+                    if (in) {
+                        const uint4 raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(xg) + (int64_t)t * p.ldx + c8 * 8);
+                        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+                        const float2 a = __bfloat1622float2(h2[0]), b2 = __bfloat1622float2(h2[1]);
+                        const float2 c2 = __bfloat1622float2(h2[2]), d2 = __bfloat1622float2(h2[3]);
+                        lo = make_float4(a.x, a.y, b2.x, b2.y); hi = make_float4(c2.x, c2.y, d2.x, d2.y);
+                    }
+                    *reinterpret_cast<float4*>(trow + c8 * 8) = lo;
+                    *reinterpret_cast<float4*>(trow + c8 * 8 + 4) = hi;
+                }
+            } else {
+                for (int c = l_; c < d; c += 32) trow[c] = in ? cb_ld<T>(xg + (int64_t)t * p.ldx + c) : 0.f;
+            }
         }
         for (int e = threadIdx.x; e < k * d; e += NT) wT[e] = __ldg(p.w + e);
         for (int e = threadIdx.x; e < 2 * d; e += NT) red[e] = 0.f;
@@ -185,12 +201,43 @@ __global__ void __launch_bounds__(32 * K2_NW) conv_bwd_dw_kernel(ConvBwdParams p
     const int rpad = k - 1 - p.left_pad;
     const T* xg = reinterpret_cast<const T*>(p.x) + (int64_t)b * p.T * p.ldx;
     const T* zg = reinterpret_cast<const T*>(p.dz) + (int64_t)b * p.T * p.lddz;
-    for (int e = threadIdx.x; e < rows * K2_CH; e += 32 * K2_NW) {
-        const int c = e % K2_CH, r = e / K2_CH;
-        const int tx = t0 + r - p.left_pad, tz = t0 + r - rpad;
-        const bool cok = c0 + c < d;
-        xwin[e] = (cok && tx >= 0 && tx < p.T) ? cb_ld<T>(xg + (int64_t)tx * p.ldx + c0 + c) : 0.f;
-        zwin[e] = (cok && tz >= 0 && tz < p.T) ? cb_ld<T>(zg + (int64_t)tz * p.lddz + c0 + c) : 0.f;
+    const bool vec2 = (sizeof(T) == 2) && (d % 8 == 0) && (p.ldx % 8 == 0) && (p.lddz % 8 == 0) &&
+                      (((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.dz)) & 15) == 0);
+    if (vec2) {
+        for (int e = threadIdx.x; e < rows * (K2_CH / 8); e += 32 * K2_NW) {
+            const int c8 = e % (K2_CH / 8), r = e / (K2_CH / 8);
+            const int tx = t0 + r - p.left_pad, tz = t0 + r - rpad;
+            const bool cok = c0 + c8 * 8 < d;
+            float xv[8], zv[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { xv[k] = 0.f; zv[k] = 0.f; }
+            if (cok && tx >= 0 && tx < p.T) {
+                const uint4 raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(xg) + (int64_t)tx * p.ldx + c0 + c8 * 8);
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h2[k]); xv[2 * k] = f.x; xv[2 * k + 1] = f.y; }
+            }
+            if (cok && tz >= 0 && tz < p.T) {
+                const uint4 raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(zg) + (int64_t)tz * p.lddz + c0 + c8 * 8);
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h2[k]); zv[2 * k] = f.x; zv[2 * k + 1] = f.y; }
+            }
+            float* xd = xwin + (size_t)r * K2_CH + c8 * 8;
+            float* zd = zwin + (size_t)r * K2_CH + c8 * 8;
+            *reinterpret_cast<float4*>(xd) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+            *reinterpret_cast<float4*>(xd + 4) = make_float4(xv[4], xv[5], xv[6], xv[7]);
+            *reinterpret_cast<float4*>(zd) = make_float4(zv[0], zv[1], zv[2], zv[3]);
+            *reinterpret_cast<float4*>(zd + 4) = make_float4(zv[4], zv[5], zv[6], zv[7]);
+        }
+    } else {
+        for (int e = threadIdx.x; e < rows * K2_CH; e += 32 * K2_NW) {
+            const int c = e % K2_CH, r = e / K2_CH;
+            const int tx = t0 + r - p.left_pad, tz = t0 + r - rpad;
+            const bool cok = c0 + c < d;
+            xwin[e] = (cok && tx >= 0 && tx < p.T) ? cb_ld<T>(xg + (int64_t)tx * p.ldx + c0 + c) : 0.f;
+            zwin[e] = (cok && tz >= 0 && tz < p.T) ? cb_ld<T>(zg + (int64_t)tz * p.lddz + c0 + c) : 0.f;
+        }
     }
     for (int e = threadIdx.x; e < k * K2_CH; e += 32 * K2_NW) {
         const int c = e % K2_CH;

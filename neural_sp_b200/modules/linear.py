@@ -25,17 +25,22 @@ class _LinearFn(torch.autograd.Function):
         gy2 = gy.reshape(-1, gy.shape[-1]).float().contiguous()
         x2 = x.reshape(-1, x.shape[-1]).float()
         gx = gw = gb = None
+        from .. import autograd as ag
+        nb = weight.shape[0] if (ctx.has_bias and ctx.needs_input_grad[2]) else 0
+        flat = torch.zeros(weight.numel() + nb, dtype=torch.float32, device=weight.device)   # this node's all-reduce bucket
         if ctx.needs_input_grad[0]:
             # dX[M,K] = dY[M,N] @ W[N,K]  ->  GEMM with "weight" W^T [K,N]
             wt = prepared(ctx.module, "wT", prec, (weight,), build=lambda w: w.t().contiguous())
             gx = ops.linear(gy2, wt, None, prec=prec, out_dtype=torch.float32).reshape(x.shape)
         if ctx.needs_input_grad[1]:
             # dW[N,K] = dY^T[N,M] @ X[M,K] on the MN-major wgrad kernel (no transposed copies)
-            gw = torch.zeros(weight.shape, dtype=torch.float32, device=weight.device)
+            gw = flat[:weight.numel()].view(weight.shape)
             ops.linear_wgrad(gy2, x2, prec, gw)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = torch.zeros(gy2.shape[1], dtype=torch.float32, device=gy2.device)
+            gb = flat[weight.numel():]
             ops.colsum_acc(gy2, gb)
+        if ag._GRAD_SYNC is not None:
+            ag._GRAD_SYNC(flat)
         return gx, gw, gb, None, None
 
 

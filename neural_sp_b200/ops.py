@@ -3,6 +3,8 @@
 Each function takes CUDA tensors, allocates outputs/workspaces through torch's caching allocator on
 the current stream, and enqueues the CUDA kernels through ctypes.  No arithmetic happens in Python.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -521,7 +523,8 @@ def linear_wgrad(dy, x, prec, dw, alpha=1.0, accumulate=True):
     return dw
 
 
-def layernorm_bwd(dy, x, gamma, eps, dres=None, dgamma=None, dbeta=None, want_fp32=True, want_bf16=False, in_scale=1.0):
+def layernorm_bwd(dy, x, gamma, eps, dres=None, dgamma=None, dbeta=None, want_fp32=True, want_bf16=False, in_scale=1.0,
+                  dcol=None, dcol_alpha=1.0):
     """dx = dres + LN'(x).dy (nsp_layernorm_bwd); dgamma/dbeta fp32 [D] are accumulated.  Returns fp32 and/or bf16 dx."""
     _require_cuda(dy, x)
     D = x.shape[-1]
@@ -533,7 +536,7 @@ def layernorm_bwd(dy, x, gamma, eps, dres=None, dgamma=None, dbeta=None, want_fp
     dxb = torch.empty(M, D, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
     _run("nsp_layernorm_bwd", lib.nsp_layernorm_bwd, ptr(dy2), dy2.stride(0), ptr(x2), x2.stride(0), ptr(gamma), float(eps),
          float(in_scale), ptr(dr2), dr2.stride(0) if dr2 is not None else 0, ptr(dx), D, ptr(dxb), D,
-         ptr(dgamma), ptr(dbeta), M, D, current_stream_ptr(), nbytes=M * D * 12.0)
+         ptr(dgamma), ptr(dbeta), ptr(dcol), float(dcol_alpha), M, D, current_stream_ptr(), nbytes=M * D * 12.0)
     outs = tuple(t.reshape(x.shape) for t in (dx, dxb) if t is not None)
     return outs[0] if len(outs) == 1 else outs
 
@@ -546,6 +549,18 @@ def act_bwd(dh, z, act):
     dz = torch.empty_like(dh)
     _run("nsp_act_bwd", lib.nsp_act_bwd, int(dh.dtype == torch.bfloat16), ACT[act], ptr(dh), ptr(z), ptr(dz), dh.numel(),
          current_stream_ptr())
+    return dz
+
+
+def act_bwd_bias(dh, z, act, dbias, glu=False):
+    """act_bwd / glu_bwd with the bias gradient fused (nsp_act_bwd_bias): dbias fp32 [N] += column sums of the result.
+    bf16, vectorisable widths only -- callers fall back to act_bwd / glu_bwd + colsum_acc otherwise."""
+    _require_cuda(dh, z, dbias)
+    N = z.shape[-1]
+    dh, z = dh.contiguous(), z.contiguous()
+    dz = torch.empty_like(z)
+    _run("nsp_act_bwd_bias", lib.nsp_act_bwd_bias, int(glu), 0 if glu else ACT[act], ptr(dh), ptr(z), ptr(dz), ptr(dbias),
+         z.numel() // N, N, current_stream_ptr())
     return dz
 
 
@@ -642,6 +657,8 @@ def relpos_attention_bwd(q, k, v, klens, n_heads, out, dout, r=None, u_bias=None
     if r is not None:
         r = r.reshape(-1, D) if r.dim() == 3 else r
     rlen = r.shape[0] if r is not None else 0
+    if os.environ.get("NSP_DISABLE_ATTN_BWD_TC"):      # debugging switch: force the CUDA-core backward kernels
+        stats = None
     dqkv = torch.empty(B, Tq, 3 * D, dtype=q.dtype, device=q.device)
     ws_bytes = lib.nsp_relpos_attention_bwd_workspace_bytes(B, n_heads, Tq, rlen, int(clamp_len), int(r is not None))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device)

@@ -82,7 +82,10 @@ def test_layernorm_bwd(D):
     y = F.layer_norm(x, (D,), gamma, beta, 1e-12)
     y.backward(dy)
     dg, db = torch.zeros(D, device=DEV), torch.zeros(D, device=DEV)
-    dx, dxb = ops.layernorm_bwd(dy, x.detach(), gamma.detach(), 1e-12, dres=dres, dgamma=dg, dbeta=db, want_bf16=True)
+    dcol = torch.ones(D, device=DEV)
+    dx, dxb = ops.layernorm_bwd(dy, x.detach(), gamma.detach(), 1e-12, dres=dres, dgamma=dg, dbeta=db, want_bf16=True,
+                                dcol=dcol, dcol_alpha=0.5)
+    assert rel_err(dcol, 1 + 0.5 * (x.grad + dres).sum(0)) <= 2e-5          # fused bias gradient of the consuming branch
     assert rel_err(dx, x.grad + dres) <= 2e-5
     assert rel_err(dxb.float(), x.grad + dres) <= 1e-2
     assert rel_err(dg, gamma.grad) <= 2e-5 and rel_err(db, beta.grad) <= 2e-5
@@ -103,6 +106,13 @@ def test_act_and_glu_bwd(act):
     dg = torch.randn(100, 64, device=DEV)
     F.glu(pre, dim=-1).backward(dg)
     assert rel_err(ops.glu_bwd(dg, pre.detach()), pre.grad) <= 1e-5
+    # fused bias-gradient variants (bf16): result and its column sums
+    db = torch.zeros(96, device=DEV)
+    dzb = ops.act_bwd_bias(dh.bfloat16(), z.detach().bfloat16(), act, db)
+    assert rel_err(dzb.float(), z.grad) <= 3e-2 and rel_err(db, z.grad.sum(0)) <= 2e-2
+    dbg = torch.zeros(128, device=DEV)
+    dpb = ops.act_bwd_bias(dg.bfloat16(), pre.detach().bfloat16(), None, dbg, glu=True)
+    assert rel_err(dpb.float(), pre.grad) <= 3e-2 and rel_err(dbg, pre.grad.sum(0)) <= 2e-2
 
 
 def test_colsum_pool_relu():
