@@ -129,8 +129,10 @@ def cpu_reference_arm(w, steps, warmup, sample_B=1, sample_T=500, train=True):
     from oracle import encoder_oracle, ctc_oracle  # noqa: F401  (checker / baseline only)
     from neural_sp_b200.encoders.conformer import ConformerEncoder
     from neural_sp_b200.encoders.conv import ConvEncoder
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except Exception:
+        avail = os.cpu_count() or 1
     torch.manual_seed(0)
     a = enc_args(w)
     a["frontend_conv"] = ConvEncoder(**conv_args(w))
@@ -171,16 +173,27 @@ def cpu_reference_arm(w, steps, warmup, sample_B=1, sample_T=500, train=True):
         (loss * 0.9 + kl * 0.1).backward()
         return float(loss)
 
-    for _ in range(warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = (time.perf_counter() - t0) / steps
+    # torch's CPU kernels stop scaling (and with many tiny ops get much slower) long before 128 threads: time the sample
+    # at 8, 16, 32, ... up to every available core and report the BEST thread count, i.e. the reference at its fastest.
+    cands = sorted({min(avail, c) for c in (8, 16, 32, 64, 128, avail)})
+    best = None
+    for nthr in cands:
+        torch.set_num_threads(nthr)
+        step()                                     # warm-up at this thread count (thread pool, oneDNN primitives)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        dt = (time.perf_counter() - t0) / steps
+        if best is None or dt < best[0]:
+            best = (dt, nthr)
+        elif dt > 1.2 * best[0]:
+            break                                   # past the knee: more threads only hurt
+    dt, cores = best
     frames = sum(xlens)
     return dict(value=frames / dt, ms_per_step=dt * 1e3, cores=cores,
-                sample="B=%d T=%d of workload, %d %s steps (oracle port of the reference's torch-CPU path)" %
-                       (sample_B, w["T"], steps, "training (fwd+loss+bwd)" if train else "fwd+loss"))
+                sample="B=%d T=%d of workload, %d %s step(s) after 1 warm-up, best of thread counts %s on %d available cores "
+                       "(oracle port of the reference's torch-CPU path)" %
+                       (sample_B, w["T"], steps, "training (fwd+loss+bwd)" if train else "fwd+loss", cands, avail))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -198,6 +211,9 @@ def main():
                     help="train: fwd + loss + bwd + grad all-reduce + optimizer; fwd: encoder fwd + CTC fwd/bwd + head bwd")
     ap.add_argument("--optimizer", default="adam", choices=["adam", "none"])
     ap.add_argument("--allreduce", default="bucketed", choices=["bucketed", "single"])
+    ap.add_argument("--ncu-step", action="store_true",
+                    help="for `ncu --profile-from-start off`: warm up, run ONE eager step between cudaProfilerStart/Stop, exit")
+    ap.add_argument("--shape-profile", default="", help="write per-shape GEMM timings of the profiled steps to this JSON file")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -265,6 +281,8 @@ def main():
     if args.step == "train" and args.optimizer == "adam":
         opt = torch.optim.Adam(all_params, lr=1e-5, fused=True, capturable=True)
 
+    works = []                             # in-flight bucket all-reduces of the current step (bucketed mode, N > 1)
+
     def step_fwd(x_dev):
         out = enc(x_dev, xlens_t.clone(), task='ys')
         eouts = out['ys']['xs'].detach().requires_grad_(True)
@@ -273,15 +291,19 @@ def main():
         loss, _ = ctc(eouts, out['ys']['xlens'], ys)
         loss.backward()
         if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in head_params] + [eouts.grad.reshape(-1)[:0]])
-            dist.all_reduce(flat)          # the single gradient all-reduce of the step (sum; DDP semantics)
+            if works:                      # bucketed hook installed: the head layers' buckets are already in flight
+                for wk in works:
+                    wk.wait()
+                works.clear()
+            else:
+                flat = torch.cat([p.grad.reshape(-1) for p in head_params] + [eouts.grad.reshape(-1)[:0]])
+                dist.all_reduce(flat)      # the single gradient all-reduce of the step (sum; DDP semantics)
         return loss
 
     # Gradient exchange (N > 1): the reference's DDP semantics (sum of per-rank mean losses, train.py:423-424).
     #   bucketed (default): every autograd node (encoder block, front-end, head layer) hands its flat fp32 gradient bucket
     #     to NCCL as soon as its backward is enqueued -> the all-reduce overlaps the rest of the backward pass;
     #   single: one all-reduce of the concatenated gradients after the backward pass.
-    works = []
     if world > 1 and args.step == "train" and args.allreduce == "bucketed":
         from neural_sp_b200 import autograd as ag
         ag.set_grad_sync(lambda flat: works.append(dist.all_reduce(flat, async_op=True)))
@@ -389,6 +411,15 @@ def main():
             barrier()
         return dict(ms_dev=ms_dev, ms_e2e=ms_e2e, launches_per_step=lps, graph=graph is not None, graph_error=graph_error)
 
+    if args.ncu_step:
+        for _ in range(3):
+            step(xs_dev)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step(xs_dev)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     if rank == 0:
         sampler.start()
     main = measure(step)
@@ -404,14 +435,32 @@ def main():
 
     # ---- per-kernel-class timing for the roofline (eager, CUDA events around every library call) ----
     # The host must run AHEAD of the device here, otherwise each event pair also brackets the idle gap while the
-    # next ctypes launch is prepared: a 60 ms spin kernel (torch utility, untimed) gives the host its head start.
+    # next ctypes launch is prepared: a spin kernel (torch utility, untimed) of 1.5x the host's enqueue time of one step
+    # gives the host its head start, so the events bracket back-to-back kernels.
     nprof = 3
+    torch.cuda.synchronize()
+    ops.SHAPE_TAGS = bool(args.shape_profile)
+    t_host = time.perf_counter()
+    step(xs_dev)                                   # host time to enqueue one eager step (no sync): the head start needed
+    t_host = time.perf_counter() - t_host
     torch.cuda.synchronize()
     ops.profile_start()
     for _ in range(nprof):
-        torch.cuda._sleep(int(0.06 * 1.9e9))
+        torch.cuda._sleep(int((1.5 * t_host + 0.05) * 1.9e9))
         step(xs_dev)
     prof = ops.profile_stop()
+    if args.shape_profile:                      # fold the per-shape records back into the per-kernel classes
+        detail = {k: dict(ms=v["ms"] / nprof, calls=v["calls"] / nprof,
+                          tflops=(v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 and v["flops"] else None))
+                  for k, v in prof.items()}
+        if rank == 0:
+            json.dump(detail, open(args.shape_profile, "w"), indent=1, sort_keys=True)
+        folded = {}
+        for k, v in prof.items():
+            f = folded.setdefault(k.split(":")[0], {"ms": 0.0, "calls": 0, "flops": 0.0, "bytes": 0.0})
+            for kk in f:
+                f[kk] += v[kk]
+        prof = folded
 
     t = torch.tensor([ms_dev, ms_e2e, fwd["ms_dev"] if fwd else 0.0], dtype=torch.float64, device=dev)
     if world > 1:

@@ -22,7 +22,7 @@ namespace {
 
 constexpr int QT = 128, KT = 128, DK = 64;
 constexpr int TILE = 128 * 128;                       // bytes of a [128 x 64] bf16 tile
-constexpr int NCW = 8;                                // compute warps (two per TMEM lane quadrant)
+constexpr int NCW = 16;                               // compute warps (four per TMEM lane quadrant: 32 query columns each)
 constexpr int NTHREADS = 64 + 32 * NCW;
 
 struct BwdTcArgs {
@@ -202,11 +202,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_bwd_tc_kernel(const __grid_c
         }
     } else {
         const int q = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int quarter = (warp - 2) >> 2;                 // which 32 of the 128 query columns (16 of the 64 dq / dk / dv columns)
         const int row = q * 32 + lane;                       // key row of S^T / dP^T, query row of BD / dQ_t
         const int j = j0 + row;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        const int ctid = threadIdx.x - 64;                   // 0..255
+        const int ctid = threadIdx.x - 64;                   // 0..511
         auto cbar = [&]() { asm volatile("bar.sync 1, %0;" :: "n"(32 * NCW) : "memory"); };
         const int clamp = a.clamp;
         const int64_t bh = (int64_t)b * a.H + h;
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_bwd_tc_kernel(const __grid_c
             }
             bwait(s_full, ph, 5);
             tc::tc_fence_after();
-            if (a.has_rel && half == 0) {
+            if (a.has_rel && quarter == 0) {
                 uint32_t r16[16];
                 tmem_ld16(tm_BD + lane_addr, r16);
                 tc::tmem_ld_wait();
@@ -233,17 +233,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_bwd_tc_kernel(const __grid_c
                 for (int c = 0; c < 16; ++c) sBD[row * 17 + c] = __uint_as_float(r16[c]);
             }
             cbar();
-            // ---- P^T and dS^T of this thread's key row for its 64 query columns ----
+            // ---- P^T and dS^T of this thread's key row for its 32 query columns (two 16-column halves) ----
 #pragma unroll 1
-            for (int c = 0; c < 64; c += 32) {
-                uint32_t rs[32], rp[32];
-                tc::tmem_ld_32x32(tm_ST + lane_addr + (uint32_t)(half * 64 + c), rs);
-                tc::tmem_ld_32x32(tm_DP + lane_addr + (uint32_t)(half * 64 + c), rp);
+            for (int c = 0; c < 32; c += 16) {
+                uint32_t rs[16], rp[16];
+                tmem_ld16(tm_ST + lane_addr + (uint32_t)(quarter * 32 + c), rs);
+                tmem_ld16(tm_DP + lane_addr + (uint32_t)(quarter * 32 + c), rp);
                 tc::tmem_ld_wait();
-                uint32_t pk[16], dk_[16];
-                const int qc0 = half * 64 + c;                // first query column (tile-local) of this chunk
+                uint32_t pk[8], dk_[8];
+                const int qc0 = quarter * 32 + c;             // first query column (tile-local) of this half chunk
 #pragma unroll
-                for (int e = 0; e < 32; e += 2) {
+                for (int e = 0; e < 16; e += 2) {
                     float pv[2], dv[2];
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
@@ -269,11 +269,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_bwd_tc_kernel(const __grid_c
                     pk[e >> 1] = *reinterpret_cast<uint32_t*>(&pb);
                     dk_[e >> 1] = *reinterpret_cast<uint32_t*>(&db);
                 }
-                uint8_t* prow = sPT + half * TILE + row * 128;
-                uint8_t* drow = sDS + half * TILE + row * 128;
+                // 128-byte rows hold 64 queries: half tile = quarter >> 1, 16-byte unit = (quarter & 1) * 4 + c / 8 + u
+                uint8_t* prow = sPT + (quarter >> 1) * TILE + row * 128;
+                uint8_t* drow = sDS + (quarter >> 1) * TILE + row * 128;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int unit = ((c & 32) >> 3) + u;
+                for (int u = 0; u < 2; ++u) {
+                    const int unit = (quarter & 1) * 4 + (c >> 3) + u;
                     const int off = (unit ^ (row & 7)) << 4;
                     *reinterpret_cast<uint4*>(prow + off) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
                     *reinterpret_cast<uint4*>(drow + off) = make_uint4(dk_[4 * u], dk_[4 * u + 1], dk_[4 * u + 2], dk_[4 * u + 3]);
@@ -286,14 +287,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_bwd_tc_kernel(const __grid_c
             bwait(o_full, ph, 6);
             tc::tc_fence_after();
             {
-                uint32_t r[32];
-                tc::tmem_ld_32x32(tm_DQ + lane_addr + (uint32_t)(half * 32), r);
+                uint32_t r[16];
+                tmem_ld16(tm_DQ + lane_addr + (uint32_t)(quarter * 16), r);
                 tc::tmem_ld_wait();
                 const int i = i0 + row;
                 if (i < a.T) {
-                    float* dst = a.dq_acc + ((int64_t)b * a.T + i) * ((int64_t)a.H * DK) + h * DK + half * 32;
+                    float* dst = a.dq_acc + ((int64_t)b * a.T + i) * ((int64_t)a.H * DK) + h * DK + quarter * 16;
 #pragma unroll
-                    for (int e = 0; e < 32; e += 4)
+                    for (int e = 0; e < 16; e += 4)
                         red_add_v4(dst + e, __uint_as_float(r[e]), __uint_as_float(r[e + 1]), __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
                 }
             }
@@ -301,41 +302,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_bwd_tc_kernel(const __grid_c
         }
         // ---- dK, dV of this key tile (complete after the last o_full) ----
         // tcgen05.ld is warp-collective (.sync.aligned): issue it from the whole warp, guard only the stores by `jin`
-        uint32_t rv[32], rk[32];
+        uint32_t rv[16], rk[16];
         if (ntiles > 0) {
-            tc::tmem_ld_32x32(tm_DV + lane_addr + (uint32_t)(half * 32), rv);
-            tc::tmem_ld_32x32(tm_DK + lane_addr + (uint32_t)(half * 32), rk);
+            tmem_ld16(tm_DV + lane_addr + (uint32_t)(quarter * 16), rv);
+            tmem_ld16(tm_DK + lane_addr + (uint32_t)(quarter * 16), rk);
             tc::tmem_ld_wait();
         }
-        if (ntiles > 0 && jin) {
-            __nv_bfloat16* ov = a.dv + ((int64_t)b * a.T + j) * a.lddv + h * DK + half * 32;
-            __nv_bfloat16* ok = a.dk + ((int64_t)b * a.T + j) * a.lddk + h * DK + half * 32;
+        if (jin) {
+            __nv_bfloat16* ov = a.dv + ((int64_t)b * a.T + j) * a.lddv + h * DK + quarter * 16;
+            __nv_bfloat16* ok = a.dk + ((int64_t)b * a.T + j) * a.lddk + h * DK + quarter * 16;
 #pragma unroll
-            for (int c = 0; c < 32; c += 8) {
-                uint4 pv, pkk;
-                __nv_bfloat162 t0, t1, t2, t3;
-                t0 = __floats2bfloat162_rn(__uint_as_float(rv[c]), __uint_as_float(rv[c + 1]));
-                t1 = __floats2bfloat162_rn(__uint_as_float(rv[c + 2]), __uint_as_float(rv[c + 3]));
-                t2 = __floats2bfloat162_rn(__uint_as_float(rv[c + 4]), __uint_as_float(rv[c + 5]));
-                t3 = __floats2bfloat162_rn(__uint_as_float(rv[c + 6]), __uint_as_float(rv[c + 7]));
-                pv.x = *reinterpret_cast<uint32_t*>(&t0); pv.y = *reinterpret_cast<uint32_t*>(&t1);
-                pv.z = *reinterpret_cast<uint32_t*>(&t2); pv.w = *reinterpret_cast<uint32_t*>(&t3);
-                t0 = __floats2bfloat162_rn(__uint_as_float(rk[c]), __uint_as_float(rk[c + 1]));
-                t1 = __floats2bfloat162_rn(__uint_as_float(rk[c + 2]), __uint_as_float(rk[c + 3]));
-                t2 = __floats2bfloat162_rn(__uint_as_float(rk[c + 4]), __uint_as_float(rk[c + 5]));
-                t3 = __floats2bfloat162_rn(__uint_as_float(rk[c + 6]), __uint_as_float(rk[c + 7]));
-                pkk.x = *reinterpret_cast<uint32_t*>(&t0); pkk.y = *reinterpret_cast<uint32_t*>(&t1);
-                pkk.z = *reinterpret_cast<uint32_t*>(&t2); pkk.w = *reinterpret_cast<uint32_t*>(&t3);
+            for (int c = 0; c < 16; c += 8) {
+                uint4 pv = make_uint4(0, 0, 0, 0), pkk = make_uint4(0, 0, 0, 0);     // no query tile sees this key tile: zeros
+                if (ntiles > 0) {
+                    __nv_bfloat162 t0, t1, t2, t3;
+                    t0 = __floats2bfloat162_rn(__uint_as_float(rv[c]), __uint_as_float(rv[c + 1]));
+                    t1 = __floats2bfloat162_rn(__uint_as_float(rv[c + 2]), __uint_as_float(rv[c + 3]));
+                    t2 = __floats2bfloat162_rn(__uint_as_float(rv[c + 4]), __uint_as_float(rv[c + 5]));
+                    t3 = __floats2bfloat162_rn(__uint_as_float(rv[c + 6]), __uint_as_float(rv[c + 7]));
+                    pv.x = *reinterpret_cast<uint32_t*>(&t0); pv.y = *reinterpret_cast<uint32_t*>(&t1);
+                    pv.z = *reinterpret_cast<uint32_t*>(&t2); pv.w = *reinterpret_cast<uint32_t*>(&t3);
+                    t0 = __floats2bfloat162_rn(__uint_as_float(rk[c]), __uint_as_float(rk[c + 1]));
+                    t1 = __floats2bfloat162_rn(__uint_as_float(rk[c + 2]), __uint_as_float(rk[c + 3]));
+                    t2 = __floats2bfloat162_rn(__uint_as_float(rk[c + 4]), __uint_as_float(rk[c + 5]));
+                    t3 = __floats2bfloat162_rn(__uint_as_float(rk[c + 6]), __uint_as_float(rk[c + 7]));
+                    pkk.x = *reinterpret_cast<uint32_t*>(&t0); pkk.y = *reinterpret_cast<uint32_t*>(&t1);
+                    pkk.z = *reinterpret_cast<uint32_t*>(&t2); pkk.w = *reinterpret_cast<uint32_t*>(&t3);
+                }
                 *reinterpret_cast<uint4*>(ov + c) = pv;
                 *reinterpret_cast<uint4*>(ok + c) = pkk;
-            }
-        } else if (jin) {                                     // no query tile sees this key tile: zero gradients
-            __nv_bfloat16* ov = a.dv + ((int64_t)b * a.T + j) * a.lddv + h * DK + half * 32;
-            __nv_bfloat16* ok = a.dk + ((int64_t)b * a.T + j) * a.lddk + h * DK + half * 32;
-#pragma unroll
-            for (int c = 0; c < 32; c += 8) {
-                *reinterpret_cast<uint4*>(ov + c) = make_uint4(0, 0, 0, 0);
-                *reinterpret_cast<uint4*>(ok + c) = make_uint4(0, 0, 0, 0);
             }
         }
     }
@@ -376,7 +371,7 @@ __global__ void __launch_bounds__(256) attn_bwd_finish_kernel(const float* __res
                                                               const __nv_bfloat16* __restrict__ q, int64_t ldq,
                                                               const __nv_bfloat16* __restrict__ r, int64_t ldr,
                                                               __nv_bfloat16* __restrict__ dq, int64_t lddq,
-                                                              float* __restrict__ dr, int64_t lddr,
+                                                              float* __restrict__ dr_part,
                                                               int B, int H, int T, int has_rel, int clamp) {
     __shared__ float sdr[16][DK];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -427,15 +422,28 @@ __global__ void __launch_bounds__(256) attn_bwd_finish_kernel(const float* __res
         }
         *reinterpret_cast<__nv_bfloat162*>(dq + bt * lddq + h * DK + lane * 2) = __floats2bfloat162_rn(o0, o1);
     }
-    if (has_rel && dr) {
+    if (has_rel && dr_part) {
 #pragma unroll
         for (int d = 0; d < 16; ++d) {
             if (d <= clamp) { atomicAdd(&sdr[d][lane * 2], dracc[d][0]); atomicAdd(&sdr[d][lane * 2 + 1], dracc[d][1]); }
         }
         __syncthreads();
-        for (int e = threadIdx.x; e < (clamp + 1) * DK; e += 256)
-            atomicAdd(dr + (int64_t)(e / DK) * lddr + h * DK + (e % DK), sdr[e / DK][e % DK]);
+        // this CTA's partial [16][64] goes to scratch (plain stores); attn_bwd_dr_reduce_kernel sums the partials of a head:
+        // atomics straight into dr would put B*T/64 adds on each of only H*(clamp+1)*64 addresses
+        float* dst = dr_part + (int64_t)blockIdx.x * 16 * DK;
+        for (int e = threadIdx.x; e < 16 * DK; e += 256) dst[e] = (&sdr[0][0])[e];
     }
+}
+
+// dr[d][h*64 + c] += sum over the (b, row block) partials of head h; grid = H * (clamp + 1), 64 threads
+__global__ void __launch_bounds__(64) attn_bwd_dr_reduce_kernel(const float* __restrict__ dr_part, float* __restrict__ dr,
+                                                                int64_t lddr, int B, int H, int rblocks) {
+    const int h = blockIdx.x % H, d = blockIdx.x / H, c = threadIdx.x;
+    float s = 0.f;
+    for (int b = 0; b < B; ++b)
+        for (int rb = 0; rb < rblocks; ++rb)
+            s += dr_part[((((int64_t)b * H + h) * rblocks + rb) * 16 + d) * DK + c];
+    atomicAdd(dr + (int64_t)d * lddr + h * DK + c, s);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -463,7 +471,8 @@ bool bwd_map3(EncodeTiledFn enc, CUtensorMap* m, const void* base, int64_t ld, i
 bool get_tma_encode(void** fn);
 
 size_t attention_bwd_tc_workspace_bytes(int B, int H, int T) {
-    return sizeof(float) * ((size_t)B * T * H * DK + (size_t)B * H * T * 16 + (size_t)B * H * T);
+    return sizeof(float) * ((size_t)B * T * H * DK + (size_t)B * H * T * 16 + (size_t)B * H * T +
+                            (size_t)B * H * ceil_div(T, 64) * 16 * DK);
 }
 
 // Returns NSP_ERR_UNSUPPORTED (nothing launched) when the shape is outside the tensor-core envelope.
@@ -525,11 +534,17 @@ nsp_status attention_bwd_tc_dispatch(const void* q, int64_t ldq, const void* k, 
     const int ktiles = ceil_div(T, KT);
     attn_bwd_tc_kernel<<<(unsigned)(B * H * ktiles), NTHREADS, smem, st>>>(mq, mk, mv, mdo, mr, a);
     NSP_LAUNCH_OK();
-    attn_bwd_finish_kernel<<<(unsigned)(B * H * ceil_div(T, 64)), 256, 0, st>>>(dq_acc, w, (const __nv_bfloat16*)q, ldq,
-                                                                               (const __nv_bfloat16*)r, ldr,
-                                                                               (__nv_bfloat16*)dq, lddq, dr, lddr,
-                                                                               B, H, T, a.has_rel, a.clamp);
+    float* dr_part = dsum + (size_t)B * H * T;
+    const int rblocks = ceil_div(T, 64);
+    attn_bwd_finish_kernel<<<(unsigned)(B * H * rblocks), 256, 0, st>>>(dq_acc, w, (const __nv_bfloat16*)q, ldq,
+                                                                      (const __nv_bfloat16*)r, ldr,
+                                                                      (__nv_bfloat16*)dq, lddq, (a.has_rel && dr) ? dr_part : nullptr,
+                                                                      B, H, T, a.has_rel, a.clamp);
     NSP_LAUNCH_OK();
+    if (a.has_rel && dr) {
+        attn_bwd_dr_reduce_kernel<<<(unsigned)(H * (a.clamp + 1)), 64, 0, st>>>(dr_part, dr, lddr, B, H, rblocks);
+        NSP_LAUNCH_OK();
+    }
     return NSP_OK;
 }
 

@@ -419,6 +419,42 @@ __global__ void __launch_bounds__(256) maxpool2d_relu_bwd_kernel(const T* __rest
     }
 }
 
+// bf16, channels-last dy, C % 8 == 0: one thread = 8 channels of one pooling window (16-byte accesses)
+__global__ void __launch_bounds__(256) maxpool2d_relu_bwd_vec_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ dy,
+                                                                     __nv_bfloat16* __restrict__ dz, int B, int Tn, int F, int C,
+                                                                     int pt, int pf) {
+    const int To = (Tn + pt - 1) / pt, Fo = (F + pf - 1) / pf, C8 = C / 8;
+    const int64_t n = (int64_t)B * To * Fo * C8;
+    for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < n; e += (int64_t)gridDim.x * 256) {
+        const int c8 = (int)(e % C8);
+        int64_t r = e / C8;
+        const int fo = (int)(r % Fo); r /= Fo;
+        const int to = (int)(r % To), b = (int)(r / To);
+        const int t0 = to * pt, t1 = min(Tn, t0 + pt), f0 = fo * pf, f1 = min(F, f0 + pf);
+        float best[8], g[8];
+        int arg[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { best[k] = -INFINITY; arg[k] = 0; }
+        int w = 0;
+        for (int t = t0; t < t1; ++t)
+            for (int f = f0; f < f1; ++f, ++w) {
+                float v[8];
+                unpack8(*reinterpret_cast<const uint4*>(a + (((int64_t)b * Tn + t) * F + f) * C + c8 * 8), v);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) if (v[k] > best[k]) { best[k] = v[k]; arg[k] = w; }
+            }
+        unpack8(*reinterpret_cast<const uint4*>(dy + (((int64_t)b * To + to) * Fo + fo) * C + c8 * 8), g);
+        w = 0;
+        for (int t = t0; t < t1; ++t)
+            for (int f = f0; f < f1; ++f, ++w) {
+                float o[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] = (arg[k] == w && best[k] > 0.f) ? g[k] : 0.f;
+                *reinterpret_cast<uint4*>(dz + (((int64_t)b * Tn + t) * F + f) * C + c8 * 8) = pack8(o);
+            }
+    }
+}
+
 unsigned bw_grid(int64_t n) {
     int64_t b = ceil_div64(n, 256);
     int64_t cap = (int64_t)num_sms() * 16;
@@ -537,7 +573,9 @@ extern "C" nsp_status nsp_maxpool2d_relu_bwd(int is_bf16, int dy_bf16, const voi
     NSP_CHECK_ARG(a && dy && dz && B > 0 && T > 0 && F > 0 && C > 0 && pool_t >= 1 && pool_f >= 1, "maxpool2d_relu_bwd: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n = (int64_t)B * ceil_div(T, pool_t) * ceil_div(F, pool_f) * C;
-    if (is_bf16 && dy_bf16)
+    if (is_bf16 && dy_bf16 && !in_chmajor && C % 8 == 0 && (((uintptr_t)a | (uintptr_t)dy | (uintptr_t)dz) & 15) == 0)
+        maxpool2d_relu_bwd_vec_kernel<<<bw_grid(n / 8), 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dz, B, T, F, C, pool_t, pool_f);
+    else if (is_bf16 && dy_bf16)
         maxpool2d_relu_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<bw_grid(n), 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dz, B, T, F, C, pool_t, pool_f, in_chmajor);
     else if (is_bf16)
         maxpool2d_relu_bwd_kernel<__nv_bfloat16, float><<<bw_grid(n), 256, 0, st>>>((const __nv_bfloat16*)a, (const float*)dy, (__nv_bfloat16*)dz, B, T, F, C, pool_t, pool_f, in_chmajor);

@@ -100,6 +100,50 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(ConvWgradParams p) {
     }
 }
 
+// C_in = 1 (the raw feature map [B,T,F]): HBM-bound on dz.  One CTA walks frame rows (b, t); the three feature rows
+// t-1, t, t+1 sit in shared memory; warp w takes bins f = w, w+8, ...; lane = output channel: one coalesced 64-byte dz
+// read per position, nine broadcast taps, nine FMAs.  Partials stay in registers across all rows of the CTA.
+template <typename TZ>
+__global__ void __launch_bounds__(256) conv3x3_wgrad_c1_kernel(const float* __restrict__ x, const TZ* __restrict__ dz,
+                                                               float* __restrict__ dw, float* __restrict__ dbias,
+                                                               int B, int T, int F) {
+    extern __shared__ float xs[];                 // [3][F + 2]
+    __shared__ float red[10][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Fp = F + 2;
+    float acc[9], accb = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+    const int64_t nrows = (int64_t)B * T;
+    for (int64_t row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int t = (int)(row % T);
+        const int64_t b = row / T;
+        __syncthreads();
+        for (int e = threadIdx.x; e < 3 * Fp; e += 256) {
+            const int ky = e / Fp, ff = e % Fp;
+            const int tt = t + ky - 1, f = ff - 1;
+            xs[e] = (tt >= 0 && tt < T && f >= 0 && f < F) ? __ldg(x + ((int64_t)b * T + tt) * F + f) : 0.f;
+        }
+        __syncthreads();
+        const TZ* zr = dz + row * (int64_t)F * 32;
+        for (int f = warp; f < F; f += 8) {
+            const float zv = fb_ld<TZ>(zr + (int64_t)f * 32 + lane);
+            accb += zv;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) acc[k] = fmaf(zv, xs[(k / 3) * Fp + f + (k % 3)], acc[k]);
+        }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 10 * 32; e += 256) (&red[0][0])[e] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 9; ++k) atomicAdd(&red[k][lane], acc[k]);
+    atomicAdd(&red[9][lane], accb);
+    __syncthreads();
+    for (int e = threadIdx.x; e < 9 * 32; e += 256) atomicAdd(dw + (int64_t)(e % 32) * 9 + e / 32, red[e / 32][e % 32]);   // dw[co][0][tap]
+    if (threadIdx.x < 32 && dbias) atomicAdd(dbias + threadIdx.x, red[9][threadIdx.x]);
+}
+
 }  // namespace
 }  // namespace nsp
 
@@ -111,6 +155,15 @@ extern "C" nsp_status nsp_conv3x3_wgrad(int a_bf16, int dz_bf16, const void* a, 
     NSP_CHECK_ARG(B > 0 && T > 0 && F > 0 && CI > 0 && CO > 0, "conv3x3_wgrad: bad shape");
     NSP_CHECK_ARG(CO % 4 == 0 && CI * (CO / 4) <= 256 && 256 % (CI * (CO / 4)) == 0,
                   "conv3x3_wgrad: CI=%d CO=%d unsupported (CI*CO/4 must divide 256)", CI, CO);
+    if (CI == 1 && CO == 32 && !a_bf16) {           // first layer: streaming kernel ([B,T,1,F] and [B,T,F,1] coincide)
+        int grid1 = 4 * num_sms();
+        if ((int64_t)B * T < grid1) grid1 = B * T;
+        const size_t sm1 = sizeof(float) * 3 * (size_t)(F + 2);
+        if (dz_bf16) conv3x3_wgrad_c1_kernel<__nv_bfloat16><<<grid1, 256, sm1, (cudaStream_t)stream>>>((const float*)a, (const __nv_bfloat16*)dz, dw, dbias, B, T, F);
+        else conv3x3_wgrad_c1_kernel<float><<<grid1, 256, sm1, (cudaStream_t)stream>>>((const float*)a, (const float*)dz, dw, dbias, B, T, F);
+        NSP_LAUNCH_OK();
+        return NSP_OK;
+    }
     ConvWgradParams p;
     p.a = a; p.in_chmajor = in_chmajor; p.dz = dz; p.dw = dw; p.dbias = dbias; p.B = B; p.T = T; p.F = F; p.CI = CI; p.CO = CO;
     const size_t smem = sizeof(float) * ((size_t)(WTH + 2) * (WTW + 2) * (CI + 1) + (size_t)WTH * WTW * CO);

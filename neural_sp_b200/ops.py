@@ -34,12 +34,17 @@ def profile_stop():
     return out
 
 
-def _run(name, fn, *args, flops=0, nbytes=0, tag=None):
+SHAPE_TAGS = False    # bench.py --shape-profile: key the GEMM records by shape
+
+
+def _run(name, fn, *args, flops=0, nbytes=0, tag=None, shape=None):
     global LAUNCHES
     LAUNCHES += KERNELS_PER_CALL.get(name, 1)
     if PROFILE is None:
         return check(fn(*args), name)
     key = tag or name
+    if SHAPE_TAGS and shape is not None:
+        key = "%s:%s" % (key, "x".join(str(v) for v in shape))
     rec = PROFILE.setdefault(key, {"ev": [], "flops": 0, "bytes": 0})
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
@@ -213,7 +218,7 @@ def linear(x, w_prepared, bias=None, prec="bf16", act=None, glu=False, residual=
          res2d.stride(0) if res2d is not None else 0, float(alpha),
          ptr(out2d), out2d.stride(0), int(out2d.dtype == torch.bfloat16),
          ptr(out2), out2.stride(0) if out2 is not None else 0, ptr(pre), N, current_stream_ptr(),
-         flops=2.0 * M * N * K, tag="gemm_%s" % prec)
+         flops=2.0 * M * N * K, tag="gemm_%s" % prec, shape=(M, N, K, "glu" if glu else (act or ""), "res" if res2d is not None else ""))
     res = out2d.reshape(*lead, nout)
     rets = (res,)
     if out2_bf16:
@@ -475,7 +480,7 @@ def lstm_seq(gates_x, w_hh, lens, n_dirs):
 # ---------------------------------------------------------------------------------------------
 # backward pass (training): hand-written gradients of the forward ops above
 # ---------------------------------------------------------------------------------------------
-KERNELS_PER_CALL["nsp_relpos_attention_bwd"] = 3
+KERNELS_PER_CALL["nsp_relpos_attention_bwd"] = 4
 KERNELS_PER_CALL["nsp_conformer_conv_bwd"] = 2
 
 
@@ -519,7 +524,7 @@ def linear_wgrad(dy, x, prec, dw, alpha=1.0, accumulate=True):
     xh, xl = _operand(x2, prec)
     _run("nsp_linear_wgrad", lib.nsp_linear_wgrad, PREC[prec], ptr(dyh), ptr(dyl), dyh.stride(0), ptr(xh), ptr(xl), xh.stride(0),
          M, N, K, float(alpha), ptr(dw), dw.stride(0), int(accumulate), current_stream_ptr(),
-         flops=2.0 * M * N * K, tag="gemm_wgrad_%s" % prec)
+         flops=2.0 * M * N * K, tag="gemm_wgrad_%s" % prec, shape=(M, N, K))
     return dw
 
 
@@ -583,7 +588,18 @@ def colsum_acc(x, y, alpha=1.0):
     x2 = x2 if x2.stride(1) == 1 else x2.contiguous()
     if x2.dtype not in (torch.bfloat16, torch.float32):
         x2 = x2.float()
-    _run("nsp_colsum_acc", lib.nsp_colsum_acc, int(x2.dtype == torch.bfloat16), ptr(x2), x2.stride(0), x2.shape[0], x2.shape[1],
+    M, N = x2.shape
+    if N < 128 and 256 % N == 0 and x2.is_contiguous() and M % (256 // N) == 0:
+        # narrow matrix (e.g. 32 channels): view as [M*N/256, 256] so that every lane of the kernel has work, then fold the
+        # 256 partial columns back onto the N real ones
+        tmp = torch.zeros(256, dtype=torch.float32, device=x2.device)
+        xw = x2.view(-1, 256)
+        _run("nsp_colsum_acc", lib.nsp_colsum_acc, int(xw.dtype == torch.bfloat16), ptr(xw), 256, xw.shape[0], 256, float(alpha),
+             ptr(tmp), current_stream_ptr())
+        part = tmp.view(256 // N, N)
+        _run("nsp_colsum_acc", lib.nsp_colsum_acc, 0, ptr(part), N, 256 // N, N, 1.0, ptr(y), current_stream_ptr())
+        return y
+    _run("nsp_colsum_acc", lib.nsp_colsum_acc, int(x2.dtype == torch.bfloat16), ptr(x2), x2.stride(0), M, N,
          float(alpha), ptr(y), current_stream_ptr())
     return y
 

@@ -55,3 +55,25 @@ elif which == "ctc":
             torch.cuda.synchronize(); tot += s.elapsed_time(e)
         ms = tot / 20
         print("ctc B=%d T=%d V=%d L=%d: %.4f ms/batch  %.1f GB/s algorithmic (8 B/logit)" % (B, T, V, L, ms, 8.0 * B * T * V / ms / 1e6))
+elif which == "attn_bwd":
+    B, T, H, dk = 32, 500, 8, 64
+    D = H * dk
+    qkv = (torch.randn(B, T, 3 * D, device=dev) * 0.5).bfloat16()
+    r = (torch.randn(11, D, device=dev) * 0.5).bfloat16()
+    klens = torch.full((B,), T, dtype=torch.int32, device=dev)
+    dout = torch.randn(B, T, D, device=dev).bfloat16()
+    q, k, v = qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:]
+    out, stats = ops.relpos_attention(q, k, v, klens, H, r=r, clamp_len=10, want_stats=True)
+    assert stats is not None
+    dr = torch.zeros(11, D, device=dev)
+    for _ in range(3):
+        ops.relpos_attention_bwd(q, k, v, klens, H, out, dout, r=r, clamp_len=10, dr=dr, stats=stats)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(10):
+        ops.relpos_attention_bwd(q, k, v, klens, H, out, dout, r=r, clamp_len=10, dr=dr, stats=stats)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / 10
+    print("attn_bwd B=%d T=%d H=%d: %.4f ms  %.1f TFLOP/s (10*T^2*d per utterance)" % (B, T, H, ms, 10.0 * B * T * T * D / ms / 1e9))

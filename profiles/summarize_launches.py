@@ -17,7 +17,7 @@ def main(path):
         d[r[12]] = float(r[14])
     L = list(byid.values())
     cuts = [i for i, d in enumerate(L) if 'FillFunctor<unsigned cha' in d["name"]]
-    step = L[cuts[0] + 1:cuts[1]] if len(cuts) >= 2 else L
+    step = L[cuts[0] + 1:cuts[1]] if len(cuts) >= 2 else L      # `bench.py --ncu-step` captures exactly one step: take it all
     agg = collections.OrderedDict()
     for d in step:
         a = agg.setdefault(d["name"][:90], [0, 0.0, 0.0])

@@ -153,6 +153,14 @@ def test_maxpool2d_relu_bwd(pool, chmajor):
         dy = dy_ref.permute(0, 2, 3, 1).contiguous()
     dz = ops.maxpool2d_relu_bwd(a_cl, dy, pool[0], pool[1], in_chmajor=chmajor)
     assert torch.equal(dz, pre.grad.permute(0, 2, 3, 1).contiguous())
+    if not chmajor:        # bf16 (vectorised) variant on bf16-exact inputs
+        pre_b = pre.detach().bfloat16().float().requires_grad_(True)
+        p_b = F.max_pool2d(pre_b.relu(), pool, pool, 0, ceil_mode=True)
+        dy_b = dy_ref.bfloat16().float()
+        p_b.backward(dy_b)
+        dz_b = ops.maxpool2d_relu_bwd(pre_b.detach().relu().permute(0, 2, 3, 1).contiguous().bfloat16(),
+                                      dy_b.permute(0, 2, 3, 1).contiguous().bfloat16(), pool[0], pool[1])
+        assert torch.equal(dz_b.float(), pre_b.grad.permute(0, 2, 3, 1).contiguous())
 
 
 @pytest.mark.parametrize("CI,first", [(1, True), (32, False)])
