@@ -435,15 +435,21 @@ __global__ void __launch_bounds__(256) attn_bwd_finish_kernel(const float* __res
     }
 }
 
-// dr[d][h*64 + c] += sum over the (b, row block) partials of head h; grid = H * (clamp + 1), 64 threads
-__global__ void __launch_bounds__(64) attn_bwd_dr_reduce_kernel(const float* __restrict__ dr_part, float* __restrict__ dr,
-                                                                int64_t lddr, int B, int H, int rblocks) {
-    const int h = blockIdx.x % H, d = blockIdx.x / H, c = threadIdx.x;
+// dr[d][h*64 + c] += sum over the (b, row block) partials of head h.  grid = (H * (clamp + 1), slices), 256 threads:
+// thread = (column c, one of 4 interleaved partial streams); every address receives `slices` atomic adds.
+__global__ void __launch_bounds__(256) attn_bwd_dr_reduce_kernel(const float* __restrict__ dr_part, float* __restrict__ dr,
+                                                                 int64_t lddr, int B, int H, int rblocks) {
+    __shared__ float part[4][DK];
+    const int h = blockIdx.x % H, d = blockIdx.x / H, c = threadIdx.x & 63, stream = threadIdx.x >> 6;
+    const int np = B * rblocks;                                   // partials of this head: index p = b * rblocks + rb
     float s = 0.f;
-    for (int b = 0; b < B; ++b)
-        for (int rb = 0; rb < rblocks; ++rb)
-            s += dr_part[((((int64_t)b * H + h) * rblocks + rb) * 16 + d) * DK + c];
-    atomicAdd(dr + (int64_t)d * lddr + h * DK + c, s);
+    for (int p = blockIdx.y * 4 + stream; p < np; p += gridDim.y * 4) {
+        const int b = p / rblocks, rb = p % rblocks;
+        s += dr_part[((((int64_t)b * H + h) * rblocks + rb) * 16 + d) * DK + c];
+    }
+    part[stream][c] = s;
+    __syncthreads();
+    if (stream == 0) atomicAdd(dr + (int64_t)d * lddr + h * DK + c, part[0][c] + part[1][c] + part[2][c] + part[3][c]);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -542,7 +548,9 @@ nsp_status attention_bwd_tc_dispatch(const void* q, int64_t ldq, const void* k, 
                                                                       B, H, T, a.has_rel, a.clamp);
     NSP_LAUNCH_OK();
     if (a.has_rel && dr) {
-        attn_bwd_dr_reduce_kernel<<<(unsigned)(H * (a.clamp + 1)), 64, 0, st>>>(dr_part, dr, lddr, B, H, rblocks);
+        const int np = B * rblocks;
+        dim3 rgrid((unsigned)(H * (a.clamp + 1)), (unsigned)(np >= 64 ? 8 : 1));
+        attn_bwd_dr_reduce_kernel<<<rgrid, 256, 0, st>>>(dr_part, dr, lddr, B, H, rblocks);
         NSP_LAUNCH_OK();
     }
     return NSP_OK;

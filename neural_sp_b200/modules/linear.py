@@ -24,6 +24,7 @@ class _LinearFn(torch.autograd.Function):
         prec = ctx.prec
         gy2 = gy.reshape(-1, gy.shape[-1]).float().contiguous()
         x2 = x.reshape(-1, x.shape[-1]).float()
+        gyo = ops.to_bf16(gy2) if prec == "bf16" else gy2      # one operand copy shared by the dgrad and wgrad GEMMs
         gx = gw = gb = None
         from .. import autograd as ag
         nb = weight.shape[0] if (ctx.has_bias and ctx.needs_input_grad[2]) else 0
@@ -31,11 +32,11 @@ class _LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             # dX[M,K] = dY[M,N] @ W[N,K]  ->  GEMM with "weight" W^T [K,N]
             wt = prepared(ctx.module, "wT", prec, (weight,), build=lambda w: w.t().contiguous())
-            gx = ops.linear(gy2, wt, None, prec=prec, out_dtype=torch.float32).reshape(x.shape)
+            gx = ops.linear(gyo, wt, None, prec=prec, out_dtype=torch.float32).reshape(x.shape)
         if ctx.needs_input_grad[1]:
             # dW[N,K] = dY^T[N,M] @ X[M,K] on the MN-major wgrad kernel (no transposed copies)
             gw = flat[:weight.numel()].view(weight.shape)
-            ops.linear_wgrad(gy2, x2, prec, gw)
+            ops.linear_wgrad(gyo, x2, prec, gw)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = flat[weight.numel():]
             ops.colsum_acc(gy2, gb)
