@@ -230,8 +230,11 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps, warmup = max(1, min(args.steps, 2)), 0      # one training step of the sample is ~40 s of 128-core CPU time
+        steps, warmup = max(1, min(args.steps, 2)), 1      # bounded sample; one warm-up step per tried thread count
         r = cpu_reference_arm(w, steps, warmup, train=args.step == "train")
+        cfg_common = dict(cfg_common, step=("train: encoder_fwd + ctc_head + ctc_loss + backward through head and encoder "
+                                            "(torch autograd on the host cores; no optimizer, no all-reduce)")
+                          if args.step == "train" else "fwd: encoder_fwd + ctc_head + ctc_loss + head backward")
         line = {"impl": "reference", "metric": "speech_frames_per_sec", "value": r["value"], "unit": "frames/s",
                 "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
