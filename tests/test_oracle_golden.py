@@ -89,3 +89,36 @@ def test_rnnt_oracle_matches_torchaudio_golden(name):
     nll, loss, grad = rnnt_oracle.rnnt_nll_and_grad(lp, g["ys"], g["flens"], g["ylens"])
     np.testing.assert_allclose(nll, g["nll"], rtol=1e-5)
     np.testing.assert_allclose(grad, g["grad_log_probs"], atol=1e-4, rtol=0)   # torchaudio is fp32
+
+
+def test_oracle_gradients_match_reference_autograd():
+    """The oracle restatement is differentiable (bench.py's CPU baseline trains through it): its parameter gradients
+    equal the UNMODIFIED reference's autograd gradients (tests/golden/encgrad_*.npz) for loss = sum(ys * w)."""
+    import glob
+    import os
+
+    import torch
+
+    from conftest import GOLDEN, load_golden
+    from enc_util import oracle_cfg, state_dict_of
+    from oracle import encoder_oracle
+
+    for path in sorted(glob.glob(os.path.join(GOLDEN, "encgrad_*.npz"))):
+        name = os.path.basename(path)[len("encgrad_"):-4]
+        g, gg = load_golden("enc_%s.npz" % name), load_golden("encgrad_%s.npz" % name)
+        sd = {k: (v.clone().float().requires_grad_(True) if v.is_floating_point() and ("g." + k) in gg.files else v)
+              for k, v in state_dict_of(g).items()}
+        out = encoder_oracle.encoder_forward(sd, torch.from_numpy(g["xs"]), g["xlens"].tolist(), oracle_cfg(g))
+        ys = out["xs"]
+        w = np.random.default_rng(4321).standard_normal(tuple(ys.shape)).astype(np.float32)
+        for b, n in enumerate(out["xlens"]):
+            w[b, int(n):] = 0.0
+        loss = (ys * torch.from_numpy(w)).sum()
+        assert abs(float(loss.detach()) - float(gg["loss"])) <= 1e-3 * max(1.0, abs(float(gg["loss"])))
+        loss.backward()
+        gmax = max(float(np.abs(gg[k]).max()) for k in gg.files if k.startswith("g."))
+        for k, v in sd.items():
+            if torch.is_tensor(v) and v.requires_grad:
+                ref = gg["g." + k]
+                err = float(np.abs(v.grad.numpy() - ref).max()) / max(float(np.abs(ref).max()), 1e-3 * gmax)
+                assert err <= 2e-3, (name, k, err)
