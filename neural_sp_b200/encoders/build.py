@@ -2,6 +2,14 @@
 
 
 def build_encoder(args):
+    # safeguard for checkpoints trained with the old option names (reference build.py:25-32)
+    if not hasattr(args, 'transformer_enc_d_model') and hasattr(args, 'transformer_d_model'):
+        args.transformer_enc_d_model = args.transformer_d_model
+        args.transformer_dec_d_model = args.transformer_d_model
+    if not hasattr(args, 'transformer_enc_d_ff') and hasattr(args, 'transformer_d_ff'):
+        args.transformer_enc_d_ff = args.transformer_d_ff
+    if not hasattr(args, 'transformer_enc_n_heads') and hasattr(args, 'transformer_n_heads'):
+        args.transformer_enc_n_heads = args.transformer_n_heads
     conv = None
     if 'conv' in args.enc_type:
         from .conv import ConvEncoder
@@ -11,6 +19,10 @@ def build_encoder(args):
                            poolings=args.conv_poolings, dropout=0., normalization=args.conv_normalization,
                            residual=False, bottleneck_dim=args.transformer_enc_d_model
                            if ('former' in args.enc_type) else args.conv_bottleneck_dim, param_init=args.param_init)
+    if args.enc_type in ('tds', 'gated_conv'):
+        raise NotImplementedError("enc_type=%r is outside the B200 hot path (SURVEY.md section 2)" % args.enc_type)
+    if 'former' not in args.enc_type:
+        return _build_rnn(args, conv)
     common = dict(
         input_dim=args.input_dim if args.input_type == 'speech' else args.emb_dim, enc_type=args.enc_type,
         n_heads=args.transformer_enc_n_heads, n_layers=args.enc_n_layers, n_layers_sub1=args.enc_n_layers_sub1,
@@ -32,8 +44,11 @@ def build_encoder(args):
     if 'transformer' in args.enc_type:
         from .transformer import TransformerEncoder
         return TransformerEncoder(ffn_activation=args.transformer_ffn_activation, **common)
-    if args.enc_type == 'conv':
-        return conv
+    raise AssertionError("unreachable")
+
+
+def _build_rnn(args, conv):
+    """RNN family, including the CNN-only encoder enc_type='conv' (the reference wraps it in RNNEncoder too)."""
     from .rnn import RNNEncoder
     return RNNEncoder(input_dim=args.input_dim if args.input_type == 'speech' else args.emb_dim, enc_type=args.enc_type,
                       n_units=args.enc_n_units, n_projs=args.enc_n_projs,

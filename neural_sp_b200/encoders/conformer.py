@@ -27,3 +27,10 @@ class ConformerEncoder(TransformerEncoder):
             layer_norm_eps, ffn_activation, param_init, pe_type, clamp_len, ffn_bottleneck_dim, causal, normalization))
             for lth in range(n_layers)])
         self.reset_parameters(param_init)
+
+
+# command-line contract of the reference (add_args / define_name static methods): see encoders/cli.py
+from . import cli as _cli  # noqa: E402
+
+ConformerEncoder.add_args = staticmethod(_cli.conformer_add_args)
+ConformerEncoder.define_name = staticmethod(_cli.conformer_define_name)

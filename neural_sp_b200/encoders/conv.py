@@ -182,3 +182,10 @@ class ConvEncoder(EncoderBase):
             if out_scale != 1.0:
                 xs = ops.scale_(xs.contiguous(), out_scale)
         return xs, xlens
+
+
+# command-line contract of the reference (add_args / define_name static methods): see encoders/cli.py
+from . import cli as _cli  # noqa: E402
+
+ConvEncoder.add_args = staticmethod(_cli.conv_add_args)
+ConvEncoder.define_name = staticmethod(_cli.conv_define_name)

@@ -295,3 +295,10 @@ class TransformerEncoder(EncoderBase):
         if self.n_layers_sub2 >= 1 and task == 'all':
             eouts['ys_sub2']['xs'], eouts['ys_sub2']['xlens'] = xs_sub2, xlens_sub2
         return eouts
+
+
+# command-line contract of the reference (add_args / define_name static methods): see encoders/cli.py
+from . import cli as _cli  # noqa: E402
+
+TransformerEncoder.add_args = staticmethod(_cli.transformer_add_args)
+TransformerEncoder.define_name = staticmethod(_cli.transformer_define_name)
