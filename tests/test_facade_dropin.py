@@ -1,0 +1,96 @@
+"""Drop-in under the UNCHANGED reference facade (INTEGRATION.md level 1), CPU only.
+
+Builds the reference's `Speech2Text` twice from the same argument namespace -- once stock, once with
+`build_encoder` / `CTC` resolved to neural_sp_b200's classes -- and checks that the facade cannot tell the difference at
+construction level: same parameter names and shapes everywhere, strict `load_state_dict` of the stock weights, same
+encoder properties the facade and the decoders read.  Needs the reference tree (/root/reference, present in the build
+container only): skipped elsewhere.  Forward/backward through the facade needs a GPU and is covered by the module tests."""
+import argparse
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference/neural_sp"), reason="reference tree not available")
+
+
+def make_args(**ov):
+    a = dict(input_type='speech', input_dim=80, enc_type='conv_conformer', dec_type='lstm', enc_n_layers=3, enc_n_layers_sub1=0,
+             enc_n_layers_sub2=0, subsample="1_2_1", subsample_type='max_pool', vocab=40, vocab_sub1=-1, vocab_sub2=-1,
+             total_weight=1.0, sub1_weight=0.0, sub2_weight=0.0, mtl_per_batch=False, task_specific_layer=False,
+             ctc_weight=1.0, ctc_weight_sub1=0.0, ctc_weight_sub2=0.0, bwd_weight=0.0, mbr_training=False,
+             input_noise_std=0.0, n_stacks=1, n_skips=1, n_splices=1, weight_noise_std=0.0, n_freq_masks=0, n_time_masks=0,
+             freq_width=27, time_width=100, time_width_upper=1.0, adaptive_number_ratio=0.0, adaptive_size_ratio=0.0,
+             max_n_time_masks=20, sequence_summary_network=False, freeze_encoder=False, external_lm=None, lm_fusion='',
+             param_init=0.1, emb_dim=32, dropout_emb=0.0,
+             conv_in_channel=1, conv_channels="32_32", conv_kernel_sizes="(3,3)_(3,3)", conv_strides="(1,1)_(1,1)",
+             conv_poolings="(1,1)_(2,2)", conv_normalization='', conv_bottleneck_dim=0,
+             transformer_enc_n_heads=4, transformer_enc_d_model=64, transformer_enc_d_ff=128, transformer_enc_pe_type='relative',
+             transformer_enc_clamp_len=10, transformer_enc_lookaheads="0_0_0", transformer_ffn_bottleneck_dim=0,
+             transformer_ffn_activation='swish', transformer_layer_norm_eps=1e-12, transformer_param_init='xavier_uniform',
+             transformer_dec_d_model=64, conformer_kernel_size=7, conformer_normalization='layer_norm',
+             dropout_in=0.0, dropout_enc=0.0, dropout_att=0.0, dropout_enc_layer=0.0,
+             lc_chunk_size_left="0", lc_chunk_size_current="0", lc_chunk_size_right="0", lc_type='reshape',
+             enc_n_units=32, enc_n_projs=0, bidirectional_sum_fwd_bwd=False, cnn_lookahead=True, rsp_prob_enc=0.0,
+             dec_n_units=32, dec_n_projs=0, dec_n_layers=1, dec_bottleneck_dim=32, tie_embedding=False, attn_type='location',
+             attn_dim=32, attn_sharpening_factor=1.0, attn_sigmoid=False, attn_conv_n_channels=10, attn_conv_width=201,
+             attn_n_heads=1, dropout_dec=0.0, lsm_prob=0.0, ss_prob=0.0, ctc_lsm_prob=0.1, ctc_fc_list="32", mbr_ce_weight=0.01,
+             lm_init=None, mocha_chunk_size=1, mocha_n_heads_mono=1, mocha_init_r=-4, mocha_eps=1e-6, mocha_std=1.0,
+             mocha_no_denominator=False, mocha_1dconv=False, mocha_decot_lookahead=0, mocha_quantity_loss_weight=0.0,
+             mocha_latency_metric='', mocha_latency_loss_weight=0.0, mocha_stableemit_weight=0.0, gmm_attn_n_mixtures=1,
+             replace_sos=False, distillation_weight=0.0, discourse_aware=False)
+    a.update(ov)
+    return argparse.Namespace(**a)
+
+
+@pytest.mark.parametrize("ov", [dict(), dict(enc_type='conv_transformer', transformer_enc_pe_type='relative_xl',
+                                             transformer_ffn_activation='relu'),
+                                dict(enc_type='blstm', subsample="1_1_1")])
+def test_speech2text_accepts_b200_modules(ov, monkeypatch):
+    from oracle.ref_import import import_reference
+    import_reference()
+    import neural_sp.models.seq2seq.decoders.ctc as ref_ctc
+    import neural_sp.models.seq2seq.decoders.las as ref_las
+    import neural_sp.models.seq2seq.speech2text as ref_s2t
+    from neural_sp_b200.decoders.ctc import CTC as B200CTC
+    from neural_sp_b200.encoders.build import build_encoder as b200_build_encoder
+
+    stock = ref_s2t.Speech2Text(make_args(**ov))
+    monkeypatch.setattr(ref_s2t, "build_encoder", b200_build_encoder)
+    monkeypatch.setattr(ref_las, "CTC", B200CTC)
+    monkeypatch.setattr(ref_ctc, "CTC", B200CTC)
+    ours = ref_s2t.Speech2Text(make_args(**ov))
+
+    assert type(ours.enc).__module__.startswith("neural_sp_b200.") and type(ours.dec_fwd.ctc).__module__.startswith("neural_sp_b200.")
+    s_ref = {k: tuple(v.shape) for k, v in stock.state_dict().items()}
+    s_our = {k: tuple(v.shape) for k, v in ours.state_dict().items()}
+    assert s_our == s_ref, set(s_our) ^ set(s_ref)
+    ours.load_state_dict(stock.state_dict(), strict=True)
+    for prop in ("output_dim", "subsampling_factor", "enc_type"):
+        assert getattr(ours.enc, prop) == getattr(stock.enc, prop), prop
+    assert ours.dec_fwd.ctc.lsm_prob == stock.dec_fwd.ctc.lsm_prob
+
+
+def test_speech2text_accepts_b200_rnn_transducer(monkeypatch):
+    """RNN-T decoder (conv + LSTM encoder, transducer + auxiliary CTC): the factory imports the class at call time, so the
+    alias is set on the module (decoders/build.py:66-85)."""
+    from oracle.ref_import import import_reference
+    import_reference()
+    import neural_sp.models.seq2seq.decoders.rnn_transducer as ref_rnnt
+    import neural_sp.models.seq2seq.speech2text as ref_s2t
+    from neural_sp_b200.decoders.rnn_transducer import RNNTransducer as B200RNNT
+    from neural_sp_b200.encoders.build import build_encoder as b200_build_encoder
+
+    ov = dict(dec_type='lstm_transducer', enc_type='conv_lstm', subsample="1_1_1", ctc_weight=0.3, conv_poolings="(2,2)_(2,2)")
+    stock = ref_s2t.Speech2Text(make_args(**ov))
+    monkeypatch.setattr(ref_s2t, "build_encoder", b200_build_encoder)
+    monkeypatch.setattr(ref_rnnt, "RNNTransducer", B200RNNT)
+    ours = ref_s2t.Speech2Text(make_args(**ov))
+    assert type(ours.dec_fwd).__module__.startswith("neural_sp_b200.") and type(ours.enc).__module__.startswith("neural_sp_b200.")
+    s_ref = {k: tuple(v.shape) for k, v in stock.state_dict().items()}
+    s_our = {k: tuple(v.shape) for k, v in ours.state_dict().items()}
+    assert s_our == s_ref, set(s_our) ^ set(s_ref)
+    ours.load_state_dict(stock.state_dict(), strict=True)
