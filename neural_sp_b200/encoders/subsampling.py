@@ -38,6 +38,11 @@ class MaxPoolSubsampler(_PoolSubsampler):       # reference :175-209
 class MeanPoolSubsampler(_PoolSubsampler):      # reference :212-246
     mode = "mean"
 
+    def _lens(self, xlens):
+        # the reference's update_lens_1d takes the FLOOR formula for nn.AvgPool1d (conv.py:446-450: only MaxPool1d gets
+        # the ceil-mode branch) although the pooled tensor itself has ceil(T / f) frames
+        return torch.IntTensor([(int(n) - self.factor) // self.factor + 1 for n in xlens])
+
 
 class DropSubsampler(_PoolSubsampler):          # reference :97-126
     mode = "drop"
@@ -76,7 +81,10 @@ class ConcatSubsampler(nn.Module):
         x = xs[:, :To * self.factor].reshape(B, To, self.factor * D)
         y = ops.linear(x, prepared(self, "proj", prec, (self.proj.weight,)), self.proj.bias, prec=prec, act="relu",
                        out_dtype=torch.float32)
-        return y, torch.IntTensor([max(1, int(n) // self.factor) for n in xlens])
+        return y, self._lens(xlens)
+
+    def _lens(self, xlens):
+        return torch.IntTensor([max(1, int(n) // self.factor) for n in xlens])
 
 
 class Conv1dSubsampler(nn.Module):
@@ -102,4 +110,8 @@ class Conv1dSubsampler(nn.Module):
         cols = xp.unfold(1, k, f)[:, :To].permute(0, 1, 3, 2).reshape(B, To, k * D)   # [B, To, k*D], index j*D + c
         w = prepared(self, "conv1d", prec, (self.conv1d.weight,), build=lambda w_: w_.permute(0, 2, 1).reshape(w_.size(0), -1))
         y = ops.linear(cols, w, self.conv1d.bias, prec=prec, act="relu", out_dtype=torch.float32)
-        return y, torch.IntTensor([(int(n) + 2 * pad - (k - 1) - 1) // f + 1 for n in xlens])
+        return y, self._lens(xlens)
+
+    def _lens(self, xlens):
+        k, pad, f = self.kernel_size, (self.kernel_size - 1) // 2, self.factor
+        return torch.IntTensor([(int(n) + 2 * pad - (k - 1) - 1) // f + 1 for n in xlens])

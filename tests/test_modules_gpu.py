@@ -190,7 +190,7 @@ def test_subsamplers_match_reference_formulas(kind, T):
     elif kind == "mean_pool":
         m = ss.MeanPoolSubsampler(f)
         ref = F.avg_pool1d(xs.transpose(1, 2), f, f, 0, ceil_mode=True).transpose(1, 2)
-        rl = [(n + 1 - f) // f + 1 for n in xlens.tolist()]
+        rl = [(n - f) // f + 1 for n in xlens.tolist()]      # the reference's floor formula for AvgPool1d (conv.py:446-450)
     elif kind == "drop":
         m = ss.DropSubsampler(f)
         ref = xs[:, ::f]
