@@ -5,6 +5,8 @@ Same constructor and parameter names (``rnn.N``, ``embed``, ``w_enc``, ``w_dec``
 as plain torch -- SURVEY.md section 2 row 4), joint network on the library's kernels (two GEMMs, fused add+tanh,
 vocabulary GEMM, row log-softmax) and the RNN-T lattice kernel, which also yields d loss / d log_probs.
 Beam search (:419-819) is out of scope."""
+import copy
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -42,7 +44,10 @@ class RNNTransducer(nn.Module):
         if self.rnnt_weight > 0:
             self.rnn = nn.ModuleList()
             dec_odim = emb_dim
-            self.proj = nn.ModuleList([nn.Linear(n_units, n_projs) for _ in range(n_layers)]) if n_projs > 0 else None
+            # one Linear deep-copied n_layers times, like the reference's repeat(): same RNG consumption, so that
+            # seeded construction yields bit-identical initial weights
+            proto = nn.Linear(n_units, n_projs) if n_projs > 0 else None
+            self.proj = nn.ModuleList([copy.deepcopy(proto) for _ in range(n_layers)]) if n_projs > 0 else None
             self.dropout = nn.Dropout(p=dropout)
             for _ in range(n_layers):
                 self.rnn += [nn.LSTM(dec_odim, n_units, 1, batch_first=True)]
@@ -52,10 +57,8 @@ class RNNTransducer(nn.Module):
             self.w_enc = nn.Linear(enc_n_units, bottleneck_dim)
             self.w_dec = nn.Linear(dec_odim, bottleneck_dim, bias=False)
             self.output = nn.Linear(bottleneck_dim, vocab)
-        for n, p in self.named_parameters():       # reference :161-172: uniform(-param_init, param_init), biases 0
-            if 'ctc.' in n:
-                continue
-            if p.dim() == 1:
+        for n, p in self.named_parameters():       # reference :161-172: uniform(-param_init, param_init), biases 0,
+            if p.dim() == 1:                       # INCLUDING the auxiliary CTC head (no exclusion in the reference)
                 nn.init.constant_(p, 0.)
             else:
                 nn.init.uniform_(p, a=-param_init, b=param_init)
@@ -124,3 +127,25 @@ class RNNTransducer(nn.Module):
             loss = loss + loss_t * (1 if self.mtl_per_batch else self.rnnt_weight)
         observation['loss'] = float(loss.detach())
         return loss, observation
+
+
+# command-line contract (reference decoders/rnn_transducer.py:130-158)
+def _rnnt_add_args(parser, args):
+    group = parser.add_argument_group("RNN-T decoder")
+    if not hasattr(args, 'dec_n_units'):           # shared with the LAS decoder's options
+        group.add_argument('--dec_n_units', type=int, default=512)
+        group.add_argument('--dec_n_projs', type=int, default=0)
+        group.add_argument('--dec_bottleneck_dim', type=int, default=1024)
+        group.add_argument('--emb_dim', type=int, default=512)
+    return parser
+
+
+def _rnnt_define_name(dir_name, args):
+    name = dir_name + '_' + args.dec_type + '%dH' % args.dec_n_units
+    if args.dec_n_projs > 0:
+        name += '%dP' % args.dec_n_projs
+    return name + '%dL' % args.dec_n_layers
+
+
+RNNTransducer.add_args = staticmethod(_rnnt_add_args)
+RNNTransducer.define_name = staticmethod(_rnnt_define_name)

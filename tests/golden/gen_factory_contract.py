@@ -2,7 +2,8 @@
 """build_encoder(args) contract from the UNMODIFIED reference (run in the build container):
     python tests/golden/gen_factory_contract.py  ->  tests/golden/factory_contract.json
 For several argument namespaces: class name, state_dict keys with shapes, and the properties callers read
-(output_dim, subsampling_factor, ...).  CPU only (modules are only constructed)."""
+(output_dim, subsampling_factor, ...), and a digest of the freshly initialised weights under torch.manual_seed(0)
+(same init distributions drawn in the same order = bit-identical initial weights).  CPU only (modules are only constructed)."""
 import argparse
 import json
 import os
@@ -43,8 +44,15 @@ def contract(build_encoder):
     for name, ov in CASES.items():
         a = dict(BASE)
         a.update(ov)
+        import hashlib
+        import torch
+        torch.manual_seed(0)
         enc = build_encoder(argparse.Namespace(**a))
-        entry = dict(cls=type(enc).__name__,
+        h = hashlib.sha256()
+        for k, v in sorted(enc.state_dict().items()):
+            h.update(k.encode())
+            h.update(v.detach().cpu().contiguous().numpy().tobytes())
+        entry = dict(cls=type(enc).__name__, init_digest=h.hexdigest(),
                      state={k: list(v.shape) for k, v in enc.state_dict().items()},
                      props={})
         for p in PROPS:

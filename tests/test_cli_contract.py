@@ -35,6 +35,8 @@ def test_build_encoder_factory_matches_reference():
         assert ours[name]["cls"] == ref[name]["cls"], name
         assert ours[name]["state"] == ref[name]["state"], (name, set(ours[name]["state"]) ^ set(ref[name]["state"]))
         assert ours[name]["props"] == ref[name]["props"], (name, ours[name]["props"], ref[name]["props"])
+        # same initialisers drawn in the same order: bit-identical fresh weights under the same seed
+        assert ours[name]["init_digest"] == ref[name]["init_digest"], name
 
 
 def test_length_arithmetic_matches_reference():

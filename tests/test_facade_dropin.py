@@ -58,11 +58,17 @@ def test_speech2text_accepts_b200_modules(ov, monkeypatch):
     from neural_sp_b200.decoders.ctc import CTC as B200CTC
     from neural_sp_b200.encoders.build import build_encoder as b200_build_encoder
 
+    import torch
+    torch.manual_seed(0)
     stock = ref_s2t.Speech2Text(make_args(**ov))
     monkeypatch.setattr(ref_s2t, "build_encoder", b200_build_encoder)
     monkeypatch.setattr(ref_las, "CTC", B200CTC)
     monkeypatch.setattr(ref_ctc, "CTC", B200CTC)
+    torch.manual_seed(0)
     ours = ref_s2t.Speech2Text(make_args(**ov))
+    # same seed -> bit-identical fresh weights (every initialiser of the mirrors draws in the reference's order)
+    diff = [k for k, v in stock.state_dict().items() if not torch.equal(v, ours.state_dict()[k])]
+    assert not diff, diff[:8]
 
     assert type(ours.enc).__module__.startswith("neural_sp_b200.") and type(ours.dec_fwd.ctc).__module__.startswith("neural_sp_b200.")
     s_ref = {k: tuple(v.shape) for k, v in stock.state_dict().items()}
@@ -85,10 +91,15 @@ def test_speech2text_accepts_b200_rnn_transducer(monkeypatch):
     from neural_sp_b200.encoders.build import build_encoder as b200_build_encoder
 
     ov = dict(dec_type='lstm_transducer', enc_type='conv_lstm', subsample="1_1_1", ctc_weight=0.3, conv_poolings="(2,2)_(2,2)")
+    import torch
+    torch.manual_seed(0)
     stock = ref_s2t.Speech2Text(make_args(**ov))
     monkeypatch.setattr(ref_s2t, "build_encoder", b200_build_encoder)
     monkeypatch.setattr(ref_rnnt, "RNNTransducer", B200RNNT)
+    torch.manual_seed(0)
     ours = ref_s2t.Speech2Text(make_args(**ov))
+    diff = [k for k, v in stock.state_dict().items() if not torch.equal(v, ours.state_dict()[k])]
+    assert not diff, diff[:8]
     assert type(ours.dec_fwd).__module__.startswith("neural_sp_b200.") and type(ours.enc).__module__.startswith("neural_sp_b200.")
     s_ref = {k: tuple(v.shape) for k, v in stock.state_dict().items()}
     s_our = {k: tuple(v.shape) for k, v in ours.state_dict().items()}
