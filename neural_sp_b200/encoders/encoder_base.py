@@ -44,3 +44,8 @@ class EncoderBase(nn.Module):
 
     def turn_off_ceil_mode(self, encoder):
         raise NotImplementedError("floor-mode pooling is not on the B200 path")
+
+    def _plot_attention(self, save_path=None, n_cols=2):
+        """Reference encoder_base.py:75: plots `self.aws_dict`.  The flash-style attention kernels never materialise the
+        `[B, H, T', T']` weights, so `aws_dict` stays empty and there is nothing to draw (kept for the trainer's call)."""
+        return None
