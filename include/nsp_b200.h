@@ -223,6 +223,20 @@ size_t nsp_lstm_workspace_bytes(int B, int H, int ndir);
 nsp_status nsp_lstm_seq_fwd(const float* gates_x, const float* w_hh, const int32_t* lens, float* y,
                             int B, int T, int H, int ndir, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Training variants of the LSTM layer recurrence (reference: autograd through nn.LSTM, encoders/rnn.py:534-546).
+ * _fwd_save additionally stores, for every valid (b, t, dir): the gate activations i,f,g,o  acts [B,T,ndir,4H], the cell
+ * state entering the step  cprev [B,T,ndir,H]  and the hidden state entering it  hprev [B,T,ndir,H]  (buffers must be
+ * zero-initialised by the caller: padded frames are not written).
+ * _bwd runs backpropagation through time: dy [B,T,ndir*H] -> dgates [B,T,ndir*4H] = d loss / d gate pre-activations
+ * (layout of gates_x; zero on padded frames).  The weight / input gradients are GEMMs on dgates (nsp_linear_wgrad, nsp_linear_fwd).
+ * workspace: >= 256 bytes. */
+nsp_status nsp_lstm_seq_fwd_save(const float* gates_x, const float* w_hh, const int32_t* lens, float* y,
+                                 int B, int T, int H, int ndir, float* acts, float* cprev, float* hprev,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+nsp_status nsp_lstm_seq_bwd(const float* dy, const float* acts, const float* cprev, const float* w_hh,
+                            const int32_t* lens, float* dgates, int B, int T, int H, int ndir,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
 
 /* ==========================================================================================
  * Backward pass of the encoder path (training).  The reference obtains all of these from torch autograd over

@@ -399,6 +399,94 @@ def linear(module, name, lin, x, prec):
     return _LinearFn.apply(x, lin.weight, lin.bias, lin, prec)
 
 
+class _LinearReluFn(torch.autograd.Function):
+    """relu(x W^T + b) with the ReLU fused into the GEMM epilogue; backward masks dy with the saved output."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, owner, name, prec):
+        y = ops.linear(x, prepared(owner, name, prec, (weight,), build=_as2d), bias, prec=prec, act="relu", out_dtype=torch.float32)
+        ctx.save_for_backward(x, weight, y)
+        ctx.owner, ctx.name, ctx.prec = owner, name, prec
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        prec = ctx.prec
+        dz = ops.relu_mask(dy.contiguous().float(), y).reshape(-1, y.shape[-1])
+        dzo = _gop(dz, prec)
+        N = weight.shape[0]
+        flat = torch.zeros(weight.numel() + N, dtype=torch.float32, device=weight.device)
+        gw, gb = flat[:weight.numel()].view(N, -1), flat[weight.numel():]
+        dx = ops.linear(dzo, _wT(ctx.owner, ctx.name, prec, (weight,)), None, prec=prec, out_dtype=torch.float32).reshape(x.shape)
+        ops.linear_wgrad(dzo, x.reshape(-1, x.shape[-1]).float(), prec, gw)
+        ops.colsum_acc(dz, gb)
+        if _GRAD_SYNC is not None:
+            _GRAD_SYNC(flat)
+        return dx, gw.view(weight.shape), gb, None, None, None
+
+
+def linear_relu(owner, name, weight, bias, x, prec):
+    """ReLU(Linear) with autograd; `weight` may be a Conv1d weight [N, C, k] whose GEMM view the caller has laid out in x."""
+    return _LinearReluFn.apply(x, weight, bias, owner, name, prec)
+
+
+# ------------------------------------------------------------------------------------------------
+# one (bi)directional LSTM layer as one node (reference: autograd through Padding / nn.LSTM, encoders/rnn.py:534-546)
+# ------------------------------------------------------------------------------------------------
+class _LstmLayerFn(torch.autograd.Function):
+    """params = (w_ih, w_hh, b_ih, b_hh) of the forward direction [+ the same four of the reverse direction]."""
+
+    @staticmethod
+    def forward(ctx, xs, enc, lth, lens_dev, prec, *params):
+        nd = len(params) // 4
+        w_ih, w_hh = params[0::4], params[1::4]
+        b_ih, b_hh = params[2::4], params[3::4]
+        w_ihp = prepared(enc, 'w_ih%d' % lth, prec, tuple(w_ih), build=lambda *ws: torch.cat(ws, dim=0))
+        bias = cached(enc, 'b%d' % lth, tuple(b_ih) + tuple(b_hh),
+                      lambda *bs: (torch.cat(bs[:nd]) + torch.cat(bs[nd:])).float().contiguous())
+        whh = cached(enc, 'w_hh%d' % lth, tuple(w_hh), lambda *ws: torch.stack(ws, dim=0).float().contiguous())
+        xs = xs.contiguous().float()
+        gates_x = ops.linear(xs, w_ihp, bias, prec=prec, out_dtype=torch.float32)
+        ys, acts, cprev, hprev = ops.lstm_seq(gates_x, whh, lens_dev, nd, save=True)
+        ctx.save_for_backward(xs, acts, cprev, hprev, whh, lens_dev)
+        ctx.enc, ctx.lth, ctx.prec, ctx.params, ctx.nd = enc, lth, prec, params, nd
+        return ys
+
+    @staticmethod
+    def backward(ctx, dy):
+        xs, acts, cprev, hprev, whh, lens_dev = ctx.saved_tensors
+        prec, nd, params = ctx.prec, ctx.nd, ctx.params
+        w_ih, w_hh = params[0::4], params[1::4]
+        b_ih, b_hh = params[2::4], params[3::4]
+        H4 = acts.shape[-1]
+        # bucket order: [w_ih of all directions | w_hh | b_ih | b_hh]: the direction-concatenated gradients are single views
+        G = _Grads(tuple(w_ih) + tuple(w_hh) + tuple(b_ih) + tuple(b_hh))
+        dg = ops.lstm_seq_bwd(dy, acts, cprev, whh, lens_dev)                     # [B, T, nd*4H] fp32
+        dgo = _gop(dg, prec)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            w_ihT = _wT(ctx.enc, 'w_ih%d' % ctx.lth, prec, tuple(w_ih), build=lambda *ws: torch.cat(ws, dim=0))
+            dx = ops.linear(dgo, w_ihT, None, prec=prec, out_dtype=torch.float32)
+        ops.linear_wgrad(dgo, xs, prec, G.fused(w_ih))                            # all directions at once
+        for d in range(nd):
+            ops.linear_wgrad(dgo[:, :, d * H4:(d + 1) * H4].contiguous(), hprev[:, :, d].contiguous(), prec, G.get(w_hh[d]))
+        gb = G.fused(b_ih)
+        ops.colsum_acc(dg, gb.view(-1))
+        G.fused(b_hh).copy_(gb)                                                    # b_ih and b_hh enter the gates as a sum
+        G.done()
+        return (dx, None, None, None, None) + tuple(G.get(p) for p in params)
+
+
+def lstm_layer(enc, lth, xs, lens_dev, prec):
+    rnn = enc.rnn[lth]
+    params = []
+    for sfx in ['_l0'] + (['_l0_reverse'] if enc.bidirectional else []):
+        params += [getattr(rnn, 'weight_ih' + sfx), getattr(rnn, 'weight_hh' + sfx),
+                   getattr(rnn, 'bias_ih' + sfx), getattr(rnn, 'bias_hh' + sfx)]
+    return _LstmLayerFn.apply(xs, enc, lth, lens_dev, prec, *params)
+
+
 # ------------------------------------------------------------------------------------------------
 # CNN front-end (Conv2dBlock stack + bridge) as one node
 # ------------------------------------------------------------------------------------------------

@@ -6,11 +6,14 @@ is one tcgen05 GEMM (both directions and both biases folded in) and the recurren
 library, which implements the packed-sequence semantics of ``Padding`` (:534-546) from device-side lengths -- so the
 reference's sort / pack / unsort round trip (:296-298, :375-377) is unnecessary.
 Supported: lstm / blstm (+ conv front-end), projections, sum of directions, the six subsamplers, sub-task outputs,
-bridge.  Latency-controlled BLSTM (``_forward_latency_controlled``), streaming state carry-over and RSP are 'next' rows."""
+bridge.  In train() + grad mode every LSTM layer is one autograd node (neural_sp_b200/autograd.py: forward keeps the gate
+activations, backward = persistent BPTT kernel + tcgen05 dgrad / wgrad GEMMs); subsamplers with a training path:
+max_pool, drop, concat.  Latency-controlled BLSTM (``_forward_latency_controlled``), streaming state carry-over and RSP are 'next' rows."""
 import numpy as np
 import torch
 import torch.nn as nn
 
+from .. import autograd as ag
 from .. import ops
 from ..modules._prep import prepared, cached, get_precision
 from .encoder_base import EncoderBase
@@ -95,10 +98,16 @@ class RNNEncoder(EncoderBase):
         self.hx_fwd = [None] * self.n_layers
         self.hx_bwd = [None] * self.n_layers
 
-    def _lstm_layer(self, lth, xs, lens_dev):
+    def _lstm_layer(self, lth, xs, lens_dev, train=False):
         """One (bi)directional LSTM layer over `[B, T, I]` with packed-sequence semantics."""
         rnn = self.rnn[lth]
         prec = get_precision(self)
+        if train:
+            ys = ag.lstm_layer(self, lth, xs, lens_dev, prec)
+            if self.bidir_sum and self.bidirectional:
+                half = ys.size(-1) // 2
+                ys = ys[:, :, :half] + ys[:, :, half:]
+            return ys
         names = ['_l0'] + (['_l0_reverse'] if self.bidirectional else [])
         w_ih = [getattr(rnn, 'weight_ih' + n) for n in names]
         w_ihp = prepared(self, 'w_ih%d' % lth, prec, tuple(w_ih), build=lambda *ws: torch.cat(ws, dim=0))
@@ -114,8 +123,15 @@ class RNNEncoder(EncoderBase):
             ys = ys[:, :, :half] + ys[:, :, half:]
         return ys
 
-    def _sub_out(self, xs, module):
+    def _sub_out(self, xs, module, train=False):
         prec = get_precision(self)
+        if train:
+            xs_sub = xs.clone()
+            if self.task_specific_layer:
+                lin = getattr(self, 'layer_' + module)
+                xs_sub = ag.linear_relu(self, 'layer_' + module, lin.weight, lin.bias, xs, prec)
+            bridge = getattr(self, 'bridge_' + module)
+            return xs_sub if bridge is None else ag.linear(self, 'bridge_' + module, bridge, xs_sub, prec)
         if self.task_specific_layer:
             lin = getattr(self, 'layer_' + module)
             xs_sub = ops.linear(xs, prepared(self, 'layer_' + module, prec, (lin.weight,)), lin.bias, prec=prec, act='relu')
@@ -126,6 +142,21 @@ class RNNEncoder(EncoderBase):
             xs_sub = ops.linear(xs_sub, prepared(self, 'bridge_' + module, prec, (bridge.weight,)), bridge.bias, prec=prec)
         return xs_sub
 
+    def _subsample_train(self, lth, xs, xlens):
+        sub = self.subsample[lth]
+        f = sub.factor
+        if f == 1:
+            return xs, xlens
+        if isinstance(sub, MaxPoolSubsampler):
+            return ag.maxpool_time(xs, f), sub._lens(xlens)
+        if isinstance(sub, DropSubsampler):
+            return xs[:, ::f].contiguous(), sub._lens(xlens)
+        if isinstance(sub, ConcatSubsampler):
+            B, T, D = xs.shape
+            x = xs[:, :(T // f) * f].reshape(B, T // f, f * D)
+            return ag.linear_relu(sub, 'proj', sub.proj.weight, sub.proj.bias, x, get_precision(sub)), sub._lens(xlens)
+        raise NotImplementedError("training: subsample_type %s has no CUDA backward yet" % type(sub).__name__)
+
     def forward(self, xs, xlens, task, streaming=False, lookback=False, lookahead=False):
         if streaming:
             raise NotImplementedError("streaming inference is a 'next' row (SURVEY.md 8f-4)")
@@ -135,32 +166,45 @@ class RNNEncoder(EncoderBase):
                  'ys_sub2': {'xs': None, 'xlens': None}}
         xlens = torch.IntTensor([int(v) for v in xlens])
         prec = get_precision(self)
-        with torch.no_grad():
+        # train() + grad mode: autograd nodes with hand-written CUDA backward; otherwise inference kernels under no_grad
+        train = ag.training_enabled(self)
+        with (torch.enable_grad() if train else torch.no_grad()):
             if self.conv is not None:
-                xs, xlens = self.conv(xs, xlens, lookback=lookback, lookahead=lookahead)
+                if train:
+                    if lookback or lookahead:
+                        raise NotImplementedError("CNN lookback/lookahead trimming (streaming) is a 'next' row")
+                    xs, xlens = ag.frontend_forward(self.conv, xs, 1.0, prec), self.conv.output_lens(xlens)
+                else:
+                    xs, xlens = self.conv(xs, xlens, lookback=lookback, lookahead=lookahead)
                 if self.enc_type == 'conv':
                     eouts['ys']['xs'], eouts['ys']['xlens'] = xs, xlens
                     return eouts
             xs = xs.float()
             for lth in range(self.n_layers):
-                xs = self._lstm_layer(lth, xs, lens_to_device(xlens, xs.device))
+                xs = self._lstm_layer(lth, xs, lens_to_device(xlens, xs.device), train)
                 if lth == self.n_layers_sub1 - 1:
-                    xs_sub1, xlens_sub1 = self._sub_out(xs, 'sub1'), xlens.clone()
+                    xs_sub1, xlens_sub1 = self._sub_out(xs, 'sub1', train), xlens.clone()
                     if task == 'ys_sub1':
                         eouts[task]['xs'], eouts[task]['xlens'] = xs_sub1, xlens_sub1
                         return eouts
                 if lth == self.n_layers_sub2 - 1:
-                    xs_sub2, xlens_sub2 = self._sub_out(xs, 'sub2'), xlens.clone()
+                    xs_sub2, xlens_sub2 = self._sub_out(xs, 'sub2', train), xlens.clone()
                     if task == 'ys_sub2':
                         eouts[task]['xs'], eouts[task]['xlens'] = xs_sub2, xlens_sub2
                         return eouts
                 if self.proj is not None and lth != self.n_layers - 1:
                     lin = self.proj[lth]
-                    xs = ops.linear(xs, prepared(self, 'proj%d' % lth, prec, (lin.weight,)), lin.bias, prec=prec, act='relu')
+                    if train:
+                        xs = ag.linear_relu(self, 'proj%d' % lth, lin.weight, lin.bias, xs, prec)
+                    else:
+                        xs = ops.linear(xs, prepared(self, 'proj%d' % lth, prec, (lin.weight,)), lin.bias, prec=prec, act='relu')
                 if self.subsample is not None:
-                    xs, xlens = self.subsample[lth](xs, xlens)
+                    xs, xlens = self._subsample_train(lth, xs, xlens) if train else self.subsample[lth](xs, xlens)
             if self.bridge is not None:
-                xs = ops.linear(xs, prepared(self, 'bridge', prec, (self.bridge.weight,)), self.bridge.bias, prec=prec)
+                if train:
+                    xs = ag.linear(self, 'bridge', self.bridge, xs, prec)
+                else:
+                    xs = ops.linear(xs, prepared(self, 'bridge', prec, (self.bridge.weight,)), self.bridge.bias, prec=prec)
             xs = xs[:, :int(xlens.max())]
         if task in ['all', 'ys']:
             eouts['ys']['xs'], eouts['ys']['xlens'] = xs, xlens

@@ -461,9 +461,10 @@ def pool_time(x, factor, mode):
     return y
 
 
-def lstm_seq(gates_x, w_hh, lens, n_dirs):
+def lstm_seq(gates_x, w_hh, lens, n_dirs, save=False):
     """LSTM recurrence of one layer (nsp_lstm_seq_fwd): gates_x fp32 `[B,T,n_dirs*4H]`, w_hh fp32 `[n_dirs,4H,H]`,
-    lens int32 `[B]` CUDA -> y fp32 `[B,T,n_dirs*H]` (zeros beyond each length)."""
+    lens int32 `[B]` CUDA -> y fp32 `[B,T,n_dirs*H]` (zeros beyond each length).
+    save=True (training, nsp_lstm_seq_fwd_save) -> (y, acts `[B,T,n_dirs,4H]`, cprev, hprev `[B,T,n_dirs,H]`)."""
     _require_cuda(gates_x, w_hh, lens)
     gates_x = gates_x.contiguous().float()
     w_hh = w_hh.contiguous().float()
@@ -472,9 +473,33 @@ def lstm_seq(gates_x, w_hh, lens, n_dirs):
     ws_bytes = lib.nsp_lstm_workspace_bytes(B, H, n_dirs)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=gates_x.device)
     y = torch.empty(B, T, n_dirs * H, dtype=torch.float32, device=gates_x.device)
+    if save:
+        acts = torch.zeros(B, T, n_dirs, 4 * H, dtype=torch.float32, device=gates_x.device)
+        cprev = torch.zeros(B, T, n_dirs, H, dtype=torch.float32, device=gates_x.device)
+        hprev = torch.zeros(B, T, n_dirs, H, dtype=torch.float32, device=gates_x.device)
+        _run("nsp_lstm_seq_fwd_save", lib.nsp_lstm_seq_fwd_save, ptr(gates_x), ptr(w_hh), ptr(lens), ptr(y), B, T, H, n_dirs,
+             ptr(acts), ptr(cprev), ptr(hprev), ptr(ws), ws_bytes, current_stream_ptr(),
+             flops=2.0 * B * T * n_dirs * 4 * H * H, tag="lstm_seq")
+        return y, acts, cprev, hprev
     _run("nsp_lstm_seq_fwd", lib.nsp_lstm_seq_fwd, ptr(gates_x), ptr(w_hh), ptr(lens), ptr(y), B, T, H, n_dirs, ptr(ws),
          ws_bytes, current_stream_ptr(), flops=2.0 * B * T * n_dirs * 4 * H * H, tag="lstm_seq")
     return y
+
+
+def lstm_seq_bwd(dy, acts, cprev, w_hh, lens):
+    """Backpropagation through time of lstm_seq (nsp_lstm_seq_bwd): dy fp32 `[B,T,n_dirs*H]` + what the forward saved ->
+    d loss / d gate pre-activations fp32 `[B,T,n_dirs*4H]` (the layout of gates_x; zero beyond each length)."""
+    _require_cuda(dy, acts, cprev, w_hh, lens)
+    B, T, n_dirs, H4 = acts.shape
+    H = H4 // 4
+    dy = dy.contiguous().float()
+    assert dy.shape == (B, T, n_dirs * H), (dy.shape, acts.shape)
+    w_hh = w_hh.contiguous().float()
+    dg = torch.empty(B, T, n_dirs * H4, dtype=torch.float32, device=dy.device)
+    ws = torch.empty(256, dtype=torch.uint8, device=dy.device)
+    _run("nsp_lstm_seq_bwd", lib.nsp_lstm_seq_bwd, ptr(dy), ptr(acts), ptr(cprev), ptr(w_hh), ptr(lens), ptr(dg), B, T, H, n_dirs,
+         ptr(ws), 256, current_stream_ptr(), flops=2.0 * B * T * n_dirs * 4 * H * H, tag="lstm_seq_bwd")
+    return dg
 
 
 # ---------------------------------------------------------------------------------------------

@@ -109,6 +109,9 @@ if __name__ == "__main__":
     if "encoder_grads" in what:
         from gen_golden_encoder import gen_encoder_grads
         gen_encoder_grads()
+    if "rnn_grads" in what:
+        from gen_golden_encoder import gen_rnn_grads
+        gen_rnn_grads()
     if "rnn" in what:
         from gen_golden_encoder import gen_rnn_encoder
         gen_rnn_encoder()

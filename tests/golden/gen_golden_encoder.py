@@ -229,3 +229,36 @@ def gen_encoder_grads():
         save["loss"] = np.array(float(loss.detach()), np.float32)
         np.savez_compressed(os.path.join(HERE, "encgrad_" + name[4:] + ".npz"), **save)
         print("encoder grads", name, float(loss), len(save) - 1, "tensors; no grad:", missing)
+
+
+RNN_GRAD_CASES = ["rnn_conv_lstm_proj", "rnn_blstm_sum"]
+
+
+def gen_rnn_grads():
+    """Parameter gradients of the UNMODIFIED reference RNNEncoder (torch autograd through nn.LSTM on packed sequences, CPU
+    fp32) for loss = sum(ys * w) [+ sum(ys_sub1 * w1)]: rnngrad_<case>.npz; inputs / weights are those of rnn_<case>.npz."""
+    import importlib
+    mod = importlib.import_module('neural_sp.models.seq2seq.encoders.rnn')
+    conv_mod = importlib.import_module('neural_sp.models.seq2seq.encoders.conv')
+    for name in RNN_GRAD_CASES:
+        base = np.load(os.path.join(HERE, name + ".npz"))
+        c = json.loads(str(base["cfg"]))
+        args = dict(c["args"])
+        torch.manual_seed(0)
+        args["frontend_conv"] = conv_mod.ConvEncoder(**c["conv"]) if c["conv"] else None
+        enc = mod.RNNEncoder(**args)
+        enc.load_state_dict({k[3:]: torch.from_numpy(base[k].astype(np.float32)) for k in base.files if k.startswith("sd.")})
+        enc.eval()                                   # dropouts are 0 in these cases
+        out = enc(torch.from_numpy(base["xs"]), torch.IntTensor(base["xlens"].tolist()), task='all')
+        ys = out['ys']['xs']
+        assert np.allclose(ys.detach().numpy(), base["ys"], atol=1e-6)
+        loss = (ys * torch.from_numpy(grad_loss_weights(tuple(ys.shape), out['ys']['xlens'].tolist()))).sum()
+        if out['ys_sub1']['xs'] is not None:
+            s1 = out['ys_sub1']['xs']
+            loss = loss + (s1 * torch.from_numpy(grad_loss_weights(tuple(s1.shape), out['ys_sub1']['xlens'].tolist(), seed=99))).sum()
+        loss.backward()
+        save = {"g." + k: p.grad.numpy() for k, p in enc.named_parameters() if p.grad is not None}
+        missing = [k for k, p in enc.named_parameters() if p.grad is None]
+        save["loss"] = np.array(float(loss.detach()), np.float32)
+        np.savez_compressed(os.path.join(HERE, "rnngrad_" + name[4:] + ".npz"), **save)
+        print("rnn grads", name, float(loss.detach()), len(save) - 1, "tensors; no grad:", missing)
