@@ -171,7 +171,7 @@ def cpu_reference_arm(w, steps, warmup, sample_B=1, sample_T=500, train=True):
         mask = (torch.arange(lp.size(1))[None, :] < elens[:, None]).unsqueeze(-1)
         kl = (lp.exp() * (lp - float(np.log(1.0 / (V - 1)))) * mask).sum() / float(elens.sum())
         (loss * 0.9 + kl * 0.1).backward()
-        return float(loss)
+        return float(loss.detach())
 
     # torch's CPU kernels stop scaling (and with many tiny ops get much slower) long before 128 threads: time the sample
     # at 8, 16, 32, ... up to every available core and report the BEST thread count, i.e. the reference at its fastest.
@@ -247,7 +247,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from neural_sp_b200 import ops
+    from neural_sp_b200 import _lib, ops
     from neural_sp_b200.decoders.ctc import CTC
     from neural_sp_b200.encoders.conformer import ConformerEncoder
     from neural_sp_b200.encoders.conv import ConvEncoder
@@ -514,7 +514,8 @@ def main():
                                              "per-step working set >> 126 MB L2",
                                encoder_fwd_tflop_per_step=fl_utt * B / 1e12, enc_out_frames=Tp,
                                cuda_graph=graph_ok, cuda_graph_error=graph_error, n_params=n_params,
-                               allreduce=(args.allreduce if world > 1 else None)),
+                               allreduce=(args.allreduce if world > 1 else None),
+                               gemm_epilogue=("tma" if _lib.lib.nsp_get_gemm_epilogue() == 1 else "direct")),
                 "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": int(xs_host.numel() * 4), "d2h_bytes_per_step": 4},

@@ -255,6 +255,16 @@ nsp_status nsp_linear_fwd_save(int prec, const void* x, const void* x_lo, int64_
                                void* out, int64_t ldo, int out_bf16, void* out2, int64_t ldo2,
                                void* pre, int64_t ldpre, void* stream);
 
+/* Process-wide tuning switch for nsp_linear_fwd / nsp_linear_fwd_save with NSP_PREC_BF16 (no reference counterpart; same
+ * results either way):  0 = every epilogue thread writes its output row with vector stores (default),
+ * 1 = outputs (and the residual operand) move through swizzled shared-memory tiles and TMA bulk tensor copies
+ * (gemm_tma_epi.cu) for the shapes inside that kernel's envelope, mode 0 elsewhere.  Not thread-safe against
+ * concurrent GEMM calls; set it once at start-up. */
+nsp_status nsp_set_gemm_epilogue(int mode);
+int nsp_get_gemm_epilogue(void);
+/* number of GEMM calls of this process that ran the mode-1 kernel (diagnostics / tests) */
+long long nsp_gemm_tma_epilogue_launches(void);
+
 /* Weight gradient of out = x w^T (nn.Linear / 1x1 Conv1d):  dw[N,K] (+)= alpha * dy[M,N]^T x[M,K]  on tcgen05
  * with MN-major operands (no transposed copies) and split-K reduction by red.global.add.  NSP_PREC_BF16 only
  * (returns NSP_ERR_UNSUPPORTED otherwise: tf32 MN-major operands need another swizzle atom; parity-mode weight

@@ -181,3 +181,15 @@ for _name, (_res, _args) in _more.items():
     _fn.restype = _res
     _fn.argtypes = _args
 SIGNATURES.update(_more)
+
+_more = {"nsp_set_gemm_epilogue": (c_int, [c_int]), "nsp_get_gemm_epilogue": (c_int, []),
+         "nsp_gemm_tma_epilogue_launches": (ctypes.c_longlong, [])}
+for _name, (_res, _args) in _more.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+SIGNATURES.update(_more)
+
+# opt-in (until validated on hardware): NSP_GEMM_EPILOGUE=tma routes the large bf16 GEMMs through gemm_tma_epi.cu
+if os.environ.get("NSP_GEMM_EPILOGUE", "").lower() == "tma":
+    check(lib.nsp_set_gemm_epilogue(1), "nsp_set_gemm_epilogue")
