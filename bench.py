@@ -515,7 +515,7 @@ def main():
                                encoder_fwd_tflop_per_step=fl_utt * B / 1e12, enc_out_frames=Tp,
                                cuda_graph=graph_ok, cuda_graph_error=graph_error, n_params=n_params,
                                allreduce=(args.allreduce if world > 1 else None),
-                               gemm_epilogue=("tma" if _lib.lib.nsp_get_gemm_epilogue() == 1 else "direct")),
+                               gemm_epilogue=("direct", "tma", "tma+cta_pairs")[_lib.lib.nsp_get_gemm_epilogue()]),
                 "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": int(xs_host.numel() * 4), "d2h_bytes_per_step": 4},

@@ -256,14 +256,18 @@ nsp_status nsp_linear_fwd_save(int prec, const void* x, const void* x_lo, int64_
                                void* pre, int64_t ldpre, void* stream);
 
 /* Process-wide tuning switch for nsp_linear_fwd / nsp_linear_fwd_save with NSP_PREC_BF16 (no reference counterpart; same
- * results either way):  0 = every epilogue thread writes its output row with vector stores (default),
- * 1 = outputs (and the residual operand) move through swizzled shared-memory tiles and TMA bulk tensor copies
- * (gemm_tma_epi.cu) for the shapes inside that kernel's envelope, mode 0 elsewhere.  Not thread-safe against
- * concurrent GEMM calls; set it once at start-up. */
+ * results in every mode):
+ *   0 = every epilogue thread writes its output row with vector stores (default);
+ *   1 = outputs (and the residual operand) move through swizzled shared-memory tiles and TMA bulk tensor copies
+ *       (gemm_tma_epi.cu) for the shapes inside that kernel's envelope, mode 0 elsewhere;
+ *   2 = mode 1, and problems with enough 256-row tiles run on CTA pairs (clusters of 2, tcgen05 cta_group::2: each CTA
+ *       stages half of the W tile, halving the L2->shared-memory operand traffic per FLOP).
+ * Not thread-safe against concurrent GEMM calls; set it once at start-up. */
 nsp_status nsp_set_gemm_epilogue(int mode);
 int nsp_get_gemm_epilogue(void);
-/* number of GEMM calls of this process that ran the mode-1 kernel (diagnostics / tests) */
+/* number of GEMM calls of this process that ran the mode-1/2 kernel, and how many of those as CTA pairs (diagnostics / tests) */
 long long nsp_gemm_tma_epilogue_launches(void);
+long long nsp_gemm_cta_pair_launches(void);
 
 /* Weight gradient of out = x w^T (nn.Linear / 1x1 Conv1d):  dw[N,K] (+)= alpha * dy[M,N]^T x[M,K]  on tcgen05
  * with MN-major operands (no transposed copies) and split-K reduction by red.global.add.  NSP_PREC_BF16 only

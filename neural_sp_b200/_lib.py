@@ -183,13 +183,18 @@ for _name, (_res, _args) in _more.items():
 SIGNATURES.update(_more)
 
 _more = {"nsp_set_gemm_epilogue": (c_int, [c_int]), "nsp_get_gemm_epilogue": (c_int, []),
-         "nsp_gemm_tma_epilogue_launches": (ctypes.c_longlong, [])}
+         "nsp_gemm_tma_epilogue_launches": (ctypes.c_longlong, []), "nsp_gemm_cta_pair_launches": (ctypes.c_longlong, [])}
 for _name, (_res, _args) in _more.items():
     _fn = getattr(lib, _name)
     _fn.restype = _res
     _fn.argtypes = _args
 SIGNATURES.update(_more)
 
-# opt-in (until validated on hardware): NSP_GEMM_EPILOGUE=tma routes the large bf16 GEMMs through gemm_tma_epi.cu
-if os.environ.get("NSP_GEMM_EPILOGUE", "").lower() == "tma":
-    check(lib.nsp_set_gemm_epilogue(1), "nsp_set_gemm_epilogue")
+# opt-in (until validated on hardware): NSP_GEMM_EPILOGUE=tma routes the large bf16 GEMMs through gemm_tma_epi.cu,
+# NSP_GEMM_EPILOGUE=pair additionally runs the largest ones on CTA pairs (cta_group::2)
+_GEMM_MODES = {"": 0, "direct": 0, "tma": 1, "pair": 2}
+_mode = os.environ.get("NSP_GEMM_EPILOGUE", "").lower()
+if _mode not in _GEMM_MODES:
+    raise NspError("NSP_GEMM_EPILOGUE=%r (expected one of %s)" % (_mode, sorted(k for k in _GEMM_MODES if k)))
+if _GEMM_MODES[_mode]:
+    check(lib.nsp_set_gemm_epilogue(_GEMM_MODES[_mode]), "nsp_set_gemm_epilogue")

@@ -9,10 +9,11 @@ nsp_status gemm_dispatch(int precision, const void* a, const void* a_lo, int64_t
 void set_gemm_epilogue_mode(int mode);
 int gemm_epilogue_mode();
 long long gemm_ts_launch_count();
+long long gemm_pair_launch_count();
 }
 
 extern "C" nsp_status nsp_set_gemm_epilogue(int mode) {
-    NSP_CHECK_ARG(mode == 0 || mode == 1, "nsp_set_gemm_epilogue: mode=%d (0 = direct stores, 1 = TMA-store epilogue)", mode);
+    NSP_CHECK_ARG(mode >= 0 && mode <= 2, "nsp_set_gemm_epilogue: mode=%d (0 = direct stores, 1 = TMA-store epilogue, 2 = 1 + CTA pairs)", mode);
     nsp::set_gemm_epilogue_mode(mode);
     return NSP_OK;
 }
@@ -20,6 +21,7 @@ extern "C" nsp_status nsp_set_gemm_epilogue(int mode) {
 extern "C" int nsp_get_gemm_epilogue(void) { return nsp::gemm_epilogue_mode(); }
 
 extern "C" long long nsp_gemm_tma_epilogue_launches(void) { return nsp::gemm_ts_launch_count(); }
+extern "C" long long nsp_gemm_cta_pair_launches(void) { return nsp::gemm_pair_launch_count(); }
 
 extern "C" nsp_status nsp_linear_fwd(int prec, const void* x, const void* x_lo, int64_t ldx,
                                      const void* w, const void* w_lo, int64_t ldw,

@@ -451,11 +451,12 @@ nsp_status dispatch_epi(const GemmMaps& maps, const GemmArgs& g, int glu, int ac
 }  // namespace
 
 // gemm_tma_epi.cu: same GEMM with a shared-memory staged TMA-store epilogue
-nsp_status gemm_ts_dispatch(const void* a, int64_t lda, const void* w, int64_t ldw, int M, int N, int K, int glu, int act,
-                            const float* bias, const float* residual, int64_t ldr, float alpha, void* out, int64_t ldo,
-                            int out_bf16, void* pre, int64_t ldpre, int BN, cudaStream_t st, bool* handled);
+nsp_status gemm_ts_dispatch(int mode, const void* a, int64_t lda, const void* w, int64_t ldw, int M, int N, int K, int glu,
+                            int act, const float* bias, const float* residual, int64_t ldr, float alpha, void* out, int64_t ldo,
+                            int out_bf16, void* pre, int64_t ldpre, int bn1, cudaStream_t st, bool* handled);
 
-static int g_epilogue_mode = 0;      // 0 = per-thread vector stores, 1 = TMA-store epilogue where its envelope allows
+static int g_epilogue_mode = 0;      // 0 = per-thread vector stores, 1 = TMA-store epilogue where its envelope allows,
+                                     // 2 = 1 + CTA pairs (256-row tiles) for the large problems
 void set_gemm_epilogue_mode(int mode) { g_epilogue_mode = mode; }
 int gemm_epilogue_mode() { return g_epilogue_mode; }
 
@@ -486,9 +487,9 @@ nsp_status gemm_dispatch(int precision, const void* a, const void* a_lo, int64_t
     int BN = 128;
     if (!glu && (int64_t)ceil_div(M, BM) * ceil_div(nout, 128) < num_sms() && nout > 64) BN = 64;
     else if (!glu && nout % 256 == 0 && (int64_t)ceil_div(M, BM) * (nout / 256) >= 3 * (int64_t)num_sms()) BN = 256;
-    if (bf16 && g_epilogue_mode == 1 && !out2) {
+    if (bf16 && g_epilogue_mode >= 1 && !out2) {
         bool handled = false;
-        const nsp_status r = gemm_ts_dispatch(a, lda, w, ldw, M, N, K, glu, act, bias, residual, ldr, alpha, out, ldo, out_bf16,
+        const nsp_status r = gemm_ts_dispatch(g_epilogue_mode, a, lda, w, ldw, M, N, K, glu, act, bias, residual, ldr, alpha, out, ldo, out_bf16,
                                               pre, ldpre, BN, st, &handled);
         if (handled) return r;
     }

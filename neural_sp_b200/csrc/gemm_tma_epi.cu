@@ -47,6 +47,7 @@ bool encode_2d(CUtensorMap* out, const void* base, bool is_bf16, uint64_t rows, 
 }
 
 long long g_ts_launches = 0;         // how many GEMMs took this kernel (tests check that the envelope logic routes here)
+long long g_pair_launches = 0;       // ... of which as CTA pairs
 
 constexpr int BM = 128;
 constexpr int KBYTES = 128;
@@ -119,6 +120,53 @@ __device__ __forceinline__ void st_row_bf16(uint8_t* tile, int r, const float* v
                pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7]));
 }
 
+// ---- CTA-pair (cta_group::2) plumbing: PTX forms as used by cute/arch/{copy_sm100_tma,mma_sm100_umma}.hpp and
+// cutlass/arch/barrier.h for 2-SM kernels ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {            // every thread of both CTAs
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {     // shared::cluster address in CTA `rank`
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+// tile into the executing CTA's shared memory, completion bytes onto a barrier that may live in the peer CTA
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(tc::smem_u32(smem_dst)), "l"(m), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_holder) {   // one full warp in EACH CTA, same warp index
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                 :: "r"(tc::smem_u32(smem_holder)), "n"(NCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(taddr), "n"(NCOLS) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[256 rows: 128 per CTA] * B[N rows: N/2 per CTA]^T, issued by the leader CTA only
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// one arrival on the barrier at the same shared-memory offset in both CTAs when the leader's MMAs retire
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(tc::smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
 // bounded mbarrier wait: a lost arrival becomes an error with a message instead of a hung GPU
 __device__ __forceinline__ void bwait(uint64_t* bar, uint32_t parity, int what) {
     if (tc::mbar_try_wait(bar, parity)) return;
@@ -131,10 +179,15 @@ __device__ __forceinline__ void bwait(uint64_t* bar, uint32_t parity, int what) 
     }
 }
 
-template <int BN, int STAGES, int ACT, bool GLU, bool RES, bool OUTBF16>
+// TWO = CTA pair (cluster of 2, cta_group::2): the pair computes a 256 x BN tile; each CTA stages its own 128 rows of A and
+// BN/2 rows of W per k-block (half the L2->SMEM operand traffic per FLOP of the single-CTA tile), the leader CTA issues
+// the M = 256 MMAs for both, and each CTA runs the epilogue of its own 128 accumulator rows.
+template <int BN, int STAGES, int ACT, bool GLU, bool RES, bool OUTBF16, bool TWO>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_ts_kernel(const __grid_constant__ TsMaps maps, const TsArgs g) {
+    static_assert(!(TWO && GLU), "GLU is single-CTA only");
     constexpr int A_BYTES = BM * KBYTES;
-    constexpr int B_BYTES = BN * KBYTES;
+    constexpr int B_BYTES = (TWO ? BN / 2 : BN) * KBYTES;
+    constexpr int TILE_M = TWO ? 2 * BM : BM;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr int TMEM_COLS = 2 * BN;
     constexpr int BN_OUT = GLU ? BN / 2 : BN;
@@ -158,10 +211,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ts_kernel(const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nout = GLU ? g.N / 2 : g.N;
-    const int m_tiles = (g.M + BM - 1) / BM;
+    const int m_tiles = (g.M + TILE_M - 1) / TILE_M;
     const int n_tiles = (nout + BN_OUT - 1) / BN_OUT;
     const int num_tiles = m_tiles * n_tiles;
     const int kblocks = (g.K + BK - 1) / BK;
+    const uint32_t rank = TWO ? cluster_ctarank() : 0u;              // 0 = leader of the pair
+    const int tile0 = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&maps.a); tc::tma_prefetch_desc(&maps.b); tc::tma_prefetch_desc(&maps.out);
@@ -169,14 +225,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ts_kernel(const __grid_const
         if constexpr (RES) tc::tma_prefetch_desc(&maps.res);
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < STAGES; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull_bar[i], 1); tc::mbar_init(&tempty_bar[i], NEPI_WARPS); }
+        // pair: the full / accumulator-empty barriers that matter are the leader's (one arrival per CTA's producer, one per
+        // epilogue warp of both CTAs); stage-empty / accumulator-full are per CTA, signalled by the leader's multicast commit
+        for (int i = 0; i < STAGES; ++i) { tc::mbar_init(&full_bar[i], TWO ? 2 : 1); tc::mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull_bar[i], 1); tc::mbar_init(&tempty_bar[i], (TWO ? 2 : 1) * NEPI_WARPS); }
         for (int i = 0; i < NEPI_WARPS; ++i) tc::mbar_init(&res_bar[i], 1);
         tc::fence_barrier_init();
     }
-    if (warp == 2) tc::tmem_alloc<TMEM_COLS>(tmem_holder);
+    if (warp == 2) {
+        if constexpr (TWO) tmem_alloc_pair<TMEM_COLS>(tmem_holder);
+        else tc::tmem_alloc<TMEM_COLS>(tmem_holder);
+    }
     tc::tc_fence_before();
-    __syncthreads();
+    if constexpr (TWO) cluster_sync_all();       // barrier inits and the allocation of BOTH CTAs are visible before any traffic
+    else __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
@@ -184,12 +246,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ts_kernel(const __grid_const
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     bwait(&empty_bar[stage], phase ^ 1, 0);
                     uint8_t* sa = smem + stage * STAGE_BYTES;
                     uint8_t* sb = sa + A_BYTES;
+                    if constexpr (TWO) {
+                        const uint32_t lead_bar = mapa_rank(tc::smem_u32(&full_bar[stage]), 0);
+                        if (rank == 0) tc::mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);   // bytes of both CTAs
+                        tma_load_2d_pair(sa, &maps.a, lead_bar, kb * BK, m_blk * TILE_M + (int)rank * BM);
+                        tma_load_2d_pair(sb, &maps.b, lead_bar, kb * BK, n_blk * BN + (int)rank * (BN / 2));
+                        if (rank != 0) mbar_arrive_cluster(lead_bar);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     tc::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
                     tc::tma_load_2d(sa, &maps.a, &full_bar[stage], kb * BK, m_blk * BM);
                     if constexpr (!GLU) {
@@ -204,11 +275,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ts_kernel(const __grid_const
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (single thread) =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = tc::make_idesc(1u, BM, BN);
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = tc::make_idesc(1u, TILE_M, BN);
             int stage = 0; uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
                 bwait(&tempty_bar[as], aphase ^ 1, 1);
@@ -224,13 +295,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ts_kernel(const __grid_const
 #pragma unroll
                     for (int k = 0; k < BK / UK; ++k) {
                         const uint64_t koff = (uint64_t)((k * 32) >> 4);     // +32 bytes of K inside the swizzle atom
-                        tc::umma_f16(d_tmem, adesc + koff, bdesc + koff, idesc, accum);
+                        if constexpr (TWO) umma_f16_pair(d_tmem, adesc + koff, bdesc + koff, idesc, accum);
+                        else tc::umma_f16(d_tmem, adesc + koff, bdesc + koff, idesc, accum);
                         accum = 1;
                     }
-                    tc::umma_commit(&empty_bar[stage]);
+                    if constexpr (TWO) umma_commit_pair(&empty_bar[stage]);
+                    else tc::umma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                tc::umma_commit(&tfull_bar[as]);
+                if constexpr (TWO) umma_commit_pair(&tfull_bar[as]);
+                else tc::umma_commit(&tfull_bar[as]);
             }
         }
     } else {
@@ -245,11 +319,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ts_kernel(const __grid_const
         uint32_t rphase = 0;
         int slot = 0;
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
             const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
-            const int row0 = m_blk * BM + q * 32;               // first row of this warp's sub-tiles
+            const int row0 = m_blk * TILE_M + (int)rank * BM + q * 32;   // first row of this warp's sub-tiles
             const int col0 = n_blk * BN_OUT + half * COLS_PER_WARP;
             const bool live = row0 < g.M && col0 < nout;        // warp-uniform: anything to write at all
             if constexpr (RES) {
@@ -378,35 +452,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ts_kernel(const __grid_const
             }
             tc::tc_fence_before();
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&tempty_bar[as]);
+            if (lane == 0) {
+                if constexpr (TWO) mbar_arrive_cluster(mapa_rank(tc::smem_u32(&tempty_bar[as]), 0));   // the leader's MMA issuer waits
+                else tc::mbar_arrive(&tempty_bar[as]);
+            }
         }
         if (lane == 0) bulk_wait_read<0>();                          // staging tiles must outlive the bulk stores reading them
     }
 
     tc::tc_fence_before();
-    __syncthreads();
+    if constexpr (TWO) cluster_sync_all();       // neither CTA may retire (or free TMEM) while the pair's MMAs / arrivals can touch it
+    else __syncthreads();
     if (warp == 2) {
         tc::tc_fence_after();
-        tc::tmem_dealloc<TMEM_COLS>(tmem_base);
+        if constexpr (TWO) tmem_dealloc_pair<TMEM_COLS>(tmem_base);
+        else tc::tmem_dealloc<TMEM_COLS>(tmem_base);
     }
 }
 
-template <int BN, bool GLU, bool RES, bool OUTBF16>
+template <int BN, bool GLU, bool RES, bool OUTBF16, bool TWO>
+constexpr int ts_staging_bytes() {
+    return NEPI_WARPS * (RES ? ((GLU ? BN / 2 : BN) / 2 / CW) * 4096 : 2 * (OUTBF16 ? 2048 : 4096));
+}
+template <int BN, bool GLU, bool RES, bool OUTBF16, bool TWO>
 constexpr int ts_stages() {
-    constexpr int stg = NEPI_WARPS * (RES ? ((GLU ? BN / 2 : BN) / 2 / CW) * 4096 : 2 * (OUTBF16 ? 2048 : 4096));
-    constexpr int n = (224 * 1024 - stg) / (BM * KBYTES + BN * KBYTES);
+    constexpr int stage = BM * KBYTES + (TWO ? BN / 2 : BN) * KBYTES;
+    constexpr int n = (224 * 1024 - ts_staging_bytes<BN, GLU, RES, OUTBF16, TWO>()) / stage;
     return n > 8 ? 8 : n;
 }
 
-template <int BN, int ACT, bool GLU, bool RES, bool OUTBF16>
+template <int BN, int ACT, bool GLU, bool RES, bool OUTBF16, bool TWO>
 nsp_status launch_ts(const TsMaps& maps, const TsArgs& g, cudaStream_t st) {
-    constexpr int STAGES = ts_stages<BN, GLU, RES, OUTBF16>();
-    constexpr int COLS_PER_WARP = (GLU ? BN / 2 : BN) / 2;
-    constexpr int STG = NEPI_WARPS * (RES ? (COLS_PER_WARP / CW) * 4096 : 2 * (OUTBF16 ? 2048 : 4096));
-    constexpr size_t smem = (size_t)STAGES * (BM * KBYTES + BN * KBYTES) + STG + 1024 /*align*/ + 512 /*barriers*/;
+    constexpr int STAGES = ts_stages<BN, GLU, RES, OUTBF16, TWO>();
+    constexpr size_t smem = (size_t)STAGES * (BM * KBYTES + (TWO ? BN / 2 : BN) * KBYTES) + ts_staging_bytes<BN, GLU, RES, OUTBF16, TWO>()
+                            + 1024 /*align*/ + 512 /*barriers*/;
     static_assert(smem <= 227 * 1024, "shared memory budget");
     static_assert(STAGES >= 3, "pipeline depth");
-    auto kern = gemm_ts_kernel<BN, STAGES, ACT, GLU, RES, OUTBF16>;
+    auto kern = gemm_ts_kernel<BN, STAGES, ACT, GLU, RES, OUTBF16, TWO>;
     static bool attr_set = false;
     if (!attr_set) {
         NSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -414,39 +496,55 @@ nsp_status launch_ts(const TsMaps& maps, const TsArgs& g, cudaStream_t st) {
     }
     const int nout = GLU ? g.N / 2 : g.N;
     const int bn_out = GLU ? BN / 2 : BN;
-    const int tiles = ceil_div(g.M, BM) * ceil_div(nout, bn_out);
-    const int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, NTHREADS, smem, st>>>(maps, g);
-    NSP_LAUNCH_OK();
+    const int tiles = ceil_div(g.M, TWO ? 2 * BM : BM) * ceil_div(nout, bn_out);
+    if constexpr (TWO) {
+        const int pairs = num_sms() / 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
+        cfg.blockDim = dim3(NTHREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        NSP_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, maps, g));
+    } else {
+        const int grid = tiles < num_sms() ? tiles : num_sms();
+        kern<<<grid, NTHREADS, smem, st>>>(maps, g);
+        NSP_LAUNCH_OK();
+    }
     ++g_ts_launches;
+    if (TWO) ++g_pair_launches;
     return NSP_OK;
 }
 
-template <int BN>
+template <int BN, bool TWO>
 nsp_status dispatch_ts(const TsMaps& maps, const TsArgs& g, int glu, int act, bool res, int out_bf16, cudaStream_t st) {
     if (glu) {
-        if constexpr (BN == 128) {
-            return out_bf16 ? launch_ts<128, ACT_NONE, true, false, true>(maps, g, st)
-                            : launch_ts<128, ACT_NONE, true, false, false>(maps, g, st);
+        if constexpr (BN == 128 && !TWO) {
+            return out_bf16 ? launch_ts<128, ACT_NONE, true, false, true, false>(maps, g, st)
+                            : launch_ts<128, ACT_NONE, true, false, false, false>(maps, g, st);
         } else {
-            set_error("gemm(tma epilogue): GLU needs the 128-wide tile"); return NSP_ERR_INVALID;
+            set_error("gemm(tma epilogue): GLU needs the single-CTA 128-wide tile"); return NSP_ERR_INVALID;
         }
     }
     if (res) {
-        if constexpr (BN == 128) return launch_ts<128, ACT_NONE, false, true, false>(maps, g, st);
+        if constexpr (BN == 128) return launch_ts<128, ACT_NONE, false, true, false, TWO>(maps, g, st);
         else { set_error("gemm(tma epilogue): residual needs the 128-wide tile"); return NSP_ERR_INVALID; }
     }
     switch (act) {
-        case ACT_NONE: return out_bf16 ? launch_ts<BN, ACT_NONE, false, false, true>(maps, g, st)
-                                       : launch_ts<BN, ACT_NONE, false, false, false>(maps, g, st);
-        case ACT_RELU: return out_bf16 ? launch_ts<BN, ACT_RELU, false, false, true>(maps, g, st)
-                                       : launch_ts<BN, ACT_RELU, false, false, false>(maps, g, st);
-        case ACT_SWISH: return out_bf16 ? launch_ts<BN, ACT_SWISH, false, false, true>(maps, g, st)
-                                        : launch_ts<BN, ACT_SWISH, false, false, false>(maps, g, st);
-        case ACT_GELU: return out_bf16 ? launch_ts<BN, ACT_GELU, false, false, true>(maps, g, st)
-                                       : launch_ts<BN, ACT_GELU, false, false, false>(maps, g, st);
-        case ACT_GELU_TANH: return out_bf16 ? launch_ts<BN, ACT_GELU_TANH, false, false, true>(maps, g, st)
-                                            : launch_ts<BN, ACT_GELU_TANH, false, false, false>(maps, g, st);
+        case ACT_NONE: return out_bf16 ? launch_ts<BN, ACT_NONE, false, false, true, TWO>(maps, g, st)
+                                       : launch_ts<BN, ACT_NONE, false, false, false, TWO>(maps, g, st);
+        case ACT_RELU: return out_bf16 ? launch_ts<BN, ACT_RELU, false, false, true, TWO>(maps, g, st)
+                                       : launch_ts<BN, ACT_RELU, false, false, false, TWO>(maps, g, st);
+        case ACT_SWISH: return out_bf16 ? launch_ts<BN, ACT_SWISH, false, false, true, TWO>(maps, g, st)
+                                        : launch_ts<BN, ACT_SWISH, false, false, false, TWO>(maps, g, st);
+        case ACT_GELU: return out_bf16 ? launch_ts<BN, ACT_GELU, false, false, true, TWO>(maps, g, st)
+                                       : launch_ts<BN, ACT_GELU, false, false, false, TWO>(maps, g, st);
+        case ACT_GELU_TANH: return out_bf16 ? launch_ts<BN, ACT_GELU_TANH, false, false, true, TWO>(maps, g, st)
+                                            : launch_ts<BN, ACT_GELU_TANH, false, false, false, TWO>(maps, g, st);
     }
     set_error("gemm(tma epilogue): act=%d", act);
     return NSP_ERR_INVALID;
@@ -457,30 +555,43 @@ bool aligned16(const void* p, int64_t ld, int es) { return ((uintptr_t)p % 16 ==
 }  // namespace
 
 long long gemm_ts_launch_count() { return g_ts_launches; }
+long long gemm_pair_launch_count() { return g_pair_launches; }
 
-// Called by gemm_dispatch (gemm_tcgen05.cu) for bf16 operands when the epilogue mode is 1.  *handled = false means
-// "outside this kernel's envelope" (the caller runs the direct-store kernel); otherwise the return value is final.
-nsp_status gemm_ts_dispatch(const void* a, int64_t lda, const void* w, int64_t ldw, int M, int N, int K, int glu, int act,
-                            const float* bias, const float* residual, int64_t ldr, float alpha, void* out, int64_t ldo,
-                            int out_bf16, void* pre, int64_t ldpre, int BN, cudaStream_t st, bool* handled) {
+// Called by gemm_dispatch (gemm_tcgen05.cu) for bf16 operands when the epilogue mode is 1 or 2.  bn1 = the tile width the
+// single-CTA heuristic picked.  *handled = false means "outside this kernel's envelope" (the caller runs the direct-store
+// kernel); otherwise the return value is final.
+nsp_status gemm_ts_dispatch(int mode, const void* a, int64_t lda, const void* w, int64_t ldw, int M, int N, int K, int glu,
+                            int act, const float* bias, const float* residual, int64_t ldr, float alpha, void* out, int64_t ldo,
+                            int out_bf16, void* pre, int64_t ldpre, int bn1, cudaStream_t st, bool* handled) {
     *handled = false;
     const int nout = glu ? N / 2 : N;
     const bool res = residual != nullptr;
-    if (BN != 128 && BN != 256) return NSP_OK;                       // small problems stay on the direct-store kernel
     if (nout % CW != 0) return NSP_OK;
-    if (res && (BN != 128 || out_bf16 || pre || act != ACT_NONE || glu)) return NSP_OK;
-    if (glu && BN != 128) return NSP_OK;
+    if (res && (out_bf16 || pre || act != ACT_NONE || glu)) return NSP_OK;
     if (!aligned16(out, ldo, out_bf16 ? 2 : 4)) return NSP_OK;
     if (pre && !aligned16(pre, ldpre, 2)) return NSP_OK;
     if (res && !aligned16(residual, ldr, 4)) return NSP_OK;
     if (bias && ((uintptr_t)bias % 4 != 0)) return NSP_OK;
+    // CTA pairs (mode 2): 256 x {256,128} tiles when they still fill most of the 74 pairs
+    bool two = false;
+    int BN = bn1;
+    if (mode == 2 && !glu) {
+        const int bn2 = (!res && nout % 256 == 0) ? 256 : 128;
+        const int64_t tiles2 = (int64_t)ceil_div(M, 2 * BM) * ceil_div(nout, bn2);
+        if (tiles2 * 5 >= (int64_t)(num_sms() / 2) * 4) { two = true; BN = bn2; }
+    }
+    if (!two) {
+        if (BN != 128 && BN != 256) return NSP_OK;                   // small problems stay on the direct-store kernel
+        if (res && BN != 128) return NSP_OK;
+        if (glu && BN != 128) return NSP_OK;
+    }
     *handled = true;
     TsMaps maps;
     TsArgs g;
     g.M = M; g.N = N; g.K = K; g.bias = bias; g.alpha = alpha; g.has_pre = pre != nullptr;
+    const uint32_t box_b = two ? (uint32_t)(BN / 2) : (glu ? (uint32_t)(BN / 2) : (uint32_t)BN);
     if (!make_tmap_2d(&maps.a, a, 2, true, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM)) return NSP_ERR_INVALID;
-    if (!make_tmap_2d(&maps.b, w, 2, true, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, glu ? (uint32_t)(BN / 2) : (uint32_t)BN))
-        return NSP_ERR_INVALID;
+    if (!make_tmap_2d(&maps.b, w, 2, true, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, box_b)) return NSP_ERR_INVALID;
     if (!encode_2d(&maps.out, out, out_bf16 != 0, (uint64_t)M, (uint64_t)nout, (uint64_t)ldo, 32, CW,
                    out_bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, "out")) return NSP_ERR_INVALID;
     maps.pre = maps.out;
@@ -489,7 +600,10 @@ nsp_status gemm_ts_dispatch(const void* a, int64_t lda, const void* w, int64_t l
         return NSP_ERR_INVALID;
     if (res && !encode_2d(&maps.res, residual, false, (uint64_t)M, (uint64_t)nout, (uint64_t)ldr, 32, CW,
                           CU_TENSOR_MAP_SWIZZLE_128B, "residual")) return NSP_ERR_INVALID;
-    return BN == 256 ? dispatch_ts<256>(maps, g, glu, act, res, out_bf16, st) : dispatch_ts<128>(maps, g, glu, act, res, out_bf16, st);
+    if (two) return BN == 256 ? dispatch_ts<256, true>(maps, g, glu, act, res, out_bf16, st)
+                              : dispatch_ts<128, true>(maps, g, glu, act, res, out_bf16, st);
+    return BN == 256 ? dispatch_ts<256, false>(maps, g, glu, act, res, out_bf16, st)
+                     : dispatch_ts<128, false>(maps, g, glu, act, res, out_bf16, st);
 }
 
 }  // namespace nsp

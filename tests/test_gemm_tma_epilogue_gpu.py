@@ -10,17 +10,26 @@ from test_gemm_gpu import _ref
 pytestmark = [pytest.mark.gpu, pytest.mark.experimental]
 
 
-@pytest.fixture
-def tma_epilogue():
+def _mode(mode):
     from neural_sp_b200 import _lib
     old = _lib.lib.nsp_get_gemm_epilogue()
-    _lib.check(_lib.lib.nsp_set_gemm_epilogue(1), "nsp_set_gemm_epilogue")
+    _lib.check(_lib.lib.nsp_set_gemm_epilogue(mode), "nsp_set_gemm_epilogue")
     yield _lib.lib
     _lib.lib.nsp_set_gemm_epilogue(old)
 
 
+@pytest.fixture
+def tma_epilogue():
+    yield from _mode(1)
+
+
+@pytest.fixture
+def cta_pairs():
+    yield from _mode(2)
+
+
 def _run(lib, M, N, K, bias=True, act=None, glu=False, residual=False, alpha=1.0, out_dtype=torch.float32, save_pre=False,
-         expect_tma=True):
+         expect_tma=True, expect_pair=False):
     from neural_sp_b200 import ops
     torch.manual_seed(M * 7 + N * 3 + K)
     x = torch.randn(M, K, device="cuda")
@@ -30,11 +39,12 @@ def _run(lib, M, N, K, bias=True, act=None, glu=False, residual=False, alpha=1.0
     r = torch.randn(M, nout, device="cuda") if residual else None
     xr, wr = x.bfloat16().float(), w.bfloat16().float()
     ref = _ref(xr, wr, b, act, glu, r, alpha)
-    before = lib.nsp_gemm_tma_epilogue_launches()
+    before, before2 = lib.nsp_gemm_tma_epilogue_launches(), lib.nsp_gemm_cta_pair_launches()
     res = ops.linear(x, ops.prepare_weight(w, "bf16"), b, prec="bf16", act=act, glu=glu, residual=r, alpha=alpha,
                      out_dtype=out_dtype, save_pre=save_pre)
     torch.cuda.synchronize()
     assert (lib.nsp_gemm_tma_epilogue_launches() - before == 1) == expect_tma, "envelope routing"
+    assert (lib.nsp_gemm_cta_pair_launches() - before2 == 1) == expect_pair, "CTA-pair routing"
     out, pre = res if save_pre else (res, None)
     assert out.shape == (M, nout)
     tol = 8e-3 if out_dtype == torch.bfloat16 else 1e-4
@@ -107,3 +117,29 @@ def test_strided_output_views(tma_epilogue):
     ref = x.bfloat16().double() @ w.bfloat16().double().t()
     assert (out.double() - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
     assert torch.all(buf[:, :N] == 7.0) and torch.all(buf[:, 2 * N:] == 7.0)
+
+
+# ---------------------------------------------------------------------------------------------
+# mode 2: CTA pairs (cta_group::2), 256-row tiles.  Run these only after the mode-1 tests above are green.
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M", [16000, 16037, 16200])             # 16200: the second CTA of the last pair has no live rows
+def test_cta_pairs_plain(cta_pairs, M):
+    _run(cta_pairs, M, 512, 512, expect_pair=True)                                         # 256 x 256 tiles, fp32 out
+    _run(cta_pairs, M, 2048, 512, out_dtype=torch.bfloat16, bias=False, expect_pair=True)
+    _run(cta_pairs, M, 1536, 512, out_dtype=torch.bfloat16, expect_pair=True)              # fused QKV projection
+    _run(cta_pairs, M, 640, 512, expect_pair=True)                                         # 256 x 128 tiles (640 % 256 != 0)
+
+
+def test_cta_pairs_epilogues(cta_pairs):
+    _run(cta_pairs, 16037, 2048, 512, act="swish", out_dtype=torch.bfloat16, save_pre=True, expect_pair=True)
+    _run(cta_pairs, 16037, 512, 2048, residual=True, alpha=0.5, expect_pair=True)          # residual: 256 x 128 tiles
+    _run(cta_pairs, 8000, 512, 512, residual=True, expect_pair=True)
+    _run(cta_pairs, 8000, 2048, 512, act="relu", expect_pair=True)
+    _run(cta_pairs, 16037, 1024, 512, glu=True, out_dtype=torch.bfloat16, save_pre=True)   # GLU stays single-CTA
+    _run(cta_pairs, 4000, 512, 2048, residual=True, expect_pair=True)                      # 64 pair tiles: one 86 % wave
+    _run(cta_pairs, 2000, 512, 2048, residual=True, expect_tma=False)                      # too few tiles for pairs and for 128-wide tiles
+
+
+def test_cta_pairs_long_k_many_tiles_per_pair(cta_pairs):
+    """Several tiles per pair and K = 4096: exercises ring wrap-around, both accumulator stages and the phase bits."""
+    _run(cta_pairs, 40000, 1024, 4096, expect_pair=True)
