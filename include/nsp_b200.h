@@ -268,6 +268,8 @@ int nsp_get_gemm_epilogue(void);
 /* number of GEMM calls of this process that ran the mode-1/2 kernel, and how many of those as CTA pairs (diagnostics / tests) */
 long long nsp_gemm_tma_epilogue_launches(void);
 long long nsp_gemm_cta_pair_launches(void);
+/* modes >= 1 also switch nsp_linear_wgrad from per-thread red.global.add to staged cp.reduce.async.bulk.tensor adds */
+long long nsp_wgrad_tma_epilogue_launches(void);
 
 /* Weight gradient of out = x w^T (nn.Linear / 1x1 Conv1d):  dw[N,K] (+)= alpha * dy[M,N]^T x[M,K]  on tcgen05
  * with MN-major operands (no transposed copies) and split-K reduction by red.global.add.  NSP_PREC_BF16 only

@@ -183,7 +183,8 @@ for _name, (_res, _args) in _more.items():
 SIGNATURES.update(_more)
 
 _more = {"nsp_set_gemm_epilogue": (c_int, [c_int]), "nsp_get_gemm_epilogue": (c_int, []),
-         "nsp_gemm_tma_epilogue_launches": (ctypes.c_longlong, []), "nsp_gemm_cta_pair_launches": (ctypes.c_longlong, [])}
+         "nsp_gemm_tma_epilogue_launches": (ctypes.c_longlong, []), "nsp_gemm_cta_pair_launches": (ctypes.c_longlong, []),
+         "nsp_wgrad_tma_epilogue_launches": (ctypes.c_longlong, [])}
 for _name, (_res, _args) in _more.items():
     _fn = getattr(lib, _name)
     _fn.restype = _res

@@ -10,6 +10,7 @@ void set_gemm_epilogue_mode(int mode);
 int gemm_epilogue_mode();
 long long gemm_ts_launch_count();
 long long gemm_pair_launch_count();
+long long wgrad_tma_launch_count();
 }
 
 extern "C" nsp_status nsp_set_gemm_epilogue(int mode) {
@@ -22,6 +23,7 @@ extern "C" int nsp_get_gemm_epilogue(void) { return nsp::gemm_epilogue_mode(); }
 
 extern "C" long long nsp_gemm_tma_epilogue_launches(void) { return nsp::gemm_ts_launch_count(); }
 extern "C" long long nsp_gemm_cta_pair_launches(void) { return nsp::gemm_pair_launch_count(); }
+extern "C" long long nsp_wgrad_tma_epilogue_launches(void) { return nsp::wgrad_tma_launch_count(); }
 
 extern "C" nsp_status nsp_linear_fwd(int prec, const void* x, const void* x_lo, int64_t ldx,
                                      const void* w, const void* w_lo, int64_t ldw,

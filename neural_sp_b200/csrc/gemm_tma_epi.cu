@@ -19,14 +19,12 @@ namespace nsp {
 
 bool get_tma_encode(void** fn);   // gemm_tcgen05.cu
 
-namespace {
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // row-major [rows, cols] matrix, box = [box_rows, box_cols]; box_cols * elem_bytes must equal the swizzle span
-bool encode_2d(CUtensorMap* out, const void* base, bool is_bf16, uint64_t rows, uint64_t cols, uint64_t ld,
+bool encode_tmap_2d(CUtensorMap* out, const void* base, bool is_bf16, uint64_t rows, uint64_t cols, uint64_t ld,
                uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swz, const char* what) {
     void* fnp = nullptr;
     if (!get_tma_encode(&fnp)) return false;
@@ -39,12 +37,14 @@ bool encode_2d(CUtensorMap* out, const void* base, bool is_bf16, uint64_t rows, 
                                       const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        set_error("gemm(tma epilogue): cuTensorMapEncodeTiled(%s) failed (%d) rows=%llu cols=%llu ld=%llu", what, (int)r,
+        set_error("cuTensorMapEncodeTiled(%s) failed (%d) rows=%llu cols=%llu ld=%llu", what, (int)r,
                   (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
         return false;
     }
     return true;
 }
+
+namespace {
 
 long long g_ts_launches = 0;         // how many GEMMs took this kernel (tests check that the envelope logic routes here)
 long long g_pair_launches = 0;       // ... of which as CTA pairs
@@ -74,50 +74,6 @@ __device__ __forceinline__ float sigmoid_fast(float x) {     // 0.5 + 0.5 * tanh
     float t;
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
     return fmaf(0.5f, t, 0.5f);
-}
-
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-    __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&p);
-}
-
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                 :: "l"(m), "r"(tc::smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
-
-// explicit shared-space accesses (the staging pointers are derived from an aligned generic pointer, which would
-// otherwise compile to generic ST.E / LD.E)
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ void lds128(uint32_t addr, float& a, float& b, float& c, float& d) {
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(addr) : "memory");
-}
-
-// row r (= lane) of a 32 x 32 fp32 sub-tile, SWIZZLE_128B, tile base 1024-byte aligned
-__device__ __forceinline__ void st_row_f32(uint8_t* tile, int r, const float* v) {
-    const uint32_t row = tc::smem_u32(tile) + r * 128;
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-        sts128(row + ((j ^ (r & 7)) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
-               __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
-}
-__device__ __forceinline__ void ld_row_f32(const uint8_t* tile, int r, float* v) {
-    const uint32_t row = tc::smem_u32(tile) + r * 128;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) lds128(row + ((j ^ (r & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-}
-// row r of a 32 x 32 bf16 sub-tile, SWIZZLE_64B, tile base 512-byte aligned
-__device__ __forceinline__ void st_row_bf16(uint8_t* tile, int r, const float* v) {
-    const uint32_t row = tc::smem_u32(tile) + r * 64;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-        sts128(row + ((j ^ ((r >> 1) & 3)) << 4), pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]),
-               pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7]));
 }
 
 // ---- CTA-pair (cta_group::2) plumbing: PTX forms as used by cute/arch/{copy_sm100_tma,mma_sm100_umma}.hpp and
@@ -329,7 +285,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ts_kernel(const __grid_const
             if constexpr (RES) {
                 // the residual sub-tiles do not depend on the accumulator: fetch them under the mainloop of this tile
                 if (live && lane == 0) {
-                    bulk_wait_read<0>();                        // stores of the previous tile have left the staging tiles
+                    tc::bulk_wait_read<0>();                        // stores of the previous tile have left the staging tiles
                     tc::mbar_arrive_expect_tx(rbar, NCH * 4096);
 #pragma unroll
                     for (int ci = 0; ci < NCH; ++ci) tc::tma_load_2d(stg + ci * 4096, &maps.res, rbar, col0 + ci * CW, row0);
@@ -387,20 +343,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ts_kernel(const __grid_const
                 }
                 if (g.has_pre) {                                     // pre-activation(s), bf16, through the slot rotation
                     if constexpr (!RES) {
-                        if (lane == 0) bulk_wait_read<1>();
+                        if (lane == 0) tc::bulk_wait_read<1>();
                         __syncwarp();
-                        st_row_bf16(stg + slot * SLOT, lane, v);
+                        tc::st_row_bf16(stg + slot * SLOT, lane, v);
                         tc::fence_proxy_async_smem();
                         __syncwarp();
-                        if (lane == 0) { tma_store_2d(&maps.pre, stg + slot * SLOT, cbase, row0); bulk_commit(); }
+                        if (lane == 0) { tc::tma_store_2d(&maps.pre, stg + slot * SLOT, cbase, row0); tc::bulk_commit(); }
                         slot ^= 1;
                         if constexpr (GLU) {
-                            if (lane == 0) bulk_wait_read<1>();
+                            if (lane == 0) tc::bulk_wait_read<1>();
                             __syncwarp();
-                            st_row_bf16(stg + slot * SLOT, lane, gv);
+                            tc::st_row_bf16(stg + slot * SLOT, lane, gv);
                             tc::fence_proxy_async_smem();
                             __syncwarp();
-                            if (lane == 0) { tma_store_2d(&maps.pre, stg + slot * SLOT, nout + cbase, row0); bulk_commit(); }
+                            if (lane == 0) { tc::tma_store_2d(&maps.pre, stg + slot * SLOT, nout + cbase, row0); tc::bulk_commit(); }
                             slot ^= 1;
                         }
                     }
@@ -427,26 +383,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ts_kernel(const __grid_const
                 if constexpr (RES) {
                     uint8_t* tile_s = stg + ci * 4096;
                     float rr[32];
-                    ld_row_f32(tile_s, lane, rr);
+                    tc::ld_row_f32(tile_s, lane, rr);
 #pragma unroll
                     for (int j = 0; j < CW; ++j) v[j] = fmaf(g.alpha, v[j], rr[j]);
-                    st_row_f32(tile_s, lane, v);                     // in place: a thread only touches its own row
+                    tc::st_row_f32(tile_s, lane, v);                     // in place: a thread only touches its own row
                     tc::fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) { tma_store_2d(&maps.out, tile_s, cbase, row0); bulk_commit(); }
+                    if (lane == 0) { tc::tma_store_2d(&maps.out, tile_s, cbase, row0); tc::bulk_commit(); }
                 } else {
                     if (g.alpha != 1.f) {
 #pragma unroll
                         for (int j = 0; j < CW; ++j) v[j] *= g.alpha;
                     }
-                    if (lane == 0) bulk_wait_read<1>();              // the store that used this slot two stores ago is done
+                    if (lane == 0) tc::bulk_wait_read<1>();              // the store that used this slot two stores ago is done
                     __syncwarp();
                     uint8_t* tile_s = stg + slot * SLOT;
-                    if constexpr (OUTBF16) st_row_bf16(tile_s, lane, v);
-                    else st_row_f32(tile_s, lane, v);
+                    if constexpr (OUTBF16) tc::st_row_bf16(tile_s, lane, v);
+                    else tc::st_row_f32(tile_s, lane, v);
                     tc::fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) { tma_store_2d(&maps.out, tile_s, cbase, row0); bulk_commit(); }
+                    if (lane == 0) { tc::tma_store_2d(&maps.out, tile_s, cbase, row0); tc::bulk_commit(); }
                     slot ^= 1;
                 }
             }
@@ -457,7 +413,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ts_kernel(const __grid_const
                 else tc::mbar_arrive(&tempty_bar[as]);
             }
         }
-        if (lane == 0) bulk_wait_read<0>();                          // staging tiles must outlive the bulk stores reading them
+        if (lane == 0) tc::bulk_wait_read<0>();                          // staging tiles must outlive the bulk stores reading them
     }
 
     tc::tc_fence_before();
@@ -592,13 +548,13 @@ nsp_status gemm_ts_dispatch(int mode, const void* a, int64_t lda, const void* w,
     const uint32_t box_b = two ? (uint32_t)(BN / 2) : (glu ? (uint32_t)(BN / 2) : (uint32_t)BN);
     if (!make_tmap_2d(&maps.a, a, 2, true, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM)) return NSP_ERR_INVALID;
     if (!make_tmap_2d(&maps.b, w, 2, true, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, box_b)) return NSP_ERR_INVALID;
-    if (!encode_2d(&maps.out, out, out_bf16 != 0, (uint64_t)M, (uint64_t)nout, (uint64_t)ldo, 32, CW,
+    if (!encode_tmap_2d(&maps.out, out, out_bf16 != 0, (uint64_t)M, (uint64_t)nout, (uint64_t)ldo, 32, CW,
                    out_bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, "out")) return NSP_ERR_INVALID;
     maps.pre = maps.out;
     maps.res = maps.out;
-    if (pre && !encode_2d(&maps.pre, pre, true, (uint64_t)M, (uint64_t)N, (uint64_t)ldpre, 32, CW, CU_TENSOR_MAP_SWIZZLE_64B, "pre"))
+    if (pre && !encode_tmap_2d(&maps.pre, pre, true, (uint64_t)M, (uint64_t)N, (uint64_t)ldpre, 32, CW, CU_TENSOR_MAP_SWIZZLE_64B, "pre"))
         return NSP_ERR_INVALID;
-    if (res && !encode_2d(&maps.res, residual, false, (uint64_t)M, (uint64_t)nout, (uint64_t)ldr, 32, CW,
+    if (res && !encode_tmap_2d(&maps.res, residual, false, (uint64_t)M, (uint64_t)nout, (uint64_t)ldr, 32, CW,
                           CU_TENSOR_MAP_SWIZZLE_128B, "residual")) return NSP_ERR_INVALID;
     if (two) return BN == 256 ? dispatch_ts<256, true>(maps, g, glu, act, res, out_bf16, st)
                               : dispatch_ts<128, true>(maps, g, glu, act, res, out_bf16, st);

@@ -12,6 +12,9 @@
 // (split-K) and reduced with vector red.global.add into the fp32 gradient buffer, which is also how gradient
 // accumulation across calls comes for free.
 //   warp 0: TMA producer | warp 1: single-thread MMA issuer | warps 2-5: epilogue (tcgen05.ld -> red.global.add.v4.f32)
+// Epilogue mode 1 (nsp_set_gemm_epilogue >= 1, opt-in): the per-thread vector reds touch 32 lines per warp instruction
+// (~8200 L1 wavefronts for a 128 x 256 tile, several times the mainloop of a short split), so the tile is instead staged as
+// swizzled 32 x 32 fp32 sub-tiles in the (by then idle) operand ring and added by cp.reduce.async.bulk.tensor (L2 adds).
 #include "tc_common.cuh"
 
 namespace nsp {
@@ -25,6 +28,7 @@ constexpr int WG_MAX_SEG = 3;
 struct WgradMaps {
     CUtensorMap a[WG_MAX_SEG];   // dY (hi / lo)
     CUtensorMap b[WG_MAX_SEG];   // X  (hi / lo)
+    CUtensorMap dw;              // epilogue mode 1: fp32 [N, K], box 32 x 32, SWIZZLE_128B
 };
 
 struct WgradArgs {
@@ -49,7 +53,7 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <typename TIn, int BN, int STAGES>
+template <typename TIn, int BN, int STAGES, bool TMAEPI>
 __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradArgs g) {
     constexpr bool kBF16 = sizeof(TIn) == 2;
     constexpr int CHUNK = 128 / (int)sizeof(TIn);          // elements per 128-byte column chunk: 64 / 32
@@ -146,6 +150,34 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
         tc::tc_fence_after();
         const int row = n_blk * WG_BM + q * 32 + lane;           // row of dW
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+        if constexpr (TMAEPI) {
+            // every MMA has retired (tfull), so every stage of the operand ring has been consumed: two 4 KiB staging slots
+            // per warp alias the start of the ring
+            uint8_t* stg = smem + (warp - 2) * 8192;
+            const int row0 = n_blk * WG_BM + q * 32;
+            int slot = 0;
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t r[32];
+                tc::tmem_ld_32x32(t_row + (uint32_t)c, r);
+                tc::tmem_ld_wait();
+                const int col0 = k_blk * BN + c;
+                if (row0 < g.N && col0 < g.K) {                  // warp-uniform; the bulk reduce clips partial sub-tiles
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = g.alpha * __uint_as_float(r[j]);
+                    if (lane == 0) tc::bulk_wait_read<1>();      // the reduce that read this slot two sub-tiles ago is done
+                    __syncwarp();
+                    tc::st_row_f32(stg + slot * 4096, lane, v);
+                    tc::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) { tc::tma_reduce_add_2d(&maps.dw, stg + slot * 4096, col0, row0); tc::bulk_commit(); }
+                    slot ^= 1;
+                }
+            }
+            if (lane == 0) tc::bulk_wait_read<0>();
+            tc::tc_fence_before();
+        } else {
         const bool vec_ok = (g.lddw % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.dw) & 15) == 0);
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
@@ -168,6 +200,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
             }
         }
         tc::tc_fence_before();
+        }
     }
 
     __syncthreads();
@@ -177,13 +210,16 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
     }
 }
 
-template <typename TIn, int BN, int STAGES>
+long long g_wgrad_tma_launches = 0;
+
+template <typename TIn, int BN, int STAGES, bool TMAEPI>
 nsp_status launch_wgrad(const WgradMaps& maps, WgradArgs& g, cudaStream_t st) {
     constexpr int CHUNK = 128 / (int)sizeof(TIn);
     constexpr size_t stage_bytes = (size_t)(WG_BM / CHUNK + BN / CHUNK) * WG_BOX;
     constexpr size_t smem = STAGES * stage_bytes + 1024 + 256;
     static_assert(smem <= 227 * 1024, "wgrad: shared memory budget");
-    auto kern = wgrad_kernel<TIn, BN, STAGES>;
+    static_assert(!TMAEPI || stage_bytes >= 4 * 8192, "staging slots alias the first stage");
+    auto kern = wgrad_kernel<TIn, BN, STAGES, TMAEPI>;
     static bool attr_set = false;
     if (!attr_set) {
         NSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -198,10 +234,15 @@ nsp_status launch_wgrad(const WgradMaps& maps, WgradArgs& g, cudaStream_t st) {
     g.splits = splits;
     kern<<<(unsigned)(tiles * splits), 192, smem, st>>>(maps, g);
     NSP_LAUNCH_OK();
+    if (TMAEPI) ++g_wgrad_tma_launches;
     return NSP_OK;
 }
 
 }  // namespace
+
+int gemm_epilogue_mode();                                  // gemm_tcgen05.cu
+long long wgrad_tma_launch_count() { return g_wgrad_tma_launches; }
+
 }  // namespace nsp
 
 using namespace nsp;
@@ -231,8 +272,16 @@ extern "C" nsp_status nsp_linear_wgrad(int prec, const void* dy, const void* dy_
         if (!make_tmap_2d(&maps.b[s], bs[s], es, bf16, (uint64_t)M, (uint64_t)K, (uint64_t)ldx, WG_ROWS)) return NSP_ERR_INVALID;
     }
     if (bf16) {
-        if (K > 128) return launch_wgrad<__nv_bfloat16, 256, 4>(maps, g, st);
-        return launch_wgrad<__nv_bfloat16, 128, 6>(maps, g, st);
+        // opt-in bulk-reduce epilogue: needs a 16-byte aligned gradient buffer with a 16-byte multiple pitch
+        const bool tma_epi = gemm_epilogue_mode() >= 1 && ((uintptr_t)dw % 16 == 0) && (lddw % 4 == 0);
+        if (tma_epi) {
+            if (!encode_tmap_2d(&maps.dw, dw, false, (uint64_t)N, (uint64_t)K, (uint64_t)lddw, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B, "dw"))
+                return NSP_ERR_INVALID;
+            if (K > 128) return launch_wgrad<__nv_bfloat16, 256, 4, true>(maps, g, st);
+            return launch_wgrad<__nv_bfloat16, 128, 6, true>(maps, g, st);
+        }
+        if (K > 128) return launch_wgrad<__nv_bfloat16, 256, 4, false>(maps, g, st);
+        return launch_wgrad<__nv_bfloat16, 128, 6, false>(maps, g, st);
     }
     // tf32 operands: the MN-major path needs the 128B_BASE32B swizzle atom (not wired up); the host side computes
     // parity-mode weight gradients on the K-major GEMM instead.

@@ -113,6 +113,56 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[32])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---------------- shared-memory staged bulk tensor stores (epilogues) ----------------
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 :: "l"(m), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
+
+// explicit shared-space accesses (the staging pointers are derived from an aligned generic pointer, which would
+// otherwise compile to generic ST.E / LD.E)
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void lds128(uint32_t addr, float& a, float& b, float& c, float& d) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(addr) : "memory");
+}
+
+// row r (= lane) of a 32 x 32 fp32 sub-tile, SWIZZLE_128B, tile base 1024-byte aligned
+__device__ __forceinline__ void st_row_f32(uint8_t* tile, int r, const float* v) {
+    const uint32_t row = smem_u32(tile) + r * 128;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        sts128(row + ((j ^ (r & 7)) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+               __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+}
+__device__ __forceinline__ void ld_row_f32(const uint8_t* tile, int r, float* v) {
+    const uint32_t row = smem_u32(tile) + r * 128;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) lds128(row + ((j ^ (r & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+// row r of a 32 x 32 bf16 sub-tile, SWIZZLE_64B, tile base 512-byte aligned
+__device__ __forceinline__ void st_row_bf16(uint8_t* tile, int r, const float* v) {
+    const uint32_t row = smem_u32(tile) + r * 64;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        sts128(row + ((j ^ ((r >> 1) & 3)) << 4), pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+               pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+}
+
+// dst[tile] += smem tile (element type and box from the tensor map; fp32 add performed by the L2)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+                 :: "l"(m), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+
 // ---------------- descriptors ----------------
 // K-major operand tile in shared memory, 128-byte swizzle: rows are 128 B apart, 8-row groups 1024 B apart.
 // bits [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major) | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B)
@@ -137,5 +187,10 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t ab_fmt, uint32_t M, u
 // box = [box_rows, 128 bytes] and 128-byte swizzle.  Returns false (and sets the error) on failure.
 bool make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, bool is_bf16, uint64_t rows, uint64_t cols,
                   uint64_t ld, uint32_t box_rows);
+
+// Row-major [rows, cols] matrix (pitch ld elements), box = [box_rows, box_cols]; box_cols * element size must equal the
+// swizzle span.  gemm_tma_epi.cu.
+bool encode_tmap_2d(CUtensorMap* out, const void* base, bool is_bf16, uint64_t rows, uint64_t cols, uint64_t ld,
+                    uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swz, const char* what);
 
 }  // namespace nsp

@@ -143,3 +143,43 @@ def test_cta_pairs_epilogues(cta_pairs):
 def test_cta_pairs_long_k_many_tiles_per_pair(cta_pairs):
     """Several tiles per pair and K = 4096: exercises ring wrap-around, both accumulator stages and the phase bits."""
     _run(cta_pairs, 40000, 1024, 4096, expect_pair=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# weight gradient: staged cp.reduce.async.bulk.tensor epilogue (modes >= 1)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(4000, 512, 2048), (4000, 2048, 512), (16000, 512, 512), (1000, 256, 512), (77, 40, 24),
+                                   (4100, 2048, 512), (11, 64, 64), (300, 1000, 136), (16037, 1536, 512)])
+def test_wgrad_bulk_reduce_epilogue(tma_epilogue, shape):
+    from neural_sp_b200 import ops
+    M, N, K = shape
+    torch.manual_seed(0)
+    dy = torch.randn(M, N, device="cuda").bfloat16().float()
+    x = torch.randn(M, K, device="cuda").bfloat16().float()
+    ref = (dy.double().t() @ x.double()) * 0.5
+    dw = torch.zeros(N, K, device="cuda")
+    before = tma_epilogue.nsp_wgrad_tma_epilogue_launches()
+    ops.linear_wgrad(dy, x, "bf16", dw, alpha=0.5, accumulate=False)
+    torch.cuda.synchronize()
+    assert tma_epilogue.nsp_wgrad_tma_epilogue_launches() - before == 1
+    err = float((dw.double() - ref).abs().max() / ref.abs().max())
+    assert err <= 2e-2, (shape, err)
+    ops.linear_wgrad(dy, x, "bf16", dw, alpha=0.5, accumulate=True)          # accumulation doubles it
+    torch.cuda.synchronize()
+    err = float((dw.double() - 2 * ref).abs().max() / (2 * ref).abs().max())
+    assert err <= 2e-2, (shape, err)
+
+
+def test_wgrad_bulk_reduce_into_a_row_block_of_a_fused_gradient(tma_epilogue):
+    """dW written into rows [512, 1024) of a [1536, 512] fused-QKV gradient view: neighbours untouched."""
+    from neural_sp_b200 import ops
+    torch.manual_seed(1)
+    M, N, K = 4000, 512, 512
+    dy = torch.randn(M, N, device="cuda").bfloat16().float()
+    x = torch.randn(M, K, device="cuda").bfloat16().float()
+    full = torch.full((3 * N, K), 3.0, device="cuda")
+    ops.linear_wgrad(dy, x, "bf16", full[N:2 * N], accumulate=True)
+    torch.cuda.synchronize()
+    ref = 3.0 + dy.double().t() @ x.double()
+    assert float((full[N:2 * N].double() - ref).abs().max() / ref.abs().max()) <= 2e-2
+    assert torch.all(full[:N] == 3.0) and torch.all(full[2 * N:] == 3.0)
