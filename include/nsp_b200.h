@@ -153,6 +153,9 @@ nsp_status nsp_conformer_conv_fwd(int is_bf16, const void* x, int64_t ldx, const
 
 /* x *= a in place (LayerDrop's eval-time 1/(1-p) rescale, encoders/conformer_block.py:122-126). */
 nsp_status nsp_scale_inplace(float* x, float a, int64_t n, void* stream);
+/* x[b,t,:] = x[b,t,:] * a + pe[t,:] in place: PositionalEncoding.forward (pe_type='add')
+ * modules/positional_embedding.py:82-90; x fp32 [B,T,D], pe fp32 [T,D] = rows offset..offset+T of the sinusoid buffer. */
+nsp_status nsp_add_pos_enc(float* x, const float* pe, float a, int B, int T, int D, void* stream);
 /* y[n] = sum_m x[m, n] for a dense fp32 [M, N] matrix (bias gradients). */
 nsp_status nsp_colsum(const float* x, float* y, int M, int N, void* stream);
 /* TransformerXL sinusoid table: XLPositionalEmbedding.forward modules/positional_embedding.py:135-138.

@@ -393,6 +393,23 @@ def scale(x, a):
     return x if a == 1.0 else _ScaleFn.apply(x, float(a))
 
 
+class _AddPosEncFn(torch.autograd.Function):
+    """y = x * a + pe[offset:offset+T]  (PositionalEncoding 'add' / 'none'); dx = a * dy."""
+
+    @staticmethod
+    def forward(ctx, x, pos_enc, offset):
+        ctx.a = pos_enc.scale
+        return pos_enc(x.detach().clone(), scale=True, offset=offset)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.scale_(dy.contiguous().float().clone(), ctx.a), None, None
+
+
+def add_pos_enc(pos_enc, x, offset=0):
+    return _AddPosEncFn.apply(x, pos_enc, offset)
+
+
 def linear(module, name, lin, x, prec):
     """nn.Linear through the tcgen05 GEMM with autograd (dgrad + wgrad on the same kernels)."""
     from .modules.linear import _LinearFn

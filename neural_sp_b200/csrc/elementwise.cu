@@ -43,6 +43,14 @@ __global__ void __launch_bounds__(256) scale_kernel(float* __restrict__ x, float
     for (; i < n; i += stride) x[i] *= a;
 }
 
+// x[b, t, :] = x[b, t, :] * a + pe[t, :]   (absolute sinusoid positions added to the scaled embedding)
+__global__ void __launch_bounds__(256) add_pos_enc_kernel(float* __restrict__ x, const float* __restrict__ pe, float a,
+                                                          int64_t n, int64_t TD) {
+    int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (; i < n; i += stride) x[i] = fmaf(x[i], a, __ldg(pe + i % TD));
+}
+
 // column sums of a row-major [M, N] fp32 matrix: block = 32 columns x 8 row slices
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, float* __restrict__ y, int M, int N) {
     __shared__ float part[8][33];
@@ -106,6 +114,15 @@ extern "C" nsp_status nsp_scale_inplace(float* x, float a, int64_t n, void* stre
     NSP_CHECK_ARG(x && n >= 0, "scale_inplace: bad arguments");
     if (n == 0) return NSP_OK;
     scale_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, a, n);
+    NSP_LAUNCH_OK();
+    return NSP_OK;
+}
+
+extern "C" nsp_status nsp_add_pos_enc(float* x, const float* pe, float a, int B, int T, int D, void* stream) {
+    NSP_CHECK_ARG(x && pe && B >= 0 && T >= 0 && D > 0, "add_pos_enc: bad arguments");
+    const int64_t n = (int64_t)B * T * D;
+    if (n == 0) return NSP_OK;
+    add_pos_enc_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, pe, a, n, (int64_t)T * D);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }

@@ -54,22 +54,32 @@ class ConformerEncoderBlock(nn.Module):
         self._xx_aws = None
 
     def forward(self, xs, klens, cache=None, pos_embs=None, rel_bias=(None, None), mask_kw=None):
-        """xs fp32 `[B, T, d]` (updated in place), klens int32 `[B]` CUDA, pos_embs fp32 `[>=T, d]`."""
-        if cache is not None:
-            raise NotImplementedError("streaming caches are a 'next' row (SURVEY.md 8f-4)")
+        """xs fp32 `[B, T, d]` (updated in place), klens int32 `[B]` CUDA (valid keys INCLUDING cached frames),
+        pos_embs fp32 `[>= n_cache + T, d]`.  cache (streaming, conformer_block.py:143-170): dict with the previous
+        chunks' normalised attention input ``input_san`` `[B, n_cache, d]` and conv-module input ``input_conv``
+        `[B, <= k + T - 1, d]`; the returned new_cache holds both extended by this chunk."""
         if self.training and (self.dropout.p > 0 or self.self_attn.dropout_attn.p > 0):
             raise NotImplementedError("dropout > 0 in training mode is not on the B200 path yet")
         prec = get_precision(self)
         mask_kw = mask_kw or {}
         u_bias, v_bias = rel_bias
+        new_cache = {}
+        qlen = xs.size(1)
         if self.dropout_layer > 0:          # LayerDrop (conformer_block.py:122-126): eval also rescales
             if self.training and random.random() < self.dropout_layer:
-                return xs, {}
+                return xs, new_cache
             ops.scale_(xs, 1.0 / (1 - self.dropout_layer))
         xs = self.feed_forward_macaron(_ln(self.norm1, xs, prec), residual=xs, scale=self.fc_factor, out=xs)
         h = _ln(self.norm2, xs, prec)
-        xs = self.self_attn(h, h, pos_embs, klens, u_bias, v_bias, residual=xs, out=xs, **mask_kw)
-        xs = self.conv(_ln(self.norm3, xs, prec), residual=xs, out=xs)
+        kv = h if cache is None else torch.cat([cache['input_san'].to(h.dtype), h], dim=1)
+        new_cache['input_san'] = kv
+        xs = self.self_attn(kv, h, pos_embs, klens, u_bias, v_bias, residual=xs, out=xs, **mask_kw)
+        c_in = _ln(self.norm3, xs, prec)
+        if cache is not None:               # left context of the depthwise convolution, restricted to the kernel size
+            c_in = torch.cat([cache['input_conv'].to(c_in.dtype), c_in], dim=1)
+            c_in = c_in[:, max(0, c_in.size(1) - (self.conv_context + qlen - 1)):].contiguous()
+        new_cache['input_conv'] = c_in
+        xs = self.conv(c_in, residual=xs, out=xs, keep_last=qlen if cache is not None else None)
         xs = self.feed_forward(_ln(self.norm4, xs, prec), residual=xs, scale=self.fc_factor, out=xs)
         xs = ops.layernorm(xs, self.norm5.weight, self.norm5.bias, self.norm5.eps)
-        return xs, {}
+        return xs, new_cache

@@ -64,9 +64,12 @@ class Conv2dBlock(EncoderBase):
         self.pool = self.pooling if self._factor > 1 or self.pooling[1] > 1 else None
 
     def forward(self, xs, xlens, B, T, F, first, last_chmajor, lookback=False, lookahead=False):
-        """xs: raw features (first block) or channels-last `[B, T, F, C]`.  Returns (xs, xlens, T', F')."""
-        if lookback or lookahead:
-            raise NotImplementedError("CNN lookback/lookahead trimming (streaming) is a 'next' row")
+        """xs: raw features (first block) or channels-last `[B, T, F, C]`.  Returns (xs, xlens, T', F').
+
+        lookback / lookahead (streaming, reference conv.py:368-374, :385-390): after each of the two convolutions the
+        leftmost / rightmost `stride` (= 1) output frames -- the ones computed from zero padding instead of real
+        neighbouring context -- are dropped, so a chunk fed with `context_size` extra frames on a side reproduces the
+        offline activations exactly."""
         if self.training and self.dropout.p > 0:
             raise NotImplementedError("dropout > 0 in training mode is not on the B200 path yet")
         prec = get_precision(self)
@@ -74,6 +77,7 @@ class Conv2dBlock(EncoderBase):
         if self.residual and self.conv1.in_channels == self.conv2.out_channels:
             raise NotImplementedError("residual CNN blocks are not on the B200 path")
         pt, pf = self.pooling if self.pool is not None else (1, 1)
+        trim = lookback or lookahead
 
         def conv(layer, name, x, first_layer, fuse_pool):
             ci, co = layer.in_channels, layer.out_channels
@@ -83,9 +87,24 @@ class Conv2dBlock(EncoderBase):
                 return ops.conv3x3_c32_tc(x.view(B, T, F, 32), wt, layer.bias, relu=True, pool2x2=fuse_pool), fuse_pool
             return ops.conv3x3_relu(x, layer.weight, layer.bias, B, T, F, in_chmajor=first_layer, out_dtype=adt), False
 
+        def trim_time(x, lens):
+            """Drop one frame per requested side of a channels-last `[B, T, F, C]` activation (time stride is 1)."""
+            nonlocal T
+            x = x.view(B, T, F, -1)
+            if lookback and T > 1:
+                x, T, lens = x[:, 1:], T - 1, lens - 1
+            if lookahead and T > 1:
+                x, T, lens = x[:, :T - 1], T - 1, lens - 1
+            return x.contiguous(), lens
+
         xs, _ = conv(self.conv1, "conv1", xs, first, False)
-        xs, pooled = conv(self.conv2, "conv2", xs, False, (pt, pf) == (2, 2) and not last_chmajor)
-        xlens = torch.IntTensor([_conv_len(_conv_len(int(n), 1), 1) for n in xlens])
+        xlens = torch.IntTensor([_conv_len(int(n), 1) for n in xlens])
+        if trim:
+            xs, xlens = trim_time(xs, xlens)
+        xs, pooled = conv(self.conv2, "conv2", xs, False, (pt, pf) == (2, 2) and not last_chmajor and not trim)
+        xlens = torch.IntTensor([_conv_len(int(n), 1) for n in xlens])
+        if trim:
+            xs, xlens = trim_time(xs, xlens)
         if self.pool is not None:
             if not pooled:
                 xs = ops.maxpool2d(xs, pt, pf, out_chmajor=last_chmajor)

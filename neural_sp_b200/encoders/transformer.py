@@ -6,7 +6,11 @@ and state_dict keys (``conv.*``, ``embed.*``, ``pos_emb.inv_freq``, ``u_bias/v_b
 key-padding / causal / chunk visibility are evaluated inside the attention kernel from device-side lengths.
 Supported here: offline full-context, unidirectional ('uni', per-layer lookahead) and latency-controlled
 ('reshape' overlapped windows / 'mask' chunk-wise visibility) encoders with all six hierarchical subsamplers and
-sub-task outputs.  Streaming inference with caches is a 'next' row and raises NotImplementedError."""
+sub-task outputs, and chunk-by-chunk streaming inference (``streaming=True``, :448-606): per-layer caches of the
+normalised attention input (and of the Conformer conv-module input) are carried in ``self.cache`` exactly like the
+reference's -- same keys, same truncation to ``cache_sizes`` -- and the attention kernel sees the cached frames as
+`mlen = klen - qlen` extra keys (query i sits at key position mlen + i for the causal / chunk masks and the relative
+distance), so nothing of the `[B, qlen, klen]` mask or the shifted position matrix is ever materialised."""
 import copy
 import math
 
@@ -19,7 +23,7 @@ import random
 from .. import autograd as ag
 from .. import ops
 from ..modules._prep import prepared, get_precision
-from ..modules.positional_embedding import XLPositionalEmbedding
+from ..modules.positional_embedding import PositionalEncoding, XLPositionalEmbedding
 from .encoder_base import EncoderBase
 from .subsampling import (AddSubsampler, ConcatSubsampler, Conv1dSubsampler, DropSubsampler, MaxPoolSubsampler,
                           MeanPoolSubsampler)
@@ -129,9 +133,8 @@ class TransformerEncoder(EncoderBase):
             if pe_type == 'relative_xl':
                 self.u_bias = nn.Parameter(torch.Tensor(n_heads, d_model // n_heads))
                 self.v_bias = nn.Parameter(torch.Tensor(n_heads, d_model // n_heads))
-        elif pe_type != 'none':
-            raise NotImplementedError("absolute positional encoding pe_type=%r is not on the B200 path "
-                                      "(none, relative, relative_xl are)" % pe_type)
+        else:
+            self.pos_enc = PositionalEncoding(d_model, dropout_in, pe_type, param_init)
 
         self.layers = nn.ModuleList([copy.deepcopy(TransformerEncoderBlock(
             d_model, d_ff, n_heads, dropout, dropout_att, dropout_layer * (lth + 1) / n_layers, layer_norm_eps,
@@ -151,6 +154,7 @@ class TransformerEncoder(EncoderBase):
             self._odim = last_proj_dim
         self.reset_parameters(param_init)
         self.reset_cache()
+        self.cache_sizes = self.calculate_cache_size()
 
     def reset_parameters(self, param_init):
         if param_init == 'xavier_uniform':
@@ -164,8 +168,40 @@ class TransformerEncoder(EncoderBase):
                 nn.init.xavier_uniform_(self.v_bias)
 
     def reset_cache(self):
+        """Reset the streaming state (reference transformer.py:370-374)."""
         self.cache = [None] * self.n_layers
         self.offset = 0
+
+    def truncate_cache(self, cache):
+        """Keep at most ``cache_sizes[lth]`` cached attention-input frames per layer (reference :376-391)."""
+        if cache[0] is not None:
+            for lth in range(self.n_layers):
+                size = self.cache_sizes[lth]
+                san = cache[lth]['input_san']
+                if san.size(1) > size:
+                    cache[lth]['input_san'] = san[:, san.size(1) - size:]
+        return cache
+
+    def calculate_cache_size(self):
+        """Maximum number of cached frames per layer, after CNN subsampling (reference :393-404)."""
+        size = self._total_chunk_size_left()
+        N_l = self.N_l // self.conv_factor
+        sizes = []
+        for lth in range(self.n_layers):
+            sizes.append(size)
+            if self.lc_bidir:
+                size = max(0, size - N_l)
+                N_l //= self.subsample_factors[lth]
+            size //= self.subsample_factors[lth]
+        return sizes
+
+    def _total_chunk_size_left(self):
+        """Left context accumulated over the layer stack, in frames after the CNN (reference :406-417)."""
+        if self.streaming_type == 'reshape':
+            return self.N_l // self.conv_factor
+        if self.streaming_type == 'mask':
+            return (self.N_l // self.conv_factor) * self.n_layers
+        return 10000 // self.conv_factor
 
     def _proj(self, name, lin, xs, scale=1.0, train=False):
         prec = get_precision(self)
@@ -201,28 +237,39 @@ class TransformerEncoder(EncoderBase):
         return ag.block_forward(layer, xs, klens, pos, (self.u_bias, self.v_bias), mask_kw, prec, in_scale)
 
     def forward(self, xs, xlens, task, streaming=False, lookback=False, lookahead=False):
-        """xs `[B, T, input_dim]` fp32 on the GPU; xlens IntTensor `[B]` on the CPU (reference contract)."""
-        if streaming:
-            raise NotImplementedError("streaming inference is a 'next' row (SURVEY.md 8f-4)")
+        """xs `[B, T, input_dim]` fp32 on the GPU; xlens IntTensor `[B]` on the CPU (reference contract).
+        streaming=True encodes one chunk and carries ``self.cache`` / ``self.offset`` over to the next call
+        (``reset_cache()`` starts a new utterance); lookback / lookahead trim the CNN context frames."""
         eouts = {'ys': {'xs': None, 'xlens': None}, 'ys_sub1': {'xs': None, 'xlens': None},
                  'ys_sub2': {'xs': None, 'xlens': None}}
         # train() + grad mode: every block / the front-end is one autograd node with a hand-written CUDA backward
         # (neural_sp_b200/autograd.py); otherwise inference kernels under no_grad (in-place residual stream).
         train = ag.training_enabled(self)
+        if streaming and train:
+            raise NotImplementedError("streaming=True is an inference path (call .eval() / torch.no_grad())")
         prec = get_precision(self)
         with (torch.enable_grad() if train else torch.no_grad()):
             rel = 'relative' in self.pe_type
-            bs = xs.size(0)
+            bs, xmax = xs.size(0), xs.size(1)
             N_l, N_c, N_r = self.N_l, self.N_c, self.N_r
-            n_chunks = 0
-            if self.lc_bidir:                                         # offline latency-controlled encoders (:456-462)
-                xs = chunkwise(xs, 0, N_c, 0) if self.streaming_type == 'mask' else chunkwise(xs, N_l, N_c, N_r)
-                n_chunks = xs.size(0) // bs
+            st = self.streaming_type
+            if streaming and st == 'mask':
+                assert xmax <= N_c
+            elif streaming and st == 'reshape':
+                assert xmax <= N_l + N_c + N_r
+            if self.lc_bidir:                                         # latency-controlled encoders (:456-465)
+                if st == 'mask' and not streaming:
+                    xs = chunkwise(xs, 0, N_c, 0)
+                elif st == 'reshape' and not streaming:
+                    xs = chunkwise(xs, N_l, N_c, N_r)
+                elif st == 'reshape':                                 # one window, already carrying both contexts
+                    assert xmax // (N_l + N_c + N_r) == 1, xs.size()
+                    xs = xs[:, :N_l + N_c + N_r]
             if self.conv is None:
                 xs = self._proj('embed', self.embed, xs.float(), scale=self.scale if rel else 1.0, train=train)
             elif train:
                 if lookback or lookahead:
-                    raise NotImplementedError("CNN lookback/lookahead trimming (streaming) is a 'next' row")
+                    raise NotImplementedError("CNN lookback/lookahead trimming is an inference (streaming) feature")
                 xs = ag.frontend_forward(self.conv, xs, self.scale if (rel and self.enc_type != 'conv') else 1.0, prec)
                 xlens = self.conv.output_lens(xlens)
                 N_l, N_c, N_r = max(0, N_l // self.conv_factor), N_c // self.conv_factor, N_r // self.conv_factor
@@ -231,26 +278,45 @@ class TransformerEncoder(EncoderBase):
                                       lookahead=False if self.lc_bidir else lookahead,
                                       out_scale=self.scale if (rel and self.enc_type != 'conv') else 1.0)
                 N_l, N_c, N_r = max(0, N_l // self.conv_factor), N_c // self.conv_factor, N_r // self.conv_factor
-            if self.streaming_type == 'mask':                         # back to utterance shape (:481-483)
+            emax = xs.size(1)
+            if streaming and st != 'reshape':                         # (:476-478)
+                xlens = torch.IntTensor([int(v) for v in xlens])
+                xs = xs[:, :int(xlens.max())].contiguous()
+                xlens = xlens.clamp(max=xs.size(1))
+            elif not streaming and st == 'mask':                      # back to utterance shape (:479-481)
                 xs = xs.contiguous().view(bs, -1, xs.size(2))[:, :int(xlens.max())].contiguous()
             if self.enc_type == 'conv':
                 eouts['ys']['xs'], eouts['ys']['xlens'] = xs, xlens
                 return eouts
-            self.reset_cache()
+            if streaming:
+                self.cache = self.truncate_cache(self.cache)
+            else:
+                self.reset_cache()
             dev = xs.device
+            if not rel:                                               # absolute positions: xs * sqrt(d) [+ pe] (:497-498)
+                if train:
+                    xs = ag.add_pos_enc(self.pos_enc, xs.contiguous(), self.offset)
+                else:
+                    xs = self.pos_enc(xs.contiguous(), scale=True, offset=self.offset)
 
-            def key_lens():
-                if self.streaming_type == 'reshape':                  # no mask at all inside a chunk (:512)
+            def cached_frames(lth):
+                c = self.cache[lth] if streaming else None
+                return c['input_san'].size(1) if c is not None else 0
+
+            def key_lens(n_cache):
+                if st == 'reshape':                                   # no mask at all inside a chunk (:512)
                     return lens_to_device(torch.IntTensor([xs.size(1)] * xs.size(0)), dev)
-                return lens_to_device(xlens, dev)
+                return lens_to_device(xlens + n_cache if n_cache else xlens, dev)
 
-            klens = key_lens()
-            pos = self.pos_emb.table(xs.size(1)) if rel else None
+            n_cache = cached_frames(0)
+            klens = key_lens(n_cache)
+            pos = self.pos_emb.table(xs.size(1) + n_cache) if rel else None
+            new_cache = [None] * self.n_layers
 
             def mask_kw(lth):
                 if self.unidir:
                     return dict(causal=True, lookahead=self.lookaheads[lth])
-                if self.streaming_type == 'mask':
+                if st == 'mask':
                     return dict(chunk_c=N_c, chunk_l=N_l)
                 return {}
 
@@ -258,8 +324,10 @@ class TransformerEncoder(EncoderBase):
                 if train:
                     xs = self._train_layer(lth, layer, xs, klens, pos, mask_kw(lth), prec)
                 else:
-                    xs, _ = layer(xs, klens, cache=None, pos_embs=pos, rel_bias=(self.u_bias, self.v_bias),
-                                  mask_kw=mask_kw(lth))
+                    xs, cache = layer(xs, klens, cache=self.cache[lth] if streaming else None, pos_embs=pos,
+                                      rel_bias=(self.u_bias, self.v_bias), mask_kw=mask_kw(lth))
+                    if streaming and st != 'reshape':                 # 'reshape' windows carry their own context
+                        new_cache[lth] = cache
                 if lth == self.n_layers_sub1 - 1:
                     xs_sub1, xlens_sub1 = self._sub_out(xs, 'sub1', train), xlens.clone()
                     if task == 'ys_sub1':
@@ -270,22 +338,29 @@ class TransformerEncoder(EncoderBase):
                     if task == 'ys_sub2':
                         eouts[task]['xs'], eouts[task]['xlens'] = xs_sub2, xlens_sub2
                         return eouts
-                if lth < len(self.layers) - 1 and self.subsample_factors[lth] > 1:
-                    if train:
-                        sub = self.subsample_layers[lth]
-                        if not isinstance(sub, MaxPoolSubsampler):
-                            raise NotImplementedError("training: only subsample_type=max_pool has a CUDA backward")
-                        xs, xlens = ag.maxpool_time(xs, sub.factor), sub._lens(xlens)
-                    else:
-                        xs, xlens = self.subsample_layers[lth](xs, xlens)
+                if lth < len(self.layers) - 1:
                     f = self.subsample_factors[lth]
-                    N_l, N_c, N_r = max(0, N_l // f), N_c // f, N_r // f
-                    klens = key_lens()
-                    if rel:
-                        pos = self.pos_emb.table(xs.size(1))
-            if self.streaming_type == 'reshape':                      # keep the centre of every window (:546-550)
+                    if f > 1:
+                        if train:
+                            sub = self.subsample_layers[lth]
+                            if not isinstance(sub, MaxPoolSubsampler):
+                                raise NotImplementedError("training: only subsample_type=max_pool has a CUDA backward")
+                            xs, xlens = ag.maxpool_time(xs, sub.factor), sub._lens(xlens)
+                        else:
+                            xs, xlens = self.subsample_layers[lth](xs, xlens)
+                        N_l, N_c, N_r = max(0, N_l // f), N_c // f, N_r // f
+                    if streaming or f > 1:                            # cache sizes differ per layer (:535-541, :582-588)
+                        n_cache = cached_frames(lth + 1)
+                        klens = key_lens(n_cache)
+                        if rel:
+                            pos = self.pos_emb.table(xs.size(1) + n_cache)
+            if st == 'reshape':                                       # keep the centre of every window (:546-550)
                 xs = xs[:, N_l:N_l + N_c].contiguous().view(bs, -1, xs.size(2))[:, :int(xlens.max())].contiguous()
             xs = self._norm(self.norm_out, xs, train)
+            if streaming:
+                self.cache = new_cache
+                if st != 'reshape':
+                    self.offset += emax
             if self.bridge is not None:
                 xs = self._proj('bridge', self.bridge, xs, train=train)
         if task in ['all', 'ys']:

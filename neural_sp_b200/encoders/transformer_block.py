@@ -4,6 +4,7 @@ Pre-norm MHSA + FFN.  The reference's ``pe_type in ['relaive', 'relative_xl']`` 
 ``relative_xl`` yields relative attention in a Transformer block; ``relative`` silently uses plain MHA."""
 import random
 
+import torch
 import torch.nn as nn
 
 from .. import ops
@@ -41,20 +42,23 @@ class TransformerEncoderBlock(nn.Module):
         self._xx_aws = None
 
     def forward(self, xs, klens, cache=None, pos_embs=None, rel_bias=(None, None), mask_kw=None):
-        if cache is not None:
-            raise NotImplementedError("streaming caches are a 'next' row (SURVEY.md 8f-4)")
+        """cache (streaming, transformer_block.py:113-122): ``input_san`` `[B, n_cache, d]`, the previous chunks'
+        normalised attention input; klens counts cached frames too."""
         if self.training and (self.dropout.p > 0 or self.self_attn.dropout_attn.p > 0):
             raise NotImplementedError("dropout > 0 in training mode is not on the B200 path yet")
         prec = get_precision(self)
         mask_kw = mask_kw or {}
+        new_cache = {}
         if self.dropout_layer > 0:
             if self.training and random.random() < self.dropout_layer:
-                return xs, {}
+                return xs, new_cache
             ops.scale_(xs, 1.0 / (1 - self.dropout_layer))
         h = _ln(self.norm1, xs, prec)
+        kv = h if cache is None else torch.cat([cache['input_san'].to(h.dtype), h], dim=1)
+        new_cache['input_san'] = kv
         if self.rel_attn:
-            xs = self.self_attn(h, h, pos_embs, klens, rel_bias[0], rel_bias[1], residual=xs, out=xs, **mask_kw)
+            xs = self.self_attn(kv, h, pos_embs, klens, rel_bias[0], rel_bias[1], residual=xs, out=xs, **mask_kw)
         else:
-            xs = self.self_attn(h, h, klens, residual=xs, out=xs, **mask_kw)
+            xs = self.self_attn(kv, h, klens, residual=xs, out=xs, **mask_kw)
         xs = self.feed_forward(_ln(self.norm2, xs, prec), residual=xs, scale=1.0, out=xs)
-        return xs, {}
+        return xs, new_cache

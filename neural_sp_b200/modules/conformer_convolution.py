@@ -43,8 +43,10 @@ class ConformerConvBlock(nn.Module):
                 for n, p in c.named_parameters():
                     init_with_lecun_normal(n, p, 0.1)
 
-    def forward(self, xs, residual=None, out=None):
-        """xs `[B, T, d]` normalised input.  Returns ``residual + conv_module(xs)`` (fp32)."""
+    def forward(self, xs, residual=None, out=None, keep_last=None):
+        """xs `[B, T, d]` normalised input.  Returns ``residual + conv_module(xs)`` (fp32).
+        keep_last = q (streaming, conformer_block.py:160-166): xs carries cached left context in front of the q new
+        frames; only the last q frames go through pointwise_conv2 / the residual add."""
         prec = get_precision(self)
         if self.normalization == 'batch_norm' and self.training:
             raise NotImplementedError("BatchNorm statistics update (training mode) is not on the B200 path; "
@@ -59,5 +61,7 @@ class ConformerConvBlock(nn.Module):
                       lambda w: w.reshape(w.size(0), -1).t().contiguous().float())          # [k, d]
         c = ops.conformer_conv(g, taps, self.depthwise_conv.bias, self.normalization,
                                self.norm.weight, self.norm.bias, self.norm.eps, rm, rv, causal=self.causal)
+        if keep_last is not None and keep_last < c.size(1):
+            c = c[:, c.size(1) - keep_last:].contiguous()
         w2 = prepared(self, "pw2", prec, (self.pointwise_conv2.weight,), build=lambda w: w.squeeze(-1))
         return ops.linear(c, w2, self.pointwise_conv2.bias, prec=prec, residual=residual, out_dtype=torch.float32, out=out)

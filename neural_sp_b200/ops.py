@@ -313,6 +313,16 @@ def scale_(x, a):
     return x
 
 
+def add_pos_enc_(x, pe, a=1.0):
+    """x[b,t,:] = x[b,t,:] * a + pe[t,:] in place (nsp_add_pos_enc); x fp32 `[B,T,D]` contiguous, pe fp32 `[T,D]`."""
+    _require_cuda(x, pe)
+    B, T, D = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and pe.dtype == torch.float32 and pe.is_contiguous()
+    assert pe.shape == (T, D), (pe.shape, x.shape)
+    _run("nsp_add_pos_enc", lib.nsp_add_pos_enc, ptr(x), ptr(pe), float(a), B, T, D, current_stream_ptr())
+    return x
+
+
 def colsum(x):
     _require_cuda(x)
     x = x.float().contiguous()

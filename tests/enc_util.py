@@ -59,3 +59,20 @@ def build_ours(g, device, precision):
     enc = enc.to(device).eval()
     enc.set_precision(precision)
     return enc
+
+
+def replay_stream(enc, g, device):
+    """Feed the fixture's chunk schedule (tests/golden/gen_golden_streaming.py) through `enc` with streaming=True.
+    Returns the list of per-chunk outputs (fp32, CPU) and their lengths."""
+    xs = torch.from_numpy(g["xs"])
+    outs, lens = [], []
+    enc.reset_cache()
+    for start, end, pl, pr, xlen, lookback, lookahead in g["sched"].tolist():
+        chunk = xs[:, start:end]
+        if pl or pr:
+            chunk = torch.cat([chunk.new_zeros(1, pl, chunk.size(2)), chunk, chunk.new_zeros(1, pr, chunk.size(2))], dim=1)
+        o = enc(chunk.contiguous().to(device), torch.IntTensor([xlen]), task='all', streaming=True,
+                lookback=bool(lookback), lookahead=bool(lookahead))['ys']
+        outs.append(o['xs'].float().cpu())
+        lens.append(int(o['xlens'][0]))
+    return outs, lens

@@ -1,0 +1,196 @@
+"""Test doubles for neural_sp_b200.ops: plain torch-CPU restatements of the INFERENCE ops' contracts (argument meaning,
+layouts, dtypes, in-place `out=` semantics), installed over the ctypes wrappers by the `cpu_ops` fixture so that the
+HOST logic of the encoders (streaming caches, chunking, length arithmetic, mask parameters handed to the attention
+kernel, module wiring) can be exercised in this GPU-less container against the unmodified reference modules.
+
+Test infrastructure only: nothing under neural_sp_b200/ imports this file, and the product ops keep failing loudly on CPU
+tensors.  The CUDA kernels behind the real ops are checked by the `-m gpu` tests against the same contracts."""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+def _act(y, act):
+    if act in (None, "none"):
+        return y
+    if act == "relu":
+        return torch.relu(y)
+    if act == "swish":
+        return y * torch.sigmoid(y)
+    if act == "gelu":
+        return F.gelu(y)
+    if act == "gelu_accurate":
+        return 0.5 * y * (1 + torch.tanh(math.sqrt(2 / math.pi) * (y + 0.044715 * y ** 3)))
+    raise NotImplementedError(act)
+
+
+def prepare_weight(w, prec):
+    w = w.detach().float()
+    K = w.shape[-1]
+    Kp = -(-K // 8) * 8
+    return (F.pad(w, (0, Kp - K)).contiguous(),)
+
+
+def to_bf16(x):
+    return x.to(torch.bfloat16)
+
+
+def linear(x, w_prepared, bias=None, prec="bf16", act=None, glu=False, residual=None, alpha=1.0,
+           out_dtype=torch.float32, out=None, out2_bf16=False, save_pre=False):
+    w = w_prepared[0]
+    K = x.shape[-1]
+    x2 = x.reshape(-1, K).float()
+    if w.shape[1] != K:
+        x2 = F.pad(x2, (0, w.shape[1] - K))
+    y = x2 @ w.t()
+    if bias is not None:
+        y = y + bias.float()
+    if glu:
+        a, b = y.chunk(2, dim=-1)
+        y = a * torch.sigmoid(b)
+    else:
+        y = _act(y, act)
+    y = alpha * y
+    if residual is not None:
+        y = y + residual.reshape(y.shape).float()
+    if out is not None:
+        out.reshape(-1, y.shape[-1]).copy_(y)
+        return out
+    assert not out2_bf16 and not save_pre, "training-only outputs are not modelled by the doubles"
+    return y.to(out_dtype).reshape(*x.shape[:-1], y.shape[-1])
+
+
+def layernorm(x, weight, bias, eps, out_fp32=True, out_bf16=False, in_scale=1.0):
+    y = F.layer_norm(x.float() * in_scale, (x.shape[-1],), weight.float(), bias.float(), eps)
+    outs = ()
+    if out_fp32:
+        outs += (y,)
+    if out_bf16:
+        outs += (y.to(torch.bfloat16),)
+    return outs[0] if len(outs) == 1 else outs
+
+
+def relpos_attention(q, k, v, klens, n_heads, r=None, u_bias=None, v_bias=None, clamp_len=-1, causal=False,
+                     lookahead=0, chunk_c=0, chunk_l=0, want_stats=False):
+    """SURVEY.md Appendix A.1 written out: query i sits at key position mlen + i."""
+    assert not want_stats
+    B, Tq, D = q.shape
+    Tk = k.shape[1]
+    dk = D // n_heads
+    mlen = Tk - Tq
+    qh = q.float().reshape(B, Tq, n_heads, dk)
+    kh = k.float().reshape(B, Tk, n_heads, dk)
+    vh = v.float().reshape(B, Tk, n_heads, dk)
+    qu = qh + (u_bias.float() if u_bias is not None else 0.)
+    e = torch.einsum("bihd,bjhd->bhij", qu, kh)
+    i = torch.arange(Tq).unsqueeze(1)
+    j = torch.arange(Tk).unsqueeze(0)
+    if r is not None:
+        qv = qh + (v_bias.float() if v_bias is not None else 0.)
+        dist = (mlen + i - j).abs()
+        if clamp_len > 0:
+            dist = dist.clamp(max=clamp_len)
+        dist = dist.clamp(max=r.shape[0] - 1)
+        rh = r.float().reshape(-1, n_heads, dk)
+        bd_raw = torch.einsum("bihd,rhd->bhir", qv, rh)                        # [B, H, Tq, rlen]
+        e = e + torch.gather(bd_raw, 3, dist.expand(B, n_heads, Tq, Tk))
+    e = e / math.sqrt(dk)
+    vis = (j < klens.reshape(B, 1, 1).long()).expand(B, Tq, Tk).clone()
+    if causal:
+        vis &= (j <= mlen + i + lookahead).unsqueeze(0)
+    if chunk_c > 0:
+        cs = ((mlen + i) // chunk_c) * chunk_c
+        vis &= ((j >= cs - chunk_l) & (j < cs + chunk_c)).unsqueeze(0)
+    e = e.masked_fill(~vis.unsqueeze(1), torch.finfo(torch.float32).min)
+    aw = torch.softmax(e, dim=-1)
+    cv = torch.einsum("bhij,bjhd->bihd", aw, vh).reshape(B, Tq, D)
+    return cv.to(q.dtype)
+
+
+def conformer_conv(x, dw_weight, dw_bias, norm_mode, norm_w, norm_b, eps, run_mean=None, run_var=None, causal=False):
+    B, T, d = x.shape
+    taps = dw_weight if dw_weight.dim() == 2 else dw_weight.reshape(d, -1).t()   # [k, d]
+    k = taps.shape[0]
+    xf = x.float().transpose(1, 2)                                              # [B, d, T]
+    w = taps.t().reshape(d, 1, k).float()
+    if causal:
+        y = F.conv1d(F.pad(xf, (k - 1, 0)), w, dw_bias.float(), groups=d)
+    else:
+        y = F.conv1d(xf, w, dw_bias.float(), padding=(k - 1) // 2, groups=d)
+    y = y.transpose(1, 2)                                                       # [B, T, d]
+    if norm_mode == "layer_norm":
+        y = F.layer_norm(y, (d,), norm_w.float(), norm_b.float(), eps)
+    elif norm_mode == "batch_norm":
+        y = (y - run_mean) / torch.sqrt(run_var + eps) * norm_w + norm_b
+    else:
+        y = F.group_norm(y.reshape(B * T, d, 1), max(1, d // 2), norm_w.float(), norm_b.float(), eps).reshape(B, T, d)
+    return (y * torch.sigmoid(y)).to(x.dtype)
+
+
+def scale_(x, a):
+    return x.mul_(a)
+
+
+def add_pos_enc_(x, pe, a=1.0):
+    assert pe.shape == x.shape[1:]
+    return x.mul_(a).add_(pe.unsqueeze(0))
+
+
+def xl_pos_table(inv_freq, rows):
+    pos = torch.arange(-1, -rows - 1, -1.0, dtype=torch.float32)
+    s = torch.einsum("i,j->ij", pos, inv_freq.float())
+    return torch.cat([s.sin(), s.cos()], dim=-1)
+
+
+def conv3x3_relu(x, weight, bias, B, T, Fq, in_chmajor=False, relu=True, out_dtype=torch.float32):
+    CO, CI = weight.shape[0], weight.shape[1]
+    if in_chmajor:                                       # raw features `[B, T, CI * F]`, index c * F + f
+        xin = x.float().reshape(B, T, CI, Fq).permute(0, 2, 1, 3)
+    else:                                                # channels-last `[B, T, F, CI]`
+        xin = x.float().reshape(B, T, Fq, CI).permute(0, 3, 1, 2)
+    y = F.conv2d(xin, weight.float(), bias.float(), padding=1)
+    if relu:
+        y = torch.relu(y)
+    return y.permute(0, 2, 3, 1).contiguous().to(out_dtype)      # [B, T, F, CO]
+
+
+def maxpool2d(x, pool_t, pool_f, out_chmajor=False, out_dtype=None):
+    B, T, Fq, C = x.shape
+    y = F.max_pool2d(x.float().permute(0, 3, 1, 2), (pool_t, pool_f), (pool_t, pool_f), ceil_mode=True)   # [B, C, To, Fo]
+    if out_chmajor:
+        y = y.permute(0, 2, 1, 3).reshape(B, y.shape[2], -1)                    # index c * Fo + f (conv.py:189)
+    else:
+        y = y.permute(0, 2, 3, 1)
+    return y.contiguous().to(out_dtype or x.dtype)
+
+
+def pool_time(x, factor, mode):
+    B, T, D = x.shape
+    xt = x.float().transpose(1, 2)
+    if mode == "max":
+        y = F.max_pool1d(xt, factor, factor, ceil_mode=True)
+    elif mode == "mean":
+        y = F.avg_pool1d(xt, factor, factor, ceil_mode=True)
+    elif mode == "drop":
+        y = xt[:, :, ::factor]
+    else:                                                # 'add' (subsampling.py:150-168): sum of each frame group, zero padded
+        Tp = -(-T // factor) * factor
+        y = F.pad(xt, (0, Tp - T)).reshape(B, D, Tp // factor, factor).sum(-1)
+    return y.transpose(1, 2).contiguous().to(x.dtype)
+
+
+def maxpool_time(x, factor):
+    return pool_time(x, factor, "max")
+
+
+DOUBLES = dict(prepare_weight=prepare_weight, to_bf16=to_bf16, linear=linear, layernorm=layernorm,
+               relpos_attention=relpos_attention, conformer_conv=conformer_conv, scale_=scale_, add_pos_enc_=add_pos_enc_, xl_pos_table=xl_pos_table,
+               conv3x3_relu=conv3x3_relu, maxpool2d=maxpool2d, pool_time=pool_time, maxpool_time=maxpool_time)
+
+
+def install(monkeypatch):
+    """Replace the ctypes-backed ops by the doubles for the duration of one test."""
+    from neural_sp_b200 import ops
+    for name, fn in DOUBLES.items():
+        monkeypatch.setattr(ops, name, fn)
