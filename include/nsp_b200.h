@@ -226,6 +226,13 @@ size_t nsp_lstm_workspace_bytes(int B, int H, int ndir);
 nsp_status nsp_lstm_seq_fwd(const float* gates_x, const float* w_hh, const int32_t* lens, float* y,
                             int B, int T, int H, int ndir, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Streaming variant (state carry-over across chunks, encoders/rnn.py:343-346 `rnn(xs, hx=prev_state)` and the LC-BLSTM
+ * chunk loop :454-498): h0, c0 fp32 [ndir, B, H] = nn.LSTM's hx (null: zeros); hN, cN fp32 [ndir, B, H] receive the
+ * state after each utterance's last valid frame (both null: not wanted). */
+nsp_status nsp_lstm_seq_fwd_state(const float* gates_x, const float* w_hh, const int32_t* lens, float* y,
+                                  int B, int T, int H, int ndir, const float* h0, const float* c0,
+                                  float* hN, float* cN, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Training variants of the LSTM layer recurrence (reference: autograd through nn.LSTM, encoders/rnn.py:534-546).
  * _fwd_save additionally stores, for every valid (b, t, dir): the gate activations i,f,g,o  acts [B,T,ndir,4H], the cell
  * state entering the step  cprev [B,T,ndir,H]  and the hidden state entering it  hprev [B,T,ndir,H]  (buffers must be

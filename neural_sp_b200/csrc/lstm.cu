@@ -35,6 +35,11 @@ struct LstmParams {
     float* acts;            // [B, T, ndir, 4H]  gate activations i, f, g, o
     float* cprev;           // [B, T, ndir, H]   cell state entering the step
     float* hprev;           // [B, T, ndir, H]   hidden state entering the step (operand of the W_hh weight gradient)
+    // optional (streaming, encoders/rnn.py:343-346): state carried across chunks, nn.LSTM's (h_n, c_n) layout [ndir, B, H]
+    const float* h0;        // initial hidden state (null: zeros); the launcher also copies it into hbuf slot 0
+    const float* c0;        // initial cell state (null: zeros)
+    float* hN;              // final hidden state = state after each utterance's last valid frame (null: not wanted)
+    float* cN;              // final cell state
 };
 
 __device__ __forceinline__ float sigmoid_exact(float x) { return 1.f / (1.f + expf(-x)); }
@@ -69,6 +74,17 @@ __global__ void __launch_bounds__(256, 1) lstm_seq_kernel(LstmParams p) {
     float c_state[4], h_state[4];                      // up to 4 batch tiles (B <= 128) kept in registers
 #pragma unroll
     for (int i = 0; i < 4; ++i) { c_state[i] = 0.f; h_state[i] = 0.f; }
+    if (p.h0 || p.c0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int b = i * BT + cb;
+            if (b < p.B) {
+                const size_t si = ((size_t)dir * p.B + b) * H + j0 + cu;
+                if (p.c0) c_state[i] = __ldg(p.c0 + si);
+                if (p.h0) h_state[i] = __ldg(p.h0 + si);
+            }
+        }
+    }
 
     for (int s = 0; s < p.T; ++s) {
         const float* hprev = p.hbuf + ((size_t)(dir * 2 + (s & 1)) * p.B) * H;
@@ -151,6 +167,17 @@ __global__ void __launch_bounds__(256, 1) lstm_seq_kernel(LstmParams p) {
             while (atomicAdd(p.bar + dir, 0u) < target) { __nanosleep(20); }
         }
         __syncthreads();
+    }
+    if (p.hN) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int b = i * BT + cb;
+            if (b < p.B) {
+                const size_t si = ((size_t)dir * p.B + b) * H + j0 + cu;
+                p.hN[si] = h_state[i];
+                p.cN[si] = c_state[i];
+            }
+        }
     }
 }
 
@@ -312,7 +339,8 @@ extern "C" size_t nsp_lstm_workspace_bytes(int B, int H, int ndir) {
 
 static nsp_status lstm_fwd_impl(const float* gates_x, const float* w_hh, const int32_t* lens, float* y,
                                 int B, int T, int H, int ndir, float* acts, float* cprev, float* hprev,
-                                void* workspace, size_t workspace_bytes, void* stream) {
+                                void* workspace, size_t workspace_bytes, void* stream,
+                                const float* h0 = nullptr, const float* c0 = nullptr, float* hN = nullptr, float* cN = nullptr) {
     NSP_CHECK_ARG(gates_x && w_hh && lens && y && workspace, "lstm_seq: null pointer");
     NSP_CHECK_ARG(B > 0 && T > 0 && H > 0 && (ndir == 1 || ndir == 2), "lstm_seq: bad shape");
     if (H % UPC != 0 || H % 4 != 0) { set_error("lstm_seq: H=%d must be a multiple of 8", H); return NSP_ERR_UNSUPPORTED; }
@@ -333,11 +361,16 @@ static nsp_status lstm_fwd_impl(const float* gates_x, const float* w_hh, const i
     LstmParams p;
     p.gx = gates_x; p.whh = w_hh; p.lens = lens; p.y = y; p.B = B; p.T = T; p.H = H; p.ndir = ndir;
     p.acts = acts; p.cprev = cprev; p.hprev = hprev;
+    p.h0 = h0; p.c0 = c0; p.hN = hN; p.cN = cN;
     const size_t hbytes = align_up((size_t)ndir * 2 * B * H * sizeof(float), 256);
     p.hbuf = (float*)workspace;
     p.bar = (unsigned int*)((char*)workspace + hbytes);
     NSP_CUDA_OK(cudaMemsetAsync(workspace, 0, hbytes + 256, st));
     NSP_CUDA_OK(cudaMemsetAsync(y, 0, (size_t)B * T * ndir * H * sizeof(float), st));
+    if (h0)     // h_{-1} as seen by the other CTAs at step 0: slot 0 of each direction's double buffer
+        for (int d = 0; d < ndir; ++d)
+            NSP_CUDA_OK(cudaMemcpyAsync(p.hbuf + (size_t)d * 2 * B * H, h0 + (size_t)d * B * H, (size_t)B * H * sizeof(float),
+                                        cudaMemcpyDeviceToDevice, st));
     // both directions in one cooperative launch when they fit together, else one launch per direction
     const int dirs_per_launch = (ndir * per_dir <= capacity) ? ndir : 1;
     for (int d0 = 0; d0 < ndir; d0 += dirs_per_launch) {
@@ -351,6 +384,14 @@ static nsp_status lstm_fwd_impl(const float* gates_x, const float* w_hh, const i
 extern "C" nsp_status nsp_lstm_seq_fwd(const float* gates_x, const float* w_hh, const int32_t* lens, float* y,
                                        int B, int T, int H, int ndir, void* workspace, size_t workspace_bytes, void* stream) {
     return lstm_fwd_impl(gates_x, w_hh, lens, y, B, T, H, ndir, nullptr, nullptr, nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" nsp_status nsp_lstm_seq_fwd_state(const float* gates_x, const float* w_hh, const int32_t* lens, float* y,
+                                             int B, int T, int H, int ndir, const float* h0, const float* c0,
+                                             float* hN, float* cN, void* workspace, size_t workspace_bytes, void* stream) {
+    NSP_CHECK_ARG((hN == nullptr) == (cN == nullptr), "lstm_seq_fwd_state: hN and cN go together");
+    return lstm_fwd_impl(gates_x, w_hh, lens, y, B, T, H, ndir, nullptr, nullptr, nullptr, workspace, workspace_bytes, stream,
+                         h0, c0, hN, cN);
 }
 
 extern "C" nsp_status nsp_lstm_seq_fwd_save(const float* gates_x, const float* w_hh, const int32_t* lens, float* y,

@@ -471,10 +471,12 @@ def pool_time(x, factor, mode):
     return y
 
 
-def lstm_seq(gates_x, w_hh, lens, n_dirs, save=False):
+def lstm_seq(gates_x, w_hh, lens, n_dirs, save=False, state=None, want_state=False):
     """LSTM recurrence of one layer (nsp_lstm_seq_fwd): gates_x fp32 `[B,T,n_dirs*4H]`, w_hh fp32 `[n_dirs,4H,H]`,
     lens int32 `[B]` CUDA -> y fp32 `[B,T,n_dirs*H]` (zeros beyond each length).
-    save=True (training, nsp_lstm_seq_fwd_save) -> (y, acts `[B,T,n_dirs,4H]`, cprev, hprev `[B,T,n_dirs,H]`)."""
+    save=True (training, nsp_lstm_seq_fwd_save) -> (y, acts `[B,T,n_dirs,4H]`, cprev, hprev `[B,T,n_dirs,H]`).
+    state=(h0, c0) fp32 `[n_dirs,B,H]` (nn.LSTM's hx) / want_state=True (streaming, nsp_lstm_seq_fwd_state)
+    -> (y, (hN, cN))."""
     _require_cuda(gates_x, w_hh, lens)
     gates_x = gates_x.contiguous().float()
     w_hh = w_hh.contiguous().float()
@@ -483,6 +485,19 @@ def lstm_seq(gates_x, w_hh, lens, n_dirs, save=False):
     ws_bytes = lib.nsp_lstm_workspace_bytes(B, H, n_dirs)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=gates_x.device)
     y = torch.empty(B, T, n_dirs * H, dtype=torch.float32, device=gates_x.device)
+    if state is not None or want_state:
+        assert not save, "the training path starts from a zero state"
+        h0 = c0 = None
+        if state is not None:
+            h0, c0 = (t.contiguous().float() for t in state)
+            _require_cuda(h0, c0)
+            assert h0.shape == (n_dirs, B, H) and c0.shape == (n_dirs, B, H), (h0.shape, c0.shape, (n_dirs, B, H))
+        hN = torch.empty(n_dirs, B, H, dtype=torch.float32, device=gates_x.device)
+        cN = torch.empty(n_dirs, B, H, dtype=torch.float32, device=gates_x.device)
+        _run("nsp_lstm_seq_fwd_state", lib.nsp_lstm_seq_fwd_state, ptr(gates_x), ptr(w_hh), ptr(lens), ptr(y), B, T, H, n_dirs,
+             ptr(h0), ptr(c0), ptr(hN), ptr(cN), ptr(ws), ws_bytes, current_stream_ptr(),
+             flops=2.0 * B * T * n_dirs * 4 * H * H, tag="lstm_seq")
+        return y, (hN, cN)
     if save:
         acts = torch.zeros(B, T, n_dirs, 4 * H, dtype=torch.float32, device=gates_x.device)
         cprev = torch.zeros(B, T, n_dirs, H, dtype=torch.float32, device=gates_x.device)

@@ -50,7 +50,10 @@ def build_ours(g, device, precision):
     a, conv, kind = golden_cfg(g)
     a = dict(a)
     a["frontend_conv"] = ConvEncoder(**conv) if conv else None
-    if kind == "conformer":
+    if kind == "rnn":
+        from neural_sp_b200.encoders.rnn import RNNEncoder
+        enc = RNNEncoder(**a)
+    elif kind == "conformer":
         enc = ConformerEncoder(**a)
     else:
         a.pop("kernel_size"), a.pop("normalization")

@@ -48,23 +48,38 @@ CASES = {
     # unidirectional Transformer with absolute positions (offset carried across chunks), no CNN
     "stream_uni_transformer_add": (dict(enc_type='uni_transformer', pe_type='add', ffn_activation='relu'), None,
                                    'transformer', (0, 4, 0), 61),
+    # C4 in miniature: CNN (1/4) + unidirectional LSTM stack with projections, (h, c) carried across chunks of 8 frames
+    "stream_conv_lstm": (dict(RNN=True, enc_type='conv_lstm', n_units=32, n_projs=16, n_layers=3, subsample="1_1_1",
+                              last_proj_dim=24), {}, 'rnn', (0, 8, 0), 150),
+    # latency-controlled BLSTM (N_c = 32, N_r = 16) behind a 1/2 CNN, hierarchical subsampling, summed directions
+    "stream_lc_blstm": (dict(RNN=True, enc_type='conv_blstm', n_units=24, n_layers=3, subsample="1_2_1",
+                             chunk_size_current="32", chunk_size_right="16", bidir_sum_fwd_bwd=True),
+                        dict(channels="32", kernel_sizes="(3,3)", strides="(1,1)", poolings="(2,2)"), 'rnn', (0, 32, 16), 175),
 }
+
+RNN_BASE = dict(input_dim=80, enc_type='blstm', n_units=16, n_projs=0, last_proj_dim=0, n_layers=2, n_layers_sub1=0,
+                n_layers_sub2=0, dropout_in=0.0, dropout=0.0, subsample="1_1", subsample_type='drop', n_stacks=1,
+                n_splices=1, frontend_conv=None, bidir_sum_fwd_bwd=False, task_specific_layer=False, param_init=0.1,
+                chunk_size_current="0", chunk_size_right="0", cnn_lookahead=True, rsp_prob=0)
 
 
 def build(name):
     import importlib
     ov, conv_ov, kind, _, _ = CASES[name]
-    args = dict(BASE)
+    ov = dict(ov)
+    args = dict(RNN_BASE) if ov.pop("RNN", False) else dict(BASE)
     args.update(ov)
     torch.manual_seed(0)
     conv_args = None
     if conv_ov is not None:
         conv_args = dict(CONV)
         conv_args.update(conv_ov)
-        conv_args["bottleneck_dim"] = args["d_model"]
+        conv_args["bottleneck_dim"] = args["d_model"] if kind != 'rnn' else 0
         conv_mod = importlib.import_module('neural_sp.models.seq2seq.encoders.conv')
         args["frontend_conv"] = conv_mod.ConvEncoder(**conv_args)
-    if kind == 'conformer':
+    if kind == 'rnn':
+        enc = importlib.import_module('neural_sp.models.seq2seq.encoders.rnn').RNNEncoder(**args)
+    elif kind == 'conformer':
         enc = importlib.import_module('neural_sp.models.seq2seq.encoders.conformer').ConformerEncoder(**args)
     else:
         a = dict(args)
@@ -76,14 +91,18 @@ def build(name):
 def main():
     for name, (_, _, _, (N_l, N_c, N_r), T) in CASES.items():
         enc, args, conv_args, kind = build(name)
-        unidir = 'uni' in args['enc_type']
-        if enc.streaming_type == 'mask':
+        unidir = 'uni' in args['enc_type'] or args['enc_type'] in ('lstm', 'conv_lstm')
+        st = getattr(enc, 'streaming_type', '')
+        if st == 'mask':
             N_l = 0
         factor = enc.subsampling_factor
-        conv_context = enc.conv.context_size if (enc.conv is not None and not enc.lc_bidir) else 0
+        if kind == 'rnn':
+            conv_context = enc.conv.context_size if enc.conv is not None else 0
+        else:
+            conv_context = enc.conv.context_size if (enc.conv is not None and not enc.lc_bidir) else 0
         rng = np.random.default_rng(4321)
         xs = rng.standard_normal((1, T, 80)).astype(np.float32)
-        if enc.streaming_type == 'mask' and enc.conv is not None and T % N_c != 0:
+        if st == 'mask' and enc.conv is not None and T % N_c != 0:
             xs = np.concatenate([xs, np.zeros((1, N_c - T % N_c, 80), np.float32)], axis=1)
         xmax = xs.shape[1]
         xs_t = torch.from_numpy(xs)
@@ -98,7 +117,7 @@ def main():
             start, end = j - N_l - conv_context, (j + N_c + N_r) + conv_context
             chunk = xs_t[:, max(0, start):end]
             pl = pr = 0
-            if enc.streaming_type == 'reshape':
+            if st == 'reshape':
                 xlen = max(factor, min(xmax - j, N_c))
                 pl = max(0, -start)
                 pr = max(0, end - xmax) if end >= xmax else 0

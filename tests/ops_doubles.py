@@ -184,9 +184,35 @@ def maxpool_time(x, factor):
     return pool_time(x, factor, "max")
 
 
+def lstm_seq(gates_x, w_hh, lens, n_dirs, save=False, state=None, want_state=False):
+    """Packed-sequence LSTM recurrence (csrc/lstm.cu contract): state frozen and outputs zero beyond each length, the
+    reverse direction of utterance b starts at its own last frame; optional initial / final state `[n_dirs, B, H]`."""
+    assert not save
+    B, T, G = gates_x.shape
+    H = G // (4 * n_dirs)
+    y = torch.zeros(B, T, n_dirs * H)
+    hN, cN = torch.zeros(n_dirs, B, H), torch.zeros(n_dirs, B, H)
+    for d in range(n_dirs):
+        for b in range(B):
+            n = min(max(int(lens[b]), 0), T)
+            h = state[0][d, b].clone().float() if state is not None else torch.zeros(H)
+            c = state[1][d, b].clone().float() if state is not None else torch.zeros(H)
+            for s in range(n):
+                t = s if d == 0 else n - 1 - s
+                g = gates_x[b, t, d * 4 * H:(d + 1) * 4 * H].float() + w_hh[d].float() @ h
+                i, f, o = torch.sigmoid(g[:H]), torch.sigmoid(g[H:2 * H]), torch.sigmoid(g[3 * H:])
+                c = f * c + i * torch.tanh(g[2 * H:3 * H])
+                h = o * torch.tanh(c)
+                y[b, t, d * H:(d + 1) * H] = h
+            hN[d, b], cN[d, b] = h, c
+    if state is not None or want_state:
+        return y, (hN, cN)
+    return y
+
+
 DOUBLES = dict(prepare_weight=prepare_weight, to_bf16=to_bf16, linear=linear, layernorm=layernorm,
                relpos_attention=relpos_attention, conformer_conv=conformer_conv, scale_=scale_, add_pos_enc_=add_pos_enc_, xl_pos_table=xl_pos_table,
-               conv3x3_relu=conv3x3_relu, maxpool2d=maxpool2d, pool_time=pool_time, maxpool_time=maxpool_time)
+               conv3x3_relu=conv3x3_relu, maxpool2d=maxpool2d, pool_time=pool_time, maxpool_time=maxpool_time, lstm_seq=lstm_seq)
 
 
 def install(monkeypatch):

@@ -9,7 +9,7 @@ from conftest import load_golden
 from enc_util import build_ours, replay_stream
 
 STREAM_CASES = ["stream_uni_conformer", "stream_lc_mask_conformer", "stream_lc_reshape_transformer",
-                "stream_uni_transformer_add"]
+                "stream_uni_transformer_add", "stream_conv_lstm", "stream_lc_blstm"]
 
 
 @pytest.mark.parametrize("name", STREAM_CASES)
