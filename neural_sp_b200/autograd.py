@@ -282,7 +282,14 @@ class _BlockFn(torch.autograd.Function):
         x = xs
         if in_scale != 1.0:
             x = ops.scale_(xs.clone(), in_scale)
-        if hasattr(block, "feed_forward_macaron"):
+        if getattr(block, "v2", False):           # conformer_block_v2.py: FFN -> conv -> plain MHA -> FFN -> LN
+            x, saved["ffm"] = ffn_fwd(block.feed_forward_macaron, block.norm1, x, block.fc_factor, prec)
+            x, saved["conv"] = convmod_fwd(block.conv, block.norm2, x, prec)
+            x, saved["att"] = attn_fwd(block.self_attn, block.norm3, x, None, klens, None, None, mask_kw, prec, False)
+            x, saved["ff"] = ffn_fwd(block.feed_forward, block.norm4, x, block.fc_factor, prec)
+            saved["x5"] = x
+            x = ops.layernorm(x, block.norm5.weight, block.norm5.bias, block.norm5.eps)
+        elif hasattr(block, "feed_forward_macaron"):
             x, saved["ffm"] = ffn_fwd(block.feed_forward_macaron, block.norm1, x, block.fc_factor, prec)
             x, saved["att"] = attn_fwd(block.self_attn, block.norm2, x, pos, klens, u_bias, v_bias, mask_kw, prec, True)
             x, saved["conv"] = convmod_fwd(block.conv, block.norm3, x, prec)
@@ -303,7 +310,17 @@ class _BlockFn(torch.autograd.Function):
         u_bias, v_bias = ctx.rel_bias
         G = _Grads(ctx.params)
         dy = dy.contiguous().float()
-        if hasattr(block, "feed_forward_macaron"):
+        if getattr(block, "v2", False):
+            fc = block.fc_factor
+            dx, dxo = _ln_bwd(block.norm5, dy, S["x5"], None, G, prec, block.feed_forward.w_2.bias, fc)
+            dx, dxo = ffn_bwd(block.feed_forward, block.norm4, S["ff"], dx, dxo, fc, prec, G, bias_done=True,
+                              nxt=(block.self_attn.w_out.bias, 1.0))
+            dx, dxo = attn_bwd(block.self_attn, block.norm3, S["att"], dx, dxo, None, ctx.klens, None, None, ctx.mask_kw,
+                               prec, False, G, (None, None), bias_done=True, nxt=(block.conv.pointwise_conv2.bias, 1.0))
+            dx, dxo = convmod_bwd(block.conv, block.norm2, S["conv"], dx, dxo, prec, G, bias_done=True,
+                                  nxt=(block.feed_forward_macaron.w_2.bias, fc))
+            dx, dxo = ffn_bwd(block.feed_forward_macaron, block.norm1, S["ffm"], dx, dxo, fc, prec, G, bias_done=True)
+        elif hasattr(block, "feed_forward_macaron"):
             # every LayerNorm backward also accumulates the bias gradient of the branch that consumes its dx
             fc = block.fc_factor
             dx, dxo = _ln_bwd(block.norm5, dy, S["x5"], None, G, prec, block.feed_forward.w_2.bias, fc)

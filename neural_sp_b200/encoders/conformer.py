@@ -1,9 +1,11 @@
-"""Conformer encoder (reference encoders/conformer.py:18-111): TransformerEncoder with Conformer blocks."""
+"""Conformer encoder (reference encoders/conformer.py:18-111): TransformerEncoder with Conformer blocks
+(version 1: FFN-MHSA(rel-pos)-Conv-FFN; ``conformer_v2`` encoder types: FFN-Conv-MHSA(plain)-FFN)."""
 import copy
 
 import torch.nn as nn
 
 from .conformer_block import ConformerEncoderBlock
+from .conformer_block_v2 import ConformerEncoderBlock_v2
 from .transformer import TransformerEncoder
 
 
@@ -18,11 +20,13 @@ class ConformerEncoder(TransformerEncoder):
                          dropout, dropout_att, dropout_layer, subsample, subsample_type, n_stacks, n_splices,
                          frontend_conv, task_specific_layer, param_init, clamp_len, lookahead, chunk_size_left,
                          chunk_size_current, chunk_size_right, streaming_type)
-        if 'conformer_v2' in enc_type:
-            raise NotImplementedError("conformer_v2 blocks are not on the B200 path")
-        assert pe_type in ['relative', 'relative_xl']
         causal = self.unidir or (self.streaming_type == 'mask')
-        self.layers = nn.ModuleList([copy.deepcopy(ConformerEncoderBlock(
+        if 'conformer_v2' in enc_type:          # conv module before a plain MHA (reference conformer.py:80-84)
+            block = ConformerEncoderBlock_v2
+        else:
+            assert pe_type in ['relative', 'relative_xl']
+            block = ConformerEncoderBlock
+        self.layers = nn.ModuleList([copy.deepcopy(block(
             d_model, d_ff, n_heads, kernel_size, dropout, dropout_att, dropout_layer * (lth + 1) / n_layers,
             layer_norm_eps, ffn_activation, param_init, pe_type, clamp_len, ffn_bottleneck_dim, causal, normalization))
             for lth in range(n_layers)])

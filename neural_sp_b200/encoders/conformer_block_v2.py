@@ -1,0 +1,78 @@
+"""Conformer encoder block, version 2 (reference encoders/conformer_block_v2.py:20-183), B200-native.
+
+Macaron FFN -> conv module -> plain multi-head self-attention (no relative positions) -> FFN -> LayerNorm: the
+convolution and the attention swap places with respect to conformer_block.py and ``norm2`` / ``norm3`` follow them.
+Same parameter names as the reference; streaming caches ``input_conv`` / ``input_san`` as in version 1."""
+import random
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..modules._prep import get_precision
+from ..modules.conformer_convolution import ConformerConvBlock
+from ..modules.multihead_attention import MultiheadAttentionMechanism as MHA
+from ..modules.positionwise_feed_forward import PositionwiseFeedForward as FFN
+from .conformer_block import _ln
+
+random.seed(1)
+
+
+class ConformerEncoderBlock_v2(nn.Module):
+    v2 = True
+
+    def __init__(self, d_model, d_ff, n_heads, kernel_size, dropout, dropout_att, dropout_layer, layer_norm_eps,
+                 ffn_activation, param_init, pe_type, clamp_len, ffn_bottleneck_dim, unidirectional,
+                 normalization='layer_norm'):
+        super().__init__()
+        self.n_heads = n_heads
+        self.fc_factor = 0.5
+        self.norm1 = nn.LayerNorm(d_model, eps=layer_norm_eps)
+        self.feed_forward_macaron = FFN(d_model, d_ff, dropout, ffn_activation, param_init, ffn_bottleneck_dim)
+        self.norm2 = nn.LayerNorm(d_model, eps=layer_norm_eps)
+        self.conv = ConformerConvBlock(d_model, kernel_size, param_init, normalization, causal=unidirectional)
+        self.conv_context = kernel_size
+        self.norm3 = nn.LayerNorm(d_model, eps=layer_norm_eps)
+        self.self_attn = MHA(kdim=d_model, qdim=d_model, adim=d_model, odim=d_model, n_heads=n_heads, dropout=dropout_att,
+                             param_init=param_init)
+        self.norm4 = nn.LayerNorm(d_model, eps=layer_norm_eps)
+        self.feed_forward = FFN(d_model, d_ff, dropout, ffn_activation, param_init, ffn_bottleneck_dim)
+        self.norm5 = nn.LayerNorm(d_model, eps=layer_norm_eps)
+        self.dropout = nn.Dropout(dropout)
+        self.dropout_layer = dropout_layer
+        self._xx_aws = None
+
+    @property
+    def xx_aws(self):
+        return self._xx_aws
+
+    def reset_visualization(self):
+        self._xx_aws = None
+
+    def forward(self, xs, klens, cache=None, pos_embs=None, rel_bias=(None, None), mask_kw=None):
+        """Same contract as ConformerEncoderBlock.forward; pos_embs is ignored, rel_bias must be (None, None)."""
+        assert rel_bias[0] is None and rel_bias[1] is None
+        if self.training and (self.dropout.p > 0 or self.self_attn.dropout_attn.p > 0):
+            raise NotImplementedError("dropout > 0 in training mode is not on the B200 path yet")
+        prec = get_precision(self)
+        mask_kw = mask_kw or {}
+        new_cache = {}
+        qlen = xs.size(1)
+        if self.dropout_layer > 0:
+            if self.training and random.random() < self.dropout_layer:
+                return xs, new_cache
+            ops.scale_(xs, 1.0 / (1 - self.dropout_layer))
+        xs = self.feed_forward_macaron(_ln(self.norm1, xs, prec), residual=xs, scale=self.fc_factor, out=xs)
+        c_in = _ln(self.norm2, xs, prec)
+        if cache is not None:
+            c_in = torch.cat([cache['input_conv'].to(c_in.dtype), c_in], dim=1)
+            c_in = c_in[:, max(0, c_in.size(1) - (self.conv_context + qlen - 1)):].contiguous()
+        new_cache['input_conv'] = c_in
+        xs = self.conv(c_in, residual=xs, out=xs, keep_last=qlen if cache is not None else None)
+        h = _ln(self.norm3, xs, prec)
+        kv = h if cache is None else torch.cat([cache['input_san'].to(h.dtype), h], dim=1)
+        new_cache['input_san'] = kv
+        xs = self.self_attn(kv, h, klens, residual=xs, out=xs, **mask_kw)
+        xs = self.feed_forward(_ln(self.norm4, xs, prec), residual=xs, scale=self.fc_factor, out=xs)
+        xs = ops.layernorm(xs, self.norm5.weight, self.norm5.bias, self.norm5.eps)
+        return xs, new_cache

@@ -220,3 +220,140 @@ def install(monkeypatch):
     from neural_sp_b200 import ops
     for name, fn in DOUBLES.items():
         monkeypatch.setattr(ops, name, fn)
+
+
+# ---------------------------------------------------------------------------------------------
+# training path: backward ops (each one = torch autograd through the forward double above)
+# ---------------------------------------------------------------------------------------------
+def _linear_train(x, w_prepared, bias=None, prec="bf16", act=None, glu=False, residual=None, alpha=1.0,
+                  out_dtype=torch.float32, out=None, out2_bf16=False, save_pre=False):
+    """ops.linear including the training-only output: save_pre -> (out, pre) with pre = x W^T + b before act / GLU."""
+    assert not out2_bf16
+    y = linear(x, w_prepared, bias, prec, act, glu, residual, alpha, out_dtype, out)
+    if not save_pre:
+        return y
+    w = w_prepared[0]
+    x2 = x.reshape(-1, x.shape[-1]).float()
+    if w.shape[1] != x2.shape[1]:
+        x2 = F.pad(x2, (0, w.shape[1] - x2.shape[1]))
+    pre = x2 @ w.t()
+    if bias is not None:
+        pre = pre + bias.float()
+    return y, pre.reshape(*x.shape[:-1], -1)
+
+
+def linear_wgrad(dy, x, prec, dw, alpha=1.0, accumulate=True):
+    N, K = dw.shape
+    v = alpha * dy.reshape(-1, N).float().t() @ x.reshape(-1, x.shape[-1])[:, :K].float()
+    dw.copy_(dw + v if accumulate else v)
+    return dw
+
+
+def colsum_acc(x, y, alpha=1.0):
+    return y.add_(alpha * x.reshape(-1, x.shape[-1]).float().sum(0))
+
+
+def layernorm_bwd(dy, x, gamma, eps, dres=None, dgamma=None, dbeta=None, want_fp32=True, want_bf16=False, in_scale=1.0,
+                  dcol=None, dcol_alpha=1.0):
+    with torch.enable_grad():
+        xx = x.detach().float().clone().requires_grad_(True)
+        g = gamma.detach().float().clone().requires_grad_(True)
+        b = torch.zeros_like(g).requires_grad_(True)
+        F.layer_norm(xx * in_scale, (x.shape[-1],), g, b, eps).backward(dy.float().reshape(x.shape))
+    dx = xx.grad + (dres.float().reshape(x.shape) if dres is not None else 0.)
+    if dgamma is not None:
+        dgamma.add_(g.grad)
+    if dbeta is not None:
+        dbeta.add_(b.grad)
+    if dcol is not None:
+        dcol.add_(dcol_alpha * dx.reshape(-1, x.shape[-1]).sum(0))
+    outs = ()
+    if want_fp32:
+        outs += (dx,)
+    if want_bf16:
+        outs += (dx.to(torch.bfloat16),)
+    return outs[0] if len(outs) == 1 else outs
+
+
+def act_bwd(dh, z, act):
+    with torch.enable_grad():
+        zz = z.detach().float().clone().requires_grad_(True)
+        _act(zz, act).backward(dh.float())
+    return zz.grad.to(dh.dtype)
+
+
+def glu_bwd(dg, pre):
+    with torch.enable_grad():
+        pp = pre.detach().float().clone().requires_grad_(True)
+        a, b = pp.chunk(2, dim=-1)
+        (a * torch.sigmoid(b)).backward(dg.float())
+    return pp.grad.to(pre.dtype)
+
+
+def _relpos_attention_train(q, k, v, klens, n_heads, r=None, u_bias=None, v_bias=None, clamp_len=-1, causal=False,
+                            lookahead=0, chunk_c=0, chunk_l=0, want_stats=False):
+    out = relpos_attention(q, k, v, klens, n_heads, r, u_bias, v_bias, clamp_len, causal, lookahead, chunk_c, chunk_l)
+    return (out, None) if want_stats else out
+
+
+def relpos_attention_bwd(q, k, v, klens, n_heads, out, dout, r=None, u_bias=None, v_bias=None, clamp_len=-1, causal=False,
+                         lookahead=0, chunk_c=0, chunk_l=0, dr=None, du=None, dvb=None, stats=None):
+    with torch.enable_grad():
+        leaves = [t.detach().float().clone().requires_grad_(True) if t is not None else None for t in (q, k, v, r, u_bias, v_bias)]
+        qq, kk, vv, rr, uu, vb = leaves
+        relpos_attention(qq, kk, vv, klens, n_heads, rr, uu, vb, clamp_len, causal, lookahead, chunk_c,
+                         chunk_l).backward(dout.float())
+    if dr is not None and rr is not None:
+        dr.add_(rr.grad.reshape(dr.shape))
+    if du is not None and uu is not None:
+        du.add_(uu.grad.reshape(du.shape))
+        dvb.add_(vb.grad.reshape(dvb.shape))
+    return torch.cat([qq.grad, kk.grad, vv.grad], dim=-1).to(q.dtype)
+
+
+def conformer_conv_bwd(x, taps, dw_bias, norm_w, norm_b, eps, dy, dtaps, dbias, dnorm_w, dnorm_b, causal=False):
+    with torch.enable_grad():
+        leaves = [t.detach().float().clone().requires_grad_(True) for t in (x, taps, dw_bias, norm_w, norm_b)]
+        xx, tt, bb, gw, gb = leaves
+        conformer_conv(xx, tt, bb, "layer_norm", gw, gb, eps, causal=causal).backward(dy.float())
+    dtaps.add_(tt.grad), dbias.add_(bb.grad), dnorm_w.add_(gw.grad), dnorm_b.add_(gb.grad)
+    return xx.grad.to(x.dtype)
+
+
+def maxpool_time_bwd(x, dy, factor):
+    with torch.enable_grad():
+        xx = x.detach().float().clone().requires_grad_(True)
+        pool_time(xx, factor, "max").backward(dy.float())
+    return xx.grad
+
+
+def frontend_forward(enc, xs, out_scale, prec):
+    """Differentiable torch restatement of the CNN front-end + bridge (reference conv.py:167-195, 347-396); replaces
+    neural_sp_b200.autograd.frontend_forward (one autograd node with hand-written CUDA backward, checked on the GPU)."""
+    B, T, Fd = xs.shape
+    x = xs.view(B, T, enc.in_channel, Fd // enc.in_channel).transpose(1, 2)
+    for blk in enc.layers:
+        x = torch.relu(F.conv2d(x, blk.conv1.weight, blk.conv1.bias, padding=1))
+        x = torch.relu(F.conv2d(x, blk.conv2.weight, blk.conv2.bias, padding=1))
+        if blk.pool is not None:
+            x = F.max_pool2d(x, blk.pooling, blk.pooling, ceil_mode=True)
+    B, C, T, Fq = x.shape
+    x = x.transpose(1, 2).reshape(B, T, C * Fq)
+    if enc.bridge is not None:
+        x = F.linear(x, enc.bridge.weight, enc.bridge.bias)
+    return x * out_scale
+
+
+TRAIN_DOUBLES = dict(DOUBLES, linear=_linear_train, linear_wgrad=linear_wgrad, colsum_acc=colsum_acc,
+                     layernorm_bwd=layernorm_bwd, act_bwd=act_bwd, glu_bwd=glu_bwd, relpos_attention=_relpos_attention_train,
+                     relpos_attention_bwd=relpos_attention_bwd, conformer_conv_bwd=conformer_conv_bwd,
+                     maxpool_time_bwd=maxpool_time_bwd)
+
+
+def install_training(monkeypatch):
+    """Doubles for the training path: forward ops with their training-only outputs + every backward op; the CNN front-end
+    node is replaced as a whole."""
+    from neural_sp_b200 import ops, autograd as ag
+    for name, fn in TRAIN_DOUBLES.items():
+        monkeypatch.setattr(ops, name, fn)
+    monkeypatch.setattr(ag, "frontend_forward", frontend_forward)

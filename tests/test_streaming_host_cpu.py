@@ -62,6 +62,13 @@ CASES = [
     ({'enc_type': 'uni_conformer', 'chunk_size_current': "4"}, None),
     ({'enc_type': 'uni_conformer', 'chunk_size_current': "4", 'pe_type': 'relative_xl'}, None),
     ({'enc_type': 'uni_conformer', 'chunk_size_current': "4", 'clamp_len': 5}, None),
+    ({'enc_type': 'uni_conformer_v2', 'chunk_size_current': "1"}, None),
+    ({'enc_type': 'uni_conformer_v2', 'chunk_size_current': "4"}, None),
+    ({'enc_type': 'conformer_v2', 'streaming_type': 'reshape', 'chunk_size_left': "8", 'chunk_size_current': "16",
+      'chunk_size_right': "8"}, None),
+    ({'enc_type': 'conformer_v2', 'streaming_type': 'mask', 'chunk_size_left': "16", 'chunk_size_current': "8"}, None),
+    ({'enc_type': 'conv_uni_conformer_v2', 'chunk_size_current': "16", 'subsample': "1_2_1"}, {}),
+    ({'enc_type': 'conv_conformer_v2', 'streaming_type': 'mask', 'chunk_size_left': "16", 'chunk_size_current': "8"}, {}),
     # latency-controlled, no CNN
     ({'enc_type': 'transformer', 'streaming_type': 'reshape', 'chunk_size_left': "8", 'chunk_size_current': "16",
       'chunk_size_right': "8"}, None),
