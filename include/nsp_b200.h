@@ -310,6 +310,9 @@ nsp_status nsp_glu_bwd(int is_bf16, const void* dg, const void* pre, void* dpre,
 nsp_status nsp_colsum_acc(int is_bf16, const void* x, int64_t ldx, int M, int N, float alpha, float* y, void* stream);
 /* MaxPoolSubsampler backward (encoders/subsampling.py:175-209): x, dx fp32 [B,T,D], dy fp32 [B,ceil(T/f),D]. */
 nsp_status nsp_maxpool_time_bwd(const float* x, const float* dy, float* dx, int B, int T, int D, int factor, void* stream);
+/* Backward of nsp_pool_time_fwd for mode 1 mean (MeanPoolSubsampler subsampling.py:212-246), 2 drop (DropSubsampler
+ * :97-126), 3 add (AddSubsampler :129-172): dy fp32 [B,ceil(T/f),D] -> dx fp32 [B,T,D]. */
+nsp_status nsp_pool_time_bwd(const float* dy, float* dx, int B, int T, int D, int factor, int mode, void* stream);
 /* ReLU backward through the saved post-activation: dz = a > 0 ? dx : 0. */
 nsp_status nsp_relu_mask(int is_bf16, const void* dx, const void* a, void* dz, int64_t n, void* stream);
 /* ReLU + MaxPool2d(ceil_mode) backward on channels-last [B,T,F,C] (encoders/conv.py:362-394): a = saved post-ReLU

@@ -123,11 +123,15 @@ def _fusable(t):
 
 
 def ffn_fwd(ffn, norm, x, scale, prec):
-    if ffn.act_name == "glu":
-        raise NotImplementedError("training with the GLU feed-forward activation is not on the B200 path yet")
     n = _ln_fwd(norm, x, prec)
     w1 = prepared(ffn, "w_1", prec, (ffn.w_1.weight,))
     w2 = prepared(ffn, "w_2", prec, (ffn.w_2.weight,))
+    if ffn.act_name == "glu":      # w_2(F.glu(fc(w_1 x))): LinearGLUBlock (modules/glu.py:11-22), GLU fused in the epilogue
+        h1 = ops.linear(n, w1, ffn.w_1.bias, prec=prec, out_dtype=act_dtype(prec))
+        wg = prepared(ffn, "glu_fc", prec, (ffn.activation.fc.weight,))
+        h, z = ops.linear(h1, wg, ffn.activation.fc.bias, prec=prec, glu=True, out_dtype=act_dtype(prec), save_pre=True)
+        y = ops.linear(h, w2, ffn.w_2.bias, prec=prec, residual=x, alpha=scale, out_dtype=torch.float32)
+        return y, (x, n, z, h, h1)
     h, z = ops.linear(n, w1, ffn.w_1.bias, prec=prec, act=ffn.act_name, out_dtype=act_dtype(prec), save_pre=True)
     y = ops.linear(h, w2, ffn.w_2.bias, prec=prec, residual=x, alpha=scale, out_dtype=torch.float32)
     return y, (x, n, z, h)
@@ -136,12 +140,22 @@ def ffn_fwd(ffn, norm, x, scale, prec):
 def ffn_bwd(ffn, norm, saved, dy, dyo, scale, prec, G, bias_done=False, nxt=(None, 1.0)):
     """bias_done: the producer of dy already accumulated w_2.bias' gradient; nxt = (bias param, alpha) of the branch that
     consumes this function's dx."""
-    x, n, z, h = saved
+    x, n, z, h = saved[:4]
     ops.linear_wgrad(dyo, h, prec, G.buf(ffn.w_2.weight), alpha=scale)
     if not bias_done:
         ops.colsum_acc(dy, G.buf(ffn.w_2.bias), alpha=scale)
     dh = ops.linear(dyo, _wT(ffn, "w_2", prec, (ffn.w_2.weight,)), None, prec=prec, alpha=scale, out_dtype=act_dtype(prec))
-    if _fusable(z):
+    if ffn.act_name == "glu":
+        h1, fc = saved[4], ffn.activation.fc
+        if _fusable(z) and z.shape[-1] % 32 == 0:
+            dpre = ops.act_bwd_bias(dh, z, None, G.buf(fc.bias), glu=True)
+        else:
+            dpre = ops.glu_bwd(dh, z)
+            ops.colsum_acc(dpre, G.buf(fc.bias))
+        ops.linear_wgrad(dpre, h1, prec, G.buf(fc.weight))
+        dz = ops.linear(dpre, _wT(ffn, "glu_fc", prec, (fc.weight,)), None, prec=prec, out_dtype=act_dtype(prec))
+        ops.colsum_acc(dz, G.buf(ffn.w_1.bias))
+    elif _fusable(z):
         dz = ops.act_bwd_bias(dh, z, ffn.act_name, G.buf(ffn.w_1.bias))
     else:
         dz = ops.act_bwd(dh, z, ffn.act_name)
@@ -393,6 +407,44 @@ class _MaxPoolTimeFn(torch.autograd.Function):
 
 def maxpool_time(x, factor):
     return _MaxPoolTimeFn.apply(x, factor)
+
+
+class _PoolTimeFn(torch.autograd.Function):
+    """mean / drop / add time pooling (MeanPool / Drop / Add subsamplers) with the CUDA backward."""
+
+    @staticmethod
+    def forward(ctx, x, factor, mode):
+        ctx.T, ctx.factor, ctx.mode = x.shape[1], factor, mode
+        return ops.pool_time(x, factor, mode)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.pool_time_bwd(dy, ctx.T, ctx.factor, ctx.mode), None, None
+
+
+def subsample_train(sub, xs, xlens):
+    """Training forward of one intermediate subsampler (encoders/subsampling.py) -> (xs, xlens): the pooling variants are
+    one autograd node each; concat / conv1d are GEMMs with a fused ReLU over re-laid-out frames (data movement only)."""
+    from .encoders.subsampling import ConcatSubsampler, Conv1dSubsampler
+    from .modules._prep import get_precision
+    f = sub.factor
+    if f == 1:
+        return xs, xlens
+    if isinstance(sub, ConcatSubsampler):
+        B, T, D = xs.shape
+        x = xs[:, :(T // f) * f].reshape(B, T // f, f * D)
+        return linear_relu(sub, 'proj', sub.proj.weight, sub.proj.bias, x, get_precision(sub)), sub._lens(xlens)
+    if isinstance(sub, Conv1dSubsampler):
+        B, T, D = xs.shape
+        k, pad = sub.kernel_size, (sub.kernel_size - 1) // 2
+        To = (T + 2 * pad - (k - 1) - 1) // f + 1
+        xp = torch.nn.functional.pad(xs, (0, 0, pad, pad))
+        cols = xp.unfold(1, k, f)[:, :To].reshape(B, To, D * k)             # column c * k + j = nn.Conv1d weight order
+        return (linear_relu(sub, 'conv1d_ck', sub.conv1d.weight, sub.conv1d.bias, cols, get_precision(sub)),
+                sub._lens(xlens))
+    if sub.mode == "max":
+        return maxpool_time(xs, f), sub._lens(xlens)
+    return _PoolTimeFn.apply(xs, f, sub.mode), sub._lens(xlens)
 
 
 class _ScaleFn(torch.autograd.Function):

@@ -383,6 +383,25 @@ __global__ void __launch_bounds__(256) maxpool_time_bwd_kernel(const float* __re
     }
 }
 
+// Mean / drop / add time-pooling backward (kernel = stride = factor, ceil_mode; forward: pool_time_kernel in frontend.cu):
+// every input frame t belongs to exactly one window to = t / factor.  mode 1 mean: dy / (frames of the window inside the
+// input), 2 drop: dy to the window's first frame only, 3 add: dy to every frame.  dy fp32 [B,ceil(T/f),D], dx fp32 [B,T,D].
+__global__ void __launch_bounds__(256) pool_time_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int B, int T,
+                                                            int D, int factor, int mode) {
+    const int To = (T + factor - 1) / factor;
+    const int64_t n = (int64_t)B * T * D;
+    for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < n; e += (int64_t)gridDim.x * 256) {
+        const int c = (int)(e % D);
+        const int64_t r = e / D;
+        const int t = (int)(r % T), b = (int)(r / T);
+        const int to = t / factor;
+        float g = __ldg(dy + ((int64_t)b * To + to) * D + c);
+        if (mode == 1) g /= (float)(min(T, (to + 1) * factor) - to * factor);
+        else if (mode == 2) g = (t == to * factor) ? g : 0.f;
+        dx[e] = g;
+    }
+}
+
 // dz = (a > 0) ? dx : 0   (ReLU backward through the saved post-activation a)
 template <typename T>
 __global__ void __launch_bounds__(256) relu_mask_kernel(const T* __restrict__ dx, const T* __restrict__ a, T* __restrict__ dz, int64_t n) {
@@ -551,6 +570,13 @@ extern "C" nsp_status nsp_maxpool_time_bwd(const float* x, const float* dy, floa
     NSP_CHECK_ARG(x && dy && dx && B > 0 && T > 0 && D > 0 && factor >= 1, "maxpool_time_bwd: bad arguments");
     const int To = (T + factor - 1) / factor;
     maxpool_time_bwd_kernel<<<bw_grid((int64_t)B * To * D), 256, 0, (cudaStream_t)stream>>>(x, dy, dx, B, T, D, factor);
+    NSP_LAUNCH_OK();
+    return NSP_OK;
+}
+
+extern "C" nsp_status nsp_pool_time_bwd(const float* dy, float* dx, int B, int T, int D, int factor, int mode, void* stream) {
+    NSP_CHECK_ARG(dy && dx && B > 0 && T > 0 && D > 0 && factor >= 1 && mode >= 1 && mode <= 3, "pool_time_bwd: bad arguments");
+    pool_time_bwd_kernel<<<bw_grid((int64_t)B * T * D), 256, 0, (cudaStream_t)stream>>>(dy, dx, B, T, D, factor, mode);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }

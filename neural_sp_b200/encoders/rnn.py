@@ -7,8 +7,7 @@ library, which implements the packed-sequence semantics of ``Padding`` (:534-546
 reference's sort / pack / unsort round trip (:296-298, :375-377) is unnecessary.
 Supported: lstm / blstm (+ conv front-end), projections, sum of directions, the six subsamplers, sub-task outputs,
 bridge.  In train() + grad mode every LSTM layer is one autograd node (neural_sp_b200/autograd.py: forward keeps the gate
-activations, backward = persistent BPTT kernel + tcgen05 dgrad / wgrad GEMMs); subsamplers with a training path:
-max_pool, drop, concat.
+activations, backward = persistent BPTT kernel + tcgen05 dgrad / wgrad GEMMs); all six subsamplers have a training path.
 Streaming inference (``streaming=True``, :343-346): every layer's (h_n, c_n) is carried in ``self.hx_fwd`` across chunks by
 the kernel's initial / final state arguments; like the reference's un-packed ``rnn(xs, hx)`` call, a streamed chunk is
 processed over all of its frames.  Latency-controlled BLSTM (``chunk_size_current/right`` with a bidirectional type,
@@ -245,19 +244,7 @@ class RNNEncoder(EncoderBase):
         return xs_sub
 
     def _subsample_train(self, lth, xs, xlens):
-        sub = self.subsample[lth]
-        f = sub.factor
-        if f == 1:
-            return xs, xlens
-        if isinstance(sub, MaxPoolSubsampler):
-            return ag.maxpool_time(xs, f), sub._lens(xlens)
-        if isinstance(sub, DropSubsampler):
-            return xs[:, ::f].contiguous(), sub._lens(xlens)
-        if isinstance(sub, ConcatSubsampler):
-            B, T, D = xs.shape
-            x = xs[:, :(T // f) * f].reshape(B, T // f, f * D)
-            return ag.linear_relu(sub, 'proj', sub.proj.weight, sub.proj.bias, x, get_precision(sub)), sub._lens(xlens)
-        raise NotImplementedError("training: subsample_type %s has no CUDA backward yet" % type(sub).__name__)
+        return ag.subsample_train(self.subsample[lth], xs, xlens)
 
     def forward(self, xs, xlens, task, streaming=False, lookback=False, lookahead=False):
         if self.training and (self.dropout_in.p > 0 or (self.enc_type != 'conv' and self.dropout.p > 0)):

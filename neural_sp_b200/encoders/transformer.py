@@ -342,10 +342,7 @@ class TransformerEncoder(EncoderBase):
                     f = self.subsample_factors[lth]
                     if f > 1:
                         if train:
-                            sub = self.subsample_layers[lth]
-                            if not isinstance(sub, MaxPoolSubsampler):
-                                raise NotImplementedError("training: only subsample_type=max_pool has a CUDA backward")
-                            xs, xlens = ag.maxpool_time(xs, sub.factor), sub._lens(xlens)
+                            xs, xlens = ag.subsample_train(self.subsample_layers[lth], xs, xlens)
                         else:
                             xs, xlens = self.subsample_layers[lth](xs, xlens)
                         N_l, N_c, N_r = max(0, N_l // f), N_c // f, N_r // f

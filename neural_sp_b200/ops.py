@@ -664,6 +664,17 @@ def maxpool_time_bwd(x, dy, factor):
     return dx
 
 
+def pool_time_bwd(dy, T, factor, mode):
+    """Backward of pool_time for mode 'mean' / 'drop' / 'add' (nsp_pool_time_bwd): dy fp32 `[B,ceil(T/f),D]` -> dx `[B,T,D]`."""
+    _require_cuda(dy)
+    dy = dy.contiguous().float()
+    B, To, D = dy.shape
+    assert To == -(-T // factor) and mode in ("mean", "drop", "add")
+    dx = torch.empty(B, T, D, dtype=torch.float32, device=dy.device)
+    _run("nsp_pool_time_bwd", lib.nsp_pool_time_bwd, ptr(dy), ptr(dx), B, T, D, int(factor), POOL_MODE[mode], current_stream_ptr())
+    return dx
+
+
 def relu_mask(dx, a):
     """dz = a > 0 ? dx : 0 (nsp_relu_mask)."""
     _require_cuda(dx, a)

@@ -29,6 +29,23 @@ ZZ_CASES = {
     "transformer_add": dict(args=dict(enc_type='conv_transformer', pe_type='add', ffn_activation='gelu', n_layers=2,
                                       subsample="1_2", lookahead="0_0", last_proj_dim=40),
                             conv=dict(poolings="(2,2)_(2,2)"), B=2, T=70, xlens=[70, 51], kind='transformer'),
+    # GLU feed-forward activation (LinearGLUBlock) + 'drop' subsampling
+    "conformer_glu_drop": dict(args=dict(ffn_activation='glu', subsample_type='drop', n_layers=2, subsample="2_1",
+                                         lookahead="0_0", d_model=32, d_ff=64, n_heads=2),
+                               conv=dict(poolings="(2,2)_(2,2)"), B=2, T=61, xlens=[61, 50]),
+    # the remaining hierarchical subsamplers in the training path: concat, conv1d, add, mean_pool
+    "transformer_concat": dict(args=dict(enc_type='conv_transformer', pe_type='relative_xl', ffn_activation='relu', n_layers=2,
+                                         subsample="2_1", lookahead="0_0", subsample_type='concat', d_model=32, d_ff=64,
+                                         n_heads=2), conv=dict(poolings="(2,2)_(2,2)"), B=2, T=66, xlens=[66, 45],
+                               kind='transformer'),
+    "conformer_conv1d": dict(args=dict(subsample_type='conv1d', n_layers=2, subsample="2_1", lookahead="0_0", d_model=32,
+                                       d_ff=64, n_heads=2), conv=dict(poolings="(2,2)_(2,2)"), B=2, T=70, xlens=[70, 52]),
+    "conformer_add": dict(args=dict(subsample_type='add', n_layers=2, subsample="2_1", lookahead="0_0", d_model=32, d_ff=64,
+                                    n_heads=2), conv=dict(poolings="(2,2)_(2,2)"), B=2, T=70, xlens=[70, 52]),
+    # (lengths chosen so that the reference's own floor-formula lengths agree with the ceil-mode pooled tensor: it asserts
+    #  on its mask shape otherwise, relative_multihead_attention.py:166)
+    "conformer_mean": dict(args=dict(subsample_type='mean_pool', n_layers=2, subsample="2_1", lookahead="0_0", d_model=32,
+                                     d_ff=64, n_heads=2), conv=dict(poolings="(2,2)_(2,2)"), B=2, T=64, xlens=[64, 56]),
 }
 
 

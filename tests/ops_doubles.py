@@ -327,6 +327,17 @@ def maxpool_time_bwd(x, dy, factor):
     return xx.grad
 
 
+def pool_time_bwd(dy, T, factor, mode):
+    with torch.enable_grad():
+        xx = torch.zeros(dy.shape[0], T, dy.shape[2], requires_grad=True)
+        pool_time(xx, factor, mode).backward(dy.float())
+    return xx.grad
+
+
+def relu_mask(dx, a):
+    return torch.where(a > 0, dx, torch.zeros_like(dx))
+
+
 def frontend_forward(enc, xs, out_scale, prec):
     """Differentiable torch restatement of the CNN front-end + bridge (reference conv.py:167-195, 347-396); replaces
     neural_sp_b200.autograd.frontend_forward (one autograd node with hand-written CUDA backward, checked on the GPU)."""
@@ -347,7 +358,7 @@ def frontend_forward(enc, xs, out_scale, prec):
 TRAIN_DOUBLES = dict(DOUBLES, linear=_linear_train, linear_wgrad=linear_wgrad, colsum_acc=colsum_acc,
                      layernorm_bwd=layernorm_bwd, act_bwd=act_bwd, glu_bwd=glu_bwd, relpos_attention=_relpos_attention_train,
                      relpos_attention_bwd=relpos_attention_bwd, conformer_conv_bwd=conformer_conv_bwd,
-                     maxpool_time_bwd=maxpool_time_bwd)
+                     maxpool_time_bwd=maxpool_time_bwd, pool_time_bwd=pool_time_bwd, relu_mask=relu_mask)
 
 
 def install_training(monkeypatch):

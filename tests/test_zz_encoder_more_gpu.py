@@ -66,3 +66,26 @@ def test_encoder_param_grads_match_reference(name, precision, tol):
         if not e <= tol:
             bad.append((k, e))
     assert not bad, (name, precision, bad[:10], len(bad))
+
+
+@pytest.mark.parametrize("mode", ["mean", "drop", "add"])
+@pytest.mark.parametrize("B,T,D,f", [(2, 17, 32, 2), (3, 40, 48, 3), (1, 5, 256, 2)])
+def test_pool_time_bwd_kernel(mode, B, T, D, f):
+    """nsp_pool_time_bwd against torch autograd through the same pooling."""
+    from neural_sp_b200 import ops
+    torch.manual_seed(T)
+    x = torch.randn(B, T, D, device="cuda", requires_grad=True)
+    xt = x.transpose(1, 2)
+    if mode == "mean":
+        ref = torch.nn.functional.avg_pool1d(xt, f, f, ceil_mode=True).transpose(1, 2)
+    elif mode == "drop":
+        ref = x[:, ::f]
+    else:
+        Tp = -(-T // f) * f
+        ref = torch.nn.functional.pad(xt, (0, Tp - T)).reshape(B, D, Tp // f, f).sum(-1).transpose(1, 2)
+    out = ops.pool_time(x.detach(), f, mode)
+    assert torch.allclose(out, ref.detach(), atol=1e-6)
+    dy = torch.randn_like(out)
+    ref.backward(dy)
+    dx = ops.pool_time_bwd(dy, T, f, mode)
+    assert torch.allclose(dx, x.grad, atol=1e-6)
