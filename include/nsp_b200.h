@@ -313,6 +313,18 @@ nsp_status nsp_maxpool_time_bwd(const float* x, const float* dy, float* dx, int 
 /* Backward of nsp_pool_time_fwd for mode 1 mean (MeanPoolSubsampler subsampling.py:212-246), 2 drop (DropSubsampler
  * :97-126), 3 add (AddSubsampler :129-172): dy fp32 [B,ceil(T/f),D] -> dx fp32 [B,T,D]. */
 nsp_status nsp_pool_time_bwd(const float* dy, float* dx, int B, int T, int D, int factor, int mode, void* stream);
+/* Dropout of the training path (nn.Dropout in the reference: conformer_block.py:133-180, transformer_block.py:128-139,
+ * positionwise_feed_forward.py:83, positional_embedding.py:139, ctc.py:87).  Masks are never stored: element i of call site
+ * `stream_id` is kept iff philox4x32_10(counter = (i/4, stream_id, offset), key = seed)[i%4] >= p * 2^32, with
+ * rng_state = {seed, offset} (two uint64 in device memory), so the backward regenerates the forward's mask.
+ *   nsp_dropout:     y = keep ? x * scale / (1-p) : 0            x, y fp32 or bf16; in place allowed for equal dtypes
+ *   nsp_dropout_add: out = res + (keep ? t * alpha / (1-p) : 0)  t fp32 or bf16; res, out fp32 (out may alias res)
+ *   nsp_rng_advance: offset += 1 (one call per training step; needed only so that CUDA-graph replays draw new masks) */
+nsp_status nsp_dropout(int in_bf16, int out_bf16, const void* x, void* y, int64_t n, float p, float scale,
+                       const uint64_t* rng_state, uint32_t stream_id, void* stream);
+nsp_status nsp_dropout_add(int t_bf16, const void* t, const float* res, float* out, int64_t n, float p, float alpha,
+                           const uint64_t* rng_state, uint32_t stream_id, void* stream);
+nsp_status nsp_rng_advance(uint64_t* rng_state, void* stream);
 /* ReLU backward through the saved post-activation: dz = a > 0 ? dx : 0. */
 nsp_status nsp_relu_mask(int is_bf16, const void* dx, const void* a, void* dz, int64_t n, void* stream);
 /* ReLU + MaxPool2d(ceil_mode) backward on channels-last [B,T,F,C] (encoders/conv.py:362-394): a = saved post-ReLU

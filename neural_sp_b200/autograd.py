@@ -13,6 +13,7 @@ allocation and the handful of `torch.zeros` gradient buffers.
 import torch
 
 from . import ops
+from . import random as nrandom
 from .modules._prep import prepared, cached, act_dtype
 
 
@@ -122,31 +123,59 @@ def _fusable(t):
     return t.dtype == torch.bfloat16 and t.shape[-1] % 16 == 0
 
 
-def ffn_fwd(ffn, norm, x, scale, prec):
+def _drop_out(t_fn, x, p_res, alpha):
+    """Residual-branch output  y = x + alpha * dropout(t)  (conformer_block.py:133-134 etc.): t_fn(fused) produces either the
+    GEMM with the residual add fused in its epilogue (p_res == 0) or the bare branch output for the dropout-add kernel.
+    Returns (y, stream id of the mask or 0)."""
+    if p_res <= 0:
+        return t_fn(True), 0
+    sid = nrandom.next_stream()
+    return ops.dropout_add(t_fn(False), x, p_res, alpha, sid), sid
+
+
+def _drop_grad(dy, dyo, p_res, sid, prec):
+    """Gradient entering a residual branch whose output was dropped: regenerate the mask on dy.
+    -> (gradient for the bias column sums, gradient in the GEMM operand dtype, bias-fusion still valid?)"""
+    if p_res <= 0:
+        return dy, dyo, True
+    dt = ops.dropout(dy, p_res, sid, out_dtype=act_dtype(prec))
+    return dt, dt, False
+
+
+def ffn_fwd(ffn, norm, x, scale, prec, p_res=0.0):
     n = _ln_fwd(norm, x, prec)
     w1 = prepared(ffn, "w_1", prec, (ffn.w_1.weight,))
     w2 = prepared(ffn, "w_2", prec, (ffn.w_2.weight,))
+    h1 = None
     if ffn.act_name == "glu":      # w_2(F.glu(fc(w_1 x))): LinearGLUBlock (modules/glu.py:11-22), GLU fused in the epilogue
         h1 = ops.linear(n, w1, ffn.w_1.bias, prec=prec, out_dtype=act_dtype(prec))
         wg = prepared(ffn, "glu_fc", prec, (ffn.activation.fc.weight,))
         h, z = ops.linear(h1, wg, ffn.activation.fc.bias, prec=prec, glu=True, out_dtype=act_dtype(prec), save_pre=True)
-        y = ops.linear(h, w2, ffn.w_2.bias, prec=prec, residual=x, alpha=scale, out_dtype=torch.float32)
-        return y, (x, n, z, h, h1)
-    h, z = ops.linear(n, w1, ffn.w_1.bias, prec=prec, act=ffn.act_name, out_dtype=act_dtype(prec), save_pre=True)
-    y = ops.linear(h, w2, ffn.w_2.bias, prec=prec, residual=x, alpha=scale, out_dtype=torch.float32)
-    return y, (x, n, z, h)
+    else:
+        h, z = ops.linear(n, w1, ffn.w_1.bias, prec=prec, act=ffn.act_name, out_dtype=act_dtype(prec), save_pre=True)
+    p_h, sid_h = ffn.dropout.p, 0
+    if p_h > 0:                    # w_2(dropout(act(w_1 x)))  (positionwise_feed_forward.py:83)
+        sid_h = nrandom.next_stream()
+        h = ops.dropout(h, p_h, sid_h, inplace=True)
+    y, sid_r = _drop_out(lambda fused: ops.linear(h, w2, ffn.w_2.bias, prec=prec, residual=x if fused else None,
+                                                  alpha=scale if fused else 1.0,
+                                                  out_dtype=torch.float32 if fused else act_dtype(prec)), x, p_res, scale)
+    return y, (x, n, z, h, h1, (p_h, sid_h, p_res, sid_r))
 
 
 def ffn_bwd(ffn, norm, saved, dy, dyo, scale, prec, G, bias_done=False, nxt=(None, 1.0)):
     """bias_done: the producer of dy already accumulated w_2.bias' gradient; nxt = (bias param, alpha) of the branch that
     consumes this function's dx."""
-    x, n, z, h = saved[:4]
+    x, n, z, h, h1, (p_h, sid_h, p_res, sid_r) = saved
+    dyb, dyo, fused_ok = _drop_grad(dy, dyo, p_res, sid_r, prec)
     ops.linear_wgrad(dyo, h, prec, G.buf(ffn.w_2.weight), alpha=scale)
-    if not bias_done:
-        ops.colsum_acc(dy, G.buf(ffn.w_2.bias), alpha=scale)
+    if not (bias_done and fused_ok):
+        ops.colsum_acc(dyb, G.buf(ffn.w_2.bias), alpha=scale)
     dh = ops.linear(dyo, _wT(ffn, "w_2", prec, (ffn.w_2.weight,)), None, prec=prec, alpha=scale, out_dtype=act_dtype(prec))
+    if p_h > 0:
+        dh = ops.dropout(dh, p_h, sid_h, inplace=True)
     if ffn.act_name == "glu":
-        h1, fc = saved[4], ffn.activation.fc
+        fc = ffn.activation.fc
         if _fusable(z) and z.shape[-1] % 32 == 0:
             dpre = ops.act_bwd_bias(dh, z, None, G.buf(fc.bias), glu=True)
         else:
@@ -173,7 +202,7 @@ def _qkv_weight(attn, prec, transposed=False):
     return prepared(attn, "qkv", prec, params, build=cat)
 
 
-def attn_fwd(attn, norm, x, pos, klens, u_bias, v_bias, mask_kw, prec, rel):
+def attn_fwd(attn, norm, x, pos, klens, u_bias, v_bias, mask_kw, prec, rel, p_res=0.0):
     n = _ln_fwd(norm, x, prec)
     D = attn.n_heads * attn.d_k
     bias = None
@@ -191,19 +220,21 @@ def attn_fwd(attn, norm, x, pos, klens, u_bias, v_bias, mask_kw, prec, rel):
     cv, stats = ops.relpos_attention(qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:], klens, attn.n_heads, r=r,
                                      u_bias=u_bias if rel else None, v_bias=v_bias if rel else None, clamp_len=clamp,
                                      want_stats=True, **mask_kw)
-    y = ops.linear(cv, prepared(attn, "w_out", prec, (attn.w_out.weight,)), attn.w_out.bias, prec=prec, residual=x,
-                   out_dtype=torch.float32)
-    return y, (x, n, qkv, r, cv, nrows, stats)
+    wo = prepared(attn, "w_out", prec, (attn.w_out.weight,))
+    y, sid_r = _drop_out(lambda fused: ops.linear(cv, wo, attn.w_out.bias, prec=prec, residual=x if fused else None,
+                                                  out_dtype=torch.float32 if fused else act_dtype(prec)), x, p_res, 1.0)
+    return y, (x, n, qkv, r, cv, nrows, stats, (p_res, sid_r))
 
 
 def attn_bwd(attn, norm, saved, dy, dyo, pos, klens, u_bias, v_bias, mask_kw, prec, rel, G, enc_bias_params,
              bias_done=False, nxt=(None, 1.0)):
-    x, n, qkv, r, cv, nrows, stats = saved
+    x, n, qkv, r, cv, nrows, stats, (p_res, sid_r) = saved
     D = attn.n_heads * attn.d_k
     d_in = x.shape[-1]
+    dyb, dyo, fused_ok = _drop_grad(dy, dyo, p_res, sid_r, prec)
     ops.linear_wgrad(dyo, cv, prec, G.buf(attn.w_out.weight))
-    if attn.w_out.bias is not None and not bias_done:
-        ops.colsum_acc(dy, G.buf(attn.w_out.bias))
+    if attn.w_out.bias is not None and not (bias_done and fused_ok):
+        ops.colsum_acc(dyb, G.buf(attn.w_out.bias))
     dcv = ops.linear(dyo, _wT(attn, "w_out", prec, (attn.w_out.weight,)), None, prec=prec, out_dtype=act_dtype(prec))
     dr = torch.zeros(nrows, D, dtype=torch.float32, device=x.device) if rel else None
     du = dvb = None
@@ -236,7 +267,7 @@ def attn_bwd(attn, norm, saved, dy, dyo, pos, klens, u_bias, v_bias, mask_kw, pr
     return _ln_bwd(norm, dn, x, dy, G, prec, nxt[0], nxt[1])
 
 
-def convmod_fwd(conv, norm, x, prec):
+def convmod_fwd(conv, norm, x, prec, p_res=0.0):
     if conv.normalization != 'layer_norm':
         raise NotImplementedError("training the Conformer conv module needs conformer_normalization=layer_norm on the B200 "
                                   "path (the LibriSpeech recipes' setting)")
@@ -247,16 +278,18 @@ def convmod_fwd(conv, norm, x, prec):
     c = ops.conformer_conv(g, taps, conv.depthwise_conv.bias, 'layer_norm', conv.norm.weight, conv.norm.bias, conv.norm.eps,
                            None, None, causal=conv.causal)
     w2 = prepared(conv, "pw2", prec, (conv.pointwise_conv2.weight,), build=lambda w: w.squeeze(-1))
-    y = ops.linear(c, w2, conv.pointwise_conv2.bias, prec=prec, residual=x, out_dtype=torch.float32)
-    return y, (x, n, pre, g, c, taps)
+    y, sid_r = _drop_out(lambda fused: ops.linear(c, w2, conv.pointwise_conv2.bias, prec=prec, residual=x if fused else None,
+                                                  out_dtype=torch.float32 if fused else act_dtype(prec)), x, p_res, 1.0)
+    return y, (x, n, pre, g, c, taps, (p_res, sid_r))
 
 
 def convmod_bwd(conv, norm, saved, dy, dyo, prec, G, bias_done=False, nxt=(None, 1.0)):
-    x, n, pre, g, c, taps = saved
+    x, n, pre, g, c, taps, (p_res, sid_r) = saved
     d = x.shape[-1]
+    dyb, dyo, fused_ok = _drop_grad(dy, dyo, p_res, sid_r, prec)
     ops.linear_wgrad(dyo, c, prec, _as2d(G.buf(conv.pointwise_conv2.weight)))
-    if not bias_done:
-        ops.colsum_acc(dy, G.buf(conv.pointwise_conv2.bias))
+    if not (bias_done and fused_ok):
+        ops.colsum_acc(dyb, G.buf(conv.pointwise_conv2.bias))
     dc = ops.linear(dyo, _wT(conv, "pw2", prec, (conv.pointwise_conv2.weight,)), None, prec=prec, out_dtype=act_dtype(prec))
     dtaps = torch.zeros_like(taps)
     dg = ops.conformer_conv_bwd(g, taps, conv.depthwise_conv.bias, conv.norm.weight, conv.norm.bias, conv.norm.eps, dc,
@@ -296,24 +329,25 @@ class _BlockFn(torch.autograd.Function):
         x = xs
         if in_scale != 1.0:
             x = ops.scale_(xs.clone(), in_scale)
+        pd = saved["p"] = float(block.dropout.p)          # dropout on every residual-branch output (block is in train mode)
         if getattr(block, "v2", False):           # conformer_block_v2.py: FFN -> conv -> plain MHA -> FFN -> LN
-            x, saved["ffm"] = ffn_fwd(block.feed_forward_macaron, block.norm1, x, block.fc_factor, prec)
-            x, saved["conv"] = convmod_fwd(block.conv, block.norm2, x, prec)
-            x, saved["att"] = attn_fwd(block.self_attn, block.norm3, x, None, klens, None, None, mask_kw, prec, False)
-            x, saved["ff"] = ffn_fwd(block.feed_forward, block.norm4, x, block.fc_factor, prec)
+            x, saved["ffm"] = ffn_fwd(block.feed_forward_macaron, block.norm1, x, block.fc_factor, prec, pd)
+            x, saved["conv"] = convmod_fwd(block.conv, block.norm2, x, prec, pd)
+            x, saved["att"] = attn_fwd(block.self_attn, block.norm3, x, None, klens, None, None, mask_kw, prec, False, pd)
+            x, saved["ff"] = ffn_fwd(block.feed_forward, block.norm4, x, block.fc_factor, prec, pd)
             saved["x5"] = x
             x = ops.layernorm(x, block.norm5.weight, block.norm5.bias, block.norm5.eps)
         elif hasattr(block, "feed_forward_macaron"):
-            x, saved["ffm"] = ffn_fwd(block.feed_forward_macaron, block.norm1, x, block.fc_factor, prec)
-            x, saved["att"] = attn_fwd(block.self_attn, block.norm2, x, pos, klens, u_bias, v_bias, mask_kw, prec, True)
-            x, saved["conv"] = convmod_fwd(block.conv, block.norm3, x, prec)
-            x, saved["ff"] = ffn_fwd(block.feed_forward, block.norm4, x, block.fc_factor, prec)
+            x, saved["ffm"] = ffn_fwd(block.feed_forward_macaron, block.norm1, x, block.fc_factor, prec, pd)
+            x, saved["att"] = attn_fwd(block.self_attn, block.norm2, x, pos, klens, u_bias, v_bias, mask_kw, prec, True, pd)
+            x, saved["conv"] = convmod_fwd(block.conv, block.norm3, x, prec, pd)
+            x, saved["ff"] = ffn_fwd(block.feed_forward, block.norm4, x, block.fc_factor, prec, pd)
             saved["x5"] = x
             x = ops.layernorm(x, block.norm5.weight, block.norm5.bias, block.norm5.eps)
         else:
             x, saved["att"] = attn_fwd(block.self_attn, block.norm1, x, pos, klens, u_bias, v_bias, mask_kw, prec,
-                                       block.rel_attn)
-            x, saved["ff"] = ffn_fwd(block.feed_forward, block.norm2, x, 1.0, prec)
+                                       block.rel_attn, pd)
+            x, saved["ff"] = ffn_fwd(block.feed_forward, block.norm2, x, 1.0, prec, pd)
         ctx.block, ctx.saved, ctx.klens, ctx.pos, ctx.rel_bias = block, saved, klens, pos, rel_bias
         ctx.mask_kw, ctx.prec, ctx.in_scale, ctx.params = mask_kw, prec, in_scale, params
         return x
@@ -324,31 +358,33 @@ class _BlockFn(torch.autograd.Function):
         u_bias, v_bias = ctx.rel_bias
         G = _Grads(ctx.params)
         dy = dy.contiguous().float()
+        # every LayerNorm backward also accumulates the bias gradient of the branch that consumes its dx -- valid only
+        # without dropout on that branch's output (with dropout the branch sums its own masked gradient)
+        nx = (lambda b, a: (None, 1.0)) if S["p"] > 0 else (lambda b, a: (b, a))
         if getattr(block, "v2", False):
             fc = block.fc_factor
-            dx, dxo = _ln_bwd(block.norm5, dy, S["x5"], None, G, prec, block.feed_forward.w_2.bias, fc)
+            dx, dxo = _ln_bwd(block.norm5, dy, S["x5"], None, G, prec, *nx(block.feed_forward.w_2.bias, fc))
             dx, dxo = ffn_bwd(block.feed_forward, block.norm4, S["ff"], dx, dxo, fc, prec, G, bias_done=True,
-                              nxt=(block.self_attn.w_out.bias, 1.0))
+                              nxt=nx(block.self_attn.w_out.bias, 1.0))
             dx, dxo = attn_bwd(block.self_attn, block.norm3, S["att"], dx, dxo, None, ctx.klens, None, None, ctx.mask_kw,
-                               prec, False, G, (None, None), bias_done=True, nxt=(block.conv.pointwise_conv2.bias, 1.0))
+                               prec, False, G, (None, None), bias_done=True, nxt=nx(block.conv.pointwise_conv2.bias, 1.0))
             dx, dxo = convmod_bwd(block.conv, block.norm2, S["conv"], dx, dxo, prec, G, bias_done=True,
-                                  nxt=(block.feed_forward_macaron.w_2.bias, fc))
+                                  nxt=nx(block.feed_forward_macaron.w_2.bias, fc))
             dx, dxo = ffn_bwd(block.feed_forward_macaron, block.norm1, S["ffm"], dx, dxo, fc, prec, G, bias_done=True)
         elif hasattr(block, "feed_forward_macaron"):
-            # every LayerNorm backward also accumulates the bias gradient of the branch that consumes its dx
             fc = block.fc_factor
-            dx, dxo = _ln_bwd(block.norm5, dy, S["x5"], None, G, prec, block.feed_forward.w_2.bias, fc)
+            dx, dxo = _ln_bwd(block.norm5, dy, S["x5"], None, G, prec, *nx(block.feed_forward.w_2.bias, fc))
             dx, dxo = ffn_bwd(block.feed_forward, block.norm4, S["ff"], dx, dxo, fc, prec, G, bias_done=True,
-                              nxt=(block.conv.pointwise_conv2.bias, 1.0))
+                              nxt=nx(block.conv.pointwise_conv2.bias, 1.0))
             dx, dxo = convmod_bwd(block.conv, block.norm3, S["conv"], dx, dxo, prec, G, bias_done=True,
-                                  nxt=(block.self_attn.w_out.bias, 1.0))
+                                  nxt=nx(block.self_attn.w_out.bias, 1.0))
             dx, dxo = attn_bwd(block.self_attn, block.norm2, S["att"], dx, dxo, ctx.pos, ctx.klens, u_bias, v_bias,
                                ctx.mask_kw, prec, True, G, ctx.rel_bias, bias_done=True,
-                               nxt=(block.feed_forward_macaron.w_2.bias, fc))
+                               nxt=nx(block.feed_forward_macaron.w_2.bias, fc))
             dx, dxo = ffn_bwd(block.feed_forward_macaron, block.norm1, S["ffm"], dx, dxo, fc, prec, G, bias_done=True)
         else:
             dx, dxo = ffn_bwd(block.feed_forward, block.norm2, S["ff"], dy, _gop(dy, prec), 1.0, prec, G,
-                              nxt=(block.self_attn.w_out.bias, 1.0))
+                              nxt=nx(block.self_attn.w_out.bias, 1.0))
             dx, dxo = attn_bwd(block.self_attn, block.norm1, S["att"], dx, dxo, ctx.pos, ctx.klens, u_bias, v_bias,
                                ctx.mask_kw, prec, block.rel_attn, G, ctx.rel_bias, bias_done=True)
         if ctx.in_scale != 1.0:
@@ -460,6 +496,24 @@ class _ScaleFn(torch.autograd.Function):
 
 def scale(x, a):
     return x if a == 1.0 else _ScaleFn.apply(x, float(a))
+
+
+class _DropoutFn(torch.autograd.Function):
+    """nn.Dropout with the library's kernel: the backward regenerates the mask from the call's stream id."""
+
+    @staticmethod
+    def forward(ctx, x, p):
+        ctx.p, ctx.sid = p, nrandom.next_stream()
+        return ops.dropout(x.detach(), p, ctx.sid)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.dropout(dy.contiguous(), ctx.p, ctx.sid), None
+
+
+def dropout(x, p):
+    """Training-mode dropout of an fp32 / bf16 CUDA tensor (identity for p == 0)."""
+    return x if p <= 0 else _DropoutFn.apply(x, float(p))
 
 
 class _AddPosEncFn(torch.autograd.Function):

@@ -16,6 +16,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from ..modules.dropout import Dropout
 from ..modules.linear import Linear
 
 
@@ -83,7 +84,7 @@ class CTC(nn.Module):
             for i in range(len(_fc_list)):
                 input_dim = enc_n_units if i == 0 else _fc_list[i - 1]
                 fc_layers['fc' + str(i)] = Linear(input_dim, _fc_list[i])
-                fc_layers['dropout' + str(i)] = nn.Dropout(p=dropout)
+                fc_layers['dropout' + str(i)] = Dropout(p=dropout)
             fc_layers['fc' + str(len(_fc_list))] = Linear(_fc_list[-1], vocab)
             self.output = nn.Sequential(fc_layers)
         else:

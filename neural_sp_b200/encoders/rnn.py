@@ -230,7 +230,7 @@ class RNNEncoder(EncoderBase):
             xs_sub = xs.clone()
             if self.task_specific_layer:
                 lin = getattr(self, 'layer_' + module)
-                xs_sub = ag.linear_relu(self, 'layer_' + module, lin.weight, lin.bias, xs, prec)
+                xs_sub = ag.dropout(ag.linear_relu(self, 'layer_' + module, lin.weight, lin.bias, xs, prec), self.dropout.p)
             bridge = getattr(self, 'bridge_' + module)
             return xs_sub if bridge is None else ag.linear(self, 'bridge_' + module, bridge, xs_sub, prec)
         if self.task_specific_layer:
@@ -247,8 +247,9 @@ class RNNEncoder(EncoderBase):
         return ag.subsample_train(self.subsample[lth], xs, xlens)
 
     def forward(self, xs, xlens, task, streaming=False, lookback=False, lookahead=False):
-        if self.training and (self.dropout_in.p > 0 or (self.enc_type != 'conv' and self.dropout.p > 0)):
-            raise NotImplementedError("dropout > 0 in training mode is not on the B200 path yet")
+        if self.training and not ag.training_enabled(self) and (
+                self.dropout_in.p > 0 or (self.enc_type != 'conv' and self.dropout.p > 0)):
+            raise NotImplementedError("dropout > 0 in train() mode needs the autograd training path (grad enabled)")
         eouts = {'ys': {'xs': None, 'xlens': None}, 'ys_sub1': {'xs': None, 'xlens': None},
                  'ys_sub2': {'xs': None, 'xlens': None}}
         xlens = torch.IntTensor([int(v) for v in xlens])
@@ -261,6 +262,8 @@ class RNNEncoder(EncoderBase):
         with (torch.enable_grad() if train else torch.no_grad()):
             bs = xs.size(0)
             N_c, N_r = self.N_c, self.N_r
+            if train:                                                     # dropout_in (:301)
+                xs = ag.dropout(xs.float().contiguous(), self.dropout_in.p)
             if self.lc_bidir and not self.cnn_lookahead:                  # CNN applied chunk by chunk (:308-312)
                 xs = chunkwise(xs, 0, N_c, 0).contiguous().view(bs, -1, xs.size(2))[:, :int(xlens.max())]
             if self.conv is not None:
@@ -292,6 +295,8 @@ class RNNEncoder(EncoderBase):
                                                             want_state=True)
                 else:
                     xs = self._lstm_layer(lth, xs, lens_to_device(xlens, xs.device), train)
+                    if train:                                             # dropout after every layer (:347)
+                        xs = ag.dropout(xs, self.dropout.p)
                 if lth == self.n_layers_sub1 - 1:
                     xs_sub1, xlens_sub1 = self._sub_out(xs, 'sub1', train), xlens.clone()
                     if task == 'ys_sub1':

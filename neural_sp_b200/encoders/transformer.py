@@ -227,8 +227,9 @@ class TransformerEncoder(EncoderBase):
 
     def _train_layer(self, lth, layer, xs, klens, pos, mask_kw, prec):
         """One block through its autograd node (training): LayerDrop as in conformer_block.py:122-126."""
-        if layer.dropout.p > 0 or layer.self_attn.dropout_attn.p > 0:
-            raise NotImplementedError("dropout > 0 in training mode is not on the B200 path yet")
+        if layer.self_attn.dropout_attn.p > 0:
+            raise NotImplementedError("dropout on the attention weights (dropout_att > 0) is not on the B200 path: the "
+                                      "flash-style kernels never materialise them (the LibriSpeech recipes use 0)")
         in_scale = 1.0
         if layer.dropout_layer > 0:
             if random.random() < layer.dropout_layer:
@@ -295,7 +296,7 @@ class TransformerEncoder(EncoderBase):
             dev = xs.device
             if not rel:                                               # absolute positions: xs * sqrt(d) [+ pe] (:497-498)
                 if train:
-                    xs = ag.add_pos_enc(self.pos_enc, xs.contiguous(), self.offset)
+                    xs = ag.dropout(ag.add_pos_enc(self.pos_enc, xs.contiguous(), self.offset), self.pos_enc.dropout.p)
                 else:
                     xs = self.pos_enc(xs.contiguous(), scale=True, offset=self.offset)
 
@@ -308,9 +309,18 @@ class TransformerEncoder(EncoderBase):
                     return lens_to_device(torch.IntTensor([xs.size(1)] * xs.size(0)), dev)
                 return lens_to_device(xlens + n_cache if n_cache else xlens, dev)
 
+            def pos_table(rows):
+                """Sinusoid rows 0..rows-1; training: dropped like the reference's `self.dropout(pos_emb)`
+                (positional_embedding.py:139) -- a constant, so no gradient flows into it."""
+                tab = self.pos_emb.table(rows)
+                if train and self.pos_emb.dropout.p > 0:
+                    from .. import random as nrandom
+                    tab = ops.dropout(tab.contiguous(), self.pos_emb.dropout.p, nrandom.next_stream())
+                return tab
+
             n_cache = cached_frames(0)
             klens = key_lens(n_cache)
-            pos = self.pos_emb.table(xs.size(1) + n_cache) if rel else None
+            pos = pos_table(xs.size(1) + n_cache) if rel else None
             new_cache = [None] * self.n_layers
 
             def mask_kw(lth):
@@ -350,7 +360,7 @@ class TransformerEncoder(EncoderBase):
                         n_cache = cached_frames(lth + 1)
                         klens = key_lens(n_cache)
                         if rel:
-                            pos = self.pos_emb.table(xs.size(1) + n_cache)
+                            pos = pos_table(xs.size(1) + n_cache)
             if st == 'reshape':                                       # keep the centre of every window (:546-550)
                 xs = xs[:, N_l:N_l + N_c].contiguous().view(bs, -1, xs.size(2))[:, :int(xlens.max())].contiguous()
             xs = self._norm(self.norm_out, xs, train)

@@ -56,9 +56,7 @@ class PositionalEncoding(nn.Module):
 
     def forward(self, xs, scale=True, offset=0):
         """xs fp32 `[B, T, d]` contiguous, updated in place."""
-        if self.training and self.dropout.p > 0:
-            raise NotImplementedError("dropout > 0 in training mode is not on the B200 path yet")
-        a = self.scale if scale else 1.0
+        a = self.scale if scale else 1.0           # (the encoder applies self.dropout in its training path)
         if self.pe_type == 'none':
             return ops.scale_(xs, a) if a != 1.0 else xs
         T = xs.size(1)

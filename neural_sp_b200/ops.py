@@ -675,6 +675,41 @@ def pool_time_bwd(dy, T, factor, mode):
     return dx
 
 
+# ---- dropout (mask regenerated from (seed, offset, stream, index); nothing is stored) ----
+def dropout(x, p, stream_id, scale=1.0, out_dtype=None, inplace=False):
+    """y = keep ? x * scale / (1 - p) : 0 (nsp_dropout).  x fp32 / bf16 contiguous; the same (p, stream_id) applied to a
+    gradient of the same shape reproduces the mask (backward)."""
+    from . import random as nrandom
+    _require_cuda(x)
+    x = x if x.is_contiguous() else x.contiguous()
+    out_dtype = out_dtype or x.dtype
+    assert x.dtype in (torch.float32, torch.bfloat16) and out_dtype in (torch.float32, torch.bfloat16)
+    y = x if (inplace and out_dtype == x.dtype) else torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    _run("nsp_dropout", lib.nsp_dropout, int(x.dtype == torch.bfloat16), int(out_dtype == torch.bfloat16), ptr(x), ptr(y),
+         x.numel(), float(p), float(scale), ptr(nrandom.state(x.device)), int(stream_id), current_stream_ptr(),
+         nbytes=float(x.numel() * (x.element_size() + y.element_size())))
+    return y
+
+
+def dropout_add(t, res, p, alpha, stream_id, out=None):
+    """out = res + alpha * dropout(t) (nsp_dropout_add): residual-branch output; res / out fp32, t fp32 or bf16."""
+    from . import random as nrandom
+    _require_cuda(t, res)
+    t = t if t.is_contiguous() else t.contiguous()
+    assert res.dtype == torch.float32 and res.is_contiguous() and res.numel() == t.numel()
+    out = torch.empty_like(res) if out is None else out
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == t.numel()
+    _run("nsp_dropout_add", lib.nsp_dropout_add, int(t.dtype == torch.bfloat16), ptr(t), ptr(res), ptr(out), t.numel(),
+         float(p), float(alpha), ptr(nrandom.state(t.device)), int(stream_id), current_stream_ptr(),
+         nbytes=float(t.numel() * (t.element_size() + 8)))
+    return out
+
+
+def rng_advance(state):
+    _require_cuda(state)
+    _run("nsp_rng_advance", lib.nsp_rng_advance, ptr(state), current_stream_ptr())
+
+
 def relu_mask(dx, a):
     """dz = a > 0 ? dx : 0 (nsp_relu_mask)."""
     _require_cuda(dx, a)

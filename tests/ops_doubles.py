@@ -338,6 +338,58 @@ def relu_mask(dx, a):
     return torch.where(a > 0, dx, torch.zeros_like(dx))
 
 
+def philox_keep(n, p, seed, offset, stream_id):
+    """numpy restatement of csrc/dropout.cu: keep[i] = philox4x32_10((i/4, (i/4 >> 32) ^ off_hi, stream, off_lo), seed)[i%4] >= p*2^32."""
+    import numpy as np
+    ngrp = (n + 3) // 4
+    grp = np.arange(ngrp, dtype=np.uint64)
+    M0, M1, W0, W1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), 0x9E3779B9, 0xBB67AE85
+    mask32 = np.uint64(0xFFFFFFFF)
+    c0 = grp & mask32
+    c1 = (grp >> np.uint64(32)) ^ np.uint64((offset >> 32) & 0xFFFFFFFF)
+    c2 = np.full(ngrp, stream_id & 0xFFFFFFFF, np.uint64)
+    c3 = np.full(ngrp, offset & 0xFFFFFFFF, np.uint64)
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask32, p1 >> np.uint64(32), p1 & mask32
+        c0, c1, c2, c3 = hi1 ^ c1 ^ np.uint64(k0), lo1, hi0 ^ c3 ^ np.uint64(k1), lo0
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    r = np.stack([c0, c1, c2, c3], axis=1).reshape(-1)[:n]
+    t = p * 4294967296.0
+    thresh = 0xFFFFFFFF if t >= 4294967295.0 else int(t)
+    return torch.from_numpy(r >= np.uint64(thresh))
+
+
+def _rng_state(device):
+    from neural_sp_b200 import random as nrandom
+    st = nrandom.state(device)
+    return int(st[0]), int(st[1])
+
+
+def dropout(x, p, stream_id, scale=1.0, out_dtype=None, inplace=False):
+    seed, off = _rng_state(x.device)
+    keep = philox_keep(x.numel(), float(torch.tensor(p, dtype=torch.float32)), seed, off, stream_id).reshape(x.shape)
+    s = torch.tensor(scale, dtype=torch.float32) / (1 - torch.tensor(p, dtype=torch.float32))
+    y = torch.where(keep, x.float() * s, torch.zeros((), dtype=torch.float32)).to(out_dtype or x.dtype)
+    if inplace and y.dtype == x.dtype:
+        x.copy_(y)
+        return x
+    return y
+
+
+def dropout_add(t, res, p, alpha, stream_id, out=None):
+    y = res + dropout(t.float(), p, stream_id, scale=alpha).reshape(res.shape)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def rng_advance(state):
+    state[1] += 1
+
+
 def frontend_forward(enc, xs, out_scale, prec):
     """Differentiable torch restatement of the CNN front-end + bridge (reference conv.py:167-195, 347-396); replaces
     neural_sp_b200.autograd.frontend_forward (one autograd node with hand-written CUDA backward, checked on the GPU)."""
@@ -358,7 +410,8 @@ def frontend_forward(enc, xs, out_scale, prec):
 TRAIN_DOUBLES = dict(DOUBLES, linear=_linear_train, linear_wgrad=linear_wgrad, colsum_acc=colsum_acc,
                      layernorm_bwd=layernorm_bwd, act_bwd=act_bwd, glu_bwd=glu_bwd, relpos_attention=_relpos_attention_train,
                      relpos_attention_bwd=relpos_attention_bwd, conformer_conv_bwd=conformer_conv_bwd,
-                     maxpool_time_bwd=maxpool_time_bwd, pool_time_bwd=pool_time_bwd, relu_mask=relu_mask)
+                     maxpool_time_bwd=maxpool_time_bwd, pool_time_bwd=pool_time_bwd, relu_mask=relu_mask, dropout=dropout, dropout_add=dropout_add,
+                     rng_advance=rng_advance)
 
 
 def install_training(monkeypatch):

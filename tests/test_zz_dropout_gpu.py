@@ -1,0 +1,96 @@
+"""Dropout kernels (csrc/dropout.cu) and the dropout training path on the GPU.
+  * the kernel's keep mask is bit-identical to the numpy restatement of its Philox counter scheme (tests/ops_doubles.py
+    philox_keep) -- the same restatement the CPU wiring test replays into the unmodified reference;
+  * the same (p, stream id) reproduces the mask (backward), another id / an advanced offset gives another one;
+  * a whole encoder training step with dropout 0.1 on the GPU equals the same step computed on CPU with the torch
+    restatements of the ops and the same Philox masks (outputs and parameter gradients).
+(File name sorts last on purpose: written after the round's GPU budget was spent.)"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from enc_util import build_ours, golden_cfg
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n", [4096, 1003, 7, 1 << 20])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("p", [0.1, 0.5])
+def test_dropout_mask_matches_philox_restatement(n, dtype, p):
+    import ops_doubles
+    from neural_sp_b200 import ops, random as nrandom
+    nrandom.manual_seed(99)
+    x = (torch.rand(n, device="cuda") + 0.5).to(dtype)
+    sid = nrandom.next_stream()
+    y = ops.dropout(x, p, sid)
+    st = nrandom.state(x.device).cpu()
+    keep = ops_doubles.philox_keep(n, float(torch.tensor(p, dtype=torch.float32)), int(st[0]), int(st[1]), sid)
+    assert torch.equal((y != 0).cpu(), keep)
+    ref = torch.where(keep.cuda(), x.float() / (1 - p), torch.zeros((), device="cuda"))
+    assert torch.allclose(y.float(), ref, rtol=1e-2 if dtype == torch.bfloat16 else 1e-6)
+    assert abs(float(keep.float().mean()) - (1 - p)) < (0.02 if n >= 4096 else 0.5)
+    # same id -> same mask (this is what the backward relies on); mixed dtypes take the scalar path: same mask again
+    assert torch.equal(ops.dropout(x, p, sid) != 0, y != 0)
+    assert torch.equal((ops.dropout(x, p, sid, out_dtype=torch.float32 if dtype == torch.bfloat16 else torch.bfloat16) != 0), y != 0)
+    if n >= 1003:
+        assert not torch.equal(ops.dropout(x, p, nrandom.next_stream()) != 0, y != 0)
+        nrandom.advance(x.device)
+        assert not torch.equal(ops.dropout(x, p, sid) != 0, y != 0)
+    # residual form
+    res = torch.randn(n, device="cuda")
+    nrandom.manual_seed(99)
+    out = ops.dropout_add(x, res, p, 0.5, sid)
+    assert torch.allclose(out, res + 0.5 * ref, rtol=1e-2 if dtype == torch.bfloat16 else 1e-5, atol=1e-5)
+
+
+def test_dropout_module_autograd():
+    from neural_sp_b200.modules.dropout import Dropout
+    m = Dropout(p=0.3).cuda().train()
+    x = torch.randn(5, 33, 16, device="cuda", requires_grad=True)
+    y = m(x)
+    y.sum().backward()
+    kept = (y != 0)
+    assert torch.allclose(x.grad[kept], torch.full_like(x.grad[kept], 1 / 0.7)) and float(x.grad[~kept].abs().max()) == 0
+    assert torch.equal(m.eval()(x), x)
+
+
+@pytest.mark.parametrize("name", ["enc_conformer_small.npz", "enc_transformer_xl.npz"])
+def test_training_step_with_dropout_equals_cpu_restatement(name, monkeypatch):
+    import ops_doubles
+    from neural_sp_b200 import random as nrandom
+    g = load_golden(name)
+    a, conv, kind = golden_cfg(g)
+
+    def build(dev):
+        enc = build_ours(g, dev, "fp32")
+        for m in enc.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.1
+        for layer in enc.layers:
+            layer.self_attn.dropout_attn.p = 0.0
+        return enc.train()
+
+    xs, xlens = torch.from_numpy(g["xs"]), torch.IntTensor(g["xlens"].tolist())
+
+    def step(enc, dev):
+        nrandom.manual_seed(7)
+        out = enc(xs.to(dev), xlens.clone(), task="ys")["ys"]
+        ys = out["xs"]
+        w = torch.from_numpy(np.random.default_rng(1).standard_normal(tuple(ys.shape)).astype(np.float32))
+        for b, n in enumerate(out["xlens"].tolist()):
+            w[b, n:] = 0
+        (ys * w.to(dev)).sum().backward()
+        return ys.detach().float().cpu(), {k: p.grad.detach().float().cpu() for k, p in enc.named_parameters()}
+
+    y_gpu, g_gpu = step(build(torch.device("cuda:0")), torch.device("cuda:0"))
+    eval_out = build_ours(g, torch.device("cuda:0"), "fp32")(xs.cuda(), xlens.clone(), task="ys")["ys"]["xs"].float().cpu()
+    assert float((y_gpu - eval_out).abs().max()) > 1e-3          # dropout really is active
+    ops_doubles.install_training(monkeypatch)
+    y_cpu, g_cpu = step(build(torch.device("cpu")), torch.device("cpu"))
+    assert float((y_gpu - y_cpu).abs().max()) <= 1e-3 * float(y_cpu.abs().max())
+    gmax = max(float(v.abs().max()) for v in g_cpu.values())
+    bad = [(k, float((g_gpu[k] - v).abs().max() / max(float(v.abs().max()), 1e-3 * gmax))) for k, v in g_cpu.items()]
+    bad = [(k, e) for k, e in bad if not e <= 2e-3]
+    assert not bad, (bad[:8], len(bad))
