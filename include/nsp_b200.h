@@ -215,6 +215,15 @@ nsp_status nsp_ctc_greedy(const float* logits, int B, int T, int V, const int32_
 nsp_status nsp_rnnt_joint_tanh(const float* enc, const float* dec, void* out, int out_bf16, int B, int T, int U1,
                                int J, void* stream);
 
+/* Training of the joint network (the reference: torch autograd through rnn_transducer.py:242 and :273).
+ * nsp_log_softmax_bwd: dz = g * (dlp - exp(lp) * rowsum(dlp)) IN PLACE on dlp; lp, dlp fp32 [rows, V]; g = optional device
+ *   scalar (upstream gradient of the loss), NULL = 1.
+ * nsp_rnnt_joint_tanh_bwd: p = dh * (1 - h^2); de[b,t,:] = sum_u p, dd[b,u,:] = sum_t p; h, dh fp32 or bf16 [B,T,U1,J],
+ *   de fp32 [B,T,J], dd fp32 [B,U1,J]. */
+nsp_status nsp_log_softmax_bwd(const float* lp, float* dlp, int64_t rows, int V, const float* gscale, void* stream);
+nsp_status nsp_rnnt_joint_tanh_bwd(int is_bf16, const void* h, const void* dh, float* de, float* dd, int B, int T, int U1,
+                                   int J, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * (Bi)LSTM layer recurrence over length-masked sequences (persistent cooperative kernel, fp32 math).
  * Replaces Padding.forward encoders/rnn.py:534-546 (pack_padded_sequence -> nn.LSTM -> pad_packed_sequence) for one

@@ -628,6 +628,58 @@ def lstm_layer(enc, lth, xs, lens_dev, prec):
 
 
 # ------------------------------------------------------------------------------------------------
+# RNN-T joint network + loss as one node
+# ------------------------------------------------------------------------------------------------
+class _RnntJointLossFn(torch.autograd.Function):
+    """(w_enc(e) `[B,T,J]`, w_dec(d) `[B,U+1,J]`) -> mean RNN-T loss (reference decoders/rnn_transducer.py:240-252, :262-276):
+    tanh of the broadcast sum, output layer, log-softmax and the lattice in ONE autograd node.  Forward keeps the joint
+    activation h, the log-probabilities and d loss / d log_probs (the lattice kernel produces it in the same pass);
+    backward = log-softmax backward in place (scaled by the upstream gradient on the device), the output layer's dgrad /
+    wgrad GEMMs and the two broadcast reductions of the tanh backward."""
+
+    @staticmethod
+    def forward(ctx, e, d, weight, bias, owner, labels, flens, ylens, blank, prec):
+        B, T, J = e.shape
+        U1, V = d.shape[1], weight.shape[0]
+        h = ops.rnnt_joint_tanh(e.detach(), d.detach(), out_dtype=act_dtype(prec))
+        logits = ops.linear(h.view(B * T * U1, J), prepared(owner, "output", prec, (weight,)), bias, prec=prec,
+                            out_dtype=torch.float32)
+        lp = ops.softmax_rows(logits.view(B, T, U1, V), log=True, inplace=True)
+        loss, nll, grad = ops.rnnt_loss_fwd_bwd(lp, labels, flens, ylens, blank, need_grad=True)
+        ctx.keep = (h, lp, grad, weight, bias)
+        ctx.owner, ctx.prec = owner, prec
+        ctx.mark_non_differentiable(nll)
+        return loss, nll
+
+    @staticmethod
+    def backward(ctx, g_loss, g_nll):
+        h, lp, grad, weight, bias = ctx.keep
+        ctx.keep = None
+        prec = ctx.prec
+        B, T, U1, J = h.shape
+        V = weight.shape[0]
+        dz = ops.log_softmax_bwd_(lp, grad, g_loss.detach().float()).view(-1, V)       # in place: grad now holds d / d logits
+        dzo = _gop(dz, prec)
+        nb = V if bias is not None else 0
+        flat = torch.zeros(weight.numel() + nb, dtype=torch.float32, device=weight.device)
+        gw = flat[:weight.numel()].view(weight.shape)
+        gb = flat[weight.numel():] if bias is not None else None
+        ops.linear_wgrad(dzo, h.view(-1, J), prec, gw)
+        if gb is not None:
+            ops.colsum_acc(dz, gb)
+        dh = ops.linear(dzo, _wT(ctx.owner, "output", prec, (weight,)), None, prec=prec, out_dtype=act_dtype(prec))
+        de, dd = ops.rnnt_joint_tanh_bwd(h, dh.view(B, T, U1, J))
+        if _GRAD_SYNC is not None:
+            _GRAD_SYNC(flat)
+        return de, dd, gw, gb, None, None, None, None, None, None
+
+
+def rnnt_joint_loss(owner, e, d, labels, flens, ylens, blank, prec):
+    """-> (loss 0-dim, nll [B]); `owner.output` is the vocabulary layer."""
+    return _RnntJointLossFn.apply(e, d, owner.output.weight, owner.output.bias, owner, labels, flens, ylens, blank, prec)
+
+
+# ------------------------------------------------------------------------------------------------
 # CNN front-end (Conv2dBlock stack + bridge) as one node
 # ------------------------------------------------------------------------------------------------
 def _conv_any(block, name, layer, x, B, T, F, first, prec, weight=None, relu=True):

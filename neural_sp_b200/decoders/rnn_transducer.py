@@ -1,18 +1,22 @@
 """RNN-Transducer decoder, training path (reference decoders/rnn_transducer.py:32-311), B200-native.
 
 Same constructor and parameter names (``rnn.N``, ``embed``, ``w_enc``, ``w_dec``, ``output``, ``ctc.*``).
-``forward`` / ``forward_transducer`` compute the loss value: prediction network (embedding + stacked nn.LSTM, kept
-as plain torch -- SURVEY.md section 2 row 4), joint network on the library's kernels (two GEMMs, fused add+tanh,
-vocabulary GEMM, row log-softmax) and the RNN-T lattice kernel, which also yields d loss / d log_probs.
-Beam search (:419-819) is out of scope."""
+``forward`` / ``forward_transducer`` compute the loss: prediction network (embedding gather + stacked LSTMs on the
+library's persistent LSTM kernel, the nn.LSTM modules only hold the parameters), joint network (two GEMMs, fused add+tanh,
+vocabulary GEMM, row log-softmax) and the RNN-T lattice kernel, which yields the loss and d loss / d log_probs in one
+pass.  In train() + grad mode the whole chain is differentiable through hand-written backward kernels
+(neural_sp_b200/autograd.py: _RnntJointLossFn, _LstmLayerFn, _LinearFn, _LinearReluFn, _DropoutFn), so the loss
+back-propagates into the encoder output, the prediction network and the embedding; only the embedding row gather /
+scatter-add is torch's (data movement).  Beam search (:419-819) is out of scope."""
 import copy
 
 import numpy as np
 import torch
 import torch.nn as nn
 
+from .. import autograd as ag
 from .. import ops
-from ..modules._prep import prepared, get_precision, act_dtype
+from ..modules._prep import prepared, cached, get_precision, act_dtype
 from .ctc import CTC, _lens_dev
 
 
@@ -36,6 +40,7 @@ class RNNTransducer(nn.Module):
         self.prev_spk = ''
         self.lmstate_final = None
         self.embed_cache = None
+        self.bidirectional = False             # read by the shared LSTM layer node (autograd.lstm_layer)
         if external_lm is not None:
             raise NotImplementedError("LM initialisation of the prediction network is out of scope")
         if ctc_weight > 0:
@@ -68,14 +73,32 @@ class RNNTransducer(nn.Module):
             m.precision = precision
         return self
 
-    def recurrency(self, ys_emb):
-        """Prediction network (reference :278-311); plain torch (cuDNN LSTM), no state carried in training."""
+    def _lstm(self, lth, xs, lens_dev):
+        """One prediction-network LSTM layer (inference kernels): input GEMM + persistent recurrence."""
+        rnn, prec = self.rnn[lth], get_precision(self)
+        w_ihp = prepared(self, 'w_ih%d' % lth, prec, (rnn.weight_ih_l0,))
+        bias = cached(self, 'b%d' % lth, (rnn.bias_ih_l0, rnn.bias_hh_l0), lambda a, b: (a + b).float().contiguous())
+        w_hh = cached(self, 'w_hh%d' % lth, (rnn.weight_hh_l0,), lambda w: w.unsqueeze(0).float().contiguous())
+        return ops.lstm_seq(ops.linear(xs, w_ihp, bias, prec=prec, out_dtype=torch.float32), w_hh, lens_dev, 1)
+
+    def recurrency(self, ys_emb, train=False):
+        """Prediction network (reference :278-311), zero initial state: stacked unidirectional LSTMs over all U+1 positions
+        (the reference does not pack here), dropout, optional projection + ReLU."""
+        prec = get_precision(self)
+        B, U1, _ = ys_emb.shape
+        lens = _lens_dev(torch.IntTensor([U1] * B), ys_emb.device)
         out = ys_emb
         for lth in range(self.n_layers):
-            out, _ = self.rnn[lth](out)
-            out = self.dropout(out)
+            if train:
+                out = ag.dropout(ag.lstm_layer(self, lth, out, lens, prec), self.dropout.p)
+            else:
+                out = self._lstm(lth, out.float(), lens)
             if self.proj is not None:
-                out = torch.relu(self.proj[lth](out))
+                lin = self.proj[lth]
+                if train:
+                    out = ag.linear_relu(self, 'proj%d' % lth, lin.weight, lin.bias, out, prec)
+                else:
+                    out = ops.linear(out, prepared(self, 'proj%d' % lth, prec, (lin.weight,)), lin.bias, prec=prec, act='relu')
         return out
 
     def joint(self, eouts, dout):
@@ -91,7 +114,8 @@ class RNNTransducer(nn.Module):
         return ops.softmax_rows(logits.view(B, T, U1, self.vocab), log=True, inplace=True)
 
     def forward_transducer(self, eouts, elens, ys):
-        """RNN-T loss (reference :217-260): mean over the batch of -log p(y|x); returns a `[1]` tensor."""
+        """RNN-T loss (reference :217-260): mean over the batch of -log p(y|x); returns a `[1]` tensor (differentiable in
+        train() + grad mode)."""
         device = eouts.device
         B = len(ys)
         ylens = [len(y) for y in ys]
@@ -103,12 +127,21 @@ class RNNTransducer(nn.Module):
             if len(y):
                 ys_in[b, 1:len(y) + 1] = torch.as_tensor(list(y), dtype=torch.long)
                 ys_out[b, :len(y)] = torch.as_tensor(list(y), dtype=torch.int32)
+        flens = _lens_dev(elens, device)
+        ylens_d = _lens_dev(torch.tensor(ylens, dtype=torch.int32), device)
+        labels = ys_out[:, :U].contiguous().to(device) if U > 0 else torch.zeros(B, 0, dtype=torch.int32, device=device)
+        prec = get_precision(self)
+        if self.training and torch.is_grad_enabled():
+            emb = torch.nn.functional.embedding(ys_in.to(device), self.embed.weight, padding_idx=self.pad)
+            dout = self.recurrency(ag.dropout(emb.float(), self.dropout_emb.p), train=True)
+            e = ag.linear(self, 'w_enc', self.w_enc, eouts.float(), prec)                  # `[B, T, J]`
+            d = ag.linear(self, 'w_dec', self.w_dec, dout, prec)                           # `[B, U+1, J]`
+            loss, _ = ag.rnnt_joint_loss(self, e, d, labels, flens, ylens_d, self.blank, prec)
+            self._grad_log_probs = None
+            return loss.reshape(1)
         with torch.no_grad():
-            dout = self.recurrency(self.dropout_emb(self.embed(ys_in.to(device))))
+            dout = self.recurrency(self.embed(ys_in.to(device)))
             log_probs = self.joint(eouts.float(), dout.float())
-            flens = _lens_dev(elens, device)
-            ylens_d = _lens_dev(torch.tensor(ylens, dtype=torch.int32), device)
-            labels = ys_out[:, :U].contiguous().to(device) if U > 0 else torch.zeros(B, 0, dtype=torch.int32, device=device)
             loss, nll, grad = ops.rnnt_loss_fwd_bwd(log_probs, labels, flens, ylens_d, self.blank, need_grad=True)
         self._grad_log_probs = grad            # d loss / d log_probs, kept for callers that chain the backward by hand
         return loss.reshape(1)

@@ -531,6 +531,7 @@ def lstm_seq_bwd(dy, acts, cprev, w_hh, lens):
 # backward pass (training): hand-written gradients of the forward ops above
 # ---------------------------------------------------------------------------------------------
 KERNELS_PER_CALL["nsp_relpos_attention_bwd"] = 4
+KERNELS_PER_CALL["nsp_rnnt_joint_tanh_bwd"] = 2
 KERNELS_PER_CALL["nsp_conformer_conv_bwd"] = 2
 
 
@@ -673,6 +674,34 @@ def pool_time_bwd(dy, T, factor, mode):
     dx = torch.empty(B, T, D, dtype=torch.float32, device=dy.device)
     _run("nsp_pool_time_bwd", lib.nsp_pool_time_bwd, ptr(dy), ptr(dx), B, T, D, int(factor), POOL_MODE[mode], current_stream_ptr())
     return dx
+
+
+def log_softmax_bwd_(lp, dlp, gscale=None):
+    """dz = g * (dlp - exp(lp) * rowsum(dlp)) in place on dlp (nsp_log_softmax_bwd); lp, dlp fp32 `[..., V]` contiguous,
+    gscale = optional 0-dim / 1-element fp32 CUDA tensor (upstream gradient of the loss)."""
+    _require_cuda(lp, dlp, gscale)
+    assert lp.dtype == torch.float32 and dlp.dtype == torch.float32 and lp.is_contiguous() and dlp.is_contiguous()
+    assert lp.shape == dlp.shape
+    V = lp.shape[-1]
+    if gscale is not None:
+        gscale = gscale.reshape(-1)[:1].float().contiguous()
+    _run("nsp_log_softmax_bwd", lib.nsp_log_softmax_bwd, ptr(lp), ptr(dlp), lp.numel() // V, V, ptr(gscale), current_stream_ptr(),
+         nbytes=12.0 * lp.numel())
+    return dlp
+
+
+def rnnt_joint_tanh_bwd(h, dh):
+    """Backward of rnnt_joint_tanh (nsp_rnnt_joint_tanh_bwd): h, dh `[B,T,U1,J]` (same dtype, fp32 or bf16) ->
+    (de fp32 `[B,T,J]`, dd fp32 `[B,U1,J]`)."""
+    _require_cuda(h, dh)
+    h, dh = h.contiguous(), dh.contiguous()
+    assert h.dtype == dh.dtype and h.shape == dh.shape and h.dim() == 4
+    B, T, U1, J = h.shape
+    de = torch.empty(B, T, J, dtype=torch.float32, device=h.device)
+    dd = torch.empty(B, U1, J, dtype=torch.float32, device=h.device)
+    _run("nsp_rnnt_joint_tanh_bwd", lib.nsp_rnnt_joint_tanh_bwd, int(h.dtype == torch.bfloat16), ptr(h), ptr(dh), ptr(de), ptr(dd),
+         B, T, U1, J, current_stream_ptr(), nbytes=4.0 * h.numel() * h.element_size())
+    return de, dd
 
 
 # ---- dropout (mask regenerated from (seed, offset, stream, index); nothing is stored) ----

@@ -187,11 +187,11 @@ def maxpool_time(x, factor):
 def lstm_seq(gates_x, w_hh, lens, n_dirs, save=False, state=None, want_state=False):
     """Packed-sequence LSTM recurrence (csrc/lstm.cu contract): state frozen and outputs zero beyond each length, the
     reverse direction of utterance b starts at its own last frame; optional initial / final state `[n_dirs, B, H]`."""
-    assert not save
     B, T, G = gates_x.shape
     H = G // (4 * n_dirs)
     y = torch.zeros(B, T, n_dirs * H)
     hN, cN = torch.zeros(n_dirs, B, H), torch.zeros(n_dirs, B, H)
+    acts, cprev, hprev = torch.zeros(B, T, n_dirs, 4 * H), torch.zeros(B, T, n_dirs, H), torch.zeros(B, T, n_dirs, H)
     for d in range(n_dirs):
         for b in range(B):
             n = min(max(int(lens[b]), 0), T)
@@ -201,13 +201,76 @@ def lstm_seq(gates_x, w_hh, lens, n_dirs, save=False, state=None, want_state=Fal
                 t = s if d == 0 else n - 1 - s
                 g = gates_x[b, t, d * 4 * H:(d + 1) * 4 * H].float() + w_hh[d].float() @ h
                 i, f, o = torch.sigmoid(g[:H]), torch.sigmoid(g[H:2 * H]), torch.sigmoid(g[3 * H:])
-                c = f * c + i * torch.tanh(g[2 * H:3 * H])
+                gg = torch.tanh(g[2 * H:3 * H])
+                acts[b, t, d], cprev[b, t, d], hprev[b, t, d] = torch.cat([i, f, gg, o]), c, h
+                c = f * c + i * gg
                 h = o * torch.tanh(c)
                 y[b, t, d * H:(d + 1) * H] = h
             hN[d, b], cN[d, b] = h, c
+    if save:
+        return y, acts, cprev, hprev
     if state is not None or want_state:
         return y, (hN, cN)
     return y
+
+
+def lstm_seq_bwd(dy, acts, cprev, w_hh, lens):
+    """BPTT with the kernel's step structure (csrc/lstm.cu): cell backward -> dG_t, then dh_rec = dG_t W_hh."""
+    B, T, nd, H4 = acts.shape
+    H = H4 // 4
+    dG = torch.zeros(B, T, nd * H4)
+    for d in range(nd):
+        for b in range(B):
+            n = min(max(int(lens[b]), 0), T)
+            dc, dhr = torch.zeros(H), torch.zeros(H)
+            for s in range(n - 1, -1, -1):
+                t = s if d == 0 else n - 1 - s
+                i, f, gg, o = acts[b, t, d].split(H)
+                c0 = cprev[b, t, d]
+                tc = torch.tanh(f * c0 + i * gg)
+                dh = dy[b, t, d * H:(d + 1) * H].float() + dhr
+                dcc = dc + dh * o * (1 - tc * tc)
+                dc = dcc * f
+                x = torch.cat([dcc * gg * i * (1 - i), dcc * c0 * f * (1 - f), dcc * i * (1 - gg * gg), dh * tc * o * (1 - o)])
+                dG[b, t, d * H4:(d + 1) * H4] = x
+                dhr = x @ w_hh[d].float()
+    return dG
+
+
+# ---- RNN-T ----
+def rnnt_joint_tanh(enc, dec, out_dtype=torch.float32):
+    return torch.tanh(enc.float()[:, :, None] + dec.float()[:, None]).to(out_dtype)
+
+
+def softmax_rows(x, log=False, temperature=1.0, inplace=False):
+    y = torch.log_softmax(x / temperature, -1) if log else torch.softmax(x / temperature, -1)
+    if inplace:
+        x.copy_(y)
+        return x
+    return y
+
+
+def rnnt_loss_fwd_bwd(log_probs, labels, flens, ylens, blank=0, need_grad=True):
+    """warp_rnnt semantics through the stand-in the fixtures use (torchaudio, un-fused log-softmax): mean over the batch."""
+    import torchaudio
+    with torch.enable_grad():
+        lp = log_probs.detach().clone().requires_grad_(True)
+        nll = torchaudio.functional.rnnt_loss(lp, labels.int(), flens.int(), ylens.int(), blank=blank, reduction='none',
+                                              fused_log_softmax=False)
+        loss = nll.mean()
+        (grad,) = torch.autograd.grad(loss, lp)
+    return loss.detach(), nll.detach(), (grad if need_grad else None)
+
+
+def log_softmax_bwd_(lp, dlp, gscale=None):
+    g = gscale.reshape(-1)[0] if gscale is not None else 1.0
+    dlp.copy_(g * (dlp - lp.exp() * dlp.sum(-1, keepdim=True)))
+    return dlp
+
+
+def rnnt_joint_tanh_bwd(h, dh):
+    p = dh.float() * (1 - h.float() ** 2)
+    return p.sum(2), p.sum(1)
 
 
 DOUBLES = dict(prepare_weight=prepare_weight, to_bf16=to_bf16, linear=linear, layernorm=layernorm,
@@ -411,7 +474,9 @@ TRAIN_DOUBLES = dict(DOUBLES, linear=_linear_train, linear_wgrad=linear_wgrad, c
                      layernorm_bwd=layernorm_bwd, act_bwd=act_bwd, glu_bwd=glu_bwd, relpos_attention=_relpos_attention_train,
                      relpos_attention_bwd=relpos_attention_bwd, conformer_conv_bwd=conformer_conv_bwd,
                      maxpool_time_bwd=maxpool_time_bwd, pool_time_bwd=pool_time_bwd, relu_mask=relu_mask, dropout=dropout, dropout_add=dropout_add,
-                     rng_advance=rng_advance)
+                     rng_advance=rng_advance, lstm_seq_bwd=lstm_seq_bwd, rnnt_joint_tanh=rnnt_joint_tanh,
+                     softmax_rows=softmax_rows, rnnt_loss_fwd_bwd=rnnt_loss_fwd_bwd, log_softmax_bwd_=log_softmax_bwd_,
+                     rnnt_joint_tanh_bwd=rnnt_joint_tanh_bwd)
 
 
 def install_training(monkeypatch):

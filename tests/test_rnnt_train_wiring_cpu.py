@@ -1,0 +1,92 @@
+"""RNN-T training path on CPU (host wiring): prediction network (embedding, LSTM layer nodes, projections), joint network and
+loss as autograd nodes (neural_sp_b200/autograd.py _RnntJointLossFn) against the UNMODIFIED reference `RNNTransducer`
+(decoders/rnn_transducer.py:174-311) with identical weights: loss value, d loss / d encoder output and every parameter
+gradient.  The reference's loss library is not installable offline (warp_rnnt / warprnnt_pytorch); a stand-in
+module `warprnnt_pytorch` backed by torchaudio.functional.rnnt_loss (the oracle of tests/golden/rnnt_*.npz) is injected.
+Needs /root/reference (build container only): skipped elsewhere."""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference/neural_sp"), reason="reference tree not available")
+
+
+def _fake_warprnnt():
+    import torchaudio
+    mod = types.ModuleType("warprnnt_pytorch")
+
+    class RNNTLoss(torch.nn.Module):
+        def forward(self, log_probs, labels, flens, ylens):          # already normalised by the batch size (:257)
+            return torchaudio.functional.rnnt_loss(log_probs, labels.int(), flens.int(), ylens.int(), blank=0,
+                                                   reduction='mean', fused_log_softmax=False)
+    mod.RNNTLoss = RNNTLoss
+    return mod
+
+
+@pytest.mark.parametrize("n_projs,ctc_weight", [(0, 0.0), (12, 0.3)])
+def test_rnnt_training_matches_reference(n_projs, ctc_weight, monkeypatch):
+    import ops_doubles
+    from oracle.ref_import import import_reference
+    import_reference()
+    import neural_sp.models.seq2seq.decoders.rnn_transducer as ref_mod
+    from neural_sp_b200.decoders.rnn_transducer import RNNTransducer
+    import neural_sp_b200.decoders.ctc as our_ctc
+    ops_doubles.install_training(monkeypatch)
+    monkeypatch.setitem(sys.modules, "warprnnt_pytorch", _fake_warprnnt())
+    # the CTC head's loss on CPU: the reference's own arithmetic (F.ctc_loss) stands in for the fused CUDA kernel
+    def ctc_double(logits, labels, elens, ylens, blank=0, lsm_prob=0.0):
+        B = logits.shape[0]
+        with torch.enable_grad():
+            z = logits.detach().clone().requires_grad_(True)
+            lp = z.log_softmax(-1)
+            tg = torch.cat([labels[b, :int(ylens[b])] for b in range(B)])
+            loss = torch.nn.functional.ctc_loss(lp.transpose(0, 1), tg, elens.int(), ylens.int(), blank=blank, reduction='sum',
+                                                zero_infinity=True) / B
+            (g,) = torch.autograd.grad(loss, z)
+        return loss.detach(), torch.zeros(B), g
+    monkeypatch.setattr(our_ctc.ops, "ctc_loss_fwd_bwd", ctc_double)
+    monkeypatch.setattr(our_ctc.ops, "pack_labels", lambda ys, dev: (
+        torch.tensor([list(y) + [0] * (max(len(v) for v in ys) - len(y)) for y in ys], dtype=torch.int32),
+        torch.tensor([len(y) for y in ys], dtype=torch.int32), max(len(v) for v in ys)))
+
+    torch.manual_seed(0)
+    sym = {'eos': 2, 'unk': 1, 'pad': 3, 'blank': 0}
+    kw = dict(special_symbols=sym, enc_n_units=24, n_units=16, n_projs=n_projs, n_layers=2, bottleneck_dim=20, emb_dim=8,
+              vocab=30, dropout=0.0, dropout_emb=0.0, ctc_weight=ctc_weight, ctc_lsm_prob=0.0, ctc_fc_list="", external_lm=None,
+              global_weight=1.0, mtl_per_batch=False, param_init=0.1)
+    ref = ref_mod.RNNTransducer(**kw).train()
+    ours = RNNTransducer(**kw)
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    ours.set_precision("fp32")
+    ours.train()
+    B, T = 3, 14
+    rng = np.random.RandomState(1)
+    e0 = torch.from_numpy(rng.randn(B, T, 24).astype(np.float32))
+    elens = torch.IntTensor([14, 11, 9])
+    ys = [[5, 6, 7, 8], [9, 10], [4]]
+    e_ref = e0.clone().requires_grad_(True)
+    e_our = e0.clone().requires_grad_(True)
+    loss_r, obs_r = ref(e_ref, elens.clone(), ys, task='all')
+    loss_o, obs_o = ours(e_our, elens.clone(), ys, task='all')
+    assert loss_o.shape == loss_r.shape == (1,)
+    assert abs(float(loss_o) - float(loss_r)) <= 1e-4 * abs(float(loss_r)), (float(loss_o), float(loss_r))
+    assert abs(obs_o['loss_transducer'] - obs_r['loss_transducer']) <= 1e-4 * abs(obs_r['loss_transducer'])
+    loss_r.sum().backward()
+    loss_o.sum().backward()
+    assert float((e_our.grad - e_ref.grad).abs().max()) <= 1e-4 * float(e_ref.grad.abs().max())
+    ref_g = dict(ref.named_parameters())
+    for k, p in ours.named_parameters():
+        g = ref_g[k].grad
+        if g is None:
+            continue
+        assert p.grad is not None, k
+        err = float((p.grad - g).abs().max() / g.abs().max().clamp_min(1e-12))
+        assert err <= 2e-4, (k, err)
