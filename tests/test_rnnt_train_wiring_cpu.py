@@ -90,3 +90,9 @@ def test_rnnt_training_matches_reference(n_projs, ctc_weight, monkeypatch):
         assert p.grad is not None, k
         err = float((p.grad - g).abs().max() / g.abs().max().clamp_min(1e-12))
         assert err <= 2e-4, (k, err)
+    # eval mode / no grad: the inference kernels' path (prediction network on the LSTM kernel, materialised log_probs)
+    ref.eval(), ours.eval()
+    with torch.no_grad():
+        l_r = ref.forward_transducer(e0.clone(), elens.clone(), ys)
+        l_o = ours.forward_transducer(e0.clone(), elens.clone(), ys)
+    assert abs(float(l_o) - float(l_r)) <= 1e-4 * abs(float(l_r)), (float(l_o), float(l_r))
