@@ -195,6 +195,17 @@ nsp_status nsp_rnnt_loss_fwd_bwd(const float* log_probs, int B, int T, int U1, i
                                  float* nll, float* loss, float* grad,
                                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* Training from logits: d loss / d logits of the same loss in ONE pass, after nsp_rnnt_loss_fwd_bwd(..., grad = NULL, ...) has
+ * run on the SAME workspace (it holds the gathered emissions and the alpha / beta lattices) with log_probs = log_softmax(logits):
+ *   dz[b,t,u,v] = g * ( gb [v == blank] + gl [v == y_{u+1}] - exp(log_probs[b,t,u,v]) (gb + gl) ),
+ * gb / gl = the two non-zero entries of d loss / d log_probs of the cell; g = optional device scalar (upstream gradient).
+ * dz fp32 (may alias log_probs: in place) or bf16 [B,T,U1,V].  Replaces torch autograd through
+ * `torch.log_softmax` + `warp_rnnt.rnnt_loss` (rnn_transducer.py:242-252) without materialising d loss / d log_probs. */
+nsp_status nsp_rnnt_grad_logits(const float* log_probs, int B, int T, int U1, int V, const int32_t* labels,
+                                const int32_t* flens, const int32_t* ylens, int blank, const float* nll,
+                                const void* workspace, size_t workspace_bytes, const float* gscale,
+                                void* dz, int dz_bf16, void* stream);
+
 /* 3x3 conv, C_in = C_out = 32, as an implicit GEMM on tcgen05 (bf16 in/out, fp32 accumulate), fused bias + ReLU
  * and optional fused 2x2 ceil-mode max-pool.  Replaces nn.Conv2d(32,32,3,pad 1)+ReLU(+MaxPool2d) of
  * Conv2dBlock.forward encoders/conv.py:362-394.  x bf16 [B,T,F,32]; w_taps bf16 [32, 288] with column

@@ -167,6 +167,8 @@ _more = {
     "nsp_dropout": (c_int, [c_int, c_int, c_vp, c_vp, c_i64, c_f32, c_f32, c_vp, ctypes.c_uint32, c_vp]),
     "nsp_dropout_add": (c_int, [c_int, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_vp, ctypes.c_uint32, c_vp]),
     "nsp_rng_advance": (c_int, [c_vp, c_vp]),
+    "nsp_rnnt_grad_logits": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_sz, c_vp, c_vp,
+                                     c_int, c_vp]),
     "nsp_log_softmax_bwd": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp]),
     "nsp_rnnt_joint_tanh_bwd": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     "nsp_pool_time_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),

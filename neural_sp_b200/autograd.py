@@ -633,9 +633,10 @@ def lstm_layer(enc, lth, xs, lens_dev, prec):
 class _RnntJointLossFn(torch.autograd.Function):
     """(w_enc(e) `[B,T,J]`, w_dec(d) `[B,U+1,J]`) -> mean RNN-T loss (reference decoders/rnn_transducer.py:240-252, :262-276):
     tanh of the broadcast sum, output layer, log-softmax and the lattice in ONE autograd node.  Forward keeps the joint
-    activation h, the log-probabilities and d loss / d log_probs (the lattice kernel produces it in the same pass);
-    backward = log-softmax backward in place (scaled by the upstream gradient on the device), the output layer's dgrad /
-    wgrad GEMMs and the two broadcast reductions of the tanh backward."""
+    activation h, the log-probabilities and the small lattice workspace (alpha, beta, gathered emissions); backward = one pass
+    that turns log-probs into d loss / d logits (log-softmax backward folded into the lattice gradient, scaled by the upstream
+    gradient on the device, written directly in the GEMM operand dtype -- d loss / d log_probs is never materialised), the
+    output layer's dgrad / wgrad GEMMs and the two broadcast reductions of the tanh backward."""
 
     @staticmethod
     def forward(ctx, e, d, weight, bias, owner, labels, flens, ylens, blank, prec):
@@ -645,21 +646,23 @@ class _RnntJointLossFn(torch.autograd.Function):
         logits = ops.linear(h.view(B * T * U1, J), prepared(owner, "output", prec, (weight,)), bias, prec=prec,
                             out_dtype=torch.float32)
         lp = ops.softmax_rows(logits.view(B, T, U1, V), log=True, inplace=True)
-        loss, nll, grad = ops.rnnt_loss_fwd_bwd(lp, labels, flens, ylens, blank, need_grad=True)
-        ctx.keep = (h, lp, grad, weight, bias)
+        loss, nll, _, ws = ops.rnnt_loss_fwd_bwd(lp, labels, flens, ylens, blank, need_grad=False, return_ws=True)
+        ctx.keep = (h, lp, ws, nll, labels, flens, ylens, blank, weight, bias)
         ctx.owner, ctx.prec = owner, prec
         ctx.mark_non_differentiable(nll)
         return loss, nll
 
     @staticmethod
     def backward(ctx, g_loss, g_nll):
-        h, lp, grad, weight, bias = ctx.keep
+        h, lp, ws, nll, labels, flens, ylens, blank, weight, bias = ctx.keep
         ctx.keep = None
         prec = ctx.prec
         B, T, U1, J = h.shape
         V = weight.shape[0]
-        dz = ops.log_softmax_bwd_(lp, grad, g_loss.detach().float()).view(-1, V)       # in place: grad now holds d / d logits
-        dzo = _gop(dz, prec)
+        bf16 = prec == "bf16"
+        dz = ops.rnnt_grad_logits(lp, ws, nll, labels, flens, ylens, blank, g_loss.detach().float(),
+                                  out_dtype=torch.bfloat16 if bf16 else torch.float32, inplace=not bf16).view(-1, V)
+        dzo = dz
         nb = V if bias is not None else 0
         flat = torch.zeros(weight.numel() + nb, dtype=torch.float32, device=weight.device)
         gw = flat[:weight.numel()].view(weight.shape)

@@ -184,6 +184,72 @@ __global__ void __launch_bounds__(256) rnnt_grad_kernel(RnntParams p) {
     }
 }
 
+// Training from logits (the joint network's output layer): d loss / d logits in ONE pass over the [B,T,U+1,V] tensor.
+// With gb, gl the two non-zero entries of d loss / d log_probs of a cell (as in rnnt_grad_kernel), the log-softmax
+// backward collapses to   dz[v] = g * ( gb [v == blank] + gl [v == y] - exp(lp[v]) (gb + gl) ):
+// lp is read once and dz written once (fp32, optionally in place over lp, or bf16 = the operand of the output layer's
+// dgrad / wgrad GEMMs) -- the dense d loss / d log_probs tensor is never materialised.  g = device scalar (upstream
+// gradient of the loss) or null.  Warp per lattice cell.
+template <int VEC, typename TO>
+__global__ void __launch_bounds__(256) rnnt_grad_logits_kernel(RnntParams p, const float* __restrict__ gscale, TO* dz) {
+    const int lane = threadIdx.x & 31;
+    const int64_t cell = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t ncell = (int64_t)p.B * p.T * p.U1;
+    if (cell >= ncell) return;
+    const int u = (int)(cell % p.U1);
+    const int64_t bt = cell / p.U1;
+    const int b = (int)(bt / p.T), t = (int)(bt % p.T);
+    const int Tb = min(max(p.flens[b], 0), p.T), Ub = min(max(p.ylens[b], 0), p.U1 - 1);
+    float gb = 0.f, gl = 0.f;
+    int y = -1;
+    if (t < Tb && u <= Ub) {
+        const float nll = p.nll[b];
+        const int64_t base = (int64_t)b * p.T * p.U1;
+        const float a = p.alpha[cell];
+        const float scale = (gscale ? __ldg(gscale) : 1.f) / (float)p.B;
+        if (t < Tb - 1) gb = -scale * __expf(a + p.bl[cell] + p.beta[base + (int64_t)(t + 1) * p.U1 + u] + nll);
+        else if (u == Ub) gb = -scale * __expf(a + p.bl[cell] + nll);
+        if (u < Ub) {
+            y = min(max(p.labels[(int64_t)b * (p.U1 - 1) + u], 0), p.V - 1);
+            gl = -scale * __expf(a + p.lb[cell] + p.beta[cell + 1] + nll);
+        }
+    }
+    if (y == p.blank) { gb += gl; y = -1; }
+    const float gsum = gb + gl;
+    const float* lrow = p.lp + cell * (int64_t)p.V;
+    TO* row = dz + cell * (int64_t)p.V;
+    if (gsum == 0.f) {                                   // padded cell (or fully underflowed): exact zeros, lp not read
+        if constexpr (VEC == 4 && sizeof(TO) == 4) {
+            for (int i = lane * 4; i < p.V; i += 128) st_stream_f4(reinterpret_cast<float*>(row) + i, make_float4(0.f, 0.f, 0.f, 0.f));
+        } else {
+            for (int i = lane; i < p.V; i += 32) {
+                if constexpr (sizeof(TO) == 4) row[i] = 0.f; else row[i] = __float2bfloat16_rn(0.f);
+            }
+        }
+        return;
+    }
+    if constexpr (VEC == 4) {
+        for (int i = lane * 4; i < p.V; i += 128) {
+            const float4 l = *reinterpret_cast<const float4*>(lrow + i);
+            float v[4] = {-__expf(l.x) * gsum, -__expf(l.y) * gsum, -__expf(l.z) * gsum, -__expf(l.w) * gsum};
+            if (p.blank >= i && p.blank < i + 4) v[p.blank - i] += gb;
+            if (y >= i && y < i + 4) v[y - i] += gl;
+            if constexpr (sizeof(TO) == 4) {
+                st_stream_f4(reinterpret_cast<float*>(row) + i, make_float4(v[0], v[1], v[2], v[3]));
+            } else {
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+                uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                *reinterpret_cast<uint2*>(row + i) = pk;
+            }
+        }
+    } else {
+        for (int i = lane; i < p.V; i += 32) {
+            float v = -__expf(lrow[i]) * gsum + ((i == p.blank) ? gb : 0.f) + ((i == y) ? gl : 0.f);
+            if constexpr (sizeof(TO) == 4) row[i] = v; else row[i] = __float2bfloat16_rn(v);
+        }
+    }
+}
+
 __global__ void rnnt_finalize_kernel(RnntParams p) {
     __shared__ float scratch[32];
     float a = 0.f;
@@ -236,5 +302,34 @@ extern "C" nsp_status nsp_rnnt_loss_fwd_bwd(const float* log_probs, int B, int T
         else rnnt_grad_kernel<1><<<grid, 256, 0, st>>>(p);
         NSP_LAUNCH_OK();
     }
+    return NSP_OK;
+}
+
+extern "C" nsp_status nsp_rnnt_grad_logits(const float* log_probs, int B, int T, int U1, int V, const int32_t* labels,
+                                           const int32_t* flens, const int32_t* ylens, int blank, const float* nll,
+                                           const void* workspace, size_t workspace_bytes, const float* gscale,
+                                           void* dz, int dz_bf16, void* stream) {
+    NSP_CHECK_ARG(log_probs && flens && ylens && nll && workspace && dz, "rnnt_grad_logits: null pointer");
+    NSP_CHECK_ARG(labels || U1 == 1, "rnnt_grad_logits: labels is null");
+    NSP_CHECK_ARG(B > 0 && T > 0 && U1 > 0 && V > 1 && blank >= 0 && blank < V, "rnnt_grad_logits: bad shape");
+    NSP_CHECK_ARG(workspace_bytes >= nsp_rnnt_loss_workspace_bytes(B, T, U1), "rnnt_grad_logits: workspace too small");
+    NSP_CHECK_ARG(!dz_bf16 || dz != (const void*)log_probs, "rnnt_grad_logits: in place only for fp32 output");
+    cudaStream_t st = (cudaStream_t)stream;
+    RnntParams p;
+    p.lp = log_probs; p.B = B; p.T = T; p.U1 = U1; p.V = V; p.labels = labels; p.flens = flens; p.ylens = ylens;
+    p.blank = blank; p.nll = const_cast<float*>(nll); p.loss = nullptr; p.grad = nullptr;
+    const size_t lat = align_up((size_t)B * T * U1 * sizeof(float), 256);
+    char* w = (char*)const_cast<void*>(workspace);
+    p.bl = (float*)w; p.lb = (float*)(w + lat); p.alpha = (float*)(w + 2 * lat); p.beta = (float*)(w + 3 * lat);
+    const unsigned grid = (unsigned)ceil_div64((int64_t)B * T * U1, 8);
+    const bool vec = V % 4 == 0 && ((uintptr_t)log_probs % 16 == 0) && ((uintptr_t)dz % 16 == 0);
+    if (dz_bf16) {
+        if (vec) rnnt_grad_logits_kernel<4, __nv_bfloat16><<<grid, 256, 0, st>>>(p, gscale, (__nv_bfloat16*)dz);
+        else rnnt_grad_logits_kernel<1, __nv_bfloat16><<<grid, 256, 0, st>>>(p, gscale, (__nv_bfloat16*)dz);
+    } else {
+        if (vec) rnnt_grad_logits_kernel<4, float><<<grid, 256, 0, st>>>(p, gscale, (float*)dz);
+        else rnnt_grad_logits_kernel<1, float><<<grid, 256, 0, st>>>(p, gscale, (float*)dz);
+    }
+    NSP_LAUNCH_OK();
     return NSP_OK;
 }

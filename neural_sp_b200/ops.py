@@ -383,9 +383,10 @@ def maxpool_time(x, factor):
 KERNELS_PER_CALL["nsp_rnnt_loss_fwd_bwd"] = 4
 
 
-def rnnt_loss_fwd_bwd(log_probs, labels, flens, ylens, blank=0, need_grad=True):
+def rnnt_loss_fwd_bwd(log_probs, labels, flens, ylens, blank=0, need_grad=True, return_ws=False):
     """RNN-T loss + d loss/d log_probs (nsp_rnnt_loss_fwd_bwd).  log_probs fp32 `[B,T,U+1,V]` CUDA,
-    labels int32 `[B,U]`, flens/ylens int32 `[B]`.  Returns (loss 0-dim mean, nll [B], grad or None)."""
+    labels int32 `[B,U]`, flens/ylens int32 `[B]`.  Returns (loss 0-dim mean, nll [B], grad or None)
+    [+ the lattice workspace when return_ws: the input of rnnt_grad_logits]."""
     _require_cuda(log_probs, labels, flens, ylens)
     log_probs = log_probs.contiguous()
     assert log_probs.dtype == torch.float32 and log_probs.dim() == 4
@@ -399,7 +400,28 @@ def rnnt_loss_fwd_bwd(log_probs, labels, flens, ylens, blank=0, need_grad=True):
     _run("nsp_rnnt_loss_fwd_bwd", lib.nsp_rnnt_loss_fwd_bwd, ptr(log_probs), B, T, U1, V, ptr(labels), ptr(flens),
          ptr(ylens), int(blank), ptr(nll), ptr(loss), ptr(grad), ptr(ws), ws_bytes, current_stream_ptr(),
          nbytes=8.0 * B * T * U1 * V, tag="rnnt_loss")
+    if return_ws:
+        return loss, nll, grad, ws
     return loss, nll, grad
+
+
+def rnnt_grad_logits(log_probs, ws, nll, labels, flens, ylens, blank=0, gscale=None, out_dtype=torch.float32, inplace=False):
+    """d loss / d logits in one pass (nsp_rnnt_grad_logits) from log_probs = log_softmax(logits) and the lattice
+    workspace of rnnt_loss_fwd_bwd(..., need_grad=False, return_ws=True).  fp32 (optionally in place over log_probs)
+    or bf16 `[B,T,U+1,V]`."""
+    _require_cuda(log_probs, ws, nll, labels, flens, ylens, gscale)
+    assert log_probs.dtype == torch.float32 and log_probs.is_contiguous() and log_probs.dim() == 4
+    B, T, U1, V = log_probs.shape
+    if gscale is not None:
+        gscale = gscale.reshape(-1)[:1].float().contiguous()
+    if inplace and out_dtype == torch.float32:
+        dz = log_probs
+    else:
+        dz = torch.empty(B, T, U1, V, dtype=out_dtype, device=log_probs.device)
+    _run("nsp_rnnt_grad_logits", lib.nsp_rnnt_grad_logits, ptr(log_probs), B, T, U1, V, ptr(labels), ptr(flens), ptr(ylens),
+         int(blank), ptr(nll), ptr(ws), ws.numel(), ptr(gscale), ptr(dz), int(out_dtype == torch.bfloat16),
+         current_stream_ptr(), nbytes=float(log_probs.numel() * (4 + dz.element_size())), tag="rnnt_grad_logits")
+    return dz
 
 
 def conv3x3_c32_tc(x, w_taps, bias, relu=True, pool2x2=False):

@@ -250,7 +250,7 @@ def softmax_rows(x, log=False, temperature=1.0, inplace=False):
     return y
 
 
-def rnnt_loss_fwd_bwd(log_probs, labels, flens, ylens, blank=0, need_grad=True):
+def rnnt_loss_fwd_bwd(log_probs, labels, flens, ylens, blank=0, need_grad=True, return_ws=False):
     """warp_rnnt semantics through the stand-in the fixtures use (torchaudio, un-fused log-softmax): mean over the batch."""
     import torchaudio
     with torch.enable_grad():
@@ -259,7 +259,18 @@ def rnnt_loss_fwd_bwd(log_probs, labels, flens, ylens, blank=0, need_grad=True):
                                               fused_log_softmax=False)
         loss = nll.mean()
         (grad,) = torch.autograd.grad(loss, lp)
+    if return_ws:                  # the double's "workspace" is the dense d loss / d log_probs the kernel never materialises
+        return loss.detach(), nll.detach(), (grad if need_grad else None), grad
     return loss.detach(), nll.detach(), (grad if need_grad else None)
+
+
+def rnnt_grad_logits(log_probs, ws, nll, labels, flens, ylens, blank=0, gscale=None, out_dtype=torch.float32, inplace=False):
+    g = gscale.reshape(-1)[0] if gscale is not None else 1.0
+    dz = (g * (ws - log_probs.exp() * ws.sum(-1, keepdim=True))).to(out_dtype)
+    if inplace and out_dtype == torch.float32:
+        log_probs.copy_(dz)
+        return log_probs
+    return dz
 
 
 def log_softmax_bwd_(lp, dlp, gscale=None):
@@ -475,7 +486,7 @@ TRAIN_DOUBLES = dict(DOUBLES, linear=_linear_train, linear_wgrad=linear_wgrad, c
                      relpos_attention_bwd=relpos_attention_bwd, conformer_conv_bwd=conformer_conv_bwd,
                      maxpool_time_bwd=maxpool_time_bwd, pool_time_bwd=pool_time_bwd, relu_mask=relu_mask, dropout=dropout, dropout_add=dropout_add,
                      rng_advance=rng_advance, lstm_seq_bwd=lstm_seq_bwd, rnnt_joint_tanh=rnnt_joint_tanh,
-                     softmax_rows=softmax_rows, rnnt_loss_fwd_bwd=rnnt_loss_fwd_bwd, log_softmax_bwd_=log_softmax_bwd_,
+                     softmax_rows=softmax_rows, rnnt_loss_fwd_bwd=rnnt_loss_fwd_bwd, rnnt_grad_logits=rnnt_grad_logits, log_softmax_bwd_=log_softmax_bwd_,
                      rnnt_joint_tanh_bwd=rnnt_joint_tanh_bwd)
 
 

@@ -95,3 +95,33 @@ def test_rnn_transducer_training_step(n_projs, precision, tol):
         if not e <= tol:
             bad.append((k, e))
     assert not bad, (bad[:8], len(bad))
+
+
+@pytest.mark.parametrize("name", ["rnnt_small.npz", "rnnt_mid.npz"])
+@pytest.mark.parametrize("mode", ["fp32", "fp32_inplace", "bf16"])
+def test_rnnt_grad_logits_matches_reference_fixture(name, mode):
+    """One-pass d loss / d logits (log-softmax backward folded into the lattice gradient) against the fixture's
+    `grad_logits` (torch autograd through log_softmax + torchaudio rnnt_loss, tests/golden/gen_golden_encoder.py::gen_rnnt)."""
+    from conftest import load_golden
+    from neural_sp_b200 import ops
+    g = load_golden(name)
+    dev = "cuda"
+    logits = torch.from_numpy(g["logits"]).to(dev)
+    lp = ops.softmax_rows(logits, log=True)
+    ys, flens, ylens = (torch.from_numpy(g[k]).to(dev) for k in ("ys", "flens", "ylens"))
+    loss, nll, _, ws = ops.rnnt_loss_fwd_bwd(lp, ys, flens, ylens, 0, need_grad=False, return_ws=True)
+    assert abs(float(loss) - float(g["loss"])) <= 1e-4 * abs(float(g["loss"]))
+    scale = torch.tensor(0.7, device=dev)
+    ref = torch.from_numpy(g["grad_logits"]).to(dev) * 0.7
+    if mode == "bf16":
+        dz = ops.rnnt_grad_logits(lp, ws, nll, ys, flens, ylens, 0, scale, out_dtype=torch.bfloat16)
+        tol = 1e-2
+    else:
+        dz = ops.rnnt_grad_logits(lp, ws, nll, ys, flens, ylens, 0, scale, inplace=(mode == "fp32_inplace"))
+        tol = 2e-4
+        assert (dz.data_ptr() == lp.data_ptr()) == (mode == "fp32_inplace")
+    assert float((dz.float() - ref).abs().max()) <= tol * max(float(ref.abs().max()), 1e-3)
+    # unit upstream gradient through the null pointer
+    lp2 = ops.softmax_rows(logits, log=True)
+    dz1 = ops.rnnt_grad_logits(lp2, ws, nll, ys, flens, ylens, 0)
+    assert float((dz1 - ref / 0.7).abs().max()) <= 2e-4 * max(float(ref.abs().max()), 1e-3)
