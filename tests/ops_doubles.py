@@ -464,6 +464,31 @@ def rng_advance(state):
     state[1] += 1
 
 
+def pack_labels(ys, device):
+    Lmax = max(1, max((len(y) for y in ys), default=1))
+    lab = torch.tensor([list(y) + [0] * (Lmax - len(y)) for y in ys], dtype=torch.int32)
+    return lab, torch.tensor([len(y) for y in ys], dtype=torch.int32), Lmax
+
+
+def ctc_loss_fwd_bwd(logits, labels, elens, ylens, blank=0, lsm_prob=0.0):
+    """The reference's own arithmetic (ctc.py:124-129, criterion.py:110-127) through torch autograd stands in for the fused
+    CUDA kernel: loss = (1 - lsm) * CTC(sum, zero_infinity) / B + lsm * KL(uniform over V - 1)."""
+    B, T, V = logits.shape
+    with torch.enable_grad():
+        z = logits.detach().clone().requires_grad_(True)
+        lp = z.log_softmax(-1)
+        tg = torch.cat([labels[b, :int(ylens[b])] for b in range(B)]) if B else labels.reshape(-1)
+        nll = torch.nn.functional.ctc_loss(lp.transpose(0, 1), tg, elens.int(), ylens.int(), blank=blank, reduction='none',
+                                           zero_infinity=True)
+        loss = nll.sum() / B
+        if lsm_prob > 0:
+            mask = (torch.arange(T)[None, :] < elens[:, None]).unsqueeze(-1)
+            kl = (lp.exp() * (lp - math.log(1.0 / (V - 1))) * mask).sum() / float(elens.sum())
+            loss = loss * (1 - lsm_prob) + kl * lsm_prob
+        (g,) = torch.autograd.grad(loss, z)
+    return loss.detach(), nll.detach(), g
+
+
 def frontend_forward(enc, xs, out_scale, prec):
     """Differentiable torch restatement of the CNN front-end + bridge (reference conv.py:167-195, 347-396); replaces
     neural_sp_b200.autograd.frontend_forward (one autograd node with hand-written CUDA backward, checked on the GPU)."""
@@ -487,7 +512,7 @@ TRAIN_DOUBLES = dict(DOUBLES, linear=_linear_train, linear_wgrad=linear_wgrad, c
                      maxpool_time_bwd=maxpool_time_bwd, pool_time_bwd=pool_time_bwd, relu_mask=relu_mask, dropout=dropout, dropout_add=dropout_add,
                      rng_advance=rng_advance, lstm_seq_bwd=lstm_seq_bwd, rnnt_joint_tanh=rnnt_joint_tanh,
                      softmax_rows=softmax_rows, rnnt_loss_fwd_bwd=rnnt_loss_fwd_bwd, rnnt_grad_logits=rnnt_grad_logits, log_softmax_bwd_=log_softmax_bwd_,
-                     rnnt_joint_tanh_bwd=rnnt_joint_tanh_bwd)
+                     rnnt_joint_tanh_bwd=rnnt_joint_tanh_bwd, pack_labels=pack_labels, ctc_loss_fwd_bwd=ctc_loss_fwd_bwd)
 
 
 def install_training(monkeypatch):

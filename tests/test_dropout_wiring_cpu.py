@@ -139,3 +139,59 @@ def test_dropout_training_matches_reference_with_replayed_masks(name, monkeypatc
         if not e <= 1e-3:
             bad.append((k, e))
     assert not bad, (name, bad[:8], len(bad))
+
+
+def test_ctc_head_dropout_matches_reference_with_replayed_masks(monkeypatch):
+    """CTC head with `fc_list` (Linear -> Dropout -> Linear, ctc.py:82-89) + label smoothing in train mode: loss, gradient
+    w.r.t. the encoder output and the head's parameter gradients against the unmodified reference `CTC` with our masks."""
+    import ops_doubles
+    from oracle.ref_import import import_reference
+    import_reference()
+    from neural_sp.models.seq2seq.decoders.ctc import CTC as RefCTC
+    from neural_sp_b200 import ops, random as nrandom
+    from neural_sp_b200.decoders.ctc import CTC
+    ops_doubles.install_training(monkeypatch)
+    nrandom.manual_seed(5)
+    torch.manual_seed(0)
+    kw = dict(eos=2, blank=0, enc_n_units=24, vocab=30, dropout=0.25, lsm_prob=0.1, fc_list="16_12")
+    ref, ours = RefCTC(**kw).train(), CTC(**kw)
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    ours.set_precision("fp32")
+    ours.train()
+    log = []
+    d_drop = ops_doubles.dropout
+
+    def drop_logged(x, p, stream_id, scale=1.0, out_dtype=None, inplace=False):
+        log.append((x.numel(), float(p), int(stream_id)))
+        return d_drop(x, p, stream_id, scale, out_dtype, inplace)
+
+    monkeypatch.setattr(ops, "dropout", drop_logged)
+    e0 = torch.randn(3, 20, 24)
+    elens = torch.IntTensor([20, 17, 12])
+    ys = [[5, 6, 7, 8], [9, 10], [4, 4, 11]]
+    e_our = e0.clone().requires_grad_(True)
+    loss_o, _ = ours(e_our, elens.clone(), ys)
+    n_fwd = len(log)
+    assert n_fwd == 2
+    loss_o.backward()
+    seed, off = int(nrandom.state("cpu")[0]), int(nrandom.state("cpu")[1])
+    it = iter(log[:n_fwd])
+
+    def replay(input, p=0.5, training=True, inplace=False):
+        if not training or p == 0:
+            return input
+        numel, p_rec, sid = next(it)
+        assert numel == input.numel()
+        keep = ops_doubles.philox_keep(numel, float(torch.tensor(p, dtype=torch.float32)), seed, off, sid).reshape(input.shape)
+        return torch.where(keep, input / (1 - torch.tensor(p, dtype=torch.float32)), torch.zeros(()))
+
+    monkeypatch.setattr(torch.nn.functional, "dropout", replay)
+    e_ref = e0.clone().requires_grad_(True)
+    loss_r, _ = ref(e_ref, elens.clone(), ys)
+    loss_r.backward()
+    assert abs(float(loss_o.detach()) - float(loss_r.detach())) <= 1e-4 * abs(float(loss_r.detach()))
+    assert float((e_our.grad - e_ref.grad).abs().max()) <= 1e-4 * float(e_ref.grad.abs().max())
+    rg = dict(ref.named_parameters())
+    for k, p in ours.named_parameters():
+        err = float((p.grad - rg[k].grad).abs().max() / rg[k].grad.abs().max().clamp_min(1e-12))
+        assert err <= 2e-4, (k, err)

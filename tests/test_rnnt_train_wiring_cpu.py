@@ -38,25 +38,8 @@ def test_rnnt_training_matches_reference(n_projs, ctc_weight, monkeypatch):
     import_reference()
     import neural_sp.models.seq2seq.decoders.rnn_transducer as ref_mod
     from neural_sp_b200.decoders.rnn_transducer import RNNTransducer
-    import neural_sp_b200.decoders.ctc as our_ctc
     ops_doubles.install_training(monkeypatch)
     monkeypatch.setitem(sys.modules, "warprnnt_pytorch", _fake_warprnnt())
-    # the CTC head's loss on CPU: the reference's own arithmetic (F.ctc_loss) stands in for the fused CUDA kernel
-    def ctc_double(logits, labels, elens, ylens, blank=0, lsm_prob=0.0):
-        B = logits.shape[0]
-        with torch.enable_grad():
-            z = logits.detach().clone().requires_grad_(True)
-            lp = z.log_softmax(-1)
-            tg = torch.cat([labels[b, :int(ylens[b])] for b in range(B)])
-            loss = torch.nn.functional.ctc_loss(lp.transpose(0, 1), tg, elens.int(), ylens.int(), blank=blank, reduction='sum',
-                                                zero_infinity=True) / B
-            (g,) = torch.autograd.grad(loss, z)
-        return loss.detach(), torch.zeros(B), g
-    monkeypatch.setattr(our_ctc.ops, "ctc_loss_fwd_bwd", ctc_double)
-    monkeypatch.setattr(our_ctc.ops, "pack_labels", lambda ys, dev: (
-        torch.tensor([list(y) + [0] * (max(len(v) for v in ys) - len(y)) for y in ys], dtype=torch.int32),
-        torch.tensor([len(y) for y in ys], dtype=torch.int32), max(len(v) for v in ys)))
-
     torch.manual_seed(0)
     sym = {'eos': 2, 'unk': 1, 'pad': 3, 'blank': 0}
     kw = dict(special_symbols=sym, enc_n_units=24, n_units=16, n_projs=n_projs, n_layers=2, bottleneck_dim=20, emb_dim=8,
