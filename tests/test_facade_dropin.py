@@ -105,3 +105,85 @@ def test_speech2text_accepts_b200_rnn_transducer(monkeypatch):
     s_our = {k: tuple(v.shape) for k, v in ours.state_dict().items()}
     assert s_our == s_ref, set(s_our) ^ set(s_ref)
     ours.load_state_dict(stock.state_dict(), strict=True)
+
+
+def _fake_warprnnt():
+    import types
+    import torch
+    import torchaudio
+    mod = types.ModuleType("warprnnt_pytorch")
+
+    class RNNTLoss(torch.nn.Module):
+        def forward(self, log_probs, labels, flens, ylens):
+            return torchaudio.functional.rnnt_loss(log_probs, labels.int(), flens.int(), ylens.int(), blank=0,
+                                                   reduction='mean', fused_log_softmax=False)
+    mod.RNNTLoss = RNNTLoss
+    return mod
+
+
+@pytest.mark.parametrize("ov", [
+    dict(),                                                                                      # conv + Conformer + CTC
+    dict(enc_type='conv_transformer', transformer_enc_pe_type='add', transformer_ffn_activation='relu'),
+    dict(enc_type='conv_blstm', subsample="1_2_1", enc_n_projs=16),                              # conv + BLSTM + CTC
+    dict(dec_type='lstm_transducer', enc_type='conv_lstm', subsample="1_1_1", ctc_weight=0.3, conv_poolings="(2,2)_(2,2)"),
+])
+def test_training_step_through_the_unchanged_facade(ov, monkeypatch):
+    """End to end under the UNCHANGED reference `Speech2Text.forward` (speech2text.py:206-345): same batch, same weights,
+    stock modules vs neural_sp_b200's -- total loss, the observation dict and every parameter gradient.  CPU: the library's
+    ops are replaced by their torch restatements (tests/ops_doubles.py), so this pins the drop-in boundary (argument
+    passing, return structures, autograd connectivity of encoder -> decoder), not the kernels."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import numpy as np
+    import torch
+    import ops_doubles
+    from oracle.ref_import import import_reference
+    import_reference()
+    import neural_sp.models.seq2seq.decoders.ctc as ref_ctc
+    import neural_sp.models.seq2seq.decoders.las as ref_las
+    import neural_sp.models.seq2seq.decoders.rnn_transducer as ref_rnnt
+    import neural_sp.models.seq2seq.speech2text as ref_s2t
+    from neural_sp_b200.decoders.ctc import CTC as B200CTC
+    from neural_sp_b200.decoders.rnn_transducer import RNNTransducer as B200RNNT
+    from neural_sp_b200.encoders.build import build_encoder as b200_build_encoder
+    monkeypatch.setitem(sys.modules, "warprnnt_pytorch", _fake_warprnnt())
+    torch.manual_seed(0)
+    stock = ref_s2t.Speech2Text(make_args(**ov))
+    monkeypatch.setattr(ref_s2t, "build_encoder", b200_build_encoder)
+    monkeypatch.setattr(ref_las, "CTC", B200CTC)
+    monkeypatch.setattr(ref_ctc, "CTC", B200CTC)
+    monkeypatch.setattr(ref_rnnt, "RNNTransducer", B200RNNT)
+    # the facade's own `isinstance(self.dec_fwd, RNNT)` (:300, :337, :629); a tuple because this test runs BOTH models
+    monkeypatch.setattr(ref_s2t, "RNNT", (ref_s2t.RNNT, B200RNNT))
+    torch.manual_seed(0)
+    ours = ref_s2t.Speech2Text(make_args(**ov))
+    ours.load_state_dict(stock.state_dict(), strict=True)
+    for m in ours.modules():
+        m.precision = "fp32"
+    ops_doubles.install_training(monkeypatch)
+    rng = np.random.RandomState(0)
+    batch = {'xs': [rng.randn(n, 80).astype(np.float32) for n in (64, 53, 40)],
+             'ys': [[5, 6, 7, 8, 9], [10, 11, 12], [13, 4]], 'ys_sub1': None, 'ys_sub2': None, 'trigger_points': None,
+             'xlens': [64, 53, 40], 'utt_ids': ['a', 'b', 'c'], 'speakers': ['s'] * 3, 'sessions': ['x'] * 3, 'text': [''] * 3,
+             'feat_path': [''] * 3, 'ylens': [5, 3, 2]}
+    stock.train(), ours.train()
+    loss_s, obs_s = stock(batch, task='all')
+    loss_o, obs_o = ours(batch, task='all')
+    assert loss_o.shape == loss_s.shape
+    assert abs(float(loss_o.detach()) - float(loss_s.detach())) <= 1e-4 * abs(float(loss_s.detach()))
+    for k, v in obs_s.items():
+        if isinstance(v, float):
+            assert abs(obs_o[k] - v) <= 1e-4 * max(1.0, abs(v)), (k, obs_o[k], v)
+    loss_s.sum().backward()
+    loss_o.sum().backward()
+    gs = dict(stock.named_parameters())
+    gmax = max(float(p.grad.abs().max()) for p in gs.values() if p.grad is not None)
+    bad = []
+    for k, p in ours.named_parameters():
+        g = gs[k].grad
+        if g is None:
+            continue
+        assert p.grad is not None, k
+        e = float((p.grad - g).abs().max() / max(float(g.abs().max()), 1e-3 * gmax))
+        if not e <= 1e-3:
+            bad.append((k, e))
+    assert not bad, (bad[:8], len(bad))
