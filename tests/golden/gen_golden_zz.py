@@ -29,6 +29,10 @@ ZZ_CASES = {
     "transformer_add": dict(args=dict(enc_type='conv_transformer', pe_type='add', ffn_activation='gelu', n_layers=2,
                                       subsample="1_2", lookahead="0_0", last_proj_dim=40),
                             conv=dict(poolings="(2,2)_(2,2)"), B=2, T=70, xlens=[70, 51], kind='transformer'),
+    # no CNN: embedding Linear + absolute positions, plain MHA
+    "transformer_embed_add": dict(args=dict(enc_type='transformer', pe_type='add', ffn_activation='relu', n_layers=2,
+                                            subsample="1_2", lookahead="0_0", n_heads=2, d_model=32, d_ff=64),
+                                  conv=None, B=2, T=50, xlens=[50, 44], kind='transformer'),
     # GLU feed-forward activation (LinearGLUBlock) + 'drop' subsampling
     "conformer_glu_drop": dict(args=dict(ffn_activation='glu', subsample_type='drop', n_layers=2, subsample="2_1",
                                          lookahead="0_0", d_model=32, d_ff=64, n_heads=2),
