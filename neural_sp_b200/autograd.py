@@ -143,37 +143,65 @@ def _drop_grad(dy, dyo, p_res, sid, prec):
 
 
 def ffn_fwd(ffn, norm, x, scale, prec, p_res=0.0):
+    """y = x + scale * dropout(out(dropout(act(in(LN(x))))));  in / out = one Linear each, or two for the low-rank form
+    (positionwise_feed_forward.py:41-45, :87); GLU = an extra Linear with the gate fused in its epilogue (modules/glu.py)."""
     n = _ln_fwd(norm, x, prec)
-    w1 = prepared(ffn, "w_1", prec, (ffn.w_1.weight,))
-    w2 = prepared(ffn, "w_2", prec, (ffn.w_2.weight,))
+    adt = act_dtype(prec)
+    ins, outs = ffn.in_layers, ffn.out_layers
+    glu = ffn.act_name == "glu"
+    xin, h, z = [], n, None                      # xin[i] = input of ins[i] (operand of its weight gradient)
+    for i, (name, lin) in enumerate(ins):
+        xin.append(h)
+        w = prepared(ffn, name, prec, (lin.weight,))
+        if i == len(ins) - 1 and not glu:
+            h, z = ops.linear(h, w, lin.bias, prec=prec, act=ffn.act_name, out_dtype=adt, save_pre=True)
+        else:
+            h = ops.linear(h, w, lin.bias, prec=prec, out_dtype=adt)
     h1 = None
-    if ffn.act_name == "glu":      # w_2(F.glu(fc(w_1 x))): LinearGLUBlock (modules/glu.py:11-22), GLU fused in the epilogue
-        h1 = ops.linear(n, w1, ffn.w_1.bias, prec=prec, out_dtype=act_dtype(prec))
+    if glu:
+        h1 = h
         wg = prepared(ffn, "glu_fc", prec, (ffn.activation.fc.weight,))
-        h, z = ops.linear(h1, wg, ffn.activation.fc.bias, prec=prec, glu=True, out_dtype=act_dtype(prec), save_pre=True)
-    else:
-        h, z = ops.linear(n, w1, ffn.w_1.bias, prec=prec, act=ffn.act_name, out_dtype=act_dtype(prec), save_pre=True)
+        h, z = ops.linear(h1, wg, ffn.activation.fc.bias, prec=prec, glu=True, out_dtype=adt, save_pre=True)
     p_h, sid_h = ffn.dropout.p, 0
-    if p_h > 0:                    # w_2(dropout(act(w_1 x)))  (positionwise_feed_forward.py:83)
+    if p_h > 0:                    # dropout(act(.))  (positionwise_feed_forward.py:83)
         sid_h = nrandom.next_stream()
         h = ops.dropout(h, p_h, sid_h, inplace=True)
-    y, sid_r = _drop_out(lambda fused: ops.linear(h, w2, ffn.w_2.bias, prec=prec, residual=x if fused else None,
+    xout = []                                    # xout[i] = input of outs[i]
+    for name, lin in outs[:-1]:
+        xout.append(h)
+        h = ops.linear(h, prepared(ffn, name, prec, (lin.weight,)), lin.bias, prec=prec, out_dtype=adt)
+    xout.append(h)
+    name, lin = outs[-1]
+    wl = prepared(ffn, name, prec, (lin.weight,))
+    y, sid_r = _drop_out(lambda fused: ops.linear(h, wl, lin.bias, prec=prec, residual=x if fused else None,
                                                   alpha=scale if fused else 1.0,
-                                                  out_dtype=torch.float32 if fused else act_dtype(prec)), x, p_res, scale)
-    return y, (x, n, z, h, h1, (p_h, sid_h, p_res, sid_r))
+                                                  out_dtype=torch.float32 if fused else adt), x, p_res, scale)
+    return y, (x, xin, z, h1, xout, (p_h, sid_h, p_res, sid_r))
 
 
 def ffn_bwd(ffn, norm, saved, dy, dyo, scale, prec, G, bias_done=False, nxt=(None, 1.0)):
-    """bias_done: the producer of dy already accumulated w_2.bias' gradient; nxt = (bias param, alpha) of the branch that
-    consumes this function's dx."""
-    x, n, z, h, h1, (p_h, sid_h, p_res, sid_r) = saved
-    dyb, dyo, fused_ok = _drop_grad(dy, dyo, p_res, sid_r, prec)
-    ops.linear_wgrad(dyo, h, prec, G.buf(ffn.w_2.weight), alpha=scale)
-    if not (bias_done and fused_ok):
-        ops.colsum_acc(dyb, G.buf(ffn.w_2.bias), alpha=scale)
-    dh = ops.linear(dyo, _wT(ffn, "w_2", prec, (ffn.w_2.weight,)), None, prec=prec, alpha=scale, out_dtype=act_dtype(prec))
+    """bias_done: the producer of dy already accumulated the last layer's bias gradient; nxt = (bias param, alpha) of the
+    branch that consumes this function's dx."""
+    x, xin, z, h1, xout, (p_h, sid_h, p_res, sid_r) = saved
+    adt = act_dtype(prec)
+    ins, outs = ffn.in_layers, ffn.out_layers
+    dyb, d, fused_ok = _drop_grad(dy, dyo, p_res, sid_r, prec)
+    # output side, last layer first; `alpha` carries the branch scale through the first (= last forward) layer only
+    alpha = scale
+    for i in range(len(outs) - 1, -1, -1):
+        name, lin = outs[i]
+        ops.linear_wgrad(d, xout[i], prec, G.buf(lin.weight), alpha=alpha)
+        if i == len(outs) - 1:
+            if not (bias_done and fused_ok):
+                ops.colsum_acc(dyb, G.buf(lin.bias), alpha=alpha)
+        else:
+            ops.colsum_acc(d, G.buf(lin.bias))
+        d = ops.linear(d, _wT(ffn, name, prec, (lin.weight,)), None, prec=prec, alpha=alpha, out_dtype=adt)
+        alpha = 1.0
+    dh = d
     if p_h > 0:
         dh = ops.dropout(dh, p_h, sid_h, inplace=True)
+    last_in = ins[-1][1]
     if ffn.act_name == "glu":
         fc = ffn.activation.fc
         if _fusable(z) and z.shape[-1] % 32 == 0:
@@ -182,16 +210,21 @@ def ffn_bwd(ffn, norm, saved, dy, dyo, scale, prec, G, bias_done=False, nxt=(Non
             dpre = ops.glu_bwd(dh, z)
             ops.colsum_acc(dpre, G.buf(fc.bias))
         ops.linear_wgrad(dpre, h1, prec, G.buf(fc.weight))
-        dz = ops.linear(dpre, _wT(ffn, "glu_fc", prec, (fc.weight,)), None, prec=prec, out_dtype=act_dtype(prec))
-        ops.colsum_acc(dz, G.buf(ffn.w_1.bias))
+        dz = ops.linear(dpre, _wT(ffn, "glu_fc", prec, (fc.weight,)), None, prec=prec, out_dtype=adt)
+        ops.colsum_acc(dz, G.buf(last_in.bias))
     elif _fusable(z):
-        dz = ops.act_bwd_bias(dh, z, ffn.act_name, G.buf(ffn.w_1.bias))
+        dz = ops.act_bwd_bias(dh, z, ffn.act_name, G.buf(last_in.bias))
     else:
         dz = ops.act_bwd(dh, z, ffn.act_name)
-        ops.colsum_acc(dz, G.buf(ffn.w_1.bias))
-    ops.linear_wgrad(dz, n, prec, G.buf(ffn.w_1.weight))
-    dn = ops.linear(dz, _wT(ffn, "w_1", prec, (ffn.w_1.weight,)), None, prec=prec, out_dtype=torch.float32)
-    return _ln_bwd(norm, dn, x, dy, G, prec, nxt[0], nxt[1])
+        ops.colsum_acc(dz, G.buf(last_in.bias))
+    d = dz
+    for i in range(len(ins) - 1, -1, -1):
+        name, lin = ins[i]
+        if i < len(ins) - 1:
+            ops.colsum_acc(d, G.buf(lin.bias))
+        ops.linear_wgrad(d, xin[i], prec, G.buf(lin.weight))
+        d = ops.linear(d, _wT(ffn, name, prec, (lin.weight,)), None, prec=prec, out_dtype=torch.float32 if i == 0 else adt)
+    return _ln_bwd(norm, d, x, dy, G, prec, nxt[0], nxt[1])
 
 
 def _qkv_weight(attn, prec, transposed=False):
@@ -363,24 +396,24 @@ class _BlockFn(torch.autograd.Function):
         nx = (lambda b, a: (None, 1.0)) if S["p"] > 0 else (lambda b, a: (b, a))
         if getattr(block, "v2", False):
             fc = block.fc_factor
-            dx, dxo = _ln_bwd(block.norm5, dy, S["x5"], None, G, prec, *nx(block.feed_forward.w_2.bias, fc))
+            dx, dxo = _ln_bwd(block.norm5, dy, S["x5"], None, G, prec, *nx(block.feed_forward.out_bias, fc))
             dx, dxo = ffn_bwd(block.feed_forward, block.norm4, S["ff"], dx, dxo, fc, prec, G, bias_done=True,
                               nxt=nx(block.self_attn.w_out.bias, 1.0))
             dx, dxo = attn_bwd(block.self_attn, block.norm3, S["att"], dx, dxo, None, ctx.klens, None, None, ctx.mask_kw,
                                prec, False, G, (None, None), bias_done=True, nxt=nx(block.conv.pointwise_conv2.bias, 1.0))
             dx, dxo = convmod_bwd(block.conv, block.norm2, S["conv"], dx, dxo, prec, G, bias_done=True,
-                                  nxt=nx(block.feed_forward_macaron.w_2.bias, fc))
+                                  nxt=nx(block.feed_forward_macaron.out_bias, fc))
             dx, dxo = ffn_bwd(block.feed_forward_macaron, block.norm1, S["ffm"], dx, dxo, fc, prec, G, bias_done=True)
         elif hasattr(block, "feed_forward_macaron"):
             fc = block.fc_factor
-            dx, dxo = _ln_bwd(block.norm5, dy, S["x5"], None, G, prec, *nx(block.feed_forward.w_2.bias, fc))
+            dx, dxo = _ln_bwd(block.norm5, dy, S["x5"], None, G, prec, *nx(block.feed_forward.out_bias, fc))
             dx, dxo = ffn_bwd(block.feed_forward, block.norm4, S["ff"], dx, dxo, fc, prec, G, bias_done=True,
                               nxt=nx(block.conv.pointwise_conv2.bias, 1.0))
             dx, dxo = convmod_bwd(block.conv, block.norm3, S["conv"], dx, dxo, prec, G, bias_done=True,
                                   nxt=nx(block.self_attn.w_out.bias, 1.0))
             dx, dxo = attn_bwd(block.self_attn, block.norm2, S["att"], dx, dxo, ctx.pos, ctx.klens, u_bias, v_bias,
                                ctx.mask_kw, prec, True, G, ctx.rel_bias, bias_done=True,
-                               nxt=nx(block.feed_forward_macaron.w_2.bias, fc))
+                               nxt=nx(block.feed_forward_macaron.out_bias, fc))
             dx, dxo = ffn_bwd(block.feed_forward_macaron, block.norm1, S["ffm"], dx, dxo, fc, prec, G, bias_done=True)
         else:
             dx, dxo = ffn_bwd(block.feed_forward, block.norm2, S["ff"], dy, _gop(dy, prec), 1.0, prec, G,

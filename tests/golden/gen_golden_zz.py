@@ -33,6 +33,13 @@ ZZ_CASES = {
     "transformer_embed_add": dict(args=dict(enc_type='transformer', pe_type='add', ffn_activation='relu', n_layers=2,
                                             subsample="1_2", lookahead="0_0", n_heads=2, d_model=32, d_ff=64),
                                   conv=None, B=2, T=50, xlens=[50, 44], kind='transformer'),
+    # low-rank feed-forward (ffn_bottleneck_dim > 0: w_1_e / w_1_d / w_2_e / w_2_d), Conformer and Transformer + GLU
+    "conformer_lowrank": dict(args=dict(ffn_bottleneck_dim=16, n_layers=2, subsample="1_1", lookahead="0_0", d_model=32, d_ff=64,
+                                        n_heads=2), conv=dict(poolings="(2,2)_(2,2)"), B=2, T=60, xlens=[60, 47]),
+    "transformer_lowrank_glu": dict(args=dict(enc_type='conv_transformer', pe_type='relative_xl', ffn_activation='glu',
+                                              ffn_bottleneck_dim=24, n_layers=2, subsample="1_1", lookahead="0_0", d_model=32,
+                                              d_ff=64, n_heads=2), conv=dict(poolings="(2,2)_(2,2)"), B=2, T=60, xlens=[60, 47],
+                                    kind='transformer'),
     # GLU feed-forward activation (LinearGLUBlock) + 'drop' subsampling
     "conformer_glu_drop": dict(args=dict(ffn_activation='glu', subsample_type='drop', n_layers=2, subsample="2_1",
                                          lookahead="0_0", d_model=32, d_ff=64, n_heads=2),
