@@ -30,6 +30,11 @@ class ConformerEncoder(TransformerEncoder):
             d_model, d_ff, n_heads, kernel_size, dropout, dropout_att, dropout_layer * (lth + 1) / n_layers,
             layer_norm_eps, ffn_activation, param_init, pe_type, clamp_len, ffn_bottleneck_dim, causal, normalization))
             for lth in range(n_layers)])
+        for sub, nl in (('sub1', n_layers_sub1), ('sub2', n_layers_sub2)):      # reference :93-107
+            if nl > 0 and task_specific_layer:
+                setattr(self, 'layer_' + sub, block(
+                    d_model, d_ff, n_heads, kernel_size, dropout, dropout_att, dropout_layer * nl / n_layers, layer_norm_eps,
+                    ffn_activation, param_init, pe_type, clamp_len, ffn_bottleneck_dim, causal, normalization))
         self.reset_parameters(param_init)
 
 

@@ -99,8 +99,6 @@ class TransformerEncoder(EncoderBase):
         self.n_layers_sub1 = n_layers_sub1
         self.n_layers_sub2 = n_layers_sub2
         self.task_specific_layer = task_specific_layer
-        if task_specific_layer and (n_layers_sub1 > 0 or n_layers_sub2 > 0):
-            raise NotImplementedError("task-specific sub-task layers are not on the B200 path")
         self.bridge = self.bridge_sub1 = self.bridge_sub2 = None
         self.aws_dict, self.data_dict = {}, {}
 
@@ -144,6 +142,10 @@ class TransformerEncoder(EncoderBase):
 
         for sub, nl in (('sub1', n_layers_sub1), ('sub2', n_layers_sub2)):
             if nl > 0:
+                if task_specific_layer:         # one extra block on top of layer `nl` for the sub task (reference :232-238)
+                    setattr(self, 'layer_' + sub, TransformerEncoderBlock(
+                        d_model, d_ff, n_heads, dropout, dropout_att, dropout_layer * nl / n_layers, layer_norm_eps,
+                        ffn_activation, param_init, pe_type, clamp_len, ffn_bottleneck_dim))
                 odim_sub = d_model
                 if last_proj_dim > 0 and last_proj_dim != self.output_dim:
                     setattr(self, 'bridge_' + sub, nn.Linear(self._odim, last_proj_dim))
@@ -215,8 +217,15 @@ class TransformerEncoder(EncoderBase):
             return ag.layernorm(norm, xs)
         return ops.layernorm(xs, norm.weight, norm.bias, norm.eps)
 
-    def _sub_out(self, xs, module, train=False):
-        xs_sub = xs.clone()
+    def _sub_out(self, xs, module, train=False, klens=None, pos=None, mask_kw=None):
+        if self.task_specific_layer:            # reference sub_module (:619-625): the extra block sees no u / v bias
+            layer = getattr(self, 'layer_' + module)
+            if train:
+                xs_sub = self._train_layer(-1, layer, xs, klens, pos, mask_kw, get_precision(self), rel_bias=(None, None))
+            else:
+                xs_sub, _ = layer(xs.clone(), klens, cache=None, pos_embs=pos, rel_bias=(None, None), mask_kw=mask_kw)
+        else:
+            xs_sub = xs.clone()
         bridge = getattr(self, 'bridge_' + module)
         if bridge is not None:
             xs_sub = self._proj('bridge_' + module, bridge, xs_sub, train=train)
@@ -225,7 +234,7 @@ class TransformerEncoder(EncoderBase):
             xs_sub = self._norm(norm, xs_sub, train)
         return xs_sub
 
-    def _train_layer(self, lth, layer, xs, klens, pos, mask_kw, prec):
+    def _train_layer(self, lth, layer, xs, klens, pos, mask_kw, prec, rel_bias=None):
         """One block through its autograd node (training): LayerDrop as in conformer_block.py:122-126."""
         if layer.self_attn.dropout_attn.p > 0:
             raise NotImplementedError("dropout on the attention weights (dropout_att > 0) is not on the B200 path: the "
@@ -235,7 +244,8 @@ class TransformerEncoder(EncoderBase):
             if random.random() < layer.dropout_layer:
                 return xs
             in_scale = 1.0 / (1 - layer.dropout_layer)
-        return ag.block_forward(layer, xs, klens, pos, (self.u_bias, self.v_bias), mask_kw, prec, in_scale)
+        rb = (self.u_bias, self.v_bias) if rel_bias is None else rel_bias
+        return ag.block_forward(layer, xs, klens, pos, rb, mask_kw, prec, in_scale)
 
     def forward(self, xs, xlens, task, streaming=False, lookback=False, lookahead=False):
         """xs `[B, T, input_dim]` fp32 on the GPU; xlens IntTensor `[B]` on the CPU (reference contract).
@@ -339,12 +349,12 @@ class TransformerEncoder(EncoderBase):
                     if streaming and st != 'reshape':                 # 'reshape' windows carry their own context
                         new_cache[lth] = cache
                 if lth == self.n_layers_sub1 - 1:
-                    xs_sub1, xlens_sub1 = self._sub_out(xs, 'sub1', train), xlens.clone()
+                    xs_sub1, xlens_sub1 = self._sub_out(xs, 'sub1', train, klens, pos, mask_kw(lth)), xlens.clone()
                     if task == 'ys_sub1':
                         eouts[task]['xs'], eouts[task]['xlens'] = xs_sub1, xlens_sub1
                         return eouts
                 if lth == self.n_layers_sub2 - 1:
-                    xs_sub2, xlens_sub2 = self._sub_out(xs, 'sub2', train), xlens.clone()
+                    xs_sub2, xlens_sub2 = self._sub_out(xs, 'sub2', train, klens, pos, mask_kw(lth)), xlens.clone()
                     if task == 'ys_sub2':
                         eouts[task]['xs'], eouts[task]['xlens'] = xs_sub2, xlens_sub2
                         return eouts

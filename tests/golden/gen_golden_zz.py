@@ -40,6 +40,10 @@ ZZ_CASES = {
                                               ffn_bottleneck_dim=24, n_layers=2, subsample="1_1", lookahead="0_0", d_model=32,
                                               d_ff=64, n_heads=2), conv=dict(poolings="(2,2)_(2,2)"), B=2, T=60, xlens=[60, 47],
                                     kind='transformer'),
+    # task-specific extra block on the sub-task output (sub_module, transformer.py:619-631) + bridge + sub-task LayerNorm
+    "conformer_task_specific": dict(args=dict(n_layers=3, n_layers_sub1=2, task_specific_layer=True, subsample="1_2_1",
+                                              d_model=32, d_ff=64, n_heads=2, last_proj_dim=24),
+                                    conv=dict(poolings="(2,2)_(2,2)"), B=2, T=60, xlens=[60, 47]),
     # GLU feed-forward activation (LinearGLUBlock) + 'drop' subsampling
     "conformer_glu_drop": dict(args=dict(ffn_activation='glu', subsample_type='drop', n_layers=2, subsample="2_1",
                                          lookahead="0_0", d_model=32, d_ff=64, n_heads=2),
@@ -77,9 +81,15 @@ def main():
                     xlens_out=out['ys']['xlens'].numpy().astype(np.int32))
         cfg = {k: v for k, v in args.items() if k != "frontend_conv"}
         save["cfg"] = np.array(json.dumps(dict(args=cfg, conv=conv_args, kind=kind)))
+        if out['ys_sub1']['xs'] is not None:
+            save["ys_sub1"] = out['ys_sub1']['xs'].detach().numpy()
         np.savez_compressed(os.path.join(HERE, "zz_" + name + ".npz"), **save)
         w = torch.from_numpy(G.grad_loss_weights(tuple(ys.shape), out['ys']['xlens'].tolist()))
         loss = (ys * w).sum()
+        if out['ys_sub1']['xs'] is not None:      # sub-task output: stored and part of the loss (weights seeded 99)
+            s1 = out['ys_sub1']['xs']
+            loss = loss + (s1 * torch.from_numpy(G.grad_loss_weights(tuple(s1.shape), out['ys_sub1']['xlens'].tolist(),
+                                                                      seed=99))).sum()
         loss.backward()
         gsave = {"g." + k: p.grad.numpy() for k, p in enc.named_parameters() if p.grad is not None}
         gsave["loss"] = np.array(float(loss.detach()), np.float32)

@@ -39,6 +39,10 @@ def test_block_training_wiring_matches_reference_gradients(case, monkeypatch):
     assert out["ys"]["xlens"].tolist() == g["xlens_out"].tolist()
     assert float((ys.detach() - torch.from_numpy(g["ys"])).abs().max()) <= 1e-4 * float(np.abs(g["ys"]).max())
     loss = (ys * torch.from_numpy(_loss_weights(tuple(ys.shape), out["ys"]["xlens"].tolist()))).sum()
+    if "ys_sub1" in g.files and case.startswith("zz_"):
+        s1 = out["ys_sub1"]["xs"]
+        assert float((s1.detach() - torch.from_numpy(g["ys_sub1"])).abs().max()) <= 1e-4 * float(np.abs(g["ys_sub1"]).max())
+        loss = loss + (s1 * torch.from_numpy(_loss_weights(tuple(s1.shape), out["ys_sub1"]["xlens"].tolist(), seed=99))).sum()
     assert abs(float(loss.detach()) - float(gg["loss"])) <= 1e-3 * max(1.0, abs(float(gg["loss"])))
     loss.backward()
     gmax = max(float(np.abs(gg[k]).max()) for k in gg.files if k.startswith("g."))

@@ -41,6 +41,9 @@ def test_encoder_matches_reference(name, precision):
     else:
         err = max(np.abs(got[b, :n] - ref[b, :n]).max() for b, n in enumerate(ylens.tolist())) / np.abs(ref).max()
     assert err <= TOL[precision], (name, precision, err)
+    if "ys_sub1" in g.files:
+        s1 = out["ys_sub1"]["xs"].float().cpu().numpy()
+        assert np.abs(s1 - g["ys_sub1"]).max() / np.abs(g["ys_sub1"]).max() <= TOL[precision] * 2
 
 
 @pytest.mark.parametrize("precision,tol", [("fp32", 2e-3), ("bf16", 2e-1)])
@@ -56,6 +59,9 @@ def test_encoder_param_grads_match_reference(name, precision, tol):
     assert ys.requires_grad
     w = torch.from_numpy(_loss_weights(tuple(ys.shape), out["ys"]["xlens"].tolist())).to(dev)
     loss = (ys * w).sum()
+    if "ys_sub1" in g.files:
+        s1 = out["ys_sub1"]["xs"]
+        loss = loss + (s1 * torch.from_numpy(_loss_weights(tuple(s1.shape), out["ys_sub1"]["xlens"].tolist(), seed=99)).to(dev)).sum()
     loss.backward()
     gmax = max(float(np.abs(gg[k]).max()) for k in gg.files if k.startswith("g."))
     bad = []
