@@ -7,7 +7,9 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnsp_b200.so")
+# NSP_LIB_PATH selects another build of the SAME library (e.g. libnsp_b200_dbg.so, `make -C neural_sp_b200/csrc debug`:
+# bounded mbarrier waits for kernel bring-up); it is not a fallback mechanism -- a missing file still raises.
+LIB_PATH = os.environ.get("NSP_LIB_PATH") or os.path.join(_HERE, "libnsp_b200.so")
 
 
 class NspError(RuntimeError):

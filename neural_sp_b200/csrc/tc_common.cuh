@@ -36,8 +36,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+// Build with `make EXTRA=-DNSP_BOUNDED_WAITS` while bringing a tcgen05 kernel up on new shapes: a lost arrival then traps
+// with a message after ~2 s instead of hanging the GPU (a hang costs a `gpurun` strike).  The default build keeps the bare
+// spin loop of the validated kernels (no printf stack frame in the hot kernels).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef NSP_BOUNDED_WAITS
+    if (mbar_try_wait(bar, parity)) return;
+    const long long deadline = clock64() + 4000000000LL;
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() > deadline) {
+            printf("mbarrier wait timed out (block %d thread %d, smem 0x%x, parity %u)\n", blockIdx.x, threadIdx.x,
+                   smem_u32(bar), parity);
+            __trap();
+        }
+    }
+#else
     while (!mbar_try_wait(bar, parity)) {}
+#endif
 }
 
 // ---------------- TMA ----------------

@@ -16,10 +16,14 @@ stage() {            # stage <name> <seconds> <command...>
 stage zz_tests 600 python -m pytest tests -m gpu -q -k zz --timeout=120 -p no:cacheprovider
 # 2. the already-validated suite (the restructured forward paths run through it)
 stage validated_suite 900 python -m pytest tests -m gpu -q -k "not zz" --timeout=300 -p no:cacheprovider
-# 3. opt-in size classes / kernels, riskiest last (bounded mbarrier waits: a protocol bug traps instead of hanging)
+# 3. opt-in size classes / kernels, riskiest last, on the bring-up build (bounded mbarrier waits in EVERY tcgen05 kernel: a
+#    protocol bug traps with a message instead of hanging the GPU)
+[ -f neural_sp_b200/libnsp_b200_dbg.so ] || stage build_dbg 400 make -C neural_sp_b200/csrc debug -j 32
+export NSP_LIB_PATH=$PWD/neural_sp_b200/libnsp_b200_dbg.so
 stage experimental_stream_bf16 300 env NSP_EXPERIMENTAL=1 python -m pytest tests/test_zz_streaming_gpu.py -q -k "bf16" --timeout=120
 stage gemm_tma_epilogue 300 env NSP_EXPERIMENTAL=1 python -m pytest tests/test_gemm_tma_epilogue_gpu.py -q --timeout=60 -k "not cta_pairs"
 stage gemm_cta_pairs 300 env NSP_EXPERIMENTAL=1 python -m pytest tests/test_gemm_tma_epilogue_gpu.py -q --timeout=60 -k "cta_pairs"
+unset NSP_LIB_PATH
 # 4. bench lines: default, recipe dropout, the two opt-in GEMM epilogue modes
 stage bench_default 600 python bench.py --steps 10 --warmup 3
 stage bench_dropout 400 python bench.py --steps 10 --warmup 3 --dropout 0.1 --no-cpu-baseline
