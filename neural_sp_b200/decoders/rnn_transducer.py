@@ -10,7 +10,6 @@ back-propagates into the encoder output, the prediction network and the embeddin
 scatter-add is torch's (data movement).  Beam search (:419-819) is out of scope."""
 import copy
 
-import numpy as np
 import torch
 import torch.nn as nn
 

@@ -4,8 +4,6 @@ Same constructor, ``forward(xs, xlens, lookback, lookahead) -> (xs, xlens)`` and
 (``layers.N.conv1/conv2.{weight,bias}``, ``bridge.{weight,bias}``).  Activations are channels-last
 ``[B, T, F, C]`` on the device; the reference's final flatten order (``c * F' + f``, conv.py:189) is
 produced by the last pooling kernel (or folded into the bridge weight's column order)."""
-import math
-
 import numpy as np
 import torch
 import torch.nn as nn
