@@ -73,7 +73,9 @@ class ConformerEncoderBlock(nn.Module):
         h = _ln(self.norm2, xs, prec)
         kv = h if cache is None else torch.cat([cache['input_san'].to(h.dtype), h], dim=1)
         new_cache['input_san'] = kv
-        xs = self.self_attn(kv, h, pos_embs, klens, u_bias, v_bias, residual=xs, out=xs, **mask_kw)
+        kvc = cache.get('_kv') if cache is not None else None      # K / V projected in earlier chunks (ours, not the reference's)
+        xs, new_cache['_kv'] = self.self_attn(kv, h, pos_embs, klens, u_bias, v_bias, residual=xs, out=xs, kv_cache=kvc,
+                                              return_kv=True, **mask_kw)
         c_in = _ln(self.norm3, xs, prec)
         if cache is not None:               # left context of the depthwise convolution, restricted to the kernel size
             c_in = torch.cat([cache['input_conv'].to(c_in.dtype), c_in], dim=1)

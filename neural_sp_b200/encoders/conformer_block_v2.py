@@ -72,7 +72,8 @@ class ConformerEncoderBlock_v2(nn.Module):
         h = _ln(self.norm3, xs, prec)
         kv = h if cache is None else torch.cat([cache['input_san'].to(h.dtype), h], dim=1)
         new_cache['input_san'] = kv
-        xs = self.self_attn(kv, h, klens, residual=xs, out=xs, **mask_kw)
+        kvc = cache.get('_kv') if cache is not None else None      # K / V projected in earlier chunks (ours, not the reference's)
+        xs, new_cache['_kv'] = self.self_attn(kv, h, klens, residual=xs, out=xs, kv_cache=kvc, return_kv=True, **mask_kw)
         xs = self.feed_forward(_ln(self.norm4, xs, prec), residual=xs, scale=self.fc_factor, out=xs)
         xs = ops.layernorm(xs, self.norm5.weight, self.norm5.bias, self.norm5.eps)
         return xs, new_cache

@@ -8,7 +8,9 @@ Supported here: offline full-context, unidirectional ('uni', per-layer lookahead
 ('reshape' overlapped windows / 'mask' chunk-wise visibility) encoders with all six hierarchical subsamplers and
 sub-task outputs, and chunk-by-chunk streaming inference (``streaming=True``, :448-606): per-layer caches of the
 normalised attention input (and of the Conformer conv-module input) are carried in ``self.cache`` exactly like the
-reference's -- same keys, same truncation to ``cache_sizes`` -- and the attention kernel sees the cached frames as
+reference's -- same keys, same truncation to ``cache_sizes``; one private extra entry ``_kv`` holds the already PROJECTED
+keys / values of the cached frames, so a chunk costs O(chunk) GEMM work instead of re-projecting the whole cache as the
+reference does -- and the attention kernel sees the cached frames as
 `mlen = klen - qlen` extra keys (query i sits at key position mlen + i for the causal / chunk masks and the relative
 distance), so nothing of the `[B, qlen, klen]` mask or the shifted position matrix is ever materialised."""
 import copy
@@ -182,6 +184,8 @@ class TransformerEncoder(EncoderBase):
                 san = cache[lth]['input_san']
                 if san.size(1) > size:
                     cache[lth]['input_san'] = san[:, san.size(1) - size:]
+                    if '_kv' in cache[lth]:     # the projected keys / values of the same frames (kept next to input_san)
+                        cache[lth]['_kv'] = tuple(t[:, t.size(1) - size:] for t in cache[lth]['_kv'])
         return cache
 
     def calculate_cache_size(self):

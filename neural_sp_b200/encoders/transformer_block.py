@@ -56,9 +56,11 @@ class TransformerEncoderBlock(nn.Module):
         h = _ln(self.norm1, xs, prec)
         kv = h if cache is None else torch.cat([cache['input_san'].to(h.dtype), h], dim=1)
         new_cache['input_san'] = kv
+        kvc = cache.get('_kv') if cache is not None else None      # K / V projected in earlier chunks (ours, not the reference's)
         if self.rel_attn:
-            xs = self.self_attn(kv, h, pos_embs, klens, rel_bias[0], rel_bias[1], residual=xs, out=xs, **mask_kw)
+            xs, new_cache['_kv'] = self.self_attn(kv, h, pos_embs, klens, rel_bias[0], rel_bias[1], residual=xs, out=xs,
+                                                  kv_cache=kvc, return_kv=True, **mask_kw)
         else:
-            xs = self.self_attn(kv, h, klens, residual=xs, out=xs, **mask_kw)
+            xs, new_cache['_kv'] = self.self_attn(kv, h, klens, residual=xs, out=xs, kv_cache=kvc, return_kv=True, **mask_kw)
         xs = self.feed_forward(_ln(self.norm2, xs, prec), residual=xs, scale=1.0, out=xs)
         return xs, new_cache

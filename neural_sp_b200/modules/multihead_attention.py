@@ -39,7 +39,9 @@ class MultiheadAttentionMechanism(nn.Module):
         self.value = None
         self.mask = None
 
-    def forward(self, key, query, klens, residual=None, out=None, causal=False, lookahead=0, chunk_c=0, chunk_l=0):
+    def forward(self, key, query, klens, residual=None, out=None, causal=False, lookahead=0, chunk_c=0, chunk_l=0,
+                kv_cache=None, return_kv=False):
+        """Streaming: kv_cache = (K, V) projected in earlier chunks, return_kv -> (out, (K, V)); see RelMHA.forward."""
         prec = get_precision(self)
         B, klen, _ = key.shape
         qlen = query.shape[1]
@@ -49,11 +51,20 @@ class MultiheadAttentionMechanism(nn.Module):
         bias = None
         if self.w_key.bias is not None:
             bias = torch.cat([self.w_query.bias, self.w_key.bias, self.w_value.bias]).detach()
-        qkv = ops.linear(key, wqkv, bias, prec=prec, out_dtype=act_dtype(prec))
-        q = qkv[:, klen - qlen:, :D]
-        if klen != qlen:
-            q = q.contiguous()
-        cv = ops.relpos_attention(q, qkv[:, :, D:2 * D], qkv[:, :, 2 * D:], klens, self.n_heads, r=None,
+        if kv_cache is not None:
+            assert kv_cache[0].size(1) == klen - qlen
+            qkv = ops.linear(query, wqkv, bias, prec=prec, out_dtype=act_dtype(prec))
+            q = qkv[:, :, :D].contiguous()
+            k = torch.cat([kv_cache[0], qkv[:, :, D:2 * D]], dim=1)
+            v = torch.cat([kv_cache[1], qkv[:, :, 2 * D:]], dim=1)
+        else:
+            qkv = ops.linear(key, wqkv, bias, prec=prec, out_dtype=act_dtype(prec))
+            q = qkv[:, klen - qlen:, :D]
+            if klen != qlen:
+                q = q.contiguous()
+            k, v = qkv[:, :, D:2 * D], qkv[:, :, 2 * D:]
+        cv = ops.relpos_attention(q, k, v, klens, self.n_heads, r=None,
                                   causal=causal, lookahead=lookahead, chunk_c=chunk_c, chunk_l=chunk_l)
         wo = prepared(self, "w_out", prec, (self.w_out.weight,))
-        return ops.linear(cv, wo, self.w_out.bias, prec=prec, residual=residual, out_dtype=torch.float32, out=out)
+        y = ops.linear(cv, wo, self.w_out.bias, prec=prec, residual=residual, out_dtype=torch.float32, out=out)
+        return (y, (k, v)) if return_kv else y

@@ -50,21 +50,31 @@ class RelativeMultiheadAttentionMechanism(nn.Module):
         return torch.cat([self.w_query.bias, self.w_key.bias, self.w_value.bias]).detach()
 
     def forward(self, key, query, pos_embs, klens, u_bias=None, v_bias=None, residual=None, out=None,
-                causal=False, lookahead=0, chunk_c=0, chunk_l=0):
+                causal=False, lookahead=0, chunk_c=0, chunk_l=0, kv_cache=None, return_kv=False):
         """key `[B, mlen+qlen, d]` normalised input (bf16/fp32 by precision); query is its last qlen frames.
         pos_embs `[>=klen, d]` fp32 sinusoid table (row = distance).  klens int32 `[B]` on the GPU.
-        Returns ``residual + w_out(attention)`` (fp32) -- the attention weights are never materialised."""
+        Returns ``residual + w_out(attention)`` (fp32) -- the attention weights are never materialised.
+        Streaming: kv_cache = (K, V) `[B, mlen, D]` projected in earlier chunks -- then only the qlen new frames go through
+        the QKV GEMM (the reference re-projects the whole cache every chunk, :169-171; row-wise the result is identical);
+        return_kv -> (out, (K, V)) with this chunk's rows appended."""
         prec = get_precision(self)
         B, klen, _ = key.shape
         qlen = query.shape[1]
         D = self.n_heads * self.d_k
         wqkv = prepared(self, "qkv", prec, (self.w_query.weight, self.w_key.weight, self.w_value.weight),
                         build=lambda q, k, v: torch.cat([q, k, v], dim=0))
-        qkv = ops.linear(key, wqkv, self._qkv_bias(), prec=prec, out_dtype=act_dtype(prec))     # `[B, klen, 3D]`
-        q = qkv[:, klen - qlen:, :D]
-        if klen != qlen:
-            q = q.contiguous()
-        k, v = qkv[:, :, D:2 * D], qkv[:, :, 2 * D:]
+        if kv_cache is not None:
+            assert kv_cache[0].size(1) == klen - qlen
+            qkv = ops.linear(query, wqkv, self._qkv_bias(), prec=prec, out_dtype=act_dtype(prec))   # `[B, qlen, 3D]`
+            q = qkv[:, :, :D].contiguous()
+            k = torch.cat([kv_cache[0], qkv[:, :, D:2 * D]], dim=1)
+            v = torch.cat([kv_cache[1], qkv[:, :, 2 * D:]], dim=1)
+        else:
+            qkv = ops.linear(key, wqkv, self._qkv_bias(), prec=prec, out_dtype=act_dtype(prec))     # `[B, klen, 3D]`
+            q = qkv[:, klen - qlen:, :D]
+            if klen != qlen:
+                q = q.contiguous()
+            k, v = qkv[:, :, D:2 * D], qkv[:, :, 2 * D:]
         # projected position table; only distances 0..clamp_len are ever gathered when clamp_len > 0.
         # The sinusoid rows are constants, so R depends only on the projection weight: cached per weight version.
         nrows = min(klen, self.clamp_len + 1) if self.clamp_len > 0 else klen
@@ -81,4 +91,5 @@ class RelativeMultiheadAttentionMechanism(nn.Module):
                                   clamp_len=self.clamp_len, causal=causal, lookahead=lookahead,
                                   chunk_c=chunk_c, chunk_l=chunk_l)
         wo = prepared(self, "w_out", prec, (self.w_out.weight,))
-        return ops.linear(cv, wo, self.w_out.bias, prec=prec, residual=residual, out_dtype=torch.float32, out=out)
+        y = ops.linear(cv, wo, self.w_out.bias, prec=prec, residual=residual, out_dtype=torch.float32, out=out)
+        return (y, (k, v)) if return_kv else y

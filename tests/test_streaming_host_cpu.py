@@ -196,7 +196,9 @@ def test_streaming_chunks_match_reference_and_offline(ov, ov_conv, monkeypatch):
                     rc, oc = ref.cache[lth], ours.cache[lth]
                     assert (rc is None) == (oc is None)
                     if rc is not None:
-                        assert sorted(rc) == sorted(oc)
+                        assert sorted(rc) == sorted(k for k in oc if not k.startswith('_'))     # '_kv': ours only
+                        n_frames = rc['input_san'].size(1)
+                        assert all(t.size(1) == n_frames for t in oc['_kv'])
                         for key in rc:
                             assert rc[key].shape == oc[key].shape, (lth, key, rc[key].shape, oc[key].shape)
                             assert torch.allclose(rc[key], oc[key].float(), atol=atol)
