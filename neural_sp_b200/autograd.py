@@ -820,7 +820,7 @@ def frontend_forward(enc, xs, out_scale, prec):
     for blk in enc.layers:
         if blk.training and blk.dropout.p > 0:
             raise NotImplementedError("dropout > 0 in training mode is not on the B200 path yet")
-        if blk.residual and blk.conv1.in_channels == blk.conv2.out_channels:
-            raise NotImplementedError("residual CNN blocks are not on the B200 path")
+        if not blk.plain:
+            raise NotImplementedError("training path of the CNN front-end: stride (1,1), no normalisation, no residual only")
     params = [p for p in enc.parameters()]
     return _FrontendFn.apply(xs, enc, float(out_scale), prec, *params)

@@ -79,6 +79,28 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     }
 }
 
+// Any D (rows wider than the register-resident kernel takes, e.g. LayerNorm2D over [C, F] = 2560 of the CNN front-end,
+// encoders/conv.py:399-421): one CTA per row, two-pass statistics like the fast kernel, the row is re-read from L1 / L2.
+__global__ void __launch_bounds__(256) layernorm_generic_kernel(const float* __restrict__ x, int64_t ldx,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                float eps, float in_scale, float* __restrict__ y, int64_t ldy,
+                                                                __nv_bfloat16* __restrict__ yb, int64_t ldyb, int D) {
+    __shared__ float scratch[32];
+    const int64_t row = blockIdx.x;
+    const float* xr = x + row * ldx;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < D; i += 256) s += xr[i] * in_scale;
+    const float mean = block_sum<256>(s, scratch) / (float)D;
+    float q = 0.f;
+    for (int i = threadIdx.x; i < D; i += 256) { const float d = xr[i] * in_scale - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(block_sum<256>(q, scratch) / (float)D + eps);
+    for (int i = threadIdx.x; i < D; i += 256) {
+        const float o = (xr[i] * in_scale - mean) * rstd * __ldg(gamma + i) + __ldg(beta + i);
+        if (y) y[row * ldy + i] = o;
+        if (yb) yb[row * ldyb + i] = __float2bfloat16_rn(o);
+    }
+}
+
 }  // namespace
 }  // namespace nsp
 
@@ -100,12 +122,12 @@ extern "C" nsp_status nsp_layernorm_fwd(const float* x, int64_t ldx, const float
         const int vpt = ceil_div(D / 4, 32);
         if (vpt <= 1) NSP_LN(1, 4); else if (vpt <= 2) NSP_LN(2, 4); else if (vpt <= 4) NSP_LN(4, 4);
         else if (vpt <= 8) NSP_LN(8, 4); else if (vpt <= 16) NSP_LN(16, 4);
-        else { set_error("layernorm: D=%d too large (max 2048)", D); return NSP_ERR_UNSUPPORTED; }
+        else layernorm_generic_kernel<<<(unsigned)M, 256, 0, st>>>(x, ldx, gamma, beta, eps, in_scale, y, ldy, yb, ldyb, D);
     } else {
         const int vpt = ceil_div(D, 32);
         if (vpt <= 1) NSP_LN(1, 1); else if (vpt <= 2) NSP_LN(2, 1); else if (vpt <= 4) NSP_LN(4, 1);
         else if (vpt <= 8) NSP_LN(8, 1); else if (vpt <= 16) NSP_LN(16, 1); else if (vpt <= 32) NSP_LN(32, 1);
-        else { set_error("layernorm: unaligned D=%d too large (max 1024)", D); return NSP_ERR_UNSUPPORTED; }
+        else layernorm_generic_kernel<<<(unsigned)M, 256, 0, st>>>(x, ldx, gamma, beta, eps, in_scale, y, ldy, yb, ldyb, D);
     }
 #undef NSP_LN
     NSP_LAUNCH_OK();

@@ -9,7 +9,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ..modules._prep import prepared, get_precision, act_dtype
+from ..modules._prep import prepared, cached, get_precision, act_dtype
 from ..modules.initialization import init_with_lecun_normal
 from .encoder_base import EncoderBase
 
@@ -34,23 +34,42 @@ def _pool_len(n, k):            # ceil-mode pool, kernel = stride = k      (conv
     return (n + 1 - k) // k + 1
 
 
+class LayerNorm2D(nn.Module):
+    """Layer normalisation over (channel, frequency) of every frame (reference conv.py:399-421); parameter ``norm.weight
+    [C, F]`` as in the reference.  On channels-last activations it is a LayerNorm over the F*C contiguous values of a frame with
+    the affine parameters permuted to (f, c) order."""
+
+    def __init__(self, channel, idim, eps=1e-12):
+        super().__init__()
+        self.norm = nn.LayerNorm([channel, idim], eps=eps)
+
+
 class Conv2dBlock(EncoderBase):
-    """conv3x3 -> ReLU -> conv3x3 -> ReLU -> max-pool (reference conv.py:289-396)."""
+    """conv3x3 -> [norm] -> ReLU -> conv3x3(stride) -> [norm] -> [+ residual] -> ReLU -> max-pool (reference conv.py:289-396).
+
+    The recipes' shape (stride 1, no normalisation, no residual) runs on the fused kernels (tcgen05 implicit GEMM with ReLU /
+    2x2 pooling in the epilogue in bf16 mode) and has a training path.  The general shape is inference-only and composed from
+    the same conv kernel: a strided 'same' 3x3 conv is the stride-1 conv sampled every s-th position; BatchNorm2d (eval) is
+    folded into the conv's weight and bias; LayerNorm2D is the library's LayerNorm over a frame's F*C values; the residual add
+    and the un-fused ReLU are elementwise kernels."""
 
     def __init__(self, input_dim, in_channel, out_channel, kernel_size, stride, pooling, dropout, normalization,
                  residual):
         super().__init__()
-        if tuple(kernel_size) != (3, 3) or tuple(stride) != (1, 1):
-            raise NotImplementedError("B200 front-end supports 3x3 kernels with stride (1,1) (all reference recipes)")
-        if normalization:
-            raise NotImplementedError("conv_normalization=%r is not on the B200 path" % normalization)
+        if tuple(kernel_size) != (3, 3):
+            raise NotImplementedError("B200 front-end supports 3x3 kernels (all reference recipes)")
+        if normalization not in ('', 'batch_norm', 'layer_norm'):
+            raise NotImplementedError("conv_normalization=%r" % normalization)
         self.residual = residual
         self.dropout = nn.Dropout(p=dropout)
         self.time_axis = 0
+        self.stride = tuple(stride)
         self.conv1 = nn.Conv2d(in_channel, out_channel, kernel_size=tuple(kernel_size), stride=(1, 1), padding=(1, 1))
-        self.conv2 = nn.Conv2d(out_channel, out_channel, kernel_size=tuple(kernel_size), stride=tuple(stride), padding=(1, 1))
-        self.norm1 = self.norm2 = None
         self._odim = input_dim
+        self.norm1 = self._make_norm(normalization, out_channel, self._odim)
+        self.conv2 = nn.Conv2d(out_channel, out_channel, kernel_size=tuple(kernel_size), stride=tuple(stride), padding=(1, 1))
+        self._odim = _conv_len(self._odim, self.stride[1])
+        self.norm2 = self._make_norm(normalization, out_channel, self._odim)
         self.pooling = [1, 1]
         self._factor = 1
         if len(pooling) > 0 and np.prod(pooling) > 1:
@@ -60,20 +79,30 @@ class Conv2dBlock(EncoderBase):
                 self._odim = (self._odim // 2) * 2
             self._factor *= pooling[0]
         self.pool = self.pooling if self._factor > 1 or self.pooling[1] > 1 else None
+        # the recipes' shape: fused kernels + training path
+        self.plain = self.norm1 is None and self.stride == (1, 1) and not (residual and in_channel == out_channel)
+
+    @staticmethod
+    def _make_norm(normalization, channel, idim):
+        if normalization == 'batch_norm':
+            return nn.BatchNorm2d(channel)
+        if normalization == 'layer_norm':
+            return LayerNorm2D(channel, idim, eps=1e-12)
+        return None
 
     def forward(self, xs, xlens, B, T, F, first, last_chmajor, lookback=False, lookahead=False):
         """xs: raw features (first block) or channels-last `[B, T, F, C]`.  Returns (xs, xlens, T', F').
 
         lookback / lookahead (streaming, reference conv.py:368-374, :385-390): after each of the two convolutions the
-        leftmost / rightmost `stride` (= 1) output frames -- the ones computed from zero padding instead of real
-        neighbouring context -- are dropped, so a chunk fed with `context_size` extra frames on a side reproduces the
-        offline activations exactly."""
+        leftmost / rightmost `stride` output frames -- the ones computed from zero padding instead of real neighbouring
+        context -- are dropped, so a chunk fed with `context_size` extra frames on a side reproduces the offline
+        activations exactly."""
         if self.training and self.dropout.p > 0:
-            raise NotImplementedError("dropout > 0 in training mode is not on the B200 path yet")
+            raise NotImplementedError("dropout > 0 in the CNN front-end is not on the B200 path (build_encoder passes 0)")
+        if not self.plain:
+            return self._forward_general(xs, xlens, B, T, F, first, last_chmajor, lookback, lookahead)
         prec = get_precision(self)
         adt = act_dtype(prec)
-        if self.residual and self.conv1.in_channels == self.conv2.out_channels:
-            raise NotImplementedError("residual CNN blocks are not on the B200 path")
         pt, pf = self.pooling if self.pool is not None else (1, 1)
         trim = lookback or lookahead
 
@@ -106,6 +135,65 @@ class Conv2dBlock(EncoderBase):
         if self.pool is not None:
             if not pooled:
                 xs = ops.maxpool2d(xs, pt, pf, out_chmajor=last_chmajor)
+            xlens = torch.IntTensor([_pool_len(int(n), pt) for n in xlens])
+            T, F = -(-T // pt), -(-F // pf)
+        elif last_chmajor:
+            xs = ops.maxpool2d(xs, 1, 1, out_chmajor=True)
+        return xs, xlens, T, F
+
+    def _folded(self, name, conv, norm):
+        """(weight, bias) of `conv`, with an eval-mode BatchNorm2d folded in: w' = w g / sigma, b' = (b - mu) g / sigma + beta."""
+        if not isinstance(norm, nn.BatchNorm2d):
+            return conv.weight, conv.bias
+        if self.training:
+            raise NotImplementedError("BatchNorm statistics updates (training mode) are not on the B200 path")
+
+        def build(w, b, g, beta, mu, var):
+            sc = g / torch.sqrt(var + norm.eps)
+            return (w * sc.view(-1, 1, 1, 1)).contiguous(), ((b - mu) * sc + beta).contiguous()
+        return cached(self, name + ".bnfold", (conv.weight, conv.bias, norm.weight, norm.bias, norm.running_mean,
+                                               norm.running_var), build)
+
+    def _forward_general(self, xs, xlens, B, T, F, first, last_chmajor, lookback, lookahead):
+        """Strided / normalised / residual blocks (inference), fp32 channels-last activations."""
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError("training path of the CNN front-end: stride (1,1), no normalisation, no residual only")
+        pt, pf = self.pooling if self.pool is not None else (1, 1)
+        res = None
+        if self.residual and first and self.conv1.in_channels == self.conv2.out_channels:
+            raise NotImplementedError("residual connection around the first CNN block (raw feature layout)")
+        if self.residual and not first and self.conv1.in_channels == self.conv2.out_channels and self.stride == (1, 1):
+            res = xs.reshape(B, T, F, -1).float().contiguous()       # same shape as the block's conv output (conv.py:379)
+
+        def stage(name, conv, norm, x, first_layer, stride, residual_t, lens):
+            nonlocal T, F
+            w, b = self._folded(name, conv, norm)
+            ln = isinstance(norm, LayerNorm2D)
+            fuse_relu = not ln and residual_t is None
+            y = ops.conv3x3_relu(x, w, b, B, T, F, in_chmajor=first_layer, relu=fuse_relu, out_dtype=torch.float32)
+            lens = torch.IntTensor([_conv_len(int(n), stride[0]) for n in lens])
+            if stride != (1, 1):                                     # 'same' 3x3 conv with stride s = stride-1 conv at 0, s, 2s, ...
+                y = y[:, ::stride[0], ::stride[1]].contiguous()
+                T, F = y.size(1), y.size(2)
+            for flag, side in ((lookback, 0), (lookahead, 1)):       # streaming context trimming (conv.py:368-374, :385-390)
+                if flag and T > stride[0]:
+                    y = (y[:, stride[0]:] if side == 0 else y[:, :T - stride[0]]).contiguous()
+                    T, lens = T - stride[0], lens - stride[0]
+            if ln:
+                gam = cached(self, name + ".ln_w", (norm.norm.weight,), lambda t: t.t().contiguous().reshape(-1).float())
+                bet = cached(self, name + ".ln_b", (norm.norm.bias,), lambda t: t.t().contiguous().reshape(-1).float())
+                y = ops.layernorm(y.view(B * T, -1), gam, bet, norm.norm.eps).view(B, T, F, -1)
+            if residual_t is not None and residual_t.shape == y.shape:
+                y = ops.dropout_add(y, residual_t, 0.0, 1.0, 0)      # p = 0: plain out = residual + y
+            if not fuse_relu:
+                y = ops.relu_mask(y, y)                              # relu(y) = (y > 0 ? y : 0)
+            return y, lens
+
+        xs, xlens = stage("conv1", self.conv1, self.norm1, xs if first else xs.reshape(B, T, F, -1).float().contiguous(),
+                          first, (1, 1), None, xlens)
+        xs, xlens = stage("conv2", self.conv2, self.norm2, xs, False, self.stride, res, xlens)
+        if self.pool is not None:
+            xs = ops.maxpool2d(xs, pt, pf, out_chmajor=last_chmajor)
             xlens = torch.IntTensor([_pool_len(int(n), pt) for n in xlens])
             T, F = -(-T // pt), -(-F // pf)
         elif last_chmajor:
@@ -171,6 +259,8 @@ class ConvEncoder(EncoderBase):
     def output_lens(self, xlens):
         """Length arithmetic of the block stack alone (reference conv.py:451-477), for the training path."""
         for block in self.layers:
+            if not block.plain:
+                raise NotImplementedError("training path of the CNN front-end: stride (1,1), no normalisation, no residual only")
             xlens = torch.IntTensor([_conv_len(_conv_len(int(n), 1), 1) for n in xlens])
             if block.pool is not None:
                 xlens = torch.IntTensor([_pool_len(int(n), block.pooling[0]) for n in xlens])

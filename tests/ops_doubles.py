@@ -294,6 +294,8 @@ def install(monkeypatch):
     from neural_sp_b200 import ops
     for name, fn in DOUBLES.items():
         monkeypatch.setattr(ops, name, fn)
+    for name in ("relu_mask", "dropout", "dropout_add"):          # elementwise pieces the general CNN block reuses in inference
+        monkeypatch.setattr(ops, name, globals()[name])
 
 
 # ---------------------------------------------------------------------------------------------

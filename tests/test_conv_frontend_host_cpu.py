@@ -1,0 +1,78 @@
+"""CNN front-end (ConvEncoder / Conv2dBlock, reference conv.py:18-396) host logic on CPU against the UNMODIFIED reference:
+the reference's own test matrix (test/encoders/test_conv_encoder.py: poolings incl. (2,1) / (1,1), three blocks, BatchNorm2d,
+LayerNorm2D, residual, bottleneck) plus strided blocks ("ConvSubsample", used by its streaming tests), in eval mode with
+non-trivial BatchNorm running statistics.  Ops replaced by their torch restatements (tests/ops_doubles.py).
+Needs /root/reference (build container only): skipped elsewhere."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference/neural_sp"), reason="reference tree not available")
+
+
+def make_args(**kw):
+    a = dict(input_dim=80, in_channel=1, channels="32_32_32", kernel_sizes="(3,3)_(3,3)_(3,3)", strides="(1,1)_(1,1)_(1,1)",
+             poolings="(2,2)_(2,2)_(2,2)", dropout=0.1, normalization='', residual=False, bottleneck_dim=0, param_init=0.1)
+    a.update(kw)
+    return a
+
+
+TWO = dict(channels="32_32", kernel_sizes="(3,3)_(3,3)", strides="(1,1)_(1,1)")
+CASES = [
+    dict(TWO, poolings="(2,2)_(2,2)"), dict(TWO, poolings="(2,2)_(2,1)"), dict(TWO, poolings="(1,1)_(1,1)"),
+    dict(poolings="(2,2)_(2,2)_(2,2)"), dict(poolings="(2,2)_(2,2)_(2,1)"), dict(poolings="(2,2)_(2,1)_(2,1)"),
+    dict(poolings="(2,2)_(1,1)_(1,1)"), dict(poolings="(2,1)_(1,1)_(1,1)"), dict(poolings="(1,1)_(1,1)_(1,1)"),
+    dict(normalization='batch_norm'), dict(normalization='layer_norm'), dict(residual=True), dict(bottleneck_dim=8),
+    dict(normalization='batch_norm', residual=True, bottleneck_dim=16),
+    # strided convolutions instead of pooling
+    dict(channels="32", kernel_sizes="(3,3)", strides="(2,2)", poolings="(1,1)"),
+    dict(TWO, strides="(2,2)_(2,2)", poolings="(1,1)_(1,1)"),
+    dict(TWO, strides="(1,1)_(2,2)", poolings="(1,1)_(1,1)", normalization='layer_norm'),
+    dict(strides="(2,2)_(2,2)_(2,2)", poolings="(1,1)_(1,1)_(1,1)", bottleneck_dim=24),
+]
+
+
+@pytest.mark.parametrize("ov", CASES)
+@pytest.mark.parametrize("look", [(False, False), (True, True)])
+def test_conv_encoder_matches_reference(ov, look, monkeypatch):
+    import ops_doubles
+    from oracle.ref_import import import_reference
+    import_reference()
+    from neural_sp_b200.encoders.conv import ConvEncoder
+    ops_doubles.install(monkeypatch)
+    torch.manual_seed(0)
+    args = make_args(**ov)
+    ref = importlib.import_module('neural_sp.models.seq2seq.encoders.conv').ConvEncoder(**args)
+    g = torch.Generator().manual_seed(1)
+    for m in ref.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.5)
+            m.weight.data.copy_(torch.rand(m.weight.shape, generator=g) + 0.5)
+            m.bias.data.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+    ours = ConvEncoder(**args)
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    ours.set_precision("fp32")
+    ref.eval(), ours.eval()
+    assert ours.output_dim == ref.output_dim and ours.subsampling_factor == ref.subsampling_factor
+    assert ours.context_size == ref.context_size
+    rng = np.random.RandomState(0)
+    for xmax in (40, 45):
+        xs = torch.from_numpy(rng.randn(4, xmax, 80).astype(np.float32))
+        xlens = torch.IntTensor([xmax - 3 * i for i in range(4)])
+        for b, n in enumerate(xlens.tolist()):
+            xs[b, n:] = 0
+        with torch.no_grad():
+            r_xs, r_lens = ref(xs.clone(), xlens.clone(), lookback=look[0], lookahead=look[1])
+        o_xs, o_lens = ours(xs.clone(), xlens.clone(), lookback=look[0], lookahead=look[1])
+        assert torch.equal(r_lens, o_lens), (r_lens, o_lens)
+        assert r_xs.shape == o_xs.shape, (r_xs.shape, o_xs.shape)
+        assert torch.allclose(r_xs, o_xs, atol=1e-4), float((r_xs - o_xs).abs().max())

@@ -92,6 +92,13 @@ CASES = [
       'chunk_size_right': "8"}, {}),
     ({'enc_type': 'conv_conformer', 'streaming_type': 'mask', 'chunk_size_left': "16", 'chunk_size_current': "8",
       'subsample': "2_2_1"}, {'poolings': "(1,1)_(2,2)"}),
+    # Conformer + "ConvSubsample": strided convolutions instead of pooling
+    ({'enc_type': 'conv_conformer', 'streaming_type': 'mask', 'chunk_size_left': "16", 'chunk_size_current': "8"},
+     {'channels': "32", 'kernel_sizes': "(3,3)", 'strides': "(2,2)", 'poolings': "(1,1)"}),
+    ({'enc_type': 'conv_conformer', 'streaming_type': 'mask', 'chunk_size_left': "16", 'chunk_size_current': "8"},
+     {'channels': "32_32", 'kernel_sizes': "(3,3)_(3,3)", 'strides': "(2,2)_(2,2)", 'poolings': "(1,1)_(1,1)"}),
+    ({'enc_type': 'conv_conformer', 'streaming_type': 'mask', 'chunk_size_left': "16", 'chunk_size_current': "8",
+      'subsample': "2_2_1"}, {'strides': "(1,1)_(2,2)", 'poolings': "(1,1)_(1,1)"}),
 ]
 
 

@@ -1,0 +1,57 @@
+"""General CNN front-end blocks on the GPU (BatchNorm2d folded, LayerNorm2D incl. the wide-row LayerNorm kernel, residual,
+strided convolutions) against the UNMODIFIED reference's outputs (tests/golden/zz_conv_*.npz, gen_golden_conv.py); the same
+fixtures are replayed on CPU through the ops' restatements in test_conv_fixtures_cpu below (runs wherever the repository does)."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, load_golden
+
+CASES = sorted(os.path.basename(f) for f in glob.glob(os.path.join(GOLDEN, "zz_conv_*.npz")))
+
+
+def _run(name, dev, precision):
+    from neural_sp_b200.encoders.conv import ConvEncoder
+    g = load_golden(name)
+    enc = ConvEncoder(**json.loads(str(g["cfg"])))
+    enc.load_state_dict({k[3:]: torch.from_numpy(np.asarray(g[k])) for k in g.files if k.startswith("sd.")}, strict=True)
+    enc = enc.to(dev).eval()
+    enc.set_precision(precision)
+    with torch.no_grad():
+        ys, ylens = enc(torch.from_numpy(g["xs"]).to(dev), torch.IntTensor(g["xlens"].tolist()))
+    assert ylens.tolist() == g["ys_lens"].tolist()
+    assert tuple(ys.shape) == g["ys"].shape
+    return float(np.abs(ys.float().cpu().numpy() - g["ys"]).max() / np.abs(g["ys"]).max())
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_conv_fixtures_cpu(name, monkeypatch):
+    import ops_doubles
+    ops_doubles.install(monkeypatch)
+    assert _run(name, torch.device("cpu"), "fp32") <= 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.experimental          # first hardware run: profiles/run_round2_validation.sh, stage 1
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 5e-2)])
+@pytest.mark.parametrize("name", CASES)
+def test_conv_fixtures_gpu(name, precision, tol):
+    assert _run(name, torch.device("cuda:0"), precision) <= tol
+
+
+@pytest.mark.gpu
+@pytest.mark.experimental
+@pytest.mark.parametrize("M,D", [(7, 2560), (3, 4100), (5, 2049)])
+def test_layernorm_wide_rows(M, D):
+    from neural_sp_b200 import ops
+    torch.manual_seed(D)
+    x = torch.randn(M, D, device="cuda") * 2 + 0.5
+    w, b = torch.rand(D, device="cuda") + 0.5, torch.randn(D, device="cuda")
+    ref = torch.nn.functional.layer_norm(x, (D,), w, b, 1e-12)
+    y, yb = ops.layernorm(x, w, b, 1e-12, out_fp32=True, out_bf16=True)
+    assert torch.allclose(y, ref, atol=2e-5, rtol=1e-5)
+    assert torch.allclose(yb.float(), ref, atol=3e-2, rtol=2e-2)
