@@ -817,6 +817,8 @@ class _FrontendFn(torch.autograd.Function):
 
 
 def frontend_forward(enc, xs, out_scale, prec):
+    if getattr(enc, "is_1dconv", False):
+        raise NotImplementedError("1-D CNN front-end: inference only on the B200 path")
     for blk in enc.layers:
         if blk.training and blk.dropout.p > 0:
             raise NotImplementedError("dropout > 0 in training mode is not on the B200 path yet")

@@ -201,39 +201,101 @@ class Conv2dBlock(EncoderBase):
         return xs, xlens, T, F
 
 
+def _conv1d_len(n, k, stride):      # nn.Conv1d, padding 1 (conv.py:446-450)
+    return (n + 2 - (k - 1) - 1) // stride + 1
+
+
+class Conv1dBlock(EncoderBase):
+    """1-D CNN block over time with the feature vector as channels (reference conv.py:197-287): Conv1d(k, pad 1) -> [LayerNorm]
+    -> ReLU -> Conv1d(k, stride, pad 1) -> [LayerNorm] -> [+ residual] -> ReLU -> MaxPool1d(ceil).  Each convolution is a
+    tcgen05 GEMM over the k gathered neighbour frames (column order c * k + j = nn.Conv1d's weight layout), bias / ReLU in the
+    epilogue.  Inference only.  `normalization='batch_norm'` is rejected: the reference applies BatchNorm1d(out_channel) to a
+    `[B, T, C]` tensor, i.e. over the TIME axis (conv.py:264-266), which only runs when T == out_channel."""
+
+    def __init__(self, in_channel, out_channel, kernel_size, stride, pooling, dropout, normalization, residual):
+        super().__init__()
+        if normalization == 'batch_norm':
+            raise NotImplementedError("conv_normalization=batch_norm with a 1-D CNN front-end (see the class docstring)")
+        self.residual = residual
+        self.dropout = nn.Dropout(p=dropout)
+        self.kernel_size, self.stride, self.pooling = kernel_size, stride, pooling
+        self.conv1 = nn.Conv1d(in_channel, out_channel, kernel_size=kernel_size, stride=1, padding=1)
+        self.norm1 = nn.LayerNorm(out_channel, eps=1e-12) if normalization == 'layer_norm' else None
+        self.conv2 = nn.Conv1d(out_channel, out_channel, kernel_size=kernel_size, stride=stride, padding=1)
+        self.norm2 = nn.LayerNorm(out_channel, eps=1e-12) if normalization == 'layer_norm' else None
+        self.pool = pooling if pooling > 1 else None
+        self._odim = out_channel
+        self.plain = False              # no training path
+
+    def _conv(self, name, conv, norm, xs, stride, residual_t):
+        prec = get_precision(self)
+        B, T, C = xs.shape
+        k = self.kernel_size
+        To = _conv1d_len(T, k, stride)
+        xp = torch.nn.functional.pad(xs, (0, 0, 1, 1))                         # layout plumbing only
+        cols = xp.unfold(1, k, stride)[:, :To].reshape(B, To, C * k)           # column c * k + j
+        w = prepared(self, name, prec, (conv.weight,), build=lambda t: t.reshape(t.size(0), -1))
+        fuse_relu = norm is None and residual_t is None
+        y = ops.linear(cols, w, conv.bias, prec=prec, act="relu" if fuse_relu else None, out_dtype=torch.float32)
+        if norm is not None:
+            y = ops.layernorm(y, norm.weight, norm.bias, norm.eps)
+        if residual_t is not None and residual_t.shape == y.shape:
+            y = ops.dropout_add(y.contiguous(), residual_t, 0.0, 1.0, 0)       # p = 0: plain out = residual + y
+        if not fuse_relu:
+            y = ops.relu_mask(y.contiguous(), y.contiguous())
+        return y
+
+    def forward(self, xs, xlens, lookback=False, lookahead=False):
+        """xs fp32 `[B, T, C_in]` -> (`[B, T', C_out]`, xlens); lookback / lookahead are accepted and unused, as in the reference."""
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError("1-D CNN front-end: inference only on the B200 path")
+        k = self.kernel_size
+        res = xs.float().contiguous() if self.residual else None
+        xs = self._conv("conv1", self.conv1, self.norm1, xs.float(), 1, None)
+        xlens = torch.IntTensor([_conv1d_len(int(n), k, 1) for n in xlens])
+        xs = self._conv("conv2", self.conv2, self.norm2, xs, self.stride, res)
+        xlens = torch.IntTensor([_conv1d_len(int(n), k, self.stride) for n in xlens])
+        if self.pool is not None:
+            xs = ops.pool_time(xs.contiguous(), self.pool, "max")
+            xlens = torch.IntTensor([_pool_len(int(n), self.pool) for n in xlens])
+        return xs, xlens
+
+
 class ConvEncoder(EncoderBase):
     def __init__(self, input_dim, in_channel, channels, kernel_sizes, strides, poolings, dropout, normalization,
                  residual, bottleneck_dim, param_init):
         super().__init__()
         assert channels
         (channels, kernel_sizes, strides, poolings), is_1dconv = parse_cnn_config(channels, kernel_sizes, strides, poolings)
-        if is_1dconv:
-            raise NotImplementedError("1-D CNN front-end (TDS-style) is out of scope")
-        self.is_1dconv = False
+        self.is_1dconv = is_1dconv
         self.in_channel = in_channel
         assert input_dim % in_channel == 0
         self.input_freq = input_dim // in_channel
         self.residual = residual
         assert len(channels) > 0 and len(channels) == len(kernel_sizes) == len(strides) == len(poolings)
         self.layers = nn.ModuleList()
-        C_i, in_freq = in_channel, self.input_freq
+        C_i, in_freq = (input_dim if is_1dconv else in_channel), self.input_freq
         for lth in range(len(channels)):
-            block = Conv2dBlock(in_freq, C_i, channels[lth], kernel_sizes[lth], strides[lth], poolings[lth],
-                                dropout, normalization, residual)
+            if is_1dconv:               # features as channels, convolution over time only (reference :60-68)
+                block = Conv1dBlock(C_i, channels[lth], kernel_sizes[lth], strides[lth], poolings[lth], dropout,
+                                    normalization, residual)
+            else:
+                block = Conv2dBlock(in_freq, C_i, channels[lth], kernel_sizes[lth], strides[lth], poolings[lth],
+                                    dropout, normalization, residual)
             self.layers += [block]
             in_freq = block.output_dim
             C_i = channels[lth]
         self._c_last, self._f_last = C_i, in_freq
-        self._odim = int(C_i * in_freq)
+        self._odim = C_i if is_1dconv else int(C_i * in_freq)
         self.bridge = None
         if bottleneck_dim > 0 and bottleneck_dim != self._odim:
             self.bridge = nn.Linear(self._odim, bottleneck_dim)
             self._odim = bottleneck_dim
         self._factor = 1
-        for s in strides:
-            self._factor *= s[0]
-        for p in poolings:
-            self._factor *= p[0]
+        for s_, p_ in zip(strides, poolings):
+            self._factor *= (s_ if is_1dconv else s_[0]) * (p_ if is_1dconv else p_[0])
+        if is_1dconv:
+            kernel_sizes, strides, poolings = ([[v] for v in lst] for lst in (kernel_sizes, strides, poolings))
         self._context_size = self._calc_context(kernel_sizes, strides, poolings)
         for n, p in self.named_parameters():
             init_with_lecun_normal(n, p, param_init)
@@ -273,6 +335,15 @@ class ConvEncoder(EncoderBase):
         prec = get_precision(self)
         xs = xs.contiguous().float()
         n = len(self.layers)
+        if self.is_1dconv:
+            for block in self.layers:
+                xs, xlens = block(xs, xlens, lookback=lookback, lookahead=lookahead)
+            if self.bridge is not None:
+                xs = ops.linear(xs, prepared(self, "bridge1d", prec, (self.bridge.weight,)), self.bridge.bias, prec=prec,
+                                alpha=out_scale, out_dtype=torch.float32)
+            elif out_scale != 1.0:
+                xs = ops.scale_(xs.contiguous(), out_scale)
+            return xs, xlens
         for i, block in enumerate(self.layers):
             # with a bridge the channels-last flatten is absorbed by permuting the bridge weight's columns
             last_chmajor = (i == n - 1) and self.bridge is None

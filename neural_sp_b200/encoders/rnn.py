@@ -50,9 +50,7 @@ class RNNEncoder(EncoderBase):
         self.lc_bidir = (self.N_c > 0 or self.N_r > 0) and self.bidirectional
         if self.lc_bidir:
             assert enc_type not in ['lstm', 'conv_lstm'] and n_layers_sub2 == 0
-        if rsp_prob > 0:
-            raise NotImplementedError("random state passing is a training-time streaming feature (out of scope)")
-        self.rsp_prob = rsp_prob
+        self.rsp_prob = rsp_prob        # random state passing acts in training only (rnn.py:323-324); see forward()
         self.n_layers_sub1, self.n_layers_sub2 = n_layers_sub1, n_layers_sub2
         self.task_specific_layer = task_specific_layer
         self.bridge = self.bridge_sub1 = self.bridge_sub2 = None
@@ -256,6 +254,9 @@ class RNNEncoder(EncoderBase):
         prec = get_precision(self)
         # train() + grad mode: autograd nodes with hand-written CUDA backward; otherwise inference kernels under no_grad
         train = ag.training_enabled(self)
+        if train and self.rsp_prob > 0:
+            raise NotImplementedError("random state passing (rsp_prob > 0) needs a carried initial state in the training "
+                                      "LSTM node; not on the B200 path (it is inactive in eval mode)")
         if train and (streaming or self.lc_bidir):
             raise NotImplementedError("streaming / latency-controlled BLSTM encoding is an inference path "
                                       "(call .eval() / torch.no_grad())")
