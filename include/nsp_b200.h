@@ -151,6 +151,22 @@ nsp_status nsp_conformer_conv_fwd(int is_bf16, const void* x, int64_t ldx, const
                                   const float* run_mean, const float* run_var, float eps,
                                   void* y, int64_t ldy, int B, int T, int d, int k, int causal, void* stream);
 
+/* Training of the convolution module with BatchNorm (the reference's default `conformer_normalization`,
+ * modules/conformer_convolution.py:118-124: statistics over all B*T frames):
+ *   nsp_dwconv_stats_fwd: z = depthwise_conv1d_k(x) + bias (same dtype as x, [B,T,d]); stats fp32 [2,d] = (sum z, sum z^2);
+ *     the normalised output then comes from nsp_conformer_conv_fwd(norm_mode 1) with run_mean / run_var = the batch statistics;
+ *   nsp_bn_swish_bwd: dy = gradient w.r.t. Swish(gamma zh + beta), zh = (z - mean) rsqrt(var + eps):
+ *     sums fp32 [2,d] = (sum du = d beta, sum du zh = d gamma), dz = gamma rstd (du - sums0 / M - zh sums1 / M), M = B*T rows;
+ *   nsp_dwconv_bwd: dx, dw [k,d] (+=), dbias [d] (+=) from dz (the depthwise half of nsp_conformer_conv_bwd). */
+nsp_status nsp_dwconv_stats_fwd(int is_bf16, const void* x, int64_t ldx, const float* w, const float* bias, void* z,
+                                int64_t ldz, float* stats, int B, int T, int d, int k, int causal, void* stream);
+nsp_status nsp_bn_swish_bwd(int is_bf16, const void* z, int64_t ldz, const void* dy, int64_t lddy, const float* mean,
+                            const float* var, const float* gamma, const float* beta, float eps, float* sums,
+                            void* dz, int64_t lddz, int64_t M, int d, void* stream);
+nsp_status nsp_dwconv_bwd(int is_bf16, const void* x, int64_t ldx, const float* w, const void* dz, int64_t lddz,
+                          void* dx, int64_t lddx, float* dw, float* dbias, int B, int T, int d, int k, int causal,
+                          void* stream);
+
 /* x *= a in place (LayerDrop's eval-time 1/(1-p) rescale, encoders/conformer_block.py:122-126). */
 nsp_status nsp_scale_inplace(float* x, float a, int64_t n, void* stream);
 /* x[b,t,:] = x[b,t,:] * a + pe[t,:] in place: PositionalEncoding.forward (pe_type='add')

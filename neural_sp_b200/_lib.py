@@ -171,6 +171,11 @@ _more = {
     "nsp_rng_advance": (c_int, [c_vp, c_vp]),
     "nsp_rnnt_grad_logits": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_sz, c_vp, c_vp,
                                      c_int, c_vp]),
+    "nsp_dwconv_stats_fwd": (c_int, [c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "nsp_bn_swish_bwd": (c_int, [c_int, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_i64, c_i64, c_int,
+                                 c_vp]),
+    "nsp_dwconv_bwd": (c_int, [c_int, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
+                               c_vp]),
     "nsp_log_softmax_bwd": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp]),
     "nsp_rnnt_joint_tanh_bwd": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     "nsp_pool_time_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),

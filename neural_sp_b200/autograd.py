@@ -300,24 +300,51 @@ def attn_bwd(attn, norm, saved, dy, dyo, pos, klens, u_bias, v_bias, mask_kw, pr
     return _ln_bwd(norm, dn, x, dy, G, prec, nxt[0], nxt[1])
 
 
+def _bn_batch_stats(bn, stats, M):
+    """(mean, biased var) fp32 `[d]` of the batch from (sum, sum of squares), and nn.BatchNorm1d's training-mode update of the
+    running statistics (momentum, UNBIASED variance, num_batches_tracked); d-length vector arithmetic, all on the device."""
+    if bn.momentum is None:
+        raise NotImplementedError("BatchNorm with momentum=None (cumulative average) is not on the B200 path")
+    s = stats.double()
+    mean = s[0] / M
+    var = (s[1] / M - mean * mean).clamp_min(0.0)
+    with torch.no_grad():
+        if bn.track_running_stats and bn.running_mean is not None:
+            m = bn.momentum
+            bn.running_mean.mul_(1 - m).add_((m * mean).to(bn.running_mean.dtype))
+            bn.running_var.mul_(1 - m).add_((m * var * (M / max(M - 1, 1))).to(bn.running_var.dtype))
+            bn.num_batches_tracked += 1
+    return mean.float().contiguous(), var.float().contiguous()
+
+
 def convmod_fwd(conv, norm, x, prec, p_res=0.0):
-    if conv.normalization != 'layer_norm':
-        raise NotImplementedError("training the Conformer conv module needs conformer_normalization=layer_norm on the B200 "
-                                  "path (the LibriSpeech recipes' setting)")
+    if conv.normalization not in ('layer_norm', 'batch_norm'):
+        raise NotImplementedError("training the Conformer conv module needs conformer_normalization=layer_norm or batch_norm "
+                                  "on the B200 path")
     n = _ln_fwd(norm, x, prec)
     w1 = prepared(conv, "pw1", prec, (conv.pointwise_conv1.weight,), build=lambda w: w.squeeze(-1))
     g, pre = ops.linear(n, w1, conv.pointwise_conv1.bias, prec=prec, glu=True, out_dtype=act_dtype(prec), save_pre=True)
     taps = cached(conv, "dw_taps", (conv.depthwise_conv.weight,), lambda w: w.reshape(w.size(0), -1).t().contiguous().float())
-    c = ops.conformer_conv(g, taps, conv.depthwise_conv.bias, 'layer_norm', conv.norm.weight, conv.norm.bias, conv.norm.eps,
-                           None, None, causal=conv.causal)
+    bn = None
+    if conv.normalization == 'batch_norm':
+        # statistics over ALL B*T frames, padded ones included (conformer_convolution.py:118-124); the normalised output comes
+        # from the same fused kernel as inference, fed with the batch statistics
+        z, stats = ops.dwconv_stats(g, taps, conv.depthwise_conv.bias, causal=conv.causal)
+        mean, var = _bn_batch_stats(conv.norm, stats, g.shape[0] * g.shape[1])
+        c = ops.conformer_conv(g, taps, conv.depthwise_conv.bias, 'batch_norm', conv.norm.weight, conv.norm.bias, conv.norm.eps,
+                               mean, var, causal=conv.causal)
+        bn = (z, mean, var)
+    else:
+        c = ops.conformer_conv(g, taps, conv.depthwise_conv.bias, 'layer_norm', conv.norm.weight, conv.norm.bias, conv.norm.eps,
+                               None, None, causal=conv.causal)
     w2 = prepared(conv, "pw2", prec, (conv.pointwise_conv2.weight,), build=lambda w: w.squeeze(-1))
     y, sid_r = _drop_out(lambda fused: ops.linear(c, w2, conv.pointwise_conv2.bias, prec=prec, residual=x if fused else None,
                                                   out_dtype=torch.float32 if fused else act_dtype(prec)), x, p_res, 1.0)
-    return y, (x, n, pre, g, c, taps, (p_res, sid_r))
+    return y, (x, n, pre, g, c, taps, bn, (p_res, sid_r))
 
 
 def convmod_bwd(conv, norm, saved, dy, dyo, prec, G, bias_done=False, nxt=(None, 1.0)):
-    x, n, pre, g, c, taps, (p_res, sid_r) = saved
+    x, n, pre, g, c, taps, bn, (p_res, sid_r) = saved
     d = x.shape[-1]
     dyb, dyo, fused_ok = _drop_grad(dy, dyo, p_res, sid_r, prec)
     ops.linear_wgrad(dyo, c, prec, _as2d(G.buf(conv.pointwise_conv2.weight)))
@@ -325,9 +352,16 @@ def convmod_bwd(conv, norm, saved, dy, dyo, prec, G, bias_done=False, nxt=(None,
         ops.colsum_acc(dyb, G.buf(conv.pointwise_conv2.bias))
     dc = ops.linear(dyo, _wT(conv, "pw2", prec, (conv.pointwise_conv2.weight,)), None, prec=prec, out_dtype=act_dtype(prec))
     dtaps = torch.zeros_like(taps)
-    dg = ops.conformer_conv_bwd(g, taps, conv.depthwise_conv.bias, conv.norm.weight, conv.norm.bias, conv.norm.eps, dc,
-                                dtaps, G.buf(conv.depthwise_conv.bias), G.buf(conv.norm.weight), G.buf(conv.norm.bias),
-                                causal=conv.causal)
+    if bn is not None:
+        z, mean, var = bn
+        dz, sums = ops.bn_swish_bwd(z, dc, mean, var, conv.norm.weight, conv.norm.bias, conv.norm.eps)
+        G.buf(conv.norm.bias).add_(sums[0])
+        G.buf(conv.norm.weight).add_(sums[1])
+        dg = ops.dwconv_bwd(g, taps, dz, dtaps, G.buf(conv.depthwise_conv.bias), causal=conv.causal)
+    else:
+        dg = ops.conformer_conv_bwd(g, taps, conv.depthwise_conv.bias, conv.norm.weight, conv.norm.bias, conv.norm.eps, dc,
+                                    dtaps, G.buf(conv.depthwise_conv.bias), G.buf(conv.norm.weight), G.buf(conv.norm.bias),
+                                    causal=conv.causal)
     G.put(conv.depthwise_conv.weight, dtaps.t())
     if _fusable(pre) and pre.shape[-1] % 32 == 0:
         dpre = ops.act_bwd_bias(dg, pre, None, G.buf(conv.pointwise_conv1.bias), glu=True)

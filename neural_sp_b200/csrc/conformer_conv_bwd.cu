@@ -342,3 +342,31 @@ extern "C" nsp_status nsp_conformer_conv_bwd(int is_bf16, const void* x, int64_t
     if (d <= 512) return launch_conv_bwd<float, 16>(p, st);
     return launch_conv_bwd<float, 32>(p, st);
 }
+
+// Depthwise part alone (K2): dx, d(taps), d(conv bias) from dz = gradient w.r.t. the depthwise-conv output.  Used by the
+// BatchNorm training path (conformer_conv_bn.cu), whose normalisation backward needs batch-wide reductions between K1 and K2.
+extern "C" nsp_status nsp_dwconv_bwd(int is_bf16, const void* x, int64_t ldx, const float* w, const void* dz, int64_t lddz,
+                                     void* dx, int64_t lddx, float* dw, float* dbias, int B, int T, int d, int k, int causal,
+                                     void* stream) {
+    NSP_CHECK_ARG(x && w && dz && dx, "dwconv_bwd: null pointer");
+    NSP_CHECK_ARG(B > 0 && T > 0 && d > 0 && k >= 1 && (k % 2 == 1), "dwconv_bwd: bad shape B=%d T=%d d=%d k=%d", B, T, d, k);
+    ConvBwdParams p;
+    p.x = x; p.ldx = ldx; p.w = w; p.bias = nullptr; p.g = nullptr; p.b = nullptr; p.dy = nullptr; p.lddy = 0;
+    p.dz = const_cast<void*>(dz); p.lddz = lddz; p.dx = dx; p.lddx = lddx; p.dw = dw; p.dbias = dbias; p.dg = nullptr; p.db = nullptr;
+    p.B = B; p.T = T; p.d = d; p.k = k; p.left_pad = causal ? (k - 1) : (k - 1) / 2; p.eps = 0.f;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem2 = sizeof(float) * ((size_t)2 * (K2_TT + k - 1) * K2_CH + (size_t)2 * k * K2_CH + K2_CH);
+    if (smem2 > 220 * 1024) { set_error("dwconv_bwd: k=%d needs %zu B smem", k, smem2); return NSP_ERR_UNSUPPORTED; }
+    const unsigned grid2 = (unsigned)(B * ceil_div(T, K2_TT) * ceil_div(d, K2_CH));
+    if (is_bf16) {
+        auto k2 = conv_bwd_dw_kernel<__nv_bfloat16>;
+        NSP_CUDA_OK(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        k2<<<grid2, 32 * K2_NW, smem2, st>>>(p);
+    } else {
+        auto k2 = conv_bwd_dw_kernel<float>;
+        NSP_CUDA_OK(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        k2<<<grid2, 32 * K2_NW, smem2, st>>>(p);
+    }
+    NSP_LAUNCH_OK();
+    return NSP_OK;
+}

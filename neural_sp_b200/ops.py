@@ -554,6 +554,7 @@ def lstm_seq_bwd(dy, acts, cprev, w_hh, lens):
 # ---------------------------------------------------------------------------------------------
 KERNELS_PER_CALL["nsp_relpos_attention_bwd"] = 4
 KERNELS_PER_CALL["nsp_rnnt_joint_tanh_bwd"] = 2
+KERNELS_PER_CALL["nsp_bn_swish_bwd"] = 2
 KERNELS_PER_CALL["nsp_conformer_conv_bwd"] = 2
 
 
@@ -695,6 +696,45 @@ def pool_time_bwd(dy, T, factor, mode):
     assert To == -(-T // factor) and mode in ("mean", "drop", "add")
     dx = torch.empty(B, T, D, dtype=torch.float32, device=dy.device)
     _run("nsp_pool_time_bwd", lib.nsp_pool_time_bwd, ptr(dy), ptr(dx), B, T, D, int(factor), POOL_MODE[mode], current_stream_ptr())
+    return dx
+
+
+def dwconv_stats(x, taps, dw_bias, causal=False):
+    """z = depthwise_conv(x) + bias `[B,T,d]` (dtype of x) and its per-channel (sum, sum of squares) over all B*T frames,
+    fp32 `[2,d]` (nsp_dwconv_stats_fwd): the first half of the BatchNorm training forward of the Conformer conv module."""
+    _require_cuda(x, taps, dw_bias)
+    B, T, d = x.shape
+    x = x if x.stride(2) == 1 and x.stride(0) == T * x.stride(1) else x.contiguous()
+    z = torch.empty(B, T, d, dtype=x.dtype, device=x.device)
+    stats = torch.empty(2, d, dtype=torch.float32, device=x.device)
+    _run("nsp_dwconv_stats_fwd", lib.nsp_dwconv_stats_fwd, int(x.dtype == torch.bfloat16), ptr(x), x.stride(1), ptr(taps),
+         ptr(dw_bias), ptr(z), d, ptr(stats), B, T, d, taps.shape[0], int(causal), current_stream_ptr())
+    return z, stats
+
+
+def bn_swish_bwd(z, dy, mean, var, gamma, beta, eps):
+    """Backward of Swish(BatchNorm(z)) with batch statistics (nsp_bn_swish_bwd): -> (dz like z, sums fp32 `[2,d]` =
+    (d beta, d gamma))."""
+    _require_cuda(z, dy, mean, var)
+    B, T, d = z.shape
+    z = z.contiguous()
+    dy = dy.to(z.dtype).contiguous()
+    dz = torch.empty_like(z)
+    sums = torch.empty(2, d, dtype=torch.float32, device=z.device)
+    _run("nsp_bn_swish_bwd", lib.nsp_bn_swish_bwd, int(z.dtype == torch.bfloat16), ptr(z), d, ptr(dy), d, ptr(mean), ptr(var),
+         ptr(gamma), ptr(beta), float(eps), ptr(sums), ptr(dz), d, B * T, d, current_stream_ptr())
+    return dz, sums
+
+
+def dwconv_bwd(x, taps, dz, dtaps, dbias, causal=False):
+    """dx, d taps (+=), d bias (+=) of the depthwise conv from dz (nsp_dwconv_bwd)."""
+    _require_cuda(x, taps, dz)
+    B, T, d = x.shape
+    x = x if x.stride(2) == 1 and x.stride(0) == T * x.stride(1) else x.contiguous()
+    dz = dz.to(x.dtype).contiguous()
+    dx = torch.empty(B, T, d, dtype=x.dtype, device=x.device)
+    _run("nsp_dwconv_bwd", lib.nsp_dwconv_bwd, int(x.dtype == torch.bfloat16), ptr(x), x.stride(1), ptr(taps), ptr(dz), d,
+         ptr(dx), d, ptr(dtaps), ptr(dbias), B, T, d, taps.shape[0], int(causal), current_stream_ptr())
     return dx
 
 

@@ -396,6 +396,45 @@ def conformer_conv_bwd(x, taps, dw_bias, norm_w, norm_b, eps, dy, dtaps, dbias, 
     return xx.grad.to(x.dtype)
 
 
+def _dwconv(x, taps, bias, causal):
+    d, k = x.shape[-1], taps.shape[0]
+    xf = x.float().transpose(1, 2)
+    w = taps.t().reshape(d, 1, k).float()
+    if causal:
+        y = F.conv1d(F.pad(xf, (k - 1, 0)), w, bias.float(), groups=d)
+    else:
+        y = F.conv1d(xf, w, bias.float(), padding=(k - 1) // 2, groups=d)
+    return y.transpose(1, 2)
+
+
+def dwconv_stats(x, taps, dw_bias, causal=False):
+    z = _dwconv(x, taps, dw_bias, causal).to(x.dtype)
+    zf = z.float().reshape(-1, z.shape[-1])
+    return z, torch.stack([zf.sum(0), (zf * zf).sum(0)])
+
+
+def bn_swish_bwd(z, dy, mean, var, gamma, beta, eps):
+    with torch.enable_grad():
+        zz = z.detach().float().clone().requires_grad_(True)
+        g = gamma.detach().float().clone().requires_grad_(True)
+        b = beta.detach().float().clone().requires_grad_(True)
+        zf = zz.reshape(-1, zz.shape[-1])
+        mu, v = zf.mean(0), zf.var(0, unbiased=False)           # statistics are functions of z (that is what makes BN's backward)
+        u = g * (zz - mu) / torch.sqrt(v + eps) + b
+        (u * torch.sigmoid(u)).backward(dy.float())
+    return zz.grad.to(z.dtype), torch.stack([b.grad, g.grad])
+
+
+def dwconv_bwd(x, taps, dz, dtaps, dbias, causal=False):
+    with torch.enable_grad():
+        xx = x.detach().float().clone().requires_grad_(True)
+        tt = taps.detach().float().clone().requires_grad_(True)
+        bb = torch.zeros(x.shape[-1], requires_grad=True)
+        _dwconv(xx, tt, bb, causal).backward(dz.float())
+    dtaps.add_(tt.grad), dbias.add_(bb.grad)
+    return xx.grad.to(x.dtype)
+
+
 def maxpool_time_bwd(x, dy, factor):
     with torch.enable_grad():
         xx = x.detach().float().clone().requires_grad_(True)
@@ -514,7 +553,8 @@ TRAIN_DOUBLES = dict(DOUBLES, linear=_linear_train, linear_wgrad=linear_wgrad, c
                      maxpool_time_bwd=maxpool_time_bwd, pool_time_bwd=pool_time_bwd, relu_mask=relu_mask, dropout=dropout, dropout_add=dropout_add,
                      rng_advance=rng_advance, lstm_seq_bwd=lstm_seq_bwd, rnnt_joint_tanh=rnnt_joint_tanh,
                      softmax_rows=softmax_rows, rnnt_loss_fwd_bwd=rnnt_loss_fwd_bwd, rnnt_grad_logits=rnnt_grad_logits, log_softmax_bwd_=log_softmax_bwd_,
-                     rnnt_joint_tanh_bwd=rnnt_joint_tanh_bwd, pack_labels=pack_labels, ctc_loss_fwd_bwd=ctc_loss_fwd_bwd)
+                     rnnt_joint_tanh_bwd=rnnt_joint_tanh_bwd, pack_labels=pack_labels, ctc_loss_fwd_bwd=ctc_loss_fwd_bwd,
+                     dwconv_stats=dwconv_stats, bn_swish_bwd=bn_swish_bwd, dwconv_bwd=dwconv_bwd)
 
 
 def install_training(monkeypatch):

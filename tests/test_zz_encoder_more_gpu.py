@@ -97,3 +97,46 @@ def test_pool_time_bwd_kernel(mode, B, T, D, f):
     ref.backward(dy)
     dx = ops.pool_time_bwd(dy, T, f, mode)
     assert torch.allclose(dx, x.grad, atol=1e-6)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 3e-2)])
+@pytest.mark.parametrize("B,T,d,k,causal", [(3, 45, 64, 7, False), (2, 100, 256, 15, False), (2, 33, 40, 3, True), (1, 5, 512, 31, False)])
+def test_conv_module_batchnorm_training_kernels(B, T, d, k, causal, dtype, tol):
+    """nsp_dwconv_stats_fwd / nsp_bn_swish_bwd / nsp_dwconv_bwd against torch autograd through
+    Swish(BatchNorm_train(depthwise_conv(x))) with statistics over all B*T frames (conformer_convolution.py:113-124)."""
+    from neural_sp_b200 import ops
+    torch.manual_seed(d + k)
+    dev = "cuda"
+    x = torch.randn(B, T, d, device=dev).to(dtype)
+    w = (torch.randn(d, 1, k, device=dev) * 0.3).requires_grad_(True)
+    bias = (torch.randn(d, device=dev) * 0.1).requires_grad_(True)
+    g = (torch.rand(d, device=dev) + 0.5).requires_grad_(True)
+    bt = (torch.randn(d, device=dev) * 0.1).requires_grad_(True)
+    eps = 1e-5
+    xr = x.float().clone().requires_grad_(True)
+    pad = k - 1 if causal else (k - 1) // 2
+    zc = torch.nn.functional.conv1d(torch.nn.functional.pad(xr.transpose(1, 2), (pad, k - 1 - pad)), w, bias, groups=d).transpose(1, 2)
+    zf = zc.reshape(-1, d)
+    mu, var = zf.mean(0), zf.var(0, unbiased=False)
+    u = g * (zc - mu) / torch.sqrt(var + eps) + bt
+    y = u * torch.sigmoid(u)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    taps = w.detach().reshape(d, k).t().contiguous()
+    z, stats = ops.dwconv_stats(x, taps, bias.detach(), causal=causal)
+    M = B * T
+    mean_k = stats[0] / M
+    var_k = (stats[1] / M - mean_k * mean_k).clamp_min(0)
+    assert float((z.float() - zc.detach()).abs().max()) <= tol * float(zc.abs().max())
+    assert float((mean_k - mu.detach()).abs().max()) <= tol and float((var_k - var.detach()).abs().max()) <= tol * max(1.0, float(var.max()))
+    yk = ops.conformer_conv(x, taps, bias.detach(), "batch_norm", g.detach(), bt.detach(), eps, mean_k.contiguous(), var_k.contiguous(),
+                            causal=causal)
+    assert float((yk.float() - y.detach()).abs().max()) <= tol * max(1.0, float(y.abs().max()))
+    dz, sums = ops.bn_swish_bwd(z, dy.to(dtype), mean_k.contiguous(), var_k.contiguous(), g.detach(), bt.detach(), eps)
+    assert float((sums[0] - bt.grad).abs().max()) <= tol * max(1.0, float(bt.grad.abs().max())) * 4
+    assert float((sums[1] - g.grad).abs().max()) <= tol * max(1.0, float(g.grad.abs().max())) * 4
+    dtaps, dbias = torch.zeros(k, d, device=dev), torch.zeros(d, device=dev)
+    dx = ops.dwconv_bwd(x, taps, dz, dtaps, dbias, causal=causal)
+    assert float((dx.float() - xr.grad).abs().max()) <= tol * max(1.0, float(xr.grad.abs().max())) * 4
+    assert float((dtaps.t().reshape(d, 1, k) - w.grad).abs().max()) <= tol * max(1.0, float(w.grad.abs().max())) * 8
+    assert float((dbias - bias.grad).abs().max()) <= tol * max(1.0, float(bias.grad.abs().max())) * 8
