@@ -850,13 +850,18 @@ class _FrontendFn(torch.autograd.Function):
         return (None, None, None, None) + tuple(G.get(p) for p in ctx.params)
 
 
-def frontend_forward(enc, xs, out_scale, prec):
+def frontend_check(enc):
+    """Raise NotImplementedError for CNN front-end variants without a training path (inference handles them)."""
     if getattr(enc, "is_1dconv", False):
         raise NotImplementedError("1-D CNN front-end: inference only on the B200 path")
     for blk in enc.layers:
         if blk.training and blk.dropout.p > 0:
-            raise NotImplementedError("dropout > 0 in training mode is not on the B200 path yet")
+            raise NotImplementedError("dropout > 0 in the CNN front-end is not on the B200 path (build_encoder passes 0)")
         if not blk.plain:
             raise NotImplementedError("training path of the CNN front-end: stride (1,1), no normalisation, no residual only")
+
+
+def frontend_forward(enc, xs, out_scale, prec):
+    frontend_check(enc)
     params = [p for p in enc.parameters()]
     return _FrontendFn.apply(xs, enc, float(out_scale), prec, *params)

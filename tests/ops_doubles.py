@@ -533,6 +533,8 @@ def ctc_loss_fwd_bwd(logits, labels, elens, ylens, blank=0, lsm_prob=0.0):
 def frontend_forward(enc, xs, out_scale, prec):
     """Differentiable torch restatement of the CNN front-end + bridge (reference conv.py:167-195, 347-396); replaces
     neural_sp_b200.autograd.frontend_forward (one autograd node with hand-written CUDA backward, checked on the GPU)."""
+    from neural_sp_b200 import autograd as ag
+    ag.frontend_check(enc)                       # same support envelope as the real node
     B, T, Fd = xs.shape
     x = xs.view(B, T, enc.in_channel, Fd // enc.in_channel).transpose(1, 2)
     for blk in enc.layers:
