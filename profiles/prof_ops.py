@@ -77,3 +77,51 @@ elif which == "attn_bwd":
     torch.cuda.synchronize()
     ms = s.elapsed_time(e) / 10
     print("attn_bwd B=%d T=%d H=%d: %.4f ms  %.1f TFLOP/s (10*T^2*d per utterance)" % (B, T, H, ms, 10.0 * B * T * T * D / ms / 1e9))
+elif which == "stream_kernels":
+    # HBM-bound kernels added late in round 1: time each on a tensor much larger than L2, report algorithmic GB/s
+    from neural_sp_b200 import random as nrandom
+
+    def timeit(name, fn, nbytes, reps=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / reps
+        print("%-34s %8.4f ms  %8.1f GB/s algorithmic" % (name, ms, nbytes / ms / 1e6))
+
+    M, dff, d = 16000, 2048, 512
+    hb = torch.randn(M, dff, device=dev).bfloat16()
+    sid = nrandom.next_stream()
+    timeit("dropout bf16 [16000,2048] in place", lambda: ops.dropout(hb, 0.1, sid, inplace=True), hb.numel() * 4)
+    t, res = torch.randn(M, d, device=dev).bfloat16(), torch.randn(M, d, device=dev)
+    out = torch.empty_like(res)
+    timeit("dropout_add bf16->fp32 [16000,512]", lambda: ops.dropout_add(t, res, 0.1, 0.5, sid, out=out), M * d * 10)
+    B, T, U1, V = 32, 250, 57, 1000
+    lp = torch.log_softmax(torch.randn(B, T, U1, V, device=dev), -1)
+    ys = torch.randint(1, V, (B, U1 - 1), dtype=torch.int32, device=dev)
+    fl = torch.full((B,), T, dtype=torch.int32, device=dev)
+    yl = torch.full((B,), U1 - 1, dtype=torch.int32, device=dev)
+    loss, nll, _, ws = ops.rnnt_loss_fwd_bwd(lp, ys, fl, yl, 0, need_grad=False, return_ws=True)
+    timeit("rnnt lattice (gather+alpha/beta)", lambda: ops.rnnt_loss_fwd_bwd(lp, ys, fl, yl, 0, need_grad=False), B * T * U1 * 8.0)
+    timeit("rnnt_grad_logits -> bf16", lambda: ops.rnnt_grad_logits(lp, ws, nll, ys, fl, yl, 0, out_dtype=torch.bfloat16), lp.numel() * 6.0, 5)
+    timeit("rnnt dense grad (old path)", lambda: ops.rnnt_loss_fwd_bwd(lp, ys, fl, yl, 0, need_grad=True), lp.numel() * 4.0, 5)
+    J = 640
+    h = torch.tanh(torch.randn(8, T, U1, J, device=dev)).bfloat16()
+    dh = torch.randn_like(h)
+    timeit("rnnt_joint_tanh_bwd bf16 [8,250,57,640]", lambda: ops.rnnt_joint_tanh_bwd(h, dh), h.numel() * 2 * 2 * 2.0, 5)
+    g = torch.randn(32, 500, 512, device=dev).bfloat16()
+    taps, bias = torch.randn(15, 512, device=dev) * 0.2, torch.zeros(512, device=dev)
+    timeit("dwconv_stats bf16 [32,500,512] k15", lambda: ops.dwconv_stats(g, taps, bias), g.numel() * 4.0)
+    z, stats = ops.dwconv_stats(g, taps, bias)
+    mean = (stats[0] / (32 * 500)).contiguous()
+    var = (stats[1] / (32 * 500) - mean * mean).clamp_min(0).contiguous()
+    gam, bet = torch.ones(512, device=dev), torch.zeros(512, device=dev)
+    timeit("bn_swish_bwd bf16 [32,500,512]", lambda: ops.bn_swish_bwd(z, g, mean, var, gam, bet, 1e-5), g.numel() * 10.0)
+    x3 = torch.randn(32, 500, 512, device=dev)
+    dy3 = torch.randn(32, 250, 512, device=dev)
+    timeit("pool_time_bwd mean fp32 [32,500,512]", lambda: ops.pool_time_bwd(dy3, 500, 2, "mean"), x3.numel() * 6.0)
