@@ -14,6 +14,7 @@ stage() {            # stage <name> <seconds> <command...>
 }
 # 1. everything added after the round-1 GPU budget was spent (simple kernels + host logic already pinned on CPU)
 stage zz_tests 600 env NSP_EXPERIMENTAL=1 python -m pytest tests -m gpu -q -k "zz and not (streamed_chunks and bf16)" --timeout=120 -p no:cacheprovider
+stage stream_kernels_gbs 200 python profiles/prof_ops.py stream_kernels      # algorithmic GB/s of the new HBM-bound kernels
 # 2. the already-validated suite (the restructured forward paths run through it)
 stage validated_suite 900 python -m pytest tests -m gpu -q -k "not zz" --timeout=300 -p no:cacheprovider
 # 3. opt-in size classes / kernels, riskiest last, on the bring-up build (bounded mbarrier waits in EVERY tcgen05 kernel: a
