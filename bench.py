@@ -53,14 +53,20 @@ def conv_args(w):
                 param_init=0.1)
 
 
-def synth_batch(w, B, seed):
-    """xs ~ N(0,1) fp32 [B,T,80]; fixed T; labels ylen = floor(0.45*T/8), ids uniform in [4, V)."""
+def synth_batch(w, B, seed, lengths="fixed"):
+    """xs ~ N(0,1) fp32 [B,T,80], zero padded; labels ylen = floor(0.45 * xlen / 8), ids uniform in [4, V).
+    lengths='fixed' (primary): every utterance T frames; 'librispeech' (secondary): xlen ~ clip(round(lognormal(ln 1200,
+    0.45)), 40, 1600), sorted by length as the reference's bucketing sampler delivers them."""
     rng = np.random.default_rng(seed)
-    T = w["T"]
-    xs = rng.standard_normal((B, T, 80)).astype(np.float32)
-    xlens = [T] * B
-    ylen = int(0.45 * T / 8)
-    ys = [rng.integers(4, w["vocab"], size=ylen).tolist() for _ in range(B)]
+    if lengths == "librispeech":
+        xlens = sorted((int(v) for v in np.clip(np.round(rng.lognormal(np.log(1200.0), 0.45, size=B)), 40, 1600)), reverse=True)
+    else:
+        xlens = [w["T"]] * B
+    T = max(xlens)
+    xs = np.zeros((B, T, 80), np.float32)
+    for b, n in enumerate(xlens):
+        xs[b, :n] = rng.standard_normal((n, 80)).astype(np.float32)
+    ys = [rng.integers(4, w["vocab"], size=max(1, int(0.45 * n / 8))).tolist() for n in xlens]
     return xs, xlens, ys
 
 
@@ -211,6 +217,9 @@ def main():
                     help="train: fwd + loss + bwd + grad all-reduce + optimizer; fwd: encoder fwd + CTC fwd/bwd + head bwd")
     ap.add_argument("--optimizer", default="adam", choices=["adam", "none"])
     ap.add_argument("--allreduce", default="bucketed", choices=["bucketed", "single"])
+    ap.add_argument("--lengths", default="fixed", choices=["fixed", "librispeech"],
+                    help="fixed: T frames per utterance (primary figure); librispeech: log-normal utterance lengths 40..1600 "
+                         "(SURVEY.md 8d secondary figure; frames/s counts valid frames only)")
     ap.add_argument("--dropout", type=float, default=0.0,
                     help="dropout_enc of the training step (LibriSpeech recipes: 0.1; dropout_att stays 0 as in the recipes). "
                          "Default 0: the dropout kernels have not been measured on hardware yet (round 2)")
@@ -229,7 +238,7 @@ def main():
                            "optimizer(%s)" % args.optimizer) if args.step == "train" else
                           "fwd: encoder_fwd + ctc_head + ctc_fwd_bwd + head_bwd (no encoder backward)",
                   "global_batch": w["B"] * world, "seq_len": w["T"], "parallelism": "dp%d" % world,
-                  "dropout": args.dropout}
+                  "dropout": args.dropout, "lengths": args.lengths}
 
     if args.impl == "reference":
         if rank != 0:
@@ -277,7 +286,7 @@ def main():
     head_params = [p for p in ctc.parameters()]
 
     B = w["B"]
-    xs_np, xlens, ys = synth_batch(w, B, 1234 + rank)
+    xs_np, xlens, ys = synth_batch(w, B, 1234 + rank, args.lengths)
     xs_host = torch.from_numpy(xs_np).pin_memory()
     xs_dev = xs_host.to(dev)
     xlens_t = torch.IntTensor(xlens)

@@ -28,6 +28,7 @@ unset NSP_LIB_PATH
 # 4. bench lines: default, recipe dropout, the two opt-in GEMM epilogue modes
 stage bench_default 600 python bench.py --steps 10 --warmup 3
 stage bench_dropout 400 python bench.py --steps 10 --warmup 3 --dropout 0.1 --no-cpu-baseline
+stage bench_librispeech_lengths 400 python bench.py --steps 10 --warmup 3 --lengths librispeech --no-cpu-baseline
 stage bench_tma 400 env NSP_GEMM_EPILOGUE=tma python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 stage bench_pair 400 env NSP_GEMM_EPILOGUE=pair python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 cat $S
