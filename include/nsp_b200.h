@@ -282,6 +282,18 @@ nsp_status nsp_lstm_seq_fwd_save(const float* gates_x, const float* w_hh, const 
 nsp_status nsp_lstm_seq_bwd(const float* dy, const float* acts, const float* cprev, const float* w_hh,
                             const int32_t* lens, float* dgates, int B, int T, int H, int ndir,
                             void* workspace, size_t workspace_bytes, void* stream);
+/* Training with a state carried across chunks (latency-controlled BLSTM, rnn.py:454-498: the forward LSTM of chunk i+1 starts
+ * from the state chunk i ended in, and autograd back-propagates through it): _fwd_save_state = _fwd_save + the initial / final
+ * state arguments of _fwd_state; _bwd_state additionally takes the gradient w.r.t. the final state (dhN, dcN; null = none)
+ * and returns the gradient w.r.t. the initial state (dh0, dc0; null = not wanted), all fp32 [ndir, B, H]. */
+nsp_status nsp_lstm_seq_fwd_save_state(const float* gates_x, const float* w_hh, const int32_t* lens, float* y,
+                                       int B, int T, int H, int ndir, float* acts, float* cprev, float* hprev,
+                                       const float* h0, const float* c0, float* hN, float* cN,
+                                       void* workspace, size_t workspace_bytes, void* stream);
+nsp_status nsp_lstm_seq_bwd_state(const float* dy, const float* acts, const float* cprev, const float* w_hh,
+                                  const int32_t* lens, float* dgates, int B, int T, int H, int ndir,
+                                  const float* dhN, const float* dcN, float* dh0, float* dc0,
+                                  void* workspace, size_t workspace_bytes, void* stream);
 
 
 /* ==========================================================================================

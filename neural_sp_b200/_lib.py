@@ -145,6 +145,10 @@ _more = {"nsp_lstm_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
          "nsp_lstm_seq_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_sz, c_vp]),
          "nsp_lstm_seq_fwd_state": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
                                             c_sz, c_vp]),
+         "nsp_lstm_seq_fwd_save_state": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                                 c_vp, c_vp, c_vp, c_sz, c_vp]),
+         "nsp_lstm_seq_bwd_state": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
+                                            c_vp, c_vp, c_sz, c_vp]),
          "nsp_lstm_seq_fwd_save": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
          "nsp_lstm_seq_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_sz, c_vp])}
 for _name, (_res, _args) in _more.items():

@@ -694,6 +694,58 @@ def lstm_layer(enc, lth, xs, lens_dev, prec):
     return _LstmLayerFn.apply(xs, enc, lth, lens_dev, prec, *params)
 
 
+class _LstmChunkFn(torch.autograd.Function):
+    """One UNIDIRECTIONAL LSTM layer over a chunk with a carried state (latency-controlled BLSTM training, rnn.py:454-498):
+    (xs, h0, c0) -> (ys, hN, cN); h0 / c0 may be None (zero state).  The backward receives the gradient w.r.t. the final state
+    from the next chunk's node and returns the gradient w.r.t. the initial one (persistent BPTT kernel, state arguments)."""
+
+    @staticmethod
+    def forward(ctx, xs, h0, c0, owner, tag, lens_dev, prec, w_ih, w_hh, b_ih, b_hh):
+        w_ihp = prepared(owner, 'w_ih' + tag, prec, (w_ih,))
+        bias = cached(owner, 'b' + tag, (b_ih, b_hh), lambda a, b: (a + b).float().contiguous())
+        whh = cached(owner, 'w_hh' + tag, (w_hh,), lambda w: w.unsqueeze(0).float().contiguous())
+        xs = xs.contiguous().float()
+        gates_x = ops.linear(xs, w_ihp, bias, prec=prec, out_dtype=torch.float32)
+        state = (h0.detach(), c0.detach()) if h0 is not None else None
+        ys, acts, cprev, hprev, (hN, cN) = ops.lstm_seq(gates_x, whh, lens_dev, 1, save=True, state=state, want_state=True)
+        ctx.save_for_backward(xs, acts, cprev, hprev, whh, lens_dev)
+        ctx.owner, ctx.tag, ctx.prec, ctx.params, ctx.has_state = owner, tag, prec, (w_ih, w_hh, b_ih, b_hh), h0 is not None
+        return ys, hN, cN
+
+    @staticmethod
+    def backward(ctx, dy, dhN, dcN):
+        xs, acts, cprev, hprev, whh, lens_dev = ctx.saved_tensors
+        prec = ctx.prec
+        w_ih, w_hh, b_ih, b_hh = ctx.params
+        G = _Grads((w_ih, w_hh, b_ih, b_hh))
+        dstate = None
+        if dhN is not None or dcN is not None:
+            z = torch.zeros_like(hprev[:, 0].transpose(0, 1))            # [1, B, H]
+            dstate = (dhN if dhN is not None else z, dcN if dcN is not None else z)
+        if dy is None:
+            dy = torch.zeros(xs.shape[0], xs.shape[1], whh.shape[-1], dtype=torch.float32, device=xs.device)
+        out = ops.lstm_seq_bwd(dy, acts, cprev, whh, lens_dev, dstate=dstate, want_dstate=ctx.has_state)
+        dg, d0 = out if ctx.has_state else (out, (None, None))
+        dgo = _gop(dg, prec)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.linear(dgo, _wT(ctx.owner, 'w_ih' + ctx.tag, prec, (w_ih,)), None, prec=prec, out_dtype=torch.float32)
+        ops.linear_wgrad(dgo, xs, prec, G.buf(w_ih))
+        ops.linear_wgrad(dgo, hprev[:, :, 0].contiguous(), prec, G.buf(w_hh))
+        ops.colsum_acc(dg, G.buf(b_ih))
+        G.buf(b_hh).copy_(G.buf(b_ih))
+        G.done()
+        return dx, d0[0], d0[1], None, None, None, None, G.get(w_ih), G.get(w_hh), G.get(b_ih), G.get(b_hh)
+
+
+def lstm_chunk(owner, tag, rnn, xs, lens_dev, state, prec):
+    """-> (ys `[B,T,H]`, (hN, cN) `[1,B,H]` each, attached to the graph)."""
+    h0, c0 = state if state is not None else (None, None)
+    ys, hN, cN = _LstmChunkFn.apply(xs, h0, c0, owner, tag, lens_dev, prec, rnn.weight_ih_l0, rnn.weight_hh_l0, rnn.bias_ih_l0,
+                                    rnn.bias_hh_l0)
+    return ys, (hN, cN)
+
+
 # ------------------------------------------------------------------------------------------------
 # RNN-T joint network + loss as one node
 # ------------------------------------------------------------------------------------------------

@@ -199,6 +199,10 @@ struct LstmBwdParams {
     float* dg;              // [B, T, ndir*4H]  (pre-zeroed)
     unsigned int* bar;      // [ndir] (pre-zeroed)
     int B, T, H, ndir, dir0;
+    // optional (state carried across chunks in training, rnn.py:470-478): gradient w.r.t. the FINAL state flowing in from the
+    // next chunk, and the gradient w.r.t. the INITIAL state flowing out to the previous one; all [ndir, B, H]
+    const float* dhN; const float* dcN;
+    float* dh0; float* dc0;
 };
 
 constexpr int KS = 8;             // k splits of the 4H-long reduction in phase c
@@ -246,8 +250,14 @@ __global__ void __launch_bounds__(256, 1) lstm_seq_bwd_kernel(LstmBwdParams p) {
                     const float cp = __ldg(p.cprev + cell * H + j0 + cu);
                     const float c = fg * cp + ig * gg;
                     const float tc = tanhf(c);
-                    const float dh = __ldg(p.dy + ((size_t)b * p.T + t) * (p.ndir * H) + (size_t)dir * H + j0 + cu) + dh_rec[bt];
-                    const float dc = dc_state[bt] + dh * og * (1.f - tc * tc);
+                    float dh = __ldg(p.dy + ((size_t)b * p.T + t) * (p.ndir * H) + (size_t)dir * H + j0 + cu) + dh_rec[bt];
+                    float dc_in = dc_state[bt];
+                    if (p.dhN && s == len - 1) {               // the final state (h_N, c_N) is the state after the last valid step
+                        const size_t si = ((size_t)dir * p.B + b) * H + j0 + cu;
+                        dh += __ldg(p.dhN + si);
+                        dc_in += __ldg(p.dcN + si);
+                    }
+                    const float dc = dc_in + dh * og * (1.f - tc * tc);
                     dc_state[bt] = dc * fg;
                     float* gr = p.dg + ((size_t)b * p.T + t) * G + (size_t)dir * H4 + j0 + cu;
                     __stcg(gr, dc * gg * ig * (1.f - ig));
@@ -257,7 +267,7 @@ __global__ void __launch_bounds__(256, 1) lstm_seq_bwd_kernel(LstmBwdParams p) {
                 }
             }
         }
-        if (s == 0) break;                             // nothing flows into the initial state
+        if (s == 0 && !p.dh0) break;                   // nothing flows into a zero initial state
         // ---- b) device-scope barrier among the CTAs of this direction ----
         __threadfence();
         __syncthreads();
@@ -323,6 +333,17 @@ __global__ void __launch_bounds__(256, 1) lstm_seq_bwd_kernel(LstmBwdParams p) {
 #pragma unroll
             for (int q = 0; q < KS; ++q) r += pre[(q * UPC + cu) * (BT + 1) + cb];
             dh_rec[bt] = r;
+        }
+    }
+    if (p.dh0) {                                       // gradient w.r.t. (h_0, c_0): what the recurrence passed below step 0
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int b = i * BT + cb;
+            if (b < p.B) {
+                const size_t si = ((size_t)dir * p.B + b) * H + j0 + cu;
+                p.dh0[si] = dh_rec[i];
+                p.dc0[si] = dc_state[i];
+            }
         }
     }
 }
@@ -401,9 +422,39 @@ extern "C" nsp_status nsp_lstm_seq_fwd_save(const float* gates_x, const float* w
     return lstm_fwd_impl(gates_x, w_hh, lens, y, B, T, H, ndir, acts, cprev, hprev, workspace, workspace_bytes, stream);
 }
 
+extern "C" nsp_status nsp_lstm_seq_fwd_save_state(const float* gates_x, const float* w_hh, const int32_t* lens, float* y,
+                                                  int B, int T, int H, int ndir, float* acts, float* cprev, float* hprev,
+                                                  const float* h0, const float* c0, float* hN, float* cN,
+                                                  void* workspace, size_t workspace_bytes, void* stream) {
+    NSP_CHECK_ARG(acts && cprev && hprev, "lstm_seq_fwd_save_state: null save buffer");
+    NSP_CHECK_ARG((hN == nullptr) == (cN == nullptr), "lstm_seq_fwd_save_state: hN and cN go together");
+    return lstm_fwd_impl(gates_x, w_hh, lens, y, B, T, H, ndir, acts, cprev, hprev, workspace, workspace_bytes, stream, h0, c0, hN, cN);
+}
+
+static nsp_status lstm_bwd_impl(const float* dy, const float* acts, const float* cprev, const float* w_hh,
+                                const int32_t* lens, float* dgates, int B, int T, int H, int ndir,
+                                const float* dhN, const float* dcN, float* dh0, float* dc0,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
 extern "C" nsp_status nsp_lstm_seq_bwd(const float* dy, const float* acts, const float* cprev, const float* w_hh,
                                        const int32_t* lens, float* dgates, int B, int T, int H, int ndir,
                                        void* workspace, size_t workspace_bytes, void* stream) {
+    return lstm_bwd_impl(dy, acts, cprev, w_hh, lens, dgates, B, T, H, ndir, nullptr, nullptr, nullptr, nullptr, workspace,
+                         workspace_bytes, stream);
+}
+
+extern "C" nsp_status nsp_lstm_seq_bwd_state(const float* dy, const float* acts, const float* cprev, const float* w_hh,
+                                             const int32_t* lens, float* dgates, int B, int T, int H, int ndir,
+                                             const float* dhN, const float* dcN, float* dh0, float* dc0,
+                                             void* workspace, size_t workspace_bytes, void* stream) {
+    NSP_CHECK_ARG((dhN == nullptr) == (dcN == nullptr) && (dh0 == nullptr) == (dc0 == nullptr), "lstm_seq_bwd_state: state gradients come in pairs");
+    return lstm_bwd_impl(dy, acts, cprev, w_hh, lens, dgates, B, T, H, ndir, dhN, dcN, dh0, dc0, workspace, workspace_bytes, stream);
+}
+
+static nsp_status lstm_bwd_impl(const float* dy, const float* acts, const float* cprev, const float* w_hh,
+                                const int32_t* lens, float* dgates, int B, int T, int H, int ndir,
+                                const float* dhN, const float* dcN, float* dh0, float* dc0,
+                                void* workspace, size_t workspace_bytes, void* stream) {
     NSP_CHECK_ARG(dy && acts && cprev && w_hh && lens && dgates && workspace, "lstm_seq_bwd: null pointer");
     NSP_CHECK_ARG(B > 0 && T > 0 && H > 0 && (ndir == 1 || ndir == 2), "lstm_seq_bwd: bad shape");
     if (H % UPC != 0 || H % 4 != 0) { set_error("lstm_seq_bwd: H=%d must be a multiple of 8", H); return NSP_ERR_UNSUPPORTED; }
@@ -424,6 +475,7 @@ extern "C" nsp_status nsp_lstm_seq_bwd(const float* dy, const float* acts, const
     LstmBwdParams p;
     p.dy = dy; p.acts = acts; p.cprev = cprev; p.whh = w_hh; p.lens = lens; p.dg = dgates;
     p.B = B; p.T = T; p.H = H; p.ndir = ndir;
+    p.dhN = dhN; p.dcN = dcN; p.dh0 = dh0; p.dc0 = dc0;
     p.bar = (unsigned int*)workspace;
     NSP_CUDA_OK(cudaMemsetAsync(workspace, 0, 256, st));
     NSP_CUDA_OK(cudaMemsetAsync(dgates, 0, (size_t)B * T * ndir * 4 * H * sizeof(float), st));

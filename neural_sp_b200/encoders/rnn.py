@@ -13,8 +13,8 @@ the kernel's initial / final state arguments; like the reference's un-packed ``r
 processed over all of its frames.  Latency-controlled BLSTM (``chunk_size_current/right`` with a bidirectional type,
 :427-510): separate ``rnn`` / ``rnn_bwd`` unidirectional LSTMs per layer, the forward one carrying its state over N_c
 frames and looking N_r frames ahead, the backward one restarted on every chunk; offline it loops over the chunks of the
-utterance, streaming it encodes one.  Inference only (the LC training path and random state passing are not on the
-B200 path).  The reference sorts the batch by length before the layers and un-sorts afterwards (:296-298, :375-377);
+utterance, streaming it encodes one; in training the forward LSTM's state stays attached to the graph from chunk to chunk
+(the BPTT kernel takes / returns state gradients).  Random state passing is not on the B200 path.  The reference sorts the batch by length before the layers and un-sorts afterwards (:296-298, :375-377);
 nothing here needs the sort, so carried states stay in the caller's batch order."""
 import math
 
@@ -147,51 +147,57 @@ class RNNEncoder(EncoderBase):
     def _full_lens(self, xs):
         return lens_to_device(torch.IntTensor([xs.size(1)] * xs.size(0)), xs.device)
 
-    def _lc_layer(self, lth, xs, n_carry):
+    def _uni(self, rnn, tag, xs, state, train):
+        """One unidirectional LSTM over all frames of `xs` from `state` -> (ys, new state)."""
+        full = self._full_lens(xs)
+        if train:
+            return ag.lstm_chunk(self, tag, rnn, xs, full, state, get_precision(self))
+        return self._run_lstm(rnn, tag, xs, full, ['_l0'], state, want_state=True)
+
+    def _lc_layer(self, lth, xs, n_carry, train=False):
         """One latency-controlled layer over a chunk `[B, <= N_c + N_r, I]` (reference :460-481): the backward LSTM runs
         over the whole chunk from a zero state; the forward LSTM continues from the carried state, which is saved after
-        the first `n_carry` (= N_c at this depth) frames so that the look-ahead frames do not leak into the next chunk."""
-        full = self._full_lens(xs)
-        rev = torch.flip(xs, dims=[1])
-        ys_bwd = torch.flip(self._run_lstm(self.rnn_bwd[lth], 'bwd%d' % lth, rev, full, ['_l0']), dims=[1])
+        the first `n_carry` (= N_c at this depth) frames so that the look-ahead frames do not leak into the next chunk.
+        In training the carried state stays attached to the graph: the loss back-propagates through it into earlier chunks."""
+        ys_bwd = torch.flip(self._uni(self.rnn_bwd[lth], 'bwd%d' % lth, torch.flip(xs, dims=[1]), None, train)[0], dims=[1])
         if xs.size(1) <= n_carry:                                   # last chunk of the utterance
-            ys_fwd, self.hx_fwd[lth] = self._run_lstm(self.rnn[lth], '%d' % lth, xs, full, ['_l0'],
-                                                      self.hx_fwd[lth], want_state=True)
+            ys_fwd, self.hx_fwd[lth] = self._uni(self.rnn[lth], '%d' % lth, xs, self.hx_fwd[lth], train)
         else:
             head, tail = xs[:, :n_carry].contiguous(), xs[:, n_carry:].contiguous()
-            y1, self.hx_fwd[lth] = self._run_lstm(self.rnn[lth], '%d' % lth, head, self._full_lens(head), ['_l0'],
-                                                  self.hx_fwd[lth], want_state=True)
-            y2, _ = self._run_lstm(self.rnn[lth], '%d' % lth, tail, self._full_lens(tail), ['_l0'], self.hx_fwd[lth],
-                                   want_state=True)
+            y1, self.hx_fwd[lth] = self._uni(self.rnn[lth], '%d' % lth, head, self.hx_fwd[lth], train)
+            y2, _ = self._uni(self.rnn[lth], '%d' % lth, tail, self.hx_fwd[lth], train)
             ys_fwd = torch.cat([y1, y2], dim=1)
-        return ys_fwd + ys_bwd if self.bidir_sum else torch.cat([ys_fwd, ys_bwd], dim=-1)
+        ys = ys_fwd + ys_bwd if self.bidir_sum else torch.cat([ys_fwd, ys_bwd], dim=-1)
+        return ag.dropout(ys, self.dropout.p) if train else ys
 
-    def _lc_tail(self, lth, xs, xlens):
+    def _lc_tail(self, lth, xs, xlens, train=False):
         """Projection (+ReLU) and subsampling after an LC layer; returns (xs, xlens)."""
         prec = get_precision(self)
         if self.proj is not None and lth != self.n_layers - 1:
             lin = self.proj[lth]
-            xs = ops.linear(xs, prepared(self, 'proj%d' % lth, prec, (lin.weight,)), lin.bias, prec=prec, act='relu')
+            if train:
+                xs = ag.linear_relu(self, 'proj%d' % lth, lin.weight, lin.bias, xs, prec)
+            else:
+                xs = ops.linear(xs, prepared(self, 'proj%d' % lth, prec, (lin.weight,)), lin.bias, prec=prec, act='relu')
         if self.subsample is not None:
-            xs, xlens = self.subsample[lth](xs, xlens)
+            xs, xlens = ag.subsample_train(self.subsample[lth], xs, xlens) if train else self.subsample[lth](xs, xlens)
         return xs, xlens
 
-    def _forward_full_context(self, xs, xlens):
+    def _forward_full_context(self, xs, xlens, train=False):
         """LC encoder without a current-chunk size (N_c <= 0): whole utterance at once (reference :385-425)."""
         xs_sub1 = xlens_sub1 = None
         for lth in range(self.n_layers):
-            full = self._full_lens(xs)
-            ys_bwd = torch.flip(self._run_lstm(self.rnn_bwd[lth], 'bwd%d' % lth, torch.flip(xs, dims=[1]), full, ['_l0']),
-                                dims=[1])
-            ys_fwd, self.hx_fwd[lth] = self._run_lstm(self.rnn[lth], '%d' % lth, xs, full, ['_l0'], self.hx_fwd[lth],
-                                                      want_state=True)
+            ys_bwd = torch.flip(self._uni(self.rnn_bwd[lth], 'bwd%d' % lth, torch.flip(xs, dims=[1]), None, train)[0], dims=[1])
+            ys_fwd, self.hx_fwd[lth] = self._uni(self.rnn[lth], '%d' % lth, xs, self.hx_fwd[lth], train)
             xs = ys_fwd + ys_bwd if self.bidir_sum else torch.cat([ys_fwd, ys_bwd], dim=-1)
+            if train:
+                xs = ag.dropout(xs, self.dropout.p)
             if lth == self.n_layers_sub1 - 1:
-                xs_sub1, xlens_sub1 = self._sub_out(xs, 'sub1'), xlens.clone()
-            xs, xlens = self._lc_tail(lth, xs, xlens)
+                xs_sub1, xlens_sub1 = self._sub_out(xs, 'sub1', train), xlens.clone()
+            xs, xlens = self._lc_tail(lth, xs, xlens, train)
         return xs, xlens, xs_sub1, xlens_sub1
 
-    def _forward_latency_controlled(self, xs, xlens, N_c, N_r, streaming):
+    def _forward_latency_controlled(self, xs, xlens, N_c, N_r, streaming, train=False):
         """Chunk loop of the LC-BLSTM (reference :427-510): layer loop inside the chunk loop; streaming = one chunk."""
         bs, xmax, _ = xs.size()
         n_chunks = math.ceil(xmax / N_c)
@@ -203,12 +209,12 @@ class RNNEncoder(EncoderBase):
             xs_chunk = xs[:, t:t + (N_c + N_r)].contiguous()
             n_c = N_c
             for lth in range(self.n_layers):
-                xs_chunk = self._lc_layer(lth, xs_chunk, n_c)
+                xs_chunk = self._lc_layer(lth, xs_chunk, n_c, train)
                 if lth == self.n_layers_sub1 - 1:
                     chunks_sub1.append(xs_chunk[:, :n_c].clone())
                     if chunk_idx == 0:
                         xlens_sub1 = xlens.clone()
-                xs_chunk, xlens_tmp = self._lc_tail(lth, xs_chunk, xlens)
+                xs_chunk, xlens_tmp = self._lc_tail(lth, xs_chunk, xlens, train)
                 if self.subsample is not None:
                     if chunk_idx == 0:
                         xlens = xlens_tmp
@@ -219,7 +225,7 @@ class RNNEncoder(EncoderBase):
         xs = torch.cat(chunks, dim=1)
         xs_sub1 = None
         if self.n_layers_sub1 > 0:
-            xs_sub1 = self._sub_out(torch.cat(chunks_sub1, dim=1), 'sub1')
+            xs_sub1 = self._sub_out(torch.cat(chunks_sub1, dim=1), 'sub1', train)
         return xs, xlens, xs_sub1, xlens_sub1
 
     def _sub_out(self, xs, module, train=False):
@@ -257,9 +263,8 @@ class RNNEncoder(EncoderBase):
         if train and self.rsp_prob > 0:
             raise NotImplementedError("random state passing (rsp_prob > 0) needs a carried initial state in the training "
                                       "LSTM node; not on the B200 path (it is inactive in eval mode)")
-        if train and (streaming or self.lc_bidir):
-            raise NotImplementedError("streaming / latency-controlled BLSTM encoding is an inference path "
-                                      "(call .eval() / torch.no_grad())")
+        if train and streaming:
+            raise NotImplementedError("streaming=True is an inference path (call .eval() / torch.no_grad())")
         with (torch.enable_grad() if train else torch.no_grad()):
             bs = xs.size(0)
             N_c, N_r = self.N_c, self.N_r
@@ -284,9 +289,9 @@ class RNNEncoder(EncoderBase):
             xs = xs.float()
             if self.lc_bidir:
                 if self.N_c <= 0:
-                    xs, xlens, xs_sub1, xlens_sub1 = self._forward_full_context(xs, xlens)
+                    xs, xlens, xs_sub1, xlens_sub1 = self._forward_full_context(xs, xlens, train)
                 else:
-                    xs, xlens, xs_sub1, xlens_sub1 = self._forward_latency_controlled(xs, xlens, N_c, N_r, streaming)
+                    xs, xlens, xs_sub1, xlens_sub1 = self._forward_latency_controlled(xs, xlens, N_c, N_r, streaming, train)
                 if task == 'ys_sub1':
                     eouts[task]['xs'], eouts[task]['xlens'] = xs_sub1, xlens_sub1
                     return eouts

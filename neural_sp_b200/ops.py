@@ -507,23 +507,28 @@ def lstm_seq(gates_x, w_hh, lens, n_dirs, save=False, state=None, want_state=Fal
     ws_bytes = lib.nsp_lstm_workspace_bytes(B, H, n_dirs)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=gates_x.device)
     y = torch.empty(B, T, n_dirs * H, dtype=torch.float32, device=gates_x.device)
+    h0 = c0 = hN = cN = None
     if state is not None or want_state:
-        assert not save, "the training path starts from a zero state"
-        h0 = c0 = None
         if state is not None:
             h0, c0 = (t.contiguous().float() for t in state)
             _require_cuda(h0, c0)
             assert h0.shape == (n_dirs, B, H) and c0.shape == (n_dirs, B, H), (h0.shape, c0.shape, (n_dirs, B, H))
         hN = torch.empty(n_dirs, B, H, dtype=torch.float32, device=gates_x.device)
         cN = torch.empty(n_dirs, B, H, dtype=torch.float32, device=gates_x.device)
-        _run("nsp_lstm_seq_fwd_state", lib.nsp_lstm_seq_fwd_state, ptr(gates_x), ptr(w_hh), ptr(lens), ptr(y), B, T, H, n_dirs,
-             ptr(h0), ptr(c0), ptr(hN), ptr(cN), ptr(ws), ws_bytes, current_stream_ptr(),
-             flops=2.0 * B * T * n_dirs * 4 * H * H, tag="lstm_seq")
-        return y, (hN, cN)
+        if not save:
+            _run("nsp_lstm_seq_fwd_state", lib.nsp_lstm_seq_fwd_state, ptr(gates_x), ptr(w_hh), ptr(lens), ptr(y), B, T, H, n_dirs,
+                 ptr(h0), ptr(c0), ptr(hN), ptr(cN), ptr(ws), ws_bytes, current_stream_ptr(),
+                 flops=2.0 * B * T * n_dirs * 4 * H * H, tag="lstm_seq")
+            return y, (hN, cN)
     if save:
         acts = torch.zeros(B, T, n_dirs, 4 * H, dtype=torch.float32, device=gates_x.device)
         cprev = torch.zeros(B, T, n_dirs, H, dtype=torch.float32, device=gates_x.device)
         hprev = torch.zeros(B, T, n_dirs, H, dtype=torch.float32, device=gates_x.device)
+        if hN is not None:          # training with a carried state (latency-controlled BLSTM)
+            _run("nsp_lstm_seq_fwd_save_state", lib.nsp_lstm_seq_fwd_save_state, ptr(gates_x), ptr(w_hh), ptr(lens), ptr(y), B, T, H,
+                 n_dirs, ptr(acts), ptr(cprev), ptr(hprev), ptr(h0), ptr(c0), ptr(hN), ptr(cN), ptr(ws), ws_bytes,
+                 current_stream_ptr(), flops=2.0 * B * T * n_dirs * 4 * H * H, tag="lstm_seq")
+            return y, acts, cprev, hprev, (hN, cN)
         _run("nsp_lstm_seq_fwd_save", lib.nsp_lstm_seq_fwd_save, ptr(gates_x), ptr(w_hh), ptr(lens), ptr(y), B, T, H, n_dirs,
              ptr(acts), ptr(cprev), ptr(hprev), ptr(ws), ws_bytes, current_stream_ptr(),
              flops=2.0 * B * T * n_dirs * 4 * H * H, tag="lstm_seq")
@@ -533,9 +538,10 @@ def lstm_seq(gates_x, w_hh, lens, n_dirs, save=False, state=None, want_state=Fal
     return y
 
 
-def lstm_seq_bwd(dy, acts, cprev, w_hh, lens):
+def lstm_seq_bwd(dy, acts, cprev, w_hh, lens, dstate=None, want_dstate=False):
     """Backpropagation through time of lstm_seq (nsp_lstm_seq_bwd): dy fp32 `[B,T,n_dirs*H]` + what the forward saved ->
-    d loss / d gate pre-activations fp32 `[B,T,n_dirs*4H]` (the layout of gates_x; zero beyond each length)."""
+    d loss / d gate pre-activations fp32 `[B,T,n_dirs*4H]` (the layout of gates_x; zero beyond each length).
+    dstate = (dhN, dcN): gradient w.r.t. the final state; want_dstate -> (dg, (dh0, dc0)) (nsp_lstm_seq_bwd_state)."""
     _require_cuda(dy, acts, cprev, w_hh, lens)
     B, T, n_dirs, H4 = acts.shape
     H = H4 // 4
@@ -544,6 +550,18 @@ def lstm_seq_bwd(dy, acts, cprev, w_hh, lens):
     w_hh = w_hh.contiguous().float()
     dg = torch.empty(B, T, n_dirs * H4, dtype=torch.float32, device=dy.device)
     ws = torch.empty(256, dtype=torch.uint8, device=dy.device)
+    if dstate is not None or want_dstate:
+        dhN = dcN = dh0 = dc0 = None
+        if dstate is not None:
+            dhN, dcN = (t.contiguous().float() for t in dstate)
+            assert dhN.shape == (n_dirs, B, H) and dcN.shape == (n_dirs, B, H)
+        if want_dstate:
+            dh0 = torch.zeros(n_dirs, B, H, dtype=torch.float32, device=dy.device)
+            dc0 = torch.zeros(n_dirs, B, H, dtype=torch.float32, device=dy.device)
+        _run("nsp_lstm_seq_bwd_state", lib.nsp_lstm_seq_bwd_state, ptr(dy), ptr(acts), ptr(cprev), ptr(w_hh), ptr(lens), ptr(dg),
+             B, T, H, n_dirs, ptr(dhN), ptr(dcN), ptr(dh0), ptr(dc0), ptr(ws), 256, current_stream_ptr(),
+             flops=2.0 * B * T * n_dirs * 4 * H * H, tag="lstm_seq_bwd")
+        return (dg, (dh0, dc0)) if want_dstate else dg
     _run("nsp_lstm_seq_bwd", lib.nsp_lstm_seq_bwd, ptr(dy), ptr(acts), ptr(cprev), ptr(w_hh), ptr(lens), ptr(dg), B, T, H, n_dirs,
          ptr(ws), 256, current_stream_ptr(), flops=2.0 * B * T * n_dirs * 4 * H * H, tag="lstm_seq_bwd")
     return dg

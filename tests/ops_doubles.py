@@ -208,21 +208,25 @@ def lstm_seq(gates_x, w_hh, lens, n_dirs, save=False, state=None, want_state=Fal
                 y[b, t, d * H:(d + 1) * H] = h
             hN[d, b], cN[d, b] = h, c
     if save:
-        return y, acts, cprev, hprev
+        return (y, acts, cprev, hprev, (hN, cN)) if (state is not None or want_state) else (y, acts, cprev, hprev)
     if state is not None or want_state:
         return y, (hN, cN)
     return y
 
 
-def lstm_seq_bwd(dy, acts, cprev, w_hh, lens):
-    """BPTT with the kernel's step structure (csrc/lstm.cu): cell backward -> dG_t, then dh_rec = dG_t W_hh."""
+def lstm_seq_bwd(dy, acts, cprev, w_hh, lens, dstate=None, want_dstate=False):
+    """BPTT with the kernel's step structure (csrc/lstm.cu): cell backward -> dG_t, then dh_rec = dG_t W_hh; optional
+    gradient w.r.t. the final state in, gradient w.r.t. the initial state out."""
     B, T, nd, H4 = acts.shape
     H = H4 // 4
     dG = torch.zeros(B, T, nd * H4)
+    dh0, dc0 = torch.zeros(nd, B, H), torch.zeros(nd, B, H)
     for d in range(nd):
         for b in range(B):
             n = min(max(int(lens[b]), 0), T)
             dc, dhr = torch.zeros(H), torch.zeros(H)
+            if dstate is not None:
+                dhr, dc = dstate[0][d, b].clone().float(), dstate[1][d, b].clone().float()
             for s in range(n - 1, -1, -1):
                 t = s if d == 0 else n - 1 - s
                 i, f, gg, o = acts[b, t, d].split(H)
@@ -234,7 +238,8 @@ def lstm_seq_bwd(dy, acts, cprev, w_hh, lens):
                 x = torch.cat([dcc * gg * i * (1 - i), dcc * c0 * f * (1 - f), dcc * i * (1 - gg * gg), dh * tc * o * (1 - o)])
                 dG[b, t, d * H4:(d + 1) * H4] = x
                 dhr = x @ w_hh[d].float()
-    return dG
+            dh0[d, b], dc0[d, b] = dhr, dc
+    return (dG, (dh0, dc0)) if want_dstate else dG
 
 
 # ---- RNN-T ----
