@@ -839,12 +839,18 @@ class _FrontendFn(torch.autograd.Function):
             a1 = _conv_any(blk, "conv1", blk.conv1, x, B, T, F, i == 0, prec)
             a2 = _conv_any(blk, "conv2", blk.conv2, a1, B, T, F, False, prec)
             rec = dict(x=x, a1=a1, a2=a2, T=T, F=F, pt=pt, pf=pf, chmajor=last_chmajor, first=(i == 0))
+            st, sf = getattr(blk, "stride", (1, 1))
+            a2s = a2
+            if (st, sf) != (1, 1):          # strided 'same' conv = the stride-1 conv sampled at 0, s, 2s, ... (ReLU commutes)
+                a2s = a2.view(B, T, F, -1)[:, ::st, ::sf].contiguous()
+                rec.update(stride=(st, sf), a2s=a2s, Ts=a2s.size(1), Fs=a2s.size(2))
+                T, F = a2s.size(1), a2s.size(2)
             if blk.pool is not None or last_chmajor:
-                x = ops.maxpool2d(a2, pt, pf, out_chmajor=last_chmajor)
+                x = ops.maxpool2d(a2s.view(B, T, F, -1), pt, pf, out_chmajor=last_chmajor)
                 rec["pooled"] = True
                 T, F = -(-T // pt), -(-F // pf)
             else:
-                x = a2
+                x = a2s
                 rec["pooled"] = False
             tape.append(rec)
         C, Fo = enc._c_last, F
@@ -887,7 +893,15 @@ class _FrontendFn(torch.autograd.Function):
         for blk, rec in zip(reversed(list(enc.layers)), reversed(tape)):
             T, F = rec["T"], rec["F"]
             a1, a2, x = rec["a1"], rec["a2"], rec["x"]
-            if rec["pooled"]:
+            if "stride" in rec:             # gradient of the sampled positions, scattered back onto the stride-1 grid
+                a2s, Ts, Fs = rec["a2s"], rec["Ts"], rec["Fs"]
+                if rec["pooled"]:
+                    dzs = ops.maxpool2d_relu_bwd(a2s.view(B, Ts, Fs, -1), d, rec["pt"], rec["pf"], in_chmajor=rec["chmajor"])
+                else:
+                    dzs = ops.relu_mask(d.reshape(a2s.shape).to(a2s.dtype), a2s)
+                dz2 = torch.zeros(B, T, F, a2s.shape[-1], dtype=dzs.dtype, device=dzs.device)
+                dz2[:, ::rec["stride"][0], ::rec["stride"][1]] = dzs.view(B, Ts, Fs, -1)
+            elif rec["pooled"]:
                 dz2 = ops.maxpool2d_relu_bwd(a2.view(B, T, F, -1), d, rec["pt"], rec["pf"], in_chmajor=rec["chmajor"])
             else:
                 dz2 = ops.relu_mask(d.reshape(a2.shape).to(a2.dtype), a2)
@@ -909,8 +923,8 @@ def frontend_check(enc):
     for blk in enc.layers:
         if blk.training and blk.dropout.p > 0:
             raise NotImplementedError("dropout > 0 in the CNN front-end is not on the B200 path (build_encoder passes 0)")
-        if not blk.plain:
-            raise NotImplementedError("training path of the CNN front-end: stride (1,1), no normalisation, no residual only")
+        if not blk.trainable:
+            raise NotImplementedError("training path of the CNN front-end: no normalisation, no residual only")
 
 
 def frontend_forward(enc, xs, out_scale, prec):

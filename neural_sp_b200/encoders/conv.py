@@ -80,7 +80,8 @@ class Conv2dBlock(EncoderBase):
             self._factor *= pooling[0]
         self.pool = self.pooling if self._factor > 1 or self.pooling[1] > 1 else None
         # the recipes' shape: fused kernels + training path
-        self.plain = self.norm1 is None and self.stride == (1, 1) and not (residual and in_channel == out_channel)
+        self.trainable = self.norm1 is None and not (residual and in_channel == out_channel)
+        self.plain = self.trainable and self.stride == (1, 1)
 
     @staticmethod
     def _make_norm(normalization, channel, idim):
@@ -157,7 +158,8 @@ class Conv2dBlock(EncoderBase):
     def _forward_general(self, xs, xlens, B, T, F, first, last_chmajor, lookback, lookahead):
         """Strided / normalised / residual blocks (inference), fp32 channels-last activations."""
         if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("training path of the CNN front-end: stride (1,1), no normalisation, no residual only")
+            raise NotImplementedError("this block shape trains through autograd.frontend_forward only (no normalisation, "
+                                      "no residual)")
         pt, pf = self.pooling if self.pool is not None else (1, 1)
         res = None
         if self.residual and first and self.conv1.in_channels == self.conv2.out_channels:
@@ -225,7 +227,7 @@ class Conv1dBlock(EncoderBase):
         self.norm2 = nn.LayerNorm(out_channel, eps=1e-12) if normalization == 'layer_norm' else None
         self.pool = pooling if pooling > 1 else None
         self._odim = out_channel
-        self.plain = False              # no training path
+        self.plain = self.trainable = False     # trains through train_forward, not through the fused 2-D node
 
     def _conv(self, name, conv, norm, xs, stride, residual_t):
         prec = get_precision(self)
@@ -245,10 +247,29 @@ class Conv1dBlock(EncoderBase):
             y = ops.relu_mask(y.contiguous(), y.contiguous())
         return y
 
+    def train_forward(self, xs, xlens):
+        """Training path (autograd nodes: GEMM + fused ReLU with tcgen05 dgrad / wgrad, time max-pool); the un-normalised,
+        non-residual block shape only."""
+        from .. import autograd as ag
+        if self.norm1 is not None or self.residual:
+            raise NotImplementedError("training path of the 1-D CNN front-end: no normalisation, no residual only")
+        prec = get_precision(self)
+        k = self.kernel_size
+        for name, conv, stride in (("conv1", self.conv1, 1), ("conv2", self.conv2, self.stride)):
+            B, T, C = xs.shape
+            To = _conv1d_len(T, k, stride)
+            cols = torch.nn.functional.pad(xs, (0, 0, 1, 1)).unfold(1, k, stride)[:, :To].reshape(B, To, C * k)
+            xs = ag.linear_relu(self, name + "_ck", conv.weight, conv.bias, cols, prec)
+            xlens = torch.IntTensor([_conv1d_len(int(n), k, stride) for n in xlens])
+        if self.pool is not None:
+            xs = ag.maxpool_time(xs, self.pool)
+            xlens = torch.IntTensor([_pool_len(int(n), self.pool) for n in xlens])
+        return xs, xlens
+
     def forward(self, xs, xlens, lookback=False, lookahead=False):
         """xs fp32 `[B, T, C_in]` -> (`[B, T', C_out]`, xlens); lookback / lookahead are accepted and unused, as in the reference."""
         if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("1-D CNN front-end: inference only on the B200 path")
+            return self.train_forward(xs.float(), xlens)
         k = self.kernel_size
         res = xs.float().contiguous() if self.residual else None
         xs = self._conv("conv1", self.conv1, self.norm1, xs.float(), 1, None)
@@ -321,9 +342,9 @@ class ConvEncoder(EncoderBase):
     def output_lens(self, xlens):
         """Length arithmetic of the block stack alone (reference conv.py:451-477), for the training path."""
         for block in self.layers:
-            if not block.plain:
-                raise NotImplementedError("training path of the CNN front-end: stride (1,1), no normalisation, no residual only")
-            xlens = torch.IntTensor([_conv_len(_conv_len(int(n), 1), 1) for n in xlens])
+            if not block.trainable:
+                raise NotImplementedError("training path of the CNN front-end: no normalisation, no residual only")
+            xlens = torch.IntTensor([_conv_len(_conv_len(int(n), 1), block.stride[0]) for n in xlens])
             if block.pool is not None:
                 xlens = torch.IntTensor([_pool_len(int(n), block.pooling[0]) for n in xlens])
         return xlens
@@ -336,6 +357,13 @@ class ConvEncoder(EncoderBase):
         xs = xs.contiguous().float()
         n = len(self.layers)
         if self.is_1dconv:
+            if self.training and torch.is_grad_enabled():
+                from .. import autograd as ag
+                for block in self.layers:
+                    xs, xlens = block.train_forward(xs, xlens)
+                if self.bridge is not None:
+                    xs = ag.linear(self, "bridge1d", self.bridge, xs, prec)
+                return ag.scale(xs, out_scale), xlens
             for block in self.layers:
                 xs, xlens = block(xs, xlens, lookback=lookback, lookahead=lookahead)
             if self.bridge is not None:

@@ -276,7 +276,10 @@ class RNNEncoder(EncoderBase):
                 if train:
                     if lookback or lookahead:
                         raise NotImplementedError("CNN lookback/lookahead trimming is an inference (streaming) feature")
-                    xs, xlens = ag.frontend_forward(self.conv, xs, 1.0, prec), self.conv.output_lens(xlens)
+                    if self.conv.is_1dconv:
+                        xs, xlens = self.conv(xs, xlens)
+                    else:
+                        xs, xlens = ag.frontend_forward(self.conv, xs, 1.0, prec), self.conv.output_lens(xlens)
                 else:
                     xs, xlens = self.conv(xs, xlens, lookback=lookback, lookahead=lookahead)
                 if self.enc_type == 'conv':

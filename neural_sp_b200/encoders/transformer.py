@@ -285,8 +285,11 @@ class TransformerEncoder(EncoderBase):
             elif train:
                 if lookback or lookahead:
                     raise NotImplementedError("CNN lookback/lookahead trimming is an inference (streaming) feature")
-                xs = ag.frontend_forward(self.conv, xs, self.scale if (rel and self.enc_type != 'conv') else 1.0, prec)
-                xlens = self.conv.output_lens(xlens)
+                if self.conv.is_1dconv:       # composed of GEMM / pooling nodes inside the front-end module
+                    xs, xlens = self.conv(xs, xlens, out_scale=self.scale if (rel and self.enc_type != 'conv') else 1.0)
+                else:
+                    xs = ag.frontend_forward(self.conv, xs, self.scale if (rel and self.enc_type != 'conv') else 1.0, prec)
+                    xlens = self.conv.output_lens(xlens)
                 N_l, N_c, N_r = max(0, N_l // self.conv_factor), N_c // self.conv_factor, N_r // self.conv_factor
             else:
                 xs, xlens = self.conv(xs, xlens, lookback=False if self.lc_bidir else lookback,

@@ -510,6 +510,34 @@ def rng_advance(state):
     state[1] += 1
 
 
+def conv3x3_wgrad(a, dz, dw, dbias, B, T, Fq, in_chmajor=False):
+    CO, CI = dw.shape[0], dw.shape[1]
+    with torch.enable_grad():
+        w = torch.zeros_like(dw, requires_grad=True)
+        b = torch.zeros(CO, requires_grad=True)
+        xin = (a.float().reshape(B, T, CI, Fq).permute(0, 2, 1, 3) if in_chmajor else a.float().reshape(B, T, Fq, CI).permute(0, 3, 1, 2))
+        y = F.conv2d(xin, w, b, padding=1).permute(0, 2, 3, 1)
+        y.backward(dz.float().reshape(B, T, Fq, CO))
+    dw.add_(w.grad)
+    if dbias is not None:
+        dbias.add_(b.grad)
+    return dw
+
+
+def maxpool2d_relu_bwd(a, dy, pool_t, pool_f, in_chmajor=False):
+    """a = saved post-ReLU activation `[B,T,F,C]`; dy = gradient of the pooled tensor (`[B,T',F',C]` or `[B,T',C*F']`)."""
+    B, T, Fq, C = a.shape
+    with torch.enable_grad():
+        aa = a.detach().float().clone().requires_grad_(True)
+        y = F.max_pool2d(aa.permute(0, 3, 1, 2), (pool_t, pool_f), (pool_t, pool_f), ceil_mode=True)      # [B, C, To, Fo]
+        if in_chmajor:
+            g = dy.float().reshape(B, y.shape[2], C, y.shape[3]).permute(0, 2, 1, 3)
+        else:
+            g = dy.float().reshape(B, y.shape[2], y.shape[3], C).permute(0, 3, 1, 2)
+        y.backward(g)
+    return torch.where(a.float() > 0, aa.grad, torch.zeros(())).to(a.dtype)
+
+
 def pack_labels(ys, device):
     Lmax = max(1, max((len(y) for y in ys), default=1))
     lab = torch.tensor([list(y) + [0] * (Lmax - len(y)) for y in ys], dtype=torch.int32)
@@ -544,7 +572,7 @@ def frontend_forward(enc, xs, out_scale, prec):
     x = xs.view(B, T, enc.in_channel, Fd // enc.in_channel).transpose(1, 2)
     for blk in enc.layers:
         x = torch.relu(F.conv2d(x, blk.conv1.weight, blk.conv1.bias, padding=1))
-        x = torch.relu(F.conv2d(x, blk.conv2.weight, blk.conv2.bias, padding=1))
+        x = torch.relu(F.conv2d(x, blk.conv2.weight, blk.conv2.bias, padding=1, stride=tuple(getattr(blk, "stride", (1, 1)))))
         if blk.pool is not None:
             x = F.max_pool2d(x, blk.pooling, blk.pooling, ceil_mode=True)
     B, C, T, Fq = x.shape
@@ -561,7 +589,8 @@ TRAIN_DOUBLES = dict(DOUBLES, linear=_linear_train, linear_wgrad=linear_wgrad, c
                      rng_advance=rng_advance, lstm_seq_bwd=lstm_seq_bwd, rnnt_joint_tanh=rnnt_joint_tanh,
                      softmax_rows=softmax_rows, rnnt_loss_fwd_bwd=rnnt_loss_fwd_bwd, rnnt_grad_logits=rnnt_grad_logits, log_softmax_bwd_=log_softmax_bwd_,
                      rnnt_joint_tanh_bwd=rnnt_joint_tanh_bwd, pack_labels=pack_labels, ctc_loss_fwd_bwd=ctc_loss_fwd_bwd,
-                     dwconv_stats=dwconv_stats, bn_swish_bwd=bn_swish_bwd, dwconv_bwd=dwconv_bwd)
+                     dwconv_stats=dwconv_stats, bn_swish_bwd=bn_swish_bwd, dwconv_bwd=dwconv_bwd, conv3x3_wgrad=conv3x3_wgrad,
+                     maxpool2d_relu_bwd=maxpool2d_relu_bwd)
 
 
 def install_training(monkeypatch):

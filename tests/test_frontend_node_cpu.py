@@ -1,0 +1,48 @@
+"""The CNN front-end's training node (neural_sp_b200/autograd.py _FrontendFn: the hand-written backward chain -- ReLU / pooling
+masks, input-gradient convolutions with flipped taps, weight gradients, the bridge's permuted columns, the strided blocks'
+scatter back onto the stride-1 grid) on CPU: the REAL node with its ops replaced by torch restatements, against torch autograd
+through the plain conv stack.  Runs wherever the repository does."""
+import numpy as np
+import pytest
+import torch
+
+
+def _cfg(**kw):
+    a = dict(input_dim=80, in_channel=1, channels="32_32", kernel_sizes="(3,3)_(3,3)", strides="(1,1)_(1,1)",
+             poolings="(2,2)_(2,2)", dropout=0.0, normalization='', residual=False, bottleneck_dim=0, param_init=0.1)
+    a.update(kw)
+    return a
+
+
+@pytest.mark.parametrize("ov", [
+    dict(), dict(poolings="(1,1)_(2,2)", bottleneck_dim=24), dict(poolings="(2,2)_(2,1)"), dict(poolings="(1,1)_(1,1)", bottleneck_dim=16),
+    dict(strides="(2,2)_(2,2)", poolings="(1,1)_(1,1)", bottleneck_dim=24), dict(strides="(1,1)_(2,2)", poolings="(1,1)_(1,1)"),
+    dict(strides="(2,2)_(1,1)", poolings="(1,1)_(2,2)", bottleneck_dim=8),
+    dict(channels="32", kernel_sizes="(3,3)", strides="(2,2)", poolings="(1,1)"),
+    dict(input_dim=240, in_channel=3),
+])
+def test_frontend_node_matches_torch_autograd(ov, monkeypatch):
+    import ops_doubles
+    from neural_sp_b200 import autograd as ag
+    from neural_sp_b200.encoders.conv import ConvEncoder
+    real_node = ag.frontend_forward                      # keep the real node; install_training replaces the module attribute
+    ops_doubles.install_training(monkeypatch)
+    torch.manual_seed(0)
+    enc = ConvEncoder(**_cfg(**ov)).train()
+    enc.set_precision("fp32")
+    rng = np.random.RandomState(1)
+    xs = torch.from_numpy(rng.randn(3, 37, enc.in_channel * enc.input_freq).astype(np.float32))
+    y_ref = ops_doubles.frontend_forward(enc, xs, 1.7, "fp32")
+    w = torch.from_numpy(rng.randn(*y_ref.shape).astype(np.float32))
+    (y_ref * w).sum().backward()
+    ref = {k: p.grad.clone() for k, p in enc.named_parameters()}
+    enc.zero_grad()
+    y = real_node(enc, xs, 1.7, "fp32")
+    assert y.shape == y_ref.shape
+    assert float((y - y_ref).abs().max()) <= 1e-5 * float(y_ref.abs().max())
+    (y * w).sum().backward()
+    for k, p in enc.named_parameters():
+        err = float((p.grad - ref[k]).abs().max() / ref[k].abs().max().clamp_min(1e-12))
+        assert err <= 2e-4, (k, err)
+    lens = enc.output_lens(torch.IntTensor([37, 30, 11]))
+    assert lens.tolist()[0] == y.shape[1]
