@@ -172,6 +172,10 @@ nsp_status nsp_scale_inplace(float* x, float a, int64_t n, void* stream);
 /* x[b,t,:] = x[b,t,:] * a + pe[t,:] in place: PositionalEncoding.forward (pe_type='add')
  * modules/positional_embedding.py:82-90; x fp32 [B,T,D], pe fp32 [T,D] = rows offset..offset+T of the sinusoid buffer. */
 nsp_status nsp_add_pos_enc(float* x, const float* pe, float a, int B, int T, int D, void* stream);
+/* SpecAugment masking in place (frontends/spec_augment.py:112-140 `xs[:, :, f0:f1] = 0`, `xs[:, t0:t1] = 0`): x fp32 [B,T,F];
+ * freq_rects / time_rects are HOST arrays of (begin, end) int32 pairs (at most 32 each), passed to the kernel by value. */
+nsp_status nsp_mask_rects(float* x, int B, int T, int F, const int32_t* freq_rects, int n_freq,
+                          const int32_t* time_rects, int n_time, void* stream);
 /* y[n] = sum_m x[m, n] for a dense fp32 [M, N] matrix (bias gradients). */
 nsp_status nsp_colsum(const float* x, float* y, int M, int N, void* stream);
 /* TransformerXL sinusoid table: XLPositionalEmbedding.forward modules/positional_embedding.py:135-138.

@@ -91,6 +91,7 @@ SIGNATURES.update(_more)
 
 _more = {
     "nsp_scale_inplace": (c_int, [c_vp, c_f32, c_i64, c_vp]),
+    "nsp_mask_rects": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_int, c_vp]),
     "nsp_add_pos_enc": (c_int, [c_vp, c_vp, c_f32, c_int, c_int, c_int, c_vp]),
     "nsp_colsum": (c_int, [c_vp, c_vp, c_int, c_int, c_vp]),
     "nsp_xl_pos_table": (c_int, [c_vp, c_vp, c_int, c_int, c_vp]),

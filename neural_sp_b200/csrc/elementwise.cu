@@ -51,6 +51,22 @@ __global__ void __launch_bounds__(256) add_pos_enc_kernel(float* __restrict__ x,
     for (; i < n; i += stride) x[i] = fmaf(x[i], a, __ldg(pe + i % TD));
 }
 
+// SpecAugment: zero every element of x [B, T, F] whose frequency bin lies in one of the frequency rectangles or whose frame
+// lies in one of the time rectangles (same rectangles for every utterance, frontends/spec_augment.py:112-140).  Write-only.
+constexpr int MAXRECT = 32;
+struct MaskRects { int nf, nt; int f0[MAXRECT], f1[MAXRECT], t0[MAXRECT], t1[MAXRECT]; };
+
+__global__ void __launch_bounds__(256) mask_rects_kernel(float* __restrict__ x, int64_t n, int T, int F, const MaskRects m) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const int f = (int)(i % F);
+        const int t = (int)((i / F) % T);
+        bool hit = false;
+        for (int r = 0; r < m.nf; ++r) hit |= (f >= m.f0[r] && f < m.f1[r]);
+        for (int r = 0; r < m.nt; ++r) hit |= (t >= m.t0[r] && t < m.t1[r]);
+        if (hit) x[i] = 0.f;
+    }
+}
+
 // column sums of a row-major [M, N] fp32 matrix: block = 32 columns x 8 row slices
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, float* __restrict__ y, int M, int N) {
     __shared__ float part[8][33];
@@ -114,6 +130,22 @@ extern "C" nsp_status nsp_scale_inplace(float* x, float a, int64_t n, void* stre
     NSP_CHECK_ARG(x && n >= 0, "scale_inplace: bad arguments");
     if (n == 0) return NSP_OK;
     scale_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, a, n);
+    NSP_LAUNCH_OK();
+    return NSP_OK;
+}
+
+extern "C" nsp_status nsp_mask_rects(float* x, int B, int T, int F, const int32_t* freq_rects, int n_freq,
+                                     const int32_t* time_rects, int n_time, void* stream) {
+    NSP_CHECK_ARG(x && B >= 0 && T >= 0 && F > 0 && n_freq >= 0 && n_time >= 0, "mask_rects: bad arguments");
+    NSP_CHECK_ARG((n_freq == 0 || freq_rects) && (n_time == 0 || time_rects), "mask_rects: null rectangle list");
+    if (n_freq > MAXRECT || n_time > MAXRECT) { set_error("mask_rects: at most %d masks per axis (got %d, %d)", MAXRECT, n_freq, n_time); return NSP_ERR_UNSUPPORTED; }
+    const int64_t n = (int64_t)B * T * F;
+    if (n == 0 || (n_freq == 0 && n_time == 0)) return NSP_OK;
+    MaskRects m;
+    m.nf = n_freq; m.nt = n_time;
+    for (int r = 0; r < n_freq; ++r) { m.f0[r] = freq_rects[2 * r]; m.f1[r] = freq_rects[2 * r + 1]; }
+    for (int r = 0; r < n_time; ++r) { m.t0[r] = time_rects[2 * r]; m.t1[r] = time_rects[2 * r + 1]; }
+    mask_rects_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, n, T, F, m);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }

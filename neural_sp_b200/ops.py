@@ -313,6 +313,22 @@ def scale_(x, a):
     return x
 
 
+def mask_rects_(x, freq_rects, time_rects):
+    """Zero frequency bands / time spans of x fp32 `[B,T,F]` in place (nsp_mask_rects): lists of (begin, end) pairs."""
+    import ctypes
+    _require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 3
+    B, T, F = x.shape
+
+    def arr(rects):
+        flat = [int(v) for r in rects for v in r]
+        return (ctypes.c_int32 * max(1, len(flat)))(*flat)
+    fa, ta = arr(freq_rects), arr(time_rects)
+    _run("nsp_mask_rects", lib.nsp_mask_rects, ptr(x), B, T, F, ctypes.cast(fa, ctypes.c_void_p), len(freq_rects),
+         ctypes.cast(ta, ctypes.c_void_p), len(time_rects), current_stream_ptr())
+    return x
+
+
 def add_pos_enc_(x, pe, a=1.0):
     """x[b,t,:] = x[b,t,:] * a + pe[t,:] in place (nsp_add_pos_enc); x fp32 `[B,T,D]` contiguous, pe fp32 `[T,D]`."""
     _require_cuda(x, pe)

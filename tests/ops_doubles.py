@@ -132,6 +132,14 @@ def scale_(x, a):
     return x.mul_(a)
 
 
+def mask_rects_(x, freq_rects, time_rects):
+    for f0, f1 in freq_rects:
+        x[:, :, f0:f1] = 0
+    for t0, t1 in time_rects:
+        x[:, t0:t1] = 0
+    return x
+
+
 def add_pos_enc_(x, pe, a=1.0):
     assert pe.shape == x.shape[1:]
     return x.mul_(a).add_(pe.unsqueeze(0))
@@ -290,7 +298,7 @@ def rnnt_joint_tanh_bwd(h, dh):
 
 
 DOUBLES = dict(prepare_weight=prepare_weight, to_bf16=to_bf16, linear=linear, layernorm=layernorm,
-               relpos_attention=relpos_attention, conformer_conv=conformer_conv, scale_=scale_, add_pos_enc_=add_pos_enc_, xl_pos_table=xl_pos_table,
+               relpos_attention=relpos_attention, conformer_conv=conformer_conv, scale_=scale_, add_pos_enc_=add_pos_enc_, mask_rects_=mask_rects_, xl_pos_table=xl_pos_table,
                conv3x3_relu=conv3x3_relu, maxpool2d=maxpool2d, pool_time=pool_time, maxpool_time=maxpool_time, lstm_seq=lstm_seq)
 
 

@@ -55,3 +55,37 @@ def test_layernorm_wide_rows(M, D):
     y, yb = ops.layernorm(x, w, b, 1e-12, out_fp32=True, out_bf16=True)
     assert torch.allclose(y, ref, atol=2e-5, rtol=1e-5)
     assert torch.allclose(yb.float(), ref, atol=3e-2, rtol=2e-2)
+
+
+@pytest.mark.gpu
+@pytest.mark.experimental
+def test_mask_rects_kernel_and_staging():
+    from neural_sp_b200 import ops
+    from neural_sp_b200.frontends.input import pad_and_upload
+    from neural_sp_b200.frontends.spec_augment import SpecAugment
+    rng = np.random.RandomState(0)
+    xs = [rng.randn(n, 80).astype(np.float32) for n in (311, 290, 57)]
+    dev, lens = pad_and_upload(xs, "cuda:0")
+    assert lens.tolist() == [311, 290, 57] and dev.shape == (3, 311, 80)
+    host = dev.cpu()
+    for b, x in enumerate(xs):
+        assert np.array_equal(host[b, :len(x)].numpy(), x) and float(host[b, len(x):].abs().sum()) == 0
+    ref = host.clone()
+    fm, tm = [(3, 20), (70, 80)], [(0, 5), (100, 180), (300, 311)]
+    for f0, f1 in fm:
+        ref[:, :, f0:f1] = 0
+    for t0, t1 in tm:
+        ref[:, t0:t1] = 0
+    out = ops.mask_rects_(dev.clone(), fm, tm)
+    assert torch.equal(out.cpu(), ref)
+    sa = SpecAugment(27, 100, 2, 2)
+    np.random.seed(3)
+    o = sa(dev.clone())
+    np.random.seed(3)
+    f, t = sa.draw(311, 80)
+    exp = host.clone()
+    for f0, f1 in f:
+        exp[:, :, f0:f1] = 0
+    for t0, t1 in t:
+        exp[:, t0:t1] = 0
+    assert torch.equal(o.cpu(), exp)
