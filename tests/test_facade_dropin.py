@@ -126,6 +126,7 @@ def _fake_warprnnt():
     dict(enc_type='conv_transformer', transformer_enc_pe_type='add', transformer_ffn_activation='relu'),
     dict(enc_type='conv_blstm', subsample="1_2_1", enc_n_projs=16),                              # conv + BLSTM + CTC
     dict(dec_type='lstm_transducer', enc_type='conv_lstm', subsample="1_1_1", ctc_weight=0.3, conv_poolings="(2,2)_(2,2)"),
+    dict(n_freq_masks=2, n_time_masks=2, freq_width=13, time_width=20),                          # SpecAugment in encode()
 ])
 def test_training_step_through_the_unchanged_facade(ov, monkeypatch):
     """End to end under the UNCHANGED reference `Speech2Text.forward` (speech2text.py:206-345): same batch, same weights,
@@ -154,11 +155,15 @@ def test_training_step_through_the_unchanged_facade(ov, monkeypatch):
     monkeypatch.setattr(ref_rnnt, "RNNTransducer", B200RNNT)
     # the facade's own `isinstance(self.dec_fwd, RNNT)` (:300, :337, :629); a tuple because this test runs BOTH models
     monkeypatch.setattr(ref_s2t, "RNNT", (ref_s2t.RNNT, B200RNNT))
+    from neural_sp_b200.frontends.spec_augment import SpecAugment as B200SpecAugment
+    monkeypatch.setattr(ref_s2t, "SpecAugment", B200SpecAugment)
     torch.manual_seed(0)
     ours = ref_s2t.Speech2Text(make_args(**ov))
     ours.load_state_dict(stock.state_dict(), strict=True)
     for m in ours.modules():
         m.precision = "fp32"
+    if ov.get("n_freq_masks", 0) > 0:
+        assert type(ours.specaug).__module__.startswith("neural_sp_b200.") and type(stock.specaug).__module__.startswith("neural_sp.")
     ops_doubles.install_training(monkeypatch)
     rng = np.random.RandomState(0)
     batch = {'xs': [rng.randn(n, 80).astype(np.float32) for n in (64, 53, 40)],
@@ -166,7 +171,9 @@ def test_training_step_through_the_unchanged_facade(ov, monkeypatch):
              'xlens': [64, 53, 40], 'utt_ids': ['a', 'b', 'c'], 'speakers': ['s'] * 3, 'sessions': ['x'] * 3, 'text': [''] * 3,
              'feat_path': [''] * 3, 'ylens': [5, 3, 2]}
     stock.train(), ours.train()
+    np.random.seed(11)                       # SpecAugment draws from numpy's global generator (same order on both sides)
     loss_s, obs_s = stock(batch, task='all')
+    np.random.seed(11)
     loss_o, obs_o = ours(batch, task='all')
     assert loss_o.shape == loss_s.shape
     assert abs(float(loss_o.detach()) - float(loss_s.detach())) <= 1e-4 * abs(float(loss_s.detach()))
