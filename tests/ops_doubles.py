@@ -163,6 +163,18 @@ def conv3x3_relu(x, weight, bias, B, T, Fq, in_chmajor=False, relu=True, out_dty
     return y.permute(0, 2, 3, 1).contiguous().to(out_dtype)      # [B, T, F, CO]
 
 
+def conv3x3_c32_tc(x, w_taps, bias, relu=True, pool2x2=False):
+    """bf16 implicit-GEMM conv double: w_taps `[32, 288]` with column = (ky*3 + kx) * 32 + ci."""
+    B, T, Fq, C = x.shape
+    w = w_taps.float().reshape(32, 3, 3, 32).permute(0, 3, 1, 2)            # [co, ci, ky, kx]
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), w, bias.float(), padding=1)
+    if relu:
+        y = torch.relu(y)
+    if pool2x2:
+        y = F.max_pool2d(y, 2, 2, ceil_mode=True)
+    return y.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
 def maxpool2d(x, pool_t, pool_f, out_chmajor=False, out_dtype=None):
     B, T, Fq, C = x.shape
     y = F.max_pool2d(x.float().permute(0, 3, 1, 2), (pool_t, pool_f), (pool_t, pool_f), ceil_mode=True)   # [B, C, To, Fo]
@@ -299,7 +311,7 @@ def rnnt_joint_tanh_bwd(h, dh):
 
 DOUBLES = dict(prepare_weight=prepare_weight, to_bf16=to_bf16, linear=linear, layernorm=layernorm,
                relpos_attention=relpos_attention, conformer_conv=conformer_conv, scale_=scale_, add_pos_enc_=add_pos_enc_, mask_rects_=mask_rects_, xl_pos_table=xl_pos_table,
-               conv3x3_relu=conv3x3_relu, maxpool2d=maxpool2d, pool_time=pool_time, maxpool_time=maxpool_time, lstm_seq=lstm_seq)
+               conv3x3_relu=conv3x3_relu, conv3x3_c32_tc=conv3x3_c32_tc, maxpool2d=maxpool2d, pool_time=pool_time, maxpool_time=maxpool_time, lstm_seq=lstm_seq)
 
 
 def install(monkeypatch):
