@@ -163,6 +163,11 @@ nsp_status nsp_dwconv_stats_fwd(int is_bf16, const void* x, int64_t ldx, const f
 nsp_status nsp_bn_swish_bwd(int is_bf16, const void* z, int64_t ldz, const void* dy, int64_t lddy, const float* mean,
                             const float* var, const float* gamma, const float* beta, float eps, float* sums,
                             void* dz, int64_t lddz, int64_t M, int d, void* stream);
+/* GroupNorm(d/2 groups = channel pairs) variant of the same module (conformer_convolution.py:47-48): per-frame pair statistics;
+ * dz = gradient w.r.t. z, dgamma / dbeta fp32 [d] are accumulated (+=). */
+nsp_status nsp_gn2_swish_bwd(int is_bf16, const void* z, int64_t ldz, const void* dy, int64_t lddy, const float* gamma,
+                             const float* beta, float eps, void* dz, int64_t lddz, float* dgamma, float* dbeta,
+                             int64_t M, int d, void* stream);
 nsp_status nsp_dwconv_bwd(int is_bf16, const void* x, int64_t ldx, const float* w, const void* dz, int64_t lddz,
                           void* dx, int64_t lddx, float* dw, float* dbias, int B, int T, int d, int k, int causal,
                           void* stream);

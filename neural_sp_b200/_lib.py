@@ -179,6 +179,7 @@ _more = {
     "nsp_dwconv_stats_fwd": (c_int, [c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "nsp_bn_swish_bwd": (c_int, [c_int, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_i64, c_i64, c_int,
                                  c_vp]),
+    "nsp_gn2_swish_bwd": (c_int, [c_int, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_f32, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_vp]),
     "nsp_dwconv_bwd": (c_int, [c_int, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
                                c_vp]),
     "nsp_log_softmax_bwd": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp]),

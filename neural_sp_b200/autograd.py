@@ -318,9 +318,8 @@ def _bn_batch_stats(bn, stats, M):
 
 
 def convmod_fwd(conv, norm, x, prec, p_res=0.0):
-    if conv.normalization not in ('layer_norm', 'batch_norm'):
-        raise NotImplementedError("training the Conformer conv module needs conformer_normalization=layer_norm or batch_norm "
-                                  "on the B200 path")
+    if conv.normalization == 'group_norm' and conv.norm.num_groups * 2 != conv.norm.num_channels:
+        raise NotImplementedError("GroupNorm with other than 2 channels per group")
     n = _ln_fwd(norm, x, prec)
     w1 = prepared(conv, "pw1", prec, (conv.pointwise_conv1.weight,), build=lambda w: w.squeeze(-1))
     g, pre = ops.linear(n, w1, conv.pointwise_conv1.bias, prec=prec, glu=True, out_dtype=act_dtype(prec), save_pre=True)
@@ -334,6 +333,12 @@ def convmod_fwd(conv, norm, x, prec, p_res=0.0):
         c = ops.conformer_conv(g, taps, conv.depthwise_conv.bias, 'batch_norm', conv.norm.weight, conv.norm.bias, conv.norm.eps,
                                mean, var, causal=conv.causal)
         bn = (z, mean, var)
+    elif conv.normalization == 'group_norm':
+        # per-frame pair statistics: the forward is the inference kernel as is; the backward wants z (no batch coupling)
+        z, _ = ops.dwconv_stats(g, taps, conv.depthwise_conv.bias, causal=conv.causal)
+        c = ops.conformer_conv(g, taps, conv.depthwise_conv.bias, 'group_norm', conv.norm.weight, conv.norm.bias, conv.norm.eps,
+                               None, None, causal=conv.causal)
+        bn = (z, None, None)
     else:
         c = ops.conformer_conv(g, taps, conv.depthwise_conv.bias, 'layer_norm', conv.norm.weight, conv.norm.bias, conv.norm.eps,
                                None, None, causal=conv.causal)
@@ -354,9 +359,13 @@ def convmod_bwd(conv, norm, saved, dy, dyo, prec, G, bias_done=False, nxt=(None,
     dtaps = torch.zeros_like(taps)
     if bn is not None:
         z, mean, var = bn
-        dz, sums = ops.bn_swish_bwd(z, dc, mean, var, conv.norm.weight, conv.norm.bias, conv.norm.eps)
-        G.buf(conv.norm.bias).add_(sums[0])
-        G.buf(conv.norm.weight).add_(sums[1])
+        if mean is None:            # GroupNorm (channel pairs, per frame)
+            dz = ops.gn2_swish_bwd(z, dc, conv.norm.weight, conv.norm.bias, conv.norm.eps, G.buf(conv.norm.weight),
+                                   G.buf(conv.norm.bias))
+        else:
+            dz, sums = ops.bn_swish_bwd(z, dc, mean, var, conv.norm.weight, conv.norm.bias, conv.norm.eps)
+            G.buf(conv.norm.bias).add_(sums[0])
+            G.buf(conv.norm.weight).add_(sums[1])
         dg = ops.dwconv_bwd(g, taps, dz, dtaps, G.buf(conv.depthwise_conv.bias), causal=conv.causal)
     else:
         dg = ops.conformer_conv_bwd(g, taps, conv.depthwise_conv.bias, conv.norm.weight, conv.norm.bias, conv.norm.eps, dc,

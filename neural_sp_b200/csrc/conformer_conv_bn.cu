@@ -109,10 +109,58 @@ __global__ void __launch_bounds__(256) bn_swish_bwd_apply_kernel(const T* __rest
     }
 }
 
+// GroupNorm with 2 channels per group on the [B*T, d, 1] view (conformer_convolution.py:47-48, :118-124: statistics per frame and
+// per channel pair, no batch coupling): backward of Swish(g zh + b) through the pair statistics.  One thread = one channel pair,
+// a CTA = 128 pairs x 64 rows; d g / d b are reduced per thread over its rows, then one atomicAdd each.
+template <typename T>
+__global__ void __launch_bounds__(CH) gn2_swish_bwd_kernel(const T* __restrict__ z, int64_t ldz, const T* __restrict__ dy,
+                                                           int64_t lddy, const float* __restrict__ g, const float* __restrict__ bta,
+                                                           float eps, T* __restrict__ dz, int64_t lddz, float* __restrict__ dgam,
+                                                           float* __restrict__ dbet, int64_t M, int d) {
+    const int pairs = d / 2;
+    const int pchunks = (pairs + CH - 1) / CH;
+    const int pc = blockIdx.x % pchunks;
+    const int64_t r0 = (int64_t)(blockIdx.x / pchunks) * 64;
+    const int pr = pc * CH + threadIdx.x;
+    if (pr >= pairs) return;
+    const int c0 = 2 * pr, c1 = c0 + 1;
+    const float g0 = __ldg(g + c0), g1 = __ldg(g + c1), b0 = __ldg(bta + c0), b1 = __ldg(bta + c1);
+    float dg0 = 0.f, dg1 = 0.f, db0 = 0.f, db1 = 0.f;
+    const int64_t r1 = min(M, r0 + 64);
+    for (int64_t r = r0; r < r1; ++r) {
+        const float a = bn_ld<T>(z + r * ldz + c0), b = bn_ld<T>(z + r * ldz + c1);
+        const float m = 0.5f * (a + b);
+        const float da = a - m, dbv = b - m;
+        const float rstd = rsqrtf(0.5f * (da * da + dbv * dbv) + eps);
+        const float zh0 = da * rstd, zh1 = dbv * rstd;
+        const float du0 = bn_ld<T>(dy + r * lddy + c0) * swish_grad(fmaf(g0, zh0, b0));
+        const float du1 = bn_ld<T>(dy + r * lddy + c1) * swish_grad(fmaf(g1, zh1, b1));
+        dg0 = fmaf(du0, zh0, dg0); dg1 = fmaf(du1, zh1, dg1); db0 += du0; db1 += du1;
+        const float e0 = du0 * g0, e1 = du1 * g1;                       // gradient w.r.t. zh
+        const float me = 0.5f * (e0 + e1), mez = 0.5f * (e0 * zh0 + e1 * zh1);
+        bn_st<T>(dz + r * lddz + c0, rstd * (e0 - me - zh0 * mez));
+        bn_st<T>(dz + r * lddz + c1, rstd * (e1 - me - zh1 * mez));
+    }
+    atomicAdd(dgam + c0, dg0); atomicAdd(dgam + c1, dg1);
+    atomicAdd(dbet + c0, db0); atomicAdd(dbet + c1, db1);
+}
+
 }  // namespace
 }  // namespace nsp
 
 using namespace nsp;
+
+extern "C" nsp_status nsp_gn2_swish_bwd(int is_bf16, const void* z, int64_t ldz, const void* dy, int64_t lddy, const float* gamma,
+                                        const float* beta, float eps, void* dz, int64_t lddz, float* dgamma, float* dbeta,
+                                        int64_t M, int d, void* stream) {
+    NSP_CHECK_ARG(z && dy && gamma && beta && dz && dgamma && dbeta && M > 0 && d > 0 && d % 2 == 0, "gn2_swish_bwd: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)(ceil_div64(M, 64) * ceil_div(d / 2, CH));
+    if (is_bf16) gn2_swish_bwd_kernel<__nv_bfloat16><<<grid, CH, 0, st>>>((const __nv_bfloat16*)z, ldz, (const __nv_bfloat16*)dy, lddy, gamma, beta, eps, (__nv_bfloat16*)dz, lddz, dgamma, dbeta, M, d);
+    else gn2_swish_bwd_kernel<float><<<grid, CH, 0, st>>>((const float*)z, ldz, (const float*)dy, lddy, gamma, beta, eps, (float*)dz, lddz, dgamma, dbeta, M, d);
+    NSP_LAUNCH_OK();
+    return NSP_OK;
+}
 
 extern "C" nsp_status nsp_dwconv_stats_fwd(int is_bf16, const void* x, int64_t ldx, const float* w, const float* bias, void* z,
                                            int64_t ldz, float* stats, int B, int T, int d, int k, int causal, void* stream) {

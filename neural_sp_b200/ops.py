@@ -760,6 +760,19 @@ def bn_swish_bwd(z, dy, mean, var, gamma, beta, eps):
     return dz, sums
 
 
+def gn2_swish_bwd(z, dy, gamma, beta, eps, dgamma, dbeta):
+    """Backward of Swish(GroupNorm(z)) with 2 channels per group on the per-frame view (nsp_gn2_swish_bwd): -> dz like z;
+    dgamma / dbeta fp32 `[d]` are accumulated."""
+    _require_cuda(z, dy, dgamma, dbeta)
+    B, T, d = z.shape
+    z = z.contiguous()
+    dy = dy.to(z.dtype).contiguous()
+    dz = torch.empty_like(z)
+    _run("nsp_gn2_swish_bwd", lib.nsp_gn2_swish_bwd, int(z.dtype == torch.bfloat16), ptr(z), d, ptr(dy), d, ptr(gamma), ptr(beta),
+         float(eps), ptr(dz), d, ptr(dgamma), ptr(dbeta), B * T, d, current_stream_ptr())
+    return dz
+
+
 def dwconv_bwd(x, taps, dz, dtaps, dbias, causal=False):
     """dx, d taps (+=), d bias (+=) of the depthwise conv from dz (nsp_dwconv_bwd)."""
     _require_cuda(x, taps, dz)

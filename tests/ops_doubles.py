@@ -450,6 +450,18 @@ def bn_swish_bwd(z, dy, mean, var, gamma, beta, eps):
     return zz.grad.to(z.dtype), torch.stack([b.grad, g.grad])
 
 
+def gn2_swish_bwd(z, dy, gamma, beta, eps, dgamma, dbeta):
+    B, T, d = z.shape
+    with torch.enable_grad():
+        zz = z.detach().float().clone().requires_grad_(True)
+        g = gamma.detach().float().clone().requires_grad_(True)
+        b = beta.detach().float().clone().requires_grad_(True)
+        u = F.group_norm(zz.reshape(B * T, d, 1), d // 2, g, b, eps).reshape(B, T, d)
+        (u * torch.sigmoid(u)).backward(dy.float())
+    dgamma.add_(g.grad), dbeta.add_(b.grad)
+    return zz.grad.to(z.dtype)
+
+
 def dwconv_bwd(x, taps, dz, dtaps, dbias, causal=False):
     with torch.enable_grad():
         xx = x.detach().float().clone().requires_grad_(True)
@@ -609,7 +621,7 @@ TRAIN_DOUBLES = dict(DOUBLES, linear=_linear_train, linear_wgrad=linear_wgrad, c
                      rng_advance=rng_advance, lstm_seq_bwd=lstm_seq_bwd, rnnt_joint_tanh=rnnt_joint_tanh,
                      softmax_rows=softmax_rows, rnnt_loss_fwd_bwd=rnnt_loss_fwd_bwd, rnnt_grad_logits=rnnt_grad_logits, log_softmax_bwd_=log_softmax_bwd_,
                      rnnt_joint_tanh_bwd=rnnt_joint_tanh_bwd, pack_labels=pack_labels, ctc_loss_fwd_bwd=ctc_loss_fwd_bwd,
-                     dwconv_stats=dwconv_stats, bn_swish_bwd=bn_swish_bwd, dwconv_bwd=dwconv_bwd, conv3x3_wgrad=conv3x3_wgrad,
+                     dwconv_stats=dwconv_stats, bn_swish_bwd=bn_swish_bwd, gn2_swish_bwd=gn2_swish_bwd, dwconv_bwd=dwconv_bwd, conv3x3_wgrad=conv3x3_wgrad,
                      maxpool2d_relu_bwd=maxpool2d_relu_bwd)
 
 

@@ -140,3 +140,26 @@ def test_conv_module_batchnorm_training_kernels(B, T, d, k, causal, dtype, tol):
     assert float((dx.float() - xr.grad).abs().max()) <= tol * max(1.0, float(xr.grad.abs().max())) * 4
     assert float((dtaps.t().reshape(d, 1, k) - w.grad).abs().max()) <= tol * max(1.0, float(w.grad.abs().max())) * 8
     assert float((dbias - bias.grad).abs().max()) <= tol * max(1.0, float(bias.grad.abs().max())) * 8
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 5e-2)])
+@pytest.mark.parametrize("B,T,d", [(3, 45, 64), (2, 100, 256), (1, 7, 10)])
+def test_conv_module_groupnorm_backward_kernel(B, T, d, dtype, tol):
+    """nsp_gn2_swish_bwd against torch autograd through Swish(GroupNorm(d/2 groups)) on the per-frame view."""
+    from neural_sp_b200 import ops
+    torch.manual_seed(d)
+    dev = "cuda"
+    z = (torch.randn(B, T, d, device=dev) * 1.5).to(dtype)
+    zr = z.float().clone().requires_grad_(True)
+    g = (torch.rand(d, device=dev) + 0.5).requires_grad_(True)
+    bt = (torch.randn(d, device=dev) * 0.1).requires_grad_(True)
+    u = torch.nn.functional.group_norm(zr.reshape(B * T, d, 1), d // 2, g, bt, 1e-5).reshape(B, T, d)
+    y = u * torch.sigmoid(u)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    dg, db = torch.zeros(d, device=dev), torch.zeros(d, device=dev)
+    dz = ops.gn2_swish_bwd(z, dy.to(dtype), g.detach(), bt.detach(), 1e-5, dg, db)
+    scale = float(zr.grad.abs().max())
+    assert float((dz.float() - zr.grad).abs().max()) <= tol * max(1.0, scale)
+    assert float((dg - g.grad).abs().max()) <= tol * max(1.0, float(g.grad.abs().max())) * 4
+    assert float((db - bt.grad).abs().max()) <= tol * max(1.0, float(bt.grad.abs().max())) * 4
