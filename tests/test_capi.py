@@ -38,3 +38,4 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 txt = open(os.path.join(d, f)).read()
                 assert "oracle" not in re.sub(r"#.*", "", txt).replace("no CPU or PyTorch fallback", ""), (d, f)
+                assert "ops_doubles" not in txt, (d, f)        # the torch restatements of the ops are test doubles only
