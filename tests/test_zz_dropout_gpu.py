@@ -32,7 +32,7 @@ def test_dropout_mask_matches_philox_restatement(n, dtype, p):
     assert torch.equal((y != 0).cpu(), keep)
     ref = torch.where(keep.cuda(), x.float() / (1 - p), torch.zeros((), device="cuda"))
     assert torch.allclose(y.float(), ref, rtol=1e-2 if dtype == torch.bfloat16 else 1e-6)
-    assert abs(float(keep.float().mean()) - (1 - p)) < (0.02 if n >= 4096 else 0.5)
+    assert abs(float(keep.float().mean()) - (1 - p)) < (0.04 if n >= 4096 else 0.5)      # 5 sigma at n = 4096
     # same id -> same mask (this is what the backward relies on); mixed dtypes take the scalar path: same mask again
     assert torch.equal(ops.dropout(x, p, sid) != 0, y != 0)
     assert torch.equal((ops.dropout(x, p, sid, out_dtype=torch.float32 if dtype == torch.bfloat16 else torch.bfloat16) != 0), y != 0)
