@@ -59,7 +59,8 @@ class ConformerEncoderBlock(nn.Module):
         chunks' normalised attention input ``input_san`` `[B, n_cache, d]` and conv-module input ``input_conv``
         `[B, <= k + T - 1, d]`; the returned new_cache holds both extended by this chunk."""
         if self.training and (self.dropout.p > 0 or self.self_attn.dropout_attn.p > 0):
-            raise NotImplementedError("dropout > 0 in training mode is not on the B200 path yet")
+            raise NotImplementedError("dropout > 0 in train() mode runs through the autograd training path only (grad enabled); "
+                                      "this is the inference-kernel path")
         prec = get_precision(self)
         mask_kw = mask_kw or {}
         u_bias, v_bias = rel_bias

@@ -53,7 +53,8 @@ class ConformerEncoderBlock_v2(nn.Module):
         """Same contract as ConformerEncoderBlock.forward; pos_embs is ignored, rel_bias must be (None, None)."""
         assert rel_bias[0] is None and rel_bias[1] is None
         if self.training and (self.dropout.p > 0 or self.self_attn.dropout_attn.p > 0):
-            raise NotImplementedError("dropout > 0 in training mode is not on the B200 path yet")
+            raise NotImplementedError("dropout > 0 in train() mode runs through the autograd training path only (grad enabled); "
+                                      "this is the inference-kernel path")
         prec = get_precision(self)
         mask_kw = mask_kw or {}
         new_cache = {}

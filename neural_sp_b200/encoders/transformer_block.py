@@ -45,7 +45,8 @@ class TransformerEncoderBlock(nn.Module):
         """cache (streaming, transformer_block.py:113-122): ``input_san`` `[B, n_cache, d]`, the previous chunks'
         normalised attention input; klens counts cached frames too."""
         if self.training and (self.dropout.p > 0 or self.self_attn.dropout_attn.p > 0):
-            raise NotImplementedError("dropout > 0 in training mode is not on the B200 path yet")
+            raise NotImplementedError("dropout > 0 in train() mode runs through the autograd training path only (grad enabled); "
+                                      "this is the inference-kernel path")
         prec = get_precision(self)
         mask_kw = mask_kw or {}
         new_cache = {}
