@@ -194,3 +194,54 @@ def test_training_step_through_the_unchanged_facade(ov, monkeypatch):
         if not e <= 1e-3:
             bad.append((k, e))
     assert not bad, (bad[:8], len(bad))
+
+
+@pytest.mark.parametrize("ov", [
+    dict(enc_type='conv_uni_conformer', conv_poolings="(2,2)_(2,2)", subsample="1_1_1"),                 # unidirectional + CNN context
+    dict(enc_type='conv_transformer', transformer_enc_pe_type='relative_xl', transformer_ffn_activation='relu',
+         conv_poolings="(2,2)_(2,2)", subsample="1_1_1", lc_chunk_size_left="32", lc_chunk_size_current="32",
+         lc_chunk_size_right="16", lc_type='reshape'),                                                   # LC Transformer, windows
+    dict(enc_type='conv_conformer', conv_poolings="(2,2)_(2,2)", subsample="1_1_1", lc_chunk_size_left="32",
+         lc_chunk_size_current="16", lc_chunk_size_right="0", lc_type='mask'),                           # LC Conformer, chunk mask
+    dict(enc_type='conv_lstm', conv_poolings="(2,2)_(2,2)", subsample="1_1_1"),                          # LSTM state carry-over
+    dict(enc_type='conv_blstm', conv_poolings="(2,2)_(2,2)", subsample="1_1_1", lc_chunk_size_left="32",
+         lc_chunk_size_right="16", bidirectional_sum_fwd_bwd=True),           # LC-BLSTM (the factory reads N_c from _left, build.py:146)
+])
+def test_streaming_encode_through_the_unchanged_facade(ov, monkeypatch):
+    """`Speech2Text.encode_streaming` (speech2text.py:513-549) with the reference's own `Streaming` block slicer driving the
+    encoder chunk by chunk: the stock encoder vs neural_sp_b200's under the same facade object -- the cached / carried state
+    contract (`reset_cache`, `streaming=True`, CNN lookback / lookahead, `xlen_block`) as the facade uses it."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import numpy as np
+    import torch
+    import ops_doubles
+    from oracle.ref_import import import_reference
+    import_reference()
+    import neural_sp.models.seq2seq.decoders.ctc as ref_ctc
+    import neural_sp.models.seq2seq.decoders.las as ref_las
+    import neural_sp.models.seq2seq.speech2text as ref_s2t
+    from neural_sp_b200.decoders.ctc import CTC as B200CTC
+    from neural_sp_b200.encoders.build import build_encoder as b200_build_encoder
+    ov = dict(ov, ctc_weight=0.5)            # hybrid model: encode_streaming asserts an attention decoder (fwd_weight > 0)
+    torch.manual_seed(0)
+    stock = ref_s2t.Speech2Text(make_args(**ov)).eval()
+    monkeypatch.setattr(ref_s2t, "build_encoder", b200_build_encoder)
+    monkeypatch.setattr(ref_las, "CTC", B200CTC)
+    monkeypatch.setattr(ref_ctc, "CTC", B200CTC)
+    torch.manual_seed(0)
+    ours = ref_s2t.Speech2Text(make_args(**ov))
+    ours.load_state_dict(stock.state_dict(), strict=True)
+    for m in ours.modules():
+        m.precision = "fp32"
+    ours.eval()
+    ops_doubles.install(monkeypatch)
+    params = dict(recog_block_sync_size=40, recog_ctc_vad=False, recog_ctc_vad_blank_threshold=40,
+                  recog_ctc_vad_spike_threshold=0.1, recog_ctc_vad_n_accum_frames=4000)
+    rng = np.random.RandomState(0)
+    for T in (170, 203):
+        x = rng.randn(T, 80).astype(np.float32)
+        with torch.no_grad():
+            e_s, l_s = stock.encode_streaming([x], params, task='ys')
+            e_o, l_o = ours.encode_streaming([x], params, task='ys')
+        assert torch.equal(l_s, l_o) and e_s.shape == e_o.shape
+        assert float((e_s - e_o).abs().max()) <= 1e-4 * float(e_s.abs().max())
