@@ -151,6 +151,50 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     }
 }
 
+// Any D, pitch and alignment (rows the register-resident kernel does not take: D % 4 != 0 such as a 10-wide last projection,
+// D > 2048): one warp per row, the row is re-read from L1 / L2 for each of the three statistics, parameter gradients go
+// straight to global atomics.  Odd shapes only -- not a tuned path.
+__global__ void __launch_bounds__(256) layernorm_bwd_generic_kernel(const float* __restrict__ dy, int64_t lddy,
+                                                                    const float* __restrict__ x, int64_t ldx,
+                                                                    const float* __restrict__ gamma, float eps, float in_scale,
+                                                                    const float* __restrict__ dres, int64_t lddr,
+                                                                    float* __restrict__ dx, int64_t lddx,
+                                                                    __nv_bfloat16* __restrict__ dxb, int64_t lddxb,
+                                                                    float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                    float* __restrict__ dcol, float dcol_alpha, int M, int D) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < M; row += (int64_t)gridDim.x * 8) {
+        const float* xr = x + row * ldx;
+        const float* dyr = dy + row * lddy;
+        float s = 0.f;
+        for (int c = lane; c < D; c += 32) s += xr[c] * in_scale;
+        const float mean = warp_sum(s) / (float)D;
+        float q = 0.f;
+        for (int c = lane; c < D; c += 32) { const float d = xr[c] * in_scale - mean; q = fmaf(d, d, q); }
+        const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+        float s1 = 0.f, s2 = 0.f;
+        for (int c = lane; c < D; c += 32) {
+            const float xh = (xr[c] * in_scale - mean) * rstd;
+            const float gg = dyr[c] * __ldg(gamma + c);
+            s1 += gg;
+            s2 = fmaf(gg, xh, s2);
+        }
+        const float m1 = warp_sum(s1) / (float)D, m2 = warp_sum(s2) / (float)D;
+        const float sc = rstd * in_scale;
+        for (int c = lane; c < D; c += 32) {
+            const float xh = (xr[c] * in_scale - mean) * rstd;
+            const float dyv = dyr[c];
+            float o = sc * (dyv * __ldg(gamma + c) - m1 - xh * m2);
+            if (dres) o += dres[row * lddr + c];
+            if (dx) dx[row * lddx + c] = o;
+            if (dxb) dxb[row * lddxb + c] = __float2bfloat16_rn(o);
+            if (dgamma) atomicAdd(dgamma + c, dyv * xh);
+            if (dbeta) atomicAdd(dbeta + c, dyv);
+            if (dcol) atomicAdd(dcol + c, dcol_alpha * o);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // dz = dh * act'(z)    (act: 1 relu, 2 swish, 3 gelu(erf), 4 gelu(tanh))
 // ------------------------------------------------------------------------------------------------
@@ -490,15 +534,21 @@ extern "C" nsp_status nsp_layernorm_bwd(const float* dy, int64_t lddy, const flo
                                         float* dx, int64_t lddx, void* dx_bf16, int64_t lddxb,
                                         float* dgamma, float* dbeta, float* dcol, float dcol_alpha, int M, int D, void* stream) {
     NSP_CHECK_ARG(dy && x && gamma && (dx || dx_bf16), "layernorm_bwd: null pointer");
-    NSP_CHECK_ARG(M > 0 && D > 0 && D % 4 == 0 && D <= 2048, "layernorm_bwd: bad shape M=%d D=%d (D %% 4 == 0, <= 2048)", M, D);
-    NSP_CHECK_ARG(lddy % 4 == 0 && ldx % 4 == 0 && (!dres || lddr % 4 == 0) && (!dx || lddx % 4 == 0) && (!dx_bf16 || lddxb % 4 == 0),
-                  "layernorm_bwd: row pitches must be multiples of 4 elements");
-    NSP_CHECK_ARG(((uintptr_t)dy % 16 == 0) && ((uintptr_t)x % 16 == 0) && (!dres || (uintptr_t)dres % 16 == 0) &&
-                  (!dx || (uintptr_t)dx % 16 == 0) && (!dx_bf16 || (uintptr_t)dx_bf16 % 8 == 0), "layernorm_bwd: unaligned pointer");
+    NSP_CHECK_ARG(M > 0 && D > 0, "layernorm_bwd: bad shape M=%d D=%d", M, D);
     cudaStream_t st = (cudaStream_t)stream;
     int grid = ceil_div(M, 8);
     const int cap = num_sms() * 4;
     if (grid > cap) grid = cap;
+    const bool vec_ok = D % 4 == 0 && D <= 2048 &&
+        lddy % 4 == 0 && ldx % 4 == 0 && (!dres || lddr % 4 == 0) && (!dx || lddx % 4 == 0) && (!dx_bf16 || lddxb % 4 == 0) &&
+        ((uintptr_t)dy % 16 == 0) && ((uintptr_t)x % 16 == 0) && (!dres || (uintptr_t)dres % 16 == 0) &&
+        (!dx || (uintptr_t)dx % 16 == 0) && (!dx_bf16 || (uintptr_t)dx_bf16 % 8 == 0);
+    if (!vec_ok) {                 // odd widths / pitches: the scalar kernel
+        layernorm_bwd_generic_kernel<<<grid, 256, 0, st>>>(dy, lddy, x, ldx, gamma, eps, in_scale, dres, lddr, dx, lddx,
+                                                           (__nv_bfloat16*)dx_bf16, lddxb, dgamma, dbeta, dcol, dcol_alpha, M, D);
+        NSP_LAUNCH_OK();
+        return NSP_OK;
+    }
     const size_t smem = sizeof(float) * 8 * (size_t)D;
     __nv_bfloat16* dxb = (__nv_bfloat16*)dx_bf16;
 #define NSP_LNB(VPT)                                                                                                     \

@@ -153,8 +153,9 @@ extern "C" nsp_status nsp_conv3x3_wgrad(int a_bf16, int dz_bf16, const void* a, 
                                         float* dbias, int B, int T, int F, int CI, int CO, void* stream) {
     NSP_CHECK_ARG(a && dz && dw, "conv3x3_wgrad: null pointer");
     NSP_CHECK_ARG(B > 0 && T > 0 && F > 0 && CI > 0 && CO > 0, "conv3x3_wgrad: bad shape");
-    NSP_CHECK_ARG(CO % 4 == 0 && CI * (CO / 4) <= 256 && 256 % (CI * (CO / 4)) == 0,
-                  "conv3x3_wgrad: CI=%d CO=%d unsupported (CI*CO/4 must divide 256)", CI, CO);
+    // thread = (position slice, ci, 4 output channels): any CI * CO/4 <= 256 maps (threads beyond the last whole slice idle,
+    // e.g. CI = 3 delta-feature planes: 10 slices of 24 threads)
+    NSP_CHECK_ARG(CO % 4 == 0 && CI * (CO / 4) <= 256, "conv3x3_wgrad: CI=%d CO=%d unsupported (CO %% 4 == 0, CI*CO/4 <= 256)", CI, CO);
     if (CI == 1 && CO == 32 && !a_bf16) {           // first layer: streaming kernel ([B,T,1,F] and [B,T,F,1] coincide)
         int grid1 = 4 * num_sms();
         if ((int64_t)B * T < grid1) grid1 = B * T;

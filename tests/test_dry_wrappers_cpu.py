@@ -1,0 +1,198 @@
+"""The reference's encoder test matrix driven through the REAL ops.py wrappers on CPU (tests/dry_lib.py: kernels replaced
+by no-op ctypes callbacks with the product's prototypes).  No values are checked -- only that every call the host code
+makes satisfies the wrapper's argument validation and the C ABI's argument list, in inference and through a whole
+forward + backward, in both precision modes.  The torch restatements used by the parity tests bypass those checks; this
+run is what stands between the CPU-verified host logic and its first launch on the GPU.
+Needs /root/reference only for the configuration tables (skipped elsewhere)."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from test_reference_matrix_cpu import FAMILIES, _matrix  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference/neural_sp"), reason="reference tree not available")
+
+
+def _build(family, ov, ov_conv):
+    from neural_sp_b200.encoders.conformer import ConformerEncoder
+    from neural_sp_b200.encoders.conv import ConvEncoder
+    from neural_sp_b200.encoders.rnn import RNNEncoder
+    from neural_sp_b200.encoders.transformer import TransformerEncoder
+    tmod, _, _ = FAMILIES[family]
+    tm = importlib.import_module(tmod)
+    ours_cls = {"conformer": ConformerEncoder, "transformer": TransformerEncoder, "rnn": RNNEncoder}[family]
+    args = tm.make_args(**ov)
+    if 'dropout_att' in args:
+        args['dropout_att'] = 0.0          # attention-weight dropout is off the B200 path by design
+    if 'rsp_prob' in args:
+        args['rsp_prob'] = 0.0             # random state passing: eval only (explicit NotImplementedError in train())
+    torch.manual_seed(0)
+    if 'conv' in args['enc_type']:
+        c = tm.make_args_conv(**ov_conv)
+        c['dropout'] = 0.0                 # build_encoder passes 0 to the CNN front-end (encoders/build.py:56)
+        if family != 'rnn':
+            c['bottleneck_dim'] = args['d_model']
+        args['frontend_conv'] = ConvEncoder(**c)
+    enc = ours_cls(**args)
+    lc = str(args.get('chunk_size_current', '0')) not in ('0',)
+    xmax = 90 if (lc or family == 'rnn') else 45
+    xs = torch.from_numpy(np.random.RandomState(0).randn(4, xmax, args['input_dim']).astype(np.float32))
+    xlens = torch.IntTensor([xmax - i * enc.subsampling_factor for i in range(4)])
+    return enc, xs, xlens
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("family, ov, ov_conv", _matrix())
+def test_real_wrappers_accept_every_call_of_the_matrix(family, ov, ov_conv, precision, monkeypatch):
+    import dry_lib
+    dry = dry_lib.install(monkeypatch, validate=True)
+    enc, xs, xlens = _build(family, ov, ov_conv)
+    enc.set_precision(precision)
+    enc.eval()
+    o = enc(xs.clone(), xlens.clone(), task='all')
+    assert o['ys']['xs'] is not None and sum(dry.calls.values()) > 0
+    n_eval = sum(dry.calls.values())
+    enc.train()                                         # dropouts at the reference's test values (> 0): dropout kernels too
+    try:
+        o = enc(xs.clone(), xlens.clone(), task='all')
+    except NotImplementedError as e:                    # the training gaps DESIGN.md 7 lists (normalised / residual CNN blocks)
+        assert any(s in str(e) for s in ('BatchNorm2d', 'LayerNorm2D', 'batch_norm', 'layer_norm', 'residual')), str(e)
+        pytest.skip("inference only: %s" % str(e)[:80])
+    loss = sum(o[k]['xs'].float().sum() for k in ('ys', 'ys_sub1', 'ys_sub2') if o[k]['xs'] is not None)
+    loss.backward()
+    assert sum(dry.calls.values()) > 2 * n_eval
+    missing = [k for k, p in enc.named_parameters() if p.requires_grad and p.grad is None]
+    if not getattr(enc, 'dropout_layer_any', any(getattr(l, 'dropout_layer', 0) > 0 for l in getattr(enc, 'layers', []))):
+        assert not missing, missing[:8]                 # (LayerDrop skips whole blocks at random: no gradient there)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "tf32", "fp32"])
+@pytest.mark.parametrize("dropout", [0.0, 0.1])
+@pytest.mark.parametrize("lengths", ["fixed", "librispeech"])
+def test_bench_training_step_through_the_real_wrappers(precision, dropout, lengths, monkeypatch):
+    """bench.py's own step (encoder + CTC head + loss + backward + Adam; the model bench.py builds, batch cut to B=3 and
+    at most 160 frames) through the real wrappers: the round-end bench line depends on every one of these calls."""
+    import bench
+    import dry_lib
+    from neural_sp_b200 import random as nrandom
+    from neural_sp_b200.decoders.ctc import CTC
+    from neural_sp_b200.encoders.conformer import ConformerEncoder
+    from neural_sp_b200.encoders.conv import ConvEncoder
+    dry = dry_lib.install(monkeypatch, validate=True)
+    w = dict(bench.WORKLOADS["conformer_m_ctc"], B=3, T=160, vocab=200)
+    torch.manual_seed(0)
+    a = bench.enc_args(w)
+    a["dropout"] = dropout
+    a["frontend_conv"] = ConvEncoder(**bench.conv_args(w))
+    enc = ConformerEncoder(**a).train()
+    enc.set_precision(precision)
+    ctc = CTC(eos=2, blank=0, enc_n_units=w["d_model"], vocab=w["vocab"], dropout=dropout, lsm_prob=0.1, fc_list="512").train()
+    for m in ctc.modules():
+        m.precision = precision
+    xs_np, xlens, ys = bench.synth_batch(w, w["B"], 1234, lengths)
+    if lengths == "librispeech":
+        xlens = [min(n, 160) // 8 * 8 for n in xlens]
+        xs_np, ys = xs_np[:, :max(xlens)], [y[:max(1, int(0.45 * n / 8))] for y, n in zip(ys, xlens)]
+    params = list(enc.parameters()) + list(ctc.parameters())
+    opt = torch.optim.Adam(params, lr=1e-5)
+    for _ in range(2):
+        for p in params:
+            p.grad = None
+        out = enc(torch.from_numpy(np.ascontiguousarray(xs_np)), torch.IntTensor(xlens), task='ys')
+        loss, _ = ctc(out['ys']['xs'], out['ys']['xlens'], ys)
+        loss.backward()
+        opt.step()
+        if dropout > 0:
+            nrandom.advance(torch.device("cpu"))
+    assert all(p.grad is not None for p in params)
+    assert dry.calls["nsp_ctc_loss_fwd_bwd"] == 2 and dry.calls["nsp_relpos_attention_bwd"] == 2 * w["n_layers"]
+    assert (dry.calls["nsp_dropout"] + dry.calls["nsp_dropout_add"] > 0) == (dropout > 0)
+    assert dry.calls["nsp_rng_advance"] == (2 if dropout > 0 else 0)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_decoders_and_input_side_through_the_real_wrappers(precision, monkeypatch):
+    """CTC head (training, greedy, trigger points / forced alignment), RNN-T (training incl. auxiliary CTC, eval loss),
+    SpecAugment and the dropout module: the calls the encoder matrix above does not reach."""
+    import dry_lib
+    from neural_sp_b200.decoders.ctc import CTC, CTCForcedAligner
+    from neural_sp_b200.decoders.rnn_transducer import RNNTransducer
+    from neural_sp_b200.frontends.spec_augment import SpecAugment
+    dry = dry_lib.install(monkeypatch, validate=True)
+    torch.manual_seed(0)
+    B, T, D, V = 3, 20, 24, 30
+    e0 = torch.randn(B, T, D)
+    elens = torch.IntTensor([20, 17, 12])
+    ys = [[5, 6, 7, 8], [9, 10], [4]]
+    for fc in ("", "16_16"):
+        ctc = CTC(eos=2, blank=0, enc_n_units=D, vocab=V, dropout=0.1, lsm_prob=0.1, fc_list=fc).train()
+        for m in ctc.modules():
+            m.precision = precision
+        e = e0.clone().requires_grad_(True)
+        loss, trig = ctc(e, elens.clone(), ys, forced_align=True)
+        loss.backward()
+        assert e.grad is not None and all(p.grad is not None for p in ctc.parameters())
+        ctc.eval()
+        with torch.no_grad():
+            hyps = ctc.greedy(e0.clone(), elens.clone())
+            ctc.trigger_points(e0.clone(), elens.clone())
+            ctc.probs(e0.clone()), ctc.scores(e0.clone())
+        assert len(hyps) == B
+    CTCForcedAligner()(torch.randn(B, T, V), elens.clone(), ys)
+    assert dry.calls["nsp_ctc_loss_fwd_bwd"] == 2 and dry.calls["nsp_ctc_forced_align"] >= 3 and dry.calls["nsp_ctc_greedy"] >= 2
+
+    sym = {'eos': 2, 'unk': 1, 'pad': 3, 'blank': 0}
+    for n_projs, ctc_weight, drop in ((0, 0.0, 0.0), (12, 0.3, 0.1)):
+        dec = RNNTransducer(special_symbols=sym, enc_n_units=D, n_units=16, n_projs=n_projs, n_layers=2, bottleneck_dim=20,
+                            emb_dim=8, vocab=V, dropout=drop, dropout_emb=drop, ctc_weight=ctc_weight, ctc_lsm_prob=0.0,
+                            ctc_fc_list="", external_lm=None, global_weight=1.0, mtl_per_batch=False, param_init=0.1)
+        dec.set_precision(precision)
+        dec.train()
+        e = e0.clone().requires_grad_(True)
+        loss, obs = dec(e, elens.clone(), ys, task='all')
+        loss.sum().backward()
+        missing = [k for k, p in dec.named_parameters() if p.grad is None]
+        assert e.grad is not None and not missing, missing
+        dec.eval()
+        with torch.no_grad():
+            dec.forward_transducer(e0.clone(), elens.clone(), ys)
+    for k in ("nsp_rnnt_joint_tanh", "nsp_rnnt_loss_fwd_bwd", "nsp_rnnt_grad_logits", "nsp_rnnt_joint_tanh_bwd", "nsp_lstm_seq_bwd"):
+        assert dry.calls[k] > 0, k
+
+    aug = SpecAugment(F=13, T=10, n_freq_masks=2, n_time_masks=2, p=1.0)
+    aug(torch.randn(B, 60, 80))
+    assert dry.calls["nsp_mask_rects"] >= 1
+
+
+@pytest.mark.parametrize("family, ov", [
+    ("conformer", dict(enc_type='conv_uni_conformer', lookahead="1_0_1")),
+    ("conformer", dict(enc_type='conv_conformer', chunk_size_left="16", chunk_size_current="16", chunk_size_right="16",
+                       streaming_type='reshape')),
+    ("conformer", dict(enc_type='conv_conformer', chunk_size_left="16", chunk_size_current="16", chunk_size_right="0",
+                       streaming_type='mask')),
+    ("transformer", dict(enc_type='conv_uni_transformer', pe_type='add')),
+    ("rnn", dict(enc_type='conv_lstm')),
+    ("rnn", dict(enc_type='conv_blstm', chunk_size_current="16", chunk_size_right="8")),
+])
+def test_streaming_calls_through_the_real_wrappers(family, ov, monkeypatch):
+    import dry_lib
+    dry = dry_lib.install(monkeypatch, validate=True)
+    enc, xs, xlens = _build(family, ov, {})
+    enc.set_precision("fp32")
+    enc.eval()
+    enc.reset_cache()
+    step = 32 if family != 'rnn' else 24
+    for t0 in range(0, 96, step):
+        chunk = torch.randn(1, step, xs.size(2))
+        if getattr(enc, 'streaming_type', '') == 'reshape':
+            chunk = torch.randn(1, 48, xs.size(2))              # one window N_l + N_c + N_r
+        elif getattr(enc, 'streaming_type', '') == 'mask':
+            chunk = torch.randn(1, 16, xs.size(2))              # at most N_c frames per call
+        o = enc(chunk, torch.IntTensor([chunk.size(1)]), task='all', streaming=True, lookback=t0 > 0, lookahead=False)
+        assert o['ys']['xs'] is not None
+    assert sum(dry.calls.values()) > 0
