@@ -247,6 +247,18 @@ def layernorm(x, weight, bias, eps, out_fp32=True, out_bf16=False, in_scale=1.0)
     return outs[0] if len(outs) == 1 else outs
 
 
+def _row_pitch(t, ref_dtype):
+    """Row pitch (elements) of a `[B, T, D]` view whose batches lie T rows apart.  torch leaves the strides of size-1
+    dimensions arbitrary (a one-frame chunk of a one-utterance batch sliced out of a fused QKV buffer stays a view), so
+    they are not trusted."""
+    B, T, D = t.shape
+    assert t.dtype == ref_dtype and t.stride(2) == 1
+    if T > 1:
+        assert B == 1 or t.stride(0) == T * t.stride(1)
+        return t.stride(1)
+    return t.stride(0) if B > 1 else D
+
+
 def relpos_attention(q, k, v, klens, n_heads, r=None, u_bias=None, v_bias=None, clamp_len=-1, causal=False,
                      lookahead=0, chunk_c=0, chunk_l=0, want_stats=False):
     """Flash-style (rel-pos) self-attention (nsp_relpos_attention_fwd).
@@ -259,8 +271,7 @@ def relpos_attention(q, k, v, klens, n_heads, r=None, u_bias=None, v_bias=None, 
     Tk = k.shape[1]
     dk = D // n_heads
     is_bf16 = q.dtype == torch.bfloat16
-    for t in (q, k, v):
-        assert t.dtype == q.dtype and t.stride(2) == 1 and t.stride(0) == t.shape[1] * t.stride(1)
+    ldq, ldk, ldv = (_row_pitch(t, q.dtype) for t in (q, k, v))
     if r is not None:
         assert r.dtype == q.dtype and r.stride(-1) == 1
         r = r.reshape(-1, D) if r.dim() == 3 else r
@@ -269,13 +280,13 @@ def relpos_attention(q, k, v, klens, n_heads, r=None, u_bias=None, v_bias=None, 
         import ctypes
         stats = torch.empty(B, n_heads, Tq, 2, dtype=torch.float32, device=q.device)
         written = ctypes.c_int(0)
-        _run("nsp_relpos_attention_fwd_stats", lib.nsp_relpos_attention_fwd_stats, int(is_bf16), ptr(q), q.stride(1), ptr(k), k.stride(1),
-             ptr(v), v.stride(1), ptr(r), r.stride(0) if r is not None else 0, r.shape[0] if r is not None else 0,
+        _run("nsp_relpos_attention_fwd_stats", lib.nsp_relpos_attention_fwd_stats, int(is_bf16), ptr(q), ldq, ptr(k), ldk,
+             ptr(v), ldv, ptr(r), r.stride(0) if r is not None else 0, r.shape[0] if r is not None else 0,
              ptr(u_bias), ptr(v_bias), ptr(klens), ptr(out), D, B, n_heads, Tq, Tk, dk,
              int(clamp_len), int(causal), int(lookahead), int(chunk_c), int(chunk_l), ptr(stats), ctypes.byref(written),
              current_stream_ptr(), flops=4.0 * B * n_heads * Tq * Tk * dk, tag="nsp_relpos_attention_fwd")
         return out, (stats if written.value else None)
-    _run("nsp_relpos_attention_fwd", lib.nsp_relpos_attention_fwd, int(is_bf16), ptr(q), q.stride(1), ptr(k), k.stride(1), ptr(v), v.stride(1),
+    _run("nsp_relpos_attention_fwd", lib.nsp_relpos_attention_fwd, int(is_bf16), ptr(q), ldq, ptr(k), ldk, ptr(v), ldv,
                                        ptr(r), r.stride(0) if r is not None else 0, r.shape[0] if r is not None else 0,
                                        ptr(u_bias), ptr(v_bias), ptr(klens), ptr(out), D, B, n_heads, Tq, Tk, dk,
                                        int(clamp_len), int(causal), int(lookahead), int(chunk_c), int(chunk_l),

@@ -72,6 +72,10 @@ def test_training_step_with_dropout_equals_cpu_restatement(name, monkeypatch):
                 m.p = 0.1
         for layer in enc.layers:
             layer.self_attn.dropout_attn.p = 0.0
+        if enc.conv is not None:                 # build_encoder passes 0 to the CNN front-end (encoders/build.py)
+            for m in enc.conv.modules():
+                if isinstance(m, torch.nn.Dropout):
+                    m.p = 0.0
         return enc.train()
 
     xs, xlens = torch.from_numpy(g["xs"]), torch.IntTensor(g["xlens"].tolist())
