@@ -232,8 +232,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cfg_common = {"workload": "%s: Conformer %dL d%d ff%d H%d k15 LN rel-pos clamp10, conv 32_32 %s, hier. max-pool, "
-                              "CTC fc512 V=%d lsm0.1; B=%d/GPU T=%d fixed" % (args.workload, w["n_layers"], w["d_model"], w["d_ff"],
-                                                                            w["n_heads"], w["poolings"], w["vocab"], w["B"], w["T"]),
+                              "CTC fc512 V=%d lsm0.1; B=%d/GPU %s" % (args.workload, w["n_layers"], w["d_model"], w["d_ff"],
+                                                                        w["n_heads"], w["poolings"], w["vocab"], w["B"],
+                                                                        "T=%d fixed" % w["T"] if args.lengths == "fixed" else
+                                                                        "log-normal lengths 40..1600 (median 1200), padded to the longest"),
                   "step": ("train: encoder_fwd + ctc_head + ctc_fwd_bwd + head_bwd + encoder_bwd + grad all-reduce + "
                            "optimizer(%s)" % args.optimizer) if args.step == "train" else
                           "fwd: encoder_fwd + ctc_head + ctc_fwd_bwd + head_bwd (no encoder backward)",
