@@ -56,7 +56,11 @@ class DryLib:
 
 
 def install(monkeypatch, validate=False):
+    import torch
     from neural_sp_b200 import _lib, ops
+    if validate and torch.cuda.is_available() and not getattr(torch.cuda.is_available, "__name__", "") == "<lambda>":
+        # with a real device the forwarded calls would LAUNCH kernels on host pointers (and poison the CUDA context)
+        raise RuntimeError("dry_lib.install(validate=True) is for GPU-less machines only")
     dry = DryLib(_lib.lib, _lib.SIGNATURES, validate)
     monkeypatch.setattr(ops, "lib", dry)
     monkeypatch.setattr(ops, "_require_cuda", lambda *ts: None)

@@ -7,8 +7,12 @@ import subprocess
 import sys
 
 import pytest
+import torch
 
 from conftest import ROOT
+
+pytestmark = pytest.mark.skipif(torch.cuda.is_available(), reason="dry runs are for GPU-less machines: with a device the "
+                                "forwarded calls would launch kernels on host pointers")
 
 
 @pytest.mark.parametrize("flags", [[], ["--dropout", "0.1", "--lengths", "librispeech"], ["--step", "fwd", "--precision", "tf32"],

@@ -15,7 +15,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from test_reference_matrix_cpu import FAMILIES, _matrix  # noqa: E402
 
-pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference/neural_sp"), reason="reference tree not available")
+pytestmark = [pytest.mark.skipif(not os.path.isdir("/root/reference/neural_sp"), reason="reference tree not available"),
+              pytest.mark.skipif(torch.cuda.is_available(), reason="dry runs are for GPU-less machines")]
 
 
 def _build(family, ov, ov_conv):
