@@ -845,15 +845,35 @@ class _FrontendFn(torch.autograd.Function):
         for i, blk in enumerate(enc.layers):
             last_chmajor = (i == n - 1) and enc.bridge is None
             pt, pf = blk.pooling if blk.pool is not None else (1, 1)
-            a1 = _conv_any(blk, "conv1", blk.conv1, x, B, T, F, i == 0, prec)
-            a2 = _conv_any(blk, "conv2", blk.conv2, a1, B, T, F, False, prec)
-            rec = dict(x=x, a1=a1, a2=a2, T=T, F=F, pt=pt, pf=pf, chmajor=last_chmajor, first=(i == 0))
             st, sf = getattr(blk, "stride", (1, 1))
-            a2s = a2
-            if (st, sf) != (1, 1):          # strided 'same' conv = the stride-1 conv sampled at 0, s, 2s, ... (ReLU commutes)
-                a2s = a2.view(B, T, F, -1)[:, ::st, ::sf].contiguous()
-                rec.update(stride=(st, sf), a2s=a2s, Ts=a2s.size(1), Fs=a2s.size(2))
-                T, F = a2s.size(1), a2s.size(2)
+            ln = blk.norm1 is not None      # LayerNorm2D block (conv.py:399-421): conv -> LN over a frame's F*C values -> ReLU, fp32
+            if ln:
+                xin = x if i == 0 else x.float()
+                z1 = ops.conv3x3_relu(xin, blk.conv1.weight, blk.conv1.bias, B, T, F, in_chmajor=(i == 0), relu=False,
+                                      out_dtype=torch.float32)
+                g1, b1 = _ln2d_affine(blk, "conv1", blk.norm1)
+                n1 = ops.layernorm(z1.view(B * T, -1), g1, b1, blk.norm1.norm.eps)
+                a1 = ops.relu_mask(n1, n1).view(B, T, F, -1)
+                z2 = ops.conv3x3_relu(a1, blk.conv2.weight, blk.conv2.bias, B, T, F, in_chmajor=False, relu=False,
+                                      out_dtype=torch.float32).view(B, T, F, -1)
+                rec = dict(x=xin, a1=a1, z1=z1, T=T, F=F, pt=pt, pf=pf, chmajor=last_chmajor, first=(i == 0), ln=True)
+                if (st, sf) != (1, 1):
+                    z2 = z2[:, ::st, ::sf].contiguous()
+                    rec.update(stride=(st, sf), Ts=z2.size(1), Fs=z2.size(2))
+                    T, F = z2.size(1), z2.size(2)
+                g2, b2 = _ln2d_affine(blk, "conv2", blk.norm2)
+                n2 = ops.layernorm(z2.view(B * T, -1), g2, b2, blk.norm2.norm.eps)
+                a2s = ops.relu_mask(n2, n2).view(B, T, F, -1)
+                rec.update(z2=z2, a2=a2s, a2s=a2s)
+            else:
+                a1 = _conv_any(blk, "conv1", blk.conv1, x, B, T, F, i == 0, prec)
+                a2 = _conv_any(blk, "conv2", blk.conv2, a1, B, T, F, False, prec)
+                rec = dict(x=x, a1=a1, a2=a2, T=T, F=F, pt=pt, pf=pf, chmajor=last_chmajor, first=(i == 0))
+                a2s = a2
+                if (st, sf) != (1, 1):      # strided 'same' conv = the stride-1 conv sampled at 0, s, 2s, ... (ReLU commutes)
+                    a2s = a2.view(B, T, F, -1)[:, ::st, ::sf].contiguous()
+                    rec.update(stride=(st, sf), a2s=a2s, Ts=a2s.size(1), Fs=a2s.size(2))
+                    T, F = a2s.size(1), a2s.size(2)
             if blk.pool is not None or last_chmajor:
                 x = ops.maxpool2d(a2s.view(B, T, F, -1), pt, pf, out_chmajor=last_chmajor)
                 rec["pooled"] = True
@@ -902,6 +922,9 @@ class _FrontendFn(torch.autograd.Function):
         for blk, rec in zip(reversed(list(enc.layers)), reversed(tape)):
             T, F = rec["T"], rec["F"]
             a1, a2, x = rec["a1"], rec["a2"], rec["x"]
+            if rec.get("ln"):
+                d = _ln2d_block_bwd(blk, rec, d, G, B)
+                continue
             if "stride" in rec:             # gradient of the sampled positions, scattered back onto the stride-1 grid
                 a2s, Ts, Fs = rec["a2s"], rec["Ts"], rec["Fs"]
                 if rec["pooled"]:
@@ -925,6 +948,54 @@ class _FrontendFn(torch.autograd.Function):
         return (None, None, None, None) + tuple(G.get(p) for p in ctx.params)
 
 
+def _ln2d_affine(blk, name, norm):
+    """LayerNorm2D's [C, F] affine parameters in the (f, c) order of a channels-last frame."""
+    gam = cached(blk, name + ".ln_w", (norm.norm.weight,), lambda t: t.t().contiguous().reshape(-1).float())
+    bet = cached(blk, name + ".ln_b", (norm.norm.bias,), lambda t: t.t().contiguous().reshape(-1).float())
+    return gam, bet
+
+
+def _ln2d_block_bwd(blk, rec, d, G, B):
+    """Backward of one LayerNorm2D block of the CNN front-end (fp32): pool/ReLU mask -> LN backward -> conv gradients, twice."""
+    T, F = rec["T"], rec["F"]
+    a1, a2, x, z1, z2 = rec["a1"], rec["a2"], rec["x"], rec["z1"], rec["z2"]
+    Ts, Fs = rec.get("Ts", T), rec.get("Fs", F)
+    C = a2.shape[-1]
+
+    def ln_bwd(dn, z, norm, name, t, f):
+        gam, _ = _ln2d_affine(blk, name, norm)
+        dgam = torch.zeros(f * C, dtype=torch.float32, device=z.device)
+        dbet = torch.zeros(f * C, dtype=torch.float32, device=z.device)
+        dz = ops.layernorm_bwd(dn.reshape(B * t, f * C).float(), z.reshape(B * t, f * C), gam, norm.norm.eps, dgamma=dgam, dbeta=dbet)
+        G.put(norm.norm.weight, dgam.view(f, C).t())            # back to the parameter's [C, F] layout (tiny)
+        G.put(norm.norm.bias, dbet.view(f, C).t())
+        return dz.view(B, t, f, C)
+
+    if rec["pooled"]:
+        dn2 = ops.maxpool2d_relu_bwd(a2.view(B, Ts, Fs, C), d.float() if d.dtype != torch.float32 else d, rec["pt"], rec["pf"],
+                                     in_chmajor=rec["chmajor"])
+    else:
+        dn2 = ops.relu_mask(d.reshape(a2.shape).float(), a2)
+    dz2s = ln_bwd(dn2, z2, blk.norm2, "conv2", Ts, Fs)
+    if "stride" in rec:
+        dz2 = torch.zeros(B, T, F, C, dtype=torch.float32, device=dz2s.device)
+        dz2[:, ::rec["stride"][0], ::rec["stride"][1]] = dz2s
+    else:
+        dz2 = dz2s
+    ops.conv3x3_wgrad(a1, dz2, G.buf(blk.conv2.weight), G.buf(blk.conv2.bias), B, T, F)
+    wd2 = cached(blk, "conv2.dgrad_w", (blk.conv2.weight,), lambda w: ops.conv3x3_dgrad_weight(w).float())
+    zb2 = cached(blk, "conv2.zero_bias_in", (blk.conv2.weight,), lambda w: torch.zeros(w.shape[1], dtype=torch.float32, device=w.device))
+    da1 = ops.conv3x3_relu(dz2, wd2, zb2, B, T, F, in_chmajor=False, relu=False, out_dtype=torch.float32)
+    dn1 = ops.relu_mask(da1.reshape(a1.shape), a1)
+    dz1 = ln_bwd(dn1, z1, blk.norm1, "conv1", T, F)
+    ops.conv3x3_wgrad(x, dz1, G.buf(blk.conv1.weight), G.buf(blk.conv1.bias), B, T, F, in_chmajor=rec["first"])
+    if rec["first"]:
+        return None
+    wd1 = cached(blk, "conv1.dgrad_w", (blk.conv1.weight,), lambda w: ops.conv3x3_dgrad_weight(w).float())
+    zb1 = cached(blk, "conv1.zero_bias_in", (blk.conv1.weight,), lambda w: torch.zeros(w.shape[1], dtype=torch.float32, device=w.device))
+    return ops.conv3x3_relu(dz1, wd1, zb1, B, T, F, in_chmajor=False, relu=False, out_dtype=torch.float32)
+
+
 def frontend_check(enc):
     """Raise NotImplementedError for CNN front-end variants without a training path (inference handles them)."""
     if getattr(enc, "is_1dconv", False):
@@ -933,7 +1004,7 @@ def frontend_check(enc):
         if blk.training and blk.dropout.p > 0:
             raise NotImplementedError("dropout > 0 in the CNN front-end is not on the B200 path (build_encoder passes 0)")
         if not blk.trainable:
-            raise NotImplementedError("training path of the CNN front-end: no normalisation, no residual only")
+            raise NotImplementedError("training path of the CNN front-end: BatchNorm2d / residual blocks are inference-only")
 
 
 def frontend_forward(enc, xs, out_scale, prec):

@@ -55,5 +55,40 @@ def main():
         print(name, tuple(ys.shape), ylens.tolist())
 
 
+sys.path.insert(0, HERE)
+from gen_golden_conv_weights import loss_weights  # noqa: E402
+
+
+def main_grads():
+    """Training-mode gradients of the LayerNorm2D cases (train(): same function, dropout 0): d sum(ys * w) / d parameter, with
+    non-trivial LayerNorm affine parameters.  -> zz_convgrad_*.npz (sd.*, xs, xlens, ys, g.*); w = loss_weights(...)."""
+    mod = importlib.import_module('neural_sp.models.seq2seq.encoders.conv')
+    for name in ("ln2d", "stride_ln"):
+        torch.manual_seed(0)
+        args = dict(BASE)
+        args.update(CASES[name])
+        enc = mod.ConvEncoder(**args).train()
+        g = torch.Generator().manual_seed(2)
+        with torch.no_grad():
+            for k, p in enc.named_parameters():
+                if ".norm" in k:
+                    p.add_(0.3 * torch.randn(p.shape, generator=g))
+        rng = np.random.default_rng(7)
+        xlens = [61, 50, 38]
+        xs = np.zeros((3, 61, 80), np.float32)
+        for b, n in enumerate(xlens):
+            xs[b, :n] = rng.standard_normal((n, 80)).astype(np.float32)
+        ys, ylens = enc(torch.from_numpy(xs), torch.IntTensor(xlens))
+        w = loss_weights(tuple(ys.shape), ylens.tolist())
+        (ys * torch.from_numpy(w)).sum().backward()
+        save = {"sd." + k: v.detach().numpy() for k, v in enc.state_dict().items()}
+        save.update({"g." + k: p.grad.numpy() for k, p in enc.named_parameters()})
+        save.update(xs=xs, xlens=np.array(xlens, np.int32), ys=ys.detach().numpy(), ys_lens=ylens.numpy().astype(np.int32),
+                    cfg=np.array(json.dumps(args)))
+        np.savez_compressed(os.path.join(HERE, "zz_convgrad_%s.npz" % name), **save)
+        print("grad", name, tuple(ys.shape), len([k for k in save if k.startswith("g.")]))
+
+
 if __name__ == "__main__":
     main()
+    main_grads()

@@ -600,6 +600,10 @@ def frontend_forward(enc, xs, out_scale, prec):
     neural_sp_b200.autograd.frontend_forward (one autograd node with hand-written CUDA backward, checked on the GPU)."""
     from neural_sp_b200 import autograd as ag
     ag.frontend_check(enc)                       # same support envelope as the real node
+    if any(getattr(blk, "norm1", None) is not None for blk in enc.layers):
+        # LayerNorm2D blocks: no second restatement -- the REAL node runs over the op doubles, so the comparison with the
+        # live reference in test_reference_matrix_train_cpu.py checks the node's own forward and backward chain
+        return ag._FrontendFn.apply(xs, enc, float(out_scale), prec, *[p for p in enc.parameters()])
     B, T, Fd = xs.shape
     x = xs.view(B, T, enc.in_channel, Fd // enc.in_channel).transpose(1, 2)
     for blk in enc.layers:

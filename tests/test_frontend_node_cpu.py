@@ -46,3 +46,61 @@ def test_frontend_node_matches_torch_autograd(ov, monkeypatch):
         assert err <= 2e-4, (k, err)
     lens = enc.output_lens(torch.IntTensor([37, 30, 11]))
     assert lens.tolist()[0] == y.shape[1]
+
+
+def _ln2d_stack(enc, xs, out_scale):
+    """torch restatement of the LayerNorm2D front-end (reference conv.py:362-421): conv -> LN over a frame's [C, F] -> ReLU."""
+    F_ = torch.nn.functional
+    B, T, Fd = xs.shape
+    x = xs.view(B, T, enc.in_channel, Fd // enc.in_channel).transpose(1, 2)
+
+    def ln(norm, t):                                     # [B, C, T, F] -> LayerNorm([C, F]) per frame
+        return norm.norm(t.transpose(1, 2)).transpose(1, 2)
+    for blk in enc.layers:
+        x = torch.relu(ln(blk.norm1, F_.conv2d(x, blk.conv1.weight, blk.conv1.bias, padding=1)))
+        x = torch.relu(ln(blk.norm2, F_.conv2d(x, blk.conv2.weight, blk.conv2.bias, padding=1, stride=tuple(blk.stride))))
+        if blk.pool is not None:
+            x = F_.max_pool2d(x, blk.pooling, blk.pooling, ceil_mode=True)
+    B, C, T, Fq = x.shape
+    x = x.transpose(1, 2).reshape(B, T, C * Fq)
+    if enc.bridge is not None:
+        x = F_.linear(x, enc.bridge.weight, enc.bridge.bias)
+    return x * out_scale
+
+
+@pytest.mark.parametrize("ov", [
+    dict(), dict(poolings="(1,1)_(2,2)", bottleneck_dim=24), dict(strides="(1,1)_(2,2)", poolings="(1,1)_(1,1)"),
+    dict(strides="(2,2)_(1,1)", poolings="(1,1)_(2,2)", bottleneck_dim=8), dict(input_dim=120, in_channel=3, channels="16_32"),
+])
+def test_layernorm2d_frontend_node_matches_torch_autograd(ov, monkeypatch):
+    """LayerNorm2D blocks in training: LN forward / backward kernels between the convolutions, affine parameters permuted
+    between the parameter's [C, F] layout and the channels-last frame's (f, c) order."""
+    import ops_doubles
+    from neural_sp_b200 import autograd as ag
+    from neural_sp_b200.encoders.conv import ConvEncoder
+    real_node = ag.frontend_forward
+    ops_doubles.install_training(monkeypatch)
+    torch.manual_seed(0)
+    enc = ConvEncoder(**_cfg(normalization='layer_norm', **ov)).train()
+    enc.set_precision("fp32")
+    with torch.no_grad():                                # non-trivial affine parameters
+        for blk in enc.layers:
+            for n in (blk.norm1, blk.norm2):
+                n.norm.weight.add_(0.3 * torch.randn_like(n.norm.weight))
+                n.norm.bias.add_(0.3 * torch.randn_like(n.norm.bias))
+    rng = np.random.RandomState(1)
+    xs = torch.from_numpy(rng.randn(3, 37, enc.in_channel * enc.input_freq).astype(np.float32))
+    y_ref = _ln2d_stack(enc, xs, 1.7)
+    w = torch.from_numpy(rng.randn(*y_ref.shape).astype(np.float32))
+    (y_ref * w).sum().backward()
+    ref = {k: p.grad.clone() for k, p in enc.named_parameters()}
+    enc.zero_grad()
+    y = real_node(enc, xs, 1.7, "fp32")
+    assert y.shape == y_ref.shape
+    assert float((y - y_ref).abs().max()) <= 1e-5 * float(y_ref.abs().max())
+    (y * w).sum().backward()
+    for k, p in enc.named_parameters():
+        d = (p.grad - ref[k]).abs() / ref[k].abs().max().clamp_min(1e-12)
+        # a normalised value within rounding of 0 may pass the ReLU in one implementation and not in the other: that flips ONE
+        # mask bit and shows up in the one (f, c) entry of the LayerNorm gradients it feeds -- tolerated, at most 2 per tensor
+        assert int((d > 1e-3).sum()) <= 2 and float(d.max()) <= 5e-2, (k, float(d.max()), int((d > 1e-3).sum()))

@@ -3,7 +3,7 @@ function): neural_sp_b200's autograd nodes (ops replaced by their torch restatem
 autograd over the UNMODIFIED reference with identical weights -- outputs (incl. sub-task outputs) and every parameter
 gradient.  Configurations whose training path is not on the B200 path raise NotImplementedError and are reported as skips
 (the inference parity of ALL configurations is tests/test_reference_matrix_cpu.py); the skip reasons are the honest list of
-training gaps: strided / normalised / residual / 1-D CNN blocks, GroupNorm conv module, latency-controlled BLSTM.
+training gaps (today: BatchNorm2d CNN blocks only).
 Needs /root/reference (build container only): skipped elsewhere."""
 import importlib
 import os
