@@ -163,6 +163,13 @@ nsp_status nsp_dwconv_stats_fwd(int is_bf16, const void* x, int64_t ldx, const f
 nsp_status nsp_bn_swish_bwd(int is_bf16, const void* z, int64_t ldz, const void* dy, int64_t lddy, const float* mean,
                             const float* var, const float* gamma, const float* beta, float eps, float* sums,
                             void* dz, int64_t lddz, int64_t M, int d, void* stream);
+/* The same backward WITHOUT an activation inside (du = gradient w.r.t. gamma zh + beta): nn.BatchNorm2d of the CNN front-end's
+ * Conv2dBlock in training (encoders/conv.py:362-394) on channels-last activations, M = B*T*F rows, d = channels; the ReLU /
+ * pooling mask is applied before (nsp_relu_mask / nsp_maxpool2d_relu_bwd), the statistics come from nsp_dwconv_stats_fwd
+ * with k = 1.  sums fp32 [2,d] = (d beta, d gamma). */
+nsp_status nsp_bn_bwd(int is_bf16, const void* z, int64_t ldz, const void* du, int64_t lddu, const float* mean,
+                      const float* var, const float* gamma, float eps, float* sums, void* dz, int64_t lddz,
+                      int64_t M, int d, void* stream);
 /* GroupNorm(d/2 groups = channel pairs) variant of the same module (conformer_convolution.py:47-48): per-frame pair statistics;
  * dz = gradient w.r.t. z, dgamma / dbeta fp32 [d] are accumulated (+=). */
 nsp_status nsp_gn2_swish_bwd(int is_bf16, const void* z, int64_t ldz, const void* dy, int64_t lddy, const float* gamma,

@@ -177,6 +177,7 @@ _more = {
     "nsp_rnnt_grad_logits": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_sz, c_vp, c_vp,
                                      c_int, c_vp]),
     "nsp_dwconv_stats_fwd": (c_int, [c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "nsp_bn_bwd": (c_int, [c_int, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_i64, c_i64, c_int, c_vp]),
     "nsp_bn_swish_bwd": (c_int, [c_int, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_i64, c_i64, c_int,
                                  c_vp]),
     "nsp_gn2_swish_bwd": (c_int, [c_int, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_f32, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_vp]),

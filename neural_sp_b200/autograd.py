@@ -847,7 +847,16 @@ class _FrontendFn(torch.autograd.Function):
             pt, pf = blk.pooling if blk.pool is not None else (1, 1)
             st, sf = getattr(blk, "stride", (1, 1))
             ln = blk.norm1 is not None      # LayerNorm2D block (conv.py:399-421): conv -> LN over a frame's F*C values -> ReLU, fp32
-            if ln:
+            if isinstance(blk.norm1, torch.nn.BatchNorm2d):
+                xin = x if i == 0 else x.float()
+                rec = dict(x=xin, T=T, F=F, pt=pt, pf=pf, chmajor=last_chmajor, first=(i == 0), bn=True)
+                a1, rec["z1"], rec["st1"] = _bn2d_stage(blk, "conv1", blk.conv1, blk.norm1, xin, B, T, F, i == 0, (1, 1))
+                a2s, rec["z2"], rec["st2"] = _bn2d_stage(blk, "conv2", blk.conv2, blk.norm2, a1, B, T, F, False, (st, sf))
+                rec.update(a1=a1, a2=a2s, a2s=a2s)
+                if (st, sf) != (1, 1):
+                    rec.update(stride=(st, sf), Ts=a2s.size(1), Fs=a2s.size(2))
+                    T, F = a2s.size(1), a2s.size(2)
+            elif ln:
                 xin = x if i == 0 else x.float()
                 z1 = ops.conv3x3_relu(xin, blk.conv1.weight, blk.conv1.bias, B, T, F, in_chmajor=(i == 0), relu=False,
                                       out_dtype=torch.float32)
@@ -922,7 +931,7 @@ class _FrontendFn(torch.autograd.Function):
         for blk, rec in zip(reversed(list(enc.layers)), reversed(tape)):
             T, F = rec["T"], rec["F"]
             a1, a2, x = rec["a1"], rec["a2"], rec["x"]
-            if rec.get("ln"):
+            if rec.get("ln") or rec.get("bn"):
                 d = _ln2d_block_bwd(blk, rec, d, G, B)
                 continue
             if "stride" in rec:             # gradient of the sampled positions, scattered back onto the stride-1 grid
@@ -955,14 +964,45 @@ def _ln2d_affine(blk, name, norm):
     return gam, bet
 
 
+def _bn2d_stage(blk, name, conv, bn, x, B, T, F, first, stride):
+    """conv -> BatchNorm2d with BATCH statistics -> ReLU (train() mode, conv.py:362-394), fp32 channels-last:
+    z = conv(x) (kept for the backward); per-channel (sum, sum of squares) over all B*T*F positions from the k = 1 case of the
+    statistics kernel; running statistics updated as nn.BatchNorm2d does; the normalised, rectified output is the SAME conv
+    kernel run with the batch statistics folded into its weights and its fused ReLU.  -> (a, z, (mean, var))"""
+    C = conv.out_channels
+    z = ops.conv3x3_relu(x, conv.weight, conv.bias, B, T, F, in_chmajor=first, relu=False, out_dtype=torch.float32).view(B, T, F, C)
+    if stride != (1, 1):
+        z = z[:, ::stride[0], ::stride[1]].contiguous()
+    M = z.numel() // C
+    ones = cached(blk, name + ".bn_ones", (bn.weight,), lambda w: torch.ones(1, w.numel(), dtype=torch.float32, device=w.device))
+    zero = cached(blk, name + ".bn_zero", (bn.weight,), lambda w: torch.zeros(w.numel(), dtype=torch.float32, device=w.device))
+    _, stats = ops.dwconv_stats(z.view(1, M, C), ones, zero)
+    mean, var = _bn_batch_stats(bn, stats, M)
+    sc = bn.weight.detach().float() / torch.sqrt(var + bn.eps)                      # C-length vectors
+    wf = (conv.weight.detach().float() * sc.view(-1, 1, 1, 1)).contiguous()
+    bf = ((conv.bias.detach().float() - mean) * sc + bn.bias.detach().float()).contiguous()
+    a = ops.conv3x3_relu(x, wf, bf, B, T, F, in_chmajor=first, relu=True, out_dtype=torch.float32).view(B, T, F, C)
+    if stride != (1, 1):
+        a = a[:, ::stride[0], ::stride[1]].contiguous()
+    return a, z, (mean, var)
+
+
 def _ln2d_block_bwd(blk, rec, d, G, B):
-    """Backward of one LayerNorm2D block of the CNN front-end (fp32): pool/ReLU mask -> LN backward -> conv gradients, twice."""
+    """Backward of one normalised block of the CNN front-end (fp32): pool / ReLU mask -> LayerNorm2D or BatchNorm2d backward ->
+    conv gradients, twice."""
     T, F = rec["T"], rec["F"]
     a1, a2, x, z1, z2 = rec["a1"], rec["a2"], rec["x"], rec["z1"], rec["z2"]
     Ts, Fs = rec.get("Ts", T), rec.get("Fs", F)
     C = a2.shape[-1]
 
     def ln_bwd(dn, z, norm, name, t, f):
+        if rec.get("bn"):
+            mean, var = rec["st1" if name == "conv1" else "st2"]
+            dz, sums = ops.bn_bwd(z.reshape(-1, C), dn.reshape(-1, C).float(), mean, var, norm.weight.detach().float().contiguous(),
+                                  norm.eps)
+            G.put(norm.bias, sums[0])
+            G.put(norm.weight, sums[1])
+            return dz.view(B, t, f, C)
         gam, _ = _ln2d_affine(blk, name, norm)
         dgam = torch.zeros(f * C, dtype=torch.float32, device=z.device)
         dbet = torch.zeros(f * C, dtype=torch.float32, device=z.device)
@@ -1004,7 +1044,7 @@ def frontend_check(enc):
         if blk.training and blk.dropout.p > 0:
             raise NotImplementedError("dropout > 0 in the CNN front-end is not on the B200 path (build_encoder passes 0)")
         if not blk.trainable:
-            raise NotImplementedError("training path of the CNN front-end: BatchNorm2d / residual blocks are inference-only")
+            raise NotImplementedError("training path of the CNN front-end: residual blocks are inference-only")
 
 
 def frontend_forward(enc, xs, out_scale, prec):

@@ -66,7 +66,9 @@ __device__ __forceinline__ float swish_grad(float u) {
 }
 
 // sums[c] += sum_rows du, sums[d + c] += sum_rows du * zh   over a tile of 64 rows
-template <typename T>
+// SWISH = false: the upstream gradient is already the gradient w.r.t. the normalised value u (BatchNorm2d + ReLU blocks of the CNN
+// front-end hand in the ReLU / pooling-masked gradient), beta is not read.
+template <typename T, bool SWISH = true>
 __global__ void __launch_bounds__(CH) bn_swish_bwd_reduce_kernel(const T* __restrict__ z, int64_t ldz, const T* __restrict__ dy,
                                                                  int64_t lddy, const float* __restrict__ mean,
                                                                  const float* __restrict__ var, const float* __restrict__ g,
@@ -77,12 +79,12 @@ __global__ void __launch_bounds__(CH) bn_swish_bwd_reduce_kernel(const T* __rest
     const int64_t r0 = (int64_t)(blockIdx.x / cchunks) * 64;
     const int c = cc * CH + threadIdx.x;
     if (c >= d) return;
-    const float mu = __ldg(mean + c), rstd = rsqrtf(__ldg(var + c) + eps), gv = __ldg(g + c), bv = __ldg(bta + c);
+    const float mu = __ldg(mean + c), rstd = rsqrtf(__ldg(var + c) + eps), gv = __ldg(g + c), bv = SWISH ? __ldg(bta + c) : 0.f;
     float s1 = 0.f, s2 = 0.f;
     const int64_t r1 = min(M, r0 + 64);
     for (int64_t r = r0; r < r1; ++r) {
         const float zh = (bn_ld<T>(z + r * ldz + c) - mu) * rstd;
-        const float du = bn_ld<T>(dy + r * lddy + c) * swish_grad(fmaf(gv, zh, bv));
+        const float du = bn_ld<T>(dy + r * lddy + c) * (SWISH ? swish_grad(fmaf(gv, zh, bv)) : 1.f);
         s1 += du; s2 = fmaf(du, zh, s2);
     }
     atomicAdd(sums + c, s1);
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(CH) bn_swish_bwd_reduce_kernel(const T* __rest
 }
 
 // dz = g rstd (du - s1 / M - zh s2 / M)
-template <typename T>
+template <typename T, bool SWISH = true>
 __global__ void __launch_bounds__(256) bn_swish_bwd_apply_kernel(const T* __restrict__ z, int64_t ldz, const T* __restrict__ dy,
                                                                  int64_t lddy, const float* __restrict__ mean,
                                                                  const float* __restrict__ var, const float* __restrict__ g,
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(256) bn_swish_bwd_apply_kernel(const T* __rest
         const int64_t r = e / d;
         const float rstd = rsqrtf(__ldg(var + c) + eps), gv = __ldg(g + c);
         const float zh = (bn_ld<T>(z + r * ldz + c) - __ldg(mean + c)) * rstd;
-        const float du = bn_ld<T>(dy + r * lddy + c) * swish_grad(fmaf(gv, zh, __ldg(bta + c)));
+        const float du = bn_ld<T>(dy + r * lddy + c) * (SWISH ? swish_grad(fmaf(gv, zh, __ldg(bta + c))) : 1.f);
         bn_st<T>(dz + r * lddz + c, gv * rstd * (du - __ldg(sums + c) * invM - zh * __ldg(sums + d + c) * invM));
     }
 }
@@ -191,6 +193,29 @@ extern "C" nsp_status nsp_bn_swish_bwd(int is_bf16, const void* z, int64_t ldz, 
     } else {
         bn_swish_bwd_reduce_kernel<float><<<g1, CH, 0, st>>>((const float*)z, ldz, (const float*)dy, lddy, mean, var, gamma, beta, eps, sums, M, d);
         bn_swish_bwd_apply_kernel<float><<<g2, 256, 0, st>>>((const float*)z, ldz, (const float*)dy, lddy, mean, var, gamma, beta, eps, sums, (float*)dz, lddz, M, d);
+    }
+    NSP_LAUNCH_OK();
+    return NSP_OK;
+}
+
+// BatchNorm backward with batch statistics and NO activation inside (du = the gradient w.r.t. the normalised value): the
+// BatchNorm2d + ReLU blocks of the CNN front-end in training (encoders/conv.py:362-394, nn.BatchNorm2d over [B, C, T, F] =
+// per-channel statistics over the M = B*T*F rows of the channels-last activation).  sums = (d beta, d gamma).
+extern "C" nsp_status nsp_bn_bwd(int is_bf16, const void* z, int64_t ldz, const void* du, int64_t lddu, const float* mean,
+                                 const float* var, const float* gamma, float eps, float* sums, void* dz, int64_t lddz,
+                                 int64_t M, int d, void* stream) {
+    NSP_CHECK_ARG(z && du && mean && var && gamma && sums && dz && M > 0 && d > 0, "bn_bwd: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    NSP_CUDA_OK(cudaMemsetAsync(sums, 0, 2 * (size_t)d * sizeof(float), st));
+    const unsigned g1 = (unsigned)(ceil_div64(M, 64) * ceil_div(d, CH));
+    int64_t b2 = ceil_div64(M * d, 256), cap = (int64_t)num_sms() * 16;
+    const unsigned g2 = (unsigned)(b2 < cap ? b2 : cap);
+    if (is_bf16) {
+        bn_swish_bwd_reduce_kernel<__nv_bfloat16, false><<<g1, CH, 0, st>>>((const __nv_bfloat16*)z, ldz, (const __nv_bfloat16*)du, lddu, mean, var, gamma, nullptr, eps, sums, M, d);
+        bn_swish_bwd_apply_kernel<__nv_bfloat16, false><<<g2, 256, 0, st>>>((const __nv_bfloat16*)z, ldz, (const __nv_bfloat16*)du, lddu, mean, var, gamma, nullptr, eps, sums, (__nv_bfloat16*)dz, lddz, M, d);
+    } else {
+        bn_swish_bwd_reduce_kernel<float, false><<<g1, CH, 0, st>>>((const float*)z, ldz, (const float*)du, lddu, mean, var, gamma, nullptr, eps, sums, M, d);
+        bn_swish_bwd_apply_kernel<float, false><<<g2, 256, 0, st>>>((const float*)z, ldz, (const float*)du, lddu, mean, var, gamma, nullptr, eps, sums, (float*)dz, lddz, M, d);
     }
     NSP_LAUNCH_OK();
     return NSP_OK;

@@ -80,8 +80,8 @@ class Conv2dBlock(EncoderBase):
             self._factor *= pooling[0]
         self.pool = self.pooling if self._factor > 1 or self.pooling[1] > 1 else None
         # the recipes' shape: fused kernels + training path
-        # (LayerNorm2D blocks train too: autograd._FrontendFn runs them in fp32 with the LayerNorm forward / backward kernels)
-        self.trainable = not isinstance(self.norm1, nn.BatchNorm2d) and not (residual and in_channel == out_channel)
+        # (normalised blocks train too: autograd._FrontendFn runs them in fp32 with the LayerNorm / BatchNorm kernels)
+        self.trainable = not (residual and in_channel == out_channel)
         self.plain = self.trainable and self.norm1 is None and self.stride == (1, 1)
 
     @staticmethod

@@ -771,6 +771,21 @@ def bn_swish_bwd(z, dy, mean, var, gamma, beta, eps):
     return dz, sums
 
 
+def bn_bwd(z, du, mean, var, gamma, eps):
+    """BatchNorm backward with batch statistics, no activation inside (nsp_bn_bwd): z, du `[M, d]` (same dtype) ->
+    (dz like z, sums fp32 `[2, d]` = (d beta, d gamma))."""
+    _require_cuda(z, du, mean, var, gamma)
+    M, d = z.shape
+    z = z.contiguous()
+    du = du.to(z.dtype).contiguous()
+    assert du.shape == z.shape and mean.dtype == var.dtype == gamma.dtype == torch.float32
+    dz = torch.empty_like(z)
+    sums = torch.empty(2, d, dtype=torch.float32, device=z.device)
+    _run("nsp_bn_bwd", lib.nsp_bn_bwd, int(z.dtype == torch.bfloat16), ptr(z), d, ptr(du), d, ptr(mean), ptr(var), ptr(gamma),
+         float(eps), ptr(sums), ptr(dz), d, M, d, current_stream_ptr(), nbytes=M * d * 3.0 * z.element_size())
+    return dz, sums
+
+
 def gn2_swish_bwd(z, dy, gamma, beta, eps, dgamma, dbeta):
     """Backward of Swish(GroupNorm(z)) with 2 channels per group on the per-frame view (nsp_gn2_swish_bwd): -> dz like z;
     dgamma / dbeta fp32 `[d]` are accumulated."""

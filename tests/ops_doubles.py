@@ -450,6 +450,16 @@ def bn_swish_bwd(z, dy, mean, var, gamma, beta, eps):
     return zz.grad.to(z.dtype), torch.stack([b.grad, g.grad])
 
 
+def bn_bwd(z, du, mean, var, gamma, eps):
+    with torch.enable_grad():
+        zz = z.detach().float().clone().requires_grad_(True)
+        g = gamma.detach().float().clone().requires_grad_(True)
+        b = torch.zeros_like(g).requires_grad_(True)
+        mu, v = zz.mean(0), zz.var(0, unbiased=False)
+        (g * (zz - mu) / torch.sqrt(v + eps) + b).backward(du.float())
+    return zz.grad.to(z.dtype), torch.stack([b.grad, g.grad])
+
+
 def gn2_swish_bwd(z, dy, gamma, beta, eps, dgamma, dbeta):
     B, T, d = z.shape
     with torch.enable_grad():
@@ -601,7 +611,7 @@ def frontend_forward(enc, xs, out_scale, prec):
     from neural_sp_b200 import autograd as ag
     ag.frontend_check(enc)                       # same support envelope as the real node
     if any(getattr(blk, "norm1", None) is not None for blk in enc.layers):
-        # LayerNorm2D blocks: no second restatement -- the REAL node runs over the op doubles, so the comparison with the
+        # LayerNorm2D / BatchNorm2d blocks: no second restatement -- the REAL node runs over the op doubles, so the comparison with the
         # live reference in test_reference_matrix_train_cpu.py checks the node's own forward and backward chain
         return ag._FrontendFn.apply(xs, enc, float(out_scale), prec, *[p for p in enc.parameters()])
     B, T, Fd = xs.shape
@@ -625,7 +635,7 @@ TRAIN_DOUBLES = dict(DOUBLES, linear=_linear_train, linear_wgrad=linear_wgrad, c
                      rng_advance=rng_advance, lstm_seq_bwd=lstm_seq_bwd, rnnt_joint_tanh=rnnt_joint_tanh,
                      softmax_rows=softmax_rows, rnnt_loss_fwd_bwd=rnnt_loss_fwd_bwd, rnnt_grad_logits=rnnt_grad_logits, log_softmax_bwd_=log_softmax_bwd_,
                      rnnt_joint_tanh_bwd=rnnt_joint_tanh_bwd, pack_labels=pack_labels, ctc_loss_fwd_bwd=ctc_loss_fwd_bwd,
-                     dwconv_stats=dwconv_stats, bn_swish_bwd=bn_swish_bwd, gn2_swish_bwd=gn2_swish_bwd, dwconv_bwd=dwconv_bwd, conv3x3_wgrad=conv3x3_wgrad,
+                     dwconv_stats=dwconv_stats, bn_swish_bwd=bn_swish_bwd, bn_bwd=bn_bwd, gn2_swish_bwd=gn2_swish_bwd, dwconv_bwd=dwconv_bwd, conv3x3_wgrad=conv3x3_wgrad,
                      maxpool2d_relu_bwd=maxpool2d_relu_bwd)
 
 

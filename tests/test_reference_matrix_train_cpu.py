@@ -3,7 +3,7 @@ function): neural_sp_b200's autograd nodes (ops replaced by their torch restatem
 autograd over the UNMODIFIED reference with identical weights -- outputs (incl. sub-task outputs) and every parameter
 gradient.  Configurations whose training path is not on the B200 path raise NotImplementedError and are reported as skips
 (the inference parity of ALL configurations is tests/test_reference_matrix_cpu.py); the skip reasons are the honest list of
-training gaps (today: BatchNorm2d CNN blocks only).
+training gaps (today: none; one configuration is skipped because the reference's own gradients are not finite).
 Needs /root/reference (build container only): skipped elsewhere."""
 import importlib
 import os
@@ -74,6 +74,13 @@ def test_reference_test_matrix_training_parity(family, ov, ov_conv, monkeypatch)
     lr.backward()
     lo.backward()
     rg = dict(ref.named_parameters())
+    nonfinite = sorted(k for k, p in rg.items() if p.grad is not None and not bool(torch.isfinite(p.grad).all()))
+    if nonfinite:
+        # the REFERENCE's own autograd overflows here (BatchNorm2d front-end + the eps = 1e-12 LayerNorms of the Conformer
+        # blocks at these toy sizes: NaN / 1e13 gradients); forward parity held above, and the overflow is reproduced:
+        ours_nonfinite = sorted(k for k, p in ours.named_parameters() if p.grad is not None and not bool(torch.isfinite(p.grad).all()))
+        assert ours_nonfinite == nonfinite
+        pytest.skip("the reference's gradients are not finite for this configuration (%d tensors; same set on both sides)" % len(nonfinite))
     gmax = max(float(p.grad.abs().max()) for p in rg.values() if p.grad is not None)
     bad = []
     for k, p in ours.named_parameters():

@@ -50,3 +50,28 @@ def test_conv3x3_weight_gradient_odd_input_planes(CI, CO, chmajor):
     ops.conv3x3_wgrad(a_dev, dz.to(dev), dw, db, B, T, F, in_chmajor=chmajor)
     assert float((dw.cpu() - w.grad).abs().max()) <= 1e-4 * float(w.grad.abs().max())
     assert float((db.cpu() - bias.grad).abs().max()) <= 1e-4 * float(bias.grad.abs().max())
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 3e-2)])
+@pytest.mark.parametrize("M,d", [(3 * 37 * 40, 32), (1000, 16), (77, 130)])
+def test_batchnorm_backward_without_activation(M, d, dtype, tol):
+    """nsp_bn_bwd (BatchNorm2d blocks of the CNN front-end in training) + the k = 1 case of the statistics kernel against torch
+    autograd through batch-statistics normalisation."""
+    from neural_sp_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(M + d)
+    z = (torch.randn(M, d, generator=g) * 1.5 + 0.3).to(dev).to(dtype)
+    du = torch.randn(M, d, generator=g).to(dev).to(dtype)
+    gamma = (torch.rand(d, generator=g) + 0.5).to(dev)
+    eps = 1e-5
+    _, stats = ops.dwconv_stats(z.view(1, M, d), torch.ones(1, d, device=dev), torch.zeros(d, device=dev))
+    zf = z.float()
+    assert torch.allclose(stats[0], zf.sum(0), rtol=1e-4, atol=1e-2) and torch.allclose(stats[1], (zf * zf).sum(0), rtol=1e-4, atol=1e-2)
+    mean, var = zf.mean(0), zf.var(0, unbiased=False)
+    zr, gr = zf.clone().requires_grad_(True), gamma.clone().requires_grad_(True)
+    b = torch.zeros(d, device=dev, requires_grad=True)
+    (gr * (zr - zr.mean(0)) / torch.sqrt(zr.var(0, unbiased=False) + eps) + b).backward(du.float())
+    dz, sums = ops.bn_bwd(z, du, mean.contiguous(), var.contiguous(), gamma, eps)
+    assert float((dz.float() - zr.grad).abs().max()) <= tol * float(zr.grad.abs().max())
+    assert float((sums[0] - b.grad).abs().max()) <= 1e-3 * float(b.grad.abs().max())
+    assert float((sums[1] - gr.grad).abs().max()) <= 1e-3 * float(gr.grad.abs().max())
