@@ -129,77 +129,209 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_arm(w, steps, warmup, sample_B=1, sample_T=500, train=True):
-    """The reference's CPU path, restated (oracle/): encoder forward + CTC forward/backward on the host cores."""
+def synth_params(w, seed=0):
+    """Random-init weights of the workload's architecture as a plain {name: fp32 tensor} dict with the reference's
+    state_dict keys (encoders/conformer.py, conv.py, decoders/ctc.py) and its init rules (xavier_uniform, gain 1/sqrt(2) for
+    q/k/v: relative_multihead_attention.py:75-77; Lecun normal for the CNN: conv.py:161-165; uniform(+-0.1) for the CTC head).
+    Pure torch: every arm (ours / reference / eager) loads the SAME tensors, and none needs another arm's code to build them."""
     import torch
-    from oracle import encoder_oracle, ctc_oracle  # noqa: F401  (checker / baseline only)
-    from neural_sp_b200.encoders.conformer import ConformerEncoder
-    from neural_sp_b200.encoders.conv import ConvEncoder
-    try:
-        avail = len(os.sched_getaffinity(0))
-    except Exception:
-        avail = os.cpu_count() or 1
-    torch.manual_seed(0)
-    a = enc_args(w)
-    a["frontend_conv"] = ConvEncoder(**conv_args(w))
-    enc = ConformerEncoder(**a)                      # parameter container only (random init); arithmetic = oracle
-    sd = {k: v.detach().float().requires_grad_(train and v.is_floating_point()) for k, v in enc.state_dict().items()}
-    D, V = w["d_model"], w["vocab"]
-    W0, b0 = torch.randn(512, D) / D ** 0.5, torch.zeros(512)
-    W1, b1 = torch.randn(V, 512) / 512 ** 0.5, torch.zeros(V)
-    nl = w["n_layers"]
-    cfg = dict(kind="conformer", n_layers=nl, n_heads=w["n_heads"], d_model=D, pe_type="relative", clamp_len=10,
-               layer_norm_eps=1e-12, normalization="layer_norm", causal=False, lookaheads=[0] * nl,
-               subsample=[int(s) for s in w["subsample"].split("_")], dropout_layer=0.0,
-               conv=dict(in_channel=1, poolings=[tuple(int(v) for v in t.strip("()").split(",")) for t in w["poolings"].split("_")]),
-               ffn_activation="swish", n_layers_sub1=0)
-    w = dict(w, T=sample_T)          # bounded sample: fewer, shorter utterances of the same model (frames/s normalises)
-    xs, xlens, ys = synth_batch(w, sample_B, 1234)
-    xs_t = torch.from_numpy(xs)
-    ys_cat = torch.tensor([v for y in ys for v in y], dtype=torch.int32)
-    ylens = torch.tensor([len(y) for y in ys], dtype=torch.int32)
+    g = torch.Generator().manual_seed(seed)
+    d, dff, k = w["d_model"], w["d_ff"], w["kernel_size"]
 
-    def step():
-        if train:                      # reference training step: autograd through the whole encoder (torch CPU kernels)
-            for v in sd.values():
-                v.grad = None
-            out = encoder_oracle.encoder_forward(sd, xs_t, xlens, cfg)
+    def xavier(*shape, gain=1.0):
+        rf = int(np.prod(shape[2:])) if len(shape) > 2 else 1
+        bound = gain * (6.0 / ((shape[0] + shape[1]) * rf)) ** 0.5
+        return (torch.rand(*shape, generator=g) * 2 - 1) * bound
+
+    def lecun(*shape):
+        return torch.randn(*shape, generator=g) / float(np.prod(shape[1:])) ** 0.5
+
+    sd = {}
+    pools = [tuple(int(v) for v in t.strip("()").split(",")) for t in w["poolings"].split("_")]
+    ci, F = 1, 80
+    for i, (pt, pf) in enumerate(pools):
+        sd["conv.layers.%d.conv1.weight" % i] = lecun(32, ci, 3, 3)
+        sd["conv.layers.%d.conv1.bias" % i] = torch.zeros(32)
+        sd["conv.layers.%d.conv2.weight" % i] = lecun(32, 32, 3, 3)
+        sd["conv.layers.%d.conv2.bias" % i] = torch.zeros(32)
+        ci, F = 32, -(-F // pf)
+    sd["conv.bridge.weight"] = lecun(d, 32 * F)
+    sd["conv.bridge.bias"] = torch.zeros(d)
+    sd["pos_emb.inv_freq"] = 1 / (10000 ** (torch.arange(0.0, d, 2.0) / d))
+    for l in range(w["n_layers"]):
+        p = "layers.%d." % l
+        for n in ("norm1", "norm2", "norm3", "norm4", "norm5", "conv.norm"):
+            sd[p + n + ".weight"], sd[p + n + ".bias"] = torch.ones(d), torch.zeros(d)
+        for ff in ("feed_forward_macaron", "feed_forward"):
+            sd[p + ff + ".w_1.weight"], sd[p + ff + ".w_1.bias"] = xavier(dff, d), torch.zeros(dff)
+            sd[p + ff + ".w_2.weight"], sd[p + ff + ".w_2.bias"] = xavier(d, dff), torch.zeros(d)
+        for n in ("w_key", "w_value", "w_query"):
+            sd[p + "self_attn." + n + ".weight"] = xavier(d, d, gain=0.5 ** 0.5)
+        sd[p + "self_attn.w_out.weight"] = xavier(d, d)
+        sd[p + "conv.pointwise_conv1.weight"], sd[p + "conv.pointwise_conv1.bias"] = xavier(2 * d, d, 1), torch.zeros(2 * d)
+        sd[p + "conv.depthwise_conv.weight"], sd[p + "conv.depthwise_conv.bias"] = xavier(d, 1, k), torch.zeros(d)
+        sd[p + "conv.pointwise_conv2.weight"], sd[p + "conv.pointwise_conv2.bias"] = xavier(d, d, 1), torch.zeros(d)
+    sd["norm_out.weight"], sd["norm_out.bias"] = torch.ones(d), torch.zeros(d)
+    V = w["vocab"]
+    head = {"output.fc0.weight": (torch.rand(512, d, generator=g) * 2 - 1) * 0.1, "output.fc0.bias": torch.zeros(512),
+            "output.fc1.weight": (torch.rand(V, 512, generator=g) * 2 - 1) * 0.1, "output.fc1.bias": torch.zeros(V)}
+    return sd, head
+
+
+def port_cfg(w):
+    nl = w["n_layers"]
+    return dict(kind="conformer", n_layers=nl, n_heads=w["n_heads"], d_model=w["d_model"], pe_type="relative", clamp_len=10,
+                layer_norm_eps=1e-12, normalization="layer_norm", causal=False, lookaheads=[0] * nl,
+                subsample=[int(s) for s in w["subsample"].split("_")], dropout_layer=0.0,
+                conv=dict(in_channel=1, poolings=[tuple(int(v) for v in t.strip("()").split(",")) for t in w["poolings"].split("_")]),
+                ffn_activation="swish", n_layers_sub1=0)
+
+
+class PortStep:
+    """One step of the reference's torch path, restated (oracle/encoder_oracle.py + torch's own ctc_loss, the arithmetic of
+    reference CTC.forward ctc.py:124-129 and kldiv_lsm_ctc criterion.py:110-127), on `device`: the host cores for the
+    cpu_baseline / --impl reference legs, cuda for the torch-eager-on-B200 baseline.  Never part of the product path."""
+
+    def __init__(self, w, sd, head, xs, xlens, ys, device, train=True, lsm=0.1):
+        import torch
+        from oracle import encoder_oracle            # checker / baseline only
+        self.torch, self.enc_fwd, self.train, self.lsm = torch, encoder_oracle.encoder_forward, train, lsm
+        self.cfg, self.V, self.B = port_cfg(w), w["vocab"], len(xlens)
+        self.sd = {k: v.to(device).requires_grad_(train and k != "pos_emb.inv_freq") for k, v in sd.items()}
+        self.head = {k: v.to(device).requires_grad_(True) for k, v in head.items()}
+        self.xs, self.xlens = torch.as_tensor(xs).to(device), list(xlens)
+        self.ys_cat = torch.tensor([v for y in ys for v in y], dtype=torch.int32)
+        self.ylens = torch.tensor([len(y) for y in ys], dtype=torch.int32)
+        self.device = device
+
+    def __call__(self):
+        torch, Fn = self.torch, self.torch.nn.functional
+        for v in list(self.sd.values()) + list(self.head.values()):
+            v.grad = None
+        if self.train:                 # reference training step: autograd through the whole encoder
+            out = self.enc_fwd(self.sd, self.xs, self.xlens, self.cfg)
             e = out["xs"]
         else:
             with torch.no_grad():
-                out = encoder_oracle.encoder_forward(sd, xs_t, xlens, cfg)
+                out = self.enc_fwd(self.sd, self.xs, self.xlens, self.cfg)
             e = out["xs"].requires_grad_(True)
-        logits = torch.nn.functional.linear(torch.nn.functional.linear(e, W0, b0), W1, b1)
+        h = self.head
+        logits = Fn.linear(Fn.linear(e, h["output.fc0.weight"], h["output.fc0.bias"]), h["output.fc1.weight"], h["output.fc1.bias"])
         elens = torch.tensor(out["xlens"], dtype=torch.int32)
-        # reference CTC.forward arithmetic (ctc.py:124-129): log_softmax -> CTCLoss(sum, zero_infinity)/B + lsm KL
-        lp = logits.log_softmax(-1)
-        loss = torch.nn.functional.ctc_loss(lp.transpose(0, 1), ys_cat, elens, ylens, reduction="sum", zero_infinity=True) / sample_B
-        mask = (torch.arange(lp.size(1))[None, :] < elens[:, None]).unsqueeze(-1)
-        kl = (lp.exp() * (lp - float(np.log(1.0 / (V - 1)))) * mask).sum() / float(elens.sum())
-        (loss * 0.9 + kl * 0.1).backward()
-        return float(loss.detach())
+        lp = logits.float().log_softmax(-1)
+        loss = Fn.ctc_loss(lp.transpose(0, 1), self.ys_cat.to(lp.device), elens, self.ylens, reduction="sum",
+                           zero_infinity=True) / self.B
+        mask = (torch.arange(lp.size(1), device=lp.device)[None, :] < elens.to(lp.device)[:, None]).unsqueeze(-1)
+        kl = (lp.exp() * (lp - float(np.log(1.0 / (self.V - 1)))) * mask).sum() / float(elens.sum())
+        total = loss * (1 - self.lsm) + kl * self.lsm
+        total.backward()
+        return total.detach()
 
-    # torch's CPU kernels stop scaling (and with many tiny ops get much slower) long before 128 threads: time the sample
-    # at 8, 16, 32, ... up to every available core and report the BEST thread count, i.e. the reference at its fastest.
-    cands = sorted({min(avail, c) for c in (8, 16, 32, 64, 128, avail)})
+
+def _avail_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_arm(w, steps, warmup, sample_B=8, train=True, lengths="fixed", budget_s=240.0):
+    """The reference's CPU path (oracle port) on the host cores: `sample_B` utterances of the workload's own batch (same
+    T, same weights), best thread count, `warmup` untimed + `steps` timed steps (cut short only by the time budget)."""
+    import torch
+    avail = _avail_cores()
+    sd, head = synth_params(w)
+    xs, xlens, ys = synth_batch(w, w["B"], 1234, lengths)
+    xs, xlens, ys = xs[:sample_B, :max(xlens[:sample_B])], xlens[:sample_B], ys[:sample_B]
+    step = PortStep(w, sd, head, xs, xlens, ys, "cpu", train=train)
+    # torch's CPU kernels stop scaling long before 128 threads (many small ops): pick the thread count with the fastest
+    # single step, i.e. the reference at its best on this host.
+    cands = sorted({min(avail, c) for c in (16, 32, 64, avail)})
     best = None
+    t_begin = time.perf_counter()
     for nthr in cands:
         torch.set_num_threads(nthr)
-        step()                                     # warm-up at this thread count (thread pool, oneDNN primitives)
+        if best is None:
+            step()                                   # first touch: thread pool, oneDNN primitive caches
         t0 = time.perf_counter()
-        for _ in range(steps):
-            step()
-        dt = (time.perf_counter() - t0) / steps
+        step()
+        dt = time.perf_counter() - t0
         if best is None or dt < best[0]:
             best = (dt, nthr)
         elif dt > 1.2 * best[0]:
-            break                                   # past the knee: more threads only hurt
-    dt, cores = best
+            break
+    torch.set_num_threads(best[1])
+    for _ in range(warmup):
+        step()
+    done, t0, loss = 0, time.perf_counter(), None
+    while done < steps:
+        loss = step()
+        done += 1
+        if time.perf_counter() - t_begin > budget_s:
+            break
+    dt = (time.perf_counter() - t0) / done
     frames = sum(xlens)
-    return dict(value=frames / dt, ms_per_step=dt * 1e3, cores=cores,
-                sample="B=%d T=%d of workload, %d %s step(s) after 1 warm-up, best of thread counts %s on %d available cores "
-                       "(oracle port of the reference's torch-CPU path)" %
-                       (sample_B, w["T"], steps, "training (fwd+loss+bwd)" if train else "fwd+loss", cands, avail))
+    return dict(value=frames / dt, ms_per_step=dt * 1e3, cores=best[1], steps=done, loss=float(loss), sample_B=sample_B,
+                sample="first %d of the workload's %d utterances (T=%d, same weights), %d timed %s step(s) after %d warm-up, "
+                       "%d threads = fastest of %s on %d available cores (oracle port of the reference's torch-CPU path)" %
+                       (sample_B, w["B"], max(xlens), done, "training (fwd+loss+bwd)" if train else "fwd+loss", warmup, best[1],
+                        cands, avail))
+
+
+def eager_cuda_arm(w, dev, steps, warmup, train=True, lengths="fixed", seed=1234):
+    """Baseline (B) of SURVEY.md 8d: the reference's module chain (oracle port: same torch ops the reference's nn.Modules
+    call) under torch eager on this B200 -- cuBLAS / cuDNN / ATen ctc_loss -- on the full per-GPU batch.  Three variants:
+    torch defaults (fp32 matmuls, cuDNN TF32), TF32 matmuls allowed, and bf16 autocast (the reference's own modules crash
+    under autocast -- SURVEY fact 3 -- the functional port does not, so this is an upper bound for 'stock torch')."""
+    import torch
+    sd, head = synth_params(w)
+    xs, xlens, ys = synth_batch(w, w["B"], seed, lengths)
+    step = PortStep(w, sd, head, xs, xlens, ys, dev, train=train)
+    frames = sum(xlens)
+    l2 = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    out = {}
+
+    def run(tag, ctx):
+        try:
+            with ctx():
+                for _ in range(max(3, warmup)):
+                    loss = step()
+                torch.cuda.synchronize()
+                evs = []
+                for _ in range(steps):
+                    l2.zero_()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    loss = step()
+                    b.record()
+                    evs.append((a, b))
+                torch.cuda.synchronize()
+            ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+            out[tag] = {"ms_per_step": ms, "frames_per_s": frames / (ms * 1e-3), "loss": float(loss)}
+        except Exception as ex:
+            out[tag] = {"error": repr(ex)[:200]}
+        torch.cuda.empty_cache()
+
+    import contextlib
+    old = torch.backends.cuda.matmul.allow_tf32
+
+    @contextlib.contextmanager
+    def tf32():
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            yield
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = old
+
+    run("fp32_torch_defaults", contextlib.nullcontext)
+    run("tf32", tf32)
+    run("bf16_autocast", lambda: torch.autocast("cuda", dtype=torch.bfloat16))
+    ok = {k: v for k, v in out.items() if "ms_per_step" in v}
+    best = min(ok, key=lambda k: ok[k]["ms_per_step"]) if ok else None
+    return {"what": "oracle port of the reference's module chain under torch eager on this GPU (cuBLAS/cuDNN/ATen), %s step, "
+                    "B=%d" % ("train (fwd+loss+bwd, no optimizer)" if train else "fwd+loss+head bwd", w["B"]),
+            "variants": out, "best": best, "ms_per_step": ok[best]["ms_per_step"] if best else None,
+            "frames_per_s": ok[best]["frames_per_s"] if best else None, "steps": steps}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -208,7 +340,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager"],
+                    help="ours: the CUDA library; reference: the reference's CPU path (oracle port) on the host cores; "
+                         "eager: the same port under torch eager on cuda (cuBLAS/cuDNN/ATen) -- SURVEY 8d baseline (B)")
+    ap.add_argument("--no-eager", action="store_true", help="skip the torch-eager-on-B200 baseline in the default line")
     ap.add_argument("--workload", default="conformer_l_ctc", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -245,18 +380,36 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps, warmup = max(1, min(args.steps, 2)), 1      # bounded sample; one warm-up step per tried thread count
-        r = cpu_reference_arm(w, steps, warmup, train=args.step == "train")
+        # Bounded sample per step: 8 utterances of the same workload (a B=32 x T=1000 training step takes ~15 s on the host;
+        # the frames/s metric normalises).  Steps / warm-up are the driver's, capped only by a 4-minute budget.
+        r = cpu_reference_arm(w, max(1, args.steps), max(0, min(args.warmup, 2)), train=args.step == "train", lengths=args.lengths)
         cfg_common = dict(cfg_common, step=("train: encoder_fwd + ctc_head + ctc_loss + backward through head and encoder "
                                             "(torch autograd on the host cores; no optimizer, no all-reduce)")
-                          if args.step == "train" else "fwd: encoder_fwd + ctc_head + ctc_loss + head backward")
+                          if args.step == "train" else "fwd: encoder_fwd + ctc_head + ctc_loss + head backward",
+                          sample_batch=r["sample_B"], sample_note="same model, T and weights as the CUDA arm; %d utterances per "
+                          "step instead of %d so that the run stays bounded" % (r["sample_B"], w["B"]))
         line = {"impl": "reference", "metric": "speech_frames_per_sec", "value": r["value"], "unit": "frames/s",
-                "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"],
+                "n_gpus": args.gpus, "steps": r["steps"], "warmup": max(0, min(args.warmup, 2)), "ms_per_step": r["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": cfg_common,
+                "config": cfg_common, "loss": r["loss"],
                 "cpu_baseline": {"value": r["value"], "unit": "frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    if args.impl == "eager":
+        if rank != 0:
+            return
+        import torch
+        dev = torch.device("cuda", local_rank)
+        torch.cuda.set_device(dev)
+        r = eager_cuda_arm(w, dev, args.steps, args.warmup, train=args.step == "train", lengths=args.lengths)
+        frames = sum(synth_batch(w, w["B"], 1234, args.lengths)[1])
+        line = {"impl": "eager", "metric": "speech_frames_per_sec", "value": r["frames_per_s"], "unit": "frames/s", "n_gpus": 1,
+                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": r["best"], "data": "synthetic", "config": cfg_common,
+                "eager_b200": r, "gpu_launches": 0}
         print(json.dumps(line))
         return
 
@@ -277,11 +430,16 @@ def main():
     a = enc_args(w)
     a["dropout"] = args.dropout
     a["frontend_conv"] = ConvEncoder(**conv_args(w))
-    enc = ConformerEncoder(**a).to(dev)
+    enc = ConformerEncoder(**a)
+    sd_synth, head_synth = synth_params(w)           # the weights every arm uses (strict: the reference's state_dict keys)
+    enc.load_state_dict(sd_synth, strict=True)
+    enc = enc.to(dev)
     enc = enc.train() if args.step == "train" else enc.eval()
     enc.set_precision(args.precision)
     ctc = CTC(eos=2, blank=0, enc_n_units=w["d_model"], vocab=w["vocab"], dropout=args.dropout, lsm_prob=0.1,
-              fc_list="512").to(dev)
+              fc_list="512")
+    ctc.load_state_dict(head_synth, strict=True)
+    ctc = ctc.to(dev)
     ctc.train()
     for m in ctc.modules():
         m.precision = args.precision
@@ -301,6 +459,7 @@ def main():
     if args.step == "train" and args.optimizer == "adam":
         opt = torch.optim.Adam(all_params, lr=1e-5, fused=True, capturable=True)
 
+    e2e_bytes = {"labels": 0}
     works = []                             # in-flight bucket all-reduces of the current step (bucketed mode, N > 1)
 
     def step_fwd(x_dev):
@@ -376,6 +535,7 @@ def main():
         return sum(s.elapsed_time(e) for s, e in evs) / steps
 
     sampler = ClockSampler(local_rank)
+    graph_keep = []
 
     def measure(step_fn, with_e2e=True):
         """Warm up, capture the step into a CUDA graph (launch-bound: hundreds of kernels per step), time K replays with
@@ -418,7 +578,19 @@ def main():
         barrier()
         ms_e2e = None
         if with_e2e:
+            labels_dev, ylens_dev, Lmax = ops.pack_labels(ys, dev)      # the device tensors every step (and the graph) reads
+            lab_host = torch.zeros(len(ys), Lmax, dtype=torch.int32).pin_memory()
+            ylen_host = torch.zeros(len(ys), dtype=torch.int32).pin_memory()
+            e2e_bytes["labels"] = int(lab_host.numel() * 4 + ylen_host.numel() * 4)
+
             def step_e2e():
+                # the host side of one step, as the facade does it (speech2text.py:396-409): pack this step's label lists,
+                # copy features + labels + label lengths host -> device, run, read the loss back
+                for b_, y_ in enumerate(ys):
+                    lab_host[b_, :len(y_)] = torch.as_tensor(y_, dtype=torch.int32)
+                    ylen_host[b_] = len(y_)
+                labels_dev.copy_(lab_host, non_blocking=True)
+                ylens_dev.copy_(ylen_host, non_blocking=True)
                 if graph is None:
                     loss = step_fn(xs_host.to(dev, non_blocking=True))
                 else:
@@ -432,7 +604,28 @@ def main():
             barrier()
             ms_e2e = timed(step_e2e, args.steps)
             barrier()
-        return dict(ms_dev=ms_dev, ms_e2e=ms_e2e, launches_per_step=lps, graph=graph is not None, graph_error=graph_error)
+        graph_keep.append(graph)
+        return dict(ms_dev=ms_dev, ms_e2e=ms_e2e, launches_per_step=lps, graph=graph is not None, graph_error=graph_error,
+                    loss=float(run_step()))
+
+    # ---- loss of the product on the CPU baseline's sample (first 8 utterances), before any parameter update ----
+    loss_check = None
+    if not args.no_cpu_baseline and world == 1 and not args.ncu_step:
+        nb = min(8, B)
+        xs8 = xs_dev[:nb, :max(xlens[:nb])].contiguous()
+        loss_check = {}
+        was_training = enc.training
+        enc.eval()
+        with torch.no_grad():
+            for prec in ("fp32", args.precision):
+                enc.set_precision(prec)
+                ctc.set_precision(prec)
+                o8 = enc(xs8, torch.IntTensor(xlens[:nb]), task='ys')
+                l8, _ = ctc(o8['ys']['xs'], o8['ys']['xlens'], ys[:nb])
+                loss_check[prec] = float(l8)
+        enc.set_precision(args.precision)
+        ctc.set_precision(args.precision)
+        enc.train(was_training)
 
     if args.ncu_step:
         for _ in range(3):
@@ -538,17 +731,33 @@ def main():
                                gemm_epilogue=("direct", "tma", "tma+cta_pairs")[_lib.lib.nsp_get_gemm_epilogue()]),
                 "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e,
-                        "h2d_bytes_per_step": int(xs_host.numel() * 4), "d2h_bytes_per_step": 4},
-                "gpu_launches": int(launches),
+                        "h2d_bytes_per_step": int(xs_host.numel() * 4) + e2e_bytes["labels"], "d2h_bytes_per_step": 4,
+                        "includes": "host packing of the label lists + H2D of features, labels, label lengths + D2H of the loss"},
+                "gpu_launches": int(launches), "loss": main["loss"],
                 "roofline": roofline, "roofline_ctc": roofline_ctc, "ctc_loss_ms_per_batch": ctc_ms,
                 "kernel_time_ms_per_step": {k: round(v["ms"] / nprof, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}}
         if fwd is not None:
             line["fwd"] = {"value": frames_per_step * world / (ms_fwd * 1e-3), "unit": "frames/s", "ms_per_step": ms_fwd,
                            "step": "encoder_fwd + ctc_head + ctc_fwd_bwd + head_bwd (inference kernels, eval mode)",
                            "cuda_graph": fwd["graph"]}
+        if not args.no_eager and world == 1:
+            del graph_keep[:]                           # release the graphs' private pools before the eager baseline allocates
+            torch.cuda.empty_cache()
+            line["eager_b200"] = eager_cuda_arm(w, dev, max(3, min(args.steps, 10)), 3, train=args.step == "train",
+                                                lengths=args.lengths, seed=1234 + rank)
+            if line["eager_b200"]["ms_per_step"]:
+                line["speedup_vs_eager_b200"] = line["eager_b200"]["ms_per_step"] / ms_dev
         if not args.no_cpu_baseline and world == 1:
-            r = cpu_reference_arm(w, 1, 0, train=args.step == "train")
+            r = cpu_reference_arm(w, 3, 1, train=args.step == "train", lengths=args.lengths, budget_s=90.0)
             line["cpu_baseline"] = {"value": r["value"], "unit": "frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+            if loss_check is not None:                 # same weights, same 8 utterances: the product's loss vs the port's
+                ref_loss = r["loss"]
+                loss_check = {"port_cpu_fp32": ref_loss, "ours": loss_check,
+                              "rel_err": {k: abs(v - ref_loss) / abs(ref_loss) for k, v in loss_check.items()},
+                              "bound": {"fp32": 1e-3, "tf32": 5e-3, "bf16": 2e-2}}
+                line["loss_check"] = loss_check
+                for k, e in loss_check["rel_err"].items():
+                    assert e <= loss_check["bound"][k], "loss parity broken in %s mode: %r" % (k, loss_check)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -36,23 +36,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-// Build with `make EXTRA=-DNSP_BOUNDED_WAITS` while bringing a tcgen05 kernel up on new shapes: a lost arrival then traps
-// with a message after ~2 s instead of hanging the GPU (a hang costs a `gpurun` strike).  The default build keeps the bare
-// spin loop of the validated kernels (no printf stack frame in the hot kernels).
+// Every mbarrier wait is bounded: a lost arrival (protocol bug at an untested size class) traps with a message after ~2 s
+// instead of hanging the GPU.  The report lives in a cold, non-inlined function so the spin loop itself stays three
+// instructions; the clock is sampled once per 256 polls.
+static __device__ __noinline__ void mbar_timeout(uint32_t bar_addr, uint32_t parity) {
+    printf("mbarrier wait timed out (block %d thread %d, smem 0x%x, parity %u)\n", blockIdx.x, threadIdx.x, bar_addr, parity);
+    __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-#ifdef NSP_BOUNDED_WAITS
     if (mbar_try_wait(bar, parity)) return;
     const long long deadline = clock64() + 4000000000LL;
+    uint32_t polls = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() > deadline) {
-            printf("mbarrier wait timed out (block %d thread %d, smem 0x%x, parity %u)\n", blockIdx.x, threadIdx.x,
-                   smem_u32(bar), parity);
-            __trap();
-        }
+        if ((++polls & 255u) == 0 && clock64() > deadline) mbar_timeout(smem_u32(bar), parity);
     }
-#else
-    while (!mbar_try_wait(bar, parity)) {}
-#endif
 }
 
 // ---------------- TMA ----------------

@@ -7,7 +7,7 @@ import torch
 
 from test_gemm_gpu import _ref
 
-pytestmark = [pytest.mark.gpu, pytest.mark.experimental]
+pytestmark = pytest.mark.gpu
 
 
 def _mode(mode):

@@ -36,7 +36,6 @@ def test_conv_fixtures_cpu(name, monkeypatch):
 
 
 @pytest.mark.gpu
-@pytest.mark.experimental          # first hardware run: profiles/run_round2_validation.sh, stage 1
 @pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 5e-2)])
 @pytest.mark.parametrize("name", CASES)
 def test_conv_fixtures_gpu(name, precision, tol):
@@ -44,7 +43,6 @@ def test_conv_fixtures_gpu(name, precision, tol):
 
 
 @pytest.mark.gpu
-@pytest.mark.experimental
 @pytest.mark.parametrize("M,D", [(7, 2560), (3, 4100), (5, 2049)])
 def test_layernorm_wide_rows(M, D):
     from neural_sp_b200 import ops
@@ -58,7 +56,6 @@ def test_layernorm_wide_rows(M, D):
 
 
 @pytest.mark.gpu
-@pytest.mark.experimental
 def test_mask_rects_kernel_and_staging():
     from neural_sp_b200 import ops
     from neural_sp_b200.frontends.input import pad_and_upload
@@ -134,7 +131,6 @@ def test_layernorm2d_training_fixtures_cpu(name, monkeypatch):
 
 
 @pytest.mark.gpu
-@pytest.mark.experimental
 @pytest.mark.parametrize("name", GRAD_CASES)
 def test_layernorm2d_training_fixtures_gpu(name):
     e_out, errs = _run_grads(name, torch.device("cuda:0"), "fp32")

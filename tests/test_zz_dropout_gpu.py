@@ -12,9 +12,7 @@ import torch
 from conftest import load_golden
 from enc_util import build_ours, golden_cfg
 
-# opt-in (NSP_EXPERIMENTAL=1) until the first supervised hardware run at the start of round 2: everything in this file was
-# written after the round's GPU budget was spent (host logic pinned on CPU; profiles/run_round2_validation.sh, stage 1)
-pytestmark = [pytest.mark.gpu, pytest.mark.experimental]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("n", [4096, 1003, 7, 1 << 20])

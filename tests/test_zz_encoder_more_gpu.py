@@ -13,9 +13,7 @@ import torch
 from conftest import GOLDEN, load_golden
 from enc_util import build_ours
 
-# opt-in (NSP_EXPERIMENTAL=1) until the first supervised hardware run at the start of round 2: everything in this file was
-# written after the round's GPU budget was spent (host logic pinned on CPU; profiles/run_round2_validation.sh, stage 1)
-pytestmark = [pytest.mark.gpu, pytest.mark.experimental]
+pytestmark = pytest.mark.gpu
 CASES = sorted(os.path.basename(f)[len("zz_enc_"):-4] for f in glob.glob(os.path.join(GOLDEN, "zz_enc_*.npz")))
 TOL = {"fp32": 1e-4, "tf32": 5e-3, "bf16": 5e-2}
 

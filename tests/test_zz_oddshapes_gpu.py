@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.experimental]     # first hardware run: profiles/run_round2_validation.sh, stage 1
+pytestmark = pytest.mark.gpu     # first hardware run: profiles/run_round2_validation.sh, stage 1
 
 
 @pytest.mark.parametrize("M,D", [(48, 10), (37, 2560), (64, 30)])

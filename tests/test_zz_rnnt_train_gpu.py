@@ -7,9 +7,7 @@ unmodified reference on CPU by tests/test_rnnt_train_wiring_cpu.py.)"""
 import pytest
 import torch
 
-# opt-in (NSP_EXPERIMENTAL=1) until the first supervised hardware run at the start of round 2: everything in this file was
-# written after the round's GPU budget was spent (host logic pinned on CPU; profiles/run_round2_validation.sh, stage 1)
-pytestmark = [pytest.mark.gpu, pytest.mark.experimental]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("rows,V", [(37, 50), (5, 1000), (3, 2500), (64, 8)])
