@@ -280,7 +280,7 @@ def cpu_reference_arm(w, steps, warmup, sample_B=8, train=True, lengths="fixed",
 
 def eager_cuda_arm(w, dev, steps, warmup, train=True, lengths="fixed", seed=1234):
     """Baseline (B) of SURVEY.md 8d: the reference's module chain (oracle port: same torch ops the reference's nn.Modules
-    call) under torch eager on this B200 -- cuBLAS / cuDNN / ATen ctc_loss -- on the full per-GPU batch.  Three variants:
+    call) under torch eager on this B200 -- cuBLAS / cuDNN / ATen ctc_loss -- on the full per-GPU batch.  Variants:
     torch defaults (fp32 matmuls, cuDNN TF32), TF32 matmuls allowed, and bf16 autocast (the reference's own modules crash
     under autocast -- SURVEY fact 3 -- the functional port does not, so this is an upper bound for 'stock torch')."""
     import torch
@@ -325,7 +325,8 @@ def eager_cuda_arm(w, dev, steps, warmup, train=True, lengths="fixed", seed=1234
 
     run("fp32_torch_defaults", contextlib.nullcontext)
     run("tf32", tf32)
-    run("bf16_autocast", lambda: torch.autocast("cuda", dtype=torch.bfloat16))
+    run("fp16_autocast", lambda: torch.autocast("cuda", dtype=torch.float16))     # the reference's own AMP mode (train.py:235-254)
+    run("bf16_autocast", lambda: torch.autocast("cuda", dtype=torch.bfloat16))    # the reference itself cannot
     ok = {k: v for k, v in out.items() if "ms_per_step" in v}
     best = min(ok, key=lambda k: ok[k]["ms_per_step"]) if ok else None
     return {"what": "oracle port of the reference's module chain under torch eager on this GPU (cuBLAS/cuDNN/ATen), %s step, "

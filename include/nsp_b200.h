@@ -429,12 +429,16 @@ nsp_status nsp_relpos_attention_bwd(int is_bf16, const void* q, int64_t ldq, con
                                     int chunk_c, int chunk_l, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Backward of nsp_conformer_conv_fwd (LayerNorm variant only): dy = gradient of y; dz_ws = scratch [B*T, d] in the
- * I/O dtype; dx = gradient of x; dw [k,d], dbias [d], dnorm_w [d], dnorm_b [d] fp32 are ACCUMULATED. */
+ * I/O dtype; dx = gradient of x; dw [k,d], dbias [d], dnorm_w [d], dnorm_b [d] fp32 are ACCUMULATED.  workspace
+ * (nsp_conformer_conv_bwd_workspace_bytes) holds the per-CTA partial sums of the four parameter gradients, which a last
+ * kernel adds up: no atomics, deterministic.  Replaces autograd over modules/conformer_convolution.py:113-124. */
+size_t nsp_conformer_conv_bwd_workspace_bytes(int B, int T, int d, int k);
 nsp_status nsp_conformer_conv_bwd(int is_bf16, const void* x, int64_t ldx, const float* w, const float* bias,
                                   int norm_mode, const float* norm_w, const float* norm_b, float eps,
                                   const void* dy, int64_t lddy, void* dz_ws, int64_t lddz, void* dx, int64_t lddx,
                                   float* dw, float* dbias, float* dnorm_w, float* dnorm_b,
-                                  int B, int T, int d, int k, int causal, void* stream);
+                                  int B, int T, int d, int k, int causal, void* workspace, size_t workspace_bytes,
+                                  void* stream);
 
 #ifdef __cplusplus
 }

@@ -199,7 +199,8 @@ _more = {
                                                c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                                c_int, c_int, c_vp, ctypes.POINTER(c_int), c_vp]),
     "nsp_conformer_conv_bwd": (c_int, [c_int, c_vp, c_i64, c_vp, c_vp, c_int, c_vp, c_vp, c_f32, c_vp, c_i64, c_vp, c_i64,
-                                       c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
+                                       c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_sz, c_vp]),
+    "nsp_conformer_conv_bwd_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
 }
 for _name, (_res, _args) in _more.items():
     _fn = getattr(lib, _name)

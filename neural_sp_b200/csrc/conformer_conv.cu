@@ -13,6 +13,8 @@
 // k x d taps sit in shared memory; a warp owns 4 frames, a lane owns channels lane, lane+32, ...;
 // the per-frame normalisation statistics are warp-shuffle reductions over registers.
 #include "common.cuh"
+#include "conv_stream.h"
+#include <stdlib.h>
 
 namespace nsp {
 namespace {
@@ -225,6 +227,11 @@ extern "C" nsp_status nsp_conformer_conv_fwd(int is_bf16, const void* x, int64_t
     p.y = y; p.ldy = ldy; p.B = B; p.T = T; p.d = d; p.k = k; p.left_pad = causal ? (k - 1) : (k - 1) / 2;
     p.mode = norm_mode; p.eps = eps;
     cudaStream_t st = (cudaStream_t)stream;
+    static const bool legacy = [] { const char* e = getenv("NSP_CONV_PATH"); return e && !strcmp(e, "legacy"); }();
+    if (norm_mode == 0 && !legacy) {        // LayerNorm variant: streaming kernel when the shape is covered
+        const nsp_status s = conv_stream_fwd(is_bf16, x, ldx, w, bias, norm_w, norm_b, eps, y, ldy, B, T, d, k, causal, st);
+        if (s != NSP_ERR_UNSUPPORTED) return s;
+    }
     if (d > 1024) { set_error("conformer_conv: d=%d unsupported (max 1024)", d); return NSP_ERR_UNSUPPORTED; }
     if (is_bf16) {
         if (d <= 256) return launch_conv<__nv_bfloat16, 8>(p, st);

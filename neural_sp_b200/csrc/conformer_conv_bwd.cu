@@ -8,6 +8,8 @@
 // Only the LayerNorm variant is differentiable here (the LibriSpeech recipes' choice); BatchNorm / GroupNorm training
 // is rejected by the host wrapper.
 #include "common.cuh"
+#include "conv_stream.h"
+#include <stdlib.h>
 
 namespace nsp {
 namespace {
@@ -323,7 +325,8 @@ extern "C" nsp_status nsp_conformer_conv_bwd(int is_bf16, const void* x, int64_t
                                              int norm_mode, const float* norm_w, const float* norm_b, float eps,
                                              const void* dy, int64_t lddy, void* dz_ws, int64_t lddz, void* dx, int64_t lddx,
                                              float* dw, float* dbias, float* dnorm_w, float* dnorm_b,
-                                             int B, int T, int d, int k, int causal, void* stream) {
+                                             int B, int T, int d, int k, int causal, void* workspace, size_t workspace_bytes,
+                                             void* stream) {
     NSP_CHECK_ARG(x && w && bias && norm_w && norm_b && dy && dz_ws && dx, "conformer_conv_bwd: null pointer");
     NSP_CHECK_ARG(B > 0 && T > 0 && d > 0 && k >= 1 && (k % 2 == 1), "conformer_conv_bwd: bad shape B=%d T=%d d=%d k=%d", B, T, d, k);
     if (norm_mode != 0) { set_error("conformer_conv_bwd: only the LayerNorm variant is differentiable on this path"); return NSP_ERR_UNSUPPORTED; }
@@ -333,6 +336,12 @@ extern "C" nsp_status nsp_conformer_conv_bwd(int is_bf16, const void* x, int64_t
     p.dz = dz_ws; p.lddz = lddz; p.dx = dx; p.lddx = lddx; p.dw = dw; p.dbias = dbias; p.dg = dnorm_w; p.db = dnorm_b;
     p.B = B; p.T = T; p.d = d; p.k = k; p.left_pad = causal ? (k - 1) : (k - 1) / 2; p.eps = eps;
     cudaStream_t st = (cudaStream_t)stream;
+    static const bool legacy = [] { const char* e = getenv("NSP_CONV_PATH"); return e && !strcmp(e, "legacy"); }();
+    if (!legacy) {
+        const nsp_status s = conv_stream_bwd(is_bf16, x, ldx, w, bias, norm_w, norm_b, eps, dy, lddy, dz_ws, lddz, dx, lddx, dw,
+                                             dbias, dnorm_w, dnorm_b, B, T, d, k, causal, workspace, workspace_bytes, st);
+        if (s != NSP_ERR_UNSUPPORTED) return s;
+    }
     if (is_bf16) {
         if (d <= 256) return launch_conv_bwd<__nv_bfloat16, 8>(p, st);
         if (d <= 512) return launch_conv_bwd<__nv_bfloat16, 16>(p, st);
@@ -341,6 +350,10 @@ extern "C" nsp_status nsp_conformer_conv_bwd(int is_bf16, const void* x, int64_t
     if (d <= 256) return launch_conv_bwd<float, 8>(p, st);
     if (d <= 512) return launch_conv_bwd<float, 16>(p, st);
     return launch_conv_bwd<float, 32>(p, st);
+}
+
+extern "C" size_t nsp_conformer_conv_bwd_workspace_bytes(int B, int T, int d, int k) {
+    return conv_stream_bwd_workspace_bytes(B, T, d, k);
 }
 
 // Depthwise part alone (K2): dx, d(taps), d(conv bias) from dz = gradient w.r.t. the depthwise-conv output.  Used by the

@@ -17,7 +17,8 @@
 //                          register prefetch ring for the emissions), then all warps apply the
 //                          sparse "-= occupancy" fix-up to the <= L+1 touched columns of each row.
 //   K3 ctc_finalize_kernel deterministic reduction of nll / KL to the scalar loss.
-#include "common.cuh"
+#include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace nsp {
 namespace {
@@ -745,6 +746,12 @@ __global__ void __launch_bounds__(256) ctc_finalize_kernel(CtcParams p) {
     if (threadIdx.x == 0) p.loss[0] = loss;
 }
 
+}  // namespace
+}  // namespace nsp
+#include "ctc_stream.cuh"
+namespace nsp {
+namespace {
+
 template <int G, int VEC>
 nsp_status launch_rows(const CtcParams& p, int nvec, cudaStream_t st) {
     const int64_t rows = (int64_t)p.B * p.T;
@@ -773,7 +780,8 @@ extern "C" size_t nsp_ctc_loss_workspace_bytes(int B, int T, int Lmax) {
     size_t Sp = align_up(2 * (size_t)Lmax + 1, 16);
     size_t bt = (size_t)B * T;
     return align_up(3 * bt * Sp * sizeof(float), 256) + 3 * align_up(bt * sizeof(float), 256) +
-           align_up((size_t)B * sizeof(float), 256) + 2 * align_up((size_t)B * Sp * sizeof(int16_t), 256) + 256;
+           align_up((size_t)B * sizeof(float), 256) + 2 * align_up((size_t)B * Sp * sizeof(int16_t), 256) +
+           align_up((size_t)B * sizeof(int32_t), 256) + 256;
 }
 
 extern "C" nsp_status nsp_ctc_loss_fwd_bwd(const float* logits, int64_t stride_b, int64_t stride_t,
@@ -808,7 +816,60 @@ extern "C" nsp_status nsp_ctc_loss_fwd_bwd(const float* logits, int64_t stride_b
     p.klrow = (float*)w; w += align_up(bt * sizeof(float), 256);
     p.nll_raw = (float*)w; w += align_up((size_t)B * sizeof(float), 256);
     p.nxt = (int16_t*)w; w += align_up((size_t)B * p.Sp * sizeof(int16_t), 256);
-    p.head = (int16_t*)w;
+    p.head = (int16_t*)w; w += align_up((size_t)B * p.Sp * sizeof(int16_t), 256);
+    int32_t* ready = (int32_t*)w;
+
+    // ---- streaming path (ctc_stream.cuh): TMA-pipelined row pass with the lattice sweeps running under it ----
+    {
+        static const bool legacy = [] { const char* e = getenv("NSP_CTC_PATH"); return e && !strcmp(e, "legacy"); }();
+        const bool al16 = (V % 4 == 0) && (stride_b % 4 == 0) && (stride_t % 4 == 0) &&
+                          (((uintptr_t)logits) % 16 == 0) && (((uintptr_t)grad) % 16 == 0);
+        const bool contiguous = (stride_t == V) && (stride_b == (int64_t)T * V);
+        const int Smax = 2 * Lmax + 1;
+        const int V4 = V / 4;
+        if (!legacy && al16 && V <= 12288 && Smax <= 512 && (V4 > 320 || contiguous)) {
+            CtcStream q;
+            memset(&q, 0, sizeof(q));
+            q.mode_warp = V4 <= 320;
+            const size_t lat = (size_t)2 * 2 * CS_CT * p.Sp * sizeof(float);
+            const size_t avail = (size_t)220 * 1024 - align_up(lat, 1024);
+            const int64_t rows = (int64_t)bt;
+            if (q.mode_warp) {
+                int R = (int)(32768 / ((size_t)V * 4)) / 16 * 16;
+                R = R < 16 ? 16 : (R > 256 ? 256 : R);
+                const int spread = (int)(rows / num_sms()) / 16 * 16;        // small problems: use every SM
+                if (spread < R) R = spread < 16 ? 16 : spread;
+                q.R = R;
+            } else {
+                q.R = 1;
+            }
+            q.tile_floats = q.R * V;
+            const size_t tile_bytes = (size_t)q.tile_floats * sizeof(float);
+            q.stages = (int)(avail / tile_bytes);
+            if (q.stages > CS_MAX_STAGES) q.stages = CS_MAX_STAGES;
+            if (q.stages >= 2) {
+                q.ntiles = ceil_div64(rows, q.R);
+                q.K = Smax <= 32 ? 1 : Smax <= 64 ? 2 : Smax <= 128 ? 4 : Smax <= 256 ? 8 : 16;
+                q.ready = ready;
+                static const int dbg = [] { const char* e = getenv("NSP_CTC_DEBUG"); return e ? atoi(e) : 0; }();
+                q.dbg = dbg;
+                const size_t smem = (size_t)q.stages * tile_bytes + lat;
+                const unsigned grid = (unsigned)(q.ntiles < num_sms() ? q.ntiles : num_sms());
+                NSP_CUDA_OK(cudaMemsetAsync(ready, 0, (size_t)B * sizeof(int32_t), st));
+                if (q.mode_warp) {
+                    NSP_CUDA_OK(cudaFuncSetAttribute(ctc_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    ctc_stream_kernel<true><<<grid, CS_THREADS, smem, st>>>(p, q);
+                } else {
+                    NSP_CUDA_OK(cudaFuncSetAttribute(ctc_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    ctc_stream_kernel<false><<<grid, CS_THREADS, smem, st>>>(p, q);
+                }
+                NSP_LAUNCH_OK();
+                ctc_fixup_write_kernel<<<(unsigned)(ceil_div64((int64_t)bt, 8) + 1), 256, 0, st>>>(p);
+                NSP_LAUNCH_OK();
+                return NSP_OK;
+            }
+        }
+    }
 
     // ---- K1 ----
     const bool vec4 = (V % 4 == 0) && (stride_b % 4 == 0) && (stride_t % 4 == 0) &&

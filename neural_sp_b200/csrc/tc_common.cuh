@@ -36,19 +36,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-// Every mbarrier wait is bounded: a lost arrival (protocol bug at an untested size class) traps with a message after ~2 s
-// instead of hanging the GPU.  The report lives in a cold, non-inlined function so the spin loop itself stays three
-// instructions; the clock is sampled once per 256 polls.
-static __device__ __noinline__ void mbar_timeout(uint32_t bar_addr, uint32_t parity) {
-    printf("mbarrier wait timed out (block %d thread %d, smem 0x%x, parity %u)\n", blockIdx.x, threadIdx.x, bar_addr, parity);
-    __trap();
-}
+// Every mbarrier wait is bounded: a lost arrival (protocol bug at an untested size class) traps after ~2 s instead of
+// hanging the GPU.  The hot loop is the bare try_wait spin of round 1 plus one counter; the clock is only read once per
+// 4096 failed polls and the failure path is a bare `trap` (a printf call here cost 9 registers in conv3x3_tc and 10-50 % of
+// the GEMM / conv kernels' time: measured, profiles/README.md round 2).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long deadline = clock64() + 4000000000LL;
     uint32_t polls = 0;
+    long long deadline = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++polls & 255u) == 0 && clock64() > deadline) mbar_timeout(smem_u32(bar), parity);
+        if ((++polls & 4095u) == 0) {
+            const long long now = clock64();
+            if (deadline == 0) deadline = now + 4000000000LL;
+            else if (now > deadline) asm volatile("trap;");
+        }
     }
 }
 

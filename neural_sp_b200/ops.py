@@ -959,7 +959,9 @@ def conformer_conv_bwd(x, taps, dw_bias, norm_w, norm_b, eps, dy, dtaps, dbias, 
     dy = dy if dy.stride(2) == 1 and dy.stride(0) == T * dy.stride(1) else dy.contiguous()
     dz = torch.empty(B, T, d, dtype=x.dtype, device=x.device)
     dx = torch.empty(B, T, d, dtype=x.dtype, device=x.device)
+    ws_bytes = lib.nsp_conformer_conv_bwd_workspace_bytes(B, T, d, k)
+    ws = torch.empty(max(1, ws_bytes), dtype=torch.uint8, device=x.device)
     _run("nsp_conformer_conv_bwd", lib.nsp_conformer_conv_bwd, int(x.dtype == torch.bfloat16), ptr(x), x.stride(1), ptr(taps), ptr(dw_bias),
          0, ptr(norm_w), ptr(norm_b), float(eps), ptr(dy), dy.stride(1), ptr(dz), d, ptr(dx), d,
-         ptr(dtaps), ptr(dbias), ptr(dnorm_w), ptr(dnorm_b), B, T, d, k, int(causal), current_stream_ptr())
+         ptr(dtaps), ptr(dbias), ptr(dnorm_w), ptr(dnorm_b), B, T, d, k, int(causal), ptr(ws), ws_bytes, current_stream_ptr())
     return dx

@@ -1,0 +1,45 @@
+#!/usr/bin/env python3
+"""CTC fwd+bwd timing at the BASELINE sizes: CUDA events around the whole C-ABI call (memset + kernels), L2 flushed between
+iterations, algorithmic bytes = 8 B per logit.  NSP_CTC_PATH=legacy selects the round-1 three-kernel path."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from neural_sp_b200 import ops  # noqa: E402
+
+peak = 6582.5
+try:
+    peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    pass
+dev = torch.device("cuda")
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+out = {}
+for (B, T, V) in [(32, 125, 10000), (32, 250, 10000), (32, 125, 1000), (2, 200, 32)]:
+    rng = np.random.default_rng(0)
+    logits = torch.randn(B, T, V, device=dev)
+    L = max(1, int(0.45 * T))
+    ys = [rng.integers(4, V, size=L).tolist() for _ in range(B)]
+    labels, ylens, _ = ops.pack_labels(ys, dev)
+    elens = torch.full((B,), T, dtype=torch.int32, device=dev)
+    for _ in range(5):
+        ops.ctc_loss_fwd_bwd(logits, labels, elens, ylens, 0, 0.1)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(20):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ops.ctc_loss_fwd_bwd(logits, labels, elens, ylens, 0, 0.1)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = float(np.median(ts))
+    gbs = 8.0 * B * T * V / (ms * 1e-3) / 1e9
+    out["B%d_T%d_V%d" % (B, T, V)] = dict(ms=ms, min_ms=float(min(ts)), gbs=gbs, frac=gbs / peak)
+    print("ctc B=%d T'=%d V=%d: %.4f ms (min %.4f)  %.0f GB/s algorithmic = %.1f %% of %.0f" % (B, T, V, ms, min(ts), gbs, 100 * gbs / peak, peak))
+print(json.dumps({"path": os.environ.get("NSP_CTC_PATH", "stream"), "ctc": out}))

@@ -370,3 +370,43 @@ def test_ctc_training_step_end_to_end():
     for k, p in list(enc.named_parameters()) + list(ctc.named_parameters()):
         assert p.grad is not None and torch.isfinite(p.grad).all(), k
         assert float(p.grad.abs().max()) > 0, k
+
+
+# ---- streaming conv-module kernels (csrc/conformer_conv_stream.cu): every covered (d, k), both dtypes, causal, ragged T ----
+@pytest.mark.parametrize("d,k,T,causal,bf16", [(512, 15, 125, False, True), (512, 15, 500, False, True), (512, 15, 77, False, False),
+                                               (256, 15, 250, False, True), (256, 7, 33, True, False), (128, 5, 64, False, True),
+                                               (64, 3, 50, True, False), (512, 7, 31, True, True), (128, 15, 200, False, False)])
+def test_conv_module_streaming_kernels(d, k, T, causal, bf16):
+    """Forward, dx and the four parameter gradients of Swish(LayerNorm(dwconv(x))) against torch autograd in fp64."""
+    ops = ops_()
+    torch.manual_seed(d + k + T)
+    B = 3
+    x = torch.randn(B, T, d, device=DEV)
+    dy = torch.randn(B, T, d, device=DEV)
+    if bf16:
+        x, dy = x.bfloat16().float(), dy.bfloat16().float()
+    w = (torch.randn(d, 1, k, device=DEV) * 0.3).double().requires_grad_(True)
+    b = torch.randn(d, device=DEV).double().requires_grad_(True)
+    g = (1 + 0.1 * torch.randn(d, device=DEV)).double().requires_grad_(True)
+    be = (0.1 * torch.randn(d, device=DEV)).double().requires_grad_(True)
+    xr = x.double().requires_grad_(True)
+    pad = k - 1 if causal else (k - 1) // 2
+    z = F.conv1d(xr.transpose(1, 2), w, b, padding=pad, groups=d)
+    if causal:
+        z = z[:, :, :-pad]
+    y = F.silu(F.layer_norm(z.transpose(1, 2), (d,), g, be, 1e-12))
+    y.backward(dy.double())
+    taps = w.detach().float().reshape(d, k).t().contiguous()
+    dt = torch.bfloat16 if bf16 else torch.float32
+    f32 = lambda t: t.detach().float()
+    yk = ops.conformer_conv(x.to(dt), taps, f32(b), "layer_norm", f32(g), f32(be), 1e-12, causal=causal)
+    tol = 3e-2 if bf16 else 1e-4
+    assert rel_err(yk.float(), f32(y)) <= tol
+    dtaps, db, dg, dbe = torch.zeros_like(taps), torch.zeros(d, device=DEV), torch.zeros(d, device=DEV), torch.zeros(d, device=DEV)
+    dx = ops.conformer_conv_bwd(x.to(dt), taps, f32(b), f32(g), f32(be), 1e-12, dy.to(dt), dtaps, db, dg, dbe, causal=causal)
+    assert rel_err(dx.float(), f32(xr.grad)) <= tol
+    assert rel_err(dtaps.t().reshape(d, 1, k), f32(w.grad)) <= tol
+    assert rel_err(db, f32(b.grad)) <= tol and rel_err(dg, f32(g.grad)) <= tol and rel_err(dbe, f32(be.grad)) <= tol
+    # accumulate semantics (+=) of the parameter gradients: a second call doubles them
+    ops.conformer_conv_bwd(x.to(dt), taps, f32(b), f32(g), f32(be), 1e-12, dy.to(dt), dtaps, db, dg, dbe, causal=causal)
+    assert rel_err(0.5 * dg, f32(g.grad)) <= tol and rel_err(0.5 * dtaps.t().reshape(d, 1, k), f32(w.grad)) <= tol

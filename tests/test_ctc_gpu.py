@@ -193,3 +193,69 @@ def test_greedy_trigger_points_probs_scores():
     p, s = ctc.probs(eouts, temperature=2.0), ctc.scores(eouts)
     assert torch.allclose(p, torch.softmax(logits / 2.0, -1), atol=1e-5)
     assert torch.allclose(s, torch.log_softmax(logits, -1), atol=2e-4)
+
+
+# ---- the streaming kernel (csrc/ctc_stream.cuh): both tile modes, every lattice width, ragged / empty / infeasible
+# ---- utterances, more utterances than SMs (several lattices per CTA), against the pinned oracle (fp64 CPU restatement)
+STREAM_CASES = [
+    # B,   T,   V,     Lmax, lsm, note
+    (6,   33,  2000,  9,   0.1),     # ROW mode, 1 float4 slot per thread, K = 1
+    (4,   64,  12288, 20,  0.1),     # ROW mode at its widest (6 slots), K = 2
+    (3,   50,  1280,  40,  0.0),     # WARP mode at its widest (10 slots per lane), K = 4
+    (2,   200, 32,    30,  0.0),     # BASELINE configs[0] shape: WARP mode, tiny rows, many rows per tile
+    (200, 40,  320,   12,  0.1),     # more utterances than SMs: every CTA sweeps several lattices
+    (2,   300, 64,    120, 0.1),     # K = 8
+    (2,   460, 48,    200, 0.0),     # K = 16
+    (5,   70,  5000,  30,  0.1),     # ROW mode, V4 = 1250 -> 3 slots, ragged with padded tiles
+]
+
+
+@pytest.mark.parametrize("B,T,V,Lmax,lsm", STREAM_CASES)
+def test_ctc_stream_kernel_vs_oracle(B, T, V, Lmax, lsm):
+    from neural_sp_b200 import ops
+    from oracle import ctc_oracle
+    rng = np.random.default_rng(B * 7 + T * 3 + V)
+    torch.manual_seed(B + T + V)
+    logits = (torch.randn(B, T, V, device="cuda") * 2.0).contiguous()
+    elens = rng.integers(max(1, T // 3), T + 1, size=B).astype(np.int32)
+    elens[0] = T
+    ylens = np.minimum(rng.integers(1, Lmax + 1, size=B), np.maximum(elens // 2, 1)).astype(np.int32)
+    ylens[0] = min(Lmax, T // 2)
+    ys = [rng.integers(1, V, size=int(n)).tolist() for n in ylens]
+    if B >= 3:
+        ys[1] = [ys[1][0]] * len(ys[1])                     # all repeats: needs 2L-1 frames, same-label chains
+        if 2 * len(ys[1]) - 1 > elens[1]:
+            pass                                            # infeasible on purpose (zero_infinity path)
+        elens[2] = 0                                        # empty utterance
+    if B >= 5:
+        ys[4] = []                                          # empty label sequence
+    labels, ylens_d, _ = ops.pack_labels(ys, logits.device)
+    loss, nll, grad = ops.ctc_loss_fwd_bwd(logits, labels, torch.from_numpy(elens).cuda(), ylens_d, 0, lsm)
+    torch.cuda.synchronize()
+    o_loss, o_grad, o_nll = ctc_oracle.ctc_forward(logits.cpu().numpy(), ys, elens, lsm)
+    np.testing.assert_allclose(nll.cpu().numpy(), o_nll, rtol=2e-4, atol=2e-3)
+    assert abs(loss.item() - o_loss) <= 2e-4 * max(1.0, abs(o_loss)), (loss.item(), o_loss)
+    tol = 2e-4 if T < 200 else (4e-4 if T <= 250 else 1e-3)  # fp32 log-domain lattices carry ~sqrt(T) ulp(|log p|) of noise (so does ATen's)
+    np.testing.assert_allclose(grad.cpu().numpy(), o_grad, atol=tol, rtol=0)
+    for b in range(B):
+        assert torch.count_nonzero(grad[b, int(elens[b]):]).item() == 0
+
+
+def test_ctc_strided_logits_take_the_row_tiles():
+    """[T,B,V]-major logits viewed as [B,T,V] (the reference's loss_fn boundary, ctc.py:139-150): rows are not contiguous
+    tile to tile; V = 2000 runs the one-row-per-tile streaming mode with strided row addresses, V = 400 the register kernel."""
+    from neural_sp_b200 import ops
+    from oracle import ctc_oracle
+    rng = np.random.default_rng(3)
+    for V in (2000, 400):
+        B, T = 4, 37
+        torch.manual_seed(V)
+        tbv = torch.randn(T, B, V, device="cuda") * 1.5
+        logits = tbv.transpose(0, 1)
+        elens = np.array([37, 30, 21, 9], np.int32)
+        ys = [rng.integers(1, V, size=n).tolist() for n in (12, 9, 4, 3)]
+        labels, ylens_d, _ = ops.pack_labels(ys, logits.device)
+        loss, nll, grad = ops.ctc_loss_fwd_bwd(logits, labels, torch.from_numpy(elens).cuda(), ylens_d, 0, 0.1)
+        o_loss, o_grad, o_nll = ctc_oracle.ctc_forward(logits.cpu().numpy(), ys, elens, 0.1)
+        assert abs(loss.item() - o_loss) <= 2e-4 * abs(o_loss)
+        np.testing.assert_allclose(grad.cpu().numpy(), o_grad, atol=2e-4, rtol=0)
