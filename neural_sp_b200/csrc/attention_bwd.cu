@@ -110,6 +110,7 @@ __device__ __forceinline__ void tile_scores(const AttnBwdParams& p, const float*
 // ------------------------------------------------------------------------------------------------
 template <typename T, int DKP>
 __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(AttnBwdParams p) {
+    pdl_entry();
     constexpr int CPT = DKP / 16;
     extern __shared__ float sm[];
     float* QuT = sm;                              // [DKP][QP]
@@ -347,6 +348,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(AttnBwdParams p) {
 // ------------------------------------------------------------------------------------------------
 template <typename T, int DKP>
 __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(AttnBwdParams p) {
+    pdl_entry();
     constexpr int CPB = DKP / 8;                  // output columns per thread
     extern __shared__ float sm[];
     float* KsT = sm;                              // [DKP][KP]
@@ -489,9 +491,9 @@ nsp_status launch_bwd(const AttnBwdParams& p, cudaStream_t st) {
     static size_t attr_a = 0, attr_b = 0;
     if (smem_a > attr_a) { NSP_CUDA_OK(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a)); attr_a = smem_a; }
     if (smem_b > attr_b) { NSP_CUDA_OK(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b)); attr_b = smem_b; }
-    ka<<<(unsigned)(p.B * p.H * ceil_div(p.Tq, QT)), 128, smem_a, st>>>(p);
+    launch_k(ka, dim3((unsigned)(p.B * p.H * ceil_div(p.Tq, QT))), dim3(128), smem_a, st, p);
     NSP_LAUNCH_OK();
-    kb<<<(unsigned)(p.B * p.H * ceil_div(p.Tk, KT)), 128, smem_b, st>>>(p);
+    launch_k(kb, dim3((unsigned)(p.B * p.H * ceil_div(p.Tk, KT))), dim3(128), smem_b, st, p);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }

@@ -62,14 +62,8 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t smem_addr, uint32_t lbo_byt
     d |= (uint64_t)2 << 61;
     return d;
 }
-// Bounded mbarrier wait: a protocol error becomes a trap with a message instead of a hung GPU.
-__device__ __forceinline__ void bwait(uint64_t* bar, uint32_t parity, int code) {
-    const long long t0 = clock64();
-    while (clock64() - t0 < 2000000000ll)                 // ~1 s
-        if (tc::mbar_try_wait(bar, parity)) return;
-    printf("attn_bwd_tc: mbarrier wait %d timed out (block %d thread %d parity %u)\n", code, (int)blockIdx.x, (int)threadIdx.x, parity);
-    __trap();
-}
+// Bounded mbarrier wait (tc_common.cuh: bare spin + one counter, the clock is read once per 4096 failed polls).
+__device__ __forceinline__ void bwait(uint64_t* bar, uint32_t parity, int) { tc::mbar_wait(bar, parity); }
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -81,6 +75,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_bwd_tc_kernel(const __grid_c
                                                                   const __grid_constant__ CUtensorMap tmap_do,
                                                                   const __grid_constant__ CUtensorMap tmap_r,
                                                                   const BwdTcArgs a) {
+    pdl_launch_dependents();      // PDL: the next kernel may start its prologue; ours overlaps the previous kernel's tail
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sK = smem;                               // 16 KiB
@@ -130,6 +125,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_bwd_tc_kernel(const __grid_c
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    pdl_wait();                    // the previous grid is complete: operands / residuals / outputs may be touched from here
     const uint32_t tm_ST = tmem_base, tm_DP = tmem_base + 128, tm_DV = tmem_base + 256, tm_DK = tmem_base + 320;
     const uint32_t tm_DQ = tmem_base + 384, tm_BD = tmem_base + 448;
 
@@ -343,6 +339,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_bwd_tc_kernel(const __grid_c
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, int64_t ldo,
                                                             const __nv_bfloat16* __restrict__ dout, int64_t lddo,
                                                             float* __restrict__ dsum, int B, int H, int T) {
+    pdl_entry();
     const int64_t n = (int64_t)B * T * H;
     for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < n; e += (int64_t)gridDim.x * 256) {
         const int h = (int)(e % H);
@@ -373,6 +370,7 @@ __global__ void __launch_bounds__(256) attn_bwd_finish_kernel(const float* __res
                                                               __nv_bfloat16* __restrict__ dq, int64_t lddq,
                                                               float* __restrict__ dr_part,
                                                               int B, int H, int T, int has_rel, int clamp) {
+    pdl_entry();
     __shared__ float sdr[16][DK];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // grid.x = (b, h, row block of 64): all rows of a CTA share the head so that dR reduces in shared memory first
@@ -439,6 +437,7 @@ __global__ void __launch_bounds__(256) attn_bwd_finish_kernel(const float* __res
 // thread = (column c, one of 4 interleaved partial streams); every address receives `slices` atomic adds.
 __global__ void __launch_bounds__(256) attn_bwd_dr_reduce_kernel(const float* __restrict__ dr_part, float* __restrict__ dr,
                                                                  int64_t lddr, int B, int H, int rblocks) {
+    pdl_entry();
     __shared__ float part[4][DK];
     const int h = blockIdx.x % H, d = blockIdx.x / H, c = threadIdx.x & 63, stream = threadIdx.x >> 6;
     const int np = B * rblocks;                                   // partials of this head: index p = b * rblocks + rb
@@ -523,7 +522,7 @@ nsp_status attention_bwd_tc_dispatch(const void* q, int64_t ldq, const void* k, 
     {
         const int64_t n = (int64_t)B * T * H;
         int grid = (int)((n + 255) / 256);
-        attn_bwd_prep_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)out, ldo, (const __nv_bfloat16*)dout, lddo, dsum, B, H, T);
+        launch_k(attn_bwd_prep_kernel, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)out, ldo, (const __nv_bfloat16*)dout, lddo, dsum, B, H, T);
         NSP_LAUNCH_OK();
     }
     BwdTcArgs a;
@@ -538,11 +537,11 @@ nsp_status attention_bwd_tc_dispatch(const void* q, int64_t ldq, const void* k, 
     static bool attr = false;
     if (!attr) { NSP_CUDA_OK(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     const int ktiles = ceil_div(T, KT);
-    attn_bwd_tc_kernel<<<(unsigned)(B * H * ktiles), NTHREADS, smem, st>>>(mq, mk, mv, mdo, mr, a);
+    launch_k(attn_bwd_tc_kernel, dim3((unsigned)(B * H * ktiles)), dim3(NTHREADS), smem, st, mq, mk, mv, mdo, mr, a);
     NSP_LAUNCH_OK();
     float* dr_part = dsum + (size_t)B * H * T;
     const int rblocks = ceil_div(T, 64);
-    attn_bwd_finish_kernel<<<(unsigned)(B * H * rblocks), 256, 0, st>>>(dq_acc, w, (const __nv_bfloat16*)q, ldq,
+    launch_k(attn_bwd_finish_kernel, dim3((unsigned)(B * H * rblocks)), dim3(256), 0, st, dq_acc, w, (const __nv_bfloat16*)q, ldq,
                                                                       (const __nv_bfloat16*)r, ldr,
                                                                       (__nv_bfloat16*)dq, lddq, (a.has_rel && dr) ? dr_part : nullptr,
                                                                       B, H, T, a.has_rel, a.clamp);
@@ -550,7 +549,7 @@ nsp_status attention_bwd_tc_dispatch(const void* q, int64_t ldq, const void* k, 
     if (a.has_rel && dr) {
         const int np = B * rblocks;
         dim3 rgrid((unsigned)(H * (a.clamp + 1)), (unsigned)(np >= 64 ? 8 : 1));
-        attn_bwd_dr_reduce_kernel<<<rgrid, 256, 0, st>>>(dr_part, dr, lddr, B, H, rblocks);
+        launch_k(attn_bwd_dr_reduce_kernel, dim3(rgrid), dim3(256), 0, st, dr_part, dr, lddr, B, H, rblocks);
         NSP_LAUNCH_OK();
     }
     return NSP_OK;

@@ -48,6 +48,7 @@ template <> __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p,
 
 template <typename T, int DKP>
 __global__ void __launch_bounds__(128) attn_simt_kernel(AttnParams p) {
+    pdl_entry();
     constexpr int CPT = DKP / 16;   // output columns per thread
     extern __shared__ float sm[];
     float* QuT = sm;                          // [DKP][QP]
@@ -248,7 +249,7 @@ nsp_status launch_attn(const AttnParams& p, cudaStream_t st) {
     static bool attr = false;
     if (!attr) { NSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     const int qtiles = ceil_div(p.Tq, QT);
-    kern<<<(unsigned)(p.B * p.H * qtiles), 128, smem, st>>>(p);
+    launch_k(kern, dim3((unsigned)(p.B * p.H * qtiles)), dim3(128), smem, st, p);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }

@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
                                                               const __grid_constant__ CUtensorMap tmap_v,
                                                               const __grid_constant__ CUtensorMap tmap_r,
                                                               const AttnTcArgs a) {
+    pdl_launch_dependents();      // PDL: the next kernel may start its prologue; ours overlaps the previous kernel's tail
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sQ = smem;                               // 16 KiB
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    pdl_wait();                    // the previous grid is complete: operands / residuals / outputs may be touched from here
     const uint32_t tm_S = tmem_base, tm_O = tmem_base + 128, tm_BD = tmem_base + 192;
 
     if (warp == 0) {
@@ -397,7 +399,7 @@ nsp_status attention_tc_dispatch(const void* q, int64_t ldq, const void* k, int6
     static bool attr = false;
     if (!attr) { NSP_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     const int qtiles = ceil_div(Tq, QT);
-    attn_tc_kernel<<<(unsigned)(B * H * qtiles), NTHREADS, smem, st>>>(mq, mk, mv, mr, a);
+    launch_k(attn_tc_kernel, dim3((unsigned)(B * H * qtiles)), dim3(NTHREADS), smem, st, mq, mk, mv, mr, a);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }

@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                             float* __restrict__ dcol, float dcol_alpha,
                                                             int M, int D) {
+    pdl_entry();
     extern __shared__ float red[];     // [8][D]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float gsum[VPT][4], bsum[VPT][4], gm[VPT][4], csum[VPT][4];
@@ -162,6 +163,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_generic_kernel(const float*
                                                                     __nv_bfloat16* __restrict__ dxb, int64_t lddxb,
                                                                     float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                     float* __restrict__ dcol, float dcol_alpha, int M, int D) {
+    pdl_entry();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < M; row += (int64_t)gridDim.x * 8) {
         const float* xr = x + row * ldx;
@@ -216,6 +218,7 @@ __device__ __forceinline__ float dact(int act, float z) {
 template <typename T>
 __global__ void __launch_bounds__(256) act_bwd_kernel(const T* __restrict__ dh, const T* __restrict__ z, T* __restrict__ dz,
                                                       int64_t n, int act) {
+    pdl_entry();
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
         bw_st<T>(dz + i, bw_ld<T>(dh + i) * dact(act, bw_ld<T>(z + i)));
 }
@@ -237,6 +240,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 
 __global__ void __launch_bounds__(256) act_bwd_vec_kernel(const uint4* __restrict__ dh, const uint4* __restrict__ z,
                                                           uint4* __restrict__ dz, int64_t n8, int act) {
+    pdl_entry();
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n8; i += (int64_t)gridDim.x * 256) {
         float a[8], b[8];
         unpack8(dh[i], a); unpack8(z[i], b);
@@ -249,6 +253,7 @@ __global__ void __launch_bounds__(256) act_bwd_vec_kernel(const uint4* __restric
 // GLU backward, bf16, one thread = 8 consecutive channels of one row (d % 8 == 0)
 __global__ void __launch_bounds__(256) glu_bwd_vec_kernel(const uint4* __restrict__ dg, const uint4* __restrict__ pre,
                                                           uint4* __restrict__ dpre, int64_t M, int d8) {
+    pdl_entry();
     const int64_t n = M * d8;
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
         const int64_t r = i / d8;
@@ -273,6 +278,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256) act_bwd_bias_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ z,
                                                            __nv_bfloat16* __restrict__ dz, float* __restrict__ dbias,
                                                            int M, int N, int act) {
+    pdl_entry();
     __shared__ float part[8][257];
     const int lane = threadIdx.x & 31, rs = threadIdx.x >> 5;
     const int c0 = (blockIdx.x * 32 + lane) * 8;
@@ -322,6 +328,7 @@ __global__ void __launch_bounds__(256) act_bwd_bias_kernel(const __nv_bfloat16* 
 
 __global__ void __launch_bounds__(256) relu_mask_vec_kernel(const uint4* __restrict__ dx, const uint4* __restrict__ a,
                                                             uint4* __restrict__ dz, int64_t n8) {
+    pdl_entry();
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n8; i += (int64_t)gridDim.x * 256) {
         float x[8], y[8];
         unpack8(dx[i], x); unpack8(a[i], y);
@@ -335,6 +342,7 @@ __global__ void __launch_bounds__(256) relu_mask_vec_kernel(const uint4* __restr
 template <typename T>
 __global__ void __launch_bounds__(256) glu_bwd_kernel(const T* __restrict__ dg, const T* __restrict__ pre, T* __restrict__ dpre,
                                                       int64_t M, int d) {
+    pdl_entry();
     const int64_t n = M * d;
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
         const int64_t r = i / d;
@@ -352,6 +360,7 @@ __global__ void __launch_bounds__(256) glu_bwd_kernel(const T* __restrict__ dg, 
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) colsum_acc_vec_kernel(const T* __restrict__ x, int64_t ldx, float* __restrict__ y,
                                                              int M, int N, float alpha) {
+    pdl_entry();
     __shared__ float part[8][32 * VEC + 1];
     const int lane = threadIdx.x & 31, rs = threadIdx.x >> 5;
     const int c0 = (blockIdx.x * 32 + lane) * VEC;
@@ -389,6 +398,7 @@ __global__ void __launch_bounds__(256) colsum_acc_vec_kernel(const T* __restrict
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_acc_kernel(const T* __restrict__ x, int64_t ldx, float* __restrict__ y,
                                                          int M, int N, float alpha) {
+    pdl_entry();
     __shared__ float part[8][33];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31), rs = threadIdx.x >> 5;
     float acc = 0.f;
@@ -408,6 +418,7 @@ __global__ void __launch_bounds__(256) colsum_acc_kernel(const T* __restrict__ x
 // frame of its window holding the maximum (torch's max_pool1d tie rule), zeros elsewhere.  x, dx fp32 [B,T,D].
 __global__ void __launch_bounds__(256) maxpool_time_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                float* __restrict__ dx, int B, int T, int D, int factor) {
+    pdl_entry();
     const int To = (T + factor - 1) / factor;
     const int64_t n = (int64_t)B * To * D;
     for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < n; e += (int64_t)gridDim.x * 256) {
@@ -432,6 +443,7 @@ __global__ void __launch_bounds__(256) maxpool_time_bwd_kernel(const float* __re
 // input), 2 drop: dy to the window's first frame only, 3 add: dy to every frame.  dy fp32 [B,ceil(T/f),D], dx fp32 [B,T,D].
 __global__ void __launch_bounds__(256) pool_time_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int B, int T,
                                                             int D, int factor, int mode) {
+    pdl_entry();
     const int To = (T + factor - 1) / factor;
     const int64_t n = (int64_t)B * T * D;
     for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < n; e += (int64_t)gridDim.x * 256) {
@@ -449,6 +461,7 @@ __global__ void __launch_bounds__(256) pool_time_bwd_kernel(const float* __restr
 // dz = (a > 0) ? dx : 0   (ReLU backward through the saved post-activation a)
 template <typename T>
 __global__ void __launch_bounds__(256) relu_mask_kernel(const T* __restrict__ dx, const T* __restrict__ a, T* __restrict__ dz, int64_t n) {
+    pdl_entry();
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
         bw_st<T>(dz + i, bw_ld<T>(a + i) > 0.f ? bw_ld<T>(dx + i) : 0.f);
 }
@@ -459,6 +472,7 @@ __global__ void __launch_bounds__(256) relu_mask_kernel(const T* __restrict__ dx
 template <typename T, typename TG>
 __global__ void __launch_bounds__(256) maxpool2d_relu_bwd_kernel(const T* __restrict__ a, const TG* __restrict__ dy, T* __restrict__ dz,
                                                                  int B, int Tn, int F, int C, int pt, int pf, int in_chmajor) {
+    pdl_entry();
     const int To = (Tn + pt - 1) / pt, Fo = (F + pf - 1) / pf;
     const int64_t n = (int64_t)B * To * Fo * C;
     for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < n; e += (int64_t)gridDim.x * 256) {
@@ -486,6 +500,7 @@ __global__ void __launch_bounds__(256) maxpool2d_relu_bwd_kernel(const T* __rest
 __global__ void __launch_bounds__(256) maxpool2d_relu_bwd_vec_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ dy,
                                                                      __nv_bfloat16* __restrict__ dz, int B, int Tn, int F, int C,
                                                                      int pt, int pf) {
+    pdl_entry();
     const int To = (Tn + pt - 1) / pt, Fo = (F + pf - 1) / pf, C8 = C / 8;
     const int64_t n = (int64_t)B * To * Fo * C8;
     for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < n; e += (int64_t)gridDim.x * 256) {
@@ -544,7 +559,7 @@ extern "C" nsp_status nsp_layernorm_bwd(const float* dy, int64_t lddy, const flo
         ((uintptr_t)dy % 16 == 0) && ((uintptr_t)x % 16 == 0) && (!dres || (uintptr_t)dres % 16 == 0) &&
         (!dx || (uintptr_t)dx % 16 == 0) && (!dx_bf16 || (uintptr_t)dx_bf16 % 8 == 0);
     if (!vec_ok) {                 // odd widths / pitches: the scalar kernel
-        layernorm_bwd_generic_kernel<<<grid, 256, 0, st>>>(dy, lddy, x, ldx, gamma, eps, in_scale, dres, lddr, dx, lddx,
+        launch_k(layernorm_bwd_generic_kernel, dim3(grid), dim3(256), 0, st, dy, lddy, x, ldx, gamma, eps, in_scale, dres, lddr, dx, lddx,
                                                            (__nv_bfloat16*)dx_bf16, lddxb, dgamma, dbeta, dcol, dcol_alpha, M, D);
         NSP_LAUNCH_OK();
         return NSP_OK;
@@ -556,7 +571,7 @@ extern "C" nsp_status nsp_layernorm_bwd(const float* dy, int64_t lddy, const flo
         auto kern = layernorm_bwd_kernel<VPT>;                                                                           \
         static size_t attr = 0;                                                                                          \
         if (smem > attr) { NSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; } \
-        kern<<<grid, 256, smem, st>>>(dy, lddy, x, ldx, gamma, eps, in_scale, dres, lddr, dx, lddx, dxb, lddxb, dgamma, dbeta, dcol, dcol_alpha, M, D); \
+        launch_k(kern, dim3(grid), dim3(256), smem, st, dy, lddy, x, ldx, gamma, eps, in_scale, dres, lddr, dx, lddx, dxb, lddxb, dgamma, dbeta, dcol, dcol_alpha, M, D); \
     } while (0)
     const int vpt = ceil_div(D / 4, 32);
     if (vpt <= 1) NSP_LNB(1); else if (vpt <= 2) NSP_LNB(2); else if (vpt <= 4) NSP_LNB(4);
@@ -572,9 +587,9 @@ extern "C" nsp_status nsp_act_bwd(int is_bf16, int act, const void* dh, const vo
     cudaStream_t st = (cudaStream_t)stream;
     const bool al16 = (((uintptr_t)dh | (uintptr_t)z | (uintptr_t)dz) & 15) == 0;
     if (is_bf16 && al16 && n % 8 == 0)
-        act_bwd_vec_kernel<<<bw_grid(n / 8), 256, 0, st>>>((const uint4*)dh, (const uint4*)z, (uint4*)dz, n / 8, act);
-    else if (is_bf16) act_bwd_kernel<__nv_bfloat16><<<bw_grid(n), 256, 0, st>>>((const __nv_bfloat16*)dh, (const __nv_bfloat16*)z, (__nv_bfloat16*)dz, n, act);
-    else act_bwd_kernel<float><<<bw_grid(n), 256, 0, st>>>((const float*)dh, (const float*)z, (float*)dz, n, act);
+        launch_k(act_bwd_vec_kernel, dim3(bw_grid(n / 8)), dim3(256), 0, st, (const uint4*)dh, (const uint4*)z, (uint4*)dz, n / 8, act);
+    else if (is_bf16) launch_k(act_bwd_kernel<__nv_bfloat16>, dim3(bw_grid(n)), dim3(256), 0, st, (const __nv_bfloat16*)dh, (const __nv_bfloat16*)z, (__nv_bfloat16*)dz, n, act);
+    else launch_k(act_bwd_kernel<float>, dim3(bw_grid(n)), dim3(256), 0, st, (const float*)dh, (const float*)z, (float*)dz, n, act);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }
@@ -584,9 +599,9 @@ extern "C" nsp_status nsp_glu_bwd(int is_bf16, const void* dg, const void* pre, 
     cudaStream_t st = (cudaStream_t)stream;
     const bool al16 = (((uintptr_t)dg | (uintptr_t)pre | (uintptr_t)dpre) & 15) == 0;
     if (is_bf16 && al16 && d % 8 == 0)
-        glu_bwd_vec_kernel<<<bw_grid(M * (d / 8)), 256, 0, st>>>((const uint4*)dg, (const uint4*)pre, (uint4*)dpre, M, d / 8);
-    else if (is_bf16) glu_bwd_kernel<__nv_bfloat16><<<bw_grid(M * d), 256, 0, st>>>((const __nv_bfloat16*)dg, (const __nv_bfloat16*)pre, (__nv_bfloat16*)dpre, M, d);
-    else glu_bwd_kernel<float><<<bw_grid(M * d), 256, 0, st>>>((const float*)dg, (const float*)pre, (float*)dpre, M, d);
+        launch_k(glu_bwd_vec_kernel, dim3(bw_grid(M * (d / 8))), dim3(256), 0, st, (const uint4*)dg, (const uint4*)pre, (uint4*)dpre, M, d / 8);
+    else if (is_bf16) launch_k(glu_bwd_kernel<__nv_bfloat16>, dim3(bw_grid(M * d)), dim3(256), 0, st, (const __nv_bfloat16*)dg, (const __nv_bfloat16*)pre, (__nv_bfloat16*)dpre, M, d);
+    else launch_k(glu_bwd_kernel<float>, dim3(bw_grid(M * d)), dim3(256), 0, st, (const float*)dg, (const float*)pre, (float*)dpre, M, d);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }
@@ -601,8 +616,8 @@ extern "C" nsp_status nsp_colsum_acc(int is_bf16, const void* x, int64_t ldx, in
         const int cap = ceil_div(num_sms() * 4, cblocks);
         if (slices > cap) slices = cap < 1 ? 1 : cap;
         dim3 vgrid((unsigned)cblocks, (unsigned)slices);
-        if (is_bf16) colsum_acc_vec_kernel<__nv_bfloat16, 8><<<vgrid, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, y, M, N, alpha);
-        else colsum_acc_vec_kernel<float, 4><<<vgrid, 256, 0, st>>>((const float*)x, ldx, y, M, N, alpha);
+        if (is_bf16) launch_k(colsum_acc_vec_kernel<__nv_bfloat16, 8>, dim3(vgrid), dim3(256), 0, st, (const __nv_bfloat16*)x, ldx, y, M, N, alpha);
+        else launch_k(colsum_acc_vec_kernel<float, 4>, dim3(vgrid), dim3(256), 0, st, (const float*)x, ldx, y, M, N, alpha);
         NSP_LAUNCH_OK();
         return NSP_OK;
     }
@@ -610,8 +625,8 @@ extern "C" nsp_status nsp_colsum_acc(int is_bf16, const void* x, int64_t ldx, in
     const int cap = ceil_div(num_sms() * 8, ceil_div(N, 32));
     if (slices > cap) slices = cap < 1 ? 1 : cap;
     dim3 grid((unsigned)ceil_div(N, 32), (unsigned)slices);
-    if (is_bf16) colsum_acc_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, y, M, N, alpha);
-    else colsum_acc_kernel<float><<<grid, 256, 0, st>>>((const float*)x, ldx, y, M, N, alpha);
+    if (is_bf16) launch_k(colsum_acc_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)x, ldx, y, M, N, alpha);
+    else launch_k(colsum_acc_kernel<float>, dim3(grid), dim3(256), 0, st, (const float*)x, ldx, y, M, N, alpha);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }
@@ -619,14 +634,14 @@ extern "C" nsp_status nsp_colsum_acc(int is_bf16, const void* x, int64_t ldx, in
 extern "C" nsp_status nsp_maxpool_time_bwd(const float* x, const float* dy, float* dx, int B, int T, int D, int factor, void* stream) {
     NSP_CHECK_ARG(x && dy && dx && B > 0 && T > 0 && D > 0 && factor >= 1, "maxpool_time_bwd: bad arguments");
     const int To = (T + factor - 1) / factor;
-    maxpool_time_bwd_kernel<<<bw_grid((int64_t)B * To * D), 256, 0, (cudaStream_t)stream>>>(x, dy, dx, B, T, D, factor);
+    launch_k(maxpool_time_bwd_kernel, dim3(bw_grid((int64_t)B * To * D)), dim3(256), 0, (cudaStream_t)stream, x, dy, dx, B, T, D, factor);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }
 
 extern "C" nsp_status nsp_pool_time_bwd(const float* dy, float* dx, int B, int T, int D, int factor, int mode, void* stream) {
     NSP_CHECK_ARG(dy && dx && B > 0 && T > 0 && D > 0 && factor >= 1 && mode >= 1 && mode <= 3, "pool_time_bwd: bad arguments");
-    pool_time_bwd_kernel<<<bw_grid((int64_t)B * T * D), 256, 0, (cudaStream_t)stream>>>(dy, dx, B, T, D, factor, mode);
+    launch_k(pool_time_bwd_kernel, dim3(bw_grid((int64_t)B * T * D)), dim3(256), 0, (cudaStream_t)stream, dy, dx, B, T, D, factor, mode);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }
@@ -637,9 +652,9 @@ extern "C" nsp_status nsp_relu_mask(int is_bf16, const void* dx, const void* a, 
     cudaStream_t st = (cudaStream_t)stream;
     const bool al16 = (((uintptr_t)dx | (uintptr_t)a | (uintptr_t)dz) & 15) == 0;
     if (is_bf16 && al16 && n % 8 == 0)
-        relu_mask_vec_kernel<<<bw_grid(n / 8), 256, 0, st>>>((const uint4*)dx, (const uint4*)a, (uint4*)dz, n / 8);
-    else if (is_bf16) relu_mask_kernel<__nv_bfloat16><<<bw_grid(n), 256, 0, st>>>((const __nv_bfloat16*)dx, (const __nv_bfloat16*)a, (__nv_bfloat16*)dz, n);
-    else relu_mask_kernel<float><<<bw_grid(n), 256, 0, st>>>((const float*)dx, (const float*)a, (float*)dz, n);
+        launch_k(relu_mask_vec_kernel, dim3(bw_grid(n / 8)), dim3(256), 0, st, (const uint4*)dx, (const uint4*)a, (uint4*)dz, n / 8);
+    else if (is_bf16) launch_k(relu_mask_kernel<__nv_bfloat16>, dim3(bw_grid(n)), dim3(256), 0, st, (const __nv_bfloat16*)dx, (const __nv_bfloat16*)a, (__nv_bfloat16*)dz, n);
+    else launch_k(relu_mask_kernel<float>, dim3(bw_grid(n)), dim3(256), 0, st, (const float*)dx, (const float*)a, (float*)dz, n);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }
@@ -650,13 +665,13 @@ extern "C" nsp_status nsp_maxpool2d_relu_bwd(int is_bf16, int dy_bf16, const voi
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n = (int64_t)B * ceil_div(T, pool_t) * ceil_div(F, pool_f) * C;
     if (is_bf16 && dy_bf16 && !in_chmajor && C % 8 == 0 && (((uintptr_t)a | (uintptr_t)dy | (uintptr_t)dz) & 15) == 0)
-        maxpool2d_relu_bwd_vec_kernel<<<bw_grid(n / 8), 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dz, B, T, F, C, pool_t, pool_f);
+        launch_k(maxpool2d_relu_bwd_vec_kernel, dim3(bw_grid(n / 8)), dim3(256), 0, st, (const __nv_bfloat16*)a, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dz, B, T, F, C, pool_t, pool_f);
     else if (is_bf16 && dy_bf16)
-        maxpool2d_relu_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<bw_grid(n), 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dz, B, T, F, C, pool_t, pool_f, in_chmajor);
+        launch_k(maxpool2d_relu_bwd_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(bw_grid(n)), dim3(256), 0, st, (const __nv_bfloat16*)a, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dz, B, T, F, C, pool_t, pool_f, in_chmajor);
     else if (is_bf16)
-        maxpool2d_relu_bwd_kernel<__nv_bfloat16, float><<<bw_grid(n), 256, 0, st>>>((const __nv_bfloat16*)a, (const float*)dy, (__nv_bfloat16*)dz, B, T, F, C, pool_t, pool_f, in_chmajor);
+        launch_k(maxpool2d_relu_bwd_kernel<__nv_bfloat16, float>, dim3(bw_grid(n)), dim3(256), 0, st, (const __nv_bfloat16*)a, (const float*)dy, (__nv_bfloat16*)dz, B, T, F, C, pool_t, pool_f, in_chmajor);
     else if (!dy_bf16)
-        maxpool2d_relu_bwd_kernel<float, float><<<bw_grid(n), 256, 0, st>>>((const float*)a, (const float*)dy, (float*)dz, B, T, F, C, pool_t, pool_f, in_chmajor);
+        launch_k(maxpool2d_relu_bwd_kernel<float, float>, dim3(bw_grid(n)), dim3(256), 0, st, (const float*)a, (const float*)dy, (float*)dz, B, T, F, C, pool_t, pool_f, in_chmajor);
     else { set_error("maxpool2d_relu_bwd: fp32 activations with bf16 gradients are not instantiated"); return NSP_ERR_UNSUPPORTED; }
     NSP_LAUNCH_OK();
     return NSP_OK;
@@ -675,8 +690,8 @@ extern "C" nsp_status nsp_act_bwd_bias(int mode, int act, const void* dh, const 
     const int cap = ceil_div(num_sms() * 4, cblocks);
     if (slices > cap) slices = cap < 1 ? 1 : cap;
     dim3 grid((unsigned)cblocks, (unsigned)slices);
-    if (mode == 0) act_bwd_bias_kernel<0><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dh, (const __nv_bfloat16*)z, (__nv_bfloat16*)dz, dbias, M, N, act);
-    else act_bwd_bias_kernel<1><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dh, (const __nv_bfloat16*)z, (__nv_bfloat16*)dz, dbias, M, N, act);
+    if (mode == 0) launch_k(act_bwd_bias_kernel<0>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)dh, (const __nv_bfloat16*)z, (__nv_bfloat16*)dz, dbias, M, N, act);
+    else launch_k(act_bwd_bias_kernel<1>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)dh, (const __nv_bfloat16*)z, (__nv_bfloat16*)dz, dbias, M, N, act);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }

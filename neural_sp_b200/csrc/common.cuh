@@ -38,8 +38,33 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int num_sms();   // cached device query (148 on B200)
+bool pdl_enabled();   // programmatic dependent launch for the kernels that opt in (NSP_PDL=0 turns it off)
+
+// ---- programmatic dependent launch (PDL) ----
+// A kernel launched through launch_k() carries cudaLaunchAttributeProgrammaticStreamSerialization: the next such kernel in
+// the stream may be scheduled while this one is still running, and its CTAs wait in pdl_entry() until this grid has
+// completed and flushed its memory.  What overlaps is the launch latency, the CTA rasterisation and the prologue
+// (barrier init, TMEM allocation, tensormap prefetch) of kernel N+1 with the tail of kernel N -- the 3-5 us per launch that
+// dominate the T' = 125 layers (profiles/README.md, round 2).  Contract for every kernel launched this way: pdl_entry()
+// (or pdl_wait()) before the FIRST global-memory access that touches data another kernel writes or reads.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // ---- device helpers ----
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Both at once, for kernels without a prologue worth overlapping: let the next kernel start its own prologue, then wait for
+// the previous grid.  (Both are no-ops when the kernel was launched without the attribute.)
+__device__ __forceinline__ void pdl_entry() { pdl_launch_dependents(); pdl_wait(); }
 #define NSP_NEG_BIG (-1.0e30f)   // finite stand-in for log(0): avoids inf-inf NaNs in log-sum-exp sweeps
 
 __device__ __forceinline__ float warp_max(float v) {

@@ -42,6 +42,7 @@ template <> __device__ __forceinline__ void cv_st<__nv_bfloat16>(__nv_bfloat16* 
 
 template <typename T, int CPLMAX, int K, int NW>   // K == 0: runtime kernel size
 __global__ void __launch_bounds__(32 * NW) conformer_conv_kernel(ConvParams p) {
+    pdl_entry();
     constexpr int NT = 32 * NW;
     constexpr int TT = NW * RT;    // frames per CTA
     extern __shared__ float sm[];
@@ -191,7 +192,7 @@ nsp_status launch_conv(const ConvParams& p, cudaStream_t st) {
                 NSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
                 attr_smem = smem;                                                                             \
             }                                                                                                 \
-            kern<<<grid, 512, smem, st>>>(p);                                                                 \
+            launch_k(kern, dim3(grid), dim3(512), smem, st, p);                                                                 \
         } else {                                                                                              \
             auto kern = conformer_conv_kernel<T, CPLMAX, KK, 8>;                                              \
             static size_t attr_smem = 0;                                                                      \
@@ -199,7 +200,7 @@ nsp_status launch_conv(const ConvParams& p, cudaStream_t st) {
                 NSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
                 attr_smem = smem;                                                                             \
             }                                                                                                 \
-            kern<<<grid, 256, smem, st>>>(p);                                                                 \
+            launch_k(kern, dim3(grid), dim3(256), smem, st, p);                                                                 \
         }                                                                                                     \
     } while (0)
     if (p.k == 15) NSP_CONV(15); else if (p.k == 31) NSP_CONV(31); else if (p.k == 7) NSP_CONV(7); else NSP_CONV(0);

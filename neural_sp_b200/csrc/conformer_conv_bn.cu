@@ -34,6 +34,7 @@ template <typename T>
 __global__ void __launch_bounds__(CH) dwconv_stats_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ w,
                                                           const float* __restrict__ bias, T* __restrict__ z, int64_t ldz,
                                                           float* __restrict__ stats, int B, int Tn, int d, int k, int left_pad) {
+    pdl_entry();
     const int cchunks = (d + CH - 1) / CH;
     const int ttiles = (Tn + TT - 1) / TT;
     const int cc = blockIdx.x % cchunks;
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(CH) bn_swish_bwd_reduce_kernel(const T* __rest
                                                                  const float* __restrict__ var, const float* __restrict__ g,
                                                                  const float* __restrict__ bta, float eps, float* __restrict__ sums,
                                                                  int64_t M, int d) {
+    pdl_entry();
     const int cchunks = (d + CH - 1) / CH;
     const int cc = blockIdx.x % cchunks;
     const int64_t r0 = (int64_t)(blockIdx.x / cchunks) * 64;
@@ -99,6 +101,7 @@ __global__ void __launch_bounds__(256) bn_swish_bwd_apply_kernel(const T* __rest
                                                                  const float* __restrict__ bta, float eps,
                                                                  const float* __restrict__ sums, T* __restrict__ dz, int64_t lddz,
                                                                  int64_t M, int d) {
+    pdl_entry();
     const int64_t n = M * d;
     const float invM = 1.f / (float)M;
     for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < n; e += (int64_t)gridDim.x * 256) {
@@ -119,6 +122,7 @@ __global__ void __launch_bounds__(CH) gn2_swish_bwd_kernel(const T* __restrict__
                                                            int64_t lddy, const float* __restrict__ g, const float* __restrict__ bta,
                                                            float eps, T* __restrict__ dz, int64_t lddz, float* __restrict__ dgam,
                                                            float* __restrict__ dbet, int64_t M, int d) {
+    pdl_entry();
     const int pairs = d / 2;
     const int pchunks = (pairs + CH - 1) / CH;
     const int pc = blockIdx.x % pchunks;
@@ -158,8 +162,8 @@ extern "C" nsp_status nsp_gn2_swish_bwd(int is_bf16, const void* z, int64_t ldz,
     NSP_CHECK_ARG(z && dy && gamma && beta && dz && dgamma && dbeta && M > 0 && d > 0 && d % 2 == 0, "gn2_swish_bwd: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned grid = (unsigned)(ceil_div64(M, 64) * ceil_div(d / 2, CH));
-    if (is_bf16) gn2_swish_bwd_kernel<__nv_bfloat16><<<grid, CH, 0, st>>>((const __nv_bfloat16*)z, ldz, (const __nv_bfloat16*)dy, lddy, gamma, beta, eps, (__nv_bfloat16*)dz, lddz, dgamma, dbeta, M, d);
-    else gn2_swish_bwd_kernel<float><<<grid, CH, 0, st>>>((const float*)z, ldz, (const float*)dy, lddy, gamma, beta, eps, (float*)dz, lddz, dgamma, dbeta, M, d);
+    if (is_bf16) launch_k(gn2_swish_bwd_kernel<__nv_bfloat16>, dim3(grid), dim3(CH), 0, st, (const __nv_bfloat16*)z, ldz, (const __nv_bfloat16*)dy, lddy, gamma, beta, eps, (__nv_bfloat16*)dz, lddz, dgamma, dbeta, M, d);
+    else launch_k(gn2_swish_bwd_kernel<float>, dim3(grid), dim3(CH), 0, st, (const float*)z, ldz, (const float*)dy, lddy, gamma, beta, eps, (float*)dz, lddz, dgamma, dbeta, M, d);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }
@@ -172,8 +176,8 @@ extern "C" nsp_status nsp_dwconv_stats_fwd(int is_bf16, const void* x, int64_t l
     NSP_CUDA_OK(cudaMemsetAsync(stats, 0, 2 * (size_t)d * sizeof(float), st));
     const unsigned grid = (unsigned)((int64_t)B * ceil_div(T, TT) * ceil_div(d, CH));
     const int left_pad = causal ? (k - 1) : (k - 1) / 2;
-    if (is_bf16) dwconv_stats_kernel<__nv_bfloat16><<<grid, CH, 0, st>>>((const __nv_bfloat16*)x, ldx, w, bias, (__nv_bfloat16*)z, ldz, stats, B, T, d, k, left_pad);
-    else dwconv_stats_kernel<float><<<grid, CH, 0, st>>>((const float*)x, ldx, w, bias, (float*)z, ldz, stats, B, T, d, k, left_pad);
+    if (is_bf16) launch_k(dwconv_stats_kernel<__nv_bfloat16>, dim3(grid), dim3(CH), 0, st, (const __nv_bfloat16*)x, ldx, w, bias, (__nv_bfloat16*)z, ldz, stats, B, T, d, k, left_pad);
+    else launch_k(dwconv_stats_kernel<float>, dim3(grid), dim3(CH), 0, st, (const float*)x, ldx, w, bias, (float*)z, ldz, stats, B, T, d, k, left_pad);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }
@@ -188,11 +192,11 @@ extern "C" nsp_status nsp_bn_swish_bwd(int is_bf16, const void* z, int64_t ldz, 
     int64_t b2 = ceil_div64(M * d, 256), cap = (int64_t)num_sms() * 16;
     const unsigned g2 = (unsigned)(b2 < cap ? b2 : cap);
     if (is_bf16) {
-        bn_swish_bwd_reduce_kernel<__nv_bfloat16><<<g1, CH, 0, st>>>((const __nv_bfloat16*)z, ldz, (const __nv_bfloat16*)dy, lddy, mean, var, gamma, beta, eps, sums, M, d);
-        bn_swish_bwd_apply_kernel<__nv_bfloat16><<<g2, 256, 0, st>>>((const __nv_bfloat16*)z, ldz, (const __nv_bfloat16*)dy, lddy, mean, var, gamma, beta, eps, sums, (__nv_bfloat16*)dz, lddz, M, d);
+        launch_k(bn_swish_bwd_reduce_kernel<__nv_bfloat16>, dim3(g1), dim3(CH), 0, st, (const __nv_bfloat16*)z, ldz, (const __nv_bfloat16*)dy, lddy, mean, var, gamma, beta, eps, sums, M, d);
+        launch_k(bn_swish_bwd_apply_kernel<__nv_bfloat16>, dim3(g2), dim3(256), 0, st, (const __nv_bfloat16*)z, ldz, (const __nv_bfloat16*)dy, lddy, mean, var, gamma, beta, eps, sums, (__nv_bfloat16*)dz, lddz, M, d);
     } else {
-        bn_swish_bwd_reduce_kernel<float><<<g1, CH, 0, st>>>((const float*)z, ldz, (const float*)dy, lddy, mean, var, gamma, beta, eps, sums, M, d);
-        bn_swish_bwd_apply_kernel<float><<<g2, 256, 0, st>>>((const float*)z, ldz, (const float*)dy, lddy, mean, var, gamma, beta, eps, sums, (float*)dz, lddz, M, d);
+        launch_k(bn_swish_bwd_reduce_kernel<float>, dim3(g1), dim3(CH), 0, st, (const float*)z, ldz, (const float*)dy, lddy, mean, var, gamma, beta, eps, sums, M, d);
+        launch_k(bn_swish_bwd_apply_kernel<float>, dim3(g2), dim3(256), 0, st, (const float*)z, ldz, (const float*)dy, lddy, mean, var, gamma, beta, eps, sums, (float*)dz, lddz, M, d);
     }
     NSP_LAUNCH_OK();
     return NSP_OK;
@@ -211,11 +215,11 @@ extern "C" nsp_status nsp_bn_bwd(int is_bf16, const void* z, int64_t ldz, const 
     int64_t b2 = ceil_div64(M * d, 256), cap = (int64_t)num_sms() * 16;
     const unsigned g2 = (unsigned)(b2 < cap ? b2 : cap);
     if (is_bf16) {
-        bn_swish_bwd_reduce_kernel<__nv_bfloat16, false><<<g1, CH, 0, st>>>((const __nv_bfloat16*)z, ldz, (const __nv_bfloat16*)du, lddu, mean, var, gamma, nullptr, eps, sums, M, d);
-        bn_swish_bwd_apply_kernel<__nv_bfloat16, false><<<g2, 256, 0, st>>>((const __nv_bfloat16*)z, ldz, (const __nv_bfloat16*)du, lddu, mean, var, gamma, nullptr, eps, sums, (__nv_bfloat16*)dz, lddz, M, d);
+        launch_k(bn_swish_bwd_reduce_kernel<__nv_bfloat16, false>, dim3(g1), dim3(CH), 0, st, (const __nv_bfloat16*)z, ldz, (const __nv_bfloat16*)du, lddu, mean, var, gamma, nullptr, eps, sums, M, d);
+        launch_k(bn_swish_bwd_apply_kernel<__nv_bfloat16, false>, dim3(g2), dim3(256), 0, st, (const __nv_bfloat16*)z, ldz, (const __nv_bfloat16*)du, lddu, mean, var, gamma, nullptr, eps, sums, (__nv_bfloat16*)dz, lddz, M, d);
     } else {
-        bn_swish_bwd_reduce_kernel<float, false><<<g1, CH, 0, st>>>((const float*)z, ldz, (const float*)du, lddu, mean, var, gamma, nullptr, eps, sums, M, d);
-        bn_swish_bwd_apply_kernel<float, false><<<g2, 256, 0, st>>>((const float*)z, ldz, (const float*)du, lddu, mean, var, gamma, nullptr, eps, sums, (float*)dz, lddz, M, d);
+        launch_k(bn_swish_bwd_reduce_kernel<float, false>, dim3(g1), dim3(CH), 0, st, (const float*)z, ldz, (const float*)du, lddu, mean, var, gamma, nullptr, eps, sums, M, d);
+        launch_k(bn_swish_bwd_apply_kernel<float, false>, dim3(g2), dim3(256), 0, st, (const float*)z, ldz, (const float*)du, lddu, mean, var, gamma, nullptr, eps, sums, (float*)dz, lddz, M, d);
     }
     NSP_LAUNCH_OK();
     return NSP_OK;

@@ -40,6 +40,7 @@ struct ConvBwdParams {
 // ---- K1 ----
 template <typename T, int CPLMAX, int NW>
 __global__ void __launch_bounds__(32 * NW) conv_bwd_norm_kernel(ConvBwdParams p) {
+    pdl_entry();
     constexpr int NT = 32 * NW;
     constexpr int TT = NW * RT;
     extern __shared__ float sm[];
@@ -186,6 +187,7 @@ constexpr int K2_CH = 128;            // channels per CTA
 
 template <typename T>
 __global__ void __launch_bounds__(32 * K2_NW) conv_bwd_dw_kernel(ConvBwdParams p) {
+    pdl_entry();
     extern __shared__ float sm[];
     const int d = p.d, k = p.k;
     const int rows = K2_TT + k - 1;
@@ -297,12 +299,12 @@ nsp_status launch_conv_bwd(const ConvBwdParams& p, cudaStream_t st) {
         auto kern = conv_bwd_norm_kernel<T, CPLMAX, 16>;
         static size_t attr = 0;
         if (smem > attr) { NSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
-        kern<<<grid, 512, smem, st>>>(p);
+        launch_k(kern, dim3(grid), dim3(512), smem, st, p);
     } else {
         auto kern = conv_bwd_norm_kernel<T, CPLMAX, 8>;
         static size_t attr = 0;
         if (smem > attr) { NSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
-        kern<<<grid, 256, smem, st>>>(p);
+        launch_k(kern, dim3(grid), dim3(256), smem, st, p);
     }
     NSP_LAUNCH_OK();
     const size_t smem2 = sizeof(float) * ((size_t)2 * (K2_TT + p.k - 1) * K2_CH + (size_t)2 * p.k * K2_CH + K2_CH);
@@ -311,7 +313,7 @@ nsp_status launch_conv_bwd(const ConvBwdParams& p, cudaStream_t st) {
     static size_t attr2 = 0;
     if (smem2 > attr2) { NSP_CUDA_OK(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); attr2 = smem2; }
     const unsigned grid2 = (unsigned)(p.B * ceil_div(p.T, K2_TT) * ceil_div(p.d, K2_CH));
-    k2<<<grid2, 32 * K2_NW, smem2, st>>>(p);
+    launch_k(k2, dim3(grid2), dim3(32 * K2_NW), smem2, st, p);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }
@@ -374,11 +376,11 @@ extern "C" nsp_status nsp_dwconv_bwd(int is_bf16, const void* x, int64_t ldx, co
     if (is_bf16) {
         auto k2 = conv_bwd_dw_kernel<__nv_bfloat16>;
         NSP_CUDA_OK(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        k2<<<grid2, 32 * K2_NW, smem2, st>>>(p);
+        launch_k(k2, dim3(grid2), dim3(32 * K2_NW), smem2, st, p);
     } else {
         auto k2 = conv_bwd_dw_kernel<float>;
         NSP_CUDA_OK(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        k2<<<grid2, 32 * K2_NW, smem2, st>>>(p);
+        launch_k(k2, dim3(grid2), dim3(32 * K2_NW), smem2, st, p);
     }
     NSP_LAUNCH_OK();
     return NSP_OK;

@@ -56,6 +56,7 @@ struct ConvLnParams {
 
 template <typename T, int D, int K, bool BWD>
 __global__ void __launch_bounds__(D / 2) conv_ln_kernel(ConvLnParams p) {
+    pdl_entry();
     constexpr int NTHR = D / 2;
     constexpr int NW = NTHR / 32;              // warps = 64-channel groups
     constexpr int FPW = TT / NW;               // frames per warp in the normalisation phase
@@ -232,6 +233,7 @@ template <> __device__ __forceinline__ void st_g<float>(float* p, float v) { *p 
 
 template <typename T, int K>
 __global__ void __launch_bounds__(K2_NT) dwconv_bwd_kernel(DwBwdParams p) {
+    pdl_entry();
     constexpr int ROWS = K2_TC + K - 1;
     constexpr int CHUNKS = K2_CH * (int)sizeof(T) / 16;      // 16-byte chunks per tile row
     extern __shared__ __align__(16) uint8_t k2_smem[];
@@ -333,6 +335,7 @@ struct ReduceParams {
     int d, k;
 };
 __global__ void __launch_bounds__(256) conv_bwd_reduce_kernel(ReduceParams p) {
+    pdl_entry();
     const int e = blockIdx.x * 256 + threadIdx.x;
     const int n_ln = 2 * p.d, n_dw = (p.k + 1) * p.d;
     if (e < n_ln) {
@@ -373,7 +376,7 @@ nsp_status launch_ln(const ConvLnParams& p, cudaStream_t st) {
         static bool done = false;
         if (!done) { NSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); done = true; }
     }
-    kern<<<(unsigned)(p.B * ceil_div(p.T, TT)), D / 2, smem, st>>>(p);
+    launch_k(kern, dim3((unsigned)(p.B * ceil_div(p.T, TT))), dim3(D / 2), smem, st, p);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }
@@ -397,7 +400,7 @@ nsp_status launch_dw(const DwBwdParams& p, unsigned grid, cudaStream_t st) {
         static bool done = false;
         if (!done) { NSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); done = true; }
     }
-    kern<<<grid, K2_NT, smem, st>>>(p);
+    launch_k(kern, dim3(grid), dim3(K2_NT), smem, st, p);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }
@@ -473,7 +476,7 @@ nsp_status conv_stream_bwd(int is_bf16, const void* x, int64_t ldx, const float*
     if (s != NSP_OK) return s;
     ReduceParams r;
     r.part1 = part1; r.n1 = n1; r.part2 = part2; r.n2 = B * q.nseg; r.dw = dw; r.dbias = dbias; r.dg = dg; r.db = db; r.d = d; r.k = k;
-    conv_bwd_reduce_kernel<<<(unsigned)ceil_div(2 * d + (k + 1) * d, 256), 256, 0, st>>>(r);
+    launch_k(conv_bwd_reduce_kernel, dim3((unsigned)ceil_div(2 * d + (k + 1) * d, 256)), dim3(256), 0, st, r);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }

@@ -47,6 +47,7 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
 __global__ void __launch_bounds__(192, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x,
                                                              const __grid_constant__ CUtensorMap tmap_w,
                                                              const ConvTcArgs a) {
+    pdl_launch_dependents();      // PDL: the next kernel may start its prologue; ours overlaps the previous kernel's tail
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sW = smem;                                   // 9 x 2 KiB
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3_tc_kernel(const __grid_constan
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    pdl_wait();                    // the previous grid is complete: operands / residuals / outputs may be touched from here
 
     if (warp == 0) {
         if (lane == 0) {
@@ -223,7 +225,7 @@ extern "C" nsp_status nsp_conv3x3_c32_tc_fwd(const void* x, const void* w_taps, 
     if (!attr) { NSP_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     const int tiles = B * ceil_div(T, TT) * ceil_div(F, TF);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    conv3x3_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(tx, tw, a);
+    launch_k(conv3x3_tc_kernel, dim3(grid), dim3(192), smem, (cudaStream_t)stream, tx, tw, a);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }

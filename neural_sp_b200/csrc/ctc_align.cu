@@ -50,6 +50,7 @@ __device__ __forceinline__ float lse3_exact(float m0, float m1, float m2) {
 
 // one CTA (128 threads) per (b,t) row: fp32 log-softmax statistics + path gather
 __global__ void __launch_bounds__(128) align_rows_kernel(AlignParams p) {
+    pdl_entry();
     __shared__ float scratch[32];
     const int64_t row = blockIdx.x;
     const int b = (int)(row / p.T), t = (int)(row % p.T);
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(128) align_rows_kernel(AlignParams p) {
 
 template <int SPT>
 __global__ void __launch_bounds__(1024) align_lattice_kernel(AlignParams p, int HALF) {
+    pdl_entry();
     extern __shared__ float sm[];
     const int Sm = p.Sm;
     float* abuf = sm;               // [2][Sm]
@@ -278,15 +280,15 @@ extern "C" nsp_status nsp_ctc_forced_align(const float* logits, int B, int T, in
     p.emit = (float*)w; p.fa = (float*)(w + lat); p.fb = (float*)(w + 2 * lat);
     p.best = (int32_t*)(w + align_up(3 * lat, 256));
     NSP_CUDA_OK(cudaMemsetAsync(trigger_points, 0, (size_t)B * (Lmax + 1) * sizeof(int32_t), st));
-    align_rows_kernel<<<(unsigned)bt, 128, 0, st>>>(p);
+    launch_k(align_rows_kernel, dim3((unsigned)bt), dim3(128), 0, st, p);
     NSP_LAUNCH_OK();
     int spt = 1, half = (int)align_up((size_t)p.Sm, 32);
     if (half > 512) { spt = 2; half = (int)align_up((size_t)ceil_div(p.Sm, 2), 32); }
     if (half > 512) { spt = 4; half = 512; }
     size_t smem = (size_t)4 * p.Sm * sizeof(float);
-    if (spt == 1) align_lattice_kernel<1><<<B, 2 * half, smem, st>>>(p, half);
-    else if (spt == 2) align_lattice_kernel<2><<<B, 2 * half, smem, st>>>(p, half);
-    else align_lattice_kernel<4><<<B, 2 * half, smem, st>>>(p, half);
+    if (spt == 1) launch_k(align_lattice_kernel<1>, dim3(B), dim3(2 * half), smem, st, p, half);
+    else if (spt == 2) launch_k(align_lattice_kernel<2>, dim3(B), dim3(2 * half), smem, st, p, half);
+    else launch_k(align_lattice_kernel<4>, dim3(B), dim3(2 * half), smem, st, p, half);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }

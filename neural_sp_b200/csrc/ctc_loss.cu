@@ -77,6 +77,7 @@ __device__ __forceinline__ float n_frames_of(const int32_t* elens, int B, int T)
 // ---------------------------------------------------------------------------------------------
 template <int G, int VPT, int VEC>
 __global__ void __launch_bounds__(256, (VPT * VEC <= 32) ? 4 : 3) ctc_rows_kernel(CtcParams p) {
+    pdl_entry();
     constexpr int NT = 256;
     constexpr int RPB = NT / G;
     __shared__ float scratch[32];
@@ -179,6 +180,7 @@ __global__ void __launch_bounds__(256, (VPT * VEC <= 32) ? 4 : 3) ctc_rows_kerne
 // K1, generic: row staged in shared memory (any V up to ~50k, any alignment).
 template <int NT>
 __global__ void __launch_bounds__(NT) ctc_rows_smem_kernel(CtcParams p) {
+    pdl_entry();
     extern __shared__ float srow[];
     __shared__ float scratch[32];
     const int64_t row = blockIdx.x;
@@ -230,6 +232,7 @@ __global__ void __launch_bounds__(NT) ctc_rows_smem_kernel(CtcParams p) {
 // ---------------------------------------------------------------------------------------------
 template <int SPT>
 __global__ void __launch_bounds__(1024) ctc_lattice_kernel(CtcParams p, int HALF) {
+    pdl_entry();
     extern __shared__ float sm[];
     const int Sp = p.Sp;
     float* abuf = sm;                 // [2][Sp] alpha ping-pong
@@ -453,6 +456,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 template <int K, int NWD>
 __global__ void __launch_bounds__(64 * NWD) ctc_lattice_warp_kernel(CtcParams p) {
+    pdl_entry();
     // NWD warps per direction (alpha: warps [0,NWD), beta: warps [NWD,2*NWD)); each lane owns K consecutive states.
     // Inside a warp neighbours travel by shuffle; across warps through a double-buffered smem slot + a named barrier
     // per direction.  Emission rows are staged CT steps at a time into shared memory with cp.async (double buffered),
@@ -655,6 +659,7 @@ __global__ void __launch_bounds__(64 * NWD) ctc_lattice_warp_kernel(CtcParams p)
 // K3: sparse gradient fix-up, one warp per (b, t) row (thousands of independent HBM read-modify-writes in flight),
 // plus the scalar loss reduction in CTA 0.
 __global__ void __launch_bounds__(256) ctc_fixup_kernel(CtcParams p) {
+    pdl_entry();
     __shared__ float scratch[32];
     if (blockIdx.x == gridDim.x - 1) {     // dedicated last CTA: loss = (1-lsm) * sum nll / B + lsm * KL
         float a = 0.f;
@@ -731,6 +736,7 @@ __global__ void __launch_bounds__(256) ctc_fixup_kernel(CtcParams p) {
 }
 
 __global__ void __launch_bounds__(256) ctc_finalize_kernel(CtcParams p) {
+    pdl_entry();
     __shared__ float scratch[32];
     float a = 0.f;
     for (int i = threadIdx.x; i < p.B; i += 256) a += p.nll[i];
@@ -758,7 +764,7 @@ nsp_status launch_rows(const CtcParams& p, int nvec, cudaStream_t st) {
     const int rpb = 256 / G;
     const unsigned grid = (unsigned)ceil_div64(rows, rpb);
     const int vpt = ceil_div(nvec, G);
-#define NSP_ROWS(VPT) ctc_rows_kernel<G, VPT, VEC><<<grid, 256, 0, st>>>(p)
+#define NSP_ROWS(VPT) launch_k(ctc_rows_kernel<G, VPT, VEC>, dim3(grid), dim3(256), 0, st, p)
     if (vpt <= 1) NSP_ROWS(1);
     else if (vpt <= 2) NSP_ROWS(2);
     else if (vpt <= 4) NSP_ROWS(4);
@@ -775,13 +781,22 @@ nsp_status launch_rows(const CtcParams& p, int nvec, cudaStream_t st) {
 
 using namespace nsp;
 
+// lattice row pitch: 32 K states (K = states per lane of the one-warp sweeps, ctc_stream.cuh) up to 512 path states, else a
+// multiple of 16 -- a lane's K-wide vector access never crosses into the next row either way
+static size_t ctc_row_pitch(int Lmax) {
+    const int Smax = 2 * Lmax + 1;
+    if (Smax <= 512) return (size_t)32 * (Smax <= 32 ? 1 : Smax <= 64 ? 2 : Smax <= 128 ? 4 : Smax <= 256 ? 8 : 16);
+    return align_up((size_t)Smax, 16);
+}
+
 extern "C" size_t nsp_ctc_loss_workspace_bytes(int B, int T, int Lmax) {
     if (B <= 0 || T <= 0 || Lmax < 0) return 0;
-    size_t Sp = align_up(2 * (size_t)Lmax + 1, 16);
+    size_t Sp = ctc_row_pitch(Lmax);
     size_t bt = (size_t)B * T;
     return align_up(3 * bt * Sp * sizeof(float), 256) + 3 * align_up(bt * sizeof(float), 256) +
            align_up((size_t)B * sizeof(float), 256) + 2 * align_up((size_t)B * Sp * sizeof(int16_t), 256) +
-           align_up((size_t)B * sizeof(int32_t), 256) + 256;
+           align_up((size_t)(B + 1) * sizeof(int32_t), 256) + 256 +
+           (size_t)(2 * 160 + 4 * (size_t)B + 64) * sizeof(unsigned long long);      /* bring-up trace (NSP_CTC_DEBUG=8) */
 }
 
 extern "C" nsp_status nsp_ctc_loss_fwd_bwd(const float* logits, int64_t stride_b, int64_t stride_t,
@@ -804,8 +819,7 @@ extern "C" nsp_status nsp_ctc_loss_fwd_bwd(const float* logits, int64_t stride_b
     p.logits = logits; p.sb = stride_b; p.st = stride_t; p.B = B; p.T = T; p.V = V;
     p.labels = labels; p.Lmax = Lmax; p.elens = elens; p.ylens = ylens;
     p.blank = blank; p.lsm = lsm_prob; p.nll = nll; p.loss = loss; p.grad = grad;
-    // pitch is a multiple of 16 states: a lane's K-wide (K <= 16) vector access never crosses into the next row
-    p.Sp = (int)align_up((size_t)(2 * Lmax + 1), 16);
+    p.Sp = (int)ctc_row_pitch(Lmax);
     const size_t bt = (size_t)B * T;
     char* w = (char*)workspace;
     const size_t lat = bt * p.Sp * sizeof(float);
@@ -851,20 +865,24 @@ extern "C" nsp_status nsp_ctc_loss_fwd_bwd(const float* logits, int64_t stride_b
                 q.ntiles = ceil_div64(rows, q.R);
                 q.K = Smax <= 32 ? 1 : Smax <= 64 ? 2 : Smax <= 128 ? 4 : Smax <= 256 ? 8 : 16;
                 q.ready = ready;
+                q.next_tile = ready + B;
                 static const int dbg = [] { const char* e = getenv("NSP_CTC_DEBUG"); return e ? atoi(e) : 0; }();
                 q.dbg = dbg;
+                q.trace = (dbg & 8) ? (unsigned long long*)((char*)ready + align_up((size_t)(B + 1) * sizeof(int32_t), 256)) : nullptr;
+                if (q.trace) NSP_CUDA_OK(cudaMemsetAsync(q.trace, 0, (size_t)(2 * 160 + 4 * (size_t)B + 64) * sizeof(unsigned long long), st));
                 const size_t smem = (size_t)q.stages * tile_bytes + lat;
                 const unsigned grid = (unsigned)(q.ntiles < num_sms() ? q.ntiles : num_sms());
-                NSP_CUDA_OK(cudaMemsetAsync(ready, 0, (size_t)B * sizeof(int32_t), st));
+                NSP_CUDA_OK(cudaMemsetAsync(ready, 0, (size_t)(B + 1) * sizeof(int32_t), st));
+                static size_t attr_w = 0, attr_r = 0;          // opt-in shared memory: raise the cap only when it grows
                 if (q.mode_warp) {
-                    NSP_CUDA_OK(cudaFuncSetAttribute(ctc_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    ctc_stream_kernel<true><<<grid, CS_THREADS, smem, st>>>(p, q);
+                    if (smem > attr_w) { NSP_CUDA_OK(cudaFuncSetAttribute(ctc_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_w = smem; }
+                    launch_k(ctc_stream_kernel<true>, dim3(grid), dim3(CS_THREADS), smem, st, p, q);
                 } else {
-                    NSP_CUDA_OK(cudaFuncSetAttribute(ctc_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    ctc_stream_kernel<false><<<grid, CS_THREADS, smem, st>>>(p, q);
+                    if (smem > attr_r) { NSP_CUDA_OK(cudaFuncSetAttribute(ctc_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_r = smem; }
+                    launch_k(ctc_stream_kernel<false>, dim3(grid), dim3(CS_THREADS), smem, st, p, q);
                 }
                 NSP_LAUNCH_OK();
-                ctc_fixup_write_kernel<<<(unsigned)(ceil_div64((int64_t)bt, 8) + 1), 256, 0, st>>>(p);
+                launch_k(ctc_fixup_write_kernel, dim3((unsigned)(ceil_div64((int64_t)bt, 8) + 1)), dim3(256), 0, st, p);
                 NSP_LAUNCH_OK();
                 return NSP_OK;
             }
@@ -885,7 +903,7 @@ extern "C" nsp_status nsp_ctc_loss_fwd_bwd(const float* logits, int64_t stride_b
         size_t smem = (size_t)V * sizeof(float);
         if (smem > 200 * 1024) { set_error("ctc_loss: V=%d too large (max 51200)", V); return NSP_ERR_UNSUPPORTED; }
         NSP_CUDA_OK(cudaFuncSetAttribute(ctc_rows_smem_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ctc_rows_smem_kernel<512><<<(unsigned)bt, 512, smem, st>>>(p);
+        launch_k(ctc_rows_smem_kernel<512>, dim3((unsigned)bt), dim3(512), smem, st, p);
         NSP_LAUNCH_OK();
         s = NSP_OK;
     }
@@ -897,19 +915,19 @@ extern "C" nsp_status nsp_ctc_loss_fwd_bwd(const float* logits, int64_t stride_b
         // four warps per direction (one per SM sub-partition) unless the path is so short that one warp holds it
         const size_t lsm = (size_t)2 * 2 * 8 * p.Sp * sizeof(float);     // [dir][buffer][CT = 8][Sp]
         if (Smax <= 32) {
-            ctc_lattice_warp_kernel<1, 1><<<B, 64, lsm, st>>>(p);
+            launch_k(ctc_lattice_warp_kernel<1, 1>, dim3(B), dim3(64), lsm, st, p);
         } else {
             const int k = ceil_div(Smax, 128);
             if (lsm > 48 * 1024) {
                 NSP_CUDA_OK(cudaFuncSetAttribute(ctc_lattice_warp_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
                 NSP_CUDA_OK(cudaFuncSetAttribute(ctc_lattice_warp_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
             }
-            if (k <= 1) ctc_lattice_warp_kernel<1, 4><<<B, 256, lsm, st>>>(p);
-            else if (k <= 2) ctc_lattice_warp_kernel<2, 4><<<B, 256, lsm, st>>>(p);
-            else ctc_lattice_warp_kernel<4, 4><<<B, 256, lsm, st>>>(p);
+            if (k <= 1) launch_k(ctc_lattice_warp_kernel<1, 4>, dim3(B), dim3(256), lsm, st, p);
+            else if (k <= 2) launch_k(ctc_lattice_warp_kernel<2, 4>, dim3(B), dim3(256), lsm, st, p);
+            else launch_k(ctc_lattice_warp_kernel<4, 4>, dim3(B), dim3(256), lsm, st, p);
         }
         NSP_LAUNCH_OK();
-        ctc_fixup_kernel<<<(unsigned)(ceil_div64((int64_t)bt, 8) + 1), 256, 0, st>>>(p);
+        launch_k(ctc_fixup_kernel, dim3((unsigned)(ceil_div64((int64_t)bt, 8) + 1)), dim3(256), 0, st, p);
         NSP_LAUNCH_OK();
         return NSP_OK;
     }
@@ -927,13 +945,13 @@ extern "C" nsp_status nsp_ctc_loss_fwd_bwd(const float* logits, int64_t stride_b
             NSP_CUDA_OK(cudaFuncSetAttribute(ctc_lattice_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             NSP_CUDA_OK(cudaFuncSetAttribute(ctc_lattice_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
-        if (spt == 1) ctc_lattice_kernel<1><<<B, block, smem, st>>>(p, half);
-        else if (spt == 2) ctc_lattice_kernel<2><<<B, block, smem, st>>>(p, half);
-        else if (spt == 4) ctc_lattice_kernel<4><<<B, block, smem, st>>>(p, half);
-        else ctc_lattice_kernel<8><<<B, block, smem, st>>>(p, half);
+        if (spt == 1) launch_k(ctc_lattice_kernel<1>, dim3(B), dim3(block), smem, st, p, half);
+        else if (spt == 2) launch_k(ctc_lattice_kernel<2>, dim3(B), dim3(block), smem, st, p, half);
+        else if (spt == 4) launch_k(ctc_lattice_kernel<4>, dim3(B), dim3(block), smem, st, p, half);
+        else launch_k(ctc_lattice_kernel<8>, dim3(B), dim3(block), smem, st, p, half);
         NSP_LAUNCH_OK();
     }
-    ctc_finalize_kernel<<<1, 256, 0, st>>>(p);
+    launch_k(ctc_finalize_kernel, dim3(1), dim3(256), 0, st, p);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }

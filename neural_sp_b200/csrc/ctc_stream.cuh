@@ -6,9 +6,12 @@
 //                     gradient (softmax and label-smoothing parts) written IN PLACE into the tile
 //   store thread      cp.async.bulk shared -> HBM of the finished tile (bulk groups; a slot is recycled when its store has
 //                     finished reading shared memory)
+//                     -- and publishes the tile's emission rows to the per-utterance counters (red.release.gpu): a fence on
+//                     the compute warps cost 4 us per row (MEMBAR.SC + L1 invalidate, measured), here it is off their path
 //   2 lattice warps   alpha (forward) and beta (backward) sweeps of the utterances this CTA owns; an utterance starts as
 //                     soon as the per-utterance row counter says all of its emission rows exist -- i.e. UNDER the row pass
-//                     of the following utterances; only the last utterance's sweep is exposed.
+//                     of the following utterances; only the last utterance's sweep is exposed.  The sweep works in the
+//                     log2 domain (ex2 / lg2.approx.ftz, 13 instructions per state and step; the round-1 loop had 37).
 // Loads, math and stores of different tiles overlap by construction (the round-1 kernel alternated load / reduce / store
 // phases inside each CTA and reached 62 % of the HBM rate).  A second small kernel then WRITES the final value of the
 // <= L+1 touched columns per row (softmax part recomputed from the emission, so no read-modify-write) and reduces the loss.
@@ -24,7 +27,11 @@ using tc::smem_u32;
 
 constexpr int CS_NCW = 16;                 // compute warps
 constexpr int CS_NCT = CS_NCW * 32;        // compute threads
-constexpr int CS_THREADS = CS_NCT + 4 * 32;   // + producer warp, store warp, alpha warp, beta warp
+constexpr int CS_GW = CS_NCW / 2;          // ROW mode: two groups of 8 warps work on two rows at once (their barrier and
+constexpr int CS_GT = CS_GW * 32;          // shuffle latencies overlap; one 16-warp group spent 4000 cycles per row, measured)
+constexpr int CS_THREADS = CS_NCT + 4 * 32;   // + producer, store/signal, alpha, beta warps (640 threads: 96 registers each)
+constexpr int CS_W_PROD = CS_NCW, CS_W_STORE = CS_NCW + 1, CS_W_ALPHA = CS_NCW + 2, CS_W_BETA = CS_NCW + 3;
+constexpr float CS_LOG2E = 1.4426950408889634f, CS_LN2 = 0.6931471805599453f;
 constexpr int CS_MAX_STAGES = 8;
 constexpr int CS_CT = 8;                   // lattice: time steps per staged emission chunk
 
@@ -36,8 +43,10 @@ struct CtcStream {
     int64_t ntiles;
     int K;                // lattice states per lane (1, 2, 4, 8, 16)
     int32_t* ready;       // [B] rows of utterance b whose emissions are in HBM (zeroed before the launch)
+    int32_t* next_tile;   // dynamic tile scheduler (zeroed with `ready`): CTAs slowed by their lattice warps take fewer tiles
     float n_frames;       // sum_b min(elens[b], T)  -- computed on the device (see kernel prologue)
-    int dbg;              // bring-up switches (NSP_CTC_DEBUG): 1 = no lattice sweeps, 2 = no row math (copy only)
+    int dbg;              // bring-up switches (NSP_CTC_DEBUG): 1 = no lattice sweeps, 2 = no row math (copy only), 8 = trace
+    unsigned long long* trace;   // dbg & 8: [gridDim.x][2] CTA start / rows done, then [B][2 dirs][2] sweep start / end (globaltimer ns)
 };
 
 __device__ __forceinline__ void bulk_load_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -49,7 +58,12 @@ __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* smem_src,
                  :: "l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void cs_bar_compute() { asm volatile("bar.sync 1, %0;" :: "n"(CS_NCT) : "memory"); }
+__device__ __forceinline__ void cs_bar_group(int g) { asm volatile("bar.sync %0, %1;" :: "r"(1 + g), "n"(CS_GT) : "memory"); }
+__device__ __forceinline__ unsigned long long cs_gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ int ld_acquire_s32(const int32_t* p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -60,35 +74,45 @@ static __device__ __noinline__ void cs_ready_timeout(int b, int have, int want) 
     __trap();
 }
 
-// ---- one direction of the lattice for one utterance, one warp, K consecutive states per lane (registers + shuffles) ----
-template <int K>
-__device__ __forceinline__ void cs_lattice_sweep(const CtcParams& p, int b, bool is_beta, float* my_em, const int32_t* s_lab,
-                                                  int lane, int L, int S, int Tb) {
-    const int Sp = p.Sp;
+__device__ __forceinline__ float cs_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float cs_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float cs_lse3(float a, float b, float c) {          // log2 domain
+    const float m = fmaxf(a, fmaxf(b, c));
+    return m + cs_lg2(cs_ex2(a - m) + cs_ex2(b - m) + cs_ex2(c - m));
+}
+__device__ __forceinline__ void cs_red_release(int32_t* p, int v) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// ---- one direction of the lattice for one utterance: one warp, K consecutive states per lane in registers, neighbours by
+// ---- shuffle, log2 domain.  The row pitch of emit / alpha / beta is exactly 32 K (host), states >= S carry emission
+// ---- NSP_NEG_BIG (written by the row pass), so no lane or state needs a predicate inside the loop.
+template <int K, bool BETA>
+__device__ __forceinline__ void cs_sweep(const CtcParams& p, int b, float* my_em, const int32_t* s_lab, int lane, int S, int Tb, bool no_store) {
+    constexpr int Sp = 32 * K;
+    constexpr int VPR = Sp / 4;                             // 16-byte vectors per emission row
     const int64_t base = (int64_t)b * p.T * Sp;
     const float* em = p.emit + base;
-    float* gout = (is_beta ? p.beta : p.alpha) + base;
+    float* gout = (BETA ? p.beta : p.alpha) + base;
     const int s0 = lane * K;
-    bool valid[K], skip[K];
+    uint32_t skipm = 0, startm = 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int s = s0 + k;
-        valid[k] = s < S;
-        skip[k] = false;
-        if (valid[k] && (s & 1)) {
-            if (!is_beta) skip[k] = (s >= 2) && (s_lab[s >> 1] != s_lab[(s >> 1) - 1]);
-            else          skip[k] = (s + 2 < S) && (s_lab[s >> 1] != s_lab[(s >> 1) + 1]);
+        if (s < S && (s & 1)) {
+            if (!BETA) { if (s >= 2 && s_lab[s >> 1] != s_lab[(s >> 1) - 1]) skipm |= 1u << k; }
+            else       { if (s + 2 < S && s_lab[s >> 1] != s_lab[(s >> 1) + 1]) skipm |= 1u << k; }
         }
+        if (BETA ? (s >= S - 2 && s < S) : (s <= 1)) startm |= 1u << k;
     }
-    const bool lane_active = s0 < S;
-    const int vec_per_row = Sp / 4;
     auto stage = [&](int c) {
         float* dst = my_em + (size_t)(c & 1) * CS_CT * Sp;
-        for (int e = lane; e < CS_CT * vec_per_row; e += 32) {
-            const int tt = e / vec_per_row, v4 = e % vec_per_row;
+#pragma unroll
+        for (int e0 = 0; e0 < CS_CT * VPR; e0 += 32) {
+            const int e = e0 + lane, tt = e / VPR, v4 = e % VPR;
             const int i = c * CS_CT + tt;
             if (i < Tb) {
-                const int t = is_beta ? (Tb - 1 - i) : i;
+                const int t = BETA ? (Tb - 1 - i) : i;
                 cp_async16(dst + tt * Sp + v4 * 4, em + (int64_t)t * Sp + v4 * 4);
             }
         }
@@ -100,184 +124,185 @@ __device__ __forceinline__ void cs_lattice_sweep(const CtcParams& p, int b, bool
     float own[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) own[k] = NSP_NEG_BIG;
-    const int64_t gstep = is_beta ? -(int64_t)Sp : (int64_t)Sp;
-    float* gptr = gout + (int64_t)(is_beta ? (Tb - 1) : 0) * Sp + s0;
+    const int64_t gstep = BETA ? -(int64_t)Sp : (int64_t)Sp;
+    float* gptr = gout + (int64_t)(BETA ? (Tb - 1) : 0) * Sp + s0;
+    auto step = [&](const float* erow, bool first) {
+        float e[K], nw[K];
+        ld_states<K>(erow, e);
+        if (first) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) nw[k] = ((startm >> k) & 1u) ? e[k] : NSP_NEG_BIG;
+        } else {
+            float n1, n2;      // alpha: states s0-1, s0-2 ; beta: states s0+K, s0+K+1 (previous step)
+            if (!BETA) {
+                n1 = __shfl_up_sync(0xffffffffu, own[K - 1], 1);
+                n2 = (K >= 2) ? __shfl_up_sync(0xffffffffu, own[K >= 2 ? K - 2 : 0], 1) : __shfl_up_sync(0xffffffffu, own[0], 2);
+                if (lane == 0) { n1 = NSP_NEG_BIG; n2 = NSP_NEG_BIG; }
+                if (K == 1 && lane == 1) n2 = NSP_NEG_BIG;
+            } else {
+                n1 = __shfl_down_sync(0xffffffffu, own[0], 1);
+                n2 = (K >= 2) ? __shfl_down_sync(0xffffffffu, own[K >= 2 ? 1 : 0], 1) : __shfl_down_sync(0xffffffffu, own[0], 2);
+                if (lane == 31) { n1 = NSP_NEG_BIG; n2 = NSP_NEG_BIG; }
+                if (K == 1 && lane == 30) n2 = NSP_NEG_BIG;
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                float a1, a2;
+                if (!BETA) {
+                    a1 = (k >= 1) ? own[k >= 1 ? k - 1 : 0] : n1;
+                    a2 = (k >= 2) ? own[k >= 2 ? k - 2 : 0] : ((k == 1) ? n1 : n2);
+                } else {
+                    a1 = (k + 1 < K) ? own[k + 1 < K ? k + 1 : 0] : n1;
+                    a2 = (k + 2 < K) ? own[k + 2 < K ? k + 2 : 0] : ((k + 2 == K) ? n1 : n2);
+                }
+                a2 = ((skipm >> k) & 1u) ? a2 : NSP_NEG_BIG;
+                nw[k] = fmaxf(cs_lse3(own[k], a1, a2) + e[k], NSP_NEG_BIG);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) own[k] = nw[k];
+        if (!no_store) st_states<K>(gptr, own);
+        gptr += gstep;
+    };
     for (int c = 0; c < nchunks; ++c) {
         cp_async_wait<1>();
         __syncwarp();
         const float* ebuf = my_em + (size_t)(c & 1) * CS_CT * Sp + s0;
         const int nst = min(CS_CT, Tb - c * CS_CT);
-        for (int tt = 0; tt < nst; ++tt) {
-            const int i = c * CS_CT + tt;
-            float e[K];
+        if (c > 0 && nst == CS_CT) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) e[k] = 0.f;
-            if (lane_active) ld_states<K>(ebuf + tt * Sp, e);
-            float nw[K];
-            if (i == 0) {
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const int s = s0 + k;
-                    const bool start = is_beta ? (s >= S - 2) : (s <= 1);
-                    nw[k] = (valid[k] && start) ? e[k] : NSP_NEG_BIG;
-                }
-            } else {
-                float n1, n2;      // alpha: states s0-1, s0-2 ; beta: states s0+K, s0+K+1 (previous step)
-                if (!is_beta) {
-                    n1 = __shfl_up_sync(0xffffffffu, own[K - 1], 1);
-                    n2 = (K >= 2) ? __shfl_up_sync(0xffffffffu, own[K >= 2 ? K - 2 : 0], 1) : __shfl_up_sync(0xffffffffu, own[0], 2);
-                    if (lane == 0) { n1 = NSP_NEG_BIG; n2 = NSP_NEG_BIG; }
-                    if (K == 1 && lane == 1) n2 = NSP_NEG_BIG;
-                } else {
-                    n1 = __shfl_down_sync(0xffffffffu, own[0], 1);
-                    n2 = (K >= 2) ? __shfl_down_sync(0xffffffffu, own[K >= 2 ? 1 : 0], 1) : __shfl_down_sync(0xffffffffu, own[0], 2);
-                    if (lane == 31) { n1 = NSP_NEG_BIG; n2 = NSP_NEG_BIG; }
-                    if (K == 1 && lane == 30) n2 = NSP_NEG_BIG;
-                }
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    float a1, a2;
-                    if (!is_beta) {
-                        a1 = (k >= 1) ? own[k >= 1 ? k - 1 : 0] : n1;
-                        a2 = (k >= 2) ? own[k >= 2 ? k - 2 : 0] : ((k == 1) ? n1 : n2);
-                    } else {
-                        a1 = (k + 1 < K) ? own[k + 1 < K ? k + 1 : 0] : n1;
-                        a2 = (k + 2 < K) ? own[k + 2 < K ? k + 2 : 0] : ((k + 2 == K) ? n1 : n2);
-                    }
-                    if (!skip[k]) a2 = NSP_NEG_BIG;
-                    const float v = lse3(own[k], a1, a2) + e[k];
-                    nw[k] = valid[k] ? fmaxf(v, NSP_NEG_BIG) : NSP_NEG_BIG;
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < K; ++k) own[k] = nw[k];
-            if (lane_active) st_states<K>(gptr, own);
-            gptr += gstep;
+            for (int tt = 0; tt < CS_CT; ++tt) step(ebuf + tt * Sp, false);
+        } else {
+            for (int tt = 0; tt < nst; ++tt) step(ebuf + tt * Sp, c == 0 && tt == 0);
         }
         __syncwarp();                                       // everyone done with buffer c & 1 before it is refilled
         if (c + 2 < nchunks) stage(c + 2); else cp_async_commit();
     }
     cp_async_wait<0>();
-    if (!is_beta) {                                         // nll = -lse(alpha_{T-1}(S-1), alpha_{T-1}(S-2))
+    if (!BETA) {                                            // nll = -ln2 * lse2(alpha_{T-1}(S-1), alpha_{T-1}(S-2))
         float m = NSP_NEG_BIG;
 #pragma unroll
         for (int k = 0; k < K; ++k) { const int s = s0 + k; if (s == S - 1 || s == S - 2) m = fmaxf(m, own[k]); }
         const float M = warp_max(m);
         float sm_ = 0.f;
 #pragma unroll
-        for (int k = 0; k < K; ++k) { const int s = s0 + k; if (s == S - 1 || s == S - 2) sm_ += __expf(own[k] - M); }
+        for (int k = 0; k < K; ++k) { const int s = s0 + k; if (s == S - 1 || s == S - 2) sm_ += cs_ex2(own[k] - M); }
         sm_ = warp_sum(sm_);
         if (lane == 0) {
-            const float nll = -(M + __logf(sm_));
+            const float nll = -(M + cs_lg2(sm_)) * CS_LN2;
             p.nll_raw[b] = nll;
             p.nll[b] = (nll < 1.0e29f) ? nll : 0.f;
         }
     }
 }
 
-// ---- row math shared by both tile modes.  NV float4 per thread, `nthr` threads on the row, `tid` this thread's rank. ----
-struct RowOut { float lse, H; };
-
+// ---- row math shared by both tile modes.  NV float4 per thread, NTHR threads on the row, `tid` this thread's rank. ----
+// Emissions are stored in log2 units ((x - lse) * log2 e; states >= S get NSP_NEG_BIG) for the sweeps.
 template <int NV, bool CTA>
-__device__ __forceinline__ void cs_process_row(const CtcParams& p, const CtcStream& q, float* buf, int64_t row, int b, int t,
-                                               int tid, float* red /*smem [2][2][16]*/, int& red_par) {
-    constexpr int NTHR = CTA ? CS_NCT : 32;
+__device__ __forceinline__ void cs_process_row(const CtcParams& p, float n_frames, float* buf, int64_t row, int b, int t,
+                                               int tid, float* red /*smem [2][32] of this group*/, int& red_par, int grp) {
+    constexpr int NTHR = CTA ? CS_GT : 32;
     const int V = p.V, V4 = V >> 2;
     float4* b4 = reinterpret_cast<float4*>(buf);
-    const int Tb = min(max(p.elens[b], 0), p.T);
+    const int Tb = min(max(__ldg(p.elens + b), 0), p.T);
     if (t >= Tb) {                                          // padded frame: zero gradient (the tile is stored as a whole)
         for (int i = tid; i < V4; i += NTHR) b4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (tid == 0) { p.klrow[row] = 0.f; p.lse[row] = 0.f; p.hrow[row] = 0.f; }
         return;
     }
-    float4 xv[NV];
+    const int S = 2 * min(max(__ldg(p.ylens + b), 0), p.Lmax) + 1;
+    const int32_t* lab = p.labels + (int64_t)b * p.Lmax;
+    // raw logits of the path states, gathered BEFORE anything overwrites the row (CTA mode: two states per thread, S <= 512)
+    float xg0 = 0.f, xg1 = 0.f;
+    if constexpr (CTA) {
+        if (tid < S) xg0 = buf[path_label(lab, tid, p.blank, V)];
+        if (tid + CS_GT < S) xg1 = buf[path_label(lab, tid + CS_GT, p.blank, V)];
+    }
+    // Instruction budget (one row per ~2 us of HBM time per SM): the first version spent 22 instructions and 2 MUFU per
+    // element (5300 cycles per row, measured); here ~10, with ex2.approx on pre-scaled arguments.  Logits are clamped to
+    // >= -1e30 so that 0 * x stays 0 for masked (-inf) entries.
+    float x[NV * 4];
     float m = -INFINITY;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
         const int i4 = j * NTHR + tid;
-        if (i4 < V4) {
-            xv[j] = b4[i4];
-            m = fmaxf(fmaxf(m, fmaxf(xv[j].x, xv[j].y)), fmaxf(xv[j].z, xv[j].w));
-        } else {
-            xv[j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        }
+        float4 v = make_float4(NSP_NEG_BIG, NSP_NEG_BIG, NSP_NEG_BIG, NSP_NEG_BIG);
+        if (i4 < V4) v = b4[i4];
+        x[4 * j + 0] = fmaxf(v.x, NSP_NEG_BIG); x[4 * j + 1] = fmaxf(v.y, NSP_NEG_BIG);
+        x[4 * j + 2] = fmaxf(v.z, NSP_NEG_BIG); x[4 * j + 3] = fmaxf(v.w, NSP_NEG_BIG);
+        m = fmaxf(fmaxf(m, fmaxf(x[4 * j], x[4 * j + 1])), fmaxf(x[4 * j + 2], x[4 * j + 3]));
     }
     m = warp_max(m);
     if constexpr (CTA) {
         float* r0 = red + red_par * 32;
         if ((tid & 31) == 0) r0[tid >> 5] = m;
-        cs_bar_compute();
-        m = r0[tid & 15];
+        cs_bar_group(grp);
+        m = r0[tid & (CS_GW - 1)];
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        for (int o = CS_GW / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
         red_par ^= 1;
     }
     float s = 0.f, sx = 0.f;
+    const float m2 = -m * CS_LOG2E;
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-        const float x[4] = {xv[j].x, xv[j].y, xv[j].z, xv[j].w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float e = __expf(x[k] - m);              // exp(-inf) = 0 for the tail / -inf logits
-            s += e;
-            sx += (e > 0.f) ? e * x[k] : 0.f;
-        }
+    for (int i = 0; i < NV * 4; ++i) {
+        const float e = cs_ex2(fmaf(x[i], CS_LOG2E, m2));   // exp(x - m); 0 for the padding / masked entries
+        s += e;
+        sx = fmaf(e, x[i], sx);
     }
     s = warp_sum(s);
     sx = warp_sum(sx);
     if constexpr (CTA) {
         float* r0 = red + red_par * 32;
         if ((tid & 31) == 0) { r0[tid >> 5] = s; r0[16 + (tid >> 5)] = sx; }
-        cs_bar_compute();
-        s = r0[tid & 15];
-        sx = r0[16 + (tid & 15)];
+        cs_bar_group(grp);                                   // (also: every gather above precedes every overwrite below)
+        s = r0[tid & (CS_GW - 1)];
+        sx = r0[16 + (tid & (CS_GW - 1))];
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); sx += __shfl_xor_sync(0xffffffffu, sx, o); }
+        for (int o = CS_GW / 2; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); sx += __shfl_xor_sync(0xffffffffu, sx, o); }
         red_par ^= 1;
     }
     const float lse = m + __logf(s);
     const float H = (p.lsm > 0.f) ? (sx / s - lse) : 0.f;   // sum_v p * lp
-    // path emissions from the staged row (still the logits)
-    const int S = 2 * min(max(p.ylens[b], 0), p.Lmax) + 1;
-    const int32_t* lab = p.labels + (int64_t)b * p.Lmax;
     float* em = p.emit + row * (int64_t)p.Sp;
-    for (int st = tid; st < S; st += NTHR) em[st] = buf[path_label(lab, st, p.blank, V)] - lse;
+    if constexpr (CTA) {
+        if (tid < p.Sp) em[tid] = (tid < S) ? (fmaxf(xg0, NSP_NEG_BIG) - lse) * CS_LOG2E : NSP_NEG_BIG;
+        if (tid + CS_GT < p.Sp) em[tid + CS_GT] = (tid + CS_GT < S) ? (fmaxf(xg1, NSP_NEG_BIG) - lse) * CS_LOG2E : NSP_NEG_BIG;
+    } else {
+        for (int st = tid; st < p.Sp; st += 32)
+            em[st] = (st < S) ? (fmaxf(buf[path_label(lab, st, p.blank, V)], NSP_NEG_BIG) - lse) * CS_LOG2E : NSP_NEG_BIG;
+        __syncwarp();                                        // gathers done before the row is overwritten
+    }
     if (tid == 0) {
         p.lse[row] = lse;
         p.hrow[row] = H;
         p.klrow[row] = (p.lsm > 0.f) ? (H + __logf((float)(V - 1))) : 0.f;
     }
-    if constexpr (CTA) cs_bar_compute(); else __syncwarp();     // gathers done before the row is overwritten
     const float c_ctc = (1.f - p.lsm) / (float)p.B;
-    const float c_kl = (p.lsm > 0.f) ? p.lsm / q.n_frames : 0.f;
+    const float c_kl = (p.lsm > 0.f) ? p.lsm / n_frames : 0.f;
+    const float c0 = c_ctc - c_kl * (lse + H);               // g = p * (c_ctc + c_kl * (x - lse - H)) = p * (c0 + c_kl * x)
+    const float l2 = -lse * CS_LOG2E;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
         const int i4 = j * NTHR + tid;
         if (i4 < V4) {
-            const float x[4] = {xv[j].x, xv[j].y, xv[j].z, xv[j].w};
             float g[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float lp = x[k] - lse;
-                const float pv = __expf(lp);
-                g[k] = (pv > 0.f) ? pv * (c_ctc + c_kl * (lp - H)) : 0.f;
-            }
+            for (int k = 0; k < 4; ++k) g[k] = cs_ex2(fmaf(x[4 * j + k], CS_LOG2E, l2)) * fmaf(c_kl, x[4 * j + k], c0);
             b4[i4] = make_float4(g[0], g[1], g[2], g[3]);
         }
-    }
-    if (tid == 0) {                                         // this row's emissions are published
-        __threadfence();
-        atomicAdd(q.ready + b, 1);
     }
 }
 
 template <bool MODE_WARP>
 __global__ void __launch_bounds__(CS_THREADS, 1) ctc_stream_kernel(CtcParams p, CtcStream q) {
+    pdl_entry();
     extern __shared__ __align__(1024) uint8_t cs_smem[];
     __shared__ __align__(8) uint64_t full_bar[CS_MAX_STAGES], comp_bar[CS_MAX_STAGES], empty_bar[CS_MAX_STAGES];
-    __shared__ float s_red[2 * 32];
+    __shared__ float s_red[2][2 * 32];                    // per compute group
     __shared__ int32_t s_lab[2][512 + 8];
     __shared__ float s_nframes;
+    __shared__ int64_t s_tile[CS_MAX_STAGES];             // tile staged in each slot (-1: no more work)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int V = p.V;
@@ -289,7 +314,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) ctc_stream_kernel(CtcParams p, 
     if (threadIdx.x == 0) {
         for (int i = 0; i < q.stages; ++i) {
             tc::mbar_init(&full_bar[i], 1);
-            tc::mbar_init(&comp_bar[i], CS_NCT);
+            tc::mbar_init(&comp_bar[i], MODE_WARP ? CS_NCW : CS_GW);     // one arrival per compute warp working on the slot
             tc::mbar_init(&empty_bar[i], 1);
         }
         tc::fence_barrier_init();
@@ -298,7 +323,8 @@ __global__ void __launch_bounds__(CS_THREADS, 1) ctc_stream_kernel(CtcParams p, 
         s_nframes = (float)acc;
     }
     __syncthreads();
-    q.n_frames = s_nframes;
+    const float n_frames = s_nframes;
+    if (q.trace && threadIdx.x == 0) q.trace[2 * blockIdx.x] = cs_gtime();
 
     auto tile_rows = [&](int64_t tile) { return (int)min((int64_t)q.R, total_rows - tile * q.R); };
     auto tile_valid = [&](int64_t tile, int nr) {           // does any row of the tile carry a real frame?
@@ -312,36 +338,57 @@ __global__ void __launch_bounds__(CS_THREADS, 1) ctc_stream_kernel(CtcParams p, 
 
     if (warp < CS_NCW) {
         // ------------------------------ compute warps ------------------------------
-        const int ctid = threadIdx.x;
+        // ROW mode: group g = warps 8g..8g+7 takes iterations g, g+2, ... ; WARP mode: all 16 warps share every tile
+        const int grp = MODE_WARP ? 0 : (warp >> 3);
+        const int gtid = MODE_WARP ? (int)threadIdx.x : (int)(threadIdx.x & (CS_GT - 1));
         int red_par = 0;
-        int it = 0;
-        for (int64_t tile = blockIdx.x; tile < q.ntiles; tile += gridDim.x, ++it) {
+        for (int it = grp;; it += (MODE_WARP ? 1 : 2)) {
             const int slot = it % q.stages;
             const uint32_t ph = (uint32_t)(it / q.stages) & 1u;
-            tc::mbar_wait(&full_bar[slot], ph);
+            unsigned long long* rt = (q.trace && threadIdx.x == 0 && blockIdx.x == 40 && (it >> 1) < 16) ? q.trace + 2 * 160 + 4 * (size_t)p.B + 4 * (it >> 1) : nullptr;
+            if (rt) rt[0] = cs_gtime();
+            tc::mbar_wait_parked(&full_bar[slot], ph);
+            if (rt) rt[1] = cs_gtime();
+            const int64_t tile = s_tile[slot];
+            if (tile < 0) break;
             float* buf = tiles + (size_t)slot * q.tile_floats;
             const int nr = tile_rows(tile);
             if (q.dbg & 2) {
             } else if constexpr (MODE_WARP) {
                 for (int r = warp; r < nr; r += CS_NCW) {
                     const int64_t row = tile * q.R + r;
-                    cs_process_row<10, false>(p, q, buf + (size_t)r * V, row, (int)(row / p.T), (int)(row % p.T), lane, s_red, red_par);
+                    cs_process_row<10, false>(p, n_frames, buf + (size_t)r * V, row, (int)(row / p.T), (int)(row % p.T), lane, s_red[0], red_par, 0);
                 }
             } else {
                 const int64_t row = tile;
-                cs_process_row<6, true>(p, q, buf, row, (int)(row / p.T), (int)(row % p.T), ctid, s_red, red_par);
+                cs_process_row<12, true>(p, n_frames, buf, row, (int)(row / p.T), (int)(row % p.T), gtid, s_red[grp], red_par, grp);
             }
+            if (rt) rt[2] = cs_gtime();
             tc::fence_proxy_async_smem();                    // generic-proxy writes of the tile -> visible to the bulk store
-            tc::mbar_arrive(&comp_bar[slot]);
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&comp_bar[slot]);
+            if (rt) rt[3] = cs_gtime();
         }
-    } else if (warp == CS_NCW) {
+        if (q.trace && threadIdx.x == 0) q.trace[2 * blockIdx.x + 1] = cs_gtime();
+    } else if (warp == CS_W_PROD) {
         // ------------------------------ producer ------------------------------
         if (lane == 0) {
-            int it = 0;
-            for (int64_t tile = blockIdx.x; tile < q.ntiles; tile += gridDim.x, ++it) {
+            for (int it = 0;; ++it) {
                 const int slot = it % q.stages;
                 const uint32_t ph = (uint32_t)(it / q.stages) & 1u;
-                tc::mbar_wait(&empty_bar[slot], ph ^ 1u);
+                tc::mbar_wait_parked(&empty_bar[slot], ph ^ 1u);
+                const int64_t tile = atomicAdd(q.next_tile, 1);
+                s_tile[slot] = tile < q.ntiles ? tile : -1;          // published by the arrive below (release, cta)
+                if (tile >= q.ntiles) {                              // end of work: one sentinel per compute group
+                    tc::mbar_arrive(&full_bar[slot]);
+                    if (!MODE_WARP) {
+                        const int slot2 = (it + 1) % q.stages;
+                        tc::mbar_wait_parked(&empty_bar[slot2], ((uint32_t)((it + 1) / q.stages) & 1u) ^ 1u);
+                        s_tile[slot2] = -1;
+                        tc::mbar_arrive(&full_bar[slot2]);
+                    }
+                    break;
+                }
                 const int nr = tile_rows(tile);
                 if (!tile_valid(tile, nr)) { tc::mbar_arrive(&full_bar[slot]); continue; }
                 float* buf = tiles + (size_t)slot * q.tile_floats;
@@ -353,29 +400,36 @@ __global__ void __launch_bounds__(CS_THREADS, 1) ctc_stream_kernel(CtcParams p, 
                 bulk_load_g2s(buf, src, bytes, &full_bar[slot]);
             }
         }
-    } else if (warp == CS_NCW + 1) {
+    } else if (warp == CS_W_STORE) {
         // ------------------------------ store ------------------------------
         if (lane == 0) {
-            int it = 0, prev_slot = -1;
-            for (int64_t tile = blockIdx.x; tile < q.ntiles; tile += gridDim.x, ++it) {
+            for (int it = 0;; ++it) {
                 const int slot = it % q.stages;
                 const uint32_t ph = (uint32_t)(it / q.stages) & 1u;
-                tc::mbar_wait(&comp_bar[slot], ph);
+                tc::mbar_wait_parked(&full_bar[slot], ph);
+                const int64_t tile = s_tile[slot];
+                if (tile < 0) break;
+                tc::mbar_wait_parked(&comp_bar[slot], ph);
                 const int nr = tile_rows(tile);
                 bulk_store_s2g(p.grad + tile * (int64_t)q.R * V, tiles + (size_t)slot * q.tile_floats,
                                (uint32_t)((size_t)nr * V * sizeof(float)));
                 tc::bulk_commit();
-                if (prev_slot >= 0) {
-                    tc::bulk_wait_read<1>();                 // the previous tile's store has left shared memory
-                    tc::mbar_arrive(&empty_bar[prev_slot]);
+                tc::bulk_wait_read<0>();                     // the tile has left shared memory (sub-microsecond): recycle the slot now --
+                tc::mbar_arrive(&empty_bar[slot]);           // waiting for the NEXT store first kept only 1-2 loads in flight (measured)
+                if (!(q.dbg & 2)) {                          // publish the tile's emission rows: per-utterance counters, release (gpu),
+                    const int64_t r0 = tile * q.R, r1 = r0 + nr;   // cumulative over the compute warps' writes (acquired through comp_bar)
+                    for (int b = (int)(r0 / p.T); (int64_t)b * p.T < r1; ++b) {
+                        const int64_t lo = max(r0, (int64_t)b * p.T);
+                        const int64_t hi = min(r1, (int64_t)b * p.T + min(max(p.elens[b], 0), p.T));
+                        if (hi > lo) cs_red_release(q.ready + b, (int)(hi - lo));
+                    }
                 }
-                prev_slot = slot;
             }
             bulk_wait_all();
         }
     } else {
         // ------------------------------ lattice warps ------------------------------
-        const bool is_beta = warp == CS_NCW + 3;
+        const bool is_beta = (q.dbg & 16) ? (warp == CS_W_ALPHA) : (warp == CS_W_BETA);     // dbg 16: swap the two warps
         if (q.dbg & 1) return;
         int32_t* lab_s = s_lab[is_beta ? 1 : 0];
         float* my_em = lat_em + (size_t)(is_beta ? 1 : 0) * 2 * CS_CT * p.Sp;
@@ -387,8 +441,8 @@ __global__ void __launch_bounds__(CS_THREADS, 1) ctc_stream_kernel(CtcParams p, 
             __syncwarp();
             for (int i = lane; i < L; i += 32) lab_s[i] = lab[i];
             __syncwarp();
-            if (!is_beta) {                                  // same-label chains for the fix-up kernel
-                for (int s = lane; s < S; s += 32) {
+            {                                                // same-label chains for the fix-up kernel (both warps, half each)
+                for (int s = lane + (is_beta ? 32 : 0); s < S; s += 64) {
                     int nx = -1, hd = 1;
                     if (s & 1) {
                         const int me = lab_s[s >> 1];
@@ -403,28 +457,38 @@ __global__ void __launch_bounds__(CS_THREADS, 1) ctc_stream_kernel(CtcParams p, 
                 if (!is_beta && lane == 0) { p.nll_raw[b] = (L == 0) ? 0.f : 1.0e30f; p.nll[b] = 0.f; }
                 continue;
             }
-            if (lane == 0) {                                 // wait until every emission row of this utterance is published
+            {   // wait until every emission row of this utterance is published.  Every lane polls (same address: one
+                // request per poll) so the loop is warp-uniform: a lane-0-only loop left the warp DIVERGED for the whole
+                // sweep -- every shuffle then took the slow reconvergence path, 0.6-0.9 us per step instead of 0.15-0.25
+                // (measured with the in-kernel trace, profiles/README.md round 2).
                 const long long deadline = clock64() + 4000000000LL;
                 int have;
                 while ((have = ld_acquire_s32(q.ready + b)) < Tb) {
-                    __nanosleep(256);
-                    if (clock64() > deadline) cs_ready_timeout(b, have, Tb);
+                    __nanosleep(128);
+                    if (clock64() > deadline) { if (lane == 0) cs_ready_timeout(b, have, Tb); __trap(); }
                 }
             }
             __syncwarp();
+            unsigned long long* tr = q.trace ? q.trace + 2 * 160 + ((size_t)b * 2 + (is_beta ? 1 : 0)) * 2 : nullptr;
+            if (tr && lane == 0) tr[0] = cs_gtime();
+#define CS_SWEEP(KK) do { if (is_beta) cs_sweep<KK, true>(p, b, my_em, lab_s, lane, S, Tb, (q.dbg & 32) != 0); \
+                          else cs_sweep<KK, false>(p, b, my_em, lab_s, lane, S, Tb, (q.dbg & 32) != 0); } while (0)
             switch (q.K) {
-                case 1: cs_lattice_sweep<1>(p, b, is_beta, my_em, lab_s, lane, L, S, Tb); break;
-                case 2: cs_lattice_sweep<2>(p, b, is_beta, my_em, lab_s, lane, L, S, Tb); break;
-                case 4: cs_lattice_sweep<4>(p, b, is_beta, my_em, lab_s, lane, L, S, Tb); break;
-                case 8: cs_lattice_sweep<8>(p, b, is_beta, my_em, lab_s, lane, L, S, Tb); break;
-                default: cs_lattice_sweep<16>(p, b, is_beta, my_em, lab_s, lane, L, S, Tb); break;
+                case 1: CS_SWEEP(1); break;
+                case 2: CS_SWEEP(2); break;
+                case 4: CS_SWEEP(4); break;
+                case 8: CS_SWEEP(8); break;
+                default: CS_SWEEP(16); break;
             }
+#undef CS_SWEEP
+            if (tr && lane == 0) tr[1] = cs_gtime();
         }
     }
 }
 
 // Second kernel: final value of the touched columns (write only) + the scalar loss.  One warp per (b, t) row.
 __global__ void __launch_bounds__(256) ctc_fixup_write_kernel(CtcParams p) {
+    pdl_entry();
     __shared__ float scratch[32];
     if (blockIdx.x == gridDim.x - 1) {     // dedicated last CTA: loss = (1-lsm) * sum nll / B + lsm * KL
         float a = 0.f;
@@ -473,37 +537,40 @@ __global__ void __launch_bounds__(256) ctc_fixup_write_kernel(CtcParams p) {
     const int32_t* lab = p.labels + (int64_t)b * p.Lmax;
     const int bl = min(max(p.blank, 0), p.V - 1);
     auto soft = [&](float lp) { const float pv = __expf(lp); return (pv > 0.f) ? pv * (c_ctc + c_kl * (lp - H)) : 0.f; };
+    // alpha / beta / emissions are in log2 units (ctc_stream_kernel); nll is natural
+    const float nll2 = nll * CS_LOG2E;
     // blank column: all even states
     float m = NSP_NEG_BIG, sum = 0.f;
     for (int s = 2 * lane; s < S; s += 64) {
-        float v = a[s] + bt[s];
-        float nm = fmaxf(m, v);
-        sum = sum * __expf(m - nm) + __expf(v - nm);
+        const float v = a[s] + bt[s];
+        const float nm = fmaxf(m, v);
+        sum = sum * cs_ex2(m - nm) + cs_ex2(v - nm);
         m = nm;
     }
     const float M = warp_max(m);
-    sum = warp_sum(sum * __expf(m - M));
+    sum = warp_sum(sum * cs_ex2(m - M));
     // label columns: head states walk their same-label chain (deterministic order); a label equal to the blank id
     // (degenerate input) is folded into the blank column's value
     float extra = 0.f;
     for (int s = 2 * lane + 1; s < S; s += 64) {
         if (head[s]) {
             float mm = a[s] + bt[s], ss = 1.f;
-            for (int q = nxt[s]; q >= 0; q = nxt[q]) {
-                float v = a[q] + bt[q];
-                float nm = fmaxf(mm, v);
-                ss = ss * __expf(mm - nm) + __expf(v - nm);
+            int guard = 0;
+            for (int q = nxt[s]; q >= 0 && q < Sp && guard < L; q = nxt[q], ++guard) {
+                const float v = a[q] + bt[q];
+                const float nm = fmaxf(mm, v);
+                ss = ss * cs_ex2(mm - nm) + cs_ex2(v - nm);
                 mm = nm;
             }
-            const float lcab = mm + __logf(ss);
+            const float lcab2 = mm + cs_lg2(ss);
             const int v = min(max(lab[s >> 1], 0), p.V - 1);
-            const float occ = c_ctc * __expf(lcab + nll - e[s]);
-            if (v != bl) grow[v] = soft(e[s]) - occ;
+            const float occ = c_ctc * cs_ex2(lcab2 + nll2 - e[s]);
+            if (v != bl) grow[v] = soft(e[s] * CS_LN2) - occ;
             else extra += occ;
         }
     }
     extra = warp_sum(extra);
-    if (lane == 0) grow[bl] = soft(e[0]) - c_ctc * __expf(M + __logf(sum) + nll - e[0]) - extra;
+    if (lane == 0) grow[bl] = soft(e[0] * CS_LN2) - c_ctc * cs_ex2(M + cs_lg2(sum) + nll2 - e[0]) - extra;
 }
 
 }  // namespace

@@ -14,6 +14,7 @@ namespace {
 template <int G, int VPT, int VEC>
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                            int64_t rows, int V, int log_mode, float inv_temp) {
+    pdl_entry();
     __shared__ float scratch[32];
     constexpr int RPB = 256 / G;
     const int lane = threadIdx.x % G;
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
 // generic fallback: any V, three passes over L1/L2-resident row
 __global__ void __launch_bounds__(256) softmax_rows_generic_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                                    int64_t rows, int V, int log_mode, float inv_temp) {
+    pdl_entry();
     __shared__ float scratch[32];
     const int64_t row = blockIdx.x;
     const float* xr = x + row * V;
@@ -80,6 +82,7 @@ __global__ void __launch_bounds__(256) softmax_rows_generic_kernel(const float* 
 
 // first-max argmax per row (warp per row)
 __global__ void __launch_bounds__(256) argmax_rows_kernel(const float* __restrict__ x, int32_t* __restrict__ best, int64_t rows, int V) {
+    pdl_entry();
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -98,6 +101,7 @@ __global__ void __launch_bounds__(256) argmax_rows_kernel(const float* __restric
 // per utterance: collapse repeats, drop blanks, record the first frame of every non-blank run
 __global__ void ctc_collapse_kernel(const int32_t* __restrict__ best, const int32_t* __restrict__ elens, int B, int T, int blank,
                                     int32_t* __restrict__ hyp, int32_t* __restrict__ hyp_lens, int32_t* __restrict__ trig) {
+    pdl_entry();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const int Tb = min(max(elens[b], 0), T);
@@ -127,7 +131,7 @@ extern "C" nsp_status nsp_softmax_rows(const float* x, float* y, int64_t rows, i
     const bool vec4 = (V % 4 == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0);
     const int vec = vec4 ? 4 : 1;
     const int nvec = V / vec;
-#define NSP_SM(G, VPT, VEC) softmax_rows_kernel<G, VPT, VEC><<<(unsigned)ceil_div64(rows, 256 / G), 256, 0, st>>>(x, y, rows, V, log_mode, it)
+#define NSP_SM(G, VPT, VEC) launch_k(softmax_rows_kernel<G, VPT, VEC>, dim3((unsigned)ceil_div64(rows, 256 / G)), dim3(256), 0, st, x, y, rows, V, log_mode, it)
     if (nvec <= 32 * 8) {
         const int vpt = ceil_div(nvec, 32);
         if (vec4) { if (vpt <= 1) NSP_SM(32, 1, 4); else if (vpt <= 2) NSP_SM(32, 2, 4); else if (vpt <= 4) NSP_SM(32, 4, 4); else NSP_SM(32, 8, 4); }
@@ -137,7 +141,7 @@ extern "C" nsp_status nsp_softmax_rows(const float* x, float* y, int64_t rows, i
         if (vec4) { if (vpt <= 2) NSP_SM(256, 2, 4); else if (vpt <= 4) NSP_SM(256, 4, 4); else if (vpt <= 8) NSP_SM(256, 8, 4); else NSP_SM(256, 12, 4); }
         else      { if (vpt <= 2) NSP_SM(256, 2, 1); else if (vpt <= 4) NSP_SM(256, 4, 1); else if (vpt <= 8) NSP_SM(256, 8, 1); else NSP_SM(256, 12, 1); }
     } else {
-        softmax_rows_generic_kernel<<<(unsigned)rows, 256, 0, st>>>(x, y, rows, V, log_mode, it);
+        launch_k(softmax_rows_generic_kernel, dim3((unsigned)rows), dim3(256), 0, st, x, y, rows, V, log_mode, it);
     }
 #undef NSP_SM
     NSP_LAUNCH_OK();
@@ -150,9 +154,9 @@ extern "C" nsp_status nsp_ctc_greedy(const float* logits, int B, int T, int V, c
     NSP_CHECK_ARG(B > 0 && T > 0 && V > 0, "ctc_greedy: bad shape");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t rows = (int64_t)B * T;
-    argmax_rows_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, st>>>(logits, best, rows, V);
+    launch_k(argmax_rows_kernel, dim3((unsigned)ceil_div64(rows, 8)), dim3(256), 0, st, logits, best, rows, V);
     NSP_LAUNCH_OK();
-    ctc_collapse_kernel<<<(unsigned)ceil_div(B, 64), 64, 0, st>>>(best, elens, B, T, blank, hyp, hyp_lens, trigger);
+    launch_k(ctc_collapse_kernel, dim3((unsigned)ceil_div(B, 64)), dim3(64), 0, st, best, elens, B, T, blank, hyp, hyp_lens, trigger);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }

@@ -59,6 +59,7 @@ template <> __device__ __forceinline__ void stv<__nv_bfloat16>(__nv_bfloat16* p,
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) dropout_kernel(const TI* x, TO* y, int64_t n, float p, float scale,
                                                       const unsigned long long* __restrict__ state, uint32_t stream) {
+    pdl_entry();
     const Rng g = load_rng(state, stream, p);
     const float s = scale / (1.f - p);
     const int64_t ngrp = (n + 3) >> 2;
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(256) dropout_kernel(const TI* x, TO* y, int64_
 __global__ void __launch_bounds__(256) dropout_f32_vec_kernel(const float4* x, float4* y, int64_t ngrp,
                                                               float p, float scale, const unsigned long long* __restrict__ state,
                                                               uint32_t stream) {
+    pdl_entry();
     const Rng g = load_rng(state, stream, p);
     const float s = scale / (1.f - p);
     for (int64_t grp = (int64_t)blockIdx.x * 256 + threadIdx.x; grp < ngrp; grp += (int64_t)gridDim.x * 256) {
@@ -89,6 +91,7 @@ __global__ void __launch_bounds__(256) dropout_f32_vec_kernel(const float4* x, f
 __global__ void __launch_bounds__(256) dropout_bf16_vec_kernel(const uint2* x, uint2* y, int64_t ngrp,
                                                                float p, float scale, const unsigned long long* __restrict__ state,
                                                                uint32_t stream) {
+    pdl_entry();
     const Rng g = load_rng(state, stream, p);
     const float s = scale / (1.f - p);
     for (int64_t grp = (int64_t)blockIdx.x * 256 + threadIdx.x; grp < ngrp; grp += (int64_t)gridDim.x * 256) {
@@ -108,6 +111,7 @@ template <typename TT>
 __global__ void __launch_bounds__(256) dropout_add_kernel(const TT* __restrict__ t, const float* res,
                                                           float* out, int64_t n, float p, float alpha,
                                                           const unsigned long long* __restrict__ state, uint32_t stream) {
+    pdl_entry();
     const Rng g = load_rng(state, stream, p);
     const float s = alpha / (1.f - p);
     const int64_t ngrp = (n + 3) >> 2;
@@ -121,7 +125,8 @@ __global__ void __launch_bounds__(256) dropout_add_kernel(const TT* __restrict__
     }
 }
 
-__global__ void rng_advance_kernel(unsigned long long* state) { state[1] += 1ull; }
+__global__ void rng_advance_kernel(unsigned long long* state) {
+    pdl_entry(); state[1] += 1ull; }
 
 unsigned dr_grid(int64_t ngrp) {
     int64_t b = ceil_div64(ngrp, 256), cap = (int64_t)num_sms() * 8;
@@ -142,17 +147,17 @@ extern "C" nsp_status nsp_dropout(int in_bf16, int out_bf16, const void* x, void
     const int64_t ngrp = (n + 3) / 4;
     const bool vec = (n % 4 == 0) && ((((uintptr_t)x | (uintptr_t)y) & 15) == 0);
     if (!in_bf16 && !out_bf16 && vec)
-        dropout_f32_vec_kernel<<<dr_grid(ngrp), 256, 0, st>>>((const float4*)x, (float4*)y, ngrp, p, scale, state, stream_id);
+        launch_k(dropout_f32_vec_kernel, dim3(dr_grid(ngrp)), dim3(256), 0, st, (const float4*)x, (float4*)y, ngrp, p, scale, state, stream_id);
     else if (in_bf16 && out_bf16 && vec)
-        dropout_bf16_vec_kernel<<<dr_grid(ngrp), 256, 0, st>>>((const uint2*)x, (uint2*)y, ngrp, p, scale, state, stream_id);
+        launch_k(dropout_bf16_vec_kernel, dim3(dr_grid(ngrp)), dim3(256), 0, st, (const uint2*)x, (uint2*)y, ngrp, p, scale, state, stream_id);
     else if (!in_bf16 && !out_bf16)
-        dropout_kernel<float, float><<<dr_grid(ngrp), 256, 0, st>>>((const float*)x, (float*)y, n, p, scale, state, stream_id);
+        launch_k(dropout_kernel<float, float>, dim3(dr_grid(ngrp)), dim3(256), 0, st, (const float*)x, (float*)y, n, p, scale, state, stream_id);
     else if (!in_bf16 && out_bf16)
-        dropout_kernel<float, __nv_bfloat16><<<dr_grid(ngrp), 256, 0, st>>>((const float*)x, (__nv_bfloat16*)y, n, p, scale, state, stream_id);
+        launch_k(dropout_kernel<float, __nv_bfloat16>, dim3(dr_grid(ngrp)), dim3(256), 0, st, (const float*)x, (__nv_bfloat16*)y, n, p, scale, state, stream_id);
     else if (in_bf16 && !out_bf16)
-        dropout_kernel<__nv_bfloat16, float><<<dr_grid(ngrp), 256, 0, st>>>((const __nv_bfloat16*)x, (float*)y, n, p, scale, state, stream_id);
+        launch_k(dropout_kernel<__nv_bfloat16, float>, dim3(dr_grid(ngrp)), dim3(256), 0, st, (const __nv_bfloat16*)x, (float*)y, n, p, scale, state, stream_id);
     else
-        dropout_kernel<__nv_bfloat16, __nv_bfloat16><<<dr_grid(ngrp), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, p, scale, state, stream_id);
+        launch_k(dropout_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(dr_grid(ngrp)), dim3(256), 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, p, scale, state, stream_id);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }
@@ -164,15 +169,15 @@ extern "C" nsp_status nsp_dropout_add(int t_bf16, const void* t, const float* re
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned long long* state = reinterpret_cast<const unsigned long long*>(rng_state);
     const int64_t ngrp = (n + 3) / 4;
-    if (t_bf16) dropout_add_kernel<__nv_bfloat16><<<dr_grid(ngrp), 256, 0, st>>>((const __nv_bfloat16*)t, res, out, n, p, alpha, state, stream_id);
-    else dropout_add_kernel<float><<<dr_grid(ngrp), 256, 0, st>>>((const float*)t, res, out, n, p, alpha, state, stream_id);
+    if (t_bf16) launch_k(dropout_add_kernel<__nv_bfloat16>, dim3(dr_grid(ngrp)), dim3(256), 0, st, (const __nv_bfloat16*)t, res, out, n, p, alpha, state, stream_id);
+    else launch_k(dropout_add_kernel<float>, dim3(dr_grid(ngrp)), dim3(256), 0, st, (const float*)t, res, out, n, p, alpha, state, stream_id);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }
 
 extern "C" nsp_status nsp_rng_advance(uint64_t* rng_state, void* stream) {
     NSP_CHECK_ARG(rng_state, "rng_advance: null state");
-    rng_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long*>(rng_state));
+    launch_k(rng_advance_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, reinterpret_cast<unsigned long long*>(rng_state));
     NSP_LAUNCH_OK();
     return NSP_OK;
 }

@@ -6,6 +6,7 @@ namespace {
 
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi,
                                                          float* __restrict__ lo, int64_t n) {
+    pdl_entry();
     int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * 256;
     for (; i < n; i += stride) {
@@ -19,6 +20,7 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
 }
 
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n) {
+    pdl_entry();
     int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * 256;
     for (; i < n; i += stride) y[i] = __float2bfloat16_rn(x[i]);
@@ -26,6 +28,7 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
 
 // 8 elements per thread and iteration: two 16-byte loads, one 16-byte store (n % 8 == 0, aligned pointers)
 __global__ void __launch_bounds__(256) cast_bf16_vec_kernel(const float4* __restrict__ x, uint4* __restrict__ y, int64_t n8) {
+    pdl_entry();
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n8; i += (int64_t)gridDim.x * 256) {
         const float4 a = x[2 * i], b = x[2 * i + 1];
         __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
@@ -38,6 +41,7 @@ __global__ void __launch_bounds__(256) cast_bf16_vec_kernel(const float4* __rest
 }
 
 __global__ void __launch_bounds__(256) scale_kernel(float* __restrict__ x, float a, int64_t n) {
+    pdl_entry();
     int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * 256;
     for (; i < n; i += stride) x[i] *= a;
@@ -46,6 +50,7 @@ __global__ void __launch_bounds__(256) scale_kernel(float* __restrict__ x, float
 // x[b, t, :] = x[b, t, :] * a + pe[t, :]   (absolute sinusoid positions added to the scaled embedding)
 __global__ void __launch_bounds__(256) add_pos_enc_kernel(float* __restrict__ x, const float* __restrict__ pe, float a,
                                                           int64_t n, int64_t TD) {
+    pdl_entry();
     int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * 256;
     for (; i < n; i += stride) x[i] = fmaf(x[i], a, __ldg(pe + i % TD));
@@ -57,6 +62,7 @@ constexpr int MAXRECT = 32;
 struct MaskRects { int nf, nt; int f0[MAXRECT], f1[MAXRECT], t0[MAXRECT], t1[MAXRECT]; };
 
 __global__ void __launch_bounds__(256) mask_rects_kernel(float* __restrict__ x, int64_t n, int T, int F, const MaskRects m) {
+    pdl_entry();
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
         const int f = (int)(i % F);
         const int t = (int)((i / F) % T);
@@ -69,6 +75,7 @@ __global__ void __launch_bounds__(256) mask_rects_kernel(float* __restrict__ x, 
 
 // column sums of a row-major [M, N] fp32 matrix: block = 32 columns x 8 row slices
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, float* __restrict__ y, int M, int N) {
+    pdl_entry();
     __shared__ float part[8][33];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31), rs = threadIdx.x >> 5;
     float acc = 0.f;
@@ -86,6 +93,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
 // TransformerXL sinusoid table (positional_embedding.py:135-138): row r <-> position -(r+1):
 // tab[r, i] = sin(-(r+1) * inv_freq[i]) for i < d/2, cos(-(r+1) * inv_freq[i - d/2]) otherwise.
 __global__ void __launch_bounds__(256) xl_pos_table_kernel(const float* __restrict__ inv_freq, float* __restrict__ tab, int rows, int d) {
+    pdl_entry();
     const int half = d / 2;
     const int64_t n = (int64_t)rows * d;
     for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < n; e += (int64_t)gridDim.x * 256) {
@@ -110,7 +118,7 @@ static unsigned ew_grid(int64_t n) {
 extern "C" nsp_status nsp_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {
     NSP_CHECK_ARG(x && hi && lo && n >= 0, "split_tf32: bad arguments");
     if (n == 0) return NSP_OK;
-    split_tf32_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, hi, lo, n);
+    launch_k(split_tf32_kernel, dim3(ew_grid(n)), dim3(256), 0, (cudaStream_t)stream, x, hi, lo, n);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }
@@ -119,9 +127,9 @@ extern "C" nsp_status nsp_cast_f32_to_bf16(const float* x, void* y, int64_t n, v
     NSP_CHECK_ARG(x && y && n >= 0, "cast_f32_to_bf16: bad arguments");
     if (n == 0) return NSP_OK;
     if (n % 8 == 0 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0)
-        cast_bf16_vec_kernel<<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>((const float4*)x, (uint4*)y, n / 8);
+        launch_k(cast_bf16_vec_kernel, dim3(ew_grid(n / 8)), dim3(256), 0, (cudaStream_t)stream, (const float4*)x, (uint4*)y, n / 8);
     else
-        cast_bf16_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n);
+        launch_k(cast_bf16_kernel, dim3(ew_grid(n)), dim3(256), 0, (cudaStream_t)stream, x, (__nv_bfloat16*)y, n);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }
@@ -129,7 +137,7 @@ extern "C" nsp_status nsp_cast_f32_to_bf16(const float* x, void* y, int64_t n, v
 extern "C" nsp_status nsp_scale_inplace(float* x, float a, int64_t n, void* stream) {
     NSP_CHECK_ARG(x && n >= 0, "scale_inplace: bad arguments");
     if (n == 0) return NSP_OK;
-    scale_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, a, n);
+    launch_k(scale_kernel, dim3(ew_grid(n)), dim3(256), 0, (cudaStream_t)stream, x, a, n);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }
@@ -145,7 +153,7 @@ extern "C" nsp_status nsp_mask_rects(float* x, int B, int T, int F, const int32_
     m.nf = n_freq; m.nt = n_time;
     for (int r = 0; r < n_freq; ++r) { m.f0[r] = freq_rects[2 * r]; m.f1[r] = freq_rects[2 * r + 1]; }
     for (int r = 0; r < n_time; ++r) { m.t0[r] = time_rects[2 * r]; m.t1[r] = time_rects[2 * r + 1]; }
-    mask_rects_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, n, T, F, m);
+    launch_k(mask_rects_kernel, dim3(ew_grid(n)), dim3(256), 0, (cudaStream_t)stream, x, n, T, F, m);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }
@@ -154,21 +162,21 @@ extern "C" nsp_status nsp_add_pos_enc(float* x, const float* pe, float a, int B,
     NSP_CHECK_ARG(x && pe && B >= 0 && T >= 0 && D > 0, "add_pos_enc: bad arguments");
     const int64_t n = (int64_t)B * T * D;
     if (n == 0) return NSP_OK;
-    add_pos_enc_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, pe, a, n, (int64_t)T * D);
+    launch_k(add_pos_enc_kernel, dim3(ew_grid(n)), dim3(256), 0, (cudaStream_t)stream, x, pe, a, n, (int64_t)T * D);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }
 
 extern "C" nsp_status nsp_colsum(const float* x, float* y, int M, int N, void* stream) {
     NSP_CHECK_ARG(x && y && M > 0 && N > 0, "colsum: bad arguments");
-    colsum_kernel<<<(unsigned)ceil_div(N, 32), 256, 0, (cudaStream_t)stream>>>(x, y, M, N);
+    launch_k(colsum_kernel, dim3((unsigned)ceil_div(N, 32)), dim3(256), 0, (cudaStream_t)stream, x, y, M, N);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }
 
 extern "C" nsp_status nsp_xl_pos_table(const float* inv_freq, float* table, int rows, int d, void* stream) {
     NSP_CHECK_ARG(inv_freq && table && rows > 0 && d > 0 && d % 2 == 0, "xl_pos_table: bad arguments");
-    xl_pos_table_kernel<<<ew_grid((int64_t)rows * d), 256, 0, (cudaStream_t)stream>>>(inv_freq, table, rows, d);
+    launch_k(xl_pos_table_kernel, dim3(ew_grid((int64_t)rows * d)), dim3(256), 0, (cudaStream_t)stream, inv_freq, table, rows, d);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }
@@ -179,6 +187,7 @@ namespace {
 template <typename TO>
 __global__ void __launch_bounds__(256) joint_tanh_kernel(const float* __restrict__ enc, const float* __restrict__ dec,
                                                          TO* __restrict__ out, int B, int T, int U1, int J) {
+    pdl_entry();
     const int64_t n4 = (int64_t)B * T * U1 * (J / 4);
     for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < n4; e += (int64_t)gridDim.x * 256) {
         const int j4 = (int)(e % (J / 4));
@@ -205,8 +214,8 @@ extern "C" nsp_status nsp_rnnt_joint_tanh(const float* enc, const float* dec, vo
                                           int J, void* stream) {
     NSP_CHECK_ARG(enc && dec && out && B > 0 && T > 0 && U1 > 0 && J > 0 && J % 4 == 0, "rnnt_joint_tanh: bad arguments");
     const int64_t n4 = (int64_t)B * T * U1 * (J / 4);
-    if (out_bf16) nsp::joint_tanh_kernel<__nv_bfloat16><<<ew_grid(n4), 256, 0, (cudaStream_t)stream>>>(enc, dec, (__nv_bfloat16*)out, B, T, U1, J);
-    else nsp::joint_tanh_kernel<float><<<ew_grid(n4), 256, 0, (cudaStream_t)stream>>>(enc, dec, (float*)out, B, T, U1, J);
+    if (out_bf16) launch_k(nsp::joint_tanh_kernel<__nv_bfloat16>, dim3(ew_grid(n4)), dim3(256), 0, (cudaStream_t)stream, enc, dec, (__nv_bfloat16*)out, B, T, U1, J);
+    else launch_k(nsp::joint_tanh_kernel<float>, dim3(ew_grid(n4)), dim3(256), 0, (cudaStream_t)stream, enc, dec, (float*)out, B, T, U1, J);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }

@@ -36,6 +36,7 @@ constexpr int TW = 16;   // tile width (frequency bins)
 // 256 threads; thread = (position group of 4 consecutive bins) x (4 output channels)
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) conv3x3_kernel(Conv3Params p) {
+    pdl_entry();
     extern __shared__ float sm[];
     const int CI = p.CI, CO = p.CO;
     const int ncg = CO / 4;                 // channel groups
@@ -127,6 +128,7 @@ struct PoolParams {
 // max-pool kernel=stride=(pt,pf), padding 0, ceil_mode=True (conv.py:330-337): edge windows are clipped
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) maxpool_kernel(PoolParams p) {
+    pdl_entry();
     const int64_t n = (int64_t)p.B * p.To * p.Fo_keep * p.C;
     for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < n; e += (int64_t)gridDim.x * 256) {
         int c = (int)(e % p.C);
@@ -155,6 +157,7 @@ __global__ void __launch_bounds__(256) maxpool_kernel(PoolParams p) {
 // 2 first frame (DropSubsampler :97-126), 3 sum (AddSubsampler :129-172)
 template <typename T>
 __global__ void __launch_bounds__(256) pool_time_kernel(const T* x, T* y, int B, int Tin, int Tout, int D, int factor, int mode) {
+    pdl_entry();
     const int64_t n = (int64_t)B * Tout * D;
     for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < n; e += (int64_t)gridDim.x * 256) {
         int c = (int)(e % D);
@@ -206,7 +209,7 @@ extern "C" nsp_status nsp_conv3x3_relu_fwd(int in_bf16, int out_bf16, const void
     do {                                                                                                 \
         auto kern = conv3x3_kernel<TI, TO>;                                                              \
         NSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        kern<<<grid, 256, smem, st>>>(p);                                                                \
+        launch_k(kern, dim3(grid), dim3(256), smem, st, p);                                                                \
     } while (0)
     if (!in_bf16 && !out_bf16) NSP_C3(float, float);
     else if (!in_bf16 && out_bf16) NSP_C3(float, __nv_bfloat16);
@@ -228,10 +231,10 @@ extern "C" nsp_status nsp_maxpool2d_fwd(int in_bf16, int out_bf16, const void* x
     p.out_chmajor = out_chmajor;
     const int64_t n = (int64_t)B * p.To * p.Fo_keep * C;
     cudaStream_t st = (cudaStream_t)stream;
-    if (!in_bf16 && !out_bf16) maxpool_kernel<float, float><<<fe_grid(n), 256, 0, st>>>(p);
-    else if (in_bf16 && out_bf16) maxpool_kernel<__nv_bfloat16, __nv_bfloat16><<<fe_grid(n), 256, 0, st>>>(p);
-    else if (!in_bf16) maxpool_kernel<float, __nv_bfloat16><<<fe_grid(n), 256, 0, st>>>(p);
-    else maxpool_kernel<__nv_bfloat16, float><<<fe_grid(n), 256, 0, st>>>(p);
+    if (!in_bf16 && !out_bf16) launch_k(maxpool_kernel<float, float>, dim3(fe_grid(n)), dim3(256), 0, st, p);
+    else if (in_bf16 && out_bf16) launch_k(maxpool_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(fe_grid(n)), dim3(256), 0, st, p);
+    else if (!in_bf16) launch_k(maxpool_kernel<float, __nv_bfloat16>, dim3(fe_grid(n)), dim3(256), 0, st, p);
+    else launch_k(maxpool_kernel<__nv_bfloat16, float>, dim3(fe_grid(n)), dim3(256), 0, st, p);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }
@@ -241,8 +244,8 @@ extern "C" nsp_status nsp_pool_time_fwd(int is_bf16, const void* x, void* y, int
     const int To = ceil_div(T, factor);
     const int64_t n = (int64_t)B * To * D;
     cudaStream_t st = (cudaStream_t)stream;
-    if (is_bf16) pool_time_kernel<__nv_bfloat16><<<fe_grid(n), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, B, T, To, D, factor, mode);
-    else pool_time_kernel<float><<<fe_grid(n), 256, 0, st>>>((const float*)x, (float*)y, B, T, To, D, factor, mode);
+    if (is_bf16) launch_k(pool_time_kernel<__nv_bfloat16>, dim3(fe_grid(n)), dim3(256), 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, B, T, To, D, factor, mode);
+    else launch_k(pool_time_kernel<float>, dim3(fe_grid(n)), dim3(256), 0, st, (const float*)x, (float*)y, B, T, To, D, factor, mode);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }

@@ -26,6 +26,7 @@ constexpr int WTH = 8, WTW = 16;
 
 template <typename TA, typename TZ>
 __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(ConvWgradParams p) {
+    pdl_entry();
     extern __shared__ float sm[];
     const int CI = p.CI, CO = p.CO;
     const int cip = CI + 1;
@@ -107,6 +108,7 @@ template <typename TZ>
 __global__ void __launch_bounds__(256) conv3x3_wgrad_c1_kernel(const float* __restrict__ x, const TZ* __restrict__ dz,
                                                                float* __restrict__ dw, float* __restrict__ dbias,
                                                                int B, int T, int F) {
+    pdl_entry();
     extern __shared__ float xs[];                 // [3][F + 2]
     __shared__ float red[10][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -160,8 +162,8 @@ extern "C" nsp_status nsp_conv3x3_wgrad(int a_bf16, int dz_bf16, const void* a, 
         int grid1 = 4 * num_sms();
         if ((int64_t)B * T < grid1) grid1 = B * T;
         const size_t sm1 = sizeof(float) * 3 * (size_t)(F + 2);
-        if (dz_bf16) conv3x3_wgrad_c1_kernel<__nv_bfloat16><<<grid1, 256, sm1, (cudaStream_t)stream>>>((const float*)a, (const __nv_bfloat16*)dz, dw, dbias, B, T, F);
-        else conv3x3_wgrad_c1_kernel<float><<<grid1, 256, sm1, (cudaStream_t)stream>>>((const float*)a, (const float*)dz, dw, dbias, B, T, F);
+        if (dz_bf16) launch_k(conv3x3_wgrad_c1_kernel<__nv_bfloat16>, dim3(grid1), dim3(256), sm1, (cudaStream_t)stream, (const float*)a, (const __nv_bfloat16*)dz, dw, dbias, B, T, F);
+        else launch_k(conv3x3_wgrad_c1_kernel<float>, dim3(grid1), dim3(256), sm1, (cudaStream_t)stream, (const float*)a, (const float*)dz, dw, dbias, B, T, F);
         NSP_LAUNCH_OK();
         return NSP_OK;
     }
@@ -177,7 +179,7 @@ extern "C" nsp_status nsp_conv3x3_wgrad(int a_bf16, int dz_bf16, const void* a, 
         auto kern = conv3x3_wgrad_kernel<TA, TZ>;                                                                         \
         static size_t attr = 0;                                                                                           \
         if (smem > 48 * 1024 && smem > attr) { NSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; } \
-        kern<<<grid, 256, smem, st>>>(p);                                                                                 \
+        launch_k(kern, dim3(grid), dim3(256), smem, st, p);                                                                                 \
     } while (0)
     if (a_bf16 && dz_bf16) NSP_WG(__nv_bfloat16, __nv_bfloat16);
     else if (!a_bf16 && dz_bf16) NSP_WG(float, __nv_bfloat16);

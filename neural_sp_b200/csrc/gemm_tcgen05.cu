@@ -145,6 +145,7 @@ __device__ __forceinline__ void store_pre(void* base, int64_t ld, int row, int c
 
 template <typename TIn, int BN, int STAGES, int ACT, bool GLU, bool RES, bool OUTBF16>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs g) {
+    pdl_launch_dependents();      // PDL: the next kernel may start its prologue; ours overlaps the previous kernel's tail
     constexpr bool kBF16 = sizeof(TIn) == 2;
     constexpr int BK = KBYTES / (int)sizeof(TIn);        // 64 (bf16) or 32 (tf32)
     constexpr int UK = 32 / (int)sizeof(TIn);            // K per tcgen05.mma: 16 (bf16) or 8 (tf32)
@@ -185,6 +186,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    pdl_wait();                    // the previous grid is complete: operands / residuals / outputs may be touched from here
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -410,7 +412,7 @@ nsp_status launch_gemm(const GemmMaps& maps, const GemmArgs& g, cudaStream_t st)
     const int bn_out = GLU ? BN / 2 : BN;
     const int tiles = ceil_div(g.M, BM) * ceil_div(nout, bn_out);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, NTHREADS, smem, st>>>(maps, g);
+    launch_k(kern, dim3(grid), dim3(NTHREADS), smem, st, maps, g);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }

@@ -123,23 +123,15 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
                  :: "r"(tc::smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 
-// bounded mbarrier wait: a lost arrival becomes an error with a message instead of a hung GPU
-__device__ __forceinline__ void bwait(uint64_t* bar, uint32_t parity, int what) {
-    if (tc::mbar_try_wait(bar, parity)) return;
-    const long long deadline = clock64() + 4000000000LL;
-    while (!tc::mbar_try_wait(bar, parity)) {
-        if (clock64() > deadline) {
-            printf("gemm_ts_kernel: mbarrier wait %d timed out (block %d thread %d)\n", what, blockIdx.x, threadIdx.x);
-            __trap();
-        }
-    }
-}
+// bounded mbarrier wait (tc_common.cuh: bare spin + one counter, the clock is read once per 4096 failed polls)
+__device__ __forceinline__ void bwait(uint64_t* bar, uint32_t parity, int) { tc::mbar_wait(bar, parity); }
 
 // TWO = CTA pair (cluster of 2, cta_group::2): the pair computes a 256 x BN tile; each CTA stages its own 128 rows of A and
 // BN/2 rows of W per k-block (half the L2->SMEM operand traffic per FLOP of the single-CTA tile), the leader CTA issues
 // the M = 256 MMAs for both, and each CTA runs the epilogue of its own 128 accumulator rows.
 template <int BN, int STAGES, int ACT, bool GLU, bool RES, bool OUTBF16, bool TWO>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_ts_kernel(const __grid_constant__ TsMaps maps, const TsArgs g) {
+    pdl_launch_dependents();      // PDL: the next kernel may start its prologue; ours overlaps the previous kernel's tail
     static_assert(!(TWO && GLU), "GLU is single-CTA only");
     constexpr int A_BYTES = BM * KBYTES;
     constexpr int B_BYTES = (TWO ? BN / 2 : BN) * KBYTES;
@@ -197,6 +189,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ts_kernel(const __grid_const
     else __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    pdl_wait();                    // the previous grid is complete: operands / residuals / outputs may be touched from here
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -460,15 +453,17 @@ nsp_status launch_ts(const TsMaps& maps, const TsArgs& g, cudaStream_t st) {
         cfg.blockDim = dim3(NTHREADS);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = st;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        cfg.numAttrs = pdl_enabled() ? 2 : 1;
         NSP_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, maps, g));
     } else {
         const int grid = tiles < num_sms() ? tiles : num_sms();
-        kern<<<grid, NTHREADS, smem, st>>>(maps, g);
+        launch_k(kern, dim3(grid), dim3(NTHREADS), smem, st, maps, g);
         NSP_LAUNCH_OK();
     }
     ++g_ts_launches;

@@ -55,6 +55,7 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 
 template <typename TIn, int BN, int STAGES, bool TMAEPI>
 __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradArgs g) {
+    pdl_launch_dependents();      // PDL: the next kernel may start its prologue; ours overlaps the previous kernel's tail
     constexpr bool kBF16 = sizeof(TIn) == 2;
     constexpr int CHUNK = 128 / (int)sizeof(TIn);          // elements per 128-byte column chunk: 64 / 32
     constexpr int A_BOXES = WG_BM / CHUNK, B_BOXES = BN / CHUNK;
@@ -97,6 +98,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    pdl_wait();                    // the previous grid is complete: operands / residuals / outputs may be touched from here
 
     if (warp == 0) {
         if (lane == 0) {
@@ -232,7 +234,7 @@ nsp_status launch_wgrad(const WgradMaps& maps, WgradArgs& g, cudaStream_t st) {
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     g.splits = splits;
-    kern<<<(unsigned)(tiles * splits), 192, smem, st>>>(maps, g);
+    launch_k(kern, dim3((unsigned)(tiles * splits)), dim3(192), smem, st, maps, g);
     NSP_LAUNCH_OK();
     if (TMAEPI) ++g_wgrad_tma_launches;
     return NSP_OK;

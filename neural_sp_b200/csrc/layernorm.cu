@@ -14,6 +14,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, float in_scale, float* __restrict__ y, int64_t ldy,
                                                         __nv_bfloat16* __restrict__ yb, int64_t ldyb, int M, int D) {
+    pdl_entry();
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= M) return;
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(256) layernorm_generic_kernel(const float* __r
                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                 float eps, float in_scale, float* __restrict__ y, int64_t ldy,
                                                                 __nv_bfloat16* __restrict__ yb, int64_t ldyb, int D) {
+    pdl_entry();
     __shared__ float scratch[32];
     const int64_t row = blockIdx.x;
     const float* xr = x + row * ldx;
@@ -117,17 +119,17 @@ extern "C" nsp_status nsp_layernorm_fwd(const float* x, int64_t ldx, const float
                       ((uintptr_t)gamma % 16 == 0) && ((uintptr_t)beta % 16 == 0);
     const unsigned grid = (unsigned)ceil_div(M, 8);
     __nv_bfloat16* yb = (__nv_bfloat16*)y_bf16;
-#define NSP_LN(VPT, VEC) layernorm_kernel<VPT, VEC><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, eps, in_scale, y, ldy, yb, ldyb, M, D)
+#define NSP_LN(VPT, VEC) launch_k(layernorm_kernel<VPT, VEC>, dim3(grid), dim3(256), 0, st, x, ldx, gamma, beta, eps, in_scale, y, ldy, yb, ldyb, M, D)
     if (vec4) {
         const int vpt = ceil_div(D / 4, 32);
         if (vpt <= 1) NSP_LN(1, 4); else if (vpt <= 2) NSP_LN(2, 4); else if (vpt <= 4) NSP_LN(4, 4);
         else if (vpt <= 8) NSP_LN(8, 4); else if (vpt <= 16) NSP_LN(16, 4);
-        else layernorm_generic_kernel<<<(unsigned)M, 256, 0, st>>>(x, ldx, gamma, beta, eps, in_scale, y, ldy, yb, ldyb, D);
+        else launch_k(layernorm_generic_kernel, dim3((unsigned)M), dim3(256), 0, st, x, ldx, gamma, beta, eps, in_scale, y, ldy, yb, ldyb, D);
     } else {
         const int vpt = ceil_div(D, 32);
         if (vpt <= 1) NSP_LN(1, 1); else if (vpt <= 2) NSP_LN(2, 1); else if (vpt <= 4) NSP_LN(4, 1);
         else if (vpt <= 8) NSP_LN(8, 1); else if (vpt <= 16) NSP_LN(16, 1); else if (vpt <= 32) NSP_LN(32, 1);
-        else layernorm_generic_kernel<<<(unsigned)M, 256, 0, st>>>(x, ldx, gamma, beta, eps, in_scale, y, ldy, yb, ldyb, D);
+        else launch_k(layernorm_generic_kernel, dim3((unsigned)M), dim3(256), 0, st, x, ldx, gamma, beta, eps, in_scale, y, ldy, yb, ldyb, D);
     }
 #undef NSP_LN
     NSP_LAUNCH_OK();

@@ -45,6 +45,7 @@ struct LstmParams {
 __device__ __forceinline__ float sigmoid_exact(float x) { return 1.f / (1.f + expf(-x)); }
 
 __global__ void __launch_bounds__(256, 1) lstm_seq_kernel(LstmParams p) {
+    pdl_entry();
     extern __shared__ float sm[];
     const int H = p.H;
     const int WP = H + 4;                              // padded row pitch (16-byte aligned, bank-staggered)
@@ -208,6 +209,7 @@ struct LstmBwdParams {
 constexpr int KS = 8;             // k splits of the 4H-long reduction in phase c
 
 __global__ void __launch_bounds__(256, 1) lstm_seq_bwd_kernel(LstmBwdParams p) {
+    pdl_entry();
     extern __shared__ float sm[];
     const int H = p.H, H4 = 4 * p.H;
     const int WP = H4 + 4;

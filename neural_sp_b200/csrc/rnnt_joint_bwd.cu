@@ -17,6 +17,7 @@ constexpr int LSB_VPT = 8;     // values per thread kept in registers: rows up t
 
 __global__ void __launch_bounds__(256) log_softmax_bwd_kernel(const float* __restrict__ lp, float* __restrict__ dlp, int V,
                                                               const float* __restrict__ gscale) {
+    pdl_entry();
     __shared__ float scratch[32];
     const int64_t row = blockIdx.x;
     const float* lr = lp + row * V;
@@ -53,6 +54,7 @@ template <> __device__ __forceinline__ float ldj<__nv_bfloat16>(const __nv_bfloa
 template <typename T>
 __global__ void __launch_bounds__(256) joint_bwd_enc_kernel(const T* __restrict__ h, const T* __restrict__ dh,
                                                             float* __restrict__ de, int64_t BT, int U1, int J) {
+    pdl_entry();
     const int64_t n = BT * J;
     for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < n; e += (int64_t)gridDim.x * 256) {
         const int j = (int)(e % J);
@@ -72,6 +74,7 @@ __global__ void __launch_bounds__(256) joint_bwd_enc_kernel(const T* __restrict_
 template <typename T>
 __global__ void __launch_bounds__(256) joint_bwd_dec_kernel(const T* __restrict__ h, const T* __restrict__ dh,
                                                             float* __restrict__ dd, int B, int Tn, int U1, int J) {
+    pdl_entry();
     const int64_t n = (int64_t)B * U1 * J;
     for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < n; e += (int64_t)gridDim.x * 256) {
         const int j = (int)(e % J);
@@ -101,7 +104,7 @@ using namespace nsp;
 
 extern "C" nsp_status nsp_log_softmax_bwd(const float* lp, float* dlp, int64_t rows, int V, const float* gscale, void* stream) {
     NSP_CHECK_ARG(lp && dlp && rows > 0 && V > 0 && rows < (1ll << 31), "log_softmax_bwd: bad arguments");
-    log_softmax_bwd_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(lp, dlp, V, gscale);
+    launch_k(log_softmax_bwd_kernel, dim3((unsigned)rows), dim3(256), 0, (cudaStream_t)stream, lp, dlp, V, gscale);
     NSP_LAUNCH_OK();
     return NSP_OK;
 }
@@ -112,11 +115,11 @@ extern "C" nsp_status nsp_rnnt_joint_tanh_bwd(int is_bf16, const void* h, const 
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t BT = (int64_t)B * T;
     if (is_bf16) {
-        joint_bwd_enc_kernel<__nv_bfloat16><<<jb_grid(BT * J), 256, 0, st>>>((const __nv_bfloat16*)h, (const __nv_bfloat16*)dh, de, BT, U1, J);
-        joint_bwd_dec_kernel<__nv_bfloat16><<<jb_grid((int64_t)B * U1 * J), 256, 0, st>>>((const __nv_bfloat16*)h, (const __nv_bfloat16*)dh, dd, B, T, U1, J);
+        launch_k(joint_bwd_enc_kernel<__nv_bfloat16>, dim3(jb_grid(BT * J)), dim3(256), 0, st, (const __nv_bfloat16*)h, (const __nv_bfloat16*)dh, de, BT, U1, J);
+        launch_k(joint_bwd_dec_kernel<__nv_bfloat16>, dim3(jb_grid((int64_t)B * U1 * J)), dim3(256), 0, st, (const __nv_bfloat16*)h, (const __nv_bfloat16*)dh, dd, B, T, U1, J);
     } else {
-        joint_bwd_enc_kernel<float><<<jb_grid(BT * J), 256, 0, st>>>((const float*)h, (const float*)dh, de, BT, U1, J);
-        joint_bwd_dec_kernel<float><<<jb_grid((int64_t)B * U1 * J), 256, 0, st>>>((const float*)h, (const float*)dh, dd, B, T, U1, J);
+        launch_k(joint_bwd_enc_kernel<float>, dim3(jb_grid(BT * J)), dim3(256), 0, st, (const float*)h, (const float*)dh, de, BT, U1, J);
+        launch_k(joint_bwd_dec_kernel<float>, dim3(jb_grid((int64_t)B * U1 * J)), dim3(256), 0, st, (const float*)h, (const float*)dh, dd, B, T, U1, J);
     }
     NSP_LAUNCH_OK();
     return NSP_OK;

@@ -30,6 +30,7 @@ struct RnntParams {
 };
 
 __global__ void __launch_bounds__(256) rnnt_gather_kernel(RnntParams p) {
+    pdl_entry();
     const int64_t n = (int64_t)p.B * p.T * p.U1;
     for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < n; e += (int64_t)gridDim.x * 256) {
         const int u = (int)(e % p.U1);
@@ -50,6 +51,7 @@ __global__ void __launch_bounds__(256) rnnt_gather_kernel(RnntParams p) {
 }
 
 __global__ void __launch_bounds__(1024) rnnt_lattice_kernel(RnntParams p, int HALF) {
+    pdl_entry();
     extern __shared__ float sm[];      // alpha: [2][U1], beta: [2][U1]
     __shared__ float s_nll;
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -148,6 +150,7 @@ __global__ void __launch_bounds__(1024) rnnt_lattice_kernel(RnntParams p, int HA
 // dense gradient: one warp per lattice cell row of V entries
 template <int VEC>
 __global__ void __launch_bounds__(256) rnnt_grad_kernel(RnntParams p) {
+    pdl_entry();
     const int lane = threadIdx.x & 31;
     const int64_t cell = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int64_t ncell = (int64_t)p.B * p.T * p.U1;
@@ -192,6 +195,7 @@ __global__ void __launch_bounds__(256) rnnt_grad_kernel(RnntParams p) {
 // gradient of the loss) or null.  Warp per lattice cell.
 template <int VEC, typename TO>
 __global__ void __launch_bounds__(256) rnnt_grad_logits_kernel(RnntParams p, const float* __restrict__ gscale, TO* dz) {
+    pdl_entry();
     const int lane = threadIdx.x & 31;
     const int64_t cell = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int64_t ncell = (int64_t)p.B * p.T * p.U1;
@@ -251,6 +255,7 @@ __global__ void __launch_bounds__(256) rnnt_grad_logits_kernel(RnntParams p, con
 }
 
 __global__ void rnnt_finalize_kernel(RnntParams p) {
+    pdl_entry();
     __shared__ float scratch[32];
     float a = 0.f;
     for (int i = threadIdx.x; i < p.B; i += 256) a += p.nll[i];
@@ -288,18 +293,18 @@ extern "C" nsp_status nsp_rnnt_loss_fwd_bwd(const float* log_probs, int B, int T
     const int64_t ncell = (int64_t)B * T * U1;
     {
         int64_t blocks = ceil_div64(ncell, 256), cap = (int64_t)num_sms() * 16;
-        rnnt_gather_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(p);
+        launch_k(rnnt_gather_kernel, dim3((unsigned)(blocks < cap ? blocks : cap)), dim3(256), 0, st, p);
         NSP_LAUNCH_OK();
     }
     const int half = (int)align_up((size_t)U1, 32);
-    rnnt_lattice_kernel<<<B, 2 * half, (size_t)4 * U1 * sizeof(float), st>>>(p, half);
+    launch_k(rnnt_lattice_kernel, dim3(B), dim3(2 * half), (size_t)4 * U1 * sizeof(float), st, p, half);
     NSP_LAUNCH_OK();
-    rnnt_finalize_kernel<<<1, 256, 0, st>>>(p);
+    launch_k(rnnt_finalize_kernel, dim3(1), dim3(256), 0, st, p);
     NSP_LAUNCH_OK();
     if (grad) {
         const unsigned grid = (unsigned)ceil_div64(ncell, 8);
-        if (V % 4 == 0 && ((uintptr_t)grad % 16 == 0)) rnnt_grad_kernel<4><<<grid, 256, 0, st>>>(p);
-        else rnnt_grad_kernel<1><<<grid, 256, 0, st>>>(p);
+        if (V % 4 == 0 && ((uintptr_t)grad % 16 == 0)) launch_k(rnnt_grad_kernel<4>, dim3(grid), dim3(256), 0, st, p);
+        else launch_k(rnnt_grad_kernel<1>, dim3(grid), dim3(256), 0, st, p);
         NSP_LAUNCH_OK();
     }
     return NSP_OK;
@@ -324,11 +329,11 @@ extern "C" nsp_status nsp_rnnt_grad_logits(const float* log_probs, int B, int T,
     const unsigned grid = (unsigned)ceil_div64((int64_t)B * T * U1, 8);
     const bool vec = V % 4 == 0 && ((uintptr_t)log_probs % 16 == 0) && ((uintptr_t)dz % 16 == 0);
     if (dz_bf16) {
-        if (vec) rnnt_grad_logits_kernel<4, __nv_bfloat16><<<grid, 256, 0, st>>>(p, gscale, (__nv_bfloat16*)dz);
-        else rnnt_grad_logits_kernel<1, __nv_bfloat16><<<grid, 256, 0, st>>>(p, gscale, (__nv_bfloat16*)dz);
+        if (vec) launch_k(rnnt_grad_logits_kernel<4, __nv_bfloat16>, dim3(grid), dim3(256), 0, st, p, gscale, (__nv_bfloat16*)dz);
+        else launch_k(rnnt_grad_logits_kernel<1, __nv_bfloat16>, dim3(grid), dim3(256), 0, st, p, gscale, (__nv_bfloat16*)dz);
     } else {
-        if (vec) rnnt_grad_logits_kernel<4, float><<<grid, 256, 0, st>>>(p, gscale, (float*)dz);
-        else rnnt_grad_logits_kernel<1, float><<<grid, 256, 0, st>>>(p, gscale, (float*)dz);
+        if (vec) launch_k(rnnt_grad_logits_kernel<4, float>, dim3(grid), dim3(256), 0, st, p, gscale, (float*)dz);
+        else launch_k(rnnt_grad_logits_kernel<1, float>, dim3(grid), dim3(256), 0, st, p, gscale, (float*)dz);
     }
     NSP_LAUNCH_OK();
     return NSP_OK;

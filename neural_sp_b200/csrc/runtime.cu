@@ -1,6 +1,7 @@
 // Library-wide plumbing: error strings, device query, version.
 #include <stdarg.h>
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace nsp {
 static thread_local char g_err[512] = "";
@@ -10,6 +11,11 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("NSP_PDL"); return !(e && e[0] == '0'); }();
+    return on;
 }
 
 int num_sms() {

@@ -52,6 +52,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Wait that does not spin: try_wait with a suspend-time hint parks the thread in hardware until the phase completes or the
+// hint (ns) expires, so waiting warps leave the issue slots of their scheduler to the warps that have work (the CTC lattice
+// warps ran 3-5x slower next to spinning producer / consumer waits: profiles/README.md round 2).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+    uint32_t polls = 0;
+    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+        if (++polls > 400000u) asm volatile("trap;");          // > 2 s even if every poll returned after 5 us
+    }
+}
+
 // ---------------- TMA ----------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" :: "l"(m) : "memory");

@@ -35,6 +35,7 @@ def profile_stop():
 
 
 SHAPE_TAGS = False    # bench.py --shape-profile: key the GEMM records by shape
+LAST_CTC_WS = None
 
 
 def _run(name, fn, *args, flops=0, nbytes=0, tag=None, shape=None):
@@ -113,6 +114,9 @@ def ctc_loss_fwd_bwd(logits, labels, elens, ylens, blank=0, lsm_prob=0.0):
                                    ptr(labels), Lmax, ptr(elens), ptr(ylens), int(blank), float(lsm_prob),
                                    ptr(nll), ptr(loss), ptr(grad), ptr(ws), ws_bytes, current_stream_ptr(),
          nbytes=8.0 * B * T * V, tag="ctc_loss")
+    if os.environ.get("NSP_CTC_DEBUG"):
+        global LAST_CTC_WS
+        LAST_CTC_WS = ws                  # bring-up: profiles/prof_ctc.py reads the kernel's trace words from the tail
     return loss, nll, grad
 
 
