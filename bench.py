@@ -33,7 +33,24 @@ WORKLOADS = {
     # BASELINE.json configs[1]: Conformer-M 12L d256 ff1024 H4
     "conformer_m_ctc": dict(n_layers=12, d_model=256, d_ff=1024, n_heads=4, kernel_size=15, B=32, T=1000, vocab=10000,
                             subsample="1_1_1_2_1_1_1_2_1_1_1_1", poolings="(1,1)_(2,2)"),
+    # BASELINE.json configs[0] at bench scale: BLSTM(2 x 256) + CTC, vocab 32, T = 200 (test/decoders/test_ctc shapes), B = 32
+    "c1_blstm_ctc": dict(kind="rnn", loss="ctc", enc_type="blstm", n_units=256, n_layers=2, conv=None, B=32, T=200, vocab=32,
+                         d_model=512, label_rate=0.45 / 1, what="BLSTM 2x256 (concat) + CTC V=32"),
+    # BASELINE.json configs[3]: conv + UniLSTM(6 x 1024) encoder + RNN-Transducer (pred. net 2 x 1024, joint 640, V = 1000;
+    # lstm_rnnt_bpe1k.yaml with enc_n_layers 6 / dec_bottleneck_dim 640), T = 1000 -> T' = 250, U = 56
+    "c4_lstm_rnnt": dict(kind="rnn", loss="rnnt", enc_type="conv_lstm", n_units=1024, n_layers=6, conv="(2,2)_(2,2)", B=32,
+                         T=1000, vocab=1000, d_model=1024, label_rate=0.45 / 8,
+                         what="conv 32_32 (2,2)_(2,2) + LSTM 6x1024 + RNN-T (pred 2x1024, joint 640, V=1000)"),
+    # BASELINE.json configs[4], encoder + CTC branch: conv + Transformer 24L d512 ff2048 H8 relative_xl, T = 3000 -> T' = 750
+    # (the Transformer decoder of the hybrid loss is SURVEY 8f-2, not built: the CTC branch carries ctc_weight of it)
+    "c5_transformer_t3000": dict(kind="transformer", loss="ctc", n_layers=24, d_model=512, d_ff=2048, n_heads=8, B=8, T=3000,
+                                 vocab=10000, poolings="(2,2)_(2,2)", label_rate=0.45 / 8,
+                                 what="conv 32_32 (2,2)_(2,2) + Transformer 24L d512 ff2048 H8 relative_xl + CTC fc512 V=10000"),
 }
+for _w in WORKLOADS.values():
+    _w.setdefault("kind", "conformer")
+    _w.setdefault("loss", "ctc")
+    _w.setdefault("label_rate", 0.45 / 8)
 
 
 def enc_args(w):
@@ -66,8 +83,74 @@ def synth_batch(w, B, seed, lengths="fixed"):
     xs = np.zeros((B, T, 80), np.float32)
     for b, n in enumerate(xlens):
         xs[b, :n] = rng.standard_normal((n, 80)).astype(np.float32)
-    ys = [rng.integers(4, w["vocab"], size=max(1, int(0.45 * n / 8))).tolist() for n in xlens]
+    ys = [rng.integers(4, w["vocab"], size=max(1, int(w.get("label_rate", 0.45 / 8) * n))).tolist() for n in xlens]
     return xs, xlens, ys
+
+
+def build_model(w, args, dev):
+    """The workload's encoder + loss head from the product package.  -> (enc, dec, loss_fn(eouts, elens, ys) -> 0-dim loss)."""
+    import torch
+    from neural_sp_b200.decoders.ctc import CTC
+    from neural_sp_b200.encoders.conv import ConvEncoder
+    torch.manual_seed(0)
+    if w["kind"] == "conformer":
+        from neural_sp_b200.encoders.conformer import ConformerEncoder
+        a = enc_args(w)
+        a["dropout"] = args.dropout
+        a["frontend_conv"] = ConvEncoder(**conv_args(w))
+        enc = ConformerEncoder(**a)
+        sd_synth, head_synth = synth_params(w)           # the weights every arm uses (strict: the reference's state_dict keys)
+        enc.load_state_dict(sd_synth, strict=True)
+        odim = w["d_model"]
+    elif w["kind"] == "transformer":
+        from neural_sp_b200.encoders.transformer import TransformerEncoder
+        nl = w["n_layers"]
+        conv = ConvEncoder(**dict(conv_args(w), bottleneck_dim=w["d_model"]))
+        enc = TransformerEncoder(input_dim=80, enc_type='conv_transformer', n_heads=w["n_heads"], n_layers=nl, n_layers_sub1=0,
+                                 n_layers_sub2=0, d_model=w["d_model"], d_ff=w["d_ff"], ffn_bottleneck_dim=0, ffn_activation='relu',
+                                 pe_type='relative_xl', layer_norm_eps=1e-12, last_proj_dim=0, dropout_in=0.0, dropout=args.dropout,
+                                 dropout_att=0.0, dropout_layer=0.0, subsample="_".join(["1"] * nl), subsample_type='max_pool',
+                                 n_stacks=1, n_splices=1, frontend_conv=conv, task_specific_layer=False, param_init='xavier_uniform',
+                                 clamp_len=-1, lookahead="_".join(["0"] * nl), chunk_size_left="0", chunk_size_current="0",
+                                 chunk_size_right="0", streaming_type='mask')
+        head_synth, odim = None, w["d_model"]
+    else:
+        from neural_sp_b200.encoders.rnn import RNNEncoder
+        nl = w["n_layers"]
+        conv = None
+        if w["conv"]:
+            conv = ConvEncoder(input_dim=80, in_channel=1, channels="32_32", kernel_sizes="(3,3)_(3,3)", strides="(1,1)_(1,1)",
+                               poolings=w["conv"], dropout=0.0, normalization='', residual=False, bottleneck_dim=0, param_init=0.1)
+        enc = RNNEncoder(input_dim=80, enc_type=w["enc_type"], n_units=w["n_units"], n_projs=0, last_proj_dim=0, n_layers=nl,
+                         n_layers_sub1=0, n_layers_sub2=0, dropout_in=0.0, dropout=args.dropout, subsample="_".join(["1"] * nl),
+                         subsample_type='drop', n_stacks=1, n_splices=1, frontend_conv=conv, bidir_sum_fwd_bwd=False,
+                         task_specific_layer=False, param_init=0.1, chunk_size_current="0", chunk_size_right="0", cnn_lookahead=True,
+                         rsp_prob=0.)
+        head_synth, odim = None, enc.output_dim
+    enc = enc.to(dev)
+    enc = enc.train() if args.step == "train" else enc.eval()
+    enc.set_precision(args.precision)
+    if w["loss"] == "ctc":
+        dec = CTC(eos=2, blank=0, enc_n_units=odim, vocab=w["vocab"], dropout=args.dropout, lsm_prob=0.1,
+                  fc_list=None if w["kind"] == "rnn" else "512")
+        if head_synth is not None:
+            dec.load_state_dict(head_synth, strict=True)
+        dec = dec.to(dev).train()
+        dec.set_precision(args.precision)
+
+        def loss_fn(eouts, elens, ys):
+            return dec(eouts, elens, ys)[0]
+    else:
+        from neural_sp_b200.decoders.rnn_transducer import RNNTransducer
+        dec = RNNTransducer({'eos': 2, 'unk': 1, 'pad': 3, 'blank': 0}, enc_n_units=odim, n_units=1024, n_projs=0, n_layers=2,
+                            bottleneck_dim=640, emb_dim=512, vocab=w["vocab"], dropout=args.dropout, dropout_emb=args.dropout,
+                            ctc_weight=0.0, ctc_lsm_prob=0.0, ctc_fc_list="", external_lm=None, global_weight=1.0,
+                            mtl_per_batch=False, param_init=0.1).to(dev).train()
+        dec.set_precision(args.precision)
+
+        def loss_fn(eouts, elens, ys):
+            return dec.forward_transducer(eouts, elens, ys).sum()
+    return enc, dec, loss_fn
 
 
 def flops_per_utt_fwd(w):
@@ -367,17 +450,23 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    cfg_common = {"workload": "%s: Conformer %dL d%d ff%d H%d k15 LN rel-pos clamp10, conv 32_32 %s, hier. max-pool, "
-                              "CTC fc512 V=%d lsm0.1; B=%d/GPU %s" % (args.workload, w["n_layers"], w["d_model"], w["d_ff"],
-                                                                        w["n_heads"], w["poolings"], w["vocab"], w["B"],
-                                                                        "T=%d fixed" % w["T"] if args.lengths == "fixed" else
-                                                                        "log-normal lengths 40..1600 (median 1200), padded to the longest"),
-                  "step": ("train: encoder_fwd + ctc_head + ctc_fwd_bwd + head_bwd + encoder_bwd + grad all-reduce + "
-                           "optimizer(%s)" % args.optimizer) if args.step == "train" else
-                          "fwd: encoder_fwd + ctc_head + ctc_fwd_bwd + head_bwd (no encoder backward)",
+    if w["kind"] == "conformer":
+        wl = "%s: Conformer %dL d%d ff%d H%d k15 LN rel-pos clamp10, conv 32_32 %s, hier. max-pool, CTC fc512 V=%d lsm0.1" % (
+            args.workload, w["n_layers"], w["d_model"], w["d_ff"], w["n_heads"], w["poolings"], w["vocab"])
+    else:
+        wl = "%s: %s" % (args.workload, w["what"])
+    cfg_common = {"workload": wl + "; B=%d/GPU %s" % (w["B"], "T=%d fixed" % w["T"] if args.lengths == "fixed" else
+                                                        "log-normal lengths 40..1600 (median 1200), padded to the longest"),
+                  "step": ("train: encoder_fwd + %s_head + %s_fwd_bwd + head_bwd + encoder_bwd + grad all-reduce + "
+                           "optimizer(%s)" % (w["loss"], w["loss"], args.optimizer)) if args.step == "train" else
+                          "fwd: encoder_fwd + %s_head + %s_fwd_bwd + head_bwd (no encoder backward)" % (w["loss"], w["loss"]),
                   "global_batch": w["B"] * world, "seq_len": w["T"], "parallelism": "dp%d" % world,
                   "dropout": args.dropout, "lengths": args.lengths}
 
+    if args.impl in ("reference", "eager") and w["kind"] != "conformer":
+        if rank == 0:
+            print(json.dumps({"impl": args.impl, "unavailable": "the oracle port covers the Conformer workloads only (workload %s)" % args.workload}))
+        return
     if args.impl == "reference":
         if rank != 0:
             return
@@ -417,33 +506,13 @@ def main():
     import torch
     import torch.distributed as dist
     from neural_sp_b200 import _lib, ops
-    from neural_sp_b200.decoders.ctc import CTC
-    from neural_sp_b200.encoders.conformer import ConformerEncoder
-    from neural_sp_b200.encoders.conv import ConvEncoder
-
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the product path)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    torch.manual_seed(0)
-    a = enc_args(w)
-    a["dropout"] = args.dropout
-    a["frontend_conv"] = ConvEncoder(**conv_args(w))
-    enc = ConformerEncoder(**a)
-    sd_synth, head_synth = synth_params(w)           # the weights every arm uses (strict: the reference's state_dict keys)
-    enc.load_state_dict(sd_synth, strict=True)
-    enc = enc.to(dev)
-    enc = enc.train() if args.step == "train" else enc.eval()
-    enc.set_precision(args.precision)
-    ctc = CTC(eos=2, blank=0, enc_n_units=w["d_model"], vocab=w["vocab"], dropout=args.dropout, lsm_prob=0.1,
-              fc_list="512")
-    ctc.load_state_dict(head_synth, strict=True)
-    ctc = ctc.to(dev)
-    ctc.train()
-    for m in ctc.modules():
-        m.precision = args.precision
+    enc, ctc, loss_fn = build_model(w, args, dev)          # `ctc` = the loss head (CTC or RNN-T decoder)
     head_params = [p for p in ctc.parameters()]
 
     B = w["B"]
@@ -468,7 +537,7 @@ def main():
         eouts = out['ys']['xs'].detach().requires_grad_(True)
         for p in head_params:
             p.grad = None
-        loss, _ = ctc(eouts, out['ys']['xlens'], ys)
+        loss = loss_fn(eouts, out['ys']['xlens'], ys)
         loss.backward()
         if world > 1:
             if works:                      # bucketed hook installed: the head layers' buckets are already in flight
@@ -492,7 +561,7 @@ def main():
         for p in all_params:
             p.grad = None                      # grads are views of the nodes' buckets: set-to-none, never accumulate
         out = enc(x_dev, xlens_t.clone(), task='ys')
-        loss, _ = ctc(out['ys']['xs'], out['ys']['xlens'], ys)
+        loss = loss_fn(out['ys']['xs'], out['ys']['xlens'], ys)
         loss.backward()
         if world > 1:
             if args.allreduce == "bucketed":
@@ -579,7 +648,11 @@ def main():
         barrier()
         ms_e2e = None
         if with_e2e:
-            labels_dev, ylens_dev, Lmax = ops.pack_labels(ys, dev)      # the device tensors every step (and the graph) reads
+            if w["loss"] == "ctc":
+                labels_dev, ylens_dev, Lmax = ops.pack_labels(ys, dev)  # the device tensors every step (and the graph) reads
+            else:                                                       # RNN-T packs its labels inside forward_transducer
+                labels_dev, ylens_dev, Lmax = (torch.zeros(len(ys), 1, dtype=torch.int32, device=dev),
+                                               torch.zeros(len(ys), dtype=torch.int32, device=dev), 1)
             lab_host = torch.zeros(len(ys), Lmax, dtype=torch.int32).pin_memory()
             ylen_host = torch.zeros(len(ys), dtype=torch.int32).pin_memory()
             e2e_bytes["labels"] = int(lab_host.numel() * 4 + ylen_host.numel() * 4)
@@ -588,7 +661,8 @@ def main():
                 # the host side of one step, as the facade does it (speech2text.py:396-409): pack this step's label lists,
                 # copy features + labels + label lengths host -> device, run, read the loss back
                 for b_, y_ in enumerate(ys):
-                    lab_host[b_, :len(y_)] = torch.as_tensor(y_, dtype=torch.int32)
+                    if w["loss"] == "ctc":
+                        lab_host[b_, :len(y_)] = torch.as_tensor(y_, dtype=torch.int32)
                     ylen_host[b_] = len(y_)
                 labels_dev.copy_(lab_host, non_blocking=True)
                 ylens_dev.copy_(ylen_host, non_blocking=True)
@@ -611,7 +685,7 @@ def main():
 
     # ---- loss of the product on the CPU baseline's sample (first 8 utterances), before any parameter update ----
     loss_check = None
-    if not args.no_cpu_baseline and world == 1 and not args.ncu_step:
+    if not args.no_cpu_baseline and world == 1 and not args.ncu_step and w["kind"] == "conformer":
         nb = min(8, B)
         xs8 = xs_dev[:nb, :max(xlens[:nb])].contiguous()
         loss_check = {}
@@ -622,8 +696,7 @@ def main():
                 enc.set_precision(prec)
                 ctc.set_precision(prec)
                 o8 = enc(xs8, torch.IntTensor(xlens[:nb]), task='ys')
-                l8, _ = ctc(o8['ys']['xs'], o8['ys']['xlens'], ys[:nb])
-                loss_check[prec] = float(l8)
+                loss_check[prec] = float(loss_fn(o8['ys']['xs'], o8['ys']['xlens'], ys[:nb]))
         enc.set_precision(args.precision)
         ctc.set_precision(args.precision)
         enc.train(was_training)
@@ -649,6 +722,31 @@ def main():
         enc.eval()
         fwd = measure(step_fwd, with_e2e=False)
         enc.train()
+
+    # ---- forced aligner (BASELINE.md "what is timed"): ms per batch at the workload's output resolution ----
+    aligner = None
+    if w["loss"] == "ctc" and rank == 0 and not args.ncu_step:
+        with torch.no_grad():
+            was_tr = enc.training
+            enc.eval()
+            Tp_ = enc(xs_dev, xlens_t.clone(), task='ys')['ys']
+            enc.train(was_tr)
+            elens_a = Tp_['xlens'].to(dev, dtype=torch.int32)
+            logits_a = torch.randn(B, Tp_['xs'].shape[1], w["vocab"], device=dev)
+            lab_a, ylen_a, _ = ops.pack_labels(ys, dev)
+            for _ in range(3):
+                ops.ctc_forced_align(logits_a, lab_a, elens_a, ylen_a, 0)
+            torch.cuda.synchronize()
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
+            for _ in range(10):
+                ops.ctc_forced_align(logits_a, lab_a, elens_a, ylen_a, 0)
+            eb.record()
+            torch.cuda.synchronize()
+            ms_a = ea.elapsed_time(eb) / 10
+            aligner = {"ms_per_batch": ms_a, "shape": [B, int(Tp_['xs'].shape[1]), w["vocab"]],
+                       "gbs_at_4B_per_logit": 4.0 * logits_a.numel() / (ms_a * 1e-3) / 1e9}
+            del logits_a
 
     # ---- per-kernel-class timing for the roofline (eager, CUDA events around every library call) ----
     # The host must run AHEAD of the device here, otherwise each event pair also brackets the idle gap while the
@@ -715,10 +813,21 @@ def main():
         c = prof.get("ctc_loss", {"ms": 0.0, "bytes": 0.0, "calls": 1})
         ctc_ms = c["ms"] / max(1, c["calls"])
         ctc_gbs = c["bytes"] / (c["ms"] * 1e-3) / 1e9 if c["ms"] > 0 else 0.0
-        roofline_ctc = {"kernel": "ctc_loss fwd+bwd (3 launches)", "bound": "hbm", "achieved": ctc_gbs, "peak": hbm_peak,
-                        "unit": "GB/s", "frac": ctc_gbs / hbm_peak,
-                        "traffic": traffic.get(args.workload, {}).get("ctc_bytes_per_call"), "ms_per_batch": ctc_ms}
-        fl_utt, Tp = flops_per_utt_fwd(w)
+        roofline_ctc = {"kernel": "ctc_loss fwd+bwd (memset + 2 launches: streaming rows/lattice kernel, fix-up)", "bound": "hbm",
+                        "achieved": ctc_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ctc_gbs / hbm_peak,
+                        "traffic": traffic.get(args.workload, {}).get("ctc_bytes_per_call"), "ms_per_batch": ctc_ms,
+                        "algorithmic_bytes": "8 B per logit (SURVEY 8d)"} if "ctc_loss" in prof else None
+        rn = prof.get("rnnt_loss")
+        roofline_rnnt = None
+        if rn and rn["ms"] > 0:
+            roofline_rnnt = {"kernel": "rnnt_loss fwd+bwd at the rnnt_loss(log_probs) boundary", "bound": "hbm",
+                             "achieved": rn["bytes"] / (rn["ms"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": rn["bytes"] / (rn["ms"] * 1e-3) / 1e9 / hbm_peak, "ms_per_batch": rn["ms"] / max(1, rn["calls"]),
+                             "algorithmic_bytes": "8 B per log-prob element [B,T',U+1,V] (SURVEY 8d)"}
+        if w["kind"] == "conformer":
+            fl_utt, Tp = flops_per_utt_fwd(w)
+        else:
+            fl_utt, Tp = None, None
         value = frames_per_step * world / (ms_dev * 1e-3)
         e2e = frames_per_step * world / (ms_e2e * 1e-3)
         line = {"metric": "speech_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
@@ -726,7 +835,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
                 "config": dict(cfg_common, l2="256 MiB memset between timed iterations (outside the event pairs); "
                                              "per-step working set >> 126 MB L2",
-                               encoder_fwd_tflop_per_step=fl_utt * B / 1e12, enc_out_frames=Tp,
+                               encoder_fwd_tflop_per_step=(fl_utt * B / 1e12 if fl_utt else None), enc_out_frames=Tp,
                                cuda_graph=graph_ok, cuda_graph_error=graph_error, n_params=n_params,
                                allreduce=(args.allreduce if world > 1 else None),
                                gemm_epilogue=("direct", "tma", "tma+cta_pairs")[_lib.lib.nsp_get_gemm_epilogue()]),
@@ -735,20 +844,21 @@ def main():
                         "h2d_bytes_per_step": int(xs_host.numel() * 4) + e2e_bytes["labels"], "d2h_bytes_per_step": 4,
                         "includes": "host packing of the label lists + H2D of features, labels, label lengths + D2H of the loss"},
                 "gpu_launches": int(launches), "loss": main["loss"],
-                "roofline": roofline, "roofline_ctc": roofline_ctc, "ctc_loss_ms_per_batch": ctc_ms,
+                "roofline": roofline, "roofline_ctc": roofline_ctc, "ctc_loss_ms_per_batch": ctc_ms if "ctc_loss" in prof else None,
+                "roofline_rnnt": roofline_rnnt, "aligner": aligner,
                 "kernel_time_ms_per_step": {k: round(v["ms"] / nprof, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}}
         if fwd is not None:
             line["fwd"] = {"value": frames_per_step * world / (ms_fwd * 1e-3), "unit": "frames/s", "ms_per_step": ms_fwd,
                            "step": "encoder_fwd + ctc_head + ctc_fwd_bwd + head_bwd (inference kernels, eval mode)",
                            "cuda_graph": fwd["graph"]}
-        if not args.no_eager and world == 1:
+        if not args.no_eager and world == 1 and w["kind"] == "conformer":
             del graph_keep[:]                           # release the graphs' private pools before the eager baseline allocates
             torch.cuda.empty_cache()
             line["eager_b200"] = eager_cuda_arm(w, dev, max(3, min(args.steps, 10)), 3, train=args.step == "train",
                                                 lengths=args.lengths, seed=1234 + rank)
             if line["eager_b200"]["ms_per_step"]:
                 line["speedup_vs_eager_b200"] = line["eager_b200"]["ms_per_step"] / ms_dev
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and w["kind"] == "conformer":
             r = cpu_reference_arm(w, 3, 1, train=args.step == "train", lengths=args.lengths, budget_s=90.0)
             line["cpu_baseline"] = {"value": r["value"], "unit": "frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
             if loss_check is not None:                 # same weights, same 8 utterances: the product's loss vs the port's

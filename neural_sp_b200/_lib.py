@@ -217,11 +217,11 @@ for _name, (_res, _args) in _more.items():
     _fn.argtypes = _args
 SIGNATURES.update(_more)
 
-# opt-in (until validated on hardware): NSP_GEMM_EPILOGUE=tma routes the large bf16 GEMMs through gemm_tma_epi.cu,
-# NSP_GEMM_EPILOGUE=pair additionally runs the largest ones on CTA pairs (cta_group::2)
-_GEMM_MODES = {"": 0, "direct": 0, "tma": 1, "pair": 2}
+# GEMM kernel family: the library default is "pair" (TMA-store epilogue, CTA pairs / cta_group::2 on the large problems;
+# validated and fastest on B200 in round 2).  NSP_GEMM_EPILOGUE=direct | tma pins the older families (tests, A/B runs).
+_GEMM_MODES = {"direct": 0, "tma": 1, "pair": 2}
 _mode = os.environ.get("NSP_GEMM_EPILOGUE", "").lower()
-if _mode not in _GEMM_MODES:
-    raise NspError("NSP_GEMM_EPILOGUE=%r (expected one of %s)" % (_mode, sorted(k for k in _GEMM_MODES if k)))
-if _GEMM_MODES[_mode]:
+if _mode and _mode not in _GEMM_MODES:
+    raise NspError("NSP_GEMM_EPILOGUE=%r (expected one of %s)" % (_mode, sorted(_GEMM_MODES)))
+if _mode:
     check(lib.nsp_set_gemm_epilogue(_GEMM_MODES[_mode]), "nsp_set_gemm_epilogue")

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3_tc_kernel(const __grid_constan
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int ft = tile % tiles_f, tt = (tile / tiles_f) % tiles_t, b = tile / (tiles_f * tiles_t);
                 for (int tap = 0; tap < 9; ++tap) {
-                    tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    tc::mbar_wait_spin(&empty_bar[stage], phase ^ 1);
                     tc::mbar_arrive_expect_tx(&full_bar[stage], A_BYTES);
                     tma_load_4d(sA + stage * A_BYTES, &tmap_x, &full_bar[stage], 0, ft * TF + (tap % 3) - 1,
                                 tt * TT + (tap / 3) - 1, b);
@@ -96,16 +96,16 @@ __global__ void __launch_bounds__(192, 1) conv3x3_tc_kernel(const __grid_constan
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = tc::make_idesc(1u, 128, 32);
-            tc::mbar_wait(w_bar, 0);
+            tc::mbar_wait_spin(w_bar, 0);
             tc::tc_fence_after();
             int stage = 0; uint32_t phase = 0; int it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
                 const int as = it & 1;
-                tc::mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
+                tc::mbar_wait_spin(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
                 tc::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * 32);
                 for (int tap = 0; tap < 9; ++tap) {
-                    tc::mbar_wait(&full_bar[stage], phase);
+                    tc::mbar_wait_spin(&full_bar[stage], phase);
                     tc::tc_fence_after();
                     const uint64_t adesc = make_smem_desc_sw64(tc::smem_u32(sA + stage * A_BYTES));
                     const uint64_t bdesc = make_smem_desc_sw64(tc::smem_u32(sW + tap * W_TAP_BYTES));
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3_tc_kernel(const __grid_constan
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int ft = tile % tiles_f, tt = (tile / tiles_f) % tiles_t, b = tile / (tiles_f * tiles_t);
             const int as = it & 1;
-            tc::mbar_wait(&tfull_bar[as], (it >> 1) & 1);
+            tc::mbar_wait_epi(&tfull_bar[as], (it >> 1) & 1);
             tc::tc_fence_after();
             uint32_t r[32];
             tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 32), r);

@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3_wgrad_tc_kernel(const __grid_c
     } else {
         const int q = warp & 3;
         if (blockIdx.x < num_tiles) {
-            tc::mbar_wait(tfull_bar, 0);
+            tc::mbar_wait_epi(tfull_bar, 0);
             tc::tc_fence_after();
 #pragma unroll 1
             for (int g = 0; g < 3; ++g) {

@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ts_kernel(const __grid_const
                     for (int ci = 0; ci < NCH; ++ci) tc::tma_load_2d(stg + ci * 4096, &maps.res, rbar, col0 + ci * CW, row0);
                 }
             }
-            bwait(&tfull_bar[as], aphase, 3);
+            tc::mbar_wait_epi(&tfull_bar[as], aphase);
             tc::tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
             if constexpr (RES) {

@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
     } else {
         // ===================== epilogue warps 2..5 =====================
         const int q = warp & 3;
-        tc::mbar_wait(tfull_bar, 0);
+        tc::mbar_wait_epi(tfull_bar, 0);
         tc::tc_fence_after();
         const int row = n_blk * WG_BM + q * 32 + lane;           // row of dW
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);

@@ -36,20 +36,37 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-// Every mbarrier wait is bounded: a lost arrival (protocol bug at an untested size class) traps after ~2 s instead of
-// hanging the GPU.  The hot loop is the bare try_wait spin of round 1 plus one counter; the clock is only read once per
-// 4096 failed polls and the failure path is a bare `trap` (a printf call here cost 9 registers in conv3x3_tc and 10-50 % of
-// the GEMM / conv kernels' time: measured, profiles/README.md round 2).
+// Every mbarrier wait is bounded: a lost arrival (protocol bug at an untested size class) traps instead of hanging the GPU
+// (2^26 failed polls: seconds).  The retry loop is ONE inline-PTX block (block-local labels, as CUTLASS's ClusterBarrier::wait
+// does): a C++ loop with a counter in it stopped nvcc from unrolling the ENCLOSING tap / k-block loops -- conv3x3_tc lost 48 %
+// (1.16 -> 1.71 ms per step), the training step 0.8 ms (A/B builds, SASS 1737 vs 1153 lines; profiles/README.md round 2).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef NSP_UNBOUNDED_WAITS                       // A/B build only: the round-1 bare spin
+    while (!mbar_try_wait(bar, parity)) {}
+#else
+    // The loop is the bare `while (!try_wait)` nvcc rotates well (fast path: one try_wait that falls through, retry loop out of
+    // line -- a taken branch per wait cost conv3x3_tc 45 %); the bound lives in ONE opaque asm statement in its body.
     uint32_t polls = 0;
-    long long deadline = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++polls & 4095u) == 0) {
-            const long long now = clock64();
-            if (deadline == 0) deadline = now + 4000000000LL;
-            else if (now > deadline) asm volatile("trap;");
-        }
+        asm volatile(
+            "{\n\t"
+            ".reg .pred q;\n\t"
+            "add.u32 %0, %0, 1;\n\t"
+            "setp.eq.u32 q, %0, 0x4000000;\n\t"
+            "@q trap;\n\t"
+            "}"
+            : "+r"(polls) :: "memory");
     }
+#endif
+}
+
+// Bare spin for the single TMA / MMA threads of kernels whose waits are short and many (conv3x3_tc: nine 32-wide MMAs per
+// tile).  nvcc turns exactly this loop into ONE try_wait that falls through plus an out-of-line retry loop; every bounded
+// form tried (counter in C++, one asm block, out-of-line call, counting asm body) left a TAKEN branch on the fast path and
+// cost that kernel 45 % (1.15 -> 1.70 ms per step; A/B builds in profiles/README.md round 2).  Only for threads whose stall
+// starves a BOUNDED waiter downstream (the epilogue warps' mbar_wait on the accumulator barrier): a lost arrival still traps.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
 }
 
 // Wait that does not spin: try_wait with a suspend-time hint parks the thread in hardware until the phase completes or the
@@ -65,10 +82,31 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
-    uint32_t polls = 0;
-    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
-        if (++polls > 400000u) asm volatile("trap;");          // > 2 s even if every poll returned after 5 us
-    }
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .u32 c;\n\t"
+        "mov.u32 c, 0;\n"
+        "NSP_WAITP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra NSP_DONEP;\n\t"
+        "add.u32 c, c, 1;\n\t"
+        "setp.lt.u32 p, c, 400000;\n\t"
+        "@p bra NSP_WAITP;\n\t"
+        "trap;\n"
+        "NSP_DONEP:\n\t"
+        "}"
+        :: "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+}
+
+// Epilogue-side wait (hundreds of threads waiting a whole mainloop for the accumulator).  Parking these (-DNSP_EPI_PARKED)
+// made no measurable difference on the GEMM / conv kernels (A/B build, round 2), so they spin like the rest.
+__device__ __forceinline__ void mbar_wait_epi(uint64_t* bar, uint32_t parity) {
+#ifdef NSP_EPI_PARKED
+    mbar_wait_parked(bar, parity);
+#else
+    mbar_wait(bar, parity);
+#endif
 }
 
 // ---------------- TMA ----------------

@@ -78,16 +78,16 @@ def test_conv_encoder_matches_reference(ov, look, monkeypatch):
         assert torch.allclose(r_xs, o_xs, atol=1e-4), float((r_xs - o_xs).abs().max())
 
 
-# OPEN (NOTES.md, round-2 list): in stacks WITHOUT a bridge whose first block is un-pooled (cases 2 and 7) the node's conv
-# gradients deviate by 0.2-0.6 % from torch autograd on CPU, while the same blocks followed by a bridge or by pooling agree to
-# 1e-6 and the pooled / bridged shapes are hardware-validated against reference gradients (tests/test_backward_gpu.py).  Not yet
-# bisected (node vs op restatement): reported as xfail instead of loosening the tolerance.
-_OPEN = {2, 7}
+# Round 1 left cases 2 and 7 (no bridge, un-pooled first block) as an open 0.2-0.6 % gradient deviation.  Bisected in round 2:
+# ONE ReLU mask bit.  With the seed-0 input the reference's pre-activation layers.1.conv1[0, 31, 5, 53] is -6.7e-8 while the
+# restatement's summation order gives +1.3e-7; the upstream gradient there is -0.70, so that single element changes the 288
+# weight-gradient entries of output channel 31 by 0.3-0.5 % of the tensor's maximum (and everything upstream of it).  Neither
+# side is wrong -- ReLU'(0+-eps) is decided by rounding.  These two cases (four times the positions of the pooled stacks, hence
+# the collision) use another input seed; every case keeps the "<= 2 entries above 3e-3" allowance for the same effect.
+_SEED = {2: 1, 7: 1}
 
 
-@pytest.mark.parametrize("ov", [pytest.param(c, marks=pytest.mark.xfail(strict=False, reason="un-pooled, bridge-less stack: "
-                                             "0.2-0.6 % gradient deviation not bisected yet (NOTES.md)")) if i in _OPEN else c
-                                for i, c in enumerate(CASES)])
+@pytest.mark.parametrize("ov", CASES)
 def test_conv_encoder_training_matches_reference(ov, monkeypatch):
     """The same matrix in train() mode (dropout 0): the REAL training node (autograd._FrontendFn: its forward and its
     hand-written backward chain, ops replaced by their restatements) against torch autograd over the unmodified reference --
@@ -113,7 +113,7 @@ def test_conv_encoder_training_matches_reference(ov, monkeypatch):
     ours.load_state_dict(ref.state_dict(), strict=True)
     ours.set_precision("fp32")
     ours.train()
-    rng = np.random.RandomState(0)
+    rng = np.random.RandomState(_SEED.get(CASES.index(ov), 0))
     xs = torch.from_numpy(rng.randn(4, 45, 80).astype(np.float32))
     xlens = torch.IntTensor([45 - 3 * i for i in range(4)])
     for b, n in enumerate(xlens.tolist()):

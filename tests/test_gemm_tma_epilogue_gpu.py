@@ -183,3 +183,25 @@ def test_wgrad_bulk_reduce_into_a_row_block_of_a_fused_gradient(tma_epilogue):
     ref = 3.0 + dy.double().t() @ x.double()
     assert float((full[N:2 * N].double() - ref).abs().max() / ref.abs().max()) <= 2e-2
     assert torch.all(full[:N] == 3.0) and torch.all(full[2 * N:] == 3.0)
+
+
+# ---- the round-1 direct-store family stays selectable (NSP_GEMM_EPILOGUE=direct) and correct: since round 2 the library
+# ---- default is the TMA-store / CTA-pair family, so these shapes pin the older kernels explicitly
+@pytest.fixture
+def direct_store():
+    yield from _mode(0)
+
+
+@pytest.mark.parametrize("M", [16000, 4001])
+def test_direct_store_family_still_correct(direct_store, M):
+    _run(direct_store, M, 512, 512, expect_tma=False)
+    _run(direct_store, M, 2048, 512, act="swish", out_dtype=torch.bfloat16, save_pre=True, expect_tma=False)
+    _run(direct_store, M, 512, 2048, residual=True, alpha=0.5, expect_tma=False)
+    _run(direct_store, M, 1024, 512, glu=True, out_dtype=torch.bfloat16, expect_tma=False)
+
+
+def test_default_family_is_tma_pairs():
+    from neural_sp_b200 import _lib
+    import os
+    if not os.environ.get("NSP_GEMM_EPILOGUE"):
+        assert _lib.lib.nsp_get_gemm_epilogue() == 2
