@@ -807,7 +807,12 @@ def main():
         roofline = {"kernel": "gemm_tcgen05 (%s)" % gk, "bound": "tensor", "achieved": gemm_tflops, "peak": tf_peak,
                     "unit": "TFLOP/s", "frac": gemm_tflops / tf_peak,
                     "traffic": traffic.get(args.workload, {}).get("gemm_bytes_per_launch"),
+                    "traffic_note": traffic.get(args.workload, {}).get("gemm_note"),
+                    "traffic_by_shape": traffic.get(args.workload, {}).get("gemm_by_shape"),
                     "traffic_source": traffic.get("source"), "peak_source": peak_src,
+                    "note": "achieved = sum of 2*M*N*K over every GEMM launch of the step (forward, input-gradient, weight-gradient) "
+                            "/ sum of their CUDA-event times in an eager replay of the step; the per-launch events add ~10 % to the "
+                            "kernel times (kernel_time_ms_per_step sums to more than ms_per_step), so frac is pessimistic by that much",
                     "share_of_step": g["ms"] / total_ms, "launches_per_step": g["calls"] / nprof,
                     "dominant_by_time": dom[0]}
         c = prof.get("ctc_loss", {"ms": 0.0, "bytes": 0.0, "calls": 1})
@@ -820,9 +825,12 @@ def main():
         rn = prof.get("rnnt_loss")
         roofline_rnnt = None
         if rn and rn["ms"] > 0:
-            roofline_rnnt = {"kernel": "rnnt_loss fwd+bwd at the rnnt_loss(log_probs) boundary", "bound": "hbm",
-                             "achieved": rn["bytes"] / (rn["ms"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": rn["bytes"] / (rn["ms"] * 1e-3) / 1e9 / hbm_peak, "ms_per_batch": rn["ms"] / max(1, rn["calls"]),
+            # the op boundary rnnt_loss(log_probs) -> (loss, d loss / d log_probs): gather + lattice (rnnt_loss) and the dense
+            # gradient pass (rnnt_grad_logits, which in training also folds the log-softmax backward in)
+            rn_ms = rn["ms"] + prof.get("rnnt_grad_logits", {"ms": 0.0})["ms"]
+            roofline_rnnt = {"kernel": "rnnt_loss fwd+bwd at the rnnt_loss(log_probs) boundary (gather + lattice + dense gradient pass)",
+                             "bound": "hbm", "achieved": rn["bytes"] / (rn_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": rn["bytes"] / (rn_ms * 1e-3) / 1e9 / hbm_peak, "ms_per_batch": rn_ms / max(1, rn["calls"]),
                              "algorithmic_bytes": "8 B per log-prob element [B,T',U+1,V] (SURVEY 8d)"}
         if w["kind"] == "conformer":
             fl_utt, Tp = flops_per_utt_fwd(w)

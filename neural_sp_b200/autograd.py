@@ -32,6 +32,7 @@ class _Grads:
         self.g = {}
         self.flat = None
         params = [p for p in params if p is not None]
+        self.params = params
         if params:
             total = sum(p.numel() for p in params)
             self.flat = torch.zeros(total, dtype=torch.float32, device=params[0].device)
@@ -69,6 +70,14 @@ class _Grads:
 
     def done(self):
         if _GRAD_SYNC is not None and self.flat is not None:
+            # The hook may start an ASYNCHRONOUS in-place all-reduce of the bucket the returned .grad tensors are views of.
+            # If a parameter already holds a gradient (gradient accumulation, or a parameter shared by several nodes such as
+            # the relative_xl u_bias / v_bias), autograd's AccumulateGrad would read the bucket while NCCL is reducing it.
+            for p in self.params:
+                if p.grad is not None:
+                    raise RuntimeError("neural_sp_b200: a gradient-sync hook is installed but a parameter of this node already "
+                                       "has .grad (accumulation or a parameter shared between nodes): set grads to None before "
+                                       "every backward, or reduce after the backward pass (dist.flat_allreduce_grads)")
             _GRAD_SYNC(self.flat)
 
 

@@ -257,6 +257,9 @@ class Conv1dBlock(EncoderBase):
         from .. import autograd as ag
         if self.norm1 is not None or self.residual:
             raise NotImplementedError("training path of the 1-D CNN front-end: no normalisation, no residual only")
+        if self.dropout.p > 0:
+            raise NotImplementedError("dropout > 0 in the 1-D CNN front-end is not on the B200 training path "
+                                      "(build_encoder passes 0; the reference applies it after each ReLU, conv.py:265-283)")
         prec = get_precision(self)
         k = self.kernel_size
         for name, conv, stride in (("conv1", self.conv1, 1), ("conv2", self.conv2, self.stride)):

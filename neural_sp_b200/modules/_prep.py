@@ -43,3 +43,14 @@ def cached(module, name, params, build):
         val = build(*params)
     cache[(name, "raw")] = (ver, val)
     return val
+
+
+def invalidate_caches(module):
+    """Drop every cached operand (bf16 copies, transposes, folded BatchNorm weights, tap tables) under ``module``.
+
+    The caches are keyed by ``(data_ptr, _version)`` of their source parameters.  Updates made through ``p.data`` (the
+    reference's forget-gate initialisation models/base.py:74, legacy weight noise / clipping / EMA swaps) do NOT bump
+    ``_version``: call this after such an update (``load_state_dict``, optimizer steps and every other in-place update through
+    the parameter itself are tracked automatically)."""
+    for m in module.modules():
+        m.__dict__.pop("_nsp_cache", None)

@@ -29,6 +29,40 @@ if which.startswith("gemm"):
     torch.cuda.synchronize()
     ms = s.elapsed_time(e) / 20
     print(which, "ms", ms, "TFLOP/s", 2.0 * M * N * K / ms / 1e9)
+elif which == "wgrad":
+    M, N, K = 16000, 2048, 512            # dW [N, K] += dY^T X,  dY [M, N], X [M, K]
+    dy = torch.randn(M, N, device=dev).bfloat16()
+    x = torch.randn(M, K, device=dev).bfloat16()
+    dw = torch.zeros(N, K, device=dev)
+    for _ in range(5):
+        ops.linear_wgrad(dy, x, "bf16", dw)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(20):
+        ops.linear_wgrad(dy, x, "bf16", dw)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / 20
+    print(which, "ms", ms, "TFLOP/s", 2.0 * M * N * K / ms / 1e9)
+elif which == "attn_fwd":
+    B, T, H, dk = 32, 500, 8, 64
+    D = H * dk
+    qkv = (torch.randn(B, T, 3 * D, device=dev) * 0.5).bfloat16()
+    r = (torch.randn(11, D, device=dev) * 0.5).bfloat16()
+    klens = torch.full((B,), T, dtype=torch.int32, device=dev)
+    q, k, v = qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:]
+    for _ in range(3):
+        ops.relpos_attention(q, k, v, klens, H, r=r, clamp_len=10)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(10):
+        ops.relpos_attention(q, k, v, klens, H, r=r, clamp_len=10)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / 10
+    print("attn_fwd B=%d T=%d H=%d: %.4f ms  %.1f TFLOP/s (4*T^2*d per utterance)" % (B, T, H, ms, 4.0 * B * T * T * D / ms / 1e9))
 elif which == "ctc":
     B, T, V = 32, 125, 10000
     import numpy as np
