@@ -510,6 +510,10 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # The gradient all-reduce runs on NCCL's own stream UNDER the backward pass.  Its kernels need a few SMs, not the default
+        # 16-32 channels: 436 MB per step over a ~14 ms backward is ~30 GB/s.  Fewer NCCL CTAs = more SMs for the persistent
+        # 148-CTA GEMMs (round 1: the GEMM class slowed 19 % at N = 8 under the all-reduce).  Respect a caller's own setting.
+        os.environ.setdefault("NCCL_MAX_CTAS", "4")
         dist.init_process_group("nccl", device_id=dev)
 
     enc, ctc, loss_fn = build_model(w, args, dev)          # `ctc` = the loss head (CTC or RNN-T decoder)
@@ -846,6 +850,7 @@ def main():
                                encoder_fwd_tflop_per_step=(fl_utt * B / 1e12 if fl_utt else None), enc_out_frames=Tp,
                                cuda_graph=graph_ok, cuda_graph_error=graph_error, n_params=n_params,
                                allreduce=(args.allreduce if world > 1 else None),
+                               nccl_max_ctas=(os.environ.get("NCCL_MAX_CTAS") if world > 1 else None),
                                gemm_epilogue=("direct", "tma", "tma+cta_pairs")[_lib.lib.nsp_get_gemm_epilogue()]),
                 "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e,

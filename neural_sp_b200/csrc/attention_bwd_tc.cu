@@ -371,15 +371,18 @@ __global__ void __launch_bounds__(256) attn_bwd_finish_kernel(const float* __res
                                                               float* __restrict__ dr_part,
                                                               int B, int H, int T, int has_rel, int clamp) {
     pdl_entry();
-    __shared__ float sdr[16][DK];
+    // Round 1 walked the CTA's 64 rows one per warp iteration, each a dependent chain of loads (accumulator, q, 16 scalar
+    // band weights) and finished with shared-memory atomics: 68 us per launch on average for a 12 us data volume
+    // (profiles/r02_launches_train_step.md).  Here a warp issues the loads of FOUR rows before it touches any of them (the band
+    // weights arrive as ONE 64-byte load, one value per lane, and are broadcast by shuffles), and the per-warp dR partials go
+    // through plain stores.
+    __shared__ float sdr[8][16][DK];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // grid.x = (b, h, row block of 64): all rows of a CTA share the head so that dR reduces in shared memory first
     const int rblocks = (T + 63) / 64;
     const int rb = blockIdx.x % rblocks;
     const int h = (blockIdx.x / rblocks) % H;
     const int b = blockIdx.x / (rblocks * H);
-    for (int e = threadIdx.x; e < 16 * DK; e += 256) (&sdr[0][0])[e] = 0.f;
-    __syncthreads();
     float rloc[16][2];
     if (has_rel) {
 #pragma unroll
@@ -394,42 +397,58 @@ __global__ void __launch_bounds__(256) attn_bwd_finish_kernel(const float* __res
     float dracc[16][2];
 #pragma unroll
     for (int d = 0; d < 16; ++d) { dracc[d][0] = 0.f; dracc[d][1] = 0.f; }
-    for (int ii = warp; ii < 64; ii += 8) {
-        const int i = rb * 64 + ii;
-        if (i >= T) break;
-        const int64_t bt = (int64_t)b * T + i;
-        const float2 acc = *reinterpret_cast<const float2*>(dq_acc + bt * ((int64_t)H * DK) + h * DK + lane * 2);
-        float o0 = acc.x, o1 = acc.y;
-        if (has_rel) {
-            const float* wr = w + (((int64_t)b * H + h) * T + i) * 16;
-            const float2 qf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(q + bt * ldq + h * DK + lane * 2));
-            float wsum = 0.f;
+    constexpr int RB = 4;                                    // rows in flight per warp
+#pragma unroll 1
+    for (int i0 = warp * 8; i0 < warp * 8 + 8; i0 += RB) {   // warp w owns rows 8w .. 8w+7 of the block
+        float2 acc[RB], qf[RB];
+        float wl[RB];
 #pragma unroll
-            for (int d = 0; d < 16; ++d) {
-                if (d < clamp) {
-                    const float wv = wr[d];
-                    wsum += wv;
-                    o0 = fmaf(wv, rloc[d][0], o0); o1 = fmaf(wv, rloc[d][1], o1);
-                    dracc[d][0] = fmaf(wv, qf.x, dracc[d][0]); dracc[d][1] = fmaf(wv, qf.y, dracc[d][1]);
-                } else if (d == clamp) {
-                    const float wv = -wsum;
-                    o0 = fmaf(wv, rloc[d][0], o0); o1 = fmaf(wv, rloc[d][1], o1);
-                    dracc[d][0] = fmaf(wv, qf.x, dracc[d][0]); dracc[d][1] = fmaf(wv, qf.y, dracc[d][1]);
+        for (int u = 0; u < RB; ++u) {
+            const int i = rb * 64 + i0 + u;
+            acc[u] = make_float2(0.f, 0.f); qf[u] = make_float2(0.f, 0.f); wl[u] = 0.f;
+            if (i < T) {
+                const int64_t bt = (int64_t)b * T + i;
+                acc[u] = *reinterpret_cast<const float2*>(dq_acc + bt * ((int64_t)H * DK) + h * DK + lane * 2);
+                if (has_rel) {
+                    qf[u] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(q + bt * ldq + h * DK + lane * 2));
+                    if (lane < 16) wl[u] = w[(((int64_t)b * H + h) * T + i) * 16 + lane];
                 }
             }
         }
-        *reinterpret_cast<__nv_bfloat162*>(dq + bt * lddq + h * DK + lane * 2) = __floats2bfloat162_rn(o0, o1);
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+            const int i = rb * 64 + i0 + u;
+            float o0 = acc[u].x, o1 = acc[u].y;
+            if (has_rel) {
+                float wsum = 0.f;
+#pragma unroll
+                for (int d = 0; d < 16; ++d) {
+                    float wv = __shfl_sync(0xffffffffu, wl[u], d);
+                    if (d < clamp) wsum += wv;
+                    else if (d == clamp) wv = -wsum;
+                    else wv = 0.f;
+                    o0 = fmaf(wv, rloc[d][0], o0); o1 = fmaf(wv, rloc[d][1], o1);
+                    dracc[d][0] = fmaf(wv, qf[u].x, dracc[d][0]); dracc[d][1] = fmaf(wv, qf[u].y, dracc[d][1]);
+                }
+            }
+            if (i < T)
+                *reinterpret_cast<__nv_bfloat162*>(dq + ((int64_t)b * T + i) * lddq + h * DK + lane * 2) = __floats2bfloat162_rn(o0, o1);
+        }
     }
     if (has_rel && dr_part) {
 #pragma unroll
-        for (int d = 0; d < 16; ++d) {
-            if (d <= clamp) { atomicAdd(&sdr[d][lane * 2], dracc[d][0]); atomicAdd(&sdr[d][lane * 2 + 1], dracc[d][1]); }
-        }
+        for (int d = 0; d < 16; ++d)
+            *reinterpret_cast<float2*>(&sdr[warp][d][lane * 2]) = make_float2(dracc[d][0], dracc[d][1]);
         __syncthreads();
         // this CTA's partial [16][64] goes to scratch (plain stores); attn_bwd_dr_reduce_kernel sums the partials of a head:
         // atomics straight into dr would put B*T/64 adds on each of only H*(clamp+1)*64 addresses
         float* dst = dr_part + (int64_t)blockIdx.x * 16 * DK;
-        for (int e = threadIdx.x; e < 16 * DK; e += 256) dst[e] = (&sdr[0][0])[e];
+        for (int e = threadIdx.x; e < 16 * DK; e += 256) {
+            float t = 0.f;
+#pragma unroll
+            for (int w_ = 0; w_ < 8; ++w_) t += (&sdr[w_][0][0])[e];
+            dst[e] = t;
+        }
     }
 }
 
