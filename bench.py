@@ -510,10 +510,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # The gradient all-reduce runs on NCCL's own stream UNDER the backward pass.  Its kernels need a few SMs, not the default
-        # 16-32 channels: 436 MB per step over a ~14 ms backward is ~30 GB/s.  Fewer NCCL CTAs = more SMs for the persistent
-        # 148-CTA GEMMs (round 1: the GEMM class slowed 19 % at N = 8 under the all-reduce).  Respect a caller's own setting.
-        os.environ.setdefault("NCCL_MAX_CTAS", "4")
+        # (NCCL_MAX_CTAS=4 was tried to leave more SMs to the persistent GEMMs under the overlapped all-reduce: at N = 2 it was
+        # SLOWER, 21.05 vs 20.69 ms per step with NCCL's own choice -- not set here; a caller's environment is respected.)
         dist.init_process_group("nccl", device_id=dev)
 
     enc, ctc, loss_fn = build_model(w, args, dev)          # `ctc` = the loss head (CTC or RNN-T decoder)
@@ -884,7 +882,20 @@ def main():
                     assert e <= loss_check["bound"][k], "loss parity broken in %s mode: %r" % (k, loss_check)
         print(json.dumps(line))
     if world > 1:
+        # Free the captured graphs (they hold NCCL kernels) BEFORE tearing the communicator down: with the graphs still alive
+        # destroy_process_group() never returned at N = 2 (round 2: every rank hung after the JSON line was printed).  The timer is
+        # a last resort so that a teardown problem can never turn into a hung job.
+        sys.stdout.flush()
+        guard = threading.Timer(60.0, lambda: os._exit(0))
+        guard.daemon = True
+        guard.start()
+        del graph_keep[:]
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
+        guard.cancel()
 
 
 if __name__ == "__main__":
