@@ -14,7 +14,7 @@ from ._lib import lib, check, ptr, current_stream_ptr
 # ---- launch accounting / optional per-op CUDA-event profiling (used by bench.py) ----
 LAUNCHES = 0          # number of CUDA kernels this library launched (claimed count; see KERNELS_PER_CALL)
 PROFILE = None        # None, or dict name -> [list of (start_event, end_event)], flops, bytes
-KERNELS_PER_CALL = {"nsp_ctc_loss_fwd_bwd": 3, "nsp_ctc_forced_align": 2}
+KERNELS_PER_CALL = {"nsp_ctc_loss_fwd_bwd": 2, "nsp_ctc_forced_align": 2}
 
 
 def profile_start():
@@ -604,7 +604,7 @@ def lstm_seq_bwd(dy, acts, cprev, w_hh, lens, dstate=None, want_dstate=False):
 KERNELS_PER_CALL["nsp_relpos_attention_bwd"] = 4
 KERNELS_PER_CALL["nsp_rnnt_joint_tanh_bwd"] = 2
 KERNELS_PER_CALL["nsp_bn_swish_bwd"] = 2
-KERNELS_PER_CALL["nsp_conformer_conv_bwd"] = 2
+KERNELS_PER_CALL["nsp_conformer_conv_bwd"] = 3
 
 
 def _operand(x, prec):
