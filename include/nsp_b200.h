@@ -311,6 +311,24 @@ nsp_status nsp_lstm_seq_bwd_state(const float* dy, const float* acts, const floa
                                   const float* dhN, const float* dcN, float* dh0, float* dc0,
                                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* bf16-mode recurrence on the tensor cores (lstm_tc.cu): the same layer, same arguments and outputs, with the per-step
+ * products h_{t-1} W_hh^T (forward) and dG_t W_hh (backward) issued as tcgen05.mma on bf16 operands with fp32 accumulation;
+ * cell state, gate math, saved activations and every output stay fp32.  This is what the reference's AMP mode does through
+ * cuDNN (encoders/rnn.py:534-546 under torch.cuda.amp.autocast, models/seq2seq/speech2text.py:207-214).
+ * One entry point per direction of time covers all the variants above: acts / cprev / hprev (all or none), h0 / c0, hN / cN,
+ * dhN / dcN, dh0 / dc0 are optional (null).  _supported: 1 when (B, H, ndir) is covered (B <= 128, H % 64 == 0, H / 8 CTAs
+ * co-resident), else the caller uses the fp32 entry points.  Workspace: _tc_workspace_bytes(B, H, ndir, backward). */
+int nsp_lstm_tc_supported(int B, int H, int ndir);
+size_t nsp_lstm_tc_workspace_bytes(int B, int H, int ndir, int backward);
+nsp_status nsp_lstm_seq_fwd_tc(const float* gates_x, const float* w_hh, const int32_t* lens, float* y,
+                               int B, int T, int H, int ndir, float* acts, float* cprev, float* hprev,
+                               const float* h0, const float* c0, float* hN, float* cN,
+                               void* workspace, size_t workspace_bytes, void* stream);
+nsp_status nsp_lstm_seq_bwd_tc(const float* dy, const float* acts, const float* cprev, const float* w_hh,
+                               const int32_t* lens, float* dgates, int B, int T, int H, int ndir,
+                               const float* dhN, const float* dcN, float* dh0, float* dc0,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
 
 /* ==========================================================================================
  * Backward pass of the encoder path (training).  The reference obtains all of these from torch autograd over

@@ -143,6 +143,12 @@ for _name, (_res, _args) in _more.items():
 SIGNATURES.update(_more)
 
 _more = {"nsp_lstm_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
+         "nsp_lstm_tc_supported": (c_int, [c_int, c_int, c_int]),
+         "nsp_lstm_tc_workspace_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
+         "nsp_lstm_seq_fwd_tc": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                         c_vp, c_vp, c_sz, c_vp]),
+         "nsp_lstm_seq_bwd_tc": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp,
+                                         c_vp, c_sz, c_vp]),
          "nsp_lstm_seq_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_sz, c_vp]),
          "nsp_lstm_seq_fwd_state": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
                                             c_sz, c_vp]),

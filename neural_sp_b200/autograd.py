@@ -673,7 +673,7 @@ class _LstmLayerFn(torch.autograd.Function):
         whh = cached(enc, 'w_hh%d' % lth, tuple(w_hh), lambda *ws: torch.stack(ws, dim=0).float().contiguous())
         xs = xs.contiguous().float()
         gates_x = ops.linear(xs, w_ihp, bias, prec=prec, out_dtype=torch.float32)
-        ys, acts, cprev, hprev = ops.lstm_seq(gates_x, whh, lens_dev, nd, save=True)
+        ys, acts, cprev, hprev = ops.lstm_seq(gates_x, whh, lens_dev, nd, save=True, prec=prec)
         ctx.save_for_backward(xs, acts, cprev, hprev, whh, lens_dev)
         ctx.enc, ctx.lth, ctx.prec, ctx.params, ctx.nd = enc, lth, prec, params, nd
         return ys
@@ -687,7 +687,7 @@ class _LstmLayerFn(torch.autograd.Function):
         H4 = acts.shape[-1]
         # bucket order: [w_ih of all directions | w_hh | b_ih | b_hh]: the direction-concatenated gradients are single views
         G = _Grads(tuple(w_ih) + tuple(w_hh) + tuple(b_ih) + tuple(b_hh))
-        dg = ops.lstm_seq_bwd(dy, acts, cprev, whh, lens_dev)                     # [B, T, nd*4H] fp32
+        dg = ops.lstm_seq_bwd(dy, acts, cprev, whh, lens_dev, prec=prec)                     # [B, T, nd*4H] fp32
         dgo = _gop(dg, prec)
         dx = None
         if ctx.needs_input_grad[0]:
@@ -725,7 +725,7 @@ class _LstmChunkFn(torch.autograd.Function):
         xs = xs.contiguous().float()
         gates_x = ops.linear(xs, w_ihp, bias, prec=prec, out_dtype=torch.float32)
         state = (h0.detach(), c0.detach()) if h0 is not None else None
-        ys, acts, cprev, hprev, (hN, cN) = ops.lstm_seq(gates_x, whh, lens_dev, 1, save=True, state=state, want_state=True)
+        ys, acts, cprev, hprev, (hN, cN) = ops.lstm_seq(gates_x, whh, lens_dev, 1, save=True, state=state, want_state=True, prec=prec)
         ctx.save_for_backward(xs, acts, cprev, hprev, whh, lens_dev)
         ctx.owner, ctx.tag, ctx.prec, ctx.params, ctx.has_state = owner, tag, prec, (w_ih, w_hh, b_ih, b_hh), h0 is not None
         return ys, hN, cN
@@ -742,7 +742,7 @@ class _LstmChunkFn(torch.autograd.Function):
             dstate = (dhN if dhN is not None else z, dcN if dcN is not None else z)
         if dy is None:
             dy = torch.zeros(xs.shape[0], xs.shape[1], whh.shape[-1], dtype=torch.float32, device=xs.device)
-        out = ops.lstm_seq_bwd(dy, acts, cprev, whh, lens_dev, dstate=dstate, want_dstate=ctx.has_state)
+        out = ops.lstm_seq_bwd(dy, acts, cprev, whh, lens_dev, dstate=dstate, want_dstate=ctx.has_state, prec=prec)
         dg, d0 = out if ctx.has_state else (out, (None, None))
         dgo = _gop(dg, prec)
         dx = None

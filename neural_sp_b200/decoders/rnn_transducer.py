@@ -78,7 +78,7 @@ class RNNTransducer(nn.Module):
         w_ihp = prepared(self, 'w_ih%d' % lth, prec, (rnn.weight_ih_l0,))
         bias = cached(self, 'b%d' % lth, (rnn.bias_ih_l0, rnn.bias_hh_l0), lambda a, b: (a + b).float().contiguous())
         w_hh = cached(self, 'w_hh%d' % lth, (rnn.weight_hh_l0,), lambda w: w.unsqueeze(0).float().contiguous())
-        return ops.lstm_seq(ops.linear(xs, w_ihp, bias, prec=prec, out_dtype=torch.float32), w_hh, lens_dev, 1)
+        return ops.lstm_seq(ops.linear(xs, w_ihp, bias, prec=prec, out_dtype=torch.float32), w_hh, lens_dev, 1, prec=prec)
 
     def recurrency(self, ys_emb, train=False):
         """Prediction network (reference :278-311), zero initial state: stacked unidirectional LSTMs over all U+1 positions
@@ -112,10 +112,14 @@ class RNNTransducer(nn.Module):
                             self.output.bias, prec=prec, out_dtype=torch.float32)
         return ops.softmax_rows(logits.view(B, T, U1, self.vocab), log=True, inplace=True)
 
-    def forward_transducer(self, eouts, elens, ys):
-        """RNN-T loss (reference :217-260): mean over the batch of -log p(y|x); returns a `[1]` tensor (differentiable in
-        train() + grad mode)."""
-        device = eouts.device
+    def _pack(self, ys, device):
+        """Label lists -> (prediction-network input `[B, U+1]` long: <eos> + labels, padded; targets int32 `[B, U]`; lengths
+        int32 `[B]`), all on `device` (reference :225-231).  Host buffers are pinned and the last batch is cached, as
+        ops.pack_labels does for CTC: a repeated batch (CUDA-graph replay) issues no new copy."""
+        key = (tuple(tuple(int(v) for v in y) for y in ys), str(device))
+        hit = self.__dict__.get("_pack_cache")
+        if hit is not None and hit[0] == key:
+            return hit[1]
         B = len(ys)
         ylens = [len(y) for y in ys]
         U = max(ylens) if ylens else 0
@@ -126,12 +130,25 @@ class RNNTransducer(nn.Module):
             if len(y):
                 ys_in[b, 1:len(y) + 1] = torch.as_tensor(list(y), dtype=torch.long)
                 ys_out[b, :len(y)] = torch.as_tensor(list(y), dtype=torch.int32)
+        labels = ys_out[:, :U].contiguous()
+        if device.type == "cuda":
+            ys_in, labels = ys_in.pin_memory(), labels.pin_memory()
+        out = (ys_in.to(device, non_blocking=True),
+               labels.to(device, non_blocking=True) if U > 0 else torch.zeros(B, 0, dtype=torch.int32, device=device),
+               _lens_dev(torch.tensor(ylens, dtype=torch.int32), device))
+        self.__dict__["_pack_cache"] = (key, out)
+        return out
+
+    def forward_transducer(self, eouts, elens, ys):
+        """RNN-T loss (reference :217-260): mean over the batch of -log p(y|x); returns a `[1]` tensor (differentiable in
+        train() + grad mode)."""
+        device = eouts.device
+        B = len(ys)
+        ys_in, labels, ylens_d = self._pack(ys, device)
         flens = _lens_dev(elens, device)
-        ylens_d = _lens_dev(torch.tensor(ylens, dtype=torch.int32), device)
-        labels = ys_out[:, :U].contiguous().to(device) if U > 0 else torch.zeros(B, 0, dtype=torch.int32, device=device)
         prec = get_precision(self)
         if self.training and torch.is_grad_enabled():
-            emb = torch.nn.functional.embedding(ys_in.to(device), self.embed.weight, padding_idx=self.pad)
+            emb = torch.nn.functional.embedding(ys_in, self.embed.weight, padding_idx=self.pad)
             dout = self.recurrency(ag.dropout(emb.float(), self.dropout_emb.p), train=True)
             e = ag.linear(self, 'w_enc', self.w_enc, eouts.float(), prec)                  # `[B, T, J]`
             d = ag.linear(self, 'w_dec', self.w_dec, dout, prec)                           # `[B, U+1, J]`
@@ -139,7 +156,7 @@ class RNNTransducer(nn.Module):
             self._grad_log_probs = None
             return loss.reshape(1)
         with torch.no_grad():
-            dout = self.recurrency(self.embed(ys_in.to(device)))
+            dout = self.recurrency(self.embed(ys_in))
             log_probs = self.joint(eouts.float(), dout.float())
             loss, nll, grad = ops.rnnt_loss_fwd_bwd(log_probs, labels, flens, ylens_d, self.blank, need_grad=True)
         self._grad_log_probs = grad            # d loss / d log_probs, kept for callers that chain the backward by hand

@@ -126,8 +126,8 @@ class RNNEncoder(EncoderBase):
                       lambda *ws: torch.stack(ws, dim=0).float().contiguous())
         gates_x = ops.linear(xs, w_ihp, bias, prec=prec, out_dtype=torch.float32)
         if state is not None or want_state:
-            return ops.lstm_seq(gates_x, w_hh, lens_dev, len(names), state=state, want_state=True)
-        return ops.lstm_seq(gates_x, w_hh, lens_dev, len(names))
+            return ops.lstm_seq(gates_x, w_hh, lens_dev, len(names), state=state, want_state=True, prec=prec)
+        return ops.lstm_seq(gates_x, w_hh, lens_dev, len(names), prec=prec)
 
     def _lstm_layer(self, lth, xs, lens_dev, train=False, state=None, want_state=False):
         """One (bi)directional LSTM layer over `[B, T, I]` with packed-sequence semantics."""

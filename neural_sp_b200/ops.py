@@ -524,17 +524,47 @@ def pool_time(x, factor, mode):
     return y
 
 
-def lstm_seq(gates_x, w_hh, lens, n_dirs, save=False, state=None, want_state=False):
+def _lstm_tc(prec, B, H, n_dirs):
+    """bf16 mode takes the tensor-core recurrence (lstm_tc.cu) when the shape is covered; NSP_LSTM_PATH=simt forces lstm.cu."""
+    return prec == "bf16" and os.environ.get("NSP_LSTM_PATH", "") != "simt" and bool(lib.nsp_lstm_tc_supported(B, H, n_dirs))
+
+
+def lstm_seq(gates_x, w_hh, lens, n_dirs, save=False, state=None, want_state=False, prec=None):
     """LSTM recurrence of one layer (nsp_lstm_seq_fwd): gates_x fp32 `[B,T,n_dirs*4H]`, w_hh fp32 `[n_dirs,4H,H]`,
     lens int32 `[B]` CUDA -> y fp32 `[B,T,n_dirs*H]` (zeros beyond each length).
     save=True (training, nsp_lstm_seq_fwd_save) -> (y, acts `[B,T,n_dirs,4H]`, cprev, hprev `[B,T,n_dirs,H]`).
     state=(h0, c0) fp32 `[n_dirs,B,H]` (nn.LSTM's hx) / want_state=True (streaming, nsp_lstm_seq_fwd_state)
-    -> (y, (hN, cN))."""
+    -> (y, (hN, cN)).  prec="bf16": the recurrent product runs on the tensor cores with bf16 operands
+    (nsp_lstm_seq_fwd_tc; cell state, gate math and every output stay fp32); otherwise fp32 CUDA-core math."""
     _require_cuda(gates_x, w_hh, lens)
     gates_x = gates_x.contiguous().float()
     w_hh = w_hh.contiguous().float()
     B, T, G = gates_x.shape
     H = G // (4 * n_dirs)
+    if _lstm_tc(prec, B, H, n_dirs):
+        dev = gates_x.device
+        ws_bytes = lib.nsp_lstm_tc_workspace_bytes(B, H, n_dirs, 0)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        y = torch.empty(B, T, n_dirs * H, dtype=torch.float32, device=dev)
+        h0 = c0 = hN = cN = acts = cprev = hprev = None
+        if state is not None:
+            h0, c0 = (t.contiguous().float() for t in state)
+            _require_cuda(h0, c0)
+            assert h0.shape == (n_dirs, B, H) and c0.shape == (n_dirs, B, H), (h0.shape, c0.shape, (n_dirs, B, H))
+        if state is not None or want_state:
+            hN = torch.empty(n_dirs, B, H, dtype=torch.float32, device=dev)
+            cN = torch.empty(n_dirs, B, H, dtype=torch.float32, device=dev)
+        if save:
+            acts = torch.zeros(B, T, n_dirs, 4 * H, dtype=torch.float32, device=dev)
+            cprev = torch.zeros(B, T, n_dirs, H, dtype=torch.float32, device=dev)
+            hprev = torch.zeros(B, T, n_dirs, H, dtype=torch.float32, device=dev)
+        _run("nsp_lstm_seq_fwd_tc", lib.nsp_lstm_seq_fwd_tc, ptr(gates_x), ptr(w_hh), ptr(lens), ptr(y), B, T, H, n_dirs,
+             ptr(acts), ptr(cprev), ptr(hprev), ptr(h0), ptr(c0), ptr(hN), ptr(cN), ptr(ws), ws_bytes, current_stream_ptr(),
+             flops=2.0 * B * T * n_dirs * 4 * H * H, tag="lstm_seq")
+        out = (y, acts, cprev, hprev) if save else (y,)
+        if hN is not None:
+            out = out + ((hN, cN),)
+        return out if len(out) > 1 else out[0]
     ws_bytes = lib.nsp_lstm_workspace_bytes(B, H, n_dirs)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=gates_x.device)
     y = torch.empty(B, T, n_dirs * H, dtype=torch.float32, device=gates_x.device)
@@ -569,10 +599,11 @@ def lstm_seq(gates_x, w_hh, lens, n_dirs, save=False, state=None, want_state=Fal
     return y
 
 
-def lstm_seq_bwd(dy, acts, cprev, w_hh, lens, dstate=None, want_dstate=False):
+def lstm_seq_bwd(dy, acts, cprev, w_hh, lens, dstate=None, want_dstate=False, prec=None):
     """Backpropagation through time of lstm_seq (nsp_lstm_seq_bwd): dy fp32 `[B,T,n_dirs*H]` + what the forward saved ->
     d loss / d gate pre-activations fp32 `[B,T,n_dirs*4H]` (the layout of gates_x; zero beyond each length).
-    dstate = (dhN, dcN): gradient w.r.t. the final state; want_dstate -> (dg, (dh0, dc0)) (nsp_lstm_seq_bwd_state)."""
+    dstate = (dhN, dcN): gradient w.r.t. the final state; want_dstate -> (dg, (dh0, dc0)) (nsp_lstm_seq_bwd_state).
+    prec="bf16": dG_t W_hh on the tensor cores (nsp_lstm_seq_bwd_tc)."""
     _require_cuda(dy, acts, cprev, w_hh, lens)
     B, T, n_dirs, H4 = acts.shape
     H = H4 // 4
@@ -580,6 +611,20 @@ def lstm_seq_bwd(dy, acts, cprev, w_hh, lens, dstate=None, want_dstate=False):
     assert dy.shape == (B, T, n_dirs * H), (dy.shape, acts.shape)
     w_hh = w_hh.contiguous().float()
     dg = torch.empty(B, T, n_dirs * H4, dtype=torch.float32, device=dy.device)
+    if _lstm_tc(prec, B, H, n_dirs):
+        ws_bytes = lib.nsp_lstm_tc_workspace_bytes(B, H, n_dirs, 1)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dy.device)
+        dhN = dcN = dh0 = dc0 = None
+        if dstate is not None:
+            dhN, dcN = (t.contiguous().float() for t in dstate)
+            assert dhN.shape == (n_dirs, B, H) and dcN.shape == (n_dirs, B, H)
+        if want_dstate:
+            dh0 = torch.zeros(n_dirs, B, H, dtype=torch.float32, device=dy.device)
+            dc0 = torch.zeros(n_dirs, B, H, dtype=torch.float32, device=dy.device)
+        _run("nsp_lstm_seq_bwd_tc", lib.nsp_lstm_seq_bwd_tc, ptr(dy), ptr(acts), ptr(cprev), ptr(w_hh), ptr(lens), ptr(dg),
+             B, T, H, n_dirs, ptr(dhN), ptr(dcN), ptr(dh0), ptr(dc0), ptr(ws), ws_bytes, current_stream_ptr(),
+             flops=2.0 * B * T * n_dirs * 4 * H * H, tag="lstm_seq_bwd")
+        return (dg, (dh0, dc0)) if want_dstate else dg
     ws = torch.empty(256, dtype=torch.uint8, device=dy.device)
     if dstate is not None or want_dstate:
         dhN = dcN = dh0 = dc0 = None

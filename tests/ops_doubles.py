@@ -204,7 +204,7 @@ def maxpool_time(x, factor):
     return pool_time(x, factor, "max")
 
 
-def lstm_seq(gates_x, w_hh, lens, n_dirs, save=False, state=None, want_state=False):
+def lstm_seq(gates_x, w_hh, lens, n_dirs, save=False, state=None, want_state=False, prec=None):
     """Packed-sequence LSTM recurrence (csrc/lstm.cu contract): state frozen and outputs zero beyond each length, the
     reverse direction of utterance b starts at its own last frame; optional initial / final state `[n_dirs, B, H]`."""
     B, T, G = gates_x.shape
@@ -234,7 +234,7 @@ def lstm_seq(gates_x, w_hh, lens, n_dirs, save=False, state=None, want_state=Fal
     return y
 
 
-def lstm_seq_bwd(dy, acts, cprev, w_hh, lens, dstate=None, want_dstate=False):
+def lstm_seq_bwd(dy, acts, cprev, w_hh, lens, dstate=None, want_dstate=False, prec=None):
     """BPTT with the kernel's step structure (csrc/lstm.cu): cell backward -> dG_t, then dh_rec = dG_t W_hh; optional
     gradient w.r.t. the final state in, gradient w.r.t. the initial state out."""
     B, T, nd, H4 = acts.shape

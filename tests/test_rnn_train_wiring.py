@@ -32,7 +32,7 @@ def _linear(x, wp, bias=None, prec="fp32", act=None, glu=False, residual=None, a
     return y.reshape(*x.shape[:-1], -1)
 
 
-def _lstm_seq(gx, whh, lens, nd, save=False):
+def _lstm_seq(gx, whh, lens, nd, save=False, prec=None):
     B, T, G = gx.shape
     H = G // (4 * nd)
     y, acts = torch.zeros(B, T, nd * H), torch.zeros(B, T, nd, 4 * H)
@@ -54,7 +54,7 @@ def _lstm_seq(gx, whh, lens, nd, save=False):
     return (y, acts, cp, hp) if save else y
 
 
-def _lstm_seq_bwd(dy, acts, cprev, whh, lens):
+def _lstm_seq_bwd(dy, acts, cprev, whh, lens, prec=None):
     """Same step structure as the kernel (csrc/lstm.cu): cell backward -> dG_t, then dh_rec = dG_t W_hh."""
     B, T, nd, H4 = acts.shape
     H = H4 // 4
