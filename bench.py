@@ -418,6 +418,112 @@ def eager_cuda_arm(w, dev, steps, warmup, train=True, lengths="fixed", seed=1234
             "frames_per_s": ok[best]["frames_per_s"] if best else None, "steps": steps}
 
 
+def eager_rnn_arm(w, dev, steps, warmup, lengths="fixed", seed=1234):
+    """Baseline (B) for the RNN workloads (C1 / C4): the torch modules the reference's RNNEncoder / ConvEncoder / CTC /
+    RNNTransducer are built from (encoders/rnn.py:100-140 nn.LSTM over pack_padded_sequence = cuDNN, conv.py Conv2d + ReLU +
+    MaxPool2d blocks, F.ctc_loss, and for RNN-T the joint of rnn_transducer.py:262-276 with torchaudio's rnnt_loss standing in
+    for warp_rnnt) under torch eager on this GPU, random weights of the same shapes, the same batch; fp32 defaults and fp16
+    autocast (the reference's AMP).  Training step = forward + loss + backward, no optimizer.  Stock torch only."""
+    import torch
+    import torch.nn as nn
+    Fn = torch.nn.functional
+    torch.manual_seed(0)
+    xs, xlens, ys = synth_batch(w, w["B"], seed, lengths)
+    B, V, H, nl = w["B"], w["vocab"], w["n_units"], w["n_layers"]
+    bidir = w["enc_type"] in ("blstm", "conv_blstm")
+    mods = nn.ModuleDict()
+    idim, sub = 80, 1
+    if w["conv"]:
+        pools = [tuple(int(v) for v in t.strip("()").split(",")) for t in w["conv"].split("_")]
+        layers, ci, F = [], 1, 80
+        for pt, pf in pools:
+            layers += [nn.Conv2d(ci, 32, 3, padding=1), nn.ReLU(), nn.Conv2d(32, 32, 3, padding=1), nn.ReLU(),
+                       nn.MaxPool2d((pt, pf), ceil_mode=True)]
+            ci, F, sub = 32, -(-F // pf), sub * pt
+        mods["conv"] = nn.Sequential(*layers)
+        idim = 32 * F
+    mods["rnn"] = nn.ModuleList([nn.LSTM(idim if l == 0 else H * (2 if bidir else 1), H, 1, batch_first=True, bidirectional=bidir)
+                                 for l in range(nl)])
+    odim = H * (2 if bidir else 1)
+    if w["loss"] == "ctc":
+        mods["out"] = nn.Linear(odim, V)
+    else:
+        mods["embed"] = nn.Embedding(V, 512, padding_idx=3)
+        mods["pred"] = nn.LSTM(512, 1024, 2, batch_first=True)
+        mods["w_enc"], mods["w_dec"], mods["out"] = nn.Linear(odim, 640, bias=False), nn.Linear(1024, 640), nn.Linear(640, V)
+    mods = mods.to(dev).train()
+    x = torch.as_tensor(xs).to(dev)
+    elens = torch.tensor([-(-n // sub) for n in xlens], dtype=torch.int32)
+    ylens = torch.tensor([len(y) for y in ys], dtype=torch.int32)
+    U = int(ylens.max())
+    ys_pad = torch.zeros(B, U, dtype=torch.int32)
+    for b, y in enumerate(ys):
+        ys_pad[b, :len(y)] = torch.tensor(y, dtype=torch.int32)
+    ys_in = torch.cat([torch.full((B, 1), 2, dtype=torch.long), ys_pad.long()], dim=1).to(dev)
+    ys_pad_d, elens_d, ylens_d = ys_pad.to(dev), elens.to(dev), ylens.to(dev)
+    rnnt_loss = None
+    if w["loss"] == "rnnt":
+        try:
+            import torchaudio
+            rnnt_loss = torchaudio.functional.rnnt_loss
+        except Exception as ex:                      # no stand-in for warp_rnnt on this box: encoder + prediction network only
+            rnnt_loss = None
+
+    def step():
+        for p_ in mods.parameters():
+            p_.grad = None
+        h = x
+        if "conv" in mods:
+            h = mods["conv"](h.unsqueeze(1))                                  # [B, C, T', F']
+            h = h.transpose(1, 2).reshape(B, h.size(2), -1)
+        for rnn in mods["rnn"]:
+            pk = nn.utils.rnn.pack_padded_sequence(h, elens, batch_first=True, enforce_sorted=False)
+            h, _ = nn.utils.rnn.pad_packed_sequence(rnn(pk)[0], batch_first=True)
+        if w["loss"] == "ctc":
+            lp = mods["out"](h).float().log_softmax(-1)
+            loss = Fn.ctc_loss(lp.transpose(0, 1), ys_pad_d, elens_d, ylens_d, reduction="sum", zero_infinity=True) / B
+        else:
+            d, _ = mods["pred"](mods["embed"](ys_in))
+            z = torch.tanh(mods["w_enc"](h).unsqueeze(2) + mods["w_dec"](d).unsqueeze(1))
+            logits = mods["out"](z).float()
+            loss = rnnt_loss(logits, ys_pad_d, elens_d, ylens_d, blank=0, reduction="mean") if rnnt_loss is not None \
+                else logits.logsumexp(-1).mean()
+        loss.backward()
+        return loss.detach()
+
+    frames = sum(xlens)
+    l2 = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    out = {}
+    import contextlib
+    for tag, ctx in (("fp32_torch_defaults", contextlib.nullcontext),
+                     ("fp16_autocast", lambda: torch.autocast("cuda", dtype=torch.float16))):
+        try:
+            with ctx():
+                for _ in range(max(3, warmup)):
+                    loss = step()
+                torch.cuda.synchronize()
+                evs = []
+                for _ in range(steps):
+                    l2.zero_()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(); loss = step(); b.record()
+                    evs.append((a, b))
+                torch.cuda.synchronize()
+            ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+            out[tag] = {"ms_per_step": ms, "frames_per_s": frames / (ms * 1e-3), "loss": float(loss)}
+        except Exception as ex:
+            out[tag] = {"error": repr(ex)[:200]}
+        torch.cuda.empty_cache()
+    ok = {k: v for k, v in out.items() if "ms_per_step" in v}
+    best = min(ok, key=lambda k: ok[k]["ms_per_step"]) if ok else None
+    return {"what": "stock torch modules of the same architecture (cuDNN nn.LSTM over packed sequences, Conv2d/MaxPool2d, "
+                    "%s) under torch eager on this GPU, train step (fwd + loss + bwd, no optimizer), B=%d"
+                    % ("F.ctc_loss" if w["loss"] == "ctc" else
+                       ("tanh joint + torchaudio rnnt_loss" if rnnt_loss is not None else "tanh joint, NO transducer loss (torchaudio missing)"), B),
+            "variants": out, "best": best, "ms_per_step": ok[best]["ms_per_step"] if best else None,
+            "frames_per_s": ok[best]["frames_per_s"] if best else None, "steps": steps}
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -463,6 +569,16 @@ def main():
                   "global_batch": w["B"] * world, "seq_len": w["T"], "parallelism": "dp%d" % world,
                   "dropout": args.dropout, "lengths": args.lengths}
 
+    if args.impl == "eager" and w["kind"] == "rnn":
+        if rank == 0:
+            import torch
+            dev = torch.device("cuda", local_rank)
+            torch.cuda.set_device(dev)
+            r = eager_rnn_arm(w, dev, args.steps, args.warmup, lengths=args.lengths)
+            print(json.dumps({"impl": "eager", "metric": "speech_frames_per_sec", "value": r["frames_per_s"], "unit": "frames/s",
+                              "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": r["ms_per_step"],
+                              "higher_is_better": True, "data": "synthetic", "config": cfg_common, "eager_b200": r}))
+        return
     if args.impl in ("reference", "eager") and w["kind"] != "conformer":
         if rank == 0:
             print(json.dumps({"impl": args.impl, "unavailable": "the oracle port covers the Conformer workloads only (workload %s)" % args.workload}))
@@ -867,6 +983,12 @@ def main():
             torch.cuda.empty_cache()
             line["eager_b200"] = eager_cuda_arm(w, dev, max(3, min(args.steps, 10)), 3, train=args.step == "train",
                                                 lengths=args.lengths, seed=1234 + rank)
+            if line["eager_b200"]["ms_per_step"]:
+                line["speedup_vs_eager_b200"] = line["eager_b200"]["ms_per_step"] / ms_dev
+        if not args.no_eager and world == 1 and w["kind"] == "rnn" and args.step == "train":
+            del graph_keep[:]
+            torch.cuda.empty_cache()
+            line["eager_b200"] = eager_rnn_arm(w, dev, max(3, min(args.steps, 10)), 3, lengths=args.lengths, seed=1234 + rank)
             if line["eager_b200"]["ms_per_step"]:
                 line["speedup_vs_eager_b200"] = line["eager_b200"]["ms_per_step"] / ms_dev
         if not args.no_cpu_baseline and world == 1 and w["kind"] == "conformer":
