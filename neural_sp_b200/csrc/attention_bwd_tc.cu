@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_bwd_tc_kernel(const __grid_c
     const uint32_t tm_DQ = tmem_base + 384, tm_BD = tmem_base + 448;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (tc::elect_one()) {
             tc::mbar_arrive_expect_tx(kv_full, 2 * TILE + (a.has_rel ? 2048 : 0));
             tc::tma_load_3d(sK, &tmap_k, kv_full, h * DK, j0, b);
             tc::tma_load_3d(sV, &tmap_v, kv_full, h * DK, j0, b);
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_bwd_tc_kernel(const __grid_c
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (tc::elect_one()) {
             constexpr uint32_t idesc_s = tc::make_idesc(1u, 128, 128);                              // K-major x K-major
             constexpr uint32_t idesc_bd = tc::make_idesc(1u, 128, 16);
             constexpr uint32_t idesc_acc = tc::make_idesc(1u, 128, 64) | (1u << 16);                // B MN-major

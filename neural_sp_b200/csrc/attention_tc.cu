@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
     const uint32_t tm_S = tmem_base, tm_O = tmem_base + 128, tm_BD = tmem_base + 192;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (tc::elect_one()) {
             tc::mbar_arrive_expect_tx(q_full, TILE_BYTES + (a.has_rel ? 2048 : 0));
             tc::tma_load_3d(sQ, &tmap_q, q_full, h * DK, i0, b);
             if (a.has_rel) tc::tma_load_2d(sR, &tmap_r, q_full, h * DK, 0);
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (tc::elect_one()) {
             constexpr uint32_t idesc_s = tc::make_idesc(1u, 128, 128);
             constexpr uint32_t idesc_bd = tc::make_idesc(1u, 128, 16);
             constexpr uint32_t idesc_pv = tc::make_idesc(1u, 128, 64) | (1u << 16);      // B operand MN-major

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3_tc_kernel(const __grid_constan
     pdl_wait();                    // the previous grid is complete: operands / residuals / outputs may be touched from here
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (tc::elect_one()) {
             tc::mbar_arrive_expect_tx(w_bar, 9 * W_TAP_BYTES);
             for (int tap = 0; tap < 9; ++tap) tc::tma_load_2d(sW + tap * W_TAP_BYTES, &tmap_w, w_bar, tap * 32, 0);
             int stage = 0; uint32_t phase = 0;
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3_tc_kernel(const __grid_constan
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (tc::elect_one()) {
             constexpr uint32_t idesc = tc::make_idesc(1u, 128, 32);
             tc::mbar_wait_spin(w_bar, 0);
             tc::tc_fence_after();

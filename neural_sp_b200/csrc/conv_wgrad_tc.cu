@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3_wgrad_tc_kernel(const __grid_c
     pdl_wait();                    // the previous grid is complete: operands / residuals / outputs may be touched from here
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (tc::elect_one()) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int ft = tile % tiles_f, tt = (tile / tiles_f) % tiles_t, b = tile / (tiles_f * tiles_t);
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3_wgrad_tc_kernel(const __grid_c
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (tc::elect_one()) {
             constexpr uint32_t idesc = tc::make_idesc(1u, 128, 32) | (1u << 15) | (1u << 16);     // A and B MN-major
             int stage = 0; uint32_t phase = 0; int it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {

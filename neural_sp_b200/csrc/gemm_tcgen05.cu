@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (tc::elect_one()) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (single thread) =====================
-        if (lane == 0) {
+        if (tc::elect_one()) {
             constexpr uint32_t idesc = tc::make_idesc(kBF16 ? 1u : 2u, BM, BN);
             int stage = 0; uint32_t phase = 0;
             int it = 0;

@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ts_kernel(const __grid_const
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (tc::elect_one()) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ts_kernel(const __grid_const
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (single thread) =====================
-        if (lane == 0 && rank == 0) {
+        if (rank == 0 && tc::elect_one()) {
             constexpr uint32_t idesc = tc::make_idesc(1u, TILE_M, BN);
             int stage = 0; uint32_t phase = 0;
             int it = 0;
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ts_kernel(const __grid_const
             const bool live = row0 < g.M && col0 < nout;        // warp-uniform: anything to write at all
             if constexpr (RES) {
                 // the residual sub-tiles do not depend on the accumulator: fetch them under the mainloop of this tile
-                if (live && lane == 0) {
+                if (live && tc::elect_sync()) {
                     tc::bulk_wait_read<0>();                        // stores of the previous tile have left the staging tiles
                     tc::mbar_arrive_expect_tx(rbar, NCH * 4096);
 #pragma unroll
@@ -336,20 +336,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ts_kernel(const __grid_const
                 }
                 if (g.has_pre) {                                     // pre-activation(s), bf16, through the slot rotation
                     if constexpr (!RES) {
-                        if (lane == 0) tc::bulk_wait_read<1>();
+                        if (tc::elect_sync()) tc::bulk_wait_read<1>();
                         __syncwarp();
                         tc::st_row_bf16(stg + slot * SLOT, lane, v);
                         tc::fence_proxy_async_smem();
                         __syncwarp();
-                        if (lane == 0) { tc::tma_store_2d(&maps.pre, stg + slot * SLOT, cbase, row0); tc::bulk_commit(); }
+                        if (tc::elect_one()) { tc::tma_store_2d(&maps.pre, stg + slot * SLOT, cbase, row0); tc::bulk_commit(); }
                         slot ^= 1;
                         if constexpr (GLU) {
-                            if (lane == 0) tc::bulk_wait_read<1>();
+                            if (tc::elect_sync()) tc::bulk_wait_read<1>();
                             __syncwarp();
                             tc::st_row_bf16(stg + slot * SLOT, lane, gv);
                             tc::fence_proxy_async_smem();
                             __syncwarp();
-                            if (lane == 0) { tc::tma_store_2d(&maps.pre, stg + slot * SLOT, nout + cbase, row0); tc::bulk_commit(); }
+                            if (tc::elect_one()) { tc::tma_store_2d(&maps.pre, stg + slot * SLOT, nout + cbase, row0); tc::bulk_commit(); }
                             slot ^= 1;
                         }
                     }
@@ -382,20 +382,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ts_kernel(const __grid_const
                     tc::st_row_f32(tile_s, lane, v);                     // in place: a thread only touches its own row
                     tc::fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) { tc::tma_store_2d(&maps.out, tile_s, cbase, row0); tc::bulk_commit(); }
+                    if (tc::elect_one()) { tc::tma_store_2d(&maps.out, tile_s, cbase, row0); tc::bulk_commit(); }
                 } else {
                     if (g.alpha != 1.f) {
 #pragma unroll
                         for (int j = 0; j < CW; ++j) v[j] *= g.alpha;
                     }
-                    if (lane == 0) tc::bulk_wait_read<1>();              // the store that used this slot two stores ago is done
+                    if (tc::elect_sync()) tc::bulk_wait_read<1>();              // the store that used this slot two stores ago is done
                     __syncwarp();
                     uint8_t* tile_s = stg + slot * SLOT;
                     if constexpr (OUTBF16) tc::st_row_bf16(tile_s, lane, v);
                     else tc::st_row_f32(tile_s, lane, v);
                     tc::fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) { tc::tma_store_2d(&maps.out, tile_s, cbase, row0); tc::bulk_commit(); }
+                    if (tc::elect_one()) { tc::tma_store_2d(&maps.out, tile_s, cbase, row0); tc::bulk_commit(); }
                     slot ^= 1;
                 }
             }
@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ts_kernel(const __grid_const
                 else tc::mbar_arrive(&tempty_bar[as]);
             }
         }
-        if (lane == 0) tc::bulk_wait_read<0>();                          // staging tiles must outlive the bulk stores reading them
+        if (tc::elect_sync()) tc::bulk_wait_read<0>();                          // staging tiles must outlive the bulk stores reading them
     }
 
     tc::tc_fence_before();

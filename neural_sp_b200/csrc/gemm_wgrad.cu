@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
     pdl_wait();                    // the previous grid is complete: operands / residuals / outputs may be touched from here
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (tc::elect_one()) {
             int stage = 0; uint32_t phase = 0;
             for (int s = 0; s < g.nseg; ++s) {
                 for (int c = c_begin; c < c_end; ++c) {
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (tc::elect_one()) {
             // both operands MN-major: bits 15 (A) and 16 (B) of the instruction descriptor
             constexpr uint32_t idesc = tc::make_idesc(kBF16 ? 1u : 2u, WG_BM, BN) | (1u << 15) | (1u << 16);
             int stage = 0; uint32_t phase = 0;
@@ -168,16 +168,16 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = g.alpha * __uint_as_float(r[j]);
-                    if (lane == 0) tc::bulk_wait_read<1>();      // the reduce that read this slot two sub-tiles ago is done
+                    if (tc::elect_sync()) tc::bulk_wait_read<1>();      // the reduce that read this slot two sub-tiles ago is done
                     __syncwarp();
                     tc::st_row_f32(stg + slot * 4096, lane, v);
                     tc::fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) { tc::tma_reduce_add_2d(&maps.dw, stg + slot * 4096, col0, row0); tc::bulk_commit(); }
+                    if (tc::elect_one()) { tc::tma_reduce_add_2d(&maps.dw, stg + slot * 4096, col0, row0); tc::bulk_commit(); }
                     slot ^= 1;
                 }
             }
-            if (lane == 0) tc::bulk_wait_read<0>();
+            if (tc::elect_sync()) tc::bulk_wait_read<0>();
             tc::tc_fence_before();
         } else {
         const bool vec_ok = (g.lddw % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.dw) & 15) == 0);

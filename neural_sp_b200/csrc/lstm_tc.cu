@@ -17,6 +17,7 @@
 // Backward:  A = dG_t    [B, 4H],  B = W_hh^T rows of the CTA's 16 units    [16, 4H]  -> dh_rec [B, 16]
 // Exchange buffers (bf16, double-buffered per direction) are written with generic stores by every CTA and read by TMA in every
 // CTA: writer and reader both issue fence.proxy.async around the release / acquire pair.
+#include <cstdlib>
 #include "tc_common.cuh"
 
 namespace nsp {
@@ -25,8 +26,10 @@ namespace {
 constexpr int LT_THREADS = 192;       // warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer (+ TMEM allocation)
 constexpr int LT_EPI = 128;
 constexpr int FWD_UPC = 8;            // forward: 8 units = 32 gate columns per CTA
-constexpr int BWD_UPC = 16;           // backward: 16 units per CTA
+constexpr int BWD_UPC_DEFAULT = 16;   // backward: 16 (or 8, NSP_LSTM_TC_BWD_UPC) units per CTA
 constexpr int LT_MAXST = 8;
+constexpr int LT_TMEM_COLS = 128;      // up to 4 accumulators of 32 columns: consecutive MMAs of a step go to different accumulators
+                                      // (a chain into ONE accumulator runs at the MMA latency, ~70 cycles per instruction at N <= 32)
 constexpr int LT_PAD = 16 * 1024;     // operand rows >= B of the last chunk read this far past the ring / W (M = 128: 16 groups x 1 KiB)
 
 struct LtFwd {
@@ -36,7 +39,7 @@ struct LtFwd {
     unsigned int* bar;                // [ndir]
     float* acts; float* cprev; float* hprev;
     const float* h0; const float* c0; float* hN; float* cN;
-    int B, T, H, ndir, dir0, ch, nst;
+    int B, T, H, ndir, dir0, ch, nst, dbg;
 };
 
 struct LtBwd {
@@ -45,7 +48,7 @@ struct LtBwd {
     __nv_bfloat16* abuf;              // [ndir][2][B][4H]
     unsigned int* bar;
     const float* dhN; const float* dcN; float* dh0; float* dc0;
-    int B, T, H, ndir, dir0, ch, nst;
+    int B, T, H, ndir, dir0, ch, nst, dbg;
 };
 
 __device__ __forceinline__ void lt_bar(int n) { asm volatile("bar.sync 1, %0;" :: "r"(n) : "memory"); }
@@ -103,7 +106,7 @@ __device__ __forceinline__ LtSmem lt_carve(uint8_t* raw, int nst, int stage_byte
 // producer + MMA loops shared by both kernels: `steps` products of [B, K] x [N, K]^T, A of step i at rows row0(i) of the map
 template <int M, int N>
 __device__ __forceinline__ void lt_producer(const CUtensorMap* amap, const LtSmem& sm, const unsigned* bar, unsigned nctas,
-                                            int steps, int B, int dirslot0, int kchunks, int ch, int nst, int chunkA) {
+                                            int steps, int B, int dirslot0, int kchunks, int ch, int nst, int chunkA, int dbg) {
     int stage = 0; uint32_t phase = 0;
     const int nit = kchunks / ch;
     const int stageA = ch * chunkA;
@@ -112,29 +115,42 @@ __device__ __forceinline__ void lt_producer(const CUtensorMap* amap, const LtSme
         const int row = (dirslot0 + (i & 1)) * B;
         for (int it = 0; it < nit; ++it) {
             tc::mbar_wait(&sm.empty[stage], phase ^ 1);
-            tc::mbar_arrive_expect_tx(&sm.full[stage], (uint32_t)(ch * B * 128));
-            for (int c = 0; c < ch; ++c)
-                tc::tma_load_2d(sm.ring + (size_t)stage * stageA + (size_t)c * chunkA, amap, &sm.full[stage], (it * ch + c) * 64, row);
+            if (dbg & 2) { tc::mbar_arrive(&sm.full[stage]); }          // timing experiment: no operand traffic
+            else {
+                tc::mbar_arrive_expect_tx(&sm.full[stage], (uint32_t)(ch * B * 128));
+                for (int c = 0; c < ch; ++c)
+                    tc::tma_load_2d(sm.ring + (size_t)stage * stageA + (size_t)c * chunkA, amap, &sm.full[stage], (it * ch + c) * 64, row);
+            }
             if (++stage == nst) { stage = 0; phase ^= 1; }
         }
     }
 }
+// The issuing thread's own instruction stream bounds these small MMAs (N <= 32: ~8 cycles of tensor-pipe work each): measured
+// 77 cycles per instruction with descriptors rebuilt per MMA, 160 with a runtime modulo in the loop (profiles/README.md,
+// round 2).  So: descriptors are built once and advanced by adds, the four K = 16 steps of a 64-column chunk are unrolled with
+// compile-time offsets, and each of the four goes to its OWN accumulator (TMEM columns 0 / 32 / 64 / 96) so that consecutive
+// instructions do not wait for each other's result; the epilogue adds the four partial tiles.
 template <int M, int N>
-__device__ __forceinline__ void lt_mma(const LtSmem& sm, uint32_t tmem, int steps, int kchunks, int ch, int nst, int chunkA) {
+__device__ __forceinline__ void lt_mma(const LtSmem& sm, uint32_t tmem, int steps, int kchunks, int ch, int nst, int chunkA, int dbg) {
     constexpr uint32_t idesc = tc::make_idesc(1u, M, N);
     int stage = 0; uint32_t phase = 0;
     const int nit = kchunks / ch;
-    const int stageA = ch * chunkA;
-    const uint32_t ring = tc::smem_u32(sm.ring), wb = tc::smem_u32(sm.w);
+    const uint64_t ad0 = tc::make_smem_desc_sw128(tc::smem_u32(sm.ring)), bd0 = tc::make_smem_desc_sw128(tc::smem_u32(sm.w));
+    const uint64_t a_chunk = (uint64_t)(chunkA >> 4), a_stage = (uint64_t)((ch * chunkA) >> 4);
+    constexpr uint64_t b_chunk = (uint64_t)((N * 128) >> 4);
+    if (dbg & 1) ch = 0;                                           // timing experiment without the MMAs
     for (int i = 0; i < steps; ++i) {
+        uint64_t bd = bd0;
+        uint32_t accum = 0;
         for (int it = 0; it < nit; ++it) {
             tc::mbar_wait(&sm.full[stage], phase);
             tc::tc_fence_after();
+            uint64_t ad = ad0 + (uint64_t)stage * a_stage;
             for (int c = 0; c < ch; ++c) {
-                const uint64_t ad = tc::make_smem_desc_sw128(ring + stage * stageA + c * chunkA);
-                const uint64_t bd = tc::make_smem_desc_sw128(wb + (it * ch + c) * (N * 128));
 #pragma unroll
-                for (int k = 0; k < 4; ++k) tc::umma_f16(tmem, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((it | c | k) != 0));
+                for (int k = 0; k < 4; ++k) tc::umma_f16(tmem + (uint32_t)(k * 32), ad + 2 * k, bd + 2 * k, idesc, accum);
+                accum = 1;
+                ad += a_chunk; bd += b_chunk;
             }
             tc::umma_commit(&sm.empty[stage]);
             if (++stage == nst) { stage = 0; phase ^= 1; }
@@ -148,14 +164,22 @@ template <int M, int NC>
 __device__ __forceinline__ void lt_tmem_to_smem(uint32_t tmem, float* pre, int B, int warp, int lane) {
     constexpr int RPW = M == 128 ? 32 : 16;
     if (warp * RPW < B) {
-        uint32_t r[32];
-        if constexpr (NC == 32) tc::tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16), r);
-        else tc::tmem_ld_32x16(tmem + ((uint32_t)(warp * 32) << 16), r);
-        tc::tmem_ld_wait();
+        float acc[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[c] = 0.f;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {                             // the step's partial sums, one per accumulator
+            uint32_t r[32];
+            if constexpr (NC > 16) tc::tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * 32), r);
+            else tc::tmem_ld_32x16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * 32), r);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < NC; ++c) acc[c] += __uint_as_float(r[c]);
+        }
         const int row = warp * RPW + lane;
         if (lane < RPW && row < B) {
 #pragma unroll
-            for (int c = 0; c < NC; ++c) pre[row * (NC + 1) + c] = __uint_as_float(r[c]);
+            for (int c = 0; c < NC; ++c) pre[row * (NC + 1) + c] = acc[c];
         }
     }
     tc::tc_fence_before();
@@ -184,7 +208,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_fwd_kernel(const __grid
         tc::mbar_init(sm.tfull, 1);
         tc::fence_barrier_init();
     }
-    if (warp == 5) tc::tmem_alloc<32>(sm.holder);
+    if (warp == 5) tc::tmem_alloc<LT_TMEM_COLS>(sm.holder);
     {   // resident B operand: row n = gate * 8 + u  <-  W_hh[dir][gate * H + j0 + u][:], bf16
         const float* wg = p.whh + (size_t)dir * 4 * H * H;
         const int k8n = H / 8;
@@ -204,10 +228,10 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_fwd_kernel(const __grid
     const uint32_t tmem = *sm.holder;
 
     if (warp == 4) {
-        if (lane == 0)
-            lt_producer<M, N>(&p.amap, sm, bar, (unsigned)per_dir, p.T, B, dir * 2, kchunks, p.ch, p.nst, chunkA);
+        if (tc::elect_one())
+            lt_producer<M, N>(&p.amap, sm, bar, (unsigned)per_dir, p.T, B, dir * 2, kchunks, p.ch, p.nst, chunkA, p.dbg);
     } else if (warp == 5) {
-        if (lane == 0) lt_mma<M, N>(sm, tmem, p.T, kchunks, p.ch, p.nst, chunkA);
+        if (tc::elect_one()) lt_mma<M, N>(sm, tmem, p.T, kchunks, p.ch, p.nst, chunkA, p.dbg);
     } else {
         // item = (batch b, unit u): consecutive threads -> consecutive units of one utterance
         float c_st[ITEMS], h_st[ITEMS];
@@ -264,7 +288,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_fwd_kernel(const __grid
                     hnext[(size_t)b * H + j0 + u] = __float2bfloat16(h_st[k]);     // a frozen state keeps being republished
                 }
             }
-            lt_fence_proxy_async();
+            if (!(p.dbg & 4)) lt_fence_proxy_async();
             lt_bar(LT_EPI);
             if (tid == 0) lt_publish(bar);
 #pragma unroll
@@ -297,10 +321,10 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_fwd_kernel(const __grid
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 5) { tc::tc_fence_after(); tc::tmem_dealloc<32>(tmem); }
+    if (warp == 5) { tc::tc_fence_after(); tc::tmem_dealloc<LT_TMEM_COLS>(tmem); }
 }
 
-template <int M>
+template <int M, int BWD_UPC>
 __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_bwd_kernel(const __grid_constant__ LtBwd p) {
     pdl_entry();
     constexpr int N = BWD_UPC;
@@ -324,7 +348,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_bwd_kernel(const __grid
         tc::mbar_init(sm.tfull, 1);
         tc::fence_barrier_init();
     }
-    if (warp == 5) tc::tmem_alloc<32>(sm.holder);
+    if (warp == 5) tc::tmem_alloc<LT_TMEM_COLS>(sm.holder);
     {   // resident B operand: row n = unit, column k = gate row r  <-  W_hh[dir][r][j0 + n], bf16
         const float* wg = p.whh + (size_t)dir * H4 * H;
         const int k8n = H4 / 8;
@@ -345,10 +369,10 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_bwd_kernel(const __grid
     const uint32_t tmem = *sm.holder;
 
     if (warp == 4) {
-        if (lane == 0)
-            lt_producer<M, N>(&p.amap, sm, bar, (unsigned)per_dir, nmm, B, dir * 2, kchunks, p.ch, p.nst, chunkA);
+        if (tc::elect_one())
+            lt_producer<M, N>(&p.amap, sm, bar, (unsigned)per_dir, nmm, B, dir * 2, kchunks, p.ch, p.nst, chunkA, p.dbg);
     } else if (warp == 5) {
-        if (lane == 0) lt_mma<M, N>(sm, tmem, nmm, kchunks, p.ch, p.nst, chunkA);
+        if (tc::elect_one()) lt_mma<M, N>(sm, tmem, nmm, kchunks, p.ch, p.nst, chunkA, p.dbg);
     } else {
         float dc_st[ITEMS], dh_rec[ITEMS];
         int len[ITEMS];
@@ -420,7 +444,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_bwd_kernel(const __grid
                 }
             }
             if (it < nmm) {
-                lt_fence_proxy_async();
+                if (!(p.dbg & 4)) lt_fence_proxy_async();
                 lt_bar(LT_EPI);
                 if (tid == 0) lt_publish(bar);
             }
@@ -453,7 +477,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_bwd_kernel(const __grid
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 5) { tc::tc_fence_after(); tc::tmem_dealloc<32>(tmem); }
+    if (warp == 5) { tc::tc_fence_after(); tc::tmem_dealloc<LT_TMEM_COLS>(tmem); }
 }
 
 // shared-memory plan: ring stages that fit next to the resident operand; 0 stages = unsupported
@@ -479,10 +503,15 @@ LtPlan lt_plan(int B, int K, int N) {
     return pl;
 }
 
+int lt_env(const char* name, int dflt) {          // experiment knobs (profiles/prof_lstm.py); unset in production
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
 bool lt_shape_ok(int B, int H, int ndir) {
     if (B <= 0 || B > 128 || H <= 0 || H % 64 != 0 || (ndir != 1 && ndir != 2)) return false;
-    if (lt_plan(B, H, 4 * FWD_UPC).nst == 0 || lt_plan(B, 4 * H, BWD_UPC).nst == 0) return false;
-    return H / BWD_UPC >= 1 && H / FWD_UPC <= num_sms();
+    if (lt_plan(B, H, 4 * FWD_UPC).nst == 0 || lt_plan(B, 4 * H, BWD_UPC_DEFAULT).nst == 0) return false;
+    return H / BWD_UPC_DEFAULT >= 1 && H / FWD_UPC <= num_sms();
 }
 
 }  // namespace
@@ -513,7 +542,7 @@ extern "C" nsp_status nsp_lstm_seq_fwd_tc(const float* gates_x, const float* w_h
     LtFwd p;
     p.gx = gates_x; p.whh = w_hh; p.lens = lens; p.y = y; p.B = B; p.T = T; p.H = H; p.ndir = ndir;
     p.acts = acts; p.cprev = cprev; p.hprev = hprev; p.h0 = h0; p.c0 = c0; p.hN = hN; p.cN = cN;
-    p.ch = pl.ch; p.nst = pl.nst;
+    p.ch = pl.ch; p.nst = pl.nst; p.dbg = lt_env("NSP_LSTM_TC_DEBUG", 0);
     const size_t abytes = align_up((size_t)ndir * 2 * B * H * sizeof(__nv_bfloat16), 256);
     p.abuf = (__nv_bfloat16*)workspace;
     p.bar = (unsigned int*)((char*)workspace + abytes);
@@ -521,7 +550,7 @@ extern "C" nsp_status nsp_lstm_seq_fwd_tc(const float* gates_x, const float* w_h
                         CU_TENSOR_MAP_SWIZZLE_128B, "lstm h exchange")) return NSP_ERR_INVALID;
     NSP_CUDA_OK(cudaMemsetAsync(p.bar, 0, 256, st));
     NSP_CUDA_OK(cudaMemsetAsync(y, 0, (size_t)B * T * ndir * H * sizeof(float), st));
-    const bool m64 = B <= 64;
+    const bool m64 = B <= 64 && lt_env("NSP_LSTM_TC_M", 64) != 128;
     void* kern = m64 ? (void*)lstm_tc_fwd_kernel<64> : (void*)lstm_tc_fwd_kernel<128>;
     NSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     const int per_dir = H / FWD_UPC;
@@ -544,11 +573,15 @@ extern "C" nsp_status nsp_lstm_seq_bwd_tc(const float* dy, const float* acts, co
     if (!lt_shape_ok(B, H, ndir)) { set_error("lstm_seq_bwd_tc: B=%d H=%d unsupported (B <= 128, H %% 64 == 0)", B, H); return NSP_ERR_UNSUPPORTED; }
     NSP_CHECK_ARG(workspace_bytes >= nsp_lstm_tc_workspace_bytes(B, H, ndir, 1), "lstm_seq_bwd_tc: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
-    const LtPlan pl = lt_plan(B, 4 * H, BWD_UPC);
+    const int upc = (lt_env("NSP_LSTM_TC_BWD_UPC", BWD_UPC_DEFAULT) == 8 && H / 8 <= num_sms()) ? 8 : BWD_UPC_DEFAULT;
+    LtPlan pl = lt_plan(B, 4 * H, upc);
+    if (pl.nst == 0) { set_error("lstm_seq_bwd_tc: no shared-memory plan for B=%d H=%d", B, H); return NSP_ERR_UNSUPPORTED; }
+    const int nst_env = lt_env("NSP_LSTM_TC_NST", 0);
+    if (nst_env >= 2 && nst_env < pl.nst) { pl.smem -= (size_t)(pl.nst - nst_env) * pl.ch * (((B + 7) & ~7) * 128); pl.nst = nst_env; }
     LtBwd p;
     p.dy = dy; p.acts = acts; p.cprev = cprev; p.whh = w_hh; p.lens = lens; p.dg = dgates;
     p.B = B; p.T = T; p.H = H; p.ndir = ndir; p.dhN = dhN; p.dcN = dcN; p.dh0 = dh0; p.dc0 = dc0;
-    p.ch = pl.ch; p.nst = pl.nst;
+    p.ch = pl.ch; p.nst = pl.nst; p.dbg = lt_env("NSP_LSTM_TC_DEBUG", 0);
     const size_t abytes = align_up((size_t)ndir * 2 * B * 4 * H * sizeof(__nv_bfloat16), 256);
     p.abuf = (__nv_bfloat16*)workspace;
     p.bar = (unsigned int*)((char*)workspace + abytes);
@@ -556,10 +589,11 @@ extern "C" nsp_status nsp_lstm_seq_bwd_tc(const float* dy, const float* acts, co
                         CU_TENSOR_MAP_SWIZZLE_128B, "lstm dG exchange")) return NSP_ERR_INVALID;
     NSP_CUDA_OK(cudaMemsetAsync(p.bar, 0, 256, st));
     NSP_CUDA_OK(cudaMemsetAsync(dgates, 0, (size_t)B * T * ndir * 4 * H * sizeof(float), st));
-    const bool m64 = B <= 64;
-    void* kern = m64 ? (void*)lstm_tc_bwd_kernel<64> : (void*)lstm_tc_bwd_kernel<128>;
+    const bool m64 = B <= 64 && lt_env("NSP_LSTM_TC_M", 64) != 128;
+    void* kern = upc == 8 ? (m64 ? (void*)lstm_tc_bwd_kernel<64, 8> : (void*)lstm_tc_bwd_kernel<128, 8>)
+                          : (m64 ? (void*)lstm_tc_bwd_kernel<64, 16> : (void*)lstm_tc_bwd_kernel<128, 16>);
     NSP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    const int per_dir = H / BWD_UPC;
+    const int per_dir = H / upc;
     const int dirs_per_launch = (ndir * per_dir <= num_sms()) ? ndir : 1;
     for (int d0 = 0; d0 < ndir; d0 += dirs_per_launch) {
         p.dir0 = d0;

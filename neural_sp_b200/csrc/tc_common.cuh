@@ -11,6 +11,21 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a converged warp (all 32 lanes must reach the call).  The single-thread roles (TMA producer, MMA issuer) are
+// entered through this instead of `lane == 0`: ptxas knows exactly one thread is active under an elect.sync predicate and
+// keeps descriptors / coordinates / barrier addresses in uniform registers; under `lane == 0` every UTCHMMA / UTMALDG is
+// wrapped in a VOTEU / ELECT / R2UR / BRA.U.ANY waterfall of ~70 cycles -- more than a 128 x 32 x 16 MMA takes (measured on
+// the LSTM step kernel: 36 -> 3 ns per instruction; profiles/README.md round 2).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// Same, at a point where convergence is not syntactically obvious (epilogue loops): reconverge first.  elect.sync is
+// deterministic for a given member mask, so per-thread state (cp.async.bulk groups) stays with one lane across calls.
+__device__ __forceinline__ bool elect_sync() { __syncwarp(); return elect_one(); }
+
 // ---------------- mbarrier ----------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
