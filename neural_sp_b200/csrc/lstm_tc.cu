@@ -14,7 +14,7 @@
 //                     reduction result dh_rec (backward), global stores, then thread 0 publishes the step
 //                     (red.release.gpu on the counter).
 // Forward :  A = h_{t-1} [B, H],   B = W_hh rows of the CTA's 4 x 8 gates  [32, H]   -> pre-activations [B, 32]
-// Backward:  A = dG_t    [B, 4H],  B = W_hh^T rows of the CTA's 16 units    [16, 4H]  -> dh_rec [B, 16]
+// Backward:  A = dG_t    [B, 4H],  B = W_hh^T rows of the CTA's 8 (16) units [8, 4H]   -> dh_rec [B, 8]
 // Exchange buffers (bf16, double-buffered per direction) are written with generic stores by every CTA and read by TMA in every
 // CTA: writer and reader both issue fence.proxy.async around the release / acquire pair.
 #include <cstdlib>
@@ -26,7 +26,7 @@ namespace {
 constexpr int LT_THREADS = 192;       // warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer (+ TMEM allocation)
 constexpr int LT_EPI = 128;
 constexpr int FWD_UPC = 8;            // forward: 8 units = 32 gate columns per CTA
-constexpr int BWD_UPC_DEFAULT = 16;   // backward: 16 (or 8, NSP_LSTM_TC_BWD_UPC) units per CTA
+constexpr int BWD_UPC_DEFAULT = 16;   // backward: 8 units per CTA when H / 8 CTAs are co-resident, else 16 (NSP_LSTM_TC_BWD_UPC overrides)
 constexpr int LT_MAXST = 8;
 constexpr int LT_TMEM_COLS = 128;      // up to 4 accumulators of 32 columns: consecutive MMAs of a step go to different accumulators
                                       // (a chain into ONE accumulator runs at the MMA latency, ~70 cycles per instruction at N <= 32)
@@ -573,7 +573,10 @@ extern "C" nsp_status nsp_lstm_seq_bwd_tc(const float* dy, const float* acts, co
     if (!lt_shape_ok(B, H, ndir)) { set_error("lstm_seq_bwd_tc: B=%d H=%d unsupported (B <= 128, H %% 64 == 0)", B, H); return NSP_ERR_UNSUPPORTED; }
     NSP_CHECK_ARG(workspace_bytes >= nsp_lstm_tc_workspace_bytes(B, H, ndir, 1), "lstm_seq_bwd_tc: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
-    const int upc = (lt_env("NSP_LSTM_TC_BWD_UPC", BWD_UPC_DEFAULT) == 8 && H / 8 <= num_sms()) ? 8 : BWD_UPC_DEFAULT;
+    // 8 units per CTA when a direction's H / 8 CTAs fit the GPU (half the resident operand -> twice the ring: the step is bound
+    // by the dG stream, 10.1 -> 9.5 us at H = 1024), else 16
+    int upc = lt_env("NSP_LSTM_TC_BWD_UPC", H / 8 <= num_sms() ? 8 : 16);
+    if (upc != 8 || H / 8 > num_sms() || lt_plan(B, 4 * H, 8).nst == 0) upc = 16;
     LtPlan pl = lt_plan(B, 4 * H, upc);
     if (pl.nst == 0) { set_error("lstm_seq_bwd_tc: no shared-memory plan for B=%d H=%d", B, H); return NSP_ERR_UNSUPPORTED; }
     const int nst_env = lt_env("NSP_LSTM_TC_NST", 0);

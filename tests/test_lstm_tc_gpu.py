@@ -43,9 +43,12 @@ def test_forward_matches_fp32_recurrence(B, T, H, nd, ragged):
         assert torch.all(y1[b, n:] == 0) and torch.all(a1[b, n:] == 0)
 
 
+@pytest.mark.parametrize("upc", ["8", "16"])
 @pytest.mark.parametrize("B,T,H,nd,ragged", CASES)
-def test_backward_matches_fp32_recurrence(B, T, H, nd, ragged):
+def test_backward_matches_fp32_recurrence(B, T, H, nd, ragged, upc, monkeypatch):
+    """Both decompositions of the backward kernel: 8 units per CTA (default when H / 8 CTAs are co-resident) and 16."""
     from neural_sp_b200 import ops
+    monkeypatch.setenv("NSP_LSTM_TC_BWD_UPC", upc)
     gx, whh, lens = _inputs(B, T, H, nd, ragged, seed=1)
     y, acts, cprev, hprev = ops.lstm_seq(gx, whh, lens, nd, save=True)
     dy = torch.randn_like(y)
