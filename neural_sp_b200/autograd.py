@@ -70,6 +70,7 @@ class _Grads:
 
     def done(self):
         if _GRAD_SYNC is not None and self.flat is not None:
+            ops.wgrad_join()                       # the bucket must be complete before it is handed to the all-reduce
             # The hook may start an ASYNCHRONOUS in-place all-reduce of the bucket the returned .grad tensors are views of.
             # If a parameter already holds a gradient (gradient accumulation, or a parameter shared by several nodes such as
             # the relative_xl u_bias / v_bias), autograd's AccumulateGrad would read the bucket while NCCL is reducing it.
@@ -199,7 +200,7 @@ def ffn_bwd(ffn, norm, saved, dy, dyo, scale, prec, G, bias_done=False, nxt=(Non
     alpha = scale
     for i in range(len(outs) - 1, -1, -1):
         name, lin = outs[i]
-        ops.linear_wgrad(d, xout[i], prec, G.buf(lin.weight), alpha=alpha)
+        ops.linear_wgrad(d, xout[i], prec, G.buf(lin.weight), alpha=alpha, side=True)
         if i == len(outs) - 1:
             if not (bias_done and fused_ok):
                 ops.colsum_acc(dyb, G.buf(lin.bias), alpha=alpha)
@@ -231,7 +232,7 @@ def ffn_bwd(ffn, norm, saved, dy, dyo, scale, prec, G, bias_done=False, nxt=(Non
         name, lin = ins[i]
         if i < len(ins) - 1:
             ops.colsum_acc(d, G.buf(lin.bias))
-        ops.linear_wgrad(d, xin[i], prec, G.buf(lin.weight))
+        ops.linear_wgrad(d, xin[i], prec, G.buf(lin.weight), side=True)
         d = ops.linear(d, _wT(ffn, name, prec, (lin.weight,)), None, prec=prec, out_dtype=torch.float32 if i == 0 else adt)
     return _ln_bwd(norm, d, x, dy, G, prec, nxt[0], nxt[1])
 
@@ -274,7 +275,7 @@ def attn_bwd(attn, norm, saved, dy, dyo, pos, klens, u_bias, v_bias, mask_kw, pr
     D = attn.n_heads * attn.d_k
     d_in = x.shape[-1]
     dyb, dyo, fused_ok = _drop_grad(dy, dyo, p_res, sid_r, prec)
-    ops.linear_wgrad(dyo, cv, prec, G.buf(attn.w_out.weight))
+    ops.linear_wgrad(dyo, cv, prec, G.buf(attn.w_out.weight), side=True)
     if attn.w_out.bias is not None and not (bias_done and fused_ok):
         ops.colsum_acc(dyb, G.buf(attn.w_out.bias))
     dcv = ops.linear(dyo, _wT(attn, "w_out", prec, (attn.w_out.weight,)), None, prec=prec, out_dtype=act_dtype(prec))
@@ -289,7 +290,7 @@ def attn_bwd(attn, norm, saved, dy, dyo, pos, klens, u_bias, v_bias, mask_kw, pr
     qkv_lins = (attn.w_query, attn.w_key, attn.w_value)
     gw = G.fused([lin.weight for lin in qkv_lins])             # the three weights are adjacent in the node's flat buffer
     if gw is not None:
-        ops.linear_wgrad(dqkv, n, prec, gw)
+        ops.linear_wgrad(dqkv, n, prec, gw, side=True)
     else:
         gw = torch.zeros(3 * D, d_in, dtype=torch.float32, device=x.device)
         ops.linear_wgrad(dqkv, n, prec, gw)
@@ -361,7 +362,7 @@ def convmod_bwd(conv, norm, saved, dy, dyo, prec, G, bias_done=False, nxt=(None,
     x, n, pre, g, c, taps, bn, (p_res, sid_r) = saved
     d = x.shape[-1]
     dyb, dyo, fused_ok = _drop_grad(dy, dyo, p_res, sid_r, prec)
-    ops.linear_wgrad(dyo, c, prec, _as2d(G.buf(conv.pointwise_conv2.weight)))
+    ops.linear_wgrad(dyo, c, prec, _as2d(G.buf(conv.pointwise_conv2.weight)), side=True)
     if not (bias_done and fused_ok):
         ops.colsum_acc(dyb, G.buf(conv.pointwise_conv2.bias))
     dc = ops.linear(dyo, _wT(conv, "pw2", prec, (conv.pointwise_conv2.weight,)), None, prec=prec, out_dtype=act_dtype(prec))
@@ -386,7 +387,7 @@ def convmod_bwd(conv, norm, saved, dy, dyo, prec, G, bias_done=False, nxt=(None,
     else:
         dpre = ops.glu_bwd(dg, pre)
         ops.colsum_acc(dpre, G.buf(conv.pointwise_conv1.bias))
-    ops.linear_wgrad(dpre, n, prec, _as2d(G.buf(conv.pointwise_conv1.weight)))
+    ops.linear_wgrad(dpre, n, prec, _as2d(G.buf(conv.pointwise_conv1.weight)), side=True)
     dn = ops.linear(dpre, _wT(conv, "pw1", prec, (conv.pointwise_conv1.weight,)), None, prec=prec, out_dtype=torch.float32)
     return _ln_bwd(norm, dn, x, dy, G, prec, nxt[0], nxt[1])
 

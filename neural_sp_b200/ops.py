@@ -663,7 +663,7 @@ def _operand(x, prec):
     return x, None
 
 
-def linear_wgrad(dy, x, prec, dw, alpha=1.0, accumulate=True):
+def linear_wgrad(dy, x, prec, dw, alpha=1.0, accumulate=True, side=False):
     """dw[N,K] (+)= alpha * dy[M,N]^T x[M,K] on the tcgen05 MN-major wgrad kernel (nsp_linear_wgrad)."""
     _require_cuda(dy, x, dw)
     assert dw.dtype == torch.float32 and dw.dim() == 2 and dw.stride(1) == 1
@@ -690,10 +690,53 @@ def linear_wgrad(dy, x, prec, dw, alpha=1.0, accumulate=True):
         return dw
     dyh, dyl = _operand(dy2, prec)
     xh, xl = _operand(x2, prec)
-    _run("nsp_linear_wgrad", lib.nsp_linear_wgrad, PREC[prec], ptr(dyh), ptr(dyl), dyh.stride(0), ptr(xh), ptr(xl), xh.stride(0),
-         M, N, K, float(alpha), ptr(dw), dw.stride(0), int(accumulate), current_stream_ptr(),
-         flops=2.0 * M * N * K, tag="gemm_wgrad_%s" % prec, shape=(M, N, K))
+
+    def launch():
+        _run("nsp_linear_wgrad", lib.nsp_linear_wgrad, PREC[prec], ptr(dyh), ptr(dyl), dyh.stride(0), ptr(xh), ptr(xl), xh.stride(0),
+             M, N, K, float(alpha), ptr(dw), dw.stride(0), int(accumulate), current_stream_ptr(),
+             flops=2.0 * M * N * K, tag="gemm_wgrad_%s" % prec, shape=(M, N, K))
+
+    if side and wgrad_side_enabled():
+        # Weight gradients feed nothing until the optimizer / all-reduce: run them on a second stream next to the input-gradient
+        # chain (they fill the SMs that chain leaves idle in its launch tails).  Operands stay referenced until wgrad_join().
+        cur = torch.cuda.current_stream()
+        st = _WG["streams"].get(dw.device)
+        if st is None:
+            st = _WG["streams"][dw.device] = torch.cuda.Stream(device=dw.device)
+        st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            launch()
+        _WG["keep"].extend((dyh, dyl, xh, xl, dw))
+        _WG["pending"].add(st)
+        if not _WG["cb"]:
+            try:                                   # once per backward pass: join when the autograd engine is done
+                torch.autograd.Variable._execution_engine.queue_callback(wgrad_join)
+                _WG["cb"] = True
+            except RuntimeError:                   # not inside a backward pass: the caller joins
+                pass
+        return dw
+    launch()
     return dw
+
+
+_WG = {"streams": {}, "keep": [], "pending": set(), "cb": False}
+
+
+def wgrad_side_enabled():
+    """NSP_WGRAD_STREAM=1: weight-gradient GEMMs of the encoder blocks go to a side stream (see linear_wgrad)."""
+    return os.environ.get("NSP_WGRAD_STREAM", "0") == "1"
+
+
+def wgrad_join():
+    """The current stream waits for every weight gradient issued on the side stream (end of backward, or before a node's
+    gradient bucket is handed to the all-reduce hook)."""
+    if _WG["pending"]:
+        cur = torch.cuda.current_stream()
+        for st in _WG["pending"]:
+            cur.wait_stream(st)
+        _WG["pending"].clear()
+    del _WG["keep"][:]
+    _WG["cb"] = False
 
 
 def layernorm_bwd(dy, x, gamma, eps, dres=None, dgamma=None, dbeta=None, want_fp32=True, want_bf16=False, in_scale=1.0,

@@ -343,7 +343,7 @@ def _linear_train(x, w_prepared, bias=None, prec="bf16", act=None, glu=False, re
     return y, pre.reshape(*x.shape[:-1], -1)
 
 
-def linear_wgrad(dy, x, prec, dw, alpha=1.0, accumulate=True):
+def linear_wgrad(dy, x, prec, dw, alpha=1.0, accumulate=True, side=False):
     N, K = dw.shape
     v = alpha * dy.reshape(-1, N).float().t() @ x.reshape(-1, x.shape[-1])[:, :K].float()
     dw.copy_(dw + v if accumulate else v)
