@@ -723,8 +723,9 @@ _WG = {"streams": {}, "keep": [], "pending": set(), "cb": False}
 
 
 def wgrad_side_enabled():
-    """NSP_WGRAD_STREAM=1: weight-gradient GEMMs of the encoder blocks go to a side stream (see linear_wgrad)."""
-    return os.environ.get("NSP_WGRAD_STREAM", "0") == "1"
+    """Weight-gradient GEMMs of the encoder blocks go to a side stream (see linear_wgrad): 19.36 -> 18.71 ms per Conformer-L
+    training step on B200 (A/B in one call, profiles/README.md round 2).  NSP_WGRAD_STREAM=0 keeps them on the caller's stream."""
+    return os.environ.get("NSP_WGRAD_STREAM", "1") != "0"
 
 
 def wgrad_join():
