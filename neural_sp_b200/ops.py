@@ -696,7 +696,7 @@ def linear_wgrad(dy, x, prec, dw, alpha=1.0, accumulate=True, side=False):
              M, N, K, float(alpha), ptr(dw), dw.stride(0), int(accumulate), current_stream_ptr(),
              flops=2.0 * M * N * K, tag="gemm_wgrad_%s" % prec, shape=(M, N, K))
 
-    if side and wgrad_side_enabled():
+    if side and wgrad_side_enabled() and torch.cuda.is_available():
         # Weight gradients feed nothing until the optimizer / all-reduce: run them on a second stream next to the input-gradient
         # chain (they fill the SMs that chain leaves idle in its launch tails).  Operands stay referenced until wgrad_join().
         cur = torch.cuda.current_stream()
