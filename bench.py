@@ -418,18 +418,24 @@ def eager_cuda_arm(w, dev, steps, warmup, train=True, lengths="fixed", seed=1234
             "frames_per_s": ok[best]["frames_per_s"] if best else None, "steps": steps}
 
 
-def eager_rnn_arm(w, dev, steps, warmup, lengths="fixed", seed=1234):
+def eager_rnn_arm(w, dev, steps, warmup, lengths="fixed", seed=1234, sample_B=None):
     """Baseline (B) for the RNN workloads (C1 / C4): the torch modules the reference's RNNEncoder / ConvEncoder / CTC /
     RNNTransducer are built from (encoders/rnn.py:100-140 nn.LSTM over pack_padded_sequence = cuDNN, conv.py Conv2d + ReLU +
     MaxPool2d blocks, F.ctc_loss, and for RNN-T the joint of rnn_transducer.py:262-276 with torchaudio's rnnt_loss standing in
     for warp_rnnt) under torch eager on this GPU, random weights of the same shapes, the same batch; fp32 defaults and fp16
-    autocast (the reference's AMP).  Training step = forward + loss + backward, no optimizer.  Stock torch only."""
+    autocast (the reference's AMP).  Training step = forward + loss + backward, no optimizer.  Stock torch only.
+    dev = cpu (+ sample_B utterances of the batch): the same modules on the host cores, wall-clock timed -- the reference's
+    CPU path for these workloads (`cpu_baseline` / `--impl reference`)."""
     import torch
     import torch.nn as nn
     Fn = torch.nn.functional
     torch.manual_seed(0)
+    dev = torch.device(dev)
+    on_cpu = dev.type == "cpu"
     xs, xlens, ys = synth_batch(w, w["B"], seed, lengths)
-    B, V, H, nl = w["B"], w["vocab"], w["n_units"], w["n_layers"]
+    B = min(sample_B or w["B"], w["B"])
+    xs, xlens, ys = xs[:B, :max(xlens[:B])], xlens[:B], ys[:B]
+    V, H, nl = w["vocab"], w["n_units"], w["n_layers"]
     bidir = w["enc_type"] in ("blstm", "conv_blstm")
     mods = nn.ModuleDict()
     idim, sub = 80, 1
@@ -492,9 +498,21 @@ def eager_rnn_arm(w, dev, steps, warmup, lengths="fixed", seed=1234):
         return loss.detach()
 
     frames = sum(xlens)
-    l2 = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     out = {}
     import contextlib
+    if on_cpu:
+        for _ in range(max(1, warmup)):
+            loss = step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            loss = step()
+        ms = (time.perf_counter() - t0) * 1e3 / steps
+        out["fp32_cpu"] = {"ms_per_step": ms, "frames_per_s": frames / (ms * 1e-3), "loss": float(loss)}
+        return {"what": "stock torch modules of the same architecture on the host cores (%d threads), train step (fwd + loss + "
+                        "bwd, no optimizer), %d of the batch's %d utterances" % (torch.get_num_threads(), B, w["B"]),
+                "variants": out, "best": "fp32_cpu", "ms_per_step": ms, "frames_per_s": frames / (ms * 1e-3), "steps": steps,
+                "sample_B": B, "cores": torch.get_num_threads()}
+    l2 = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     for tag, ctx in (("fp32_torch_defaults", contextlib.nullcontext),
                      ("fp16_autocast", lambda: torch.autocast("cuda", dtype=torch.float16))):
         try:
@@ -578,6 +596,18 @@ def main():
             print(json.dumps({"impl": "eager", "metric": "speech_frames_per_sec", "value": r["frames_per_s"], "unit": "frames/s",
                               "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": r["ms_per_step"],
                               "higher_is_better": True, "data": "synthetic", "config": cfg_common, "eager_b200": r}))
+        return
+    if args.impl == "reference" and w["kind"] == "rnn":
+        if rank == 0:
+            r = eager_rnn_arm(w, "cpu", max(1, min(args.steps, 3)), max(0, min(args.warmup, 1)), lengths=args.lengths, sample_B=8)
+            print(json.dumps({"impl": "reference", "metric": "speech_frames_per_sec", "value": r["frames_per_s"], "unit": "frames/s",
+                              "n_gpus": args.gpus, "steps": r["steps"], "warmup": max(0, min(args.warmup, 1)),
+                              "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                              "dtype": "f32", "data": "synthetic", "config": dict(cfg_common, sample_batch=r["sample_B"]),
+                              "cpu_baseline": {"value": r["frames_per_s"], "unit": "frames/s", "cores": r["cores"], "kind": "port",
+                                               "sample": r["what"]},
+                              "e2e": {"value": r["frames_per_s"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                              "gpu_launches": 0}))
         return
     if args.impl in ("reference", "eager") and w["kind"] != "conformer":
         if rank == 0:
@@ -991,6 +1021,9 @@ def main():
             line["eager_b200"] = eager_rnn_arm(w, dev, max(3, min(args.steps, 10)), 3, lengths=args.lengths, seed=1234 + rank)
             if line["eager_b200"]["ms_per_step"]:
                 line["speedup_vs_eager_b200"] = line["eager_b200"]["ms_per_step"] / ms_dev
+        if not args.no_cpu_baseline and world == 1 and w["kind"] == "rnn" and args.step == "train":
+            r = eager_rnn_arm(w, "cpu", 2, 1, lengths=args.lengths, seed=1234 + rank, sample_B=8)
+            line["cpu_baseline"] = {"value": r["frames_per_s"], "unit": "frames/s", "cores": r["cores"], "kind": "port", "sample": r["what"]}
         if not args.no_cpu_baseline and world == 1 and w["kind"] == "conformer":
             r = cpu_reference_arm(w, 3, 1, train=args.step == "train", lengths=args.lengths, budget_s=90.0)
             line["cpu_baseline"] = {"value": r["value"], "unit": "frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
