@@ -6,8 +6,9 @@ Drop-in for ``neural_sp.models.seq2seq.decoders.ctc.CTC`` (reference ctc.py:35-1
 keys (``output.weight/bias`` or ``output.fc{i}.weight/bias``).  The arithmetic runs in
 libnsp_b200.so: one fused CUDA pass computes the loss AND d(loss)/d(logits); ``backward`` only scales.
 
-Host-side decode helpers of the reference class (greedy / beam search / prefix scorer,
-ctc.py:197-531, 756-871) are out of scope.
+Decode helpers: greedy / trigger points on the device (decode.cu); prefix beam search, offline and block-synchronous
+(ctc.py:245-531, the decoder half of streaming), in ctc_beam.py on top of the log-softmax kernel.  The attention decoders'
+prefix scorer (ctc.py:756-871) is out of scope.
 """
 from collections import OrderedDict
 
@@ -16,6 +17,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from . import ctc_beam
 from ..modules.dropout import Dropout
 from ..modules.linear import Linear
 
@@ -58,6 +60,13 @@ class CTCForcedAligner(object):
             labels, ylens_d, _ = ops.pack_labels(ys, logits.device)
             elens_d = elens.to(device=logits.device, dtype=torch.int32, non_blocking=True)
             return ops.ctc_forced_align(logits.detach().float(), labels, elens_d, ylens_d, self.blank)
+
+
+class _BeamParams:
+    """What `_beam_search` reads from the reference's BeamSearch helper (beam_search.py:19-31)."""
+
+    def __init__(self, beam_width, lm_weight):
+        self.beam_width, self.lm_weight = beam_width, lm_weight
 
 
 class CTC(nn.Module):
@@ -135,6 +144,90 @@ class CTC(nn.Module):
         """Log-scale CTC probabilities `[B, T, vocab]` (reference ctc.py:208-217)."""
         with torch.no_grad():
             return ops.softmax_rows(self.output(eouts).float(), log=True, temperature=temperature)
+
+    # ---- prefix beam search (host bookkeeping in ctc_beam.py; the frame scores come from the kernels behind `scores`) ----
+    def initialize_beam(self, hyp, lmstate):
+        return ctc_beam.initialize_beam(hyp, lmstate)
+
+    def _frame_scores(self, eouts, softmax_smoothing):
+        """log_softmax(output(eouts) * softmax_smoothing) `[B, T, vocab]` (reference ctc.py:299 / :509)."""
+        with torch.no_grad():
+            logits = self.output(eouts).float()
+            if softmax_smoothing != 1.0:
+                logits = logits * softmax_smoothing
+            return ops.softmax_rows(logits, log=True)
+
+    def _beam_search(self, hyps, helper, scores_ctc, lm, lp_weight):
+        """`scores_ctc` `[T, vocab]` log-probabilities; `helper` supplies `beam_width` and `lm_weight` (reference :365-483)."""
+        if not hasattr(self, 'state_cache'):
+            self.state_cache = OrderedDict()
+        block = ctc_beam.frame_scores_to_host(scores_ctc)
+        return ctc_beam.prefix_beam_search(hyps, block, helper.beam_width, self.vocab, self.blank, lm, helper.lm_weight,
+                                           lp_weight, self.state_cache)
+
+    def beam_search(self, eouts, elens, params, idx2token, lm=None, lm_second=None, lm_second_bwd=None,
+                    nbest=1, refs_id=None, utt_ids=None, speakers=None):
+        """Offline prefix beam search (reference ctc.py:256-363) -> N-best token-id arrays per utterance (without <eos>).
+        Like the reference, every frame of `eouts` is consumed (`elens` is not used to cut the padding).  First-pass LM
+        shallow fusion is supported through the LM's `predict`; second-pass rescoring LMs are outside this package."""
+        if lm_second is not None or lm_second_bwd is not None:
+            raise NotImplementedError("second-pass LM rescoring (reference beam_search.py:116-141) is not part of the B200 path")
+        beam_width = params.get('recog_beam_width')
+        lp_weight = params.get('recog_length_penalty')
+        lm_weight = params.get('recog_lm_weight')
+        lm_state_CO = params.get('recog_lm_state_carry_over')
+        softmax_smoothing = params.get('recog_softmax_smoothing')
+        if lm is not None:                                  # reference beam_search.py:143-149
+            assert lm_weight > 0
+            lm.eval()
+            if params.get('recog_cache_embedding'):
+                lm.cache_embedding(lm.device)
+        helper = _BeamParams(beam_width, lm_weight)
+        log_probs = self._frame_scores(eouts, softmax_smoothing if softmax_smoothing is not None else 1.0)
+        nbest_hyps_idx, end_hyps = [], []
+        for b in range(eouts.size(0)):
+            lmstate = {'hxs': eouts.new_zeros(lm.n_layers, 1, lm.n_units),
+                       'cxs': eouts.new_zeros(lm.n_layers, 1, lm.n_units)} if lm is not None else None
+            if speakers is not None:
+                if speakers[b] == self.prev_spk and lm_state_CO:
+                    lmstate = self.lmstate_final
+                self.prev_spk = speakers[b]
+            self.state_cache = OrderedDict()
+            hyps, new_hyps = self._beam_search(self.initialize_beam([self.eos], lmstate), helper, log_probs[b], lm, lp_weight)
+            end_hyps = hyps[:]
+            if len(end_hyps) < nbest and nbest > 1:
+                end_hyps.extend(new_hyps[:nbest - len(end_hyps)])
+            end_hyps = sorted(end_hyps, key=lambda x: x['score'] / max(len(x['hyp'][1:]), 1), reverse=True)   # length-normalised
+            nbest_hyps_idx += [[np.array(end_hyps[n]['hyp'][1:]) for n in range(nbest)]]
+        if eouts.size(0) == 1:
+            self.lmstate_final = end_hyps[0]['lmstate']
+        return nbest_hyps_idx
+
+    def beam_search_block_sync(self, eouts, params, helper, idx2token, hyps, lm):
+        """One block of streaming decoding (reference ctc.py:485-531; caller speech2text.py:627): `eouts` `[1, T_block, D]`,
+        `hyps` = what the previous block returned (None at the start of an utterance) -> (end_hyps = [], hyps)."""
+        assert eouts.size(0) == 1
+        beam_width = params.get('recog_beam_width')
+        lp_weight = params.get('recog_length_penalty')
+        lm_state_CO = params.get('recog_lm_state_carry_over')
+        softmax_smoothing = params.get('recog_softmax_smoothing')
+        end_hyps = []
+        if hyps is None:
+            if lm_state_CO:
+                lmstate = self.lmstate_final
+            else:
+                lmstate = {'hxs': eouts.new_zeros(lm.n_layers, 1, lm.n_units),
+                           'cxs': eouts.new_zeros(lm.n_layers, 1, lm.n_units)} if lm is not None else None
+            self.n_frames = 0
+            hyps = self.initialize_beam([self.eos], lmstate)
+            self.state_cache = OrderedDict()
+        log_probs = self._frame_scores(eouts, softmax_smoothing if softmax_smoothing is not None else 1.0)
+        hyps, _ = self._beam_search(hyps, helper, log_probs[0], lm, lp_weight)
+        merged_hyps = sorted(end_hyps + hyps, key=lambda x: x['score'], reverse=True)[:beam_width]
+        if len(merged_hyps) > 0:
+            self.lmstate_final = merged_hyps[0]['lmstate']
+        self.n_frames += eouts.size(1)
+        return end_hyps, hyps
 
     def _greedy_device(self, eouts, elens):
         with torch.no_grad():

@@ -245,3 +245,63 @@ def test_streaming_encode_through_the_unchanged_facade(ov, monkeypatch):
             e_o, l_o = ours.encode_streaming([x], params, task='ys')
         assert torch.equal(l_s, l_o) and e_s.shape == e_o.shape
         assert float((e_s - e_o).abs().max()) <= 1e-4 * float(e_s.abs().max())
+
+
+@pytest.mark.parametrize("beam", [1, 4])
+def test_ctc_decode_through_the_unchanged_facade(beam, monkeypatch):
+    """`Speech2Text.decode` (speech2text.py:709-767) on a CTC-weighted model: greedy (`recog_beam_width` 1) and the prefix beam
+    search (ctc.py:256-363) -- the stock decoder vs neural_sp_b200's CTC under the same facade, same weights: identical N-best
+    token ids."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import numpy as np
+    import torch
+    import ops_doubles
+    from oracle.ref_import import import_reference
+    import_reference()
+    import neural_sp.models.seq2seq.decoders.ctc as ref_ctc
+    import neural_sp.models.seq2seq.decoders.las as ref_las
+    import neural_sp.models.seq2seq.speech2text as ref_s2t
+    from neural_sp_b200 import ops
+    from neural_sp_b200.decoders.ctc import CTC as B200CTC
+    from neural_sp_b200.encoders.build import build_encoder as b200_build_encoder
+    ov = dict(enc_type='conv_conformer', conv_poolings="(2,2)_(2,2)", subsample="1_1_1", ctc_weight=0.5)
+    torch.manual_seed(0)
+    stock = ref_s2t.Speech2Text(make_args(**ov))
+    monkeypatch.setattr(ref_s2t, "build_encoder", b200_build_encoder)
+    monkeypatch.setattr(ref_las, "CTC", B200CTC)
+    monkeypatch.setattr(ref_ctc, "CTC", B200CTC)
+    torch.manual_seed(0)
+    ours = ref_s2t.Speech2Text(make_args(**ov))
+    ours.load_state_dict(stock.state_dict(), strict=True)
+    for m in ours.modules():
+        m.precision = "fp32"
+    ops_doubles.install(monkeypatch)
+    monkeypatch.setattr(ops, "softmax_rows", ops_doubles.softmax_rows)
+
+    def greedy_double(logits, elens, blank=0):          # nsp_ctc_greedy restated: best path, collapsed + blank-free, lengths
+        B, T, _ = logits.shape
+        best = logits.argmax(-1).int()
+        hyp, lens, trig = torch.zeros(B, T, dtype=torch.int32), torch.zeros(B, dtype=torch.int32), torch.zeros(B, T, dtype=torch.int32)
+        for b in range(B):
+            prev, n = -1, 0
+            for t in range(int(elens[b])):
+                c = int(best[b, t])
+                if c != prev and c != blank:
+                    hyp[b, n], trig[b, n] = c, t
+                    n += 1
+                prev = c
+            lens[b] = n
+        return best, hyp, lens, trig
+    monkeypatch.setattr(ops, "ctc_greedy", greedy_double)
+    rng = np.random.RandomState(3)
+    xs = [rng.randn(n, 80).astype(np.float32) * 2 for n in (72, 60)]
+    params = {'recog_beam_width': beam, 'recog_ctc_weight': 1.0, 'recog_length_penalty': 0.1, 'recog_lm_weight': 0.0,
+              'recog_lm_second_weight': 0.0, 'recog_lm_bwd_weight': 0.0, 'recog_lm_state_carry_over': False,
+              'recog_softmax_smoothing': 1.0, 'recog_cache_embedding': False, 'recog_streaming_encoding': False,
+              'recog_bwd_attention': False}
+    hs, _ = stock.decode(xs, params, None, utt_ids=['u1', 'u2'], speakers=['a', 'b'])
+    ho, _ = ours.decode(xs, params, None, utt_ids=['u1', 'u2'], speakers=['a', 'b'])
+    assert type(ours.dec_fwd.ctc).__module__.startswith("neural_sp_b200.")
+    assert len(hs) == len(ho) == 2
+    for a, b in zip(hs, ho):
+        assert [list(map(int, x)) for x in a] == [list(map(int, x)) for x in b]
