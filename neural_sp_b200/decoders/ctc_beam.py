@@ -4,7 +4,7 @@ reference decoders/ctc.py:245-531 (`initialize_beam`, `beam_search`, `_beam_sear
 What runs where.  The device produces the frame scores (output head + log-softmax kernel, `CTC.scores`) and ONE copy brings
 the `[T, V]` block to pinned host memory; everything after that is per-frame bookkeeping over at most
 `beam_width * (beam_width + 1)` candidates.  The reference does that bookkeeping with one `torch.topk` launch per frame and one
-`.item()` device synchronisation per (frame, beam, candidate); here the top-k of all frames is one `argpartition`-free sort on
+`.item()` device synchronisation per (frame, beam, candidate); here the top-k of all frames is ONE batched `torch.topk` on
 the host block and the candidate scores of a frame are formed as arrays (one row per live hypothesis, one column per
 extension), ranked with a stable sort and merged by token sequence.
 
@@ -37,23 +37,25 @@ def initialize_beam(hyp, lmstate):
 
 
 def frame_scores_to_host(log_probs):
-    """`[T, V]` device tensor -> float64 numpy block (one copy through pinned memory)."""
+    """`[T, V]` device tensor -> fp32 host tensor (one copy through pinned memory)."""
     lp = log_probs.detach().float()
     if lp.is_cuda:
         host = torch.empty(lp.shape, dtype=torch.float32, pin_memory=True)
         host.copy_(lp, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         lp = host
-    return lp.numpy().astype(np.float64)
+    return lp.contiguous()
 
 
-def _topk_tokens(block, k):
-    """Per frame, the k best non-blank-column tokens in descending score order, ties by ascending id (torch.topk on CPU and the
-    reference's use of it resolve ties that way for distinct columns; exact ties between fp32 scores are the only difference a
-    different rule could make).  `block` is `[T, V]`; column 0 is excluded like the reference's `scores_ctc[t, 1:]`."""
-    sub = block[:, 1:]
-    order = np.argsort(-sub, axis=1, kind='stable')[:, :k]
-    return order + 1
+def _topk_tokens(block32, k):
+    """Per frame, the k best tokens of columns 1.. (column 0 = blank is excluded like the reference's `scores_ctc[t, 1:]`) in
+    descending score order: ONE batched `torch.topk` over the host block.  Exact ties between fp32 scores resolve as torch's
+    CPU top-k resolves them, which is what the reference does when it runs on the host (on a GPU its order among tied tokens
+    is whatever the CUDA top-k returns)."""
+    if block32.shape[0] == 0:
+        return np.zeros((0, k), dtype=np.int64)
+    _, ids = torch.topk(block32[:, 1:], k=k, dim=-1, largest=True, sorted=True)
+    return ids.numpy().astype(np.int64) + 1
 
 
 def _update_lm(hyps, lm, state_cache):
@@ -79,13 +81,15 @@ def _update_lm(hyps, lm, state_cache):
 
 
 def prefix_beam_search(hyps, block, beam_width, vocab, blank, lm, lm_weight, lp_weight, state_cache):
-    """Advance `hyps` over the frames of `block` (`[T, V]` float64 log-probabilities).  -> (hyps, candidates of the last frame).
-    The arithmetic of reference ctc.py:365-483."""
+    """Advance `hyps` over the frames of `block` (`[T, V]` fp32 log-probabilities, host tensor or array).
+    -> (hyps, candidates of the last frame).  The arithmetic of reference ctc.py:365-483, in float64."""
+    block32 = torch.as_tensor(np.asarray(block, dtype=np.float32)) if not torch.is_tensor(block) else block.float()
+    block = block32.numpy().astype(np.float64)
     T = block.shape[0]
     lm_weight = 0.0 if lm_weight is None else lm_weight
     lp_weight = 0.0 if lp_weight is None else lp_weight
-    k = min(beam_width, vocab)
-    topk = _topk_tokens(block, k) if T > 0 else None
+    k = min(beam_width, vocab, max(block.shape[1] - 1, 1))
+    topk = _topk_tokens(block32, k) if T > 0 else None
     # the reference indexes topk_ids[kk] for kk < beam_width: with vocab - 1 < beam_width it would fail; same guard here
     n_ext = min(beam_width, topk.shape[1]) if T > 0 else 0
     new_hyps = []

@@ -131,3 +131,34 @@ def test_golden_beams():
         want = g["hyps_%d" % c]
         assert [h['hyp'] for h in hyps] == [list(w) for w in want]
         np.testing.assert_allclose([h['score'] for h in hyps], g["scores_out_%d" % c], rtol=1e-9, atol=1e-9)
+
+
+@needs_ref
+def test_per_frame_search_many_random_blocks(monkeypatch):
+    """60 random `[T, V]` blocks (beam 1-9, vocabularies down to beam + 1, peaked and flat distributions, quantised scores that
+    tie often, length penalties of both signs) against the reference's `_beam_search`."""
+    from collections import OrderedDict
+    from oracle.ref_import import import_reference
+    import_reference()
+    from neural_sp.models.seq2seq.decoders.beam_search import BeamSearch
+    rng = np.random.RandomState(0)
+    for case in range(60):
+        beam = int(rng.randint(1, 10))
+        V = int(rng.randint(beam + 2, 40))
+        T = int(rng.randint(1, 35))
+        ref, ours = _pair(V, None, monkeypatch)
+        g = torch.Generator().manual_seed(case)
+        raw = torch.randn(T, V, generator=g) * float(rng.choice([0.3, 1.0, 4.0]))
+        if case % 3 == 0:
+            raw = (raw * 2).round() / 2                      # many exact ties between tokens
+        scores = torch.log_softmax(raw, dim=-1)
+        lp = float(rng.choice([0.0, 0.2, -0.1]))
+        helper = BeamSearch(beam, 2, 1.0, 0.0, torch.device("cpu"))
+        ref.state_cache, ours.state_cache = OrderedDict(), OrderedDict()
+        hr, nr = ref._beam_search(ref.initialize_beam([2], None), helper, scores, None, lp)
+        ho, no = ours._beam_search(ours.initialize_beam([2], None), helper, scores, None, lp)
+        try:
+            _same_hyps(ho, hr)
+            _same_hyps(no, nr)
+        except AssertionError as e:
+            raise AssertionError("case %d (beam %d, V %d, T %d, lp %g): %s" % (case, beam, V, T, lp, e))
