@@ -829,7 +829,7 @@ def main():
             barrier()
         graph_keep.append(graph)
         return dict(ms_dev=ms_dev, ms_e2e=ms_e2e, launches_per_step=lps, graph=graph is not None, graph_error=graph_error,
-                    loss=float(run_step()))
+                    loss=float(run_step().detach()))
 
     # ---- loss of the product on the CPU baseline's sample (first 8 utterances), before any parameter update ----
     loss_check = None
